@@ -1,0 +1,118 @@
+"""CPU: independent cross-checks of the third-party semantics the oracle restates
+(tf NMS vs torchvision, skimage<=0.15 resize vs cv2 interior pixels, crop_and_resize loop vs
+vectorised twin, zscale sanity on the shipped FITS files)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import _native, graph_layers as GL, host_ops as H
+
+
+def _rand_boxes(rng, n, size=1.0):
+    yx = rng.random((n, 2)).astype(np.float32) * 0.8 * size
+    hw = (rng.random((n, 2)).astype(np.float32) * 0.2 + 0.01) * size
+    return np.concatenate([yx, yx + hw], axis=1).astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_nms_matches_torchvision_without_ties(seed):
+    import torchvision
+    rng = np.random.default_rng(seed)
+    b = _rand_boxes(rng, 800)
+    s = rng.permutation(800).astype(np.float32) / 800.0            # distinct scores
+    keep = _native.nms_tf113(b, s, 800, 0.5)
+    tv = torchvision.ops.nms(torch.from_numpy(b[:, [1, 0, 3, 2]].copy()), torch.from_numpy(s), 0.5).numpy()
+    assert np.array_equal(keep, tv)
+    # truncation at max_out
+    assert np.array_equal(_native.nms_tf113(b, s, 17, 0.5), tv[:17])
+
+
+def test_nms_properties_and_zero_area():
+    rng = np.random.default_rng(5)
+    b = _rand_boxes(rng, 500)
+    b[::7, 2] = b[::7, 0]                                          # zero-area boxes
+    s = rng.random(500).astype(np.float32)
+    keep = _native.nms_tf113(b, s, 500, 0.3)
+    assert np.all(np.diff(s[keep]) <= 0)                           # score-sorted
+    za = set(range(0, 500, 7))
+    assert za.issubset(set(keep.tolist()))                         # zero-area never suppressed
+    lib = _native.lib()
+    bc = np.ascontiguousarray(b)
+    for i in keep[:40]:
+        for j in keep[:40]:
+            if i != j:
+                assert lib.oracle_iou(bc.ctypes.data, int(i), int(j)) <= 0.3
+
+
+def test_heap_pop_order_ties_is_not_index_order():
+    # all-equal scores: libstdc++'s heap does NOT pop in index order — the quirk the CUDA
+    # kernels must reproduce (TF 1.13 has no index tie-break).
+    order = _native.heap_pop_order(np.ones(16, dtype=np.float32))
+    assert sorted(order.tolist()) == list(range(16))
+    assert order[0] == 0 and order.tolist() != list(range(16))
+    # strictly decreasing scores: index order
+    assert _native.heap_pop_order(np.arange(50, 0, -1).astype(np.float32)).tolist() == list(range(50))
+
+
+def test_crop_and_resize_loop_equals_vectorised():
+    rng = np.random.default_rng(3)
+    img = rng.normal(size=(2, 9, 11, 5)).astype(np.float32)
+    boxes = _rand_boxes(rng, 30)
+    boxes[0] = [0, 0, 1, 1]
+    boxes[1] = [-0.2, 0.1, 1.3, 0.9]                               # partly outside -> zeros
+    boxes[2] = [0.5, 0.5, 0.5, 0.5]                                # zero area
+    bi = rng.integers(0, 2, 30)
+    a = GL.crop_and_resize(img, boxes, bi, (7, 7))
+    b = GL.crop_and_resize_fast(img, boxes, bi, (7, 7))
+    assert np.array_equal(a, b)
+    # full-image box with crop == image size is the identity
+    c = GL.crop_and_resize(img, np.array([[0, 0, 1, 1]], np.float32), [1], (9, 11))
+    assert np.allclose(c[0], img[1], atol=1e-6)
+
+
+def test_roi_levels_edge_cases():
+    boxes = np.array([[[0, 0, 1, 1], [0, 0, 0, 0], [0.1, 0.1, 0.1, 0.5], [0, 0, 224 / 256, 224 / 256],
+                       [0, 0, 0.05, 0.05]]], dtype=np.float32)
+    lv = GL.roi_levels(boxes, np.float32(256 * 256))
+    assert lv.tolist() == [[4, 2, 2, 4, 2]]
+    lv = GL.roi_levels(boxes, np.float32(1024 * 1024))
+    assert lv.tolist() == [[5, 2, 2, 5, 2]]
+
+
+def test_skimage_resize_vs_cv2_interior():
+    import cv2
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(132, 132), dtype=np.uint8)
+    out = H.skimage_resize(img, (256, 256), preserve_range=True)
+    ref = cv2.resize(img.astype(np.float64), (256, 256), interpolation=cv2.INTER_LINEAR)
+    # identical half-pixel-centre bilinear in the interior; borders differ (cval=0 blend vs replicate)
+    assert np.allclose(out[2:-2, 2:-2], ref[2:-2, 2:-2], atol=1e-9)
+    assert out[0, 5] < ref[0, 5] + 1e-9
+    # 28x28 float mask up-scaling used by unmold_mask
+    m = rng.random((28, 28)).astype(np.float32)
+    o2 = H.skimage_resize(m, (61, 35))
+    r2 = cv2.resize(m.astype(np.float64), (35, 61), interpolation=cv2.INTER_LINEAR)
+    assert np.allclose(o2[2:-2, 2:-2], r2[2:-2, 2:-2], atol=1e-9)
+
+
+def test_zscale_on_shipped_fits(golden_dir):
+    for name, nan_count in (("galaxy0002.fits", 288), ("sidelobe0001.fits", 0)):
+        raw = open(os.path.join(golden_dir, name), "rb").read()
+        data, hdr = H.parse_fits_primary(raw)
+        assert data.shape == (132, 132) and hdr["BITPIX"] == -32
+        assert int(np.isnan(data).sum()) == nan_count
+        rgb = H.fits_to_rgb(data)
+        assert rgb.shape == (132, 132, 3) and rgb.dtype == np.uint8
+        assert np.array_equal(rgb[..., 0], rgb[..., 1]) and np.array_equal(rgb[..., 1], rgb[..., 2])
+        assert rgb.max() == 255 and rgb.min() == 0
+        x = np.array(data, dtype=np.float32)
+        x[np.isnan(x)] = np.nanmin(x)
+        vmin, vmax = H.zscale_limits(x, 0.25)
+        assert x.min() <= vmin < vmax <= x.max()
+
+
+def test_top_k_ties_lower_index_first():
+    v = np.array([0.5, 1.0, 0.5, 1.0, 0.25], dtype=np.float32)
+    assert GL.top_k_indices(v, 4).tolist() == [1, 3, 0, 2]
