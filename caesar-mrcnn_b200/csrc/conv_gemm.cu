@@ -1,0 +1,574 @@
+// bf16 implicit-GEMM convolution for sm_100a: TMA (cp.async.bulk.tensor, 128B swizzle, OOB zero fill
+// = SAME padding) -> shared memory ring -> tcgen05.mma (UMMA 128 x BLOCK_N x 16, fp32 accumulators in
+// TMEM) -> tcgen05.ld epilogue (folded BN scale/shift, residual add incl. nearest-2x FPN upsample,
+// ReLU, bf16/f32 store, 2x2-stride-2 transposed-conv scatter).
+//
+// Replaces every KL.Conv2D / TimeDistributed(Conv2D|Dense) / Conv2DTranspose on the detect path:
+// mrcnn/model.py:99-210 (ResNet-101), :2003-2026 (FPN), :916-957 (RPN), :986-1039 (class head),
+// :1042-1091 (mask head).  One CTA computes a 128 x BLOCK_N output tile:
+//   warp 0   : TMA producer (one lane)      — A box (64ch, tw, th, nb) per filter tap, B box (64, BLOCK_N)
+//   warp 1   : TMEM alloc + MMA issuer (one lane), tcgen05.commit releases ring slots
+//   warps 2-5: epilogue, warp (w%4) owns TMEM lanes 32*(w%4)..+31 = output rows
+// Two CTAs fit per SM (<= 100 KB smem, <= 256 TMEM columns each) so one CTA's epilogue overlaps the
+// other's main loop.
+#include <cuda.h>
+#include <mutex>
+#include "conv_gemm.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle-128B atom row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+template <int BLOCK_N> struct TileCfg {
+  static constexpr int STAGES = (BLOCK_N <= 64) ? 4 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (error surfaces on the host) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > 400000000u) {
+      printf("conv_gemm: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart):
+// start address>>4 | LBO(ignored for swizzled K-major)=1 | SBO = 1024>>4 | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                  const __grid_constant__ CUtensorMap tmap_b,
+                                                                  const ConvGemmParams p) {
+  using Cfg = TileCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment required by the 128B swizzle
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+  unsigned char* base_ptr = smem_raw + (base_addr - raw_addr);
+  const uint32_t bar_base = base_addr + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x % p.n_tiles;   // N fastest: CTAs sharing an A tile are co-scheduled (L2 reuse)
+  const int m_tile = blockIdx.x / p.n_tiles;
+  const int tw_i = m_tile % p.tiles_w;
+  const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
+  const int tn_i = m_tile / (p.tiles_w * p.tiles_h);
+  const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.nb;
+  const int num_kb = p.kh * p.kw * p.cin_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const uint32_t a_bytes = (uint32_t)(p.tw * p.th * p.nb) * (BLOCK_K * 2);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const int tap = kb / p.cin_blocks;
+        const int cb = kb - tap * p.cin_blocks;
+        const int r = tap / p.kw, sx = tap - r * p.kw;
+        const uint32_t a_dst = base_addr + s * Cfg::STAGE_BYTES;
+        const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+        mbar_expect_tx(full_bar(s), a_bytes + Cfg::B_BYTES);
+        tma_load_4d(a_dst, &tmap_a, full_bar(s), cb * BLOCK_K, w0 + sx - p.pad, h0 + r - p.pad, n0);
+        tma_load_2d(b_dst, &tmap_b, full_bar(s), kb * BLOCK_K, n_tile * BLOCK_N);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BLOCK_N, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                                 ((uint32_t)(BLOCK_M >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tcgen05_fence_after();
+        const uint32_t a_addr = base_addr + s * Cfg::STAGE_BYTES;
+        const uint64_t da = make_sw128_desc(a_addr);
+        const uint64_t db = make_sw128_desc(a_addr + Cfg::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the >>4 address field
+          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));   // frees the ring slot once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;   // output row inside the tile
+    const int per_img = p.tw * p.th;
+    const int ni = row / per_img;
+    const int rem = row - ni * per_img;
+    const int hi = rem / p.tw;
+    const int wi = rem - hi * p.tw;
+    const int n = n0 + ni, h = h0 + hi, w = w0 + wi;
+    const bool row_ok = (row < per_img * p.nb) && (n < p.N) && (h < p.OH) && (w < p.OW);
+    const int col_base = n_tile * BLOCK_N;
+    size_t out_off;
+    int ch_base = col_base;          // channel index used for scale/shift and the store column
+    if (p.out_mode == 1) {
+      const int tap = col_base / p.cout;
+      ch_base = col_base - tap * p.cout;
+      const int oi = tap >> 1, oj = tap & 1;
+      out_off = (((size_t)n * (2 * p.OH) + (2 * h + oi)) * (size_t)(2 * p.OW) + (2 * w + oj)) * (size_t)p.out_ld;
+    } else {
+      out_off = (((size_t)n * p.OH + h) * (size_t)p.OW + w) * (size_t)p.out_ld;
+    }
+    const __nv_bfloat16* res_row = nullptr;
+    if (p.residual != nullptr && row_ok) {
+      if (p.res_up2)
+        res_row = p.residual + (((size_t)n * (p.OH >> 1) + (h >> 1)) * (size_t)(p.OW >> 1) + (w >> 1)) * (size_t)p.cout;
+      else
+        res_row = p.residual + (((size_t)n * p.OH + h) * (size_t)p.OW + w) * (size_t)p.cout;
+    }
+    const int cout_store = min((p.cout + 7) & ~7, p.out_ld);
+
+    mbar_wait(tmem_full_bar, 0);
+    __syncwarp();
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {   // groups of 8 columns
+          const int ch = ch_base + c + g * 8;
+          if (ch < cout_store) {
+            float o[8];
+            if (ch + 8 <= p.cout) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + ch));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + ch + 4));
+              const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.shift + ch));
+              const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.shift + ch + 4));
+              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] = fmaf(__uint_as_float(v[g * 8 + k]), sc[k], sh[k]);
+              if (res_row != nullptr) {
+                const uint4 rr = __ldg(reinterpret_cast<const uint4*>(res_row + ch));
+                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  o[2 * k] += __uint_as_float(rw[k] << 16);
+                  o[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int cc = ch + k;
+                float val = 0.f;
+                if (cc < p.cout) {
+                  val = fmaf(__uint_as_float(v[g * 8 + k]), __ldg(p.scale + cc), __ldg(p.shift + cc));
+                  if (res_row != nullptr) val += __bfloat162float(res_row[cc]);
+                }
+                o[k] = val;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
+            }
+            if (p.out_f32) {
+              float* dst = static_cast<float*>(p.out) + out_off + ch;
+              *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + out_off + ch;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core reference (tests only): same descriptor semantics, fp32 accumulation
+// ---------------------------------------------------------------------------------------------
+struct SimtParams {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* w;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  void* out;
+  int N, H, W, Cin, KH, KW, stride, pad, OH, OW, cout, cout_total, relu, res_up2, out_f32, out_mode, out_ld;
+};
+
+__global__ void conv_simt_kernel(SimtParams p) {
+  const size_t total = (size_t)p.N * p.OH * p.OW * p.cout_total;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % p.cout_total);
+    size_t pix = idx / p.cout_total;
+    const int ow = (int)(pix % p.OW);
+    pix /= p.OW;
+    const int oh = (int)(pix % p.OH);
+    const int n = (int)(pix / p.OH);
+    const int K = p.KH * p.KW * p.Cin;
+    const __nv_bfloat16* wrow = p.w + (size_t)col * K;
+    float acc = 0.f;
+    for (int r = 0; r < p.KH; ++r) {
+      const int ih = oh * p.stride + r - p.pad;
+      if (ih < 0 || ih >= p.H) continue;
+      for (int s = 0; s < p.KW; ++s) {
+        const int iw = ow * p.stride + s - p.pad;
+        if (iw < 0 || iw >= p.W) continue;
+        const __nv_bfloat16* xp = p.x + (((size_t)n * p.H + ih) * p.W + iw) * p.Cin;
+        const __nv_bfloat16* wp = wrow + (size_t)(r * p.KW + s) * p.Cin;
+        for (int c = 0; c < p.Cin; ++c) acc = fmaf(__bfloat162float(xp[c]), __bfloat162float(wp[c]), acc);
+      }
+    }
+    int ch = col;
+    size_t off;
+    if (p.out_mode == 1) {
+      const int tap = col / p.cout;
+      ch = col - tap * p.cout;
+      off = (((size_t)n * (2 * p.OH) + (2 * oh + (tap >> 1))) * (size_t)(2 * p.OW) + (2 * ow + (tap & 1))) * (size_t)p.out_ld + ch;
+    } else {
+      off = (((size_t)n * p.OH + oh) * (size_t)p.OW + ow) * (size_t)p.out_ld + ch;
+    }
+    float v = fmaf(acc, p.scale[ch], p.shift[ch]);
+    if (p.residual) {
+      size_t ro = p.res_up2 ? (((size_t)n * (p.OH >> 1) + (oh >> 1)) * (size_t)(p.OW >> 1) + (ow >> 1)) * (size_t)p.cout + ch
+                            : (((size_t)n * p.OH + oh) * (size_t)p.OW + ow) * (size_t)p.cout + ch;
+      v += __bfloat162float(p.residual[ro]);
+    }
+    if (p.relu) v = fmaxf(v, 0.f);
+    if (p.out_f32)
+      static_cast<float*>(p.out)[off] = v;
+    else
+      static_cast<__nv_bfloat16*>(p.out)[off] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+int encode_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    mrcnn_set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return MRCNN_ERR_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mrcnn_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r, rank,
+                    (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                    (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return MRCNN_ERR_CUDA;
+  }
+  return MRCNN_OK;
+}
+
+template <int BN> int launch_tile(const ConvPlan* plan, cudaStream_t st) {
+  using Cfg = TileCfg<BN>;
+  static bool attr_done[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_done[dev]) {
+    MRCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done[dev] = true;
+  }
+  conv_gemm_kernel<BN><<<plan->grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(plan->tmap_a, plan->tmap_b, plan->p);
+  MRCNN_CHECK_CUDA(cudaGetLastError());
+  mrcnn_count_launch(1);
+  return MRCNN_OK;
+}
+
+int validate_desc(const mrcnn_conv_desc* d, int* OH, int* OW) {
+  MRCNN_REQUIRE(d != nullptr, "conv2d: null descriptor");
+  MRCNN_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "conv2d: empty tensor");
+  MRCNN_REQUIRE(d->cin % 64 == 0, "conv2d: Cin=%d must be a multiple of 64", d->cin);
+  const bool k1 = d->kh == 1 && d->kw == 1 && d->pad == 0 && (d->stride == 1 || d->stride == 2);
+  const bool k3 = d->kh == 3 && d->kw == 3 && d->pad == 1 && d->stride == 1;
+  MRCNN_REQUIRE(k1 || k3, "conv2d: unsupported filter %dx%d stride %d pad %d", d->kh, d->kw, d->stride, d->pad);
+  *OH = (d->h + 2 * d->pad - d->kh) / d->stride + 1;
+  *OW = (d->w + 2 * d->pad - d->kw) / d->stride + 1;
+  if (d->stride == 2) MRCNN_REQUIRE(d->h % 2 == 0 && d->w % 2 == 0, "conv2d: stride 2 needs even H, W");
+  if (d->residual_upsample2) MRCNN_REQUIRE(*OH % 2 == 0 && *OW % 2 == 0, "conv2d: upsampled residual needs even output size");
+  MRCNN_REQUIRE(d->out_dtype == MRCNN_DTYPE_F32 || d->out_dtype == MRCNN_DTYPE_BF16, "conv2d: bad out_dtype");
+  MRCNN_REQUIRE(d->out_mode == 0 || d->out_mode == 1, "conv2d: bad out_mode");
+  const int ld = d->out_ld ? d->out_ld : d->cout;
+  MRCNN_REQUIRE(ld % 8 == 0 && ld >= d->cout, "conv2d: out_ld=%d must be a multiple of 8 and >= cout", ld);
+  if (d->out_mode == 1) MRCNN_REQUIRE(d->cout % 32 == 0, "conv2d: deconv mode needs cout %% 32 == 0");
+  return MRCNN_OK;
+}
+
+}  // namespace
+
+int conv_plan_create(const mrcnn_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
+                     const void* residual, void* out, int block_n, ConvPlan* plan) {
+  int OH, OW;
+  int rc = validate_desc(d, &OH, &OW);
+  if (rc) return rc;
+  MRCNN_REQUIRE(x && w && scale && shift && out && plan, "conv2d: null pointer");
+  ConvGemmParams& p = plan->p;
+  const int cout_total = d->out_mode == 1 ? 4 * d->cout : d->cout;
+  if (block_n == 0) {
+    if (d->out_mode == 1) block_n = 128;
+    else if (cout_total <= 32) block_n = 32;
+    else if (cout_total <= 64) block_n = 64;
+    else block_n = 128;
+  }
+  MRCNN_REQUIRE(block_n == 32 || block_n == 64 || block_n == 128, "conv2d: block_n must be 32/64/128");
+  if (d->out_mode == 1) MRCNN_REQUIRE(d->cout % block_n == 0, "conv2d: deconv cout %% block_n != 0");
+  plan->block_n = block_n;
+
+  // ---- A view: 4-D (C, W', H', N) where stride-2 1x1 convs see the sub-sampled view ----------
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4];
+  // 1x1 stride 1 == plain [M, Cin] GEMM (rows need no (n,h,w) decode unless the residual is upsampled)
+  const bool flat = (d->kh == 1 && d->stride == 1 && !d->residual_upsample2);
+  if (flat) {
+    const unsigned long long M = (unsigned long long)d->n * d->h * d->w;
+    dims[0] = d->cin; dims[1] = M; dims[2] = 1; dims[3] = 1;
+    strides[0] = (cuuint64_t)d->cin * 2; strides[1] = strides[0] * M; strides[2] = strides[1];
+    p.tw = 128; p.th = 1; p.nb = 1;
+    p.OW = (int)M; p.OH = 1; p.N = 1;
+    MRCNN_REQUIRE(M < (1ull << 31), "conv2d: M too large");
+  } else {
+    dims[0] = d->cin; dims[1] = OW; dims[2] = OH; dims[3] = d->n;
+    if (d->kh == 3) { dims[1] = d->w; dims[2] = d->h; }
+    strides[0] = (cuuint64_t)d->cin * 2 * d->stride;
+    strides[1] = (cuuint64_t)d->cin * 2 * d->w * d->stride;
+    strides[2] = (cuuint64_t)d->cin * 2 * d->w * d->h;
+    p.OW = OW; p.OH = OH; p.N = d->n;
+    p.tw = OW < 128 ? OW : 128;
+    p.th = 128 / p.tw; if (p.th > OH) p.th = OH;
+    p.nb = (p.th == OH) ? 128 / (p.tw * p.th) : 1;
+    if (p.nb < 1) p.nb = 1;
+    if (p.nb > d->n) p.nb = d->n;
+  }
+  p.tiles_w = ceil_div(p.OW, p.tw);
+  p.tiles_h = ceil_div(p.OH, p.th);
+  p.tiles_nb = ceil_div(p.N, p.nb);
+  box[0] = 64; box[1] = p.tw; box[2] = p.th; box[3] = p.nb;
+  rc = encode_map(&plan->tmap_a, x, 4, dims, strides, box);
+  if (rc) return rc;
+
+  // ---- B: weights [cout_total, K] K-major; rows beyond cout_total are OOB -> zero fill --------
+  const unsigned long long K = (unsigned long long)d->kh * d->kw * d->cin;
+  cuuint64_t bdims[2] = {K, (cuuint64_t)cout_total};
+  cuuint64_t bstr[1] = {K * 2};
+  cuuint32_t bbox[2] = {64, (cuuint32_t)block_n};
+  rc = encode_map(&plan->tmap_b, w, 2, bdims, bstr, bbox);
+  if (rc) return rc;
+
+  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad;
+  p.cin_blocks = d->cin / 64;
+  p.cout = d->cout;
+  p.cout_total = cout_total;
+  p.relu = d->relu;
+  p.res_up2 = d->residual_upsample2;
+  p.out_f32 = d->out_dtype == MRCNN_DTYPE_F32;
+  p.out_mode = d->out_mode;
+  p.out_ld = d->out_ld ? d->out_ld : d->cout;
+  p.scale = scale;
+  p.shift = shift;
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.out = out;
+  if (residual) MRCNN_REQUIRE(d->cout % 8 == 0, "conv2d: residual needs cout %% 8 == 0");
+  p.n_tiles = ceil_div(cout_total, block_n);
+  const long long ctas = (long long)p.n_tiles * p.tiles_w * p.tiles_h * p.tiles_nb;
+  MRCNN_REQUIRE(ctas < 2147483647LL, "conv2d: grid too large");
+  plan->grid = dim3((unsigned)ctas, 1, 1);
+  plan->flops = 2.0 * (double)d->n * OH * OW * (double)cout_total * (double)K;
+  return MRCNN_OK;
+}
+
+int conv_plan_launch(const ConvPlan* plan, cudaStream_t st) {
+  switch (plan->block_n) {
+    case 32: return launch_tile<32>(plan, st);
+    case 64: return launch_tile<64>(plan, st);
+    case 128: return launch_tile<128>(plan, st);
+  }
+  mrcnn_set_error("conv2d: bad block_n %d", plan->block_n);
+  return MRCNN_ERR_INVALID;
+}
+
+extern "C" int mrcnn_conv2d_bf16(const mrcnn_conv_desc* desc, const void* x, const void* w, const float* scale,
+                                 const float* shift, const void* residual, void* out, void* stream) {
+  ConvPlan plan;
+  int rc = conv_plan_create(desc, x, w, scale, shift, residual, out, 0, &plan);
+  if (rc) return rc;
+  return conv_plan_launch(&plan, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mrcnn_conv2d_bf16_simt(const mrcnn_conv_desc* d, const void* x, const void* w, const float* scale,
+                                      const float* shift, const void* residual, void* out, void* stream) {
+  int OH, OW;
+  int rc = validate_desc(d, &OH, &OW);
+  if (rc) return rc;
+  SimtParams p;
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.w = static_cast<const __nv_bfloat16*>(w);
+  p.scale = scale; p.shift = shift;
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.out = out;
+  p.N = d->n; p.H = d->h; p.W = d->w; p.Cin = d->cin; p.KH = d->kh; p.KW = d->kw; p.stride = d->stride; p.pad = d->pad;
+  p.OH = OH; p.OW = OW; p.cout = d->cout; p.cout_total = d->out_mode == 1 ? 4 * d->cout : d->cout;
+  p.relu = d->relu; p.res_up2 = d->residual_upsample2; p.out_f32 = d->out_dtype == MRCNN_DTYPE_F32;
+  p.out_mode = d->out_mode; p.out_ld = d->out_ld ? d->out_ld : d->cout;
+  const size_t total = (size_t)p.N * OH * OW * p.cout_total;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  conv_simt_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MRCNN_CHECK_CUDA(cudaGetLastError());
+  return MRCNN_OK;
+}

@@ -1,0 +1,38 @@
+// Internal C++ interface of the bf16 implicit-GEMM convolution family (conv_gemm.cu).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "mrcnn_b200.h"
+
+struct ConvGemmParams {
+  // M tiling: an M tile is a TMA box (64ch, tw, th, nb) of the (possibly strided) input view
+  int tiles_w, tiles_h, tiles_nb, n_tiles;
+  int tw, th, nb;
+  int OW, OH, N;      // output spatial size and image count
+  int kh, kw, pad;    // filter taps (stride is folded into the tensor-map view)
+  int cin_blocks;     // Cin / 64
+  int cout;           // real output channels (per tap in deconv mode)
+  int cout_total;     // GEMM N extent (4*cout in deconv mode)
+  int relu, res_up2, out_f32, out_mode, out_ld;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  void* out;
+};
+
+struct ConvPlan {
+  CUtensorMap tmap_a;
+  CUtensorMap tmap_b;
+  ConvGemmParams p;
+  int block_n;
+  dim3 grid;
+  double flops;
+};
+
+// Builds the tensor maps + launch geometry for one layer.  x/w/out are device pointers that must
+// stay valid for the life of the plan.  block_n = 0 picks a tile width from cout.
+int conv_plan_create(const mrcnn_conv_desc* d, const void* x, const void* w, const float* scale,
+                     const float* shift, const void* residual, void* out, int block_n, ConvPlan* plan);
+int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);
+
+void mrcnn_count_launch(unsigned long long n);

@@ -1,0 +1,265 @@
+// ProposalLayer — one fused pass per image (one 1024-thread CTA per image):
+//   radix-select + bitonic sort top-k over the anchor fg scores (ties -> lower index first)
+//   -> gather deltas/anchors, apply_box_deltas, clip to [0,1]
+//   -> greedy NMS in shared memory in TF-1.13 pop order -> zero-padded rois.
+// Replaces mrcnn/model.py:329-406 (ProposalLayer.call), :287-326 (apply_box_deltas_graph,
+// clip_boxes_graph) and the per-image Python unrolling of utils.batch_slice (utils.py:872-906).
+// Bit-exact contract: top-k indices, NMS keep indices and rois equal oracle/graph_layers.py
+// proposal_layer() for identical float32 inputs.
+#include "box_ops.cuh"
+#include "mrcnn_b200.h"
+
+namespace {
+
+constexpr int PROP_THREADS = 1024;
+constexpr int PROP_MAX_K = 6144;
+constexpr int PROP_MAX_R = 1024;
+
+struct PropParams {
+  const float* rpn_class;  // [B,A,2]
+  const float* rpn_bbox;   // [B,A,4]
+  const float* anchors;    // [A,4] (stride 0) or [B,A,4]
+  long long anchor_bstride;
+  int A, K, Kpad, R;
+  float thr;
+  float sd[4];
+  float* rois;        // [B,R,4]
+  int32_t* topk_idx;  // [B,K]   (required: caller or workspace)
+  int32_t* keep_idx;  // [B,R] or null (index into the top-k order, -1 padded)
+  int32_t* keep_cnt;  // [B] or null
+  int r0_bytes;
+};
+
+__device__ __forceinline__ int block_excl_scan_flag(bool flag, int* warp_tot, int& total) {
+  // exclusive prefix count of `flag` over the block (blockDim multiple of 32, <= 1024)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  unsigned bal = __ballot_sync(0xffffffffu, flag);
+  int pre = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) warp_tot[warp] = __popc(bal);
+  __syncthreads();
+  int off = 0, tot = 0;
+  for (int w = 0; w < nw; ++w) {
+    int v = warp_tot[w];
+    if (w < warp) off += v;
+    tot += v;
+  }
+  __syncthreads();
+  total = tot;
+  return off + pre;
+}
+
+__global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int nt = blockDim.x;
+  const int A = p.A, K = p.K, Kpad = p.Kpad, R = p.R;
+
+  // ---- shared memory carve-up ---------------------------------------------------------------
+  unsigned char* r0 = smem;                                              // phase A / phase B region
+  Box4* boxes = reinterpret_cast<Box4*>(smem + p.r0_bytes);              // [K]
+  float* s_scores = reinterpret_cast<float*>(boxes + K);                 // [K]
+  NmsScratch* sc = reinterpret_cast<NmsScratch*>(s_scores + ((K + 3) & ~3));
+  int* hist = reinterpret_cast<int*>(sc + 1);                            // [256]
+  int* warp_tot = hist + 256;                                            // [32]
+  int* misc = warp_tot + 32;                                             // [8]
+
+  unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(r0);
+  const float* scores = p.rpn_class + (size_t)b * A * 2 + 1;             // fg score, stride 2
+
+  // ---- 1. radix select: key of the K-th largest score ---------------------------------------
+  uint32_t prefix = 0, mask = 0;
+  int need = K;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 256; i += nt) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < A; i += nt) {
+      uint32_t key = float_to_key(scores[2 * (size_t)i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int cum = 0, bin = 0;
+      for (int bb = 255; bb >= 0; --bb) {
+        int h = hist[bb];
+        if (cum + h >= need) {
+          bin = bb;
+          break;
+        }
+        cum += h;
+      }
+      misc[0] = bin;
+      misc[1] = need - cum;
+    }
+    __syncthreads();
+    prefix |= (uint32_t)misc[0] << shift;
+    mask |= 255u << shift;
+    need = misc[1];
+    __syncthreads();
+  }
+  const uint32_t T = prefix;       // K-th largest key; `need` elements equal to T are taken,
+  const int cnt_gt = K - need;     // lowest indices first (tf.nn.top_k tie rule)
+
+  // ---- 2. compaction into the sort buffer -----------------------------------------------------
+  if (tid == 0) misc[2] = 0;
+  for (int i = K + tid; i < Kpad; i += nt) sortbuf[i] = 0ull;
+  __syncthreads();
+  int eq_base = 0;
+  for (int base = 0; base < A; base += nt) {
+    const int i = base + tid;
+    const bool valid = i < A;
+    const uint32_t key = valid ? float_to_key(scores[2 * (size_t)i]) : 0u;
+    const bool gt = valid && key > T;
+    const bool eq = valid && key == T;
+    int tot_eq;
+    const int rank = eq_base + block_excl_scan_flag(eq, warp_tot, tot_eq);
+    const unsigned long long comp = ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)i);
+    if (eq && rank < need) sortbuf[cnt_gt + rank] = comp;
+    if (gt) sortbuf[atomicAdd(&misc[2], 1)] = comp;
+    eq_base += tot_eq;
+  }
+  __syncthreads();
+
+  // ---- 3. bitonic sort, descending on (key, ~index) ------------------------------------------
+  for (int k = 2; k <= Kpad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < Kpad; i += nt) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = sortbuf[i], c = sortbuf[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < c) : (a > c)) {
+            sortbuf[i] = c;
+            sortbuf[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- 4. gather + decode + clip --------------------------------------------------------------
+  const float* deltas = p.rpn_bbox + (size_t)b * A * 4;
+  const float* anch = p.anchors + (size_t)b * p.anchor_bstride;
+  int32_t* topk = p.topk_idx + (size_t)b * K;
+  for (int q = tid; q < K; q += nt) {
+    const uint32_t idx = ~(uint32_t)(sortbuf[q] & 0xffffffffull);
+    topk[q] = (int32_t)idx;
+    s_scores[q] = scores[2 * (size_t)idx];
+    const float4 d = *reinterpret_cast<const float4*>(deltas + 4 * (size_t)idx);
+    const float4 a = *reinterpret_cast<const float4*>(anch + 4 * (size_t)idx);
+    Box4 bx = {a.x, a.y, a.z, a.w};
+    bx = apply_box_deltas(bx, __fmul_rn(d.x, p.sd[0]), __fmul_rn(d.y, p.sd[1]),
+                          __fmul_rn(d.z, p.sd[2]), __fmul_rn(d.w, p.sd[3]));
+    boxes[q] = clip_box(bx, 0.f, 0.f, 1.f, 1.f);
+  }
+  __syncthreads();
+
+  // ---- 5. pop order (identity unless scores tie) ----------------------------------------------
+  HeapEntry* heap = reinterpret_cast<HeapEntry*>(r0);                  // [K]
+  uint16_t* order = reinterpret_cast<uint16_t*>(heap + K);             // [K]
+  uint16_t* selected = order + ((K + 1) & ~1);                          // [R]
+  uint32_t* removed = reinterpret_cast<uint32_t*>(selected + ((R + 1) & ~1));
+  bool tie = false;
+  for (int q = tid; q + 1 < K; q += nt) tie |= (s_scores[q] == s_scores[q + 1]);
+  const int any_tie = __syncthreads_or(tie ? 1 : 0);
+  if (any_tie) {
+    for (int q = tid; q < K; q += nt) {
+      HeapEntry e;
+      e.score = s_scores[q];
+      e.id = q;
+      heap[q] = e;
+    }
+    __syncthreads();
+    if (tid == 0) heap_pop_order_serial(heap, K, /*presorted_desc=*/true, order);
+  } else {
+    for (int q = tid; q < K; q += nt) order[q] = (uint16_t)q;
+  }
+  __syncthreads();
+
+  // ---- 6. NMS + output ------------------------------------------------------------------------
+  const int count = block_nms(boxes, order, K, R, p.thr, removed, selected, sc);
+  __syncthreads();
+  float4* out = reinterpret_cast<float4*>(p.rois + (size_t)b * R * 4);
+  for (int r = tid; r < R; r += nt) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cand = -1;
+    if (r < count) {
+      cand = order[selected[r]];
+      const Box4 bx = boxes[cand];
+      v = make_float4(bx.y1, bx.x1, bx.y2, bx.x2);
+    }
+    out[r] = v;
+    if (p.keep_idx) p.keep_idx[(size_t)b * R + r] = cand;
+  }
+  if (tid == 0 && p.keep_cnt) p.keep_cnt[b] = count;
+}
+
+int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+size_t prop_smem_bytes(int K, int R, int* r0_bytes) {
+  const int Kpad = next_pow2(K);
+  size_t a = (size_t)Kpad * 8;
+  size_t bsz = (size_t)K * sizeof(HeapEntry) + (size_t)((K + 1) & ~1) * 2 + (size_t)((R + 1) & ~1) * 2 +
+               (size_t)((K + 31) / 32 + 2) * 4;
+  size_t r0 = a > bsz ? a : bsz;
+  r0 = (r0 + 15) & ~(size_t)15;
+  *r0_bytes = (int)r0;
+  return r0 + (size_t)K * sizeof(Box4) + (size_t)((K + 3) & ~3) * 4 + sizeof(NmsScratch) + (256 + 32 + 8) * 4;
+}
+
+}  // namespace
+
+extern "C" size_t mrcnn_proposal_workspace_bytes(int batch, int num_anchors, int pre_nms_limit) {
+  int K = pre_nms_limit < num_anchors ? pre_nms_limit : num_anchors;
+  return (size_t)batch * (size_t)(K > 0 ? K : 1) * sizeof(int32_t);
+}
+
+extern "C" int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox, const float* anchors,
+                                    int anchors_batched, int batch, int num_anchors, int pre_nms_limit,
+                                    int proposal_count, float nms_threshold, const float* bbox_std_dev,
+                                    float* rpn_rois, int32_t* topk_idx, int32_t* keep_idx,
+                                    int32_t* keep_count, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  MRCNN_REQUIRE(rpn_class && rpn_bbox && anchors && rpn_rois && bbox_std_dev, "proposal_layer: null pointer");
+  MRCNN_REQUIRE(batch > 0 && num_anchors > 0, "proposal_layer: empty input (batch=%d anchors=%d)", batch, num_anchors);
+  const int K = pre_nms_limit < num_anchors ? pre_nms_limit : num_anchors;
+  MRCNN_REQUIRE(K >= 1 && K <= PROP_MAX_K, "proposal_layer: min(PRE_NMS_LIMIT, anchors)=%d outside [1,%d]", K, PROP_MAX_K);
+  MRCNN_REQUIRE(proposal_count >= 1 && proposal_count <= PROP_MAX_R, "proposal_layer: proposal_count=%d outside [1,%d]", proposal_count, PROP_MAX_R);
+  PropParams p;
+  p.rpn_class = rpn_class;
+  p.rpn_bbox = rpn_bbox;
+  p.anchors = anchors;
+  p.anchor_bstride = anchors_batched ? (long long)num_anchors * 4 : 0;
+  p.A = num_anchors;
+  p.K = K;
+  p.Kpad = next_pow2(K);
+  p.R = proposal_count;
+  p.thr = nms_threshold;
+  for (int i = 0; i < 4; ++i) p.sd[i] = bbox_std_dev[i];
+  p.rois = rpn_rois;
+  p.keep_idx = keep_idx;
+  p.keep_cnt = keep_count;
+  if (topk_idx) {
+    p.topk_idx = topk_idx;
+  } else {
+    MRCNN_REQUIRE(workspace && workspace_bytes >= mrcnn_proposal_workspace_bytes(batch, num_anchors, pre_nms_limit),
+                  "proposal_layer: workspace too small");
+    p.topk_idx = static_cast<int32_t*>(workspace);
+  }
+  size_t smem = prop_smem_bytes(K, proposal_count, &p.r0_bytes);
+  MRCNN_REQUIRE(smem <= 227 * 1024, "proposal_layer: shared memory %zu exceeds 227 KB", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MRCNN_CHECK_CUDA(cudaFuncSetAttribute(proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  proposal_kernel<<<batch, PROP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  MRCNN_CHECK_CUDA(cudaGetLastError());
+  return MRCNN_OK;
+}

@@ -1,0 +1,173 @@
+// PyramidROIAlign — level-routed tf.image.crop_and_resize(bilinear), one CTA per ROI, NHWC features,
+// 16-byte vector loads (8 bf16 / 4 f32 channels per lane), streaming 16-byte stores.
+// Replaces mrcnn/model.py:428-534 (PyramidROIAlign.call: 4x tf.where + gather_nd + crop_and_resize,
+// concat, top_k re-sort) and :413-423 (log2_graph).  The reference's "route, crop, restore order"
+// is the identity out[b,n] = crop(P_level(b,n)[b], boxes[b,n]), which is what is computed here.
+// Contract: ROI levels bit-exact; float32 features -> bit-exact samples (no FMA contraction);
+// bf16 features -> float32 lerp of the bf16 values, one rounding to bf16 on store.
+#include "box_ops.cuh"
+#include "mrcnn_b200.h"
+
+namespace {
+
+struct RoiParams {
+  const void* feat[4];  // P2..P5, [B,H_l,W_l,C]
+  int H[4], W[4];
+  const float* boxes;   // [B,N,4] normalised (y1,x1,y2,x2)
+  int N, C, P;
+  float image_area;
+  void* out;            // [B,N,P,P,C]
+  int32_t* levels;      // [B,N] or null
+};
+
+// mrcnn/model.py:465-477 — level = min(5, max(2, 4 + int32(round(log2(sqrt(h*w)/(224/sqrt(area)))))))
+// log convention: double log, one rounding to float (oracle/graph_layers.py: log_f32).
+__device__ __forceinline__ int roi_level(float y1, float x1, float y2, float x2, float image_area) {
+  const float h = __fsub_rn(y2, y1);
+  const float w = __fsub_rn(x2, x1);
+  const float denom = __fdiv_rn(224.0f, __fsqrt_rn(image_area));
+  const float v = __fdiv_rn(__fsqrt_rn(__fmul_rn(h, w)), denom);
+  const float lg = (float)log((double)v);
+  const float ln2 = (float)log(2.0);
+  const float r = rintf(__fdiv_rn(lg, ln2));  // tf.round: half to even
+  // tf.cast(float -> int32) on x86 (cvttss2si): NaN / out-of-range -> INT_MIN
+  int ri;
+  if (!(fabsf(r) < 2147483648.0f)) ri = INT_MIN; else ri = (int)r;
+  const int lvl = (int)((unsigned)4 + (unsigned)ri);  // int32 wrap-around
+  return min(5, max(2, lvl));
+}
+
+template <typename T> struct Vec;  // 16-byte channel vector
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float* v) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static void store(float* p, const float* v) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float* v) {
+    uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    __stcs(reinterpret_cast<uint4*>(p), make_uint4(w[0], w[1], w[2], w[3]));
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) roialign_kernel(RoiParams p) {
+  constexpr int VN = Vec<T>::N;
+  const int roi = blockIdx.x;  // b*N + n
+  const int b = roi / p.N;
+  const float4 bx = *reinterpret_cast<const float4*>(p.boxes + (size_t)roi * 4);
+  const float y1 = bx.x, x1 = bx.y, y2 = bx.z, x2 = bx.w;
+  const int lvl = roi_level(y1, x1, y2, x2, p.image_area);
+  if (threadIdx.x == 0 && p.levels) p.levels[roi] = lvl;
+  const int li = lvl - 2;
+  const int H = p.H[li], W = p.W[li], C = p.C, P = p.P;
+  const T* feat = static_cast<const T*>(p.feat[li]) + (size_t)b * H * W * C;
+  T* out = static_cast<T*>(p.out) + (size_t)roi * P * P * C;
+  const float Hm1 = (float)(H - 1), Wm1 = (float)(W - 1);
+  // tf.image.crop_and_resize coordinates (float32, left-to-right evaluation)
+  const float hs = (P > 1) ? __fdiv_rn(__fmul_rn(__fsub_rn(y2, y1), Hm1), (float)(P - 1)) : 0.f;
+  const float ws = (P > 1) ? __fdiv_rn(__fmul_rn(__fsub_rn(x2, x1), Wm1), (float)(P - 1)) : 0.f;
+  const int cv = C / VN;
+  const int items = P * P * cv;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int pix = it / cv;
+    const int c0 = (it - pix * cv) * VN;
+    const int iy = pix / P, ix = pix - iy * P;
+    const float in_y = (P > 1) ? __fadd_rn(__fmul_rn(y1, Hm1), __fmul_rn((float)iy, hs))
+                               : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(y1, y2)), Hm1);
+    const float in_x = (P > 1) ? __fadd_rn(__fmul_rn(x1, Wm1), __fmul_rn((float)ix, ws))
+                               : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(x1, x2)), Wm1);
+    float o[VN];
+    const bool valid = (in_y >= 0.f) && (in_y <= Hm1) && (in_x >= 0.f) && (in_x <= Wm1);
+    if (valid) {
+      const float ty = floorf(in_y), by = ceilf(in_y);
+      const float lx0 = floorf(in_x), rx = ceilf(in_x);
+      const float ly = __fsub_rn(in_y, ty), lx = __fsub_rn(in_x, lx0);
+      const int t = (int)ty, bt = (int)by, l = (int)lx0, r = (int)rx;
+      float tl[VN], tr[VN], bl[VN], br[VN];
+      Vec<T>::load(feat + ((size_t)t * W + l) * C + c0, tl);
+      Vec<T>::load(feat + ((size_t)t * W + r) * C + c0, tr);
+      Vec<T>::load(feat + ((size_t)bt * W + l) * C + c0, bl);
+      Vec<T>::load(feat + ((size_t)bt * W + r) * C + c0, br);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) {
+        const float top = __fadd_rn(tl[k], __fmul_rn(__fsub_rn(tr[k], tl[k]), lx));
+        const float bot = __fadd_rn(bl[k], __fmul_rn(__fsub_rn(br[k], bl[k]), lx));
+        o[k] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VN; ++k) o[k] = 0.f;
+    }
+    Vec<T>::store(out + (size_t)pix * C + c0, o);
+  }
+}
+
+__global__ void roi_levels_kernel(const float* boxes, int n, float image_area, int32_t* levels) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float4 bx = *reinterpret_cast<const float4*>(boxes + (size_t)i * 4);
+    levels[i] = roi_level(bx.x, bx.y, bx.z, bx.w, image_area);
+  }
+}
+
+}  // namespace
+
+extern "C" int mrcnn_roi_levels(const float* boxes, int num_boxes, float image_area, int32_t* levels, void* stream) {
+  MRCNN_REQUIRE(boxes && levels && num_boxes > 0, "roi_levels: bad arguments");
+  roi_levels_kernel<<<ceil_div(num_boxes, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(boxes, num_boxes, image_area, levels);
+  MRCNN_CHECK_CUDA(cudaGetLastError());
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_pyramid_roi_align(const void* const* feature_maps, const int* feat_h, const int* feat_w,
+                                       int channels, int dtype, const float* boxes, int batch, int num_boxes,
+                                       int pool_size, float image_area, void* pooled, int32_t* levels,
+                                       void* stream) {
+  MRCNN_REQUIRE(feature_maps && feat_h && feat_w && boxes && pooled, "pyramid_roi_align: null pointer");
+  MRCNN_REQUIRE(batch > 0 && num_boxes > 0 && pool_size >= 1, "pyramid_roi_align: empty input");
+  MRCNN_REQUIRE(dtype == MRCNN_DTYPE_F32 || dtype == MRCNN_DTYPE_BF16, "pyramid_roi_align: dtype must be f32 or bf16");
+  const int vn = dtype == MRCNN_DTYPE_F32 ? 4 : 8;
+  MRCNN_REQUIRE(channels % vn == 0, "pyramid_roi_align: channels=%d must be a multiple of %d", channels, vn);
+  RoiParams p;
+  for (int i = 0; i < 4; ++i) {
+    MRCNN_REQUIRE(feature_maps[i] && feat_h[i] >= 1 && feat_w[i] >= 1, "pyramid_roi_align: bad level %d", i + 2);
+    p.feat[i] = feature_maps[i];
+    p.H[i] = feat_h[i];
+    p.W[i] = feat_w[i];
+  }
+  p.boxes = boxes;
+  p.N = num_boxes;
+  p.C = channels;
+  p.P = pool_size;
+  p.image_area = image_area;
+  p.out = pooled;
+  p.levels = levels;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MRCNN_DTYPE_F32)
+    roialign_kernel<float><<<batch * num_boxes, 256, 0, st>>>(p);
+  else
+    roialign_kernel<__nv_bfloat16><<<batch * num_boxes, 256, 0, st>>>(p);
+  MRCNN_CHECK_CUDA(cudaGetLastError());
+  return MRCNN_OK;
+}

@@ -1,0 +1,223 @@
+/*
+ * mrcnn_b200.h — C ABI of libmrcnn_b200.so: the B200 (sm_100a) implementation of the
+ * caesar-mrcnn Mask R-CNN *detect* hot path.
+ *
+ * The reference (SKA-INAF/caesar-mrcnn) is pure Python on TensorFlow 1.13 / Keras 2.2 and has no
+ * FFI of its own; its plug-in boundary for this path is the Python class surface
+ * mrcnn.model.MaskRCNN / mrcnn.config.Config.  This header is the boundary one
+ * level below it: one entry point per graph layer / host utility of the path, so that a
+ * maintainer can bind each of them from the reference's own call sites with ctypes
+ * (INTEGRATION.md shows the stubs), plus an engine object that runs the whole
+ * keras_model.predict() of mode='inference'.  Each declaration cites the reference code it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.  `stream` is a cudaStream_t passed as
+ *     void* (NULL = default stream).  Unless stated otherwise pointers are DEVICE pointers and
+ *     calls are asynchronous on `stream`.
+ *   - tensors are dense, C-order, NHWC; boxes are (y1, x1, y2, x2).
+ *   - every function returns 0 (MRCNN_STATUS_OK) or a negative status; mrcnn_last_error() gives the
+ *     message of the last failure on the calling thread.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MRCNN_B200_H_
+#define MRCNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRCNN_STATUS_OK 0
+#define MRCNN_STATUS_INVALID (-1)
+#define MRCNN_STATUS_CUDA (-2)
+#define MRCNN_STATUS_UNSUPPORTED (-3)
+#define MRCNN_STATUS_NOTFOUND (-4)
+
+#define MRCNN_DTYPE_F32 0
+#define MRCNN_DTYPE_BF16 1
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* mrcnn_last_error(void);
+int mrcnn_abi_version(void);
+/* number of kernels this library has launched in this process (bench.py: gpu_launches) */
+unsigned long long mrcnn_kernel_launch_count(void);
+
+/* ---- a1: FITS map -> uint8 RGB  (mrcnn/utils.py:1081-1208 read_fits after the FITS decode,
+ *      stretch_img :1166-1172 = astropy ZScaleInterval, normalize_img :1182-1188, gray2rgb :1190-1208)
+ * maps [n,H,W] float32 (NaN allowed).  params [n,3,4] float32 = per channel
+ * (nan_fill, vmin, range, zmax): pixel -> clip((x-vmin)/range,0,1)/zmax.  One CTA per image. */
+int mrcnn_zscale_params(const float* maps, int n_images, int height, int width,
+                        const float* contrasts3, float* params, void* stream);
+/* rgb [n,H,W,3] uint8 = round_half_even(255 * normalised stretch); minmax [n,2] int32 receives
+ * the per-image min / max byte (needed by the skimage clip of the following resize). */
+int mrcnn_stretch_to_rgb8(const float* maps, const float* params, int n_images, int height,
+                          int width, uint8_t* rgb, int32_t* minmax, void* stream);
+
+/* ---- a2: mold_inputs  (mrcnn/model.py:2519-2556; utils.resize_image mrcnn/utils.py:456-561 mode
+ *      "square"; utils.resize :957-978 = skimage<=0.15 bilinear warp, cval 0, clip; mold_image
+ *      mrcnn/model.py:2964-2969).  All n images share one original size (height,width).
+ * rgb [n,H,W,3] uint8, minmax [n,2] (or NULL = recompute) -> molded [n,S,S,3] float32:
+ * resize to (out_h,out_w) (skipped when equal to (H,W)), truncate to uint8, paste at (top,left)
+ * into a zero S x S frame, subtract mean_pixel (host pointer, 3 floats). */
+int mrcnn_resize_pad_mold(const uint8_t* rgb, const int32_t* minmax, int n_images, int height,
+                          int width, int out_h, int out_w, int square, int top, int left,
+                          const float* mean_pixel3, float* molded, void* stream);
+
+/* ---- a7: ProposalLayer  (mrcnn/model.py:329-406, apply_box_deltas_graph :287-308,
+ *      clip_boxes_graph :311-326, utils.batch_slice mrcnn/utils.py:872-906)
+ * rpn_class [B,A,2], rpn_bbox [B,A,4], anchors [A,4] (anchors_batched=0) or [B,A,4] -> rpn_rois
+ * [B,R,4] zero padded.  Optional taps: topk_idx [B,min(K,A)] (tf.nn.top_k order), keep_idx [B,R]
+ * (NMS picks as indices into that order, -1 padded), keep_count [B].  If topk_idx is NULL a
+ * workspace of mrcnn_proposal_workspace_bytes() must be given.  bbox_std_dev: HOST, 4 floats. */
+size_t mrcnn_proposal_workspace_bytes(int batch, int num_anchors, int pre_nms_limit);
+int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbox, const float* anchors,
+                         int anchors_batched, int batch, int num_anchors, int pre_nms_limit,
+                         int proposal_count, float nms_threshold, const float* bbox_std_dev,
+                         float* rpn_rois, int32_t* topk_idx, int32_t* keep_idx,
+                         int32_t* keep_count, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ---- a8: PyramidROIAlign  (mrcnn/model.py:428-534, log2_graph :413-423)
+ * feature_maps: HOST array of 4 device pointers P2..P5, each [B,feat_h[l],feat_w[l],C] of
+ * `dtype`; boxes [B,N,4] float32 normalised -> pooled [B,N,P,P,C] (same dtype); levels [B,N]
+ * int32 optional.  image_area = IMAGE_SHAPE[0]*IMAGE_SHAPE[1] as float32. */
+int mrcnn_roi_levels(const float* boxes, int num_boxes, float image_area, int32_t* levels,
+                     void* stream);
+int mrcnn_pyramid_roi_align(const void* const* feature_maps, const int* feat_h, const int* feat_w,
+                            int channels, int dtype, const float* boxes, int batch, int num_boxes,
+                            int pool_size, float image_area, void* pooled, int32_t* levels,
+                            void* stream);
+
+/* ---- a10: DetectionLayer  (mrcnn/model.py:868-909, refine_detections_graph :770-865,
+ *      norm_boxes_graph :3003-3017)
+ * rois [B,N,4], mrcnn_class [B,N,NC], mrcnn_bbox [B,N,NC,4], image_metas [B,meta_size] float32
+ * -> detections [B,D,6] = (y1,x1,y2,x2,class_id,score), zero padded.  min_confidence == 0
+ * skips the confidence filter (reference truthiness test).  bbox_std_dev: HOST, 4 floats. */
+int mrcnn_detection_layer(const float* rois, const float* mrcnn_class, const float* mrcnn_bbox,
+                          const float* image_metas, int meta_size, int batch, int num_rois,
+                          int num_classes, int max_instances, float min_confidence,
+                          float nms_threshold, const float* bbox_std_dev, float* detections,
+                          void* stream);
+
+/* ---- a12: unmold_detections  (mrcnn/model.py:2558-2621; utils.norm_boxes / denorm_boxes /
+ *      unmold_mask mrcnn/utils.py:923-954, 629-645)
+ * detections [B,D,6], mrcnn_mask [B,D,MH,MW,NC] float32; orig_hw (HOST int[2]) = original image
+ * size shared by the batch; image_hw (HOST int[2]) molded size; windows [B,4] int32 DEVICE
+ * (pixel window of each image in the molded frame).
+ * Outputs: rois [B,D,4] int32, class_ids [B,D] int32, scores [B,D] float32 (first counts[b] rows
+ * valid, zero-area rows already removed), counts [B] int32, masks [B,H0,W0,D] uint8 (0/1), the
+ * reference's [H,W,N] layout with N padded to D. */
+int mrcnn_unmold_detections(const float* detections, const float* mrcnn_mask, int batch,
+                            int max_instances, int mask_h, int mask_w, int num_classes,
+                            const int* orig_hw, const int* image_hw, const int32_t* windows,
+                            int32_t* rois, int32_t* class_ids, float* scores, int32_t* counts,
+                            uint8_t* masks, void* workspace, size_t workspace_bytes, void* stream);
+size_t mrcnn_unmold_workspace_bytes(int batch, int max_instances);
+
+/* ---- a4-a6, a9, a11: the dense contractions — one bf16 tcgen05/TMEM implicit-GEMM family
+ * (KL.Conv2D / TimeDistributed(Conv2D|Dense) / Conv2DTranspose call sites:
+ *  mrcnn/model.py:99-210 backbone, :2003-2026 FPN, :916-957 RPN, :986-1039 class head,
+ *  :1042-1091 mask head).
+ * y[n,oh,ow,:] = act( scale * sum_{r,s,c} x[n, oh*stride+r-pad, ow*stride+s-pad, c] * w[:,r,s,c]
+ *                     + shift + residual )
+ * x: [N,H,W,Cin] bf16, Cin % 64 == 0; w: [Cout_pad, KH*KW*Cin] bf16 (K-major, Cout padded to the
+ * N tile); scale/shift [Cout] float32 (folded BatchNorm + bias); residual optional bf16
+ * [N,OH,OW,Cout] (or [N,OH/2,OW/2,Cout] with residual_upsample2 = nearest 2x); out bf16 or f32.
+ * KHxKW in {1x1 (stride 1|2, pad 0), 3x3 (stride 1, pad 1)}; out_mode 1 = 2x2-stride-2 transposed
+ * convolution scatter (Cout_total = 4*Cout taps-major). */
+typedef struct mrcnn_conv_desc {
+  int n, h, w, cin;          /* input tensor */
+  int kh, kw, stride, pad;   /* filter geometry */
+  int cout;                  /* real output channels (per tap for out_mode 1) */
+  int relu;
+  int residual_upsample2;
+  int out_dtype;             /* MRCNN_DTYPE_* */
+  int out_mode;              /* 0 = NHWC, 1 = deconv 2x2 s2 scatter */
+  int out_ld;                /* output row pitch in elements (0 = cout) */
+} mrcnn_conv_desc;
+int mrcnn_conv2d_bf16(const mrcnn_conv_desc* desc, const void* x, const void* w, const float* scale,
+                      const float* shift, const void* residual, void* out, void* stream);
+/* reference implementation on CUDA cores (fp32 accumulate) used only by the tests to check the
+ * tcgen05 path on the device at full size */
+int mrcnn_conv2d_bf16_simt(const mrcnn_conv_desc* desc, const void* x, const void* w, const float* scale,
+                           const float* shift, const void* residual, void* out, void* stream);
+
+/* ---- engine: keras_model.predict([molded_images, image_metas, anchors]) of mode='inference'
+ *      (graph built at mrcnn/model.py:1935-2054, 2133-2159; outputs :2156-2158)
+ *      + MaskRCNN.load_weights by layer name (mrcnn/model.py:2197-2239). */
+typedef struct mrcnn_engine mrcnn_engine;
+
+typedef struct mrcnn_engine_config {
+  int batch_size;              /* config.BATCH_SIZE */
+  int image_size;              /* config.IMAGE_SHAPE[0] == [1], multiple of 64 */
+  int num_classes;             /* config.NUM_CLASSES */
+  int pre_nms_limit;           /* config.PRE_NMS_LIMIT */
+  int post_nms_rois;           /* config.POST_NMS_ROIS_INFERENCE */
+  int detection_max_instances; /* config.DETECTION_MAX_INSTANCES */
+  int pool_size;               /* config.POOL_SIZE */
+  int mask_pool_size;          /* config.MASK_POOL_SIZE */
+  int fc_layers_size;          /* config.FPN_CLASSIF_FC_LAYERS_SIZE */
+  int top_down_pyramid_size;   /* config.TOP_DOWN_PYRAMID_SIZE */
+  int anchors_per_location;    /* len(config.RPN_ANCHOR_RATIOS) */
+  float rpn_nms_threshold;     /* config.RPN_NMS_THRESHOLD */
+  float detection_min_confidence;
+  float detection_nms_threshold;
+  float rpn_bbox_std_dev[4];
+  float bbox_std_dev[4];
+  int backbone_strides[5];
+} mrcnn_engine_config;
+
+int mrcnn_engine_create(const mrcnn_engine_config* cfg, int device, mrcnn_engine** out);
+void mrcnn_engine_destroy(mrcnn_engine* e);
+/* number of weighted layers the graph expects, and their names / kinds / shapes */
+int mrcnn_engine_num_layers(const mrcnn_engine* e);
+int mrcnn_engine_layer_info(const mrcnn_engine* e, int index, const char** name, int* kind /*0 conv,1 bn,2 dense,3 deconv*/,
+                            int* num_weights, int* shape4 /* kernel shape, padded with 0 */);
+/* by-name weight load; weight_index follows Keras layer.weights order (kernel,bias | gamma,beta,
+ * mean,var); data: HOST float32 in the Keras layout; count = number of floats (checked). */
+int mrcnn_engine_set_weight(mrcnn_engine* e, const char* layer_name, int weight_index,
+                            const float* data, size_t count);
+/* fold BN, convert to bf16 GEMM layout, upload.  Fails listing the first missing layer unless
+ * allow_missing (missing layers keep zeros). */
+int mrcnn_engine_finalize(mrcnn_engine* e, int allow_missing);
+/* anchors [A,4] float32 normalised (HOST), as MaskRCNN.get_anchors returns them */
+int mrcnn_engine_set_anchors(mrcnn_engine* e, const float* anchors, int num_anchors);
+/* Runs the graph.  molded [B,S,S,3] float32 and image_metas [B,12+NC] float32: HOST pointers when
+ * inputs_on_host != 0 (copied H2D on the engine stream), else device pointers.  Blocks until the
+ * outputs are resident (device) unless async != 0. */
+int mrcnn_engine_predict(mrcnn_engine* e, const float* molded, const float* image_metas,
+                         int inputs_on_host, int async);
+/* device pointers of the graph outputs / taps, valid until the next predict:
+ * "detections" [B,D,6] f32, "mrcnn_class" [B,R,NC] f32, "mrcnn_bbox" [B,R,NC,4] f32, "mrcnn_mask"
+ * [B,D,28,28,NC] f32, "rpn_rois" [B,R,4] f32, "rpn_class" [B,A,2] f32, "rpn_bbox" [B,A,4] f32,
+ * "P2".."P6" bf16 NHWC, "C2".."C5" bf16, "pooled" / "pooled_mask" bf16, "topk_idx", "keep_idx",
+ * "keep_count", "roi_levels" int32.  Returns NOTFOUND for unknown names. */
+int mrcnn_engine_tensor(const mrcnn_engine* e, const char* name, void** device_ptr, size_t* bytes);
+/* copies a named tensor to a HOST buffer as float32 (bf16 tensors are widened) or int32 */
+int mrcnn_engine_read(const mrcnn_engine* e, const char* name, void* host_dst, size_t dst_bytes);
+/* run individual stages on engine-owned tensors from caller-provided DEVICE inputs ("reference-fed"
+ * microbenchmarks, BASELINE config #3): stage in {"proposal","roialign","class_head",
+ * "detection","roialign_mask","mask_head"}; consumes the current contents of the engine's input
+ * tensors for that stage (writable through mrcnn_engine_write). */
+int mrcnn_engine_run_stage(mrcnn_engine* e, const char* stage);
+int mrcnn_engine_write(mrcnn_engine* e, const char* name, const void* host_src, size_t src_bytes);
+/* whole detect(): predict + unmold, results to HOST buffers (pinned recommended).
+ * images are already molded (MaskRCNN.mold_inputs output); orig_hw/windows as for
+ * mrcnn_unmold_detections (windows: HOST int32 [B,4]).  masks [B,H0,W0,D] uint8. */
+int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded_host, const float* metas_host,
+                               const int* orig_hw, const int32_t* windows_host, int32_t* rois_host,
+                               int32_t* class_ids_host, float* scores_host, int32_t* counts_host,
+                               uint8_t* masks_host);
+void* mrcnn_engine_stream(const mrcnn_engine* e);
+/* per-stage device time of the last predict in milliseconds (CUDA events); names via index */
+int mrcnn_engine_stage_times(const mrcnn_engine* e, int max_stages, const char** names, float* ms);
+/* FLOPs (2*M*N*K over all GEMM launches) of one predict at the configured batch */
+double mrcnn_engine_flops(const mrcnn_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRCNN_B200_H_ */
