@@ -218,13 +218,26 @@ __global__ void __launch_bounds__(GEMM_THREADS) conv_gemm_kernel(const __grid_co
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;   // output row inside the tile
-    const int per_img = p.tw * p.th;
-    const int ni = row / per_img;
-    const int rem = row - ni * per_img;
-    const int hi = rem / p.tw;
-    const int wi = rem - hi * p.tw;
-    const int n = n0 + ni, h = h0 + hi, w = w0 + wi;
-    const bool row_ok = (row < per_img * p.nb) && (n < p.N) && (h < p.OH) && (w < p.OW);
+    int n, h, w;
+    bool row_ok;
+    if (p.flat) {
+      // 1x1 stride-1 layers tile the flattened pixel index; decode (n,h,w) from the real geometry
+      const long long m = (long long)m_tile * BLOCK_M + row;
+      row_ok = m < p.M;
+      const int hw = p.OH * p.OW;
+      n = (int)(m / hw);
+      const int rem = (int)(m - (long long)n * hw);
+      h = rem / p.OW;
+      w = rem - h * p.OW;
+    } else {
+      const int per_img = p.tw * p.th;
+      const int ni = row / per_img;
+      const int rem = row - ni * per_img;
+      const int hi = rem / p.tw;
+      const int wi = rem - hi * p.tw;
+      n = n0 + ni; h = h0 + hi; w = w0 + wi;
+      row_ok = (row < per_img * p.nb) && (n < p.N) && (h < p.OH) && (w < p.OW);
+    }
     const int col_base = n_tile * BLOCK_N;
     size_t out_off;
     int ch_base = col_base;          // channel index used for scale/shift and the store column
@@ -474,30 +487,34 @@ int conv_plan_create(const mrcnn_conv_desc* d, const void* x, const void* w, con
   cuuint64_t dims[4], strides[3];
   cuuint32_t box[4];
   // 1x1 stride 1 == plain [M, Cin] GEMM (rows need no (n,h,w) decode unless the residual is upsampled)
-  const bool flat = (d->kh == 1 && d->stride == 1 && !d->residual_upsample2);
+  const bool flat = (d->kh == 1 && d->stride == 1);
+  p.flat = flat ? 1 : 0;
+  p.OW = OW; p.OH = OH; p.N = d->n;
+  p.M = (long long)d->n * OH * OW;
+  int ext_w, ext_h, ext_n;   // extents the M tiles cover
   if (flat) {
-    const unsigned long long M = (unsigned long long)d->n * d->h * d->w;
+    const unsigned long long M = (unsigned long long)p.M;
     dims[0] = d->cin; dims[1] = M; dims[2] = 1; dims[3] = 1;
     strides[0] = (cuuint64_t)d->cin * 2; strides[1] = strides[0] * M; strides[2] = strides[1];
     p.tw = 128; p.th = 1; p.nb = 1;
-    p.OW = (int)M; p.OH = 1; p.N = 1;
     MRCNN_REQUIRE(M < (1ull << 31), "conv2d: M too large");
+    ext_w = (int)M; ext_h = 1; ext_n = 1;
   } else {
     dims[0] = d->cin; dims[1] = OW; dims[2] = OH; dims[3] = d->n;
     if (d->kh == 3) { dims[1] = d->w; dims[2] = d->h; }
     strides[0] = (cuuint64_t)d->cin * 2 * d->stride;
     strides[1] = (cuuint64_t)d->cin * 2 * d->w * d->stride;
     strides[2] = (cuuint64_t)d->cin * 2 * d->w * d->h;
-    p.OW = OW; p.OH = OH; p.N = d->n;
     p.tw = OW < 128 ? OW : 128;
     p.th = 128 / p.tw; if (p.th > OH) p.th = OH;
     p.nb = (p.th == OH) ? 128 / (p.tw * p.th) : 1;
     if (p.nb < 1) p.nb = 1;
     if (p.nb > d->n) p.nb = d->n;
+    ext_w = OW; ext_h = OH; ext_n = d->n;
   }
-  p.tiles_w = ceil_div(p.OW, p.tw);
-  p.tiles_h = ceil_div(p.OH, p.th);
-  p.tiles_nb = ceil_div(p.N, p.nb);
+  p.tiles_w = ceil_div(ext_w, p.tw);
+  p.tiles_h = ceil_div(ext_h, p.th);
+  p.tiles_nb = ceil_div(ext_n, p.nb);
   box[0] = 64; box[1] = p.tw; box[2] = p.th; box[3] = p.nb;
   rc = encode_map(&plan->tmap_a, x, 4, dims, strides, box);
   if (rc) return rc;

@@ -1,0 +1,875 @@
+// mrcnn_engine — keras_model.predict([molded_images, image_metas, anchors]) of mode='inference'
+// (graph built at mrcnn/model.py:1935-2054, 2133-2159) as a static plan of kernel launches on one
+// CUDA stream, plus by-name weight loading (MaskRCNN.load_weights, mrcnn/model.py:2197-2239) and
+// unmold (mrcnn/model.py:2558-2621).  Layer names / kernel layouts follow SURVEY.md Appendix B.
+//
+// HBM layout: activations are NHWC bf16, one allocation per tensor (a 64-image batch at S=256
+// needs ~12 GB of the 180 GB); weights are bf16 [Cout, KH*KW*Cin] (K-major GEMM-B operands) with
+// the frozen BatchNorm folded into per-channel fp32 (scale, shift) applied in the GEMM epilogue.
+#include <math.h>
+#include <string.h>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+#include "conv_gemm.cuh"
+#include "elementwise.cuh"
+#include "mrcnn_b200.h"
+
+int launch_pyramid_roi_align(const void* const* feature_maps, const int* feat_h, const int* feat_w, int channels,
+                             int dtype, const float* boxes, int box_stride, int batch, int num_boxes, int pool_size,
+                             float image_area, void* pooled, int32_t* levels, cudaStream_t st);
+
+namespace {
+
+enum { KIND_CONV = 0, KIND_BN = 1, KIND_DENSE = 2, KIND_DECONV = 3 };
+enum { DT_F32 = 0, DT_BF16 = 1, DT_I32 = 2, DT_U8 = 3 };
+
+struct LayerSpec {
+  std::string name;
+  int kind;
+  int shape[4];
+  int nweights;
+  std::vector<std::vector<float>> host;  // per weight_index
+  std::vector<bool> set;
+  size_t count(int wi) const {
+    if (kind == KIND_BN) return (size_t)shape[0];
+    if (wi == 0) {
+      size_t c = 1;
+      for (int i = 0; i < 4; ++i) if (shape[i] > 0) c *= (size_t)shape[i];
+      return c;
+    }
+    // bias length
+    if (kind == KIND_DENSE) return (size_t)shape[1];
+    if (kind == KIND_DECONV) return (size_t)shape[2];
+    return (size_t)shape[3];
+  }
+};
+
+struct Tensor {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  int dtype = DT_F32;
+  size_t elems = 0;
+};
+
+struct GemmW {   // device-side parameters of one GEMM layer
+  __nv_bfloat16* w = nullptr;
+  float* scale = nullptr;
+  float* shift = nullptr;
+  int cout = 0, K = 0;
+};
+
+struct Step {
+  std::string stage;
+  std::function<int(cudaStream_t)> run;
+};
+
+uint16_t f2bf(float f) {  // round to nearest even
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+}  // namespace
+
+struct mrcnn_engine {
+  mrcnn_engine_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<LayerSpec> layers;
+  std::map<std::string, int> layer_index;
+  std::map<std::string, Tensor> tensors;
+  std::map<std::string, GemmW> gemm;
+  std::vector<void*> allocs;
+  std::vector<Step> steps;
+  std::vector<ConvPlan*> plans;
+  bool finalized = false;
+  int num_anchors = 0;
+  int feat[5] = {0, 0, 0, 0, 0};
+  double flops = 0;
+  // timing
+  std::vector<std::string> stage_names;
+  std::vector<cudaEvent_t> stage_events;  // stage_names.size() + 1
+  // unmold scratch
+  void* unmold_ws = nullptr;
+  size_t unmold_ws_bytes = 0;
+  size_t mask_out_bytes = 0;
+  uint8_t* d_masks = nullptr;
+  int32_t* d_windows = nullptr;
+
+  int meta_size() const { return 12 + cfg.num_classes; }
+};
+
+namespace {
+
+void add_layer(mrcnn_engine* e, const std::string& name, int kind, int a, int b = 0, int c = 0, int d = 0) {
+  LayerSpec l;
+  l.name = name;
+  l.kind = kind;
+  l.shape[0] = a; l.shape[1] = b; l.shape[2] = c; l.shape[3] = d;
+  l.nweights = kind == KIND_BN ? 4 : 2;
+  l.host.resize(l.nweights);
+  l.set.assign(l.nweights, false);
+  e->layer_index[name] = (int)e->layers.size();
+  e->layers.push_back(l);
+}
+
+void build_layer_table(mrcnn_engine* e) {
+  const int NC = e->cfg.num_classes, FC = e->cfg.fc_layers_size, PY = e->cfg.top_down_pyramid_size;
+  const int apl = e->cfg.anchors_per_location;
+  add_layer(e, "conv1", KIND_CONV, 7, 7, 3, 64);
+  add_layer(e, "bn_conv1", KIND_BN, 64);
+  int cin = 64;
+  const int nblocks[4] = {3, 4, 23, 3};
+  const int f[4][3] = {{64, 64, 256}, {128, 128, 512}, {256, 256, 1024}, {512, 512, 2048}};
+  for (int s = 0; s < 4; ++s) {
+    for (int b = 0; b < nblocks[s]; ++b) {
+      const std::string blk(1, (char)('a' + b));
+      const std::string base = "res" + std::to_string(s + 2) + blk + "_branch";
+      const std::string bnb = "bn" + std::to_string(s + 2) + blk + "_branch";
+      add_layer(e, base + "2a", KIND_CONV, 1, 1, cin, f[s][0]);
+      add_layer(e, bnb + "2a", KIND_BN, f[s][0]);
+      add_layer(e, base + "2b", KIND_CONV, 3, 3, f[s][0], f[s][1]);
+      add_layer(e, bnb + "2b", KIND_BN, f[s][1]);
+      add_layer(e, base + "2c", KIND_CONV, 1, 1, f[s][1], f[s][2]);
+      add_layer(e, bnb + "2c", KIND_BN, f[s][2]);
+      if (b == 0) {
+        add_layer(e, base + "1", KIND_CONV, 1, 1, cin, f[s][2]);
+        add_layer(e, bnb + "1", KIND_BN, f[s][2]);
+      }
+      cin = f[s][2];
+    }
+  }
+  add_layer(e, "fpn_c5p5", KIND_CONV, 1, 1, 2048, PY);
+  add_layer(e, "fpn_c4p4", KIND_CONV, 1, 1, 1024, PY);
+  add_layer(e, "fpn_c3p3", KIND_CONV, 1, 1, 512, PY);
+  add_layer(e, "fpn_c2p2", KIND_CONV, 1, 1, 256, PY);
+  for (int l = 2; l <= 5; ++l) add_layer(e, "fpn_p" + std::to_string(l), KIND_CONV, 3, 3, PY, PY);
+  add_layer(e, "rpn_conv_shared", KIND_CONV, 3, 3, PY, 512);
+  add_layer(e, "rpn_class_raw", KIND_CONV, 1, 1, 512, 2 * apl);
+  add_layer(e, "rpn_bbox_pred", KIND_CONV, 1, 1, 512, 4 * apl);
+  add_layer(e, "mrcnn_class_conv1", KIND_CONV, e->cfg.pool_size, e->cfg.pool_size, PY, FC);
+  add_layer(e, "mrcnn_class_bn1", KIND_BN, FC);
+  add_layer(e, "mrcnn_class_conv2", KIND_CONV, 1, 1, FC, FC);
+  add_layer(e, "mrcnn_class_bn2", KIND_BN, FC);
+  add_layer(e, "mrcnn_class_logits", KIND_DENSE, FC, NC);
+  add_layer(e, "mrcnn_bbox_fc", KIND_DENSE, FC, 4 * NC);
+  for (int i = 1; i <= 4; ++i) {
+    add_layer(e, "mrcnn_mask_conv" + std::to_string(i), KIND_CONV, 3, 3, PY, PY);
+    add_layer(e, "mrcnn_mask_bn" + std::to_string(i), KIND_BN, PY);
+  }
+  add_layer(e, "mrcnn_mask_deconv", KIND_DECONV, 2, 2, PY, PY);
+  add_layer(e, "mrcnn_mask", KIND_CONV, 1, 1, PY, NC);
+}
+
+int dev_alloc(mrcnn_engine* e, size_t bytes, void** out) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  MRCNN_CHECK_CUDA(cudaMalloc(&p, bytes));
+  e->allocs.push_back(p);
+  *out = p;
+  return MRCNN_OK;
+}
+
+int new_tensor(mrcnn_engine* e, const std::string& name, int dtype, size_t elems, Tensor* out, bool zero = false) {
+  Tensor t;
+  t.dtype = dtype;
+  t.elems = elems;
+  const size_t es = dtype == DT_BF16 ? 2 : (dtype == DT_U8 ? 1 : 4);
+  t.bytes = elems * es;
+  int rc = dev_alloc(e, t.bytes, &t.ptr);
+  if (rc) return rc;
+  if (zero) MRCNN_CHECK_CUDA(cudaMemset(t.ptr, 0, t.bytes));
+  e->tensors[name] = t;
+  if (out) *out = t;
+  return MRCNN_OK;
+}
+
+const LayerSpec* find_layer(const mrcnn_engine* e, const std::string& name) {
+  auto it = e->layer_index.find(name);
+  return it == e->layer_index.end() ? nullptr : &e->layers[it->second];
+}
+
+// (scale, shift) with y = acc*scale + shift: folded Keras BatchNormalization (eps 1e-3) + conv bias
+void fold_affine(const LayerSpec* conv, const LayerSpec* bn, int cout, std::vector<float>* scale, std::vector<float>* shift) {
+  scale->assign(cout, 1.0f);
+  shift->assign(cout, 0.0f);
+  const std::vector<float>* bias = (conv && conv->set[1]) ? &conv->host[1] : nullptr;
+  for (int c = 0; c < cout; ++c) {
+    const double b = bias ? (double)(*bias)[c] : 0.0;
+    if (bn && bn->set[0] && bn->set[1] && bn->set[2] && bn->set[3]) {
+      const double s = (double)bn->host[0][c] / sqrt((double)bn->host[3][c] + 1e-3);
+      (*scale)[c] = (float)s;
+      (*shift)[c] = (float)((b - (double)bn->host[2][c]) * s + (double)bn->host[1][c]);
+    } else {
+      (*shift)[c] = (float)b;
+    }
+  }
+}
+
+int upload_gemm(mrcnn_engine* e, const std::string& key, const std::vector<uint16_t>& w, int cout, int K,
+                const std::vector<float>& scale, const std::vector<float>& shift) {
+  GemmW g;
+  g.cout = cout;
+  g.K = K;
+  int rc;
+  // rows padded to a multiple of 128 so a B tile never reads past the allocation even without OOB fill
+  const size_t rows = (size_t)((cout + 127) / 128) * 128;
+  if ((rc = dev_alloc(e, rows * K * 2, (void**)&g.w))) return rc;
+  MRCNN_CHECK_CUDA(cudaMemset(g.w, 0, rows * K * 2));
+  MRCNN_CHECK_CUDA(cudaMemcpy(g.w, w.data(), (size_t)cout * K * 2, cudaMemcpyHostToDevice));
+  const size_t cpad = rows;
+  if ((rc = dev_alloc(e, cpad * 4, (void**)&g.scale))) return rc;
+  if ((rc = dev_alloc(e, cpad * 4, (void**)&g.shift))) return rc;
+  MRCNN_CHECK_CUDA(cudaMemset(g.scale, 0, cpad * 4));
+  MRCNN_CHECK_CUDA(cudaMemset(g.shift, 0, cpad * 4));
+  MRCNN_CHECK_CUDA(cudaMemcpy(g.scale, scale.data(), (size_t)cout * 4, cudaMemcpyHostToDevice));
+  MRCNN_CHECK_CUDA(cudaMemcpy(g.shift, shift.data(), (size_t)cout * 4, cudaMemcpyHostToDevice));
+  e->gemm[key] = g;
+  return MRCNN_OK;
+}
+
+// Keras Conv2D kernel [kh,kw,cin,cout] -> [cout][(r*kw+s)*cin + c] (+ zero K padding to kpad)
+void conv_to_gemm(const std::vector<float>& k, int kh, int kw, int cin, int cout, int kpad, std::vector<uint16_t>* out,
+                  int row0 = 0, int rows_total = -1) {
+  const int K = kh * kw * cin;
+  if (rows_total < 0) rows_total = cout;
+  if (out->empty()) out->assign((size_t)rows_total * kpad, 0);
+  for (int t = 0; t < kh * kw; ++t)
+    for (int c = 0; c < cin; ++c) {
+      const float* src = k.empty() ? nullptr : &k[((size_t)t * cin + c) * cout];
+      for (int o = 0; o < cout; ++o)
+        (*out)[(size_t)(row0 + o) * kpad + (size_t)t * cin + c] = src ? f2bf(src[o]) : 0;
+    }
+  (void)K;
+}
+
+int build_weights(mrcnn_engine* e) {
+  int rc;
+  auto L = [&](const std::string& n) { return find_layer(e, n); };
+  auto kernel = [&](const std::string& n) -> const std::vector<float>& { return L(n)->host[0]; };
+  // plain conv (+ optional BN) layers
+  for (const LayerSpec& l : e->layers) {
+    if (l.kind != KIND_CONV) continue;
+    if (l.name == "rpn_class_raw" || l.name == "rpn_bbox_pred") continue;
+    const int kh = l.shape[0], kw = l.shape[1], cin = l.shape[2], cout = l.shape[3];
+    int kpad = kh * kw * cin;
+    if (l.name == "conv1") kpad = 192;
+    std::vector<uint16_t> w;
+    conv_to_gemm(l.host[0], kh, kw, cin, cout, kpad, &w);
+    // BN partner by naming convention
+    std::string bn;
+    if (l.name == "conv1") bn = "bn_conv1";
+    else if (l.name.rfind("res", 0) == 0) bn = "bn" + l.name.substr(3);
+    else if (l.name.rfind("mrcnn_class_conv", 0) == 0) bn = "mrcnn_class_bn" + l.name.substr(16);
+    else if (l.name.rfind("mrcnn_mask_conv", 0) == 0) bn = "mrcnn_mask_bn" + l.name.substr(15);
+    std::vector<float> sc, sh;
+    fold_affine(&l, bn.empty() ? nullptr : L(bn), cout, &sc, &sh);
+    if ((rc = upload_gemm(e, l.name, w, cout, kpad, sc, sh))) return rc;
+  }
+  {  // RPN head: [class_raw(2*apl) ; bbox_pred(4*apl)] x 512
+    const LayerSpec* a = L("rpn_class_raw");
+    const LayerSpec* b = L("rpn_bbox_pred");
+    const int ca = a->shape[3], cb = b->shape[3], cin = a->shape[2];
+    std::vector<uint16_t> w;
+    conv_to_gemm(a->host[0], 1, 1, cin, ca, cin, &w, 0, ca + cb);
+    conv_to_gemm(b->host[0], 1, 1, cin, cb, cin, &w, ca, ca + cb);
+    std::vector<float> sc(ca + cb, 1.0f), sh(ca + cb, 0.0f);
+    for (int i = 0; i < ca; ++i) sh[i] = a->set[1] ? a->host[1][i] : 0.f;
+    for (int i = 0; i < cb; ++i) sh[ca + i] = b->set[1] ? b->host[1][i] : 0.f;
+    if ((rc = upload_gemm(e, "rpn_head", w, ca + cb, cin, sc, sh))) return rc;
+  }
+  {  // class head: Dense [in,out] kernels -> [logits(NC) ; bbox(4NC)] x FC
+    const LayerSpec* a = L("mrcnn_class_logits");
+    const LayerSpec* b = L("mrcnn_bbox_fc");
+    const int in = a->shape[0], ca = a->shape[1], cb = b->shape[1];
+    std::vector<uint16_t> w((size_t)(ca + cb) * in, 0);
+    for (int i = 0; i < in; ++i) {
+      for (int o = 0; o < ca; ++o) w[(size_t)o * in + i] = a->host[0].empty() ? 0 : f2bf(a->host[0][(size_t)i * ca + o]);
+      for (int o = 0; o < cb; ++o) w[(size_t)(ca + o) * in + i] = b->host[0].empty() ? 0 : f2bf(b->host[0][(size_t)i * cb + o]);
+    }
+    std::vector<float> sc(ca + cb, 1.0f), sh(ca + cb, 0.0f);
+    for (int i = 0; i < ca; ++i) sh[i] = a->set[1] ? a->host[1][i] : 0.f;
+    for (int i = 0; i < cb; ++i) sh[ca + i] = b->set[1] ? b->host[1][i] : 0.f;
+    if ((rc = upload_gemm(e, "class_head", w, ca + cb, in, sc, sh))) return rc;
+  }
+  {  // Conv2DTranspose kernel [2,2,cout,cin] -> [(i*2+j)*cout + o][c]
+    const LayerSpec* d = L("mrcnn_mask_deconv");
+    const int cout = d->shape[2], cin = d->shape[3];
+    std::vector<uint16_t> w((size_t)4 * cout * cin, 0);
+    if (!d->host[0].empty())
+      for (int t = 0; t < 4; ++t)
+        for (int o = 0; o < cout; ++o)
+          for (int c = 0; c < cin; ++c) w[((size_t)t * cout + o) * cin + c] = f2bf(d->host[0][((size_t)t * cout + o) * cin + c]);
+    std::vector<float> sc((size_t)4 * cout, 1.0f), sh((size_t)4 * cout, 0.0f);
+    for (int t = 0; t < 4; ++t)
+      for (int i = 0; i < cout; ++i) sh[(size_t)t * cout + i] = d->set[1] ? d->host[1][i] : 0.f;
+    // the kernel indexes scale/shift per output channel (first `cout` entries; same for the 4 taps)
+    if ((rc = upload_gemm(e, "mrcnn_mask_deconv", w, 4 * cout, cin, sc, sh))) return rc;
+    e->gemm["mrcnn_mask_deconv"].cout = cout;
+  }
+  (void)kernel;
+  return MRCNN_OK;
+}
+
+struct Act {   // NHWC bf16 activation
+  __nv_bfloat16* p;
+  int n, h, w, c;
+};
+
+int add_conv(mrcnn_engine* e, const std::string& stage, const std::string& wname, Act in, int k, int stride, int relu,
+             const __nv_bfloat16* residual, int res_up2, const std::string& out_name, Act* out, int out_f32 = 0,
+             int out_ld = 0, int out_mode = 0, void** raw_out = nullptr) {
+  auto it = e->gemm.find(wname);
+  if (it == e->gemm.end()) {
+    mrcnn_set_error("engine: no GEMM weights for %s", wname.c_str());
+    return MRCNN_ERR_NOTFOUND;
+  }
+  const GemmW& g = it->second;
+  mrcnn_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.n = in.n; d.h = in.h; d.w = in.w; d.cin = in.c;
+  d.kh = k; d.kw = k; d.stride = stride; d.pad = k == 3 ? 1 : 0;
+  d.cout = g.cout;
+  d.relu = relu;
+  d.residual_upsample2 = res_up2;
+  d.out_dtype = out_f32 ? MRCNN_DTYPE_F32 : MRCNN_DTYPE_BF16;
+  d.out_mode = out_mode;
+  d.out_ld = out_ld;
+  const int oh = (in.h + 2 * d.pad - k) / stride + 1, ow = (in.w + 2 * d.pad - k) / stride + 1;
+  const int ld = out_ld ? out_ld : g.cout;
+  const int mult = out_mode == 1 ? 4 : 1;
+  Tensor t;
+  int rc = new_tensor(e, out_name, out_f32 ? DT_F32 : DT_BF16, (size_t)in.n * oh * ow * mult * ld, &t, /*zero=*/true);
+  if (rc) return rc;
+  ConvPlan* plan = new ConvPlan();
+  e->plans.push_back(plan);
+  rc = conv_plan_create(&d, in.p, g.w, g.scale, g.shift, residual, t.ptr, 0, plan);
+  if (rc) return rc;
+  e->flops += plan->flops;
+  e->steps.push_back({stage, [plan](cudaStream_t st) { return conv_plan_launch(plan, st); }});
+  if (out) {
+    out->p = static_cast<__nv_bfloat16*>(t.ptr);
+    out->n = in.n;
+    out->h = out_mode == 1 ? 2 * oh : oh;
+    out->w = out_mode == 1 ? 2 * ow : ow;
+    out->c = ld;
+  }
+  if (raw_out) *raw_out = t.ptr;
+  return MRCNN_OK;
+}
+
+#define RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+int build_graph(mrcnn_engine* e) {
+  const mrcnn_engine_config& c = e->cfg;
+  const int B = c.batch_size, S = c.image_size, NC = c.num_classes, R = c.post_nms_rois, D = c.detection_max_instances;
+  const int PY = c.top_down_pyramid_size, apl = c.anchors_per_location;
+  Tensor t_img, t_meta;
+  RC(new_tensor(e, "input_image", DT_F32, (size_t)B * S * S * 3, &t_img, true));
+  RC(new_tensor(e, "input_image_meta", DT_F32, (size_t)B * e->meta_size(), &t_meta, true));
+
+  // ---- stem --------------------------------------------------------------------------------
+  Tensor t_col;
+  RC(new_tensor(e, "conv1_im2col", DT_BF16, (size_t)B * (S / 2) * (S / 2) * 192, &t_col));
+  {
+    const float* img = static_cast<const float*>(t_img.ptr);
+    __nv_bfloat16* col = static_cast<__nv_bfloat16*>(t_col.ptr);
+    e->steps.push_back({"backbone", [=](cudaStream_t st) { return launch_stem_im2col(img, B, S, col, st); }});
+  }
+  Act x = {static_cast<__nv_bfloat16*>(t_col.ptr), 1, 1, B * (S / 2) * (S / 2), 192};
+  Act c1;
+  RC(add_conv(e, "backbone", "conv1", x, 1, 1, 1, nullptr, 0, "conv1_out", &c1));
+  c1.n = B; c1.h = S / 2; c1.w = S / 2; c1.c = 64;
+  Tensor t_pool;
+  RC(new_tensor(e, "C1", DT_BF16, (size_t)B * (S / 4) * (S / 4) * 64, &t_pool));
+  {
+    const __nv_bfloat16* src = c1.p;
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(t_pool.ptr);
+    e->steps.push_back({"backbone", [=](cudaStream_t st) { return launch_maxpool3x3s2(src, B, S / 2, S / 2, 64, dst, st); }});
+  }
+  x = {static_cast<__nv_bfloat16*>(t_pool.ptr), B, S / 4, S / 4, 64};
+
+  // ---- ResNet-101 stages 2..5 ----------------------------------------------------------------
+  const int nblocks[4] = {3, 4, 23, 3};
+  Act C[6];
+  for (int s = 0; s < 4; ++s) {
+    for (int b = 0; b < nblocks[s]; ++b) {
+      const std::string blk(1, (char)('a' + b));
+      const std::string base = "res" + std::to_string(s + 2) + blk + "_branch";
+      const int stride = (b == 0 && s > 0) ? 2 : 1;
+      Act y1, y2, sc, y3;
+      RC(add_conv(e, "backbone", base + "2a", x, 1, stride, 1, nullptr, 0, base + "2a_out", &y1));
+      RC(add_conv(e, "backbone", base + "2b", y1, 3, 1, 1, nullptr, 0, base + "2b_out", &y2));
+      if (b == 0) RC(add_conv(e, "backbone", base + "1", x, 1, stride, 0, nullptr, 0, base + "1_out", &sc));
+      else sc = x;
+      const std::string oname = (b == nblocks[s] - 1) ? ("C" + std::to_string(s + 2)) : ("res" + std::to_string(s + 2) + blk + "_out");
+      RC(add_conv(e, "backbone", base + "2c", y2, 1, 1, 1, sc.p, 0, oname, &y3));
+      x = y3;
+    }
+    C[s + 2] = x;
+  }
+
+  // ---- FPN ---------------------------------------------------------------------------------------
+  Act p5, p4, p3, p2, P[7];
+  RC(add_conv(e, "fpn", "fpn_c5p5", C[5], 1, 1, 0, nullptr, 0, "fpn_p5_pre", &p5));
+  RC(add_conv(e, "fpn", "fpn_c4p4", C[4], 1, 1, 0, p5.p, 1, "fpn_p4add", &p4));
+  RC(add_conv(e, "fpn", "fpn_c3p3", C[3], 1, 1, 0, p4.p, 1, "fpn_p3add", &p3));
+  RC(add_conv(e, "fpn", "fpn_c2p2", C[2], 1, 1, 0, p3.p, 1, "fpn_p2add", &p2));
+  RC(add_conv(e, "fpn", "fpn_p2", p2, 3, 1, 0, nullptr, 0, "P2", &P[2]));
+  RC(add_conv(e, "fpn", "fpn_p3", p3, 3, 1, 0, nullptr, 0, "P3", &P[3]));
+  RC(add_conv(e, "fpn", "fpn_p4", p4, 3, 1, 0, nullptr, 0, "P4", &P[4]));
+  RC(add_conv(e, "fpn", "fpn_p5", p5, 3, 1, 0, nullptr, 0, "P5", &P[5]));
+  {
+    Tensor t6;
+    const int h6 = (P[5].h + 1) / 2, w6 = (P[5].w + 1) / 2;
+    RC(new_tensor(e, "P6", DT_BF16, (size_t)B * h6 * w6 * PY, &t6));
+    const __nv_bfloat16* src = P[5].p;
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(t6.ptr);
+    const int h5 = P[5].h, w5 = P[5].w;
+    e->steps.push_back({"fpn", [=](cudaStream_t st) { return launch_subsample2(src, B, h5, w5, PY, dst, st); }});
+    P[6] = {dst, B, h6, w6, PY};
+  }
+  for (int l = 2; l <= 6; ++l) e->feat[l - 2] = P[l].h;
+
+  // ---- RPN ---------------------------------------------------------------------------------------
+  int A = 0;
+  for (int l = 2; l <= 6; ++l) A += P[l].h * P[l].w * apl;
+  e->num_anchors = A;
+  Tensor t_rc, t_rb, t_anch;
+  RC(new_tensor(e, "rpn_class", DT_F32, (size_t)B * A * 2, &t_rc, true));
+  RC(new_tensor(e, "rpn_bbox", DT_F32, (size_t)B * A * 4, &t_rb, true));
+  RC(new_tensor(e, "anchors", DT_F32, (size_t)A * 4, &t_anch, true));
+  int level_off = 0;
+  for (int l = 2; l <= 6; ++l) {
+    Act sh;
+    void* head = nullptr;
+    const std::string ls = std::to_string(l);
+    RC(add_conv(e, "rpn", "rpn_conv_shared", P[l], 3, 1, 1, nullptr, 0, "rpn_shared_p" + ls, &sh));
+    RC(add_conv(e, "rpn", "rpn_head", sh, 1, 1, 0, nullptr, 0, "rpn_head_p" + ls, nullptr, 1, 32, 0, &head));
+    const int hw = P[l].h * P[l].w;
+    const int off = level_off;
+    float* rc_ = static_cast<float*>(t_rc.ptr);
+    float* rb_ = static_cast<float*>(t_rb.ptr);
+    const float* hd = static_cast<const float*>(head);
+    e->steps.push_back({"rpn", [=](cudaStream_t st) { return launch_rpn_post(hd, 32, B, hw, apl, A, off, rc_, rb_, st); }});
+    level_off += hw * apl;
+  }
+
+  // ---- ProposalLayer -----------------------------------------------------------------------------
+  const int K = c.pre_nms_limit < A ? c.pre_nms_limit : A;
+  Tensor t_rois, t_topk, t_keep, t_kcnt;
+  RC(new_tensor(e, "rpn_rois", DT_F32, (size_t)B * R * 4, &t_rois, true));
+  RC(new_tensor(e, "topk_idx", DT_I32, (size_t)B * K, &t_topk, true));
+  RC(new_tensor(e, "keep_idx", DT_I32, (size_t)B * R, &t_keep, true));
+  RC(new_tensor(e, "keep_count", DT_I32, (size_t)B, &t_kcnt, true));
+  {
+    const float* rc_ = static_cast<const float*>(t_rc.ptr);
+    const float* rb_ = static_cast<const float*>(t_rb.ptr);
+    const float* an = static_cast<const float*>(t_anch.ptr);
+    float* rois = static_cast<float*>(t_rois.ptr);
+    int32_t* tk = static_cast<int32_t*>(t_topk.ptr);
+    int32_t* kp = static_cast<int32_t*>(t_keep.ptr);
+    int32_t* kc = static_cast<int32_t*>(t_kcnt.ptr);
+    const mrcnn_engine_config cc = c;
+    e->steps.push_back({"proposal", [=](cudaStream_t st) {
+      return mrcnn_proposal_layer(rc_, rb_, an, 0, B, A, cc.pre_nms_limit, R, cc.rpn_nms_threshold, cc.rpn_bbox_std_dev,
+                                  rois, tk, kp, kc, nullptr, 0, st);
+    }});
+  }
+
+  // ---- class head --------------------------------------------------------------------------------
+  const int PS = c.pool_size, MP = c.mask_pool_size;
+  Tensor t_pooled, t_lvl;
+  RC(new_tensor(e, "pooled", DT_BF16, (size_t)B * R * PS * PS * PY, &t_pooled));
+  RC(new_tensor(e, "roi_levels", DT_I32, (size_t)B * R, &t_lvl, true));
+  const float image_area = (float)S * (float)S;
+  struct FeatPack { const void* p[4]; int h[4]; int w[4]; };
+  FeatPack fp;
+  for (int l = 0; l < 4; ++l) { fp.p[l] = P[l + 2].p; fp.h[l] = P[l + 2].h; fp.w[l] = P[l + 2].w; }
+  {
+    const float* rois = static_cast<const float*>(t_rois.ptr);
+    void* pooled = t_pooled.ptr;
+    int32_t* lv = static_cast<int32_t*>(t_lvl.ptr);
+    e->steps.push_back({"roialign", [=](cudaStream_t st) {
+      return launch_pyramid_roi_align(fp.p, fp.h, fp.w, PY, MRCNN_DTYPE_BF16, rois, 4, B, R, PS, image_area, pooled, lv, st);
+    }});
+  }
+  Act pooled = {static_cast<__nv_bfloat16*>(t_pooled.ptr), 1, 1, B * R, PS * PS * PY};
+  Act fc1, fc2;
+  void* head = nullptr;
+  RC(add_conv(e, "class_head", "mrcnn_class_conv1", pooled, 1, 1, 1, nullptr, 0, "mrcnn_class_fc1", &fc1));
+  RC(add_conv(e, "class_head", "mrcnn_class_conv2", fc1, 1, 1, 1, nullptr, 0, "mrcnn_class_fc2", &fc2));
+  RC(add_conv(e, "class_head", "class_head", fc2, 1, 1, 0, nullptr, 0, "mrcnn_class_head_raw", nullptr, 1, 32, 0, &head));
+  MRCNN_REQUIRE(5 * NC <= 32, "engine: NUM_CLASSES=%d too large for the fused class/bbox head (max 6)", NC);
+  Tensor t_cls, t_bbox;
+  RC(new_tensor(e, "mrcnn_class", DT_F32, (size_t)B * R * NC, &t_cls, true));
+  RC(new_tensor(e, "mrcnn_bbox", DT_F32, (size_t)B * R * NC * 4, &t_bbox, true));
+  {
+    const float* hd = static_cast<const float*>(head);
+    float* pc = static_cast<float*>(t_cls.ptr);
+    float* pb = static_cast<float*>(t_bbox.ptr);
+    e->steps.push_back({"class_head", [=](cudaStream_t st) { return launch_class_post(hd, 32, B * R, NC, pc, pb, st); }});
+  }
+
+  // ---- DetectionLayer ----------------------------------------------------------------------------
+  Tensor t_det;
+  RC(new_tensor(e, "detections", DT_F32, (size_t)B * D * 6, &t_det, true));
+  {
+    const float* rois = static_cast<const float*>(t_rois.ptr);
+    const float* pc = static_cast<const float*>(t_cls.ptr);
+    const float* pb = static_cast<const float*>(t_bbox.ptr);
+    const float* meta = static_cast<const float*>(t_meta.ptr);
+    float* det = static_cast<float*>(t_det.ptr);
+    const mrcnn_engine_config cc = c;
+    const int ms = e->meta_size();
+    e->steps.push_back({"detection", [=](cudaStream_t st) {
+      return mrcnn_detection_layer(rois, pc, pb, meta, ms, B, R, NC, D, cc.detection_min_confidence,
+                                   cc.detection_nms_threshold, cc.bbox_std_dev, det, st);
+    }});
+  }
+
+  // ---- mask head ---------------------------------------------------------------------------------
+  Tensor t_pm;
+  RC(new_tensor(e, "pooled_mask", DT_BF16, (size_t)B * D * MP * MP * PY, &t_pm));
+  {
+    const float* det = static_cast<const float*>(t_det.ptr);
+    void* pm = t_pm.ptr;
+    e->steps.push_back({"roialign_mask", [=](cudaStream_t st) {
+      return launch_pyramid_roi_align(fp.p, fp.h, fp.w, PY, MRCNN_DTYPE_BF16, det, 6, B, D, MP, image_area, pm, nullptr, st);
+    }});
+  }
+  Act m = {static_cast<__nv_bfloat16*>(t_pm.ptr), B * D, MP, MP, PY};
+  for (int i = 1; i <= 4; ++i) {
+    Act o;
+    RC(add_conv(e, "mask_head", "mrcnn_mask_conv" + std::to_string(i), m, 3, 1, 1, nullptr, 0,
+                "mrcnn_mask_conv" + std::to_string(i) + "_out", &o));
+    m = o;
+  }
+  Act dc;
+  RC(add_conv(e, "mask_head", "mrcnn_mask_deconv", m, 1, 1, 1, nullptr, 0, "mrcnn_mask_deconv_out", &dc, 0, 0, 1));
+  void* mlog = nullptr;
+  RC(add_conv(e, "mask_head", "mrcnn_mask", dc, 1, 1, 0, nullptr, 0, "mrcnn_mask_logits", nullptr, 1, 8, 0, &mlog));
+  MRCNN_REQUIRE(NC <= 8, "engine: NUM_CLASSES=%d too large for the mask logits pitch (max 8)", NC);
+  Tensor t_mask;
+  RC(new_tensor(e, "mrcnn_mask", DT_F32, (size_t)B * D * 4 * MP * MP * NC, &t_mask, true));
+  {
+    const float* lg = static_cast<const float*>(mlog);
+    float* out = static_cast<float*>(t_mask.ptr);
+    const size_t M = (size_t)B * D * 4 * MP * MP;
+    e->steps.push_back({"mask_head", [=](cudaStream_t st) { return launch_mask_post(lg, 8, M, NC, out, st); }});
+  }
+
+  // ---- stage table for timing / run_stage ----------------------------------------------------------
+  for (const Step& s : e->steps)
+    if (e->stage_names.empty() || e->stage_names.back() != s.stage) e->stage_names.push_back(s.stage);
+  e->stage_events.resize(e->stage_names.size() + 1);
+  for (auto& ev : e->stage_events) MRCNN_CHECK_CUDA(cudaEventCreate(&ev));
+  return MRCNN_OK;
+}
+
+int run_steps(mrcnn_engine* e, const char* only_stage, bool timed) {
+  size_t si = 0;
+  std::string cur;
+  for (const Step& s : e->steps) {
+    if (only_stage && s.stage != only_stage) continue;
+    if (timed && s.stage != cur) {
+      while (si < e->stage_names.size() && e->stage_names[si] != s.stage) ++si;
+      MRCNN_CHECK_CUDA(cudaEventRecord(e->stage_events[si], e->stream));
+      cur = s.stage;
+    }
+    int rc = s.run(e->stream);
+    if (rc) return rc;
+  }
+  if (timed) MRCNN_CHECK_CUDA(cudaEventRecord(e->stage_events[e->stage_names.size()], e->stream));
+  return MRCNN_OK;
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------
+extern "C" int mrcnn_engine_create(const mrcnn_engine_config* cfg, int device, mrcnn_engine** out) {
+  MRCNN_REQUIRE(cfg && out, "engine_create: null pointer");
+  MRCNN_REQUIRE(cfg->batch_size >= 1, "engine_create: batch_size must be >= 1");
+  // mrcnn/model.py:1944-1948: image size must be divisible by 2^6
+  MRCNN_REQUIRE(cfg->image_size >= 64 && cfg->image_size % 64 == 0,
+                "Image size must be dividable by 2 at least 6 times to avoid fractions when downscaling and upscaling."
+                "For example, use 256, 320, 384, 448, 512, ... etc. (got %d)", cfg->image_size);
+  MRCNN_REQUIRE(cfg->num_classes >= 1 && cfg->num_classes <= 6, "engine_create: num_classes must be in [1,6]");
+  MRCNN_REQUIRE(cfg->top_down_pyramid_size % 64 == 0 && cfg->fc_layers_size % 64 == 0, "engine_create: pyramid / fc sizes must be multiples of 64");
+  MRCNN_REQUIRE(cfg->anchors_per_location >= 1 && 6 * cfg->anchors_per_location <= 32, "engine_create: anchors_per_location must be in [1,5]");
+  const int strides[5] = {4, 8, 16, 32, 64};
+  for (int i = 0; i < 5; ++i)
+    MRCNN_REQUIRE(cfg->backbone_strides[i] == strides[i], "engine_create: BACKBONE_STRIDES must be [4,8,16,32,64] (resnet101)");
+  int ndev = 0;
+  MRCNN_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+  MRCNN_REQUIRE(device >= 0 && device < ndev, "engine_create: device %d not available (%d devices)", device, ndev);
+  MRCNN_CHECK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MRCNN_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    mrcnn_set_error("engine_create: device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+    return MRCNN_ERR_UNSUPPORTED;
+  }
+  mrcnn_engine* e = new mrcnn_engine();
+  e->cfg = *cfg;
+  e->device = device;
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete e;
+    mrcnn_set_error("engine_create: cudaStreamCreate failed");
+    return MRCNN_ERR_CUDA;
+  }
+  build_layer_table(e);
+  *out = e;
+  return MRCNN_OK;
+}
+
+extern "C" void mrcnn_engine_destroy(mrcnn_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (void* p : e->allocs) cudaFree(p);
+  for (ConvPlan* p : e->plans) delete p;
+  for (auto ev : e->stage_events) cudaEventDestroy(ev);
+  if (e->unmold_ws) cudaFree(e->unmold_ws);
+  if (e->d_masks) cudaFree(e->d_masks);
+  if (e->d_windows) cudaFree(e->d_windows);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+extern "C" int mrcnn_engine_num_layers(const mrcnn_engine* e) { return e ? (int)e->layers.size() : 0; }
+
+extern "C" int mrcnn_engine_layer_info(const mrcnn_engine* e, int index, const char** name, int* kind, int* num_weights, int* shape4) {
+  MRCNN_REQUIRE(e && index >= 0 && index < (int)e->layers.size(), "layer_info: bad index");
+  const LayerSpec& l = e->layers[index];
+  if (name) *name = l.name.c_str();
+  if (kind) *kind = l.kind;
+  if (num_weights) *num_weights = l.nweights;
+  if (shape4) for (int i = 0; i < 4; ++i) shape4[i] = l.shape[i];
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_set_weight(mrcnn_engine* e, const char* layer_name, int weight_index, const float* data, size_t count) {
+  MRCNN_REQUIRE(e && layer_name && data, "set_weight: null pointer");
+  MRCNN_REQUIRE(!e->finalized, "set_weight: engine already finalized");
+  auto it = e->layer_index.find(layer_name);
+  if (it == e->layer_index.end()) {
+    mrcnn_set_error("set_weight: no layer named '%s' in the inference graph", layer_name);
+    return MRCNN_ERR_NOTFOUND;
+  }
+  LayerSpec& l = e->layers[it->second];
+  MRCNN_REQUIRE(weight_index >= 0 && weight_index < l.nweights, "set_weight: layer %s has %d weights", layer_name, l.nweights);
+  const size_t expect = l.count(weight_index);
+  MRCNN_REQUIRE(count == expect, "set_weight: layer %s weight %d has %zu elements, expected %zu (shape mismatch)", layer_name,
+                weight_index, count, expect);
+  l.host[weight_index].assign(data, data + count);
+  l.set[weight_index] = true;
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_finalize(mrcnn_engine* e, int allow_missing) {
+  MRCNN_REQUIRE(e, "finalize: null engine");
+  MRCNN_REQUIRE(!e->finalized, "finalize: already finalized");
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  for (LayerSpec& l : e->layers)
+    for (int wi = 0; wi < l.nweights; ++wi)
+      if (!l.set[wi]) {
+        if (!allow_missing) {
+          mrcnn_set_error("finalize: layer '%s' weight %d was never loaded", l.name.c_str(), wi);
+          return MRCNN_ERR_NOTFOUND;
+        }
+        if (l.kind == KIND_BN) {   // identity BN: gamma 1, beta 0, mean 0, var 1
+          l.host[wi].assign(l.count(wi), (wi == 0 || wi == 3) ? 1.0f : 0.0f);
+          l.set[wi] = true;
+        } else {
+          l.host[wi].assign(l.count(wi), 0.0f);
+          l.set[wi] = true;
+        }
+      }
+  int rc = build_weights(e);
+  if (rc) return rc;
+  rc = build_graph(e);
+  if (rc) return rc;
+  for (LayerSpec& l : e->layers) { l.host.clear(); l.host.shrink_to_fit(); l.host.resize(l.nweights); }
+  MRCNN_CHECK_CUDA(cudaDeviceSynchronize());
+  e->finalized = true;
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_set_anchors(mrcnn_engine* e, const float* anchors, int num_anchors) {
+  MRCNN_REQUIRE(e && anchors && e->finalized, "set_anchors: engine not finalized / null pointer");
+  MRCNN_REQUIRE(num_anchors == e->num_anchors, "set_anchors: got %d anchors, the graph has %d", num_anchors, e->num_anchors);
+  MRCNN_CHECK_CUDA(cudaMemcpy(e->tensors["anchors"].ptr, anchors, (size_t)num_anchors * 16, cudaMemcpyHostToDevice));
+  return MRCNN_OK;
+}
+
+static int predict_internal(mrcnn_engine* e, const float* molded, cudaMemcpyKind molded_kind, const float* image_metas,
+                            cudaMemcpyKind metas_kind) {
+  MRCNN_REQUIRE(e && e->finalized, "predict: engine not finalized (load weights first)");
+  MRCNN_REQUIRE(molded && image_metas, "predict: null input");
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  const Tensor& ti = e->tensors["input_image"];
+  const Tensor& tm = e->tensors["input_image_meta"];
+  if (molded != ti.ptr) MRCNN_CHECK_CUDA(cudaMemcpyAsync(ti.ptr, molded, ti.bytes, molded_kind, e->stream));
+  if (image_metas != tm.ptr) MRCNN_CHECK_CUDA(cudaMemcpyAsync(tm.ptr, image_metas, tm.bytes, metas_kind, e->stream));
+  return run_steps(e, nullptr, true);
+}
+
+extern "C" int mrcnn_engine_predict(mrcnn_engine* e, const float* molded, const float* image_metas, int inputs_on_host, int async) {
+  const cudaMemcpyKind kind = inputs_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  int rc = predict_internal(e, molded, kind, image_metas, kind);
+  if (rc) return rc;
+  if (!async) MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_tensor(const mrcnn_engine* e, const char* name, void** device_ptr, size_t* bytes) {
+  MRCNN_REQUIRE(e && name, "engine_tensor: null pointer");
+  auto it = e->tensors.find(name);
+  if (it == e->tensors.end()) {
+    mrcnn_set_error("engine_tensor: unknown tensor '%s'", name);
+    return MRCNN_ERR_NOTFOUND;
+  }
+  if (device_ptr) *device_ptr = it->second.ptr;
+  if (bytes) *bytes = it->second.bytes;
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_read(const mrcnn_engine* e, const char* name, void* host_dst, size_t dst_bytes) {
+  MRCNN_REQUIRE(e && name && host_dst, "engine_read: null pointer");
+  auto it = e->tensors.find(name);
+  if (it == e->tensors.end()) {
+    mrcnn_set_error("engine_read: unknown tensor '%s'", name);
+    return MRCNN_ERR_NOTFOUND;
+  }
+  const Tensor& t = it->second;
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+  if (t.dtype == DT_BF16) {
+    MRCNN_REQUIRE(dst_bytes >= t.elems * 4, "engine_read: %s needs %zu bytes (float32)", name, t.elems * 4);
+    std::vector<uint16_t> tmp(t.elems);
+    MRCNN_CHECK_CUDA(cudaMemcpy(tmp.data(), t.ptr, t.bytes, cudaMemcpyDeviceToHost));
+    uint32_t* dst = static_cast<uint32_t*>(host_dst);
+    for (size_t i = 0; i < t.elems; ++i) dst[i] = (uint32_t)tmp[i] << 16;
+  } else {
+    MRCNN_REQUIRE(dst_bytes >= t.bytes, "engine_read: %s needs %zu bytes", name, t.bytes);
+    MRCNN_CHECK_CUDA(cudaMemcpy(host_dst, t.ptr, t.bytes, cudaMemcpyDeviceToHost));
+  }
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_write(mrcnn_engine* e, const char* name, const void* host_src, size_t src_bytes) {
+  MRCNN_REQUIRE(e && name && host_src, "engine_write: null pointer");
+  auto it = e->tensors.find(name);
+  if (it == e->tensors.end()) {
+    mrcnn_set_error("engine_write: unknown tensor '%s'", name);
+    return MRCNN_ERR_NOTFOUND;
+  }
+  const Tensor& t = it->second;
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+  if (t.dtype == DT_BF16) {   // source is float32, narrowed here
+    MRCNN_REQUIRE(src_bytes == t.elems * 4, "engine_write: %s expects %zu float32 values", name, t.elems);
+    const float* src = static_cast<const float*>(host_src);
+    std::vector<uint16_t> tmp(t.elems);
+    for (size_t i = 0; i < t.elems; ++i) tmp[i] = f2bf(src[i]);
+    MRCNN_CHECK_CUDA(cudaMemcpy(t.ptr, tmp.data(), t.bytes, cudaMemcpyHostToDevice));
+  } else {
+    MRCNN_REQUIRE(src_bytes == t.bytes, "engine_write: %s expects %zu bytes", name, t.bytes);
+    MRCNN_CHECK_CUDA(cudaMemcpy(t.ptr, host_src, t.bytes, cudaMemcpyHostToDevice));
+  }
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_run_stage(mrcnn_engine* e, const char* stage) {
+  MRCNN_REQUIRE(e && e->finalized && stage, "run_stage: engine not finalized / null stage");
+  bool known = false;
+  for (const std::string& s : e->stage_names) known |= (s == stage);
+  if (!known) {
+    mrcnn_set_error("run_stage: unknown stage '%s'", stage);
+    return MRCNN_ERR_NOTFOUND;
+  }
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  int rc = run_steps(e, stage, false);
+  if (rc) return rc;
+  MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+  return MRCNN_OK;
+}
+
+extern "C" void* mrcnn_engine_stream(const mrcnn_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+extern "C" int mrcnn_engine_stage_times(const mrcnn_engine* e, int max_stages, const char** names, float* ms) {
+  MRCNN_REQUIRE(e && e->finalized, "stage_times: engine not finalized");
+  const int n = (int)e->stage_names.size();
+  for (int i = 0; i < n && i < max_stages; ++i) {
+    if (names) names[i] = e->stage_names[i].c_str();
+    if (ms) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, e->stage_events[i], e->stage_events[i + 1]) != cudaSuccess) t = -1.f;
+      ms[i] = t;
+    }
+  }
+  return n;
+}
+
+extern "C" double mrcnn_engine_flops(const mrcnn_engine* e) { return e ? e->flops : 0.0; }
+
+extern "C" int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, int molded_on_host,
+                                          const float* metas_host, const int* orig_hw, const int32_t* windows_host, int32_t* rois_host,
+                                          int32_t* class_ids_host, float* scores_host, int32_t* counts_host,
+                                          uint8_t* masks_host) {
+  MRCNN_REQUIRE(e && e->finalized, "detect_molded: engine not finalized");
+  MRCNN_REQUIRE(molded && metas_host && orig_hw && windows_host && rois_host && class_ids_host && scores_host &&
+                    counts_host && masks_host, "detect_molded: null pointer");
+  const mrcnn_engine_config& c = e->cfg;
+  const int B = c.batch_size, D = c.detection_max_instances;
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  int rc = predict_internal(e, molded, molded_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, metas_host,
+                           cudaMemcpyHostToDevice);
+  if (rc) return rc;
+  // scratch (grown on demand)
+  const size_t ws = mrcnn_unmold_workspace_bytes(B, D);
+  if (e->unmold_ws_bytes < ws) {
+    if (e->unmold_ws) cudaFree(e->unmold_ws);
+    MRCNN_CHECK_CUDA(cudaMalloc(&e->unmold_ws, ws));
+    e->unmold_ws_bytes = ws;
+  }
+  const size_t mbytes = (size_t)B * orig_hw[0] * orig_hw[1] * D;
+  if (e->mask_out_bytes < mbytes) {
+    if (e->d_masks) cudaFree(e->d_masks);
+    MRCNN_CHECK_CUDA(cudaMalloc((void**)&e->d_masks, mbytes));
+    e->mask_out_bytes = mbytes;
+  }
+  if (!e->d_windows) MRCNN_CHECK_CUDA(cudaMalloc((void**)&e->d_windows, (size_t)B * 16));
+  if (e->tensors.find("unmold_rois") == e->tensors.end()) {
+    RC(new_tensor(e, "unmold_rois", DT_I32, (size_t)B * D * 4, nullptr, true));
+    RC(new_tensor(e, "unmold_class_ids", DT_I32, (size_t)B * D, nullptr, true));
+    RC(new_tensor(e, "unmold_scores", DT_F32, (size_t)B * D, nullptr, true));
+    RC(new_tensor(e, "unmold_counts", DT_I32, (size_t)B, nullptr, true));
+  }
+  MRCNN_CHECK_CUDA(cudaMemcpyAsync(e->d_windows, windows_host, (size_t)B * 16, cudaMemcpyHostToDevice, e->stream));
+  const int image_hw[2] = {c.image_size, c.image_size};
+  Tensor& tr = e->tensors["unmold_rois"];
+  Tensor& tc = e->tensors["unmold_class_ids"];
+  Tensor& ts = e->tensors["unmold_scores"];
+  Tensor& tn = e->tensors["unmold_counts"];
+  rc = mrcnn_unmold_detections(static_cast<const float*>(e->tensors["detections"].ptr),
+                               static_cast<const float*>(e->tensors["mrcnn_mask"].ptr), B, D, 2 * c.mask_pool_size,
+                               2 * c.mask_pool_size, c.num_classes, orig_hw, image_hw, e->d_windows,
+                               static_cast<int32_t*>(tr.ptr), static_cast<int32_t*>(tc.ptr), static_cast<float*>(ts.ptr),
+                               static_cast<int32_t*>(tn.ptr), e->d_masks, e->unmold_ws, e->unmold_ws_bytes, e->stream);
+  if (rc) return rc;
+  MRCNN_CHECK_CUDA(cudaMemcpyAsync(rois_host, tr.ptr, tr.bytes, cudaMemcpyDeviceToHost, e->stream));
+  MRCNN_CHECK_CUDA(cudaMemcpyAsync(class_ids_host, tc.ptr, tc.bytes, cudaMemcpyDeviceToHost, e->stream));
+  MRCNN_CHECK_CUDA(cudaMemcpyAsync(scores_host, ts.ptr, ts.bytes, cudaMemcpyDeviceToHost, e->stream));
+  MRCNN_CHECK_CUDA(cudaMemcpyAsync(counts_host, tn.ptr, tn.bytes, cudaMemcpyDeviceToHost, e->stream));
+  MRCNN_CHECK_CUDA(cudaMemcpyAsync(masks_host, e->d_masks, mbytes, cudaMemcpyDeviceToHost, e->stream));
+  MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+  return MRCNN_OK;
+}

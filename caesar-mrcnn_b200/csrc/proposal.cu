@@ -9,6 +9,8 @@
 #include "box_ops.cuh"
 #include "mrcnn_b200.h"
 
+void mrcnn_count_launch(unsigned long long n);
+
 namespace {
 
 constexpr int PROP_THREADS = 1024;
@@ -254,12 +256,9 @@ extern "C" int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbo
   }
   size_t smem = prop_smem_bytes(K, proposal_count, &p.r0_bytes);
   MRCNN_REQUIRE(smem <= 227 * 1024, "proposal_layer: shared memory %zu exceeds 227 KB", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MRCNN_CHECK_CUDA(cudaFuncSetAttribute(proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  MRCNN_CHECK_CUDA(cudaFuncSetAttribute(proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   proposal_kernel<<<batch, PROP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
   MRCNN_CHECK_CUDA(cudaGetLastError());
+  mrcnn_count_launch(1);
   return MRCNN_OK;
 }

@@ -8,12 +8,15 @@
 #include "box_ops.cuh"
 #include "mrcnn_b200.h"
 
+void mrcnn_count_launch(unsigned long long n);
+
 namespace {
 
 struct RoiParams {
   const void* feat[4];  // P2..P5, [B,H_l,W_l,C]
   int H[4], W[4];
-  const float* boxes;   // [B,N,4] normalised (y1,x1,y2,x2)
+  const float* boxes;   // [B,N,box_stride] normalised (y1,x1,y2,x2,...)
+  int box_stride;
   int N, C, P;
   float image_area;
   void* out;            // [B,N,P,P,C]
@@ -75,8 +78,8 @@ __global__ void __launch_bounds__(256) roialign_kernel(RoiParams p) {
   constexpr int VN = Vec<T>::N;
   const int roi = blockIdx.x;  // b*N + n
   const int b = roi / p.N;
-  const float4 bx = *reinterpret_cast<const float4*>(p.boxes + (size_t)roi * 4);
-  const float y1 = bx.x, x1 = bx.y, y2 = bx.z, x2 = bx.w;
+  const float* bp = p.boxes + (size_t)roi * p.box_stride;
+  const float y1 = bp[0], x1 = bp[1], y2 = bp[2], x2 = bp[3];
   const int lvl = roi_level(y1, x1, y2, x2, p.image_area);
   if (threadIdx.x == 0 && p.levels) p.levels[roi] = lvl;
   const int li = lvl - 2;
@@ -140,10 +143,9 @@ extern "C" int mrcnn_roi_levels(const float* boxes, int num_boxes, float image_a
   return MRCNN_OK;
 }
 
-extern "C" int mrcnn_pyramid_roi_align(const void* const* feature_maps, const int* feat_h, const int* feat_w,
-                                       int channels, int dtype, const float* boxes, int batch, int num_boxes,
-                                       int pool_size, float image_area, void* pooled, int32_t* levels,
-                                       void* stream) {
+int launch_pyramid_roi_align(const void* const* feature_maps, const int* feat_h, const int* feat_w, int channels,
+                             int dtype, const float* boxes, int box_stride, int batch, int num_boxes, int pool_size,
+                             float image_area, void* pooled, int32_t* levels, cudaStream_t st) {
   MRCNN_REQUIRE(feature_maps && feat_h && feat_w && boxes && pooled, "pyramid_roi_align: null pointer");
   MRCNN_REQUIRE(batch > 0 && num_boxes > 0 && pool_size >= 1, "pyramid_roi_align: empty input");
   MRCNN_REQUIRE(dtype == MRCNN_DTYPE_F32 || dtype == MRCNN_DTYPE_BF16, "pyramid_roi_align: dtype must be f32 or bf16");
@@ -157,17 +159,26 @@ extern "C" int mrcnn_pyramid_roi_align(const void* const* feature_maps, const in
     p.W[i] = feat_w[i];
   }
   p.boxes = boxes;
+  p.box_stride = box_stride;
   p.N = num_boxes;
   p.C = channels;
   p.P = pool_size;
   p.image_area = image_area;
   p.out = pooled;
   p.levels = levels;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == MRCNN_DTYPE_F32)
     roialign_kernel<float><<<batch * num_boxes, 256, 0, st>>>(p);
   else
     roialign_kernel<__nv_bfloat16><<<batch * num_boxes, 256, 0, st>>>(p);
   MRCNN_CHECK_CUDA(cudaGetLastError());
+  mrcnn_count_launch(1);
   return MRCNN_OK;
+}
+
+extern "C" int mrcnn_pyramid_roi_align(const void* const* feature_maps, const int* feat_h, const int* feat_w,
+                                       int channels, int dtype, const float* boxes, int batch, int num_boxes,
+                                       int pool_size, float image_area, void* pooled, int32_t* levels,
+                                       void* stream) {
+  return launch_pyramid_roi_align(feature_maps, feat_h, feat_w, channels, dtype, boxes, 4, batch, num_boxes, pool_size,
+                                  image_area, pooled, levels, static_cast<cudaStream_t>(stream));
 }

@@ -79,7 +79,7 @@ SIGNATURES = {
     "mrcnn_engine_read": (c_int, [c_void_p, ctypes.c_char_p, c_void_p, c_size_t]),
     "mrcnn_engine_run_stage": (c_int, [c_void_p, ctypes.c_char_p]),
     "mrcnn_engine_write": (c_int, [c_void_p, ctypes.c_char_p, c_void_p, c_size_t]),
-    "mrcnn_engine_detect_molded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "mrcnn_engine_detect_molded": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p]),
     "mrcnn_engine_stream": (c_void_p, [c_void_p]),
     "mrcnn_engine_stage_times": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_float)]),

@@ -1,0 +1,408 @@
+"""mrcnn.model — B200-native `MaskRCNN` with the reference's inference API surface
+(mrcnn/model.py:1911-2884): MaskRCNN(mode, config, model_dir), load_weights(filepath, by_name,
+exclude), detect(images, verbose), detect_molded, mold_inputs, unmold_detections, get_anchors,
+print_model, plus the module functions compose_image_meta / parse_image_meta / mold_image /
+unmold_image / compute_backbone_shapes.
+
+`keras_model.predict` is replaced by the C++/CUDA engine of libmrcnn_b200.so (csrc/engine.cu): one
+static plan of sm_100a kernels per (BATCH_SIZE, IMAGE_SHAPE).  mode='training' is not part of this
+build and raises.  No TensorFlow, no Keras, no CPU fallback.
+"""
+import ctypes
+import datetime
+import errno
+import logging
+import os
+import re
+
+import numpy as np
+
+from . import _native, utils
+from .utils import compute_backbone_shapes  # noqa: F401  (re-exported, as in the reference)
+
+logger = logging.getLogger("mrcnn")
+
+# names of the graph outputs in keras_model.predict order (mrcnn/model.py:2156-2158)
+OUTPUT_NAMES = ["detections", "mrcnn_class", "mrcnn_bbox", "mrcnn_mask", "rpn_rois", "rpn_class", "rpn_bbox"]
+
+
+def log(text, array=None):
+    if array is not None:
+        text = text.ljust(25) + "shape: {:20}  ".format(str(array.shape))
+        if array.size:
+            text += "min: {:10.5f}  max: {:10.5f}".format(array.min(), array.max())
+        text += "  {}".format(array.dtype)
+    print(text)
+
+
+# --------------------------------------------------------------------------------------------
+# data formatting (mrcnn/model.py:2891-2975)
+# --------------------------------------------------------------------------------------------
+
+def compose_image_meta(image_id, original_image_shape, image_shape, window, scale, active_class_ids):
+    return np.array([image_id] + list(original_image_shape) + list(image_shape) + list(window) + [scale]
+                    + list(active_class_ids))
+
+
+def parse_image_meta(meta):
+    return {
+        "image_id": meta[:, 0].astype(np.int32),
+        "original_image_shape": meta[:, 1:4].astype(np.int32),
+        "image_shape": meta[:, 4:7].astype(np.int32),
+        "window": meta[:, 7:11].astype(np.int32),
+        "scale": meta[:, 11].astype(np.float32),
+        "active_class_ids": meta[:, 12:].astype(np.int32),
+    }
+
+
+def mold_image(images, config):
+    return images.astype(np.float32) - config.MEAN_PIXEL
+
+
+def unmold_image(normalized_images, config):
+    return (normalized_images + config.MEAN_PIXEL).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------------
+# MaskRCNN
+# --------------------------------------------------------------------------------------------
+
+class MaskRCNN(object):
+    """Mask R-CNN inference model; drop-in for mrcnn.model.MaskRCNN(mode='inference')."""
+
+    def __init__(self, mode, config, model_dir, device=None):
+        assert mode in ['training', 'inference']
+        self.mode = mode
+        self.config = config
+        self.model_dir = model_dir
+        self.set_log_dir()
+        self._engine = None
+        self._weights_loaded = False
+        self._device = device
+        self.keras_model = self.build(mode=mode, config=config)
+
+    # -- construction ---------------------------------------------------------------------------
+    def build(self, mode, config):
+        if mode != "inference":
+            raise NotImplementedError("mrcnn (B200 build): only mode='inference' is implemented (SURVEY.md §8f)")
+        h, w = config.IMAGE_SHAPE[:2]
+        if h / 2 ** 6 != int(h / 2 ** 6) or w / 2 ** 6 != int(w / 2 ** 6):
+            raise Exception("Image size must be dividable by 2 at least 6 times "
+                            "to avoid fractions when downscaling and upscaling."
+                            "For example, use 256, 320, 384, 448, 512, ... etc. ")
+        if h != w:
+            raise NotImplementedError("mrcnn (B200 build): square IMAGE_SHAPE only")
+        if config.BACKBONE != "resnet101":
+            raise NotImplementedError("mrcnn (B200 build): BACKBONE must be 'resnet101' (SURVEY.md §8a row a17)")
+        if config.IMAGE_CHANNEL_COUNT != 3:
+            raise NotImplementedError("mrcnn (B200 build): IMAGE_CHANNEL_COUNT must be 3 (SURVEY.md §8a row a17)")
+        torch = utils._torch()
+        lib = _native.lib()
+        if self._device is None:
+            self._device = torch.cuda.current_device()
+        cfg = _native.EngineConfig()
+        cfg.batch_size = int(config.BATCH_SIZE)
+        cfg.image_size = int(h)
+        cfg.num_classes = int(config.NUM_CLASSES)
+        cfg.pre_nms_limit = int(config.PRE_NMS_LIMIT)
+        cfg.post_nms_rois = int(config.POST_NMS_ROIS_INFERENCE)
+        cfg.detection_max_instances = int(config.DETECTION_MAX_INSTANCES)
+        cfg.pool_size = int(config.POOL_SIZE)
+        cfg.mask_pool_size = int(config.MASK_POOL_SIZE)
+        cfg.fc_layers_size = int(config.FPN_CLASSIF_FC_LAYERS_SIZE)
+        cfg.top_down_pyramid_size = int(config.TOP_DOWN_PYRAMID_SIZE)
+        cfg.anchors_per_location = len(config.RPN_ANCHOR_RATIOS)
+        cfg.rpn_nms_threshold = float(config.RPN_NMS_THRESHOLD)
+        cfg.detection_min_confidence = float(config.DETECTION_MIN_CONFIDENCE or 0.0)
+        cfg.detection_nms_threshold = float(config.DETECTION_NMS_THRESHOLD)
+        for i in range(4):
+            cfg.rpn_bbox_std_dev[i] = float(np.float32(config.RPN_BBOX_STD_DEV[i]))
+            cfg.bbox_std_dev[i] = float(np.float32(config.BBOX_STD_DEV[i]))
+        for i in range(5):
+            cfg.backbone_strides[i] = int(config.BACKBONE_STRIDES[i])
+        handle = ctypes.c_void_p()
+        _native.check(lib.mrcnn_engine_create(ctypes.byref(cfg), int(self._device), ctypes.byref(handle)), "engine_create")
+        self._engine = handle
+        self._lib = lib
+        return self     # callers only use .predict() on it
+
+    def __del__(self):
+        try:
+            if getattr(self, "_engine", None):
+                self._lib.mrcnn_engine_destroy(self._engine)
+                self._engine = None
+        except Exception:
+            pass
+
+    def layer_table(self):
+        """[(name, kind, [kernel shape])] of the weighted layers the inference graph expects."""
+        lib, out = self._lib, []
+        kinds = {0: "conv", 1: "bn", 2: "dense", 3: "deconv"}
+        for i in range(lib.mrcnn_engine_num_layers(self._engine)):
+            name = ctypes.c_char_p()
+            kind, nw = ctypes.c_int(), ctypes.c_int()
+            shape = (ctypes.c_int * 4)()
+            _native.check(lib.mrcnn_engine_layer_info(self._engine, i, ctypes.byref(name), ctypes.byref(kind),
+                                                      ctypes.byref(nw), shape))
+            out.append((name.value.decode(), kinds[kind.value], [s for s in shape if s > 0], nw.value))
+        return out
+
+    def print_model(self):
+        print("mask_rcnn (B200 engine): %d weighted layers" % self._lib.mrcnn_engine_num_layers(self._engine))
+        for name, kind, shape, _ in self.layer_table():
+            print("  {:28} {:7} {}".format(name, kind, shape))
+
+    # -- weights --------------------------------------------------------------------------------
+    def set_weights(self, weights, exclude=None, allow_missing=False):
+        """weights: {layer_name: [arrays in Keras layer.weights order]}."""
+        if self._weights_loaded:
+            raise RuntimeError("weights already loaded into this engine; create a new MaskRCNN")
+        lib = self._lib
+        known = {name for name, _, _, _ in self.layer_table()}
+        for name, arrays in weights.items():
+            if name not in known:
+                continue                                    # by_name semantics: unknown layers are skipped
+            if exclude and name in exclude:                 # NB: `in` on a str is a substring test,
+                continue                                    # as in the reference (model.py:2229, run.py:1738)
+            for wi, arr in enumerate(arrays):
+                a = np.ascontiguousarray(arr, dtype=np.float32)
+                _native.check(lib.mrcnn_engine_set_weight(self._engine, name.encode(), wi, a.ctypes.data, a.size),
+                              "load_weights(%s)" % name)
+        _native.check(lib.mrcnn_engine_finalize(self._engine, 1 if (allow_missing or exclude) else 0), "load_weights")
+        self._weights_loaded = True
+        self._set_anchors()
+
+    def load_weights(self, filepath, by_name=False, exclude=None):
+        """Keras-HDF5 weight file -> engine (reference: mrcnn/model.py:2197-2239). Loading is always
+        by layer name (the inference graph has no positional layer list)."""
+        from . import h5weights
+        weights = h5weights.read_keras_weights(filepath)
+        self.set_weights(weights, exclude=exclude)
+        self.set_log_dir(filepath)
+
+    def find_last(self):
+        dir_names = next(os.walk(self.model_dir))[1]
+        key = self.config.NAME.lower()
+        dir_names = sorted(filter(lambda f: f.startswith(key), dir_names))
+        if not dir_names:
+            raise FileNotFoundError(errno.ENOENT, "Could not find model directory under {}".format(self.model_dir))
+        dir_name = os.path.join(self.model_dir, dir_names[-1])
+        checkpoints = sorted(filter(lambda f: f.startswith("mask_rcnn"), next(os.walk(dir_name))[2]))
+        if not checkpoints:
+            raise FileNotFoundError(errno.ENOENT, "Could not find weight files in {}".format(dir_name))
+        return os.path.join(dir_name, checkpoints[-1])
+
+    def set_log_dir(self, model_path=None):
+        """log_dir / checkpoint_path / epoch bookkeeping (mrcnn/model.py:2357-2393); strings only."""
+        self.epoch = 0
+        now = datetime.datetime.now()
+        if model_path:
+            regex = r".*[/\\][\w-]+(\d{4})(\d{2})(\d{2})T(\d{2})(\d{2})[/\\]mask\_rcnn\_[\w-]+(\d{4})\.h5"
+            m = re.match(regex, str(model_path))
+            if m:
+                now = datetime.datetime(int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(4)), int(m.group(5)))
+                self.epoch = int(m.group(6)) - 1 + 1
+        name = (self.config.NAME or "mrcnn").lower()
+        self.log_dir = os.path.join(self.model_dir or ".", "{}{:%Y%m%dT%H%M}".format(name, now))
+        self.checkpoint_path = os.path.join(self.log_dir, "mask_rcnn_{}_*epoch*.h5".format(name)).replace("*epoch*", "{epoch:04d}")
+
+    # -- anchors --------------------------------------------------------------------------------
+    def get_anchors(self, image_shape):
+        backbone_shapes = compute_backbone_shapes(self.config, image_shape)
+        if not hasattr(self, "_anchor_cache"):
+            self._anchor_cache = {}
+        key = tuple(image_shape)
+        if key not in self._anchor_cache:
+            a = utils.generate_pyramid_anchors(self.config.RPN_ANCHOR_SCALES, self.config.RPN_ANCHOR_RATIOS, backbone_shapes,
+                                               self.config.BACKBONE_STRIDES, self.config.RPN_ANCHOR_STRIDE)
+            self.anchors = a
+            self._anchor_cache[key] = utils.norm_boxes(a, image_shape[:2])
+        return self._anchor_cache[key]
+
+    def _set_anchors(self):
+        a = np.ascontiguousarray(self.get_anchors(tuple(int(v) for v in self.config.IMAGE_SHAPE)), dtype=np.float32)
+        _native.check(self._lib.mrcnn_engine_set_anchors(self._engine, a.ctypes.data, a.shape[0]), "set_anchors")
+
+    # -- molding --------------------------------------------------------------------------------
+    def _mold_inputs_device(self, images):
+        """-> (molded CUDA float32 [B,S,S,3], image_metas float64 [B,12+NC], windows int [B,4])."""
+        torch = utils._torch()
+        cfg = self.config
+        S = int(cfg.IMAGE_SHAPE[0])
+        molded = torch.empty((len(images), S, S, 3), dtype=torch.float32, device="cuda:%d" % self._device)
+        metas, windows = [], []
+        groups = {}
+        for i, im in enumerate(images):
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+                raise NotImplementedError("mrcnn (B200 build): detect() takes uint8 [H,W,3] images (SURVEY.md §8a row a17)")
+            groups.setdefault(im.shape, []).append(i)
+        geo = {}
+        for shape, idxs in groups.items():
+            h, w = shape[:2]
+            scale, out_hw, top_left, window, _pad = utils.square_geometry(h, w, cfg.IMAGE_MIN_DIM, cfg.IMAGE_MAX_DIM,
+                                                                          cfg.IMAGE_MIN_SCALE, cfg.IMAGE_RESIZE_MODE)
+            if cfg.IMAGE_RESIZE_MODE == "none":
+                assert (h, w) == (S, S), "After resizing, all images must have the same size. Check IMAGE_RESIZE_MODE and image sizes."
+            geo[shape] = (scale, window)
+            host = torch.from_numpy(np.stack([images[i] for i in idxs]))
+            rgb = host.to(molded.device, non_blocking=False)
+            sub = utils.mold_rgb8_device(rgb, None, out_hw, S, top_left, cfg.MEAN_PIXEL)
+            molded[torch.as_tensor(idxs, device=molded.device)] = sub
+        for im in images:
+            scale, window = geo[im.shape]
+            metas.append(compose_image_meta(0, im.shape, (S, S, 3), window, scale, np.zeros([cfg.NUM_CLASSES], dtype=np.int32)))
+            windows.append(window)
+        return molded, np.stack(metas), np.stack(windows)
+
+    def mold_inputs(self, images):
+        """reference signature (mrcnn/model.py:2519-2556): numpy (molded_images, image_metas, windows)."""
+        molded, metas, windows = self._mold_inputs_device(images)
+        return molded.cpu().numpy(), metas, windows
+
+    # -- the graph ------------------------------------------------------------------------------
+    def predict(self, inputs, verbose=0):
+        """keras_model.predict([molded_images, image_metas, anchors]) -> the 7 graph outputs as numpy."""
+        molded, metas = inputs[0], inputs[1]
+        self._predict_device(molded, metas)
+        return [self.read_tensor(n) for n in OUTPUT_NAMES]
+
+    def _predict_device(self, molded, metas):
+        if not self._weights_loaded:
+            raise RuntimeError("load_weights() / set_weights() must be called before predict/detect")
+        torch = utils._torch()
+        B = self.config.BATCH_SIZE
+        metas32 = np.ascontiguousarray(metas, dtype=np.float32)
+        assert metas32.shape == (B, self.config.IMAGE_META_SIZE)
+        d_meta = torch.from_numpy(metas32).to("cuda:%d" % self._device)
+        if isinstance(molded, np.ndarray):
+            molded = torch.from_numpy(np.ascontiguousarray(molded, dtype=np.float32)).to("cuda:%d" % self._device)
+        assert tuple(molded.shape) == (B,) + tuple(int(v) for v in self.config.IMAGE_SHAPE), "molded images do not match IMAGE_SHAPE"
+        torch.cuda.current_stream().synchronize()
+        _native.check(self._lib.mrcnn_engine_predict(self._engine, _native.ptr(molded.contiguous()), _native.ptr(d_meta), 0, 0),
+                      "predict")
+
+    _TENSOR_SHAPES = None
+
+    def read_tensor(self, name):
+        """Host copy (float32 / int32) of a named engine tensor (graph outputs and taps)."""
+        c = self.config
+        B, R, D, NC = c.BATCH_SIZE, c.POST_NMS_ROIS_INFERENCE, c.DETECTION_MAX_INSTANCES, c.NUM_CLASSES
+        ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+        _native.check(self._lib.mrcnn_engine_tensor(self._engine, name.encode(), ctypes.byref(ptr), ctypes.byref(nbytes)), name)
+        int_names = ("topk_idx", "keep_idx", "keep_count", "roi_levels")
+        dt = np.int32 if name in int_names or name.startswith("unmold_rois") or name in ("unmold_class_ids", "unmold_counts") else np.float32
+        f32_names = set(OUTPUT_NAMES) | {"anchors", "input_image", "input_image_meta", "unmold_scores", "mrcnn_class_head_raw",
+                                          "mrcnn_mask_logits"}
+        is_wide = name in f32_names or dt == np.int32 or name.startswith("rpn_head_p")
+        n = nbytes.value // 4 if is_wide else nbytes.value // 2
+        out = np.empty((n,), dtype=dt)
+        _native.check(self._lib.mrcnn_engine_read(self._engine, name.encode(), out.ctypes.data, out.nbytes), "read " + name)
+        shapes = {"detections": (B, D, 6), "mrcnn_class": (B, R, NC), "mrcnn_bbox": (B, R, NC, 4),
+                  "mrcnn_mask": (B, D, c.MASK_SHAPE[0], c.MASK_SHAPE[1], NC), "rpn_rois": (B, R, 4),
+                  "rpn_class": (B, -1, 2), "rpn_bbox": (B, -1, 4), "keep_idx": (B, R), "keep_count": (B,),
+                  "topk_idx": (B, -1), "roi_levels": (B, R),
+                  "pooled": (B, R, c.POOL_SIZE, c.POOL_SIZE, c.TOP_DOWN_PYRAMID_SIZE),
+                  "pooled_mask": (B, D, c.MASK_POOL_SIZE, c.MASK_POOL_SIZE, c.TOP_DOWN_PYRAMID_SIZE)}
+        if name in shapes:
+            return out.reshape(shapes[name])
+        if re.match(r"^[PC][2-6]$", name):
+            ch = c.TOP_DOWN_PYRAMID_SIZE if name[0] == "P" else {"C2": 256, "C3": 512, "C4": 1024, "C5": 2048}[name]
+            side = int(round((n // (B * ch)) ** 0.5))
+            return out.reshape(B, side, side, ch)
+        return out
+
+    def write_tensor(self, name, array):
+        a = np.ascontiguousarray(array, dtype=np.int32 if array.dtype.kind in "iu" else np.float32)
+        _native.check(self._lib.mrcnn_engine_write(self._engine, name.encode(), a.ctypes.data, a.nbytes), "write " + name)
+
+    def run_stage(self, stage):
+        _native.check(self._lib.mrcnn_engine_run_stage(self._engine, stage.encode()), "run_stage " + stage)
+
+    def stage_times(self):
+        names = (ctypes.c_char_p * 32)()
+        ms = (ctypes.c_float * 32)()
+        n = self._lib.mrcnn_engine_stage_times(self._engine, 32, names, ms)
+        return {names[i].decode(): float(ms[i]) for i in range(n)}
+
+    # -- detection ------------------------------------------------------------------------------
+    def _detect_device(self, molded_dev, metas, windows, orig_shapes):
+        """engine predict + device unmold -> list of result dicts (numpy views of pinned buffers)."""
+        torch = utils._torch()
+        c = self.config
+        B, D = c.BATCH_SIZE, c.DETECTION_MAX_INSTANCES
+        shapes = {tuple(s[:2]) for s in orig_shapes}
+        if len(shapes) != 1:
+            raise NotImplementedError("mrcnn (B200 build): detect() needs the images of one batch to share one original size")
+        H0, W0 = next(iter(shapes))
+        metas32 = torch.from_numpy(np.ascontiguousarray(metas, dtype=np.float32)).pin_memory()
+        wins = torch.from_numpy(np.ascontiguousarray(windows, dtype=np.int32))
+        rois = torch.empty((B, D, 4), dtype=torch.int32).pin_memory()
+        cls = torch.empty((B, D), dtype=torch.int32).pin_memory()
+        scores = torch.empty((B, D), dtype=torch.float32).pin_memory()
+        counts = torch.empty((B,), dtype=torch.int32).pin_memory()
+        masks = torch.empty((B, H0, W0, D), dtype=torch.uint8).pin_memory()
+        orig = (ctypes.c_int * 2)(int(H0), int(W0))
+        torch.cuda.current_stream().synchronize()
+        on_host = 0 if molded_dev.is_cuda else 1
+        _native.check(self._lib.mrcnn_engine_detect_molded(self._engine, _native.ptr(molded_dev), on_host, _native.ptr(metas32), orig,
+                                                           _native.ptr(wins), _native.ptr(rois), _native.ptr(cls),
+                                                           _native.ptr(scores), _native.ptr(counts), _native.ptr(masks)),
+                      "detect")
+        results = []
+        rois_n, cls_n, sc_n, cnt_n, m_n = rois.numpy(), cls.numpy(), scores.numpy(), counts.numpy(), masks.numpy()
+        for i in range(B):
+            n = int(cnt_n[i])
+            results.append({"rois": rois_n[i, :n], "class_ids": cls_n[i, :n], "scores": sc_n[i, :n],
+                            "masks": m_n[i, :, :, :n].view(np.bool_)})
+        return results
+
+    def detect(self, images, verbose=0):
+        """Runs the detection pipeline (reference: mrcnn/model.py:2623-2704).
+        images: list of BATCH_SIZE uint8 [H,W,3] arrays. Returns one dict per image with
+        rois [N,4] int32, class_ids [N] int32, scores [N] float32, masks [H,W,N] bool."""
+        assert self.mode == "inference", "Create model in inference mode."
+        assert len(images) == self.config.BATCH_SIZE, "len(images) must be equal to BATCH_SIZE"
+        if verbose:
+            log("Processing {} images".format(len(images)))
+            for image in images:
+                log("image", image)
+        molded, metas, windows = self._mold_inputs_device(images)
+        return self._detect_device(molded, metas, windows, [im.shape for im in images])
+
+    def detect_molded(self, molded_images, image_metas, verbose=0):
+        """reference: mrcnn/model.py:2706-2762 — inputs already molded; the window is the whole image."""
+        assert self.mode == "inference", "Create model in inference mode."
+        assert len(molded_images) == self.config.BATCH_SIZE, "Number of images must be equal to BATCH_SIZE"
+        torch = utils._torch()
+        molded = np.ascontiguousarray(np.stack(molded_images), dtype=np.float32)
+        image_shape = molded[0].shape
+        windows = np.array([[0, 0, image_shape[0], image_shape[1]]] * len(molded_images))
+        return self._detect_device(torch.from_numpy(molded).pin_memory(), np.asarray(image_metas), windows,
+                                   [image_shape] * len(molded_images))
+
+    def unmold_detections(self, detections, mrcnn_mask, original_image_shape, image_shape, window):
+        """reference: mrcnn/model.py:2558-2621, for one image, computed on the GPU."""
+        torch = utils._torch()
+        lib = self._lib
+        D = detections.shape[0]
+        dev = "cuda:%d" % self._device
+        d_det = torch.from_numpy(np.ascontiguousarray(detections, dtype=np.float32)).to(dev)
+        d_mask = torch.from_numpy(np.ascontiguousarray(mrcnn_mask, dtype=np.float32)).to(dev)
+        d_win = torch.from_numpy(np.ascontiguousarray(window, dtype=np.int32).reshape(1, 4)).to(dev)
+        H0, W0 = int(original_image_shape[0]), int(original_image_shape[1])
+        rois = torch.empty((D, 4), dtype=torch.int32, device=dev)
+        cls = torch.empty((D,), dtype=torch.int32, device=dev)
+        sc = torch.empty((D,), dtype=torch.float32, device=dev)
+        cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+        masks = torch.empty((H0, W0, D), dtype=torch.uint8, device=dev)
+        ws = torch.empty((lib.mrcnn_unmold_workspace_bytes(1, D),), dtype=torch.uint8, device=dev)
+        orig = (ctypes.c_int * 2)(H0, W0)
+        img = (ctypes.c_int * 2)(int(image_shape[0]), int(image_shape[1]))
+        _native.check(lib.mrcnn_unmold_detections(_native.ptr(d_det), _native.ptr(d_mask), 1, D, mrcnn_mask.shape[1],
+                                                  mrcnn_mask.shape[2], mrcnn_mask.shape[3], orig, img, _native.ptr(d_win),
+                                                  _native.ptr(rois), _native.ptr(cls), _native.ptr(sc), _native.ptr(cnt),
+                                                  _native.ptr(masks), _native.ptr(ws), ws.numel(),
+                                                  torch.cuda.current_stream().cuda_stream), "unmold_detections")
+        n = int(cnt.item())
+        full = masks.cpu().numpy()[:, :, :n].view(np.bool_)
+        return rois.cpu().numpy()[:n], cls.cpu().numpy()[:n], sc.cpu().numpy()[:n], full

@@ -1,0 +1,211 @@
+"""mrcnn.utils — host-side mirror of the utilities the detect path uses (reference:
+mrcnn/utils.py).  Array maths that sits on the hot path (zscale stretch, uint8 conversion, resize /
+pad) runs on the GPU through libmrcnn_b200.so; there is no CPU fallback.  Anchor generation and box
+normalisation are cached one-off host computations, as in the reference.
+
+Mirrors: read_fits :1033-1163 (default flag set), get_fits_header :992-1005, get_fits_size
+:1009-1030, resize_image :456-561 (modes none/square), compute/generate anchors :652-708,
+norm_boxes :923-937, denorm_boxes :940-954.
+"""
+import logging
+import math
+
+import numpy as np
+
+from . import _native, fitsio
+
+logger = logging.getLogger("mrcnn")
+
+
+# --------------------------------------------------------------------------------------------
+# device helpers
+# --------------------------------------------------------------------------------------------
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _native.NativeError("mrcnn (B200 build) needs a CUDA device; there is no CPU fallback")
+    return torch
+
+
+def maps_to_rgb8_device(maps, zscale_contrasts=(0.25, 0.25, 0.25)):
+    """maps: CUDA float32 tensor [n,H,W] (NaN allowed) -> (rgb uint8 [n,H,W,3], minmax int32 [n,2]).
+    The GPU form of read_fits' NaN fill + zscale + normalise + uint8 RGB (utils.py:1090-1208)."""
+    torch = _torch()
+    lib = _native.lib()
+    assert maps.is_cuda and maps.dtype == torch.float32 and maps.dim() == 3 and maps.is_contiguous()
+    n, H, W = maps.shape
+    params = torch.empty((n, 3, 4), dtype=torch.float32, device=maps.device)
+    rgb = torch.empty((n, H, W, 3), dtype=torch.uint8, device=maps.device)
+    minmax = torch.empty((n, 2), dtype=torch.int32, device=maps.device)
+    stream = torch.cuda.current_stream().cuda_stream
+    con = _native.float_array(list(zscale_contrasts))
+    _native.check(lib.mrcnn_zscale_params(_native.ptr(maps), n, H, W, con, _native.ptr(params), stream), "zscale_params")
+    _native.check(lib.mrcnn_stretch_to_rgb8(_native.ptr(maps), _native.ptr(params), n, H, W, _native.ptr(rgb),
+                                            _native.ptr(minmax), stream), "stretch_to_rgb8")
+    return rgb, minmax, params
+
+
+def square_geometry(h, w, min_dim, max_dim, min_scale, mode):
+    """scale / output size / padding / window of utils.resize_image (utils.py:489-533)."""
+    scale = 1
+    if mode == "none":
+        return 1, (h, w), (0, 0), (0, 0, h, w), [(0, 0), (0, 0), (0, 0)]
+    if mode != "square":
+        raise Exception("Mode {} not supported".format(mode))
+    if min_dim:
+        scale = max(1, min_dim / min(h, w))
+    if min_scale and scale < min_scale:
+        scale = min_scale
+    if max_dim:
+        image_max = max(h, w)
+        if round(image_max * scale) > max_dim:
+            scale = max_dim / image_max
+    oh, ow = (round(h * scale), round(w * scale)) if scale != 1 else (h, w)
+    top = (max_dim - oh) // 2
+    left = (max_dim - ow) // 2
+    padding = [(top, max_dim - oh - top), (left, max_dim - ow - left), (0, 0)]
+    window = (top, left, oh + top, ow + left)
+    return scale, (oh, ow), (top, left), window, padding
+
+
+def mold_rgb8_device(rgb, minmax, out_hw, square, top_left, mean_pixel, out=None):
+    """rgb CUDA uint8 [n,H,W,3] -> molded CUDA float32 [n,S,S,3] (resize + pad + mean subtraction)."""
+    torch = _torch()
+    lib = _native.lib()
+    n, H, W, _ = rgb.shape
+    if minmax is None:
+        flat = rgb.reshape(n, -1)
+        minmax = torch.stack([flat.amin(dim=1), flat.amax(dim=1)], dim=1).to(torch.int32).contiguous()
+    if out is None:
+        out = torch.empty((n, square, square, 3), dtype=torch.float32, device=rgb.device)
+    mean = _native.float_array([float(v) for v in np.asarray(mean_pixel).reshape(-1)[:3]])
+    stream = torch.cuda.current_stream().cuda_stream
+    _native.check(lib.mrcnn_resize_pad_mold(_native.ptr(rgb), _native.ptr(minmax), n, H, W, int(out_hw[0]), int(out_hw[1]),
+                                            int(square), int(top_left[0]), int(top_left[1]), mean, _native.ptr(out), stream),
+                  "resize_pad_mold")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# FITS
+# --------------------------------------------------------------------------------------------
+
+def get_fits_header(filename):
+    try:
+        _, header = fitsio.read_primary(filename)
+    except Exception:
+        logger.error("ERROR: Cannot read image file: " + str(filename))
+        return None
+    return header
+
+
+def get_fits_size(filename):
+    header = get_fits_header(filename)
+    if header is None:
+        return None
+    for key in ("NAXIS1", "NAXIS2"):
+        if key not in header:
+            logger.error("%s keyword missing in header!" % key)
+            return None
+    return header["NAXIS1"], header["NAXIS2"]
+
+
+def read_fits(filename, xmin=-1, xmax=-1, ymin=-1, ymax=-1, stretch=True, normalize=True, convertToRGB=True,
+              zscale_contrasts=[0.25, 0.25, 0.25], to_uint8=True, stretch_biascontrast=False, contrast=1, bias=0.5):
+    """FITS file -> ([H,W,3] uint8 image, header); None when the file cannot be read or is not a
+    2-D / 4-D image (same convention as the reference).  Only the flag combination `run.py detect`
+    uses is supported (zscale stretch + normalise + uint8 RGB); other combinations raise."""
+    if len(zscale_contrasts) != 3:
+        logger.warning("Size of input zscale_contrasts is !=3, ignoring inputs and using default (0.25,0.25,0.25)...")
+        zscale_contrasts = [0.25, 0.25, 0.25]
+    try:
+        data, header = fitsio.read_primary(filename)
+    except Exception:
+        logger.error("ERROR: Cannot read image file: " + str(filename))
+        return None
+    read_tile = (xmin >= 0 and xmax >= 0 and ymin >= 0 and ymax >= 0)
+    if read_tile:
+        if xmax <= xmin:
+            logger.error("xmax must be >xmin for tile reading!")
+            return None
+        if ymax <= ymin:
+            logger.error("ymax must be >ymin for tile reading!")
+            return None
+    if data is None or data.ndim not in (2, 4):
+        logger.error("ERROR: Invalid/unsupported number of channels found in file " + str(filename))
+        return None
+    plane = data[0, 0] if data.ndim == 4 else data
+    if read_tile:
+        plane = plane[ymin:ymax, xmin:xmax]
+    if not (stretch and normalize and convertToRGB and to_uint8) or stretch_biascontrast:
+        raise NotImplementedError("read_fits (B200 build): only stretch=True, normalize=True, convertToRGB=True, "
+                                  "to_uint8=True, stretch_biascontrast=False is implemented (SURVEY.md §8a row a17)")
+    torch = _torch()
+    maps = torch.from_numpy(np.ascontiguousarray(plane, dtype=np.float32)).cuda().unsqueeze(0).contiguous()
+    rgb, _, _ = maps_to_rgb8_device(maps, zscale_contrasts)
+    return rgb[0].cpu().numpy(), header
+
+
+# --------------------------------------------------------------------------------------------
+# resize (host API, GPU arithmetic)
+# --------------------------------------------------------------------------------------------
+
+def resize_image(image, min_dim=None, max_dim=None, min_scale=None, mode="square"):
+    """uint8 [H,W,3] -> (image, window, scale, padding, crop), reference utils.resize_image."""
+    h, w = image.shape[:2]
+    if mode == "none":
+        return image, (0, 0, h, w), 1, [(0, 0), (0, 0), (0, 0)], None
+    if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
+        raise NotImplementedError("resize_image (B200 build): uint8 [H,W,3] images only")
+    scale, out_hw, top_left, window, padding = square_geometry(h, w, min_dim, max_dim, min_scale, mode)
+    torch = _torch()
+    rgb = torch.from_numpy(np.ascontiguousarray(image)).cuda().unsqueeze(0)
+    molded = mold_rgb8_device(rgb, None, out_hw, max_dim, top_left, (0.0, 0.0, 0.0))
+    return molded[0].to(torch.uint8).cpu().numpy(), window, scale, padding, None
+
+
+# --------------------------------------------------------------------------------------------
+# anchors / box normalisation (host, cached by the model)
+# --------------------------------------------------------------------------------------------
+
+def compute_backbone_shapes(config, image_shape):
+    if callable(config.BACKBONE):
+        return config.COMPUTE_BACKBONE_SHAPE(image_shape)
+    assert config.BACKBONE in ["resnet50", "resnet101", "custom"]
+    return np.array([[int(math.ceil(image_shape[0] / s)), int(math.ceil(image_shape[1] / s))]
+                     for s in config.BACKBONE_STRIDES])
+
+
+def generate_anchors(scales, ratios, shape, feature_stride, anchor_stride):
+    """[(y,x) grid positions x ratios, (y1,x1,y2,x2)] anchors of one pyramid level, float64."""
+    scales = np.atleast_1d(np.asarray(scales))
+    ratios = np.asarray(ratios)
+    # ratio-major over scales, as np.meshgrid(scales, ratios).flatten() orders them
+    sc = np.repeat(scales[None, :], len(ratios), axis=0).reshape(-1)
+    ra = np.repeat(ratios[:, None], len(scales), axis=1).reshape(-1)
+    hh = sc / np.sqrt(ra)
+    ww = sc * np.sqrt(ra)
+    ys = np.arange(0, shape[0], anchor_stride) * feature_stride
+    xs = np.arange(0, shape[1], anchor_stride) * feature_stride
+    cy = np.broadcast_to(ys[:, None, None], (len(ys), len(xs), len(hh)))
+    cx = np.broadcast_to(xs[None, :, None], (len(ys), len(xs), len(hh)))
+    h = np.broadcast_to(hh[None, None, :], cy.shape)
+    w = np.broadcast_to(ww[None, None, :], cy.shape)
+    boxes = np.stack([cy - 0.5 * h, cx - 0.5 * w, cy + 0.5 * h, cx + 0.5 * w], axis=-1)
+    return boxes.reshape(-1, 4)
+
+
+def generate_pyramid_anchors(scales, ratios, feature_shapes, feature_strides, anchor_stride):
+    return np.concatenate([generate_anchors(scales[i], ratios, feature_shapes[i], feature_strides[i], anchor_stride)
+                           for i in range(len(scales))], axis=0)
+
+
+def norm_boxes(boxes, shape):
+    h, w = shape
+    return ((boxes - np.array([0, 0, 1, 1])) / np.array([h - 1, w - 1, h - 1, w - 1])).astype(np.float32)
+
+
+def denorm_boxes(boxes, shape):
+    h, w = shape
+    return np.around(np.multiply(boxes, np.array([h - 1, w - 1, h - 1, w - 1])) + np.array([0, 0, 1, 1])).astype(np.int32)

@@ -59,7 +59,7 @@ int mrcnn_stretch_to_rgb8(const float* maps, const float* params, int n_images, 
 /* ---- a2: mold_inputs  (mrcnn/model.py:2519-2556; utils.resize_image mrcnn/utils.py:456-561 mode
  *      "square"; utils.resize :957-978 = skimage<=0.15 bilinear warp, cval 0, clip; mold_image
  *      mrcnn/model.py:2964-2969).  All n images share one original size (height,width).
- * rgb [n,H,W,3] uint8, minmax [n,2] (or NULL = recompute) -> molded [n,S,S,3] float32:
+ * rgb [n,H,W,3] uint8, minmax [n,2] (from mrcnn_stretch_to_rgb8) -> molded [n,S,S,3] float32:
  * resize to (out_h,out_w) (skipped when equal to (H,W)), truncate to uint8, paste at (top,left)
  * into a zero S x S frame, subtract mean_pixel (host pointer, 3 floats). */
 int mrcnn_resize_pad_mold(const uint8_t* rgb, const int32_t* minmax, int n_images, int height,
@@ -205,10 +205,12 @@ int mrcnn_engine_read(const mrcnn_engine* e, const char* name, void* host_dst, s
 int mrcnn_engine_run_stage(mrcnn_engine* e, const char* stage);
 int mrcnn_engine_write(mrcnn_engine* e, const char* name, const void* host_src, size_t src_bytes);
 /* whole detect(): predict + unmold, results to HOST buffers (pinned recommended).
- * images are already molded (MaskRCNN.mold_inputs output); orig_hw/windows as for
- * mrcnn_unmold_detections (windows: HOST int32 [B,4]).  masks [B,H0,W0,D] uint8. */
-int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded_host, const float* metas_host,
-                               const int* orig_hw, const int32_t* windows_host, int32_t* rois_host,
+ * molded [B,S,S,3] float32 (MaskRCNN.mold_inputs output): HOST pointer when molded_on_host != 0,
+ * else DEVICE; metas / windows (int32 [B,4]) / orig_hw: HOST.  Outputs as for
+ * mrcnn_unmold_detections, written to HOST buffers; masks [B,H0,W0,D] uint8.  Blocking. */
+int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, int molded_on_host,
+                               const float* metas_host, const int* orig_hw,
+                               const int32_t* windows_host, int32_t* rois_host,
                                int32_t* class_ids_host, float* scores_host, int32_t* counts_host,
                                uint8_t* masks_host);
 void* mrcnn_engine_stream(const mrcnn_engine* e);

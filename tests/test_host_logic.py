@@ -1,0 +1,151 @@
+"""CPU: host-side mirror of the reference interface (mrcnn package) + C-ABI library surface.
+No compute call needs a GPU here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import host_ops as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_config_defaults_match_reference(golden):
+    from mrcnn.config import Config
+    base = Config()
+    names = sorted(a for a in dir(base) if not a.startswith("__") and not callable(getattr(base, a)))
+    assert names == list(golden["config_attr_names"])
+    for n, r in zip(golden["config_attr_names"], golden["config_attr_reprs"]):
+        assert repr(getattr(base, n)) == r, n
+
+    class C(Config):
+        NUM_CLASSES = 4
+        GPU_COUNT = 1
+        IMAGES_PER_GPU = 1
+        IMAGE_MIN_DIM = 256
+        IMAGE_MAX_DIM = 256
+    c = C()
+    assert [c.BATCH_SIZE, c.IMAGE_META_SIZE] + list(c.IMAGE_SHAPE) == list(golden["config_derived"])
+    c.display()
+
+
+def test_anchor_and_box_helpers_match_reference(golden):
+    from mrcnn import utils
+
+    class Cfg:
+        BACKBONE = "resnet101"
+        BACKBONE_STRIDES = [4, 8, 16, 32, 64]
+    for S in (256, 128):
+        shapes = utils.compute_backbone_shapes(Cfg, (S, S, 3))
+        assert np.array_equal(shapes, golden["backbone_shapes_%d" % S])
+        a = utils.generate_pyramid_anchors((4, 8, 16, 32, 64), [0.5, 1, 2], shapes, [4, 8, 16, 32, 64], 1)
+        assert np.array_equal(a, golden["anchors_px_%d" % S])
+        assert np.array_equal(utils.norm_boxes(a, (S, S)), golden["anchors_norm_%d" % S])
+    assert np.array_equal(utils.generate_anchors(32, [0.5, 1, 2], [3, 5], 16, 2), golden["gen_anchors_small"])
+    assert np.array_equal(utils.norm_boxes(golden["norm_in"], (132, 200)), golden["norm_out"])
+    assert np.array_equal(utils.denorm_boxes(golden["denorm_in"], (132, 132)), golden["denorm_out"])
+
+
+def test_square_geometry_matches_reference_resize_bookkeeping(golden):
+    from mrcnn import utils
+    h, w = golden["resize_in"].shape[:2]
+    scale, out_hw, top_left, window, padding = utils.square_geometry(h, w, 128, 128, 0, "square")
+    assert float(scale) == float(golden["resize_scale"][0])
+    assert tuple(window) == tuple(golden["resize_window"])
+    assert np.array_equal(np.array(padding), golden["resize_padding"])
+    # galaxy0002 case of SURVEY.md Appendix D: 132 -> 256, no padding
+    scale, out_hw, top_left, window, _ = utils.square_geometry(132, 132, 256, 256, 0, "square")
+    assert out_hw == (256, 256) and window == (0, 0, 256, 256) and abs(scale - 256 / 132) < 1e-12
+    # oracle agreement on a down-scaling case
+    img = np.zeros((300, 500, 3), np.uint8)
+    _, owin, oscale, opad, _ = H.resize_image(img, min_dim=256, max_dim=256, min_scale=0, mode="square")
+    scale, out_hw, top_left, window, padding = utils.square_geometry(300, 500, 256, 256, 0, "square")
+    assert (scale, tuple(window), padding) == (oscale, tuple(owin), opad)
+
+
+def test_meta_helpers(golden):
+    from mrcnn import model as modellib
+    meta = modellib.compose_image_meta(3, (132, 132, 3), (256, 256, 3), (0, 0, 256, 256), 1.9393939,
+                                       np.zeros([4], dtype=np.int32))
+    assert np.array_equal(meta, golden["compose_meta"])
+    p = modellib.parse_image_meta(meta[None])
+    assert p["image_shape"].tolist() == [[256, 256, 3]] and p["window"].tolist() == [[0, 0, 256, 256]]
+
+    class Cfg:
+        MEAN_PIXEL = np.array([0, 0, 0])
+    assert np.array_equal(modellib.mold_image(golden["resize_in"][:4, :4], Cfg), golden["mold_image_f"])
+
+
+def test_fits_reader(golden_dir, tmp_path):
+    from mrcnn import fitsio
+    for name in ("galaxy0002.fits", "sidelobe0001.fits"):
+        path = os.path.join(golden_dir, name)
+        data, hdr = fitsio.read_primary(path)
+        ref, rhdr = H.parse_fits_primary(open(path, "rb").read())
+        assert data.dtype == np.float32 and data.dtype.isnative
+        assert np.array_equal(data, ref, equal_nan=True)
+        assert hdr["NAXIS1"] == 132 and hdr["BITPIX"] == -32
+    _, hdr = fitsio.read_primary(os.path.join(golden_dir, "galaxy0002.fits"))
+    assert hdr["TELESCOP"] == "EVLA" and abs(hdr["BMAJ"] - 1.7778e-3) < 1e-6
+    # 4-D cube + int16 with BSCALE/BZERO, written by hand
+    cards = ["SIMPLE  =                    T", "BITPIX  =                   16", "NAXIS   =                    4",
+             "NAXIS1  =                    3", "NAXIS2  =                    2", "NAXIS3  =                    1",
+             "NAXIS4  =                    1", "BSCALE  =                  0.5", "BZERO   =                 10.0", "END"]
+    hdrb = "".join(c.ljust(80) for c in cards).ljust(2880).encode()
+    payload = np.arange(6, dtype=">i2").tobytes().ljust(2880, b"\0")
+    f = tmp_path / "cube.fits"
+    f.write_bytes(hdrb + payload)
+    data, hdr = fitsio.read_primary(str(f))
+    assert data.shape == (1, 1, 2, 3) and np.allclose(data.ravel(), np.arange(6) * 0.5 + 10)
+    with pytest.raises(IOError):
+        fitsio.read_primary(__file__)
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    import ctypes
+    from mrcnn import _native
+    hdr = open(os.path.join(ROOT, "include", "mrcnn_b200.h")).read()
+    declared = set(re.findall(r"\b(mrcnn_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    lib = _native.lib()                       # loads without a GPU (static cudart, no driver needed)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mrcnn_abi_version() == 1
+    assert ctypes.sizeof(_native.ConvDesc) == 14 * 4
+    assert ctypes.sizeof(_native.EngineConfig) == (11 + 3 + 8 + 5) * 4
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ctypes
+    from mrcnn import _native, model as modellib
+    from mrcnn.config import Config
+
+    class C(Config):
+        NUM_CLASSES = 4
+        IMAGE_MIN_DIM = 256
+        IMAGE_MAX_DIM = 256
+    with pytest.raises(_native.NativeError, match="no CPU fallback"):
+        modellib.MaskRCNN(mode="inference", config=C(), model_dir="/tmp/x")
+    lib = _native.lib()
+    cfg = _native.EngineConfig(batch_size=1, image_size=256, num_classes=4, pre_nms_limit=6000, post_nms_rois=1000,
+                               detection_max_instances=100, pool_size=7, mask_pool_size=14, fc_layers_size=1024,
+                               top_down_pyramid_size=256, anchors_per_location=3)
+    for i, s in enumerate((4, 8, 16, 32, 64)):
+        cfg.backbone_strides[i] = s
+    h = ctypes.c_void_p()
+    assert lib.mrcnn_engine_create(ctypes.byref(cfg), 0, ctypes.byref(h)) != 0
+    assert b"CUDA" in lib.mrcnn_last_error() or b"device" in lib.mrcnn_last_error()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "caesar-mrcnn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
+                assert "oracle/" not in src or f.endswith((".cu", ".cuh")), os.path.join(dirpath, f)
