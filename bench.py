@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — detect images/s of the B200 Mask R-CNN detect path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one pass of the whole hot path over one batch of 64 synthetic FITS-like radio maps
+ at IMAGE_MAX_DIM = 256: NaN fill + zscale + uint8 RGB -> resize/pad/mold ->
+ResNet-101-FPN + RPN -> ProposalLayer -> ROIAlign -> class head -> DetectionLayer -> ROIAlign ->
+mask head -> unmold to full-frame masks.  `value` times that with the float32 maps already resident
+in HBM and results left in HBM; `e2e` times the same call with pinned HOST maps in and HOST results
+(rois, class ids, scores, [H,W,N] masks) out.  Multi-GPU: one process per GPU, each rank runs its
+own batches (weak scaling, no collective on the data path).
+
+--impl reference times the CPU restatement of the reference path (oracle/: torch-CPU fp32 convs +
+numpy/C++ layers; TensorFlow 1.13 cannot run in this image) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "caesar-mrcnn_b200"))
+
+import numpy as np  # noqa: E402
+
+S = 256
+BATCH = 64
+METRIC = "detect_images_per_sec"
+UNIT = "images/s"
+WORKLOAD = "batched detect, 64 synthetic radio maps at IMAGE_MAX_DIM=256 (BASELINE.json configs[1])"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def _oracle_cfg():
+    return dict(PRE_NMS_LIMIT=6000, POST_NMS_ROIS_INFERENCE=1000, RPN_NMS_THRESHOLD=0.7,
+                RPN_BBOX_STD_DEV=(0.1, 0.1, 0.2, 0.2), BBOX_STD_DEV=(0.1, 0.1, 0.2, 0.2), DETECTION_MIN_CONFIDENCE=0,
+                DETECTION_NMS_THRESHOLD=0.3, DETECTION_MAX_INSTANCES=100, POOL_SIZE=7, MASK_POOL_SIZE=14)
+
+
+def cpu_detect_images(maps, weights, threads):
+    """The reference detect path restated on the CPU (oracle): read_fits stretch -> mold -> graph -> unmold."""
+    from oracle import host_ops as H, network as N
+    net = N.OracleNet(weights, 4, emulate_bf16=False, threads=threads)
+    anchors = H.get_anchors((S, S, 3), (4, 8, 16, 32, 64))
+    t0 = time.perf_counter()
+    for m in maps:
+        img = H.fits_to_rgb(m)
+        molded, metas, windows = H.mold_inputs([img], min_dim=S, max_dim=S, min_scale=0, mode="square",
+                                               mean_pixel=np.array([0, 0, 0]), num_classes=4)
+        out = net.predict(molded, metas, anchors, _oracle_cfg())
+        H.unmold_detections(out["detections"][0], out["mrcnn_mask"][0], img.shape, (S, S, 3), windows[0])
+    return time.perf_counter() - t0
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._halt, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self._halt.is_set():
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self._halt.set()
+        if self.proc:
+            self.proc.terminate()
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(self.samples)}
+        try:
+            sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["sm_max_mhz"] = float(self.samples[0][1])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for k, n in enumerate(names):
+                if any(len(s) > 3 + k and s[3 + k].lower().startswith("active") for s in self.samples):
+                    out["reasons"].append(n)
+        except Exception:
+            pass
+        return out
+
+
+def run_reference(args, rank, world):
+    """Reference arm: CPU restatement on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+    import synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    weights = synth.make_random_weights(0, 4)
+    per_step = 1                                   # bounded sample: 1 image per step
+    maps = synth.radio_maps(per_step * (args.steps + args.warmup), S)
+    for w in range(args.warmup):
+        cpu_detect_images(maps[w * per_step:(w + 1) * per_step], weights, threads)
+    t = cpu_detect_images(maps[args.warmup * per_step:], weights, threads)
+    n_img = per_step * args.steps
+    value = n_img / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch": per_step, "image_size": S},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d image(s) per step x %d steps, oracle CPU restatement (TF 1.13 cannot run here)" % (per_step, args.steps)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import synth
+    from mrcnn import _native, model as modellib
+    from mrcnn.config import Config
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = args.batch
+
+    class BenchConfig(Config):
+        NAME = "rg-dataset"
+        GPU_COUNT = 1
+        IMAGES_PER_GPU = B
+        NUM_CLASSES = 4
+        IMAGE_MIN_DIM = S
+        IMAGE_MAX_DIM = S
+        RPN_ANCHOR_SCALES = (4, 8, 16, 32, 64)
+        MEAN_PIXEL = np.array([0, 0, 0])
+        DETECTION_MIN_CONFIDENCE = 0
+        RPN_NMS_THRESHOLD = 0.7
+
+    weights = synth.make_random_weights(0, 4)
+    model = modellib.MaskRCNN(mode="inference", config=BenchConfig(), model_dir="/tmp/mrcnn_bench", device=local_rank)
+    model.set_weights(weights)
+    model.set_profiling(True)
+    lib = _native.lib()
+
+    # distinct input batches per step (rotated) so no step re-reads the previous step's inputs from L2;
+    # the per-step working set (~12 GB of activations) is ~100x the 126 MB L2 anyway
+    n_sets = 4
+    base = synth.radio_maps(B, S, start=1000 * rank)
+    host_sets, dev_sets = [], []
+    for k in range(n_sets):
+        arr = np.roll(base, k * 7, axis=0).copy()
+        if k % 2:
+            arr = arr[:, ::-1, :].copy()
+        t = torch.from_numpy(arr).pin_memory()
+        host_sets.append(t)
+        dev_sets.append(t.cuda())
+    stream = model._stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for i in range(steps):
+                fn(i)
+            ev1.record(stream)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    # ---- device-resident throughput ("value") ------------------------------------------------
+    dev_step = lambda i: model.detect_maps(dev_sets[i % n_sets], device_only=True)  # noqa: E731
+    for i in range(args.warmup):
+        dev_step(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = lib.mrcnn_kernel_launch_count()
+    kt_acc, st_acc = {}, {}
+
+    prof = {"n": 0}
+
+    def dev_step_profiled(i):
+        dev_step(i)
+        if i % 5:                      # read the per-launch events of every 5th timed step
+            return
+        prof["n"] += 1
+        for k, (ms, n) in model.kernel_times().items():
+            a = kt_acc.setdefault(k, [0.0, 0])
+            a[0] += ms
+            a[1] += n
+        for k, ms in model.stage_times().items():
+            st_acc[k] = st_acc.get(k, 0.0) + ms
+    ms_total = timed(dev_step_profiled, args.steps)
+    launches = lib.mrcnn_kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- end to end: pinned host maps in, host results out, every step -------------------------------
+    e2e_results = [None]
+
+    def e2e_step(i):
+        e2e_results[0] = model.detect_maps(host_sets[i % n_sets])
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    D = 100
+    h2d = B * S * S * 4 + B * 16 * 4 + B * 16
+    d2h = B * (D * 4 * 4 + D * 4 + D * 4 + 4) + B * S * S * D
+
+    # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM convolutions) ---------------
+    peaks = _peaks()
+    flops = model.flops_per_predict()
+    gemm_ms, gemm_launches = kt_acc.get("conv_gemm", [0.0, 0])
+    nprof = max(1, prof["n"])
+    gemm_ms_step = gemm_ms / nprof
+    achieved = flops / (gemm_ms_step / 1e3) / 1e12 if gemm_ms_step > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("conv_gemm_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<BLOCK_N> (all %d launches of a step)" % (gemm_launches // nprof),
+                "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16",
+                "flops_per_step": flops, "kernel_ms_per_step": gemm_ms_step}
+    # HBM-bound stages the north star asks about (algorithmic bytes from SURVEY.md §8d, per image, bf16)
+    alg = {"roialign": (27.89e6 + 12.82e6) * B, "proposal": 0.6707e6 * B, "detection": 0.096e6 * B}
+    stages = {}
+    for k, (ms, n) in kt_acc.items():
+        per_step = ms / nprof
+        ent = {"ms_per_step": per_step, "us_per_image": 1e3 * per_step / B, "launches_per_step": n // nprof}
+        if k in alg and per_step > 0:
+            gbs = alg[k] / (per_step / 1e3) / 1e9
+            ent.update({"algorithmic_bytes_per_step": alg[k], "achieved_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"]})
+        stages[k] = ent
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "image_size": S, "num_classes": 4, "weights": "seeded random (LFS pointer unresolved)",
+                       "l2": "4 rotated input batches; per-step working set ~12 GB >> 126 MB L2", "parallelism": "batch-sharded, no collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_families": stages,
+            "stage_ms_per_step": {k: v / nprof for k, v in st_acc.items()},
+            "detections_in_last_batch": int(sum(len(r["class_ids"]) for r in e2e_results[0]))}
+
+    # ---- CPU baseline: bounded sample of the same workload on the host cores (rank 0, N = 1) --------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = 4
+        cpu_detect_images(base[:1], weights, threads)            # warm-up (page-in, thread pool)
+        t = cpu_detect_images(base[:sample], weights, threads)
+        line["cpu_baseline"] = {"value": sample / t, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "%d of the 64 maps, fp32 oracle restatement of the reference path (TF1 unavailable)" % sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) conv_gemm_kernel(const __grid_co
       else
         res_row = p.residual + (((size_t)n * p.OH + h) * (size_t)p.OW + w) * (size_t)p.cout;
     }
-    const int cout_store = min((p.cout + 7) & ~7, p.out_ld);
+    // pitch padding (columns cout..out_ld-1) is written as zeros so the output row is fully defined
+    const int cout_store = p.out_mode == 1 ? p.cout : p.out_ld;
 
     mbar_wait(tmem_full_bar, 0);
     __syncwarp();

@@ -63,6 +63,7 @@ struct GemmW {   // device-side parameters of one GEMM layer
 struct Step {
   std::string stage;
   std::function<int(cudaStream_t)> run;
+  std::string kind;   // kernel family, for per-kernel timing ("conv_gemm", "roialign", ...)
 };
 
 uint16_t f2bf(float f) {  // round to nearest even
@@ -93,12 +94,19 @@ struct mrcnn_engine {
   // timing
   std::vector<std::string> stage_names;
   std::vector<cudaEvent_t> stage_events;  // stage_names.size() + 1
+  bool profiling = false;
+  std::vector<cudaEvent_t> step_events;   // steps.size() + 1, recorded when profiling
+  std::vector<std::string> kind_names;    // scratch for kernel_times()
   // unmold scratch
   void* unmold_ws = nullptr;
   size_t unmold_ws_bytes = 0;
   size_t mask_out_bytes = 0;
   uint8_t* d_masks = nullptr;
   int32_t* d_windows = nullptr;
+  // preprocessing scratch (detect_maps)
+  void* pre_maps = nullptr; size_t pre_maps_bytes = 0;
+  void* pre_rgb = nullptr; size_t pre_rgb_bytes = 0;
+  void* pre_small = nullptr; size_t pre_small_bytes = 0;
 
   int meta_size() const { return 12 + cfg.num_classes; }
 };
@@ -350,7 +358,7 @@ int add_conv(mrcnn_engine* e, const std::string& stage, const std::string& wname
   rc = conv_plan_create(&d, in.p, g.w, g.scale, g.shift, residual, t.ptr, 0, plan);
   if (rc) return rc;
   e->flops += plan->flops;
-  e->steps.push_back({stage, [plan](cudaStream_t st) { return conv_plan_launch(plan, st); }});
+  e->steps.push_back({stage, [plan](cudaStream_t st) { return conv_plan_launch(plan, st); }, "conv_gemm"});
   if (out) {
     out->p = static_cast<__nv_bfloat16*>(t.ptr);
     out->n = in.n;
@@ -378,7 +386,7 @@ int build_graph(mrcnn_engine* e) {
   {
     const float* img = static_cast<const float*>(t_img.ptr);
     __nv_bfloat16* col = static_cast<__nv_bfloat16*>(t_col.ptr);
-    e->steps.push_back({"backbone", [=](cudaStream_t st) { return launch_stem_im2col(img, B, S, col, st); }});
+    e->steps.push_back({"backbone", [=](cudaStream_t st) { return launch_stem_im2col(img, B, S, col, st); }, "stem_im2col"});
   }
   Act x = {static_cast<__nv_bfloat16*>(t_col.ptr), 1, 1, B * (S / 2) * (S / 2), 192};
   Act c1;
@@ -389,7 +397,7 @@ int build_graph(mrcnn_engine* e) {
   {
     const __nv_bfloat16* src = c1.p;
     __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(t_pool.ptr);
-    e->steps.push_back({"backbone", [=](cudaStream_t st) { return launch_maxpool3x3s2(src, B, S / 2, S / 2, 64, dst, st); }});
+    e->steps.push_back({"backbone", [=](cudaStream_t st) { return launch_maxpool3x3s2(src, B, S / 2, S / 2, 64, dst, st); }, "maxpool"});
   }
   x = {static_cast<__nv_bfloat16*>(t_pool.ptr), B, S / 4, S / 4, 64};
 
@@ -430,7 +438,7 @@ int build_graph(mrcnn_engine* e) {
     const __nv_bfloat16* src = P[5].p;
     __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(t6.ptr);
     const int h5 = P[5].h, w5 = P[5].w;
-    e->steps.push_back({"fpn", [=](cudaStream_t st) { return launch_subsample2(src, B, h5, w5, PY, dst, st); }});
+    e->steps.push_back({"fpn", [=](cudaStream_t st) { return launch_subsample2(src, B, h5, w5, PY, dst, st); }, "subsample"});
     P[6] = {dst, B, h6, w6, PY};
   }
   for (int l = 2; l <= 6; ++l) e->feat[l - 2] = P[l].h;
@@ -455,7 +463,7 @@ int build_graph(mrcnn_engine* e) {
     float* rc_ = static_cast<float*>(t_rc.ptr);
     float* rb_ = static_cast<float*>(t_rb.ptr);
     const float* hd = static_cast<const float*>(head);
-    e->steps.push_back({"rpn", [=](cudaStream_t st) { return launch_rpn_post(hd, 32, B, hw, apl, A, off, rc_, rb_, st); }});
+    e->steps.push_back({"rpn", [=](cudaStream_t st) { return launch_rpn_post(hd, 32, B, hw, apl, A, off, rc_, rb_, st); }, "rpn_post"});
     level_off += hw * apl;
   }
 
@@ -478,7 +486,7 @@ int build_graph(mrcnn_engine* e) {
     e->steps.push_back({"proposal", [=](cudaStream_t st) {
       return mrcnn_proposal_layer(rc_, rb_, an, 0, B, A, cc.pre_nms_limit, R, cc.rpn_nms_threshold, cc.rpn_bbox_std_dev,
                                   rois, tk, kp, kc, nullptr, 0, st);
-    }});
+    }, "proposal"});
   }
 
   // ---- class head --------------------------------------------------------------------------------
@@ -496,7 +504,7 @@ int build_graph(mrcnn_engine* e) {
     int32_t* lv = static_cast<int32_t*>(t_lvl.ptr);
     e->steps.push_back({"roialign", [=](cudaStream_t st) {
       return launch_pyramid_roi_align(fp.p, fp.h, fp.w, PY, MRCNN_DTYPE_BF16, rois, 4, B, R, PS, image_area, pooled, lv, st);
-    }});
+    }, "roialign"});
   }
   Act pooled = {static_cast<__nv_bfloat16*>(t_pooled.ptr), 1, 1, B * R, PS * PS * PY};
   Act fc1, fc2;
@@ -512,7 +520,7 @@ int build_graph(mrcnn_engine* e) {
     const float* hd = static_cast<const float*>(head);
     float* pc = static_cast<float*>(t_cls.ptr);
     float* pb = static_cast<float*>(t_bbox.ptr);
-    e->steps.push_back({"class_head", [=](cudaStream_t st) { return launch_class_post(hd, 32, B * R, NC, pc, pb, st); }});
+    e->steps.push_back({"class_head", [=](cudaStream_t st) { return launch_class_post(hd, 32, B * R, NC, pc, pb, st); }, "class_post"});
   }
 
   // ---- DetectionLayer ----------------------------------------------------------------------------
@@ -529,7 +537,7 @@ int build_graph(mrcnn_engine* e) {
     e->steps.push_back({"detection", [=](cudaStream_t st) {
       return mrcnn_detection_layer(rois, pc, pb, meta, ms, B, R, NC, D, cc.detection_min_confidence,
                                    cc.detection_nms_threshold, cc.bbox_std_dev, det, st);
-    }});
+    }, "detection"});
   }
 
   // ---- mask head ---------------------------------------------------------------------------------
@@ -540,7 +548,7 @@ int build_graph(mrcnn_engine* e) {
     void* pm = t_pm.ptr;
     e->steps.push_back({"roialign_mask", [=](cudaStream_t st) {
       return launch_pyramid_roi_align(fp.p, fp.h, fp.w, PY, MRCNN_DTYPE_BF16, det, 6, B, D, MP, image_area, pm, nullptr, st);
-    }});
+    }, "roialign"});
   }
   Act m = {static_cast<__nv_bfloat16*>(t_pm.ptr), B * D, MP, MP, PY};
   for (int i = 1; i <= 4; ++i) {
@@ -560,7 +568,7 @@ int build_graph(mrcnn_engine* e) {
     const float* lg = static_cast<const float*>(mlog);
     float* out = static_cast<float*>(t_mask.ptr);
     const size_t M = (size_t)B * D * 4 * MP * MP;
-    e->steps.push_back({"mask_head", [=](cudaStream_t st) { return launch_mask_post(lg, 8, M, NC, out, st); }});
+    e->steps.push_back({"mask_head", [=](cudaStream_t st) { return launch_mask_post(lg, 8, M, NC, out, st); }, "mask_post"});
   }
 
   // ---- stage table for timing / run_stage ----------------------------------------------------------
@@ -581,9 +589,12 @@ int run_steps(mrcnn_engine* e, const char* only_stage, bool timed) {
       MRCNN_CHECK_CUDA(cudaEventRecord(e->stage_events[si], e->stream));
       cur = s.stage;
     }
+    const size_t step_i = (size_t)(&s - &e->steps[0]);
+    if (e->profiling && !only_stage) MRCNN_CHECK_CUDA(cudaEventRecord(e->step_events[step_i], e->stream));
     int rc = s.run(e->stream);
     if (rc) return rc;
   }
+  if (e->profiling && !only_stage) MRCNN_CHECK_CUDA(cudaEventRecord(e->step_events[e->steps.size()], e->stream));
   if (timed) MRCNN_CHECK_CUDA(cudaEventRecord(e->stage_events[e->stage_names.size()], e->stream));
   return MRCNN_OK;
 }
@@ -636,9 +647,13 @@ extern "C" void mrcnn_engine_destroy(mrcnn_engine* e) {
   for (void* p : e->allocs) cudaFree(p);
   for (ConvPlan* p : e->plans) delete p;
   for (auto ev : e->stage_events) cudaEventDestroy(ev);
+  for (auto ev : e->step_events) cudaEventDestroy(ev);
   if (e->unmold_ws) cudaFree(e->unmold_ws);
   if (e->d_masks) cudaFree(e->d_masks);
   if (e->d_windows) cudaFree(e->d_windows);
+  if (e->pre_maps) cudaFree(e->pre_maps);
+  if (e->pre_rgb) cudaFree(e->pre_rgb);
+  if (e->pre_small) cudaFree(e->pre_small);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -820,32 +835,62 @@ extern "C" int mrcnn_engine_stage_times(const mrcnn_engine* e, int max_stages, c
 
 extern "C" double mrcnn_engine_flops(const mrcnn_engine* e) { return e ? e->flops : 0.0; }
 
-extern "C" int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, int molded_on_host,
-                                          const float* metas_host, const int* orig_hw, const int32_t* windows_host, int32_t* rois_host,
-                                          int32_t* class_ids_host, float* scores_host, int32_t* counts_host,
-                                          uint8_t* masks_host) {
-  MRCNN_REQUIRE(e && e->finalized, "detect_molded: engine not finalized");
-  MRCNN_REQUIRE(molded && metas_host && orig_hw && windows_host && rois_host && class_ids_host && scores_host &&
-                    counts_host && masks_host, "detect_molded: null pointer");
+extern "C" int mrcnn_engine_set_profiling(mrcnn_engine* e, int enable) {
+  MRCNN_REQUIRE(e && e->finalized, "set_profiling: engine not finalized");
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  if (enable && e->step_events.empty()) {
+    e->step_events.resize(e->steps.size() + 1);
+    for (auto& ev : e->step_events) MRCNN_CHECK_CUDA(cudaEventCreate(&ev));
+  }
+  e->profiling = enable != 0;
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_kernel_times(mrcnn_engine* e, int max_kinds, const char** names, float* ms, int* launches) {
+  MRCNN_REQUIRE(e && e->finalized && !e->step_events.empty(), "kernel_times: profiling was never enabled");
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+  e->kind_names.clear();
+  std::vector<float> tot;
+  std::vector<int> cnt;
+  for (size_t i = 0; i < e->steps.size(); ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, e->step_events[i], e->step_events[i + 1]) != cudaSuccess) {
+      mrcnn_set_error("kernel_times: no profiled predict has completed yet");
+      return MRCNN_ERR_INVALID;
+    }
+    size_t k = 0;
+    for (; k < e->kind_names.size(); ++k) if (e->kind_names[k] == e->steps[i].kind) break;
+    if (k == e->kind_names.size()) { e->kind_names.push_back(e->steps[i].kind); tot.push_back(0.f); cnt.push_back(0); }
+    tot[k] += t;
+    cnt[k] += 1;
+  }
+  const int n = (int)e->kind_names.size();
+  for (int k = 0; k < n && k < max_kinds; ++k) {
+    if (names) names[k] = e->kind_names[k].c_str();
+    if (ms) ms[k] = tot[k];
+    if (launches) launches[k] = cnt[k];
+  }
+  return n;
+}
+
+// ---- unmold + result fetch (shared by detect_molded / detect_maps) ---------------------------------
+static int ensure_scratch(mrcnn_engine* e, void** ptr, size_t* have, size_t need) {
+  if (*have >= need) return MRCNN_OK;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *have = 0;
+  MRCNN_CHECK_CUDA(cudaMalloc(ptr, need));
+  *have = need;
+  return MRCNN_OK;
+}
+
+static int unmold_internal(mrcnn_engine* e, const int* orig_hw, const int32_t* windows_host) {
   const mrcnn_engine_config& c = e->cfg;
   const int B = c.batch_size, D = c.detection_max_instances;
-  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
-  int rc = predict_internal(e, molded, molded_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, metas_host,
-                           cudaMemcpyHostToDevice);
-  if (rc) return rc;
-  // scratch (grown on demand)
-  const size_t ws = mrcnn_unmold_workspace_bytes(B, D);
-  if (e->unmold_ws_bytes < ws) {
-    if (e->unmold_ws) cudaFree(e->unmold_ws);
-    MRCNN_CHECK_CUDA(cudaMalloc(&e->unmold_ws, ws));
-    e->unmold_ws_bytes = ws;
-  }
+  RC(ensure_scratch(e, &e->unmold_ws, &e->unmold_ws_bytes, mrcnn_unmold_workspace_bytes(B, D)));
   const size_t mbytes = (size_t)B * orig_hw[0] * orig_hw[1] * D;
-  if (e->mask_out_bytes < mbytes) {
-    if (e->d_masks) cudaFree(e->d_masks);
-    MRCNN_CHECK_CUDA(cudaMalloc((void**)&e->d_masks, mbytes));
-    e->mask_out_bytes = mbytes;
-  }
+  RC(ensure_scratch(e, (void**)&e->d_masks, &e->mask_out_bytes, mbytes));
   if (!e->d_windows) MRCNN_CHECK_CUDA(cudaMalloc((void**)&e->d_windows, (size_t)B * 16));
   if (e->tensors.find("unmold_rois") == e->tensors.end()) {
     RC(new_tensor(e, "unmold_rois", DT_I32, (size_t)B * D * 4, nullptr, true));
@@ -855,21 +900,79 @@ extern "C" int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, 
   }
   MRCNN_CHECK_CUDA(cudaMemcpyAsync(e->d_windows, windows_host, (size_t)B * 16, cudaMemcpyHostToDevice, e->stream));
   const int image_hw[2] = {c.image_size, c.image_size};
+  return mrcnn_unmold_detections(static_cast<const float*>(e->tensors["detections"].ptr),
+                                 static_cast<const float*>(e->tensors["mrcnn_mask"].ptr), B, D, 2 * c.mask_pool_size,
+                                 2 * c.mask_pool_size, c.num_classes, orig_hw, image_hw, e->d_windows,
+                                 static_cast<int32_t*>(e->tensors["unmold_rois"].ptr),
+                                 static_cast<int32_t*>(e->tensors["unmold_class_ids"].ptr),
+                                 static_cast<float*>(e->tensors["unmold_scores"].ptr),
+                                 static_cast<int32_t*>(e->tensors["unmold_counts"].ptr), e->d_masks, e->unmold_ws,
+                                 e->unmold_ws_bytes, e->stream);
+}
+
+static int fetch_internal(mrcnn_engine* e, const int* orig_hw, int32_t* rois_host, int32_t* class_ids_host,
+                          float* scores_host, int32_t* counts_host, uint8_t* masks_host) {
+  const mrcnn_engine_config& c = e->cfg;
+  const size_t mbytes = (size_t)c.batch_size * orig_hw[0] * orig_hw[1] * c.detection_max_instances;
   Tensor& tr = e->tensors["unmold_rois"];
   Tensor& tc = e->tensors["unmold_class_ids"];
   Tensor& ts = e->tensors["unmold_scores"];
   Tensor& tn = e->tensors["unmold_counts"];
-  rc = mrcnn_unmold_detections(static_cast<const float*>(e->tensors["detections"].ptr),
-                               static_cast<const float*>(e->tensors["mrcnn_mask"].ptr), B, D, 2 * c.mask_pool_size,
-                               2 * c.mask_pool_size, c.num_classes, orig_hw, image_hw, e->d_windows,
-                               static_cast<int32_t*>(tr.ptr), static_cast<int32_t*>(tc.ptr), static_cast<float*>(ts.ptr),
-                               static_cast<int32_t*>(tn.ptr), e->d_masks, e->unmold_ws, e->unmold_ws_bytes, e->stream);
-  if (rc) return rc;
-  MRCNN_CHECK_CUDA(cudaMemcpyAsync(rois_host, tr.ptr, tr.bytes, cudaMemcpyDeviceToHost, e->stream));
-  MRCNN_CHECK_CUDA(cudaMemcpyAsync(class_ids_host, tc.ptr, tc.bytes, cudaMemcpyDeviceToHost, e->stream));
-  MRCNN_CHECK_CUDA(cudaMemcpyAsync(scores_host, ts.ptr, ts.bytes, cudaMemcpyDeviceToHost, e->stream));
-  MRCNN_CHECK_CUDA(cudaMemcpyAsync(counts_host, tn.ptr, tn.bytes, cudaMemcpyDeviceToHost, e->stream));
-  MRCNN_CHECK_CUDA(cudaMemcpyAsync(masks_host, e->d_masks, mbytes, cudaMemcpyDeviceToHost, e->stream));
+  if (rois_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(rois_host, tr.ptr, tr.bytes, cudaMemcpyDeviceToHost, e->stream));
+  if (class_ids_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(class_ids_host, tc.ptr, tc.bytes, cudaMemcpyDeviceToHost, e->stream));
+  if (scores_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(scores_host, ts.ptr, ts.bytes, cudaMemcpyDeviceToHost, e->stream));
+  if (counts_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(counts_host, tn.ptr, tn.bytes, cudaMemcpyDeviceToHost, e->stream));
+  if (masks_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(masks_host, e->d_masks, mbytes, cudaMemcpyDeviceToHost, e->stream));
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, int molded_on_host,
+                                          const float* metas_host, const int* orig_hw,
+                                          const int32_t* windows_host, int32_t* rois_host,
+                                          int32_t* class_ids_host, float* scores_host, int32_t* counts_host,
+                                          uint8_t* masks_host) {
+  MRCNN_REQUIRE(e && e->finalized, "detect_molded: engine not finalized");
+  MRCNN_REQUIRE(molded && metas_host && orig_hw && windows_host, "detect_molded: null pointer");
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  RC(predict_internal(e, molded, molded_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, metas_host,
+                      cudaMemcpyHostToDevice));
+  RC(unmold_internal(e, orig_hw, windows_host));
+  RC(fetch_internal(e, orig_hw, rois_host, class_ids_host, scores_host, counts_host, masks_host));
+  MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_detect_maps(mrcnn_engine* e, const float* maps, int maps_on_host, int map_h, int map_w,
+                                        const float* contrasts3, const float* mean_pixel3, int out_h, int out_w,
+                                        int top, int left, const float* metas_host, const int32_t* windows_host,
+                                        int32_t* rois_host, int32_t* class_ids_host, float* scores_host,
+                                        int32_t* counts_host, uint8_t* masks_host) {
+  MRCNN_REQUIRE(e && e->finalized, "detect_maps: engine not finalized");
+  MRCNN_REQUIRE(maps && contrasts3 && mean_pixel3 && metas_host && windows_host, "detect_maps: null pointer");
+  MRCNN_REQUIRE(map_h > 0 && map_w > 0, "detect_maps: empty maps");
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  const mrcnn_engine_config& c = e->cfg;
+  const int B = c.batch_size;
+  const size_t npx = (size_t)map_h * map_w;
+  RC(ensure_scratch(e, &e->pre_maps, &e->pre_maps_bytes, (size_t)B * npx * 4));
+  RC(ensure_scratch(e, &e->pre_rgb, &e->pre_rgb_bytes, (size_t)B * npx * 3));
+  RC(ensure_scratch(e, &e->pre_small, &e->pre_small_bytes, (size_t)B * (12 * 4 + 2 * 4)));
+  const float* d_maps = maps;
+  if (maps_on_host) {
+    MRCNN_CHECK_CUDA(cudaMemcpyAsync(e->pre_maps, maps, (size_t)B * npx * 4, cudaMemcpyHostToDevice, e->stream));
+    d_maps = static_cast<const float*>(e->pre_maps);
+  }
+  float* d_params = static_cast<float*>(e->pre_small);
+  int32_t* d_minmax = reinterpret_cast<int32_t*>(d_params + (size_t)B * 12);
+  uint8_t* d_rgb = static_cast<uint8_t*>(e->pre_rgb);
+  RC(mrcnn_zscale_params(d_maps, B, map_h, map_w, contrasts3, d_params, e->stream));
+  RC(mrcnn_stretch_to_rgb8(d_maps, d_params, B, map_h, map_w, d_rgb, d_minmax, e->stream));
+  float* d_img = static_cast<float*>(e->tensors["input_image"].ptr);
+  RC(mrcnn_resize_pad_mold(d_rgb, d_minmax, B, map_h, map_w, out_h, out_w, c.image_size, top, left, mean_pixel3, d_img, e->stream));
+  RC(predict_internal(e, d_img, cudaMemcpyDeviceToDevice, metas_host, cudaMemcpyHostToDevice));
+  const int orig_hw[2] = {map_h, map_w};
+  RC(unmold_internal(e, orig_hw, windows_host));
+  RC(fetch_internal(e, orig_hw, rois_host, class_ids_host, scores_host, counts_host, masks_host));
   MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
   return MRCNN_OK;
 }

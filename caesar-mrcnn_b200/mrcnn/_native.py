@@ -81,9 +81,14 @@ SIGNATURES = {
     "mrcnn_engine_write": (c_int, [c_void_p, ctypes.c_char_p, c_void_p, c_size_t]),
     "mrcnn_engine_detect_molded": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p]),
+    "mrcnn_engine_detect_maps": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mrcnn_engine_stream": (c_void_p, [c_void_p]),
     "mrcnn_engine_stage_times": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_float)]),
     "mrcnn_engine_flops": (ctypes.c_double, [c_void_p]),
+    "mrcnn_engine_set_profiling": (c_int, [c_void_p, c_int]),
+    "mrcnn_engine_kernel_times": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_float),
+                                          ctypes.POINTER(c_int)]),
 }
 
 _lib = None

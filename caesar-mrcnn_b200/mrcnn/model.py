@@ -124,6 +124,9 @@ class MaskRCNN(object):
         _native.check(lib.mrcnn_engine_create(ctypes.byref(cfg), int(self._device), ctypes.byref(handle)), "engine_create")
         self._engine = handle
         self._lib = lib
+        # everything this model launches (torch plumbing included) is ordered on the engine's stream
+        self._stream = torch.cuda.ExternalStream(lib.mrcnn_engine_stream(handle), device=int(self._device))
+        self._pinned = {}
         return self     # callers only use .predict() on it
 
     def __del__(self):
@@ -256,8 +259,11 @@ class MaskRCNN(object):
 
     def mold_inputs(self, images):
         """reference signature (mrcnn/model.py:2519-2556): numpy (molded_images, image_metas, windows)."""
-        molded, metas, windows = self._mold_inputs_device(images)
-        return molded.cpu().numpy(), metas, windows
+        torch = utils._torch()
+        with torch.cuda.stream(self._stream):
+            molded, metas, windows = self._mold_inputs_device(images)
+            out = molded.cpu().numpy()
+        return out, metas, windows
 
     # -- the graph ------------------------------------------------------------------------------
     def predict(self, inputs, verbose=0):
@@ -273,13 +279,13 @@ class MaskRCNN(object):
         B = self.config.BATCH_SIZE
         metas32 = np.ascontiguousarray(metas, dtype=np.float32)
         assert metas32.shape == (B, self.config.IMAGE_META_SIZE)
-        d_meta = torch.from_numpy(metas32).to("cuda:%d" % self._device)
-        if isinstance(molded, np.ndarray):
-            molded = torch.from_numpy(np.ascontiguousarray(molded, dtype=np.float32)).to("cuda:%d" % self._device)
-        assert tuple(molded.shape) == (B,) + tuple(int(v) for v in self.config.IMAGE_SHAPE), "molded images do not match IMAGE_SHAPE"
-        torch.cuda.current_stream().synchronize()
-        _native.check(self._lib.mrcnn_engine_predict(self._engine, _native.ptr(molded.contiguous()), _native.ptr(d_meta), 0, 0),
-                      "predict")
+        with torch.cuda.stream(self._stream):
+            d_meta = torch.from_numpy(metas32).to("cuda:%d" % self._device)
+            if isinstance(molded, np.ndarray):
+                molded = torch.from_numpy(np.ascontiguousarray(molded, dtype=np.float32)).to("cuda:%d" % self._device)
+            assert tuple(molded.shape) == (B,) + tuple(int(v) for v in self.config.IMAGE_SHAPE), "molded images do not match IMAGE_SHAPE"
+            _native.check(self._lib.mrcnn_engine_predict(self._engine, _native.ptr(molded.contiguous()), _native.ptr(d_meta), 0, 0),
+                          "predict")
 
     _TENSOR_SHAPES = None
 
@@ -325,36 +331,93 @@ class MaskRCNN(object):
         return {names[i].decode(): float(ms[i]) for i in range(n)}
 
     # -- detection ------------------------------------------------------------------------------
-    def _detect_device(self, molded_dev, metas, windows, orig_shapes):
-        """engine predict + device unmold -> list of result dicts (numpy views of pinned buffers)."""
+    def _result_buffers(self, H0, W0):
+        """Pinned host buffers for one batch of results. Fresh per call: the arrays handed back to
+        the caller are views of them (torch's caching host allocator recycles the memory later)."""
         torch = utils._torch()
         c = self.config
         B, D = c.BATCH_SIZE, c.DETECTION_MAX_INSTANCES
+        return (torch.empty((B, D, 4), dtype=torch.int32).pin_memory(), torch.empty((B, D), dtype=torch.int32).pin_memory(),
+                torch.empty((B, D), dtype=torch.float32).pin_memory(), torch.empty((B,), dtype=torch.int32).pin_memory(),
+                torch.empty((B, H0, W0, D), dtype=torch.uint8).pin_memory())
+
+    @staticmethod
+    def _results_from_buffers(bufs, B):
+        rois_n, cls_n, sc_n, cnt_n, m_n = [b.numpy() for b in bufs]
+        out = []
+        for i in range(B):
+            n = int(cnt_n[i])
+            out.append({"rois": rois_n[i, :n], "class_ids": cls_n[i, :n], "scores": sc_n[i, :n],
+                        "masks": m_n[i, :, :, :n].view(np.bool_)})
+        return out
+
+    def _detect_device(self, molded, metas, windows, orig_shapes):
+        """engine predict + device unmold -> list of result dicts (numpy views of pinned buffers)."""
+        torch = utils._torch()
         shapes = {tuple(s[:2]) for s in orig_shapes}
         if len(shapes) != 1:
             raise NotImplementedError("mrcnn (B200 build): detect() needs the images of one batch to share one original size")
+        if not self._weights_loaded:
+            raise RuntimeError("load_weights() / set_weights() must be called before predict/detect")
         H0, W0 = next(iter(shapes))
-        metas32 = torch.from_numpy(np.ascontiguousarray(metas, dtype=np.float32)).pin_memory()
-        wins = torch.from_numpy(np.ascontiguousarray(windows, dtype=np.int32))
-        rois = torch.empty((B, D, 4), dtype=torch.int32).pin_memory()
-        cls = torch.empty((B, D), dtype=torch.int32).pin_memory()
-        scores = torch.empty((B, D), dtype=torch.float32).pin_memory()
-        counts = torch.empty((B,), dtype=torch.int32).pin_memory()
-        masks = torch.empty((B, H0, W0, D), dtype=torch.uint8).pin_memory()
+        metas32 = np.ascontiguousarray(metas, dtype=np.float32)
+        wins = np.ascontiguousarray(windows, dtype=np.int32)
+        bufs = self._result_buffers(H0, W0)
         orig = (ctypes.c_int * 2)(int(H0), int(W0))
-        torch.cuda.current_stream().synchronize()
-        on_host = 0 if molded_dev.is_cuda else 1
-        _native.check(self._lib.mrcnn_engine_detect_molded(self._engine, _native.ptr(molded_dev), on_host, _native.ptr(metas32), orig,
-                                                           _native.ptr(wins), _native.ptr(rois), _native.ptr(cls),
-                                                           _native.ptr(scores), _native.ptr(counts), _native.ptr(masks)),
-                      "detect")
-        results = []
-        rois_n, cls_n, sc_n, cnt_n, m_n = rois.numpy(), cls.numpy(), scores.numpy(), counts.numpy(), masks.numpy()
-        for i in range(B):
-            n = int(cnt_n[i])
-            results.append({"rois": rois_n[i, :n], "class_ids": cls_n[i, :n], "scores": sc_n[i, :n],
-                            "masks": m_n[i, :, :, :n].view(np.bool_)})
-        return results
+        on_host = 0 if molded.is_cuda else 1
+        with torch.cuda.stream(self._stream):
+            _native.check(self._lib.mrcnn_engine_detect_molded(self._engine, _native.ptr(molded), on_host, metas32.ctypes.data, orig,
+                                                               wins.ctypes.data, *[_native.ptr(b) for b in bufs]), "detect")
+        return self._results_from_buffers(bufs, self.config.BATCH_SIZE)
+
+    def detect_maps(self, maps, zscale_contrasts=(0.25, 0.25, 0.25), device_only=False):
+        """Fast path from FITS-like maps (extension; the numpy contract of detect() is unchanged):
+        maps [BATCH_SIZE,H,W] float32 — numpy / pinned torch tensor (copied H2D) or a CUDA tensor —
+        -> read_fits stretch + mold + graph + unmold in one C-ABI call. Returns detect()-style dicts,
+        or None with device_only=True (results stay in the engine's 'unmold_*' tensors)."""
+        torch = utils._torch()
+        c = self.config
+        if not self._weights_loaded:
+            raise RuntimeError("load_weights() / set_weights() must be called before predict/detect")
+        if isinstance(maps, np.ndarray):
+            maps = torch.from_numpy(np.ascontiguousarray(maps, dtype=np.float32))
+        assert maps.dim() == 3 and maps.shape[0] == c.BATCH_SIZE and maps.dtype == torch.float32 and maps.is_contiguous()
+        H0, W0 = int(maps.shape[1]), int(maps.shape[2])
+        key = (H0, W0)
+        if key not in self._pinned:
+            scale, out_hw, top_left, window, _ = utils.square_geometry(H0, W0, c.IMAGE_MIN_DIM, c.IMAGE_MAX_DIM, c.IMAGE_MIN_SCALE,
+                                                                       c.IMAGE_RESIZE_MODE)
+            S = int(c.IMAGE_SHAPE[0])
+            meta = compose_image_meta(0, (H0, W0, 3), (S, S, 3), window, scale, np.zeros([c.NUM_CLASSES], dtype=np.int32))
+            metas32 = np.ascontiguousarray(np.stack([meta] * c.BATCH_SIZE), dtype=np.float32)
+            wins = np.ascontiguousarray(np.stack([window] * c.BATCH_SIZE), dtype=np.int32)
+            self._pinned[key] = (out_hw, top_left, metas32, wins)
+        out_hw, top_left, metas32, wins = self._pinned[key]
+        con = _native.float_array(list(zscale_contrasts))
+        mean = _native.float_array([float(v) for v in np.asarray(c.MEAN_PIXEL).reshape(-1)[:3]])
+        bufs = None if device_only else self._result_buffers(H0, W0)
+        outs = [None] * 5 if device_only else [_native.ptr(b) for b in bufs]
+        with torch.cuda.stream(self._stream):
+            _native.check(self._lib.mrcnn_engine_detect_maps(self._engine, _native.ptr(maps), 0 if maps.is_cuda else 1, H0, W0, con, mean,
+                                                             int(out_hw[0]), int(out_hw[1]), int(top_left[0]), int(top_left[1]),
+                                                             metas32.ctypes.data, wins.ctypes.data, *outs), "detect_maps")
+        return None if device_only else self._results_from_buffers(bufs, c.BATCH_SIZE)
+
+    def kernel_times(self):
+        """{family: (ms, launches)} of the last predict; needs set_profiling(True) beforehand."""
+        names = (ctypes.c_char_p * 32)()
+        ms = (ctypes.c_float * 32)()
+        cnt = (ctypes.c_int * 32)()
+        n = self._lib.mrcnn_engine_kernel_times(self._engine, 32, names, ms, cnt)
+        if n < 0:
+            _native.check(n, "kernel_times")
+        return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def set_profiling(self, on=True):
+        _native.check(self._lib.mrcnn_engine_set_profiling(self._engine, 1 if on else 0), "set_profiling")
+
+    def flops_per_predict(self):
+        return float(self._lib.mrcnn_engine_flops(self._engine))
 
     def detect(self, images, verbose=0):
         """Runs the detection pipeline (reference: mrcnn/model.py:2623-2704).
@@ -366,7 +429,9 @@ class MaskRCNN(object):
             log("Processing {} images".format(len(images)))
             for image in images:
                 log("image", image)
-        molded, metas, windows = self._mold_inputs_device(images)
+        torch = utils._torch()
+        with torch.cuda.stream(self._stream):
+            molded, metas, windows = self._mold_inputs_device(images)
         return self._detect_device(molded, metas, windows, [im.shape for im in images])
 
     def detect_molded(self, molded_images, image_metas, verbose=0):

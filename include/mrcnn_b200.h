@@ -213,9 +213,25 @@ int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, int molded_
                                const int32_t* windows_host, int32_t* rois_host,
                                int32_t* class_ids_host, float* scores_host, int32_t* counts_host,
                                uint8_t* masks_host);
+/* The whole hot path from FITS-like maps in ONE call: maps [B,map_h,map_w] float32 (HOST when
+ * maps_on_host != 0, else DEVICE; NaN allowed) -> zscale/uint8 RGB (read_fits, mrcnn/utils.py:
+ * 1090-1208) -> resize to (out_h,out_w), pad at (top,left), minus mean (mold_inputs, mrcnn/model.py:
+ * 2519-2556) -> graph -> unmold against the original (map_h,map_w) frame.  metas / windows: HOST.
+ * Host result pointers may be NULL (all of them = results stay on the device, readable through
+ * mrcnn_engine_tensor "unmold_rois"/"unmold_class_ids"/"unmold_scores"/"unmold_counts").  Blocking. */
+int mrcnn_engine_detect_maps(mrcnn_engine* e, const float* maps, int maps_on_host, int map_h, int map_w,
+                             const float* contrasts3, const float* mean_pixel3, int out_h, int out_w,
+                             int top, int left, const float* metas_host, const int32_t* windows_host,
+                             int32_t* rois_host, int32_t* class_ids_host, float* scores_host,
+                             int32_t* counts_host, uint8_t* masks_host);
 void* mrcnn_engine_stream(const mrcnn_engine* e);
 /* per-stage device time of the last predict in milliseconds (CUDA events); names via index */
 int mrcnn_engine_stage_times(const mrcnn_engine* e, int max_stages, const char** names, float* ms);
+/* Per-kernel-family device time of the last predict (CUDA events recorded around every launch
+ * on the engine stream while profiling is enabled): returns the number of families; names[k] in
+ * {"conv_gemm","roialign","proposal","detection","stem_im2col","maxpool",...}. */
+int mrcnn_engine_set_profiling(mrcnn_engine* e, int enable);
+int mrcnn_engine_kernel_times(mrcnn_engine* e, int max_kinds, const char** names, float* ms, int* launches);
 /* FLOPs (2*M*N*K over all GEMM launches) of one predict at the configured batch */
 double mrcnn_engine_flops(const mrcnn_engine* e);
 

@@ -18,8 +18,6 @@ Two arithmetic modes:
                        y = acc*s + t.  Used for tight kernel-vs-oracle comparisons.
 parity: UNPINNED against TF/Keras (cannot run here); torch.nn.functional is the independent check.
 """
-import zlib
-
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -29,85 +27,9 @@ from . import graph_layers as GL
 BN_EPS = 1e-3
 
 
-# --------------------------------------------------------------------------------------------
-# layer inventory
-# --------------------------------------------------------------------------------------------
-
-def layer_specs(num_classes=4, fc_size=1024, pyramid=256):
-    """Ordered list of (layer_name, kind, kernel_shape) with kind in conv|bn|dense|deconv."""
-    specs = [("conv1", "conv", (7, 7, 3, 64)), ("bn_conv1", "bn", (64,))]
-    cin = 64
-    stages = [(2, "abc", (64, 64, 256)), (3, "abcd", (128, 128, 512)),
-              (4, "a" + "".join(chr(98 + i) for i in range(22)), (256, 256, 1024)),
-              (5, "abc", (512, 512, 2048))]
-    for stage, blocks, (f1, f2, f3) in stages:
-        for blk in blocks:
-            base = "res%d%s_branch" % (stage, blk)
-            bnb = "bn%d%s_branch" % (stage, blk)
-            specs += [(base + "2a", "conv", (1, 1, cin, f1)), (bnb + "2a", "bn", (f1,)),
-                      (base + "2b", "conv", (3, 3, f1, f2)), (bnb + "2b", "bn", (f2,)),
-                      (base + "2c", "conv", (1, 1, f2, f3)), (bnb + "2c", "bn", (f3,))]
-            if blk == "a":
-                specs += [(base + "1", "conv", (1, 1, cin, f3)), (bnb + "1", "bn", (f3,))]
-            cin = f3
-    for name, c in (("fpn_c5p5", 2048), ("fpn_c4p4", 1024), ("fpn_c3p3", 512), ("fpn_c2p2", 256)):
-        specs.append((name, "conv", (1, 1, c, pyramid)))
-    for name in ("fpn_p2", "fpn_p3", "fpn_p4", "fpn_p5"):
-        specs.append((name, "conv", (3, 3, pyramid, pyramid)))
-    specs += [("rpn_conv_shared", "conv", (3, 3, pyramid, 512)),
-              ("rpn_class_raw", "conv", (1, 1, 512, 6)),
-              ("rpn_bbox_pred", "conv", (1, 1, 512, 12))]
-    specs += [("mrcnn_class_conv1", "conv", (7, 7, pyramid, fc_size)),
-              ("mrcnn_class_bn1", "bn", (fc_size,)),
-              ("mrcnn_class_conv2", "conv", (1, 1, fc_size, fc_size)),
-              ("mrcnn_class_bn2", "bn", (fc_size,)),
-              ("mrcnn_class_logits", "dense", (fc_size, num_classes)),
-              ("mrcnn_bbox_fc", "dense", (fc_size, 4 * num_classes))]
-    for i in range(1, 5):
-        specs += [("mrcnn_mask_conv%d" % i, "conv", (3, 3, pyramid, pyramid)),
-                  ("mrcnn_mask_bn%d" % i, "bn", (pyramid,))]
-    specs += [("mrcnn_mask_deconv", "deconv", (2, 2, pyramid, pyramid)),
-              ("mrcnn_mask", "conv", (1, 1, pyramid, num_classes))]
-    return specs
-
-
-# per-layer gain on the He-normal std, tuned so that with inputs in 0..255 the pyramid has
-# std ~1-2, RPN/class logits std ~2 and box deltas std ~1 (a non-degenerate detect workload)
-_GAIN = {"conv1": 1.0 / 64.0, "fpn_c5p5": 0.12, "fpn_c4p4": 0.12, "fpn_c3p3": 0.2, "fpn_c2p2": 0.2,
-         "fpn_p": 0.6, "rpn_conv_shared": 0.7, "rpn_class_raw": 1.6, "rpn_bbox_pred": 0.8,
-         "mrcnn_class_logits": 1.5, "mrcnn_bbox_fc": 0.8, "mrcnn_mask": 1.5}
-
-
-def make_random_weights(seed=0, num_classes=4):
-    """Deterministic stand-in for share/mrcnn_weights.h5 (an unresolved LFS pointer).
-    Returns {layer_name: [arrays in Keras layer.weights order]} (float32)."""
-    out = {}
-    for name, kind, shape in layer_specs(num_classes):
-        rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
-        if kind == "bn":
-            c = shape[0]
-            gamma = rng.uniform(0.6, 1.0, c)
-            if name.endswith("_branch2c"):
-                gamma = rng.uniform(0.2, 0.4, c)      # keep the residual trunk from blowing up
-            beta = rng.normal(0.0, 0.1, c)
-            mean = rng.normal(0.0, 0.1, c)
-            var = rng.uniform(0.5, 1.5, c)
-            out[name] = [a.astype(np.float32) for a in (gamma, beta, mean, var)]
-        else:
-            if kind == "dense":
-                fan_in = shape[0]
-                cout = shape[1]
-            elif kind == "deconv":
-                fan_in = shape[3]
-                cout = shape[2]
-            else:
-                fan_in = shape[0] * shape[1] * shape[2]
-                cout = shape[3]
-            std = np.sqrt(2.0 / fan_in) * _GAIN.get(name, _GAIN.get(name.rstrip("0123456789"), 1.0))
-            k = rng.normal(0.0, std, shape)
-            b = rng.normal(0.0, 0.05, cout)
-            out[name] = [k.astype(np.float32), b.astype(np.float32)]
-    return out
+# layer inventory + seeded random weights live in synth.py (neutral workload generator shared with
+# bench.py); re-exported here for the tests
+from synth import layer_specs, make_random_weights  # noqa: E402,F401
 
 
 # --------------------------------------------------------------------------------------------
