@@ -8,9 +8,14 @@
 // :1042-1091 (mask head).  One CTA computes a 128 x BLOCK_N output tile:
 //   warp 0   : TMA producer (one lane)      — A box (64ch, tw, th, nb) per filter tap, B box (64, BLOCK_N)
 //   warp 1   : TMEM alloc + MMA issuer (one lane), tcgen05.commit releases ring slots
-//   warps 2-5: epilogue, warp (w%4) owns TMEM lanes 32*(w%4)..+31 = output rows
-// Two CTAs fit per SM (<= 100 KB smem, <= 256 TMEM columns each) so one CTA's epilogue overlaps the
-// other's main loop.
+//   warps 2-9: epilogue; warp w owns TMEM lanes 32*(w%4)..+31 (= output rows) and half of the
+//              tile's columns; per-channel scale/shift are staged in smem once per tile and the
+//              TMEM loads are software-pipelined against the math/stores of the previous chunk
+// PERSISTENT: one CTA per SM walks a static tile schedule (N fastest, so the CTAs that share an A
+// tile run at the same time and re-read it from L2).  The smem ring runs across tile boundaries and
+// the accumulator is double-buffered in TMEM (2 x BLOCK_N columns), so the TMA loads and MMAs of
+// tile i+1 overlap the epilogue of tile i — layers with K = 64..256 (1-4 k-blocks per tile) are
+// otherwise dominated by per-tile latency.
 #include <cuda.h>
 #include <mutex>
 #include "conv_gemm.cuh"
@@ -20,15 +25,17 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle-128B atom row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;        // TMA warp + MMA warp + 8 epilogue warps
+constexpr int EPI_THREADS = 256;
 
 template <int BLOCK_N> struct TileCfg {
-  static constexpr int STAGES = (BLOCK_N <= 64) ? 4 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int STAGES = (BLOCK_N <= 64) ? 8 : (BLOCK_N == 128 ? 6 : 4);
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int EPI_BYTES = 2 * 2 * BLOCK_N * 4;   // [acc][scale|shift][BLOCK_N] floats
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;   // double-buffered accumulator (64..512, power of two)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -125,10 +132,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 template <int BLOCK_N>
-__global__ void __launch_bounds__(GEMM_THREADS) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                                                                  const __grid_constant__ CUtensorMap tmap_b,
-                                                                  const ConvGemmParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                     const __grid_constant__ CUtensorMap tmap_b,
+                                                                     const ConvGemmParams p) {
   using Cfg = TileCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_raw[];
@@ -139,25 +150,26 @@ __global__ void __launch_bounds__(GEMM_THREADS) conv_gemm_kernel(const __grid_co
   const uint32_t bar_base = base_addr + STAGES * Cfg::STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 1));
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
+  float* s_affine = reinterpret_cast<float*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 256);   // [2][2][BLOCK_N]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x % p.n_tiles;   // N fastest: CTAs sharing an A tile are co-scheduled (L2 reuse)
-  const int m_tile = blockIdx.x / p.n_tiles;
-  const int tw_i = m_tile % p.tiles_w;
-  const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
-  const int tn_i = m_tile / (p.tiles_w * p.tiles_h);
-  const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.nb;
   const int num_kb = p.kh * p.kw * p.cin_blocks;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_nb;
+  const int num_tiles = m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 8);   // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
@@ -174,151 +186,199 @@ __global__ void __launch_bounds__(GEMM_THREADS) conv_gemm_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: runs ahead across tile boundaries, bounded only by the smem ring =====
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(p.tw * p.th * p.nb) * (BLOCK_K * 2);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const int tap = kb / p.cin_blocks;
-        const int cb = kb - tap * p.cin_blocks;
-        const int r = tap / p.kw, sx = tap - r * p.kw;
-        const uint32_t a_dst = base_addr + s * Cfg::STAGE_BYTES;
-        const uint32_t b_dst = a_dst + Cfg::A_BYTES;
-        mbar_expect_tx(full_bar(s), a_bytes + Cfg::B_BYTES);
-        tma_load_4d(a_dst, &tmap_a, full_bar(s), cb * BLOCK_K, w0 + sx - p.pad, h0 + r - p.pad, n0);
-        tma_load_2d(b_dst, &tmap_b, full_bar(s), kb * BLOCK_K, n_tile * BLOCK_N);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int tw_i = m_tile % p.tiles_w;
+        const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn_i = m_tile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.nb;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const int tap = kb / p.cin_blocks;
+          const int cb = kb - tap * p.cin_blocks;
+          const int r = tap / p.kw, sx = tap - r * p.kw;
+          const uint32_t a_dst = base_addr + s * Cfg::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+          mbar_expect_tx(full_bar(s), a_bytes + Cfg::B_BYTES);
+          tma_load_4d(a_dst, &tmap_a, full_bar(s), cb * BLOCK_K, w0 + sx - p.pad, h0 + r - p.pad, n0);
+          tma_load_2d(b_dst, &tmap_b, full_bar(s), kb * BLOCK_K, n_tile * BLOCK_N);
+        }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: alternates between the two TMEM accumulators =====
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BLOCK_N, M = 128
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                                  ((uint32_t)(BLOCK_M >> 4) << 24);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(full_bar(s), ph);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u;
+        const uint32_t aph = (tcount >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(acc), aph ^ 1u);      // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t a_addr = base_addr + s * Cfg::STAGE_BYTES;
-        const uint64_t da = make_sw128_desc(a_addr);
-        const uint64_t db = make_sw128_desc(a_addr + Cfg::A_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = base_addr + s * Cfg::STAGE_BYTES;
+          const uint64_t da = make_sw128_desc(a_addr);
+          const uint64_t db = make_sw128_desc(a_addr + Cfg::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the >>4 address field
-          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the >>4 address field
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));          // frees the ring slot once these MMAs have read it
         }
-        umma_commit(empty_bar(s));   // frees the ring slot once these MMAs have read it
+        umma_commit(tmem_full_bar(acc));      // accumulator complete
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
+    const int ew = warp - 2;         // 0..7
     const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;        // which half of the tile's columns
+    const int et = threadIdx.x - 64; // 0..255 within the epilogue group
     const int row = q * 32 + lane;   // output row inside the tile
-    int n, h, w;
-    bool row_ok;
-    if (p.flat) {
-      // 1x1 stride-1 layers tile the flattened pixel index; decode (n,h,w) from the real geometry
-      const long long m = (long long)m_tile * BLOCK_M + row;
-      row_ok = m < p.M;
-      const int hw = p.OH * p.OW;
-      n = (int)(m / hw);
-      const int rem = (int)(m - (long long)n * hw);
-      h = rem / p.OW;
-      w = rem - h * p.OW;
-    } else {
-      const int per_img = p.tw * p.th;
-      const int ni = row / per_img;
-      const int rem = row - ni * per_img;
-      const int hi = rem / p.tw;
-      const int wi = rem - hi * p.tw;
-      n = n0 + ni; h = h0 + hi; w = w0 + wi;
-      row_ok = (row < per_img * p.nb) && (n < p.N) && (h < p.OH) && (w < p.OW);
-    }
-    const int col_base = n_tile * BLOCK_N;
-    size_t out_off;
-    int ch_base = col_base;          // channel index used for scale/shift and the store column
-    if (p.out_mode == 1) {
-      const int tap = col_base / p.cout;
-      ch_base = col_base - tap * p.cout;
-      const int oi = tap >> 1, oj = tap & 1;
-      out_off = (((size_t)n * (2 * p.OH) + (2 * h + oi)) * (size_t)(2 * p.OW) + (2 * w + oj)) * (size_t)p.out_ld;
-    } else {
-      out_off = (((size_t)n * p.OH + h) * (size_t)p.OW + w) * (size_t)p.out_ld;
-    }
-    const __nv_bfloat16* res_row = nullptr;
-    if (p.residual != nullptr && row_ok) {
-      if (p.res_up2)
-        res_row = p.residual + (((size_t)n * (p.OH >> 1) + (h >> 1)) * (size_t)(p.OW >> 1) + (w >> 1)) * (size_t)p.cout;
-      else
-        res_row = p.residual + (((size_t)n * p.OH + h) * (size_t)p.OW + w) * (size_t)p.cout;
-    }
-    // pitch padding (columns cout..out_ld-1) is written as zeros so the output row is fully defined
-    const int cout_store = p.out_mode == 1 ? p.cout : p.out_ld;
+    constexpr int COLS_PER_WARP = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
+    const bool has_cols = (BLOCK_N >= 64) || (half == 0);
+    const int c_begin = (BLOCK_N >= 64) ? half * COLS_PER_WARP : 0;
+    const int cout_store = p.out_mode == 1 ? p.cout : p.out_ld;   // pitch padding is written as zeros
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1u;
+      const uint32_t aph = (tcount >> 1) & 1u;
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int col_base = n_tile * BLOCK_N;
+      int ch_base = col_base;          // channel index used for scale/shift and the store column
+      int tap = 0;
+      if (p.out_mode == 1) {
+        tap = col_base / p.cout;
+        ch_base = col_base - tap * p.cout;
+      }
+      // stage this tile's per-channel affine in smem (overlaps the MMAs of the tile)
+      float* t_scale = s_affine + acc * (2 * BLOCK_N);
+      float* t_shift = t_scale + BLOCK_N;
+      for (int c = et; c < BLOCK_N; c += EPI_THREADS) {
+        const int ch = ch_base + c;
+        t_scale[c] = ch < p.cout ? __ldg(p.scale + ch) : 0.f;
+        t_shift[c] = ch < p.cout ? __ldg(p.shift + ch) : 0.f;
+      }
+      int n, h, w;
+      bool row_ok;
+      if (p.flat) {
+        // 1x1 stride-1 layers tile the flattened pixel index; decode (n,h,w) from the real geometry
+        const long long m = (long long)m_tile * BLOCK_M + row;
+        row_ok = m < p.M;
+        const int hw = p.OH * p.OW;
+        n = (int)(m / hw);
+        const int rem = (int)(m - (long long)n * hw);
+        h = rem / p.OW;
+        w = rem - h * p.OW;
+      } else {
+        const int tw_i = m_tile % p.tiles_w;
+        const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn_i = m_tile / (p.tiles_w * p.tiles_h);
+        const int per_img = p.tw * p.th;
+        const int ni = row / per_img;
+        const int rem = row - ni * per_img;
+        const int hi = rem / p.tw;
+        const int wi = rem - hi * p.tw;
+        n = tn_i * p.nb + ni; h = th_i * p.th + hi; w = tw_i * p.tw + wi;
+        row_ok = (row < per_img * p.nb) && (n < p.N) && (h < p.OH) && (w < p.OW);
+      }
+      size_t out_off;
+      if (p.out_mode == 1) {
+        const int oi = tap >> 1, oj = tap & 1;
+        out_off = (((size_t)n * (2 * p.OH) + (2 * h + oi)) * (size_t)(2 * p.OW) + (2 * w + oj)) * (size_t)p.out_ld;
+      } else {
+        out_off = (((size_t)n * p.OH + h) * (size_t)p.OW + w) * (size_t)p.out_ld;
+      }
+      const __nv_bfloat16* res_row = nullptr;
+      if (p.residual != nullptr && row_ok) {
+        if (p.res_up2)
+          res_row = p.residual + (((size_t)n * (p.OH >> 1) + (h >> 1)) * (size_t)(p.OW >> 1) + (w >> 1)) * (size_t)p.cout;
+        else
+          res_row = p.residual + (((size_t)n * p.OH + h) * (size_t)p.OW + w) * (size_t)p.cout;
+      }
+      // affine staged by all 256 epilogue threads -> visible to all of them
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 
-    mbar_wait(tmem_full_bar, 0);
-    __syncwarp();
-    tcgen05_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      tmem_ld_wait();
-      if (row_ok) {
+      mbar_wait(tmem_full_bar(acc), aph);
+      __syncwarp();
+      tcgen05_fence_after();
+      if (has_cols) {
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + (uint32_t)c_begin;
+        uint32_t vbuf[2][32];
+        tmem_ld_32x32b_x32(t_addr, vbuf[0]);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {   // groups of 8 columns
-          const int ch = ch_base + c + g * 8;
-          if (ch < cout_store) {
-            float o[8];
-            if (ch + 8 <= p.cout) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + ch));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + ch + 4));
-              const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.shift + ch));
-              const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.shift + ch + 4));
-              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-              const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        for (int ci = 0; ci < COLS_PER_WARP / 32; ++ci) {
+          tmem_ld_wait();                                   // chunk ci has landed
+          if (ci + 1 < COLS_PER_WARP / 32) tmem_ld_32x32b_x32(t_addr + (uint32_t)(32 * (ci + 1)), vbuf[(ci + 1) & 1]);
+          const uint32_t* v = vbuf[ci & 1];
+          const int c = c_begin + 32 * ci;                  // column inside the tile
+          if (row_ok) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) o[k] = fmaf(__uint_as_float(v[g * 8 + k]), sc[k], sh[k]);
-              if (res_row != nullptr) {
-                const uint4 rr = __ldg(reinterpret_cast<const uint4*>(res_row + ch));
-                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+            for (int g = 0; g < 4; ++g) {   // groups of 8 columns
+              const int ch = ch_base + c + g * 8;
+              if (ch < cout_store) {
+                float o[8];
+                const float4 s0 = *reinterpret_cast<const float4*>(t_scale + c + g * 8);
+                const float4 s1 = *reinterpret_cast<const float4*>(t_scale + c + g * 8 + 4);
+                const float4 t0 = *reinterpret_cast<const float4*>(t_shift + c + g * 8);
+                const float4 t1 = *reinterpret_cast<const float4*>(t_shift + c + g * 8 + 4);
+                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  o[2 * k] += __uint_as_float(rw[k] << 16);
-                  o[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
+                for (int k = 0; k < 8; ++k) o[k] = fmaf(__uint_as_float(v[g * 8 + k]), sc[k], sh[k]);
+                if (res_row != nullptr) {
+                  if (ch + 8 <= p.cout) {
+                    const uint4 rr = __ldg(reinterpret_cast<const uint4*>(res_row + ch));
+                    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      o[2 * k] += __uint_as_float(rw[k] << 16);
+                      o[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
+                    }
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                      if (ch + k < p.cout) o[k] += __bfloat162float(res_row[ch + k]);
+                  }
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
+                }
+                if (p.out_f32) {
+                  float* dst = static_cast<float*>(p.out) + out_off + ch;
+                  *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                  *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                } else {
+                  __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + out_off + ch;
+                  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                              pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
                 }
               }
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int cc = ch + k;
-                float val = 0.f;
-                if (cc < p.cout) {
-                  val = fmaf(__uint_as_float(v[g * 8 + k]), __ldg(p.scale + cc), __ldg(p.shift + cc));
-                  if (res_row != nullptr) val += __bfloat162float(res_row[cc]);
-                }
-                o[k] = val;
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
-            }
-            if (p.out_f32) {
-              float* dst = static_cast<float*>(p.out) + out_off + ch;
-              *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-              *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
-            } else {
-              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + out_off + ch;
-              *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
             }
           }
         }
       }
+      // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
     }
   }
   tcgen05_fence_before();
@@ -439,7 +499,11 @@ template <int BN> int launch_tile(const ConvPlan* plan, cudaStream_t st) {
     MRCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done[dev] = true;
   }
-  conv_gemm_kernel<BN><<<plan->grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(plan->tmap_a, plan->tmap_b, plan->p);
+  static int num_sms = 0;
+  if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned tiles = plan->grid.x;
+  const unsigned grid = tiles < (unsigned)num_sms ? tiles : (unsigned)num_sms;   // one persistent CTA per SM
+  conv_gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(plan->tmap_a, plan->tmap_b, plan->p);
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;
@@ -475,12 +539,16 @@ int conv_plan_create(const mrcnn_conv_desc* d, const void* x, const void* w, con
   ConvGemmParams& p = plan->p;
   const int cout_total = d->out_mode == 1 ? 4 * d->cout : d->cout;
   if (block_n == 0) {
-    if (d->out_mode == 1) block_n = 128;
-    else if (cout_total <= 32) block_n = 32;
+    // widest tile that still leaves >= 2 tiles per SM (fewer A re-reads, less per-tile overhead)
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long m_tiles_est = ((long long)d->n * OH * OW + BLOCK_M - 1) / BLOCK_M;
+    if (cout_total <= 32) block_n = 32;
     else if (cout_total <= 64) block_n = 64;
+    else if (cout_total % 256 == 0 && m_tiles_est * (cout_total / 256) >= 2LL * sms) block_n = 256;
     else block_n = 128;
   }
-  MRCNN_REQUIRE(block_n == 32 || block_n == 64 || block_n == 128, "conv2d: block_n must be 32/64/128");
+  MRCNN_REQUIRE(block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256, "conv2d: block_n must be 32/64/128/256");
   if (d->out_mode == 1) MRCNN_REQUIRE(d->cout % block_n == 0, "conv2d: deconv cout %% block_n != 0");
   plan->block_n = block_n;
 
@@ -555,6 +623,7 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t st) {
     case 32: return launch_tile<32>(plan, st);
     case 64: return launch_tile<64>(plan, st);
     case 128: return launch_tile<128>(plan, st);
+    case 256: return launch_tile<256>(plan, st);
   }
   mrcnn_set_error("conv2d: bad block_n %d", plan->block_n);
   return MRCNN_ERR_INVALID;

@@ -33,7 +33,7 @@ struct DetSmem {
   Box4 refined[DET_MAX_N];
   Box4 cboxes[DET_MAX_N];
   float score[DET_MAX_N];
-  HeapEntry heap[DET_MAX_N];
+  __align__(16) HeapEntry heap[DET_MAX_N + 2];   // 1-indexed
   unsigned long long sortbuf[DET_MAX_N];
   int cls[DET_MAX_N];
   uint16_t ixs[DET_MAX_N];
@@ -164,16 +164,16 @@ __global__ void __launch_bounds__(DET_THREADS, 1) detection_kernel(DetParams p) 
         HeapEntry e;
         e.score = s.score[s.ixs[r]];
         e.id = r;
-        s.heap[r] = e;
+        s.heap[r + 1] = e;
       }
       __syncthreads();
-      if (tid == 0) heap_pop_order_serial(s.heap, n_c, /*presorted_desc=*/false, s.order);
+      if (tid == 0) heap_push_all_serial(s.heap, n_c);
     } else {
       for (int r = tid; r < n_c; r += nt)
         s.order[r] = (uint16_t)(~(uint32_t)(s.sortbuf[r] & 0xffffffffull));
     }
     __syncthreads();
-    const int cnt = block_nms(s.cboxes, s.order, n_c, D, p.thr, s.removed, s.selected, &s.sc);
+    const int cnt = block_nms(s.cboxes, s.order, n_c, D, p.thr, s.removed, s.selected, &s.sc, any_tie ? s.heap : nullptr);
     __syncthreads();
     for (int r = tid; r < cnt; r += nt) s.nmskeep[s.ixs[s.order[s.selected[r]]]] = 1;
     __syncthreads();

@@ -64,6 +64,8 @@ struct Step {
   std::string stage;
   std::function<int(cudaStream_t)> run;
   std::string kind;   // kernel family, for per-kernel timing ("conv_gemm", "roialign", ...)
+  std::string label;  // output tensor / layer name
+  double flops = 0;
 };
 
 uint16_t f2bf(float f) {  // round to nearest even
@@ -358,7 +360,7 @@ int add_conv(mrcnn_engine* e, const std::string& stage, const std::string& wname
   rc = conv_plan_create(&d, in.p, g.w, g.scale, g.shift, residual, t.ptr, 0, plan);
   if (rc) return rc;
   e->flops += plan->flops;
-  e->steps.push_back({stage, [plan](cudaStream_t st) { return conv_plan_launch(plan, st); }, "conv_gemm"});
+  e->steps.push_back({stage, [plan](cudaStream_t st) { return conv_plan_launch(plan, st); }, "conv_gemm", out_name, plan->flops});
   if (out) {
     out->p = static_cast<__nv_bfloat16*>(t.ptr);
     out->n = in.n;
@@ -843,6 +845,23 @@ extern "C" int mrcnn_engine_set_profiling(mrcnn_engine* e, int enable) {
     for (auto& ev : e->step_events) MRCNN_CHECK_CUDA(cudaEventCreate(&ev));
   }
   e->profiling = enable != 0;
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_step_info(mrcnn_engine* e, int index, const char** label, const char** kind, float* ms, double* flops) {
+  MRCNN_REQUIRE(e && e->finalized, "step_info: engine not finalized");
+  if (index < 0 || index >= (int)e->steps.size()) return MRCNN_ERR_NOTFOUND;
+  const Step& s = e->steps[index];
+  if (label) *label = s.label.empty() ? s.kind.c_str() : s.label.c_str();
+  if (kind) *kind = s.kind.c_str();
+  if (flops) *flops = s.flops;
+  if (ms) {
+    *ms = -1.f;
+    if (!e->step_events.empty()) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, e->step_events[index], e->step_events[index + 1]) == cudaSuccess) *ms = t;
+    }
+  }
   return MRCNN_OK;
 }
 

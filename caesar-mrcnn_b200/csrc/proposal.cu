@@ -158,30 +158,29 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
   }
   __syncthreads();
 
-  // ---- 5. pop order (identity unless scores tie) ----------------------------------------------
-  HeapEntry* heap = reinterpret_cast<HeapEntry*>(r0);                  // [K]
-  uint16_t* order = reinterpret_cast<uint16_t*>(heap + K);             // [K]
+  // ---- 5. pop order: identity unless scores tie, else popped lazily from the emulated heap ------
+  HeapEntry* heap = reinterpret_cast<HeapEntry*>(r0);                  // 1-indexed: [K+2], 16-byte aligned
+  uint16_t* order = reinterpret_cast<uint16_t*>(heap + ((K + 2 + 1) & ~1));   // [K]
   uint16_t* selected = order + ((K + 1) & ~1);                          // [R]
   uint32_t* removed = reinterpret_cast<uint32_t*>(selected + ((R + 1) & ~1));
   bool tie = false;
   for (int q = tid; q + 1 < K; q += nt) tie |= (s_scores[q] == s_scores[q + 1]);
   const int any_tie = __syncthreads_or(tie ? 1 : 0);
   if (any_tie) {
+    // pushing the (already sorted) scores in order never sifts up: the array IS the initial heap
     for (int q = tid; q < K; q += nt) {
       HeapEntry e;
       e.score = s_scores[q];
       e.id = q;
-      heap[q] = e;
+      heap[q + 1] = e;
     }
-    __syncthreads();
-    if (tid == 0) heap_pop_order_serial(heap, K, /*presorted_desc=*/true, order);
   } else {
     for (int q = tid; q < K; q += nt) order[q] = (uint16_t)q;
   }
   __syncthreads();
 
   // ---- 6. NMS + output ------------------------------------------------------------------------
-  const int count = block_nms(boxes, order, K, R, p.thr, removed, selected, sc);
+  const int count = block_nms(boxes, order, K, R, p.thr, removed, selected, sc, any_tie ? heap : nullptr);
   __syncthreads();
   float4* out = reinterpret_cast<float4*>(p.rois + (size_t)b * R * 4);
   for (int r = tid; r < R; r += nt) {
@@ -207,8 +206,8 @@ int next_pow2(int v) {
 size_t prop_smem_bytes(int K, int R, int* r0_bytes) {
   const int Kpad = next_pow2(K);
   size_t a = (size_t)Kpad * 8;
-  size_t bsz = (size_t)K * sizeof(HeapEntry) + (size_t)((K + 1) & ~1) * 2 + (size_t)((R + 1) & ~1) * 2 +
-               (size_t)((K + 31) / 32 + 2) * 4;
+  size_t bsz = (size_t)((K + 2 + 1) & ~1) * sizeof(HeapEntry) + (size_t)((K + 1) & ~1) * 2 + (size_t)((R + 1) & ~1) * 2 +
+               (size_t)((K + 31) / 32 + 2) * 4 + 16;
   size_t r0 = a > bsz ? a : bsz;
   r0 = (r0 + 15) & ~(size_t)15;
   *r0_bytes = (int)r0;

@@ -87,6 +87,8 @@ SIGNATURES = {
     "mrcnn_engine_stage_times": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_float)]),
     "mrcnn_engine_flops": (ctypes.c_double, [c_void_p]),
     "mrcnn_engine_set_profiling": (c_int, [c_void_p, c_int]),
+    "mrcnn_engine_step_info": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p),
+                                       ctypes.POINTER(c_float), ctypes.POINTER(ctypes.c_double)]),
     "mrcnn_engine_kernel_times": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_float),
                                           ctypes.POINTER(c_int)]),
 }

@@ -413,6 +413,19 @@ class MaskRCNN(object):
             _native.check(n, "kernel_times")
         return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
 
+    def step_table(self):
+        """[(label, kernel family, ms, flops)] per launch of the last profiled predict."""
+        out, i = [], 0
+        while True:
+            label, kind = ctypes.c_char_p(), ctypes.c_char_p()
+            ms, fl = ctypes.c_float(), ctypes.c_double()
+            if self._lib.mrcnn_engine_step_info(self._engine, i, ctypes.byref(label), ctypes.byref(kind), ctypes.byref(ms),
+                                                ctypes.byref(fl)) != 0:
+                break
+            out.append((label.value.decode(), kind.value.decode(), float(ms.value), float(fl.value)))
+            i += 1
+        return out
+
     def set_profiling(self, on=True):
         _native.check(self._lib.mrcnn_engine_set_profiling(self._engine, 1 if on else 0), "set_profiling")
 

@@ -1,7 +1,10 @@
 #!/bin/bash
 # scratch: development GPU run
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_conv.py -q -m gpu > gpurun_out/conv.log 2>&1; echo "conv exit $?" >> gpurun_out/conv.log
-timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/bench.err
-tail -3 gpurun_out/conv.log; tail -5 gpurun_out/smoke.log; cat gpurun_out/bench.log; tail -20 gpurun_out/bench.err
+timeout 900 python -m pytest tests/test_gpu_conv.py -q -m gpu -x > gpurun_out/conv.log 2>&1; echo "conv exit $?" >> gpurun_out/conv.log
+tail -25 gpurun_out/conv.log
+if grep -q "conv exit 0" gpurun_out/conv.log; then
+timeout 900 python -m pytest tests/test_gpu_engine.py -q -m gpu -x > gpurun_out/tests.log 2>&1; echo "tests exit $?" >> gpurun_out/tests.log
+timeout 600 python tools/layer_table.py 64 > gpurun_out/layer_table.txt 2>&1; echo "table exit $?" >> gpurun_out/layer_table.txt
+tail -5 gpurun_out/tests.log; grep -v "res4[b-v]" gpurun_out/layer_table.txt
+fi

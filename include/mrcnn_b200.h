@@ -232,6 +232,9 @@ int mrcnn_engine_stage_times(const mrcnn_engine* e, int max_stages, const char**
  * {"conv_gemm","roialign","proposal","detection","stem_im2col","maxpool",...}. */
 int mrcnn_engine_set_profiling(mrcnn_engine* e, int enable);
 int mrcnn_engine_kernel_times(mrcnn_engine* e, int max_kinds, const char** names, float* ms, int* launches);
+/* one launch of the plan: label (output tensor), kernel family, device ms of the last profiled
+ * predict (-1 if none) and GEMM FLOPs; returns NOTFOUND past the last launch */
+int mrcnn_engine_step_info(mrcnn_engine* e, int index, const char** label, const char** kind, float* ms, double* flops);
 /* FLOPs (2*M*N*K over all GEMM launches) of one predict at the configured batch */
 double mrcnn_engine_flops(const mrcnn_engine* e);
 

@@ -87,6 +87,12 @@ CASES = {
     "rpn_head_f32_padded": dict(n=2, h=16, w=16, cin=512, cout=18, k=1, out_f32=True, out_ld=32),
     "fc_12544": dict(n=1, h=1, w=300, cin=12544, cout=1024, k=1, relu=True),
     "mask_logits_f32": dict(n=2, h=28, w=28, cin=256, cout=4, k=1, out_f32=True, out_ld=8),
+    # many tiles per persistent CTA (ring + TMEM double buffer wrap several times), 256-wide tiles
+    "1x1_many_tiles_bn256": dict(n=16, h=64, w=64, cin=128, cout=256, k=1, relu=True, residual=True),
+    "1x1_many_tiles_k64": dict(n=8, h=64, w=64, cin=64, cout=64, k=1, relu=True),
+    "3x3_mask_head_many_bn256": dict(n=200, h=14, w=14, cin=256, cout=256, k=3, relu=True),
+    "deconv_many_bn256": dict(n=100, h=14, w=14, cin=256, cout=256, k=1, relu=True, deconv=True),
+    "3x3_p2_like": dict(n=4, h=64, w=64, cin=256, cout=512, k=3, relu=True),
 }
 
 
