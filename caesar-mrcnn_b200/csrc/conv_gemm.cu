@@ -314,19 +314,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       }
       // affine staged by all 256 epilogue threads -> visible to all of them
       asm volatile("bar.sync 1, 256;" ::: "memory");
-
-      mbar_wait(tmem_full_bar(acc), aph);
-      __syncwarp();
-      tcgen05_fence_after();
       if (has_cols) {
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + (uint32_t)c_begin;
         uint32_t vbuf[2][32];
+        uint4 rbuf[2][4];     // residual of the chunk, fetched one chunk ahead (scattered 16-byte loads)
+        const bool res_vec = (res_row != nullptr);
+        auto load_residual = [&](int ci, uint4* r) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int ch = ch_base + c_begin + 32 * ci + g * 8;
+            r[g] = (res_vec && ch + 8 <= p.cout) ? __ldg(reinterpret_cast<const uint4*>(res_row + ch)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        };
+        load_residual(0, rbuf[0]);                            // before the accumulator is even ready
+        mbar_wait(tmem_full_bar(acc), aph);
+        __syncwarp();
+        tcgen05_fence_after();
         tmem_ld_32x32b_x32(t_addr, vbuf[0]);
 #pragma unroll
         for (int ci = 0; ci < COLS_PER_WARP / 32; ++ci) {
           tmem_ld_wait();                                   // chunk ci has landed
-          if (ci + 1 < COLS_PER_WARP / 32) tmem_ld_32x32b_x32(t_addr + (uint32_t)(32 * (ci + 1)), vbuf[(ci + 1) & 1]);
+          if (ci + 1 < COLS_PER_WARP / 32) {
+            tmem_ld_32x32b_x32(t_addr + (uint32_t)(32 * (ci + 1)), vbuf[(ci + 1) & 1]);
+            load_residual(ci + 1, rbuf[(ci + 1) & 1]);
+          }
           const uint32_t* v = vbuf[ci & 1];
+          const uint4* rr4 = rbuf[ci & 1];
           const int c = c_begin + 32 * ci;                  // column inside the tile
           if (row_ok) {
 #pragma unroll
@@ -344,8 +357,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 for (int k = 0; k < 8; ++k) o[k] = fmaf(__uint_as_float(v[g * 8 + k]), sc[k], sh[k]);
                 if (res_row != nullptr) {
                   if (ch + 8 <= p.cout) {
-                    const uint4 rr = __ldg(reinterpret_cast<const uint4*>(res_row + ch));
-                    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+                    const uint32_t rw[4] = {rr4[g].x, rr4[g].y, rr4[g].z, rr4[g].w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                       o[2 * k] += __uint_as_float(rw[k] << 16);
@@ -374,6 +386,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             }
           }
         }
+      } else {
+        mbar_wait(tmem_full_bar(acc), aph);
+        __syncwarp();
+        tcgen05_fence_after();
       }
       // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
       tcgen05_fence_before();

@@ -40,42 +40,45 @@ __device__ __forceinline__ int roi_level(float y1, float x1, float y2, float x2,
   return min(5, max(2, lvl));
 }
 
-template <typename T> struct Vec;  // 16-byte channel vector
+template <typename T> struct Vec;  // 16-byte channel vector, kept raw in registers until the lerp
 template <> struct Vec<float> {
   static constexpr int N = 4;
-  __device__ static void load(const float* p, float* v) {
-    float4 t = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-  }
+  typedef float4 Raw;
+  __device__ static Raw load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ static void unpack(const Raw& t, float* v) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   __device__ static void store(float* p, const float* v) {
     __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
   }
 };
 template <> struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
-  __device__ static void load(const __nv_bfloat16* p, float* v) {
-    uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
-    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[2 * i] = __uint_as_float(w[i] << 16);
-      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
+  typedef uint4 Raw;
+  __device__ static Raw load(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ static void unpack(const Raw& t, float* v) {
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xffff0000u);
+    v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xffff0000u);
   }
   __device__ static void store(__nv_bfloat16* p, const float* v) {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-      w[i] = *reinterpret_cast<uint32_t*>(&h);
-    }
-    __stcs(reinterpret_cast<uint4*>(p), make_uint4(w[0], w[1], w[2], w[3]));
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    __stcs(reinterpret_cast<uint4*>(p), make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                   *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3)));
   }
 };
+
+// One CTA per ROI.  The P sample rows / columns of the crop are computed once per ROI into shared
+// memory (tf.image.crop_and_resize coordinates, float32, left-to-right evaluation); then each warp
+// takes output pixels round-robin with one lane per 16-byte channel vector, so a pixel is 4 coalesced
+// 512-byte reads (bf16, C=256) and one coalesced 512-byte streaming store.
+constexpr int ROI_MAX_P = 32;
 
 template <typename T>
 __global__ void __launch_bounds__(256) roialign_kernel(RoiParams p) {
   constexpr int VN = Vec<T>::N;
+  __shared__ int s_lo[2][ROI_MAX_P], s_hi[2][ROI_MAX_P];   // [0] = rows (top/bottom), [1] = cols (left/right); -1 = outside
+  __shared__ float s_w[2][ROI_MAX_P];                      // lerp weights
   const int roi = blockIdx.x;  // b*N + n
   const int b = roi / p.N;
   const float* bp = p.boxes + (size_t)roi * p.box_stride;
@@ -86,43 +89,59 @@ __global__ void __launch_bounds__(256) roialign_kernel(RoiParams p) {
   const int H = p.H[li], W = p.W[li], C = p.C, P = p.P;
   const T* feat = static_cast<const T*>(p.feat[li]) + (size_t)b * H * W * C;
   T* out = static_cast<T*>(p.out) + (size_t)roi * P * P * C;
-  const float Hm1 = (float)(H - 1), Wm1 = (float)(W - 1);
-  // tf.image.crop_and_resize coordinates (float32, left-to-right evaluation)
-  const float hs = (P > 1) ? __fdiv_rn(__fmul_rn(__fsub_rn(y2, y1), Hm1), (float)(P - 1)) : 0.f;
-  const float ws = (P > 1) ? __fdiv_rn(__fmul_rn(__fsub_rn(x2, x1), Wm1), (float)(P - 1)) : 0.f;
-  const int cv = C / VN;
-  const int items = P * P * cv;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int pix = it / cv;
-    const int c0 = (it - pix * cv) * VN;
-    const int iy = pix / P, ix = pix - iy * P;
-    const float in_y = (P > 1) ? __fadd_rn(__fmul_rn(y1, Hm1), __fmul_rn((float)iy, hs))
-                               : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(y1, y2)), Hm1);
-    const float in_x = (P > 1) ? __fadd_rn(__fmul_rn(x1, Wm1), __fmul_rn((float)ix, ws))
-                               : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(x1, x2)), Wm1);
-    float o[VN];
-    const bool valid = (in_y >= 0.f) && (in_y <= Hm1) && (in_x >= 0.f) && (in_x <= Wm1);
-    if (valid) {
-      const float ty = floorf(in_y), by = ceilf(in_y);
-      const float lx0 = floorf(in_x), rx = ceilf(in_x);
-      const float ly = __fsub_rn(in_y, ty), lx = __fsub_rn(in_x, lx0);
-      const int t = (int)ty, bt = (int)by, l = (int)lx0, r = (int)rx;
-      float tl[VN], tr[VN], bl[VN], br[VN];
-      Vec<T>::load(feat + ((size_t)t * W + l) * C + c0, tl);
-      Vec<T>::load(feat + ((size_t)t * W + r) * C + c0, tr);
-      Vec<T>::load(feat + ((size_t)bt * W + l) * C + c0, bl);
-      Vec<T>::load(feat + ((size_t)bt * W + r) * C + c0, br);
-#pragma unroll
-      for (int k = 0; k < VN; ++k) {
-        const float top = __fadd_rn(tl[k], __fmul_rn(__fsub_rn(tr[k], tl[k]), lx));
-        const float bot = __fadd_rn(bl[k], __fmul_rn(__fsub_rn(br[k], bl[k]), lx));
-        o[k] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+  if (threadIdx.x < 2 * ROI_MAX_P) {
+    const int axis = threadIdx.x / ROI_MAX_P, i = threadIdx.x % ROI_MAX_P;
+    if (i < P) {
+      const float a1 = axis == 0 ? y1 : x1, a2 = axis == 0 ? y2 : x2;
+      const float Dm1 = (float)((axis == 0 ? H : W) - 1);
+      const float sc = (P > 1) ? __fdiv_rn(__fmul_rn(__fsub_rn(a2, a1), Dm1), (float)(P - 1)) : 0.f;
+      const float in = (P > 1) ? __fadd_rn(__fmul_rn(a1, Dm1), __fmul_rn((float)i, sc))
+                               : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(a1, a2)), Dm1);
+      int lo = -1, hi = -1;
+      float wgt = 0.f;
+      if ((in >= 0.f) && (in <= Dm1)) {
+        const float f = floorf(in);
+        lo = (int)f;
+        hi = (int)ceilf(in);
+        wgt = __fsub_rn(in, f);
       }
-    } else {
-#pragma unroll
-      for (int k = 0; k < VN; ++k) o[k] = 0.f;
+      s_lo[axis][i] = lo;
+      s_hi[axis][i] = hi;
+      s_w[axis][i] = wgt;
     }
-    Vec<T>::store(out + (size_t)pix * C + c0, o);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int pix = warp; pix < P * P; pix += nwarps) {
+    const int iy = pix / P, ix = pix - iy * P;
+    const int t = s_lo[0][iy], bt = s_hi[0][iy], l = s_lo[1][ix], r = s_hi[1][ix];
+    const float ly = s_w[0][iy], lx = s_w[1][ix];
+    const bool valid = (t >= 0) && (l >= 0);
+    const T* ptl = feat + ((size_t)t * W + l) * C;
+    const T* ptr_ = feat + ((size_t)t * W + r) * C;
+    const T* pbl = feat + ((size_t)bt * W + l) * C;
+    const T* pbr = feat + ((size_t)bt * W + r) * C;
+    T* po = out + (size_t)pix * C;
+    for (int c0 = lane * VN; c0 < C; c0 += 32 * VN) {
+      float o[VN];
+      if (valid) {
+        float a[VN], bq[VN], c[VN], d[VN];
+        Vec<T>::unpack(Vec<T>::load(ptl + c0), a);
+        Vec<T>::unpack(Vec<T>::load(ptr_ + c0), bq);
+        Vec<T>::unpack(Vec<T>::load(pbl + c0), c);
+        Vec<T>::unpack(Vec<T>::load(pbr + c0), d);
+#pragma unroll
+        for (int k = 0; k < VN; ++k) {
+          const float top = __fadd_rn(a[k], __fmul_rn(__fsub_rn(bq[k], a[k]), lx));
+          const float bot = __fadd_rn(c[k], __fmul_rn(__fsub_rn(d[k], c[k]), lx));
+          o[k] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < VN; ++k) o[k] = 0.f;
+      }
+      Vec<T>::store(po + c0, o);
+    }
   }
 }
 
@@ -148,6 +167,7 @@ int launch_pyramid_roi_align(const void* const* feature_maps, const int* feat_h,
                              float image_area, void* pooled, int32_t* levels, cudaStream_t st) {
   MRCNN_REQUIRE(feature_maps && feat_h && feat_w && boxes && pooled, "pyramid_roi_align: null pointer");
   MRCNN_REQUIRE(batch > 0 && num_boxes > 0 && pool_size >= 1, "pyramid_roi_align: empty input");
+  MRCNN_REQUIRE(pool_size <= ROI_MAX_P, "pyramid_roi_align: pool_size %d > %d", pool_size, ROI_MAX_P);
   MRCNN_REQUIRE(dtype == MRCNN_DTYPE_F32 || dtype == MRCNN_DTYPE_BF16, "pyramid_roi_align: dtype must be f32 or bf16");
   const int vn = dtype == MRCNN_DTYPE_F32 ? 4 : 8;
   MRCNN_REQUIRE(channels % vn == 0, "pyramid_roi_align: channels=%d must be a multiple of %d", channels, vn);

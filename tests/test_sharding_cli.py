@@ -1,0 +1,70 @@
+"""CPU: sharded-run host logic (gloo, world_size 2) and the CLI's argument handling."""
+import os
+import sys
+
+import pytest
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "caesar-mrcnn_b200"))
+    from mrcnn import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 4096 + 3
+    start, stop = sharding.shard_range(n, rank, world)
+    done = sum(c for _, c in sharding.batches(start, stop, 64))
+    counts = sharding.gather_counts(done)
+    tmax = sharding.max_over_ranks(10.0 + rank)
+    dist.barrier()
+    with open(os.path.join(out_dir, "r%d.txt" % rank), "w") as f:
+        f.write("%d %d %s %.1f" % (start, stop, ",".join(map(str, counts)), tmax))
+    dist.destroy_process_group()
+
+
+def test_shard_ranges_cover_everything_once():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "caesar-mrcnn_b200"))
+    from mrcnn import sharding
+    for n in (0, 1, 63, 64, 4096, 4099):
+        for world in (1, 2, 4, 8):
+            seen = []
+            for r in range(world):
+                a, b = sharding.shard_range(n, r, world)
+                seen += list(range(a, b))
+            assert seen == list(range(n))
+    assert sharding.batches(10, 150, 64) == [(10, 64), (74, 64), (138, 12)]
+    with pytest.raises(ValueError):
+        sharding.shard_range(10, 2, 2)
+
+
+def test_two_rank_gloo_run(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = open(tmp_path / "r0.txt").read().split()
+    r1 = open(tmp_path / "r1.txt").read().split()
+    assert (int(r0[0]), int(r0[1]), int(r1[0]), int(r1[1])) == (0, 2050, 2050, 4099)
+    assert r0[2] == r1[2] == "2050,2049"
+    assert r0[3] == r1[3] == "11.0"          # max over ranks, identical everywhere
+
+
+def test_cli_argument_validation(tmp_path, golden_dir):
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "caesar-mrcnn_b200", "scripts", "run.py")
+    spec = importlib.util.spec_from_file_location("b200_run", path)
+    run = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(run)
+    fits = os.path.join(golden_dir, "galaxy0002.fits")
+    ok = run.parse_args(["detect", "--image", fits, "--random_weights", "0"])
+    assert run.validate_args(ok) == 0
+    cfg = run.make_config(ok)
+    assert cfg.NUM_CLASSES == 4 and cfg.CLASS_NAMES == ["bkg", "sidelobe", "source", "galaxy"]
+    assert cfg.IMAGE_META_SIZE == 16 and list(cfg.IMAGE_SHAPE) == [256, 256, 3] and cfg.BATCH_SIZE == 1
+    assert cfg.RPN_ANCHOR_SCALES == (4, 8, 16, 32, 64) and cfg.DETECTION_MIN_CONFIDENCE == 0 and cfg.RPN_NMS_THRESHOLD == 0.7
+    assert run.main(["train"]) == 1
+    assert run.main(["detect", "--image", "/nonexistent.fits", "--weights", "w.h5"]) == 1
+    assert run.main(["detect", "--image", fits]) == 1                              # no weights
+    assert run.main(["detect", "--image", fits, "--random_weights", "0", "--grayimg"]) == 1
+    assert run.main(["detect", "--image", fits, "--random_weights", "0", "--backbone", "resnet50"]) == 1
+    assert run.main(["test", "--weights", "w.h5"]) == 1                            # no datalist
