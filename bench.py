@@ -247,12 +247,22 @@ def main():
     value = world * B * args.steps / (ms_total / 1e3)
 
     # ---- end to end: pinned host maps in, host results out, every step -------------------------------
+    # software-pipelined through the public API: batch i+1 is queued (H2D + compute) while the
+    # device->host copy of batch i drains on the copy stream; every step's results are on the host
+    # (and turned into detect()-style dicts) before the timed region ends
     e2e_results = [None]
+    pending = [None]
 
     def e2e_step(i):
-        e2e_results[0] = model.detect_maps(host_sets[i % n_sets])
+        h = model.detect_maps_async(host_sets[i % n_sets])
+        if pending[0] is not None:
+            e2e_results[0] = pending[0].result()
+        pending[0] = h
+        if i == args.steps - 1:
+            e2e_results[0] = pending[0].result()
+            pending[0] = None
     for i in range(2):
-        e2e_step(i)
+        e2e_results[0] = model.detect_maps(host_sets[i % n_sets])
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     D = 100

@@ -100,6 +100,16 @@ __device__ inline void heap_push_all_serial(HeapEntry* h, int n) {
   }
 }
 
+__device__ __forceinline__ uint4 lds128(const void* p) {
+  // volatile asm: the loads of one look-ahead step are issued back to back, never sunk behind the
+  // data-dependent selects (the compiler otherwise predicates them and serialises the latencies)
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+
 // priority_queue::top + pop: std::pop_heap (__adjust_heap: the hole sinks to a leaf always taking
 // the right child unless it is strictly smaller, then the former last element sifts up) + pop_back.
 __device__ inline int heap_pop(HeapEntry* h, int& len_ref) {
@@ -110,21 +120,42 @@ __device__ inline int heap_pop(HeapEntry* h, int& len_ref) {
   len_ref = len;
   if (len == 0) return top_id;
   int c = 1;
-  // two levels per step while all four grandchildren exist (3 independent 16-byte loads in flight)
+  // three levels per step while all eight great-grandchildren exist (7 independent 16-byte loads)
+  while (8 * c + 7 <= len) {
+    const uint4 k0 = lds128(&h[2 * c]);
+    const uint4 g0 = lds128(&h[4 * c]);
+    const uint4 g1 = lds128(&h[4 * c + 2]);
+    const uint4 q0 = lds128(&h[8 * c]);
+    const uint4 q1 = lds128(&h[8 * c + 2]);
+    const uint4 q2 = lds128(&h[8 * c + 4]);
+    const uint4 q3 = lds128(&h[8 * c + 6]);
+    const bool r1 = !(__uint_as_float(k0.z) < __uint_as_float(k0.x));
+    const uint4 g = r1 ? g1 : g0;
+    const bool r2 = !(__uint_as_float(g.z) < __uint_as_float(g.x));
+    const uint4 qa = r2 ? q1 : q0, qb = r2 ? q3 : q2;
+    const uint4 q = r1 ? qb : qa;
+    const bool r3 = !(__uint_as_float(q.z) < __uint_as_float(q.x));
+    const int c1 = 2 * c + (r1 ? 1 : 0);
+    const int c2 = 2 * c1 + (r2 ? 1 : 0);
+    *reinterpret_cast<uint2*>(&h[c]) = r1 ? make_uint2(k0.z, k0.w) : make_uint2(k0.x, k0.y);
+    *reinterpret_cast<uint2*>(&h[c1]) = r2 ? make_uint2(g.z, g.w) : make_uint2(g.x, g.y);
+    *reinterpret_cast<uint2*>(&h[c2]) = r3 ? make_uint2(q.z, q.w) : make_uint2(q.x, q.y);
+    c = 2 * c2 + (r3 ? 1 : 0);
+  }
   while (4 * c + 3 <= len) {
-    const uint4 kids = *reinterpret_cast<const uint4*>(&h[2 * c]);
-    const uint4 g0 = *reinterpret_cast<const uint4*>(&h[4 * c]);
-    const uint4 g1 = *reinterpret_cast<const uint4*>(&h[4 * c + 2]);
-    const bool right = !(__uint_as_float(kids.z) < __uint_as_float(kids.x));
-    const uint4 g = right ? g1 : g0;
-    const bool gright = !(__uint_as_float(g.z) < __uint_as_float(g.x));
-    const int cc = 2 * c + (right ? 1 : 0);
-    *reinterpret_cast<uint2*>(&h[c]) = right ? make_uint2(kids.z, kids.w) : make_uint2(kids.x, kids.y);
-    *reinterpret_cast<uint2*>(&h[cc]) = gright ? make_uint2(g.z, g.w) : make_uint2(g.x, g.y);
-    c = 2 * cc + (gright ? 1 : 0);
+    const uint4 k0 = lds128(&h[2 * c]);
+    const uint4 g0 = lds128(&h[4 * c]);
+    const uint4 g1 = lds128(&h[4 * c + 2]);
+    const bool r1 = !(__uint_as_float(k0.z) < __uint_as_float(k0.x));
+    const uint4 g = r1 ? g1 : g0;
+    const bool r2 = !(__uint_as_float(g.z) < __uint_as_float(g.x));
+    const int c1 = 2 * c + (r1 ? 1 : 0);
+    *reinterpret_cast<uint2*>(&h[c]) = r1 ? make_uint2(k0.z, k0.w) : make_uint2(k0.x, k0.y);
+    *reinterpret_cast<uint2*>(&h[c1]) = r2 ? make_uint2(g.z, g.w) : make_uint2(g.x, g.y);
+    c = 2 * c1 + (r2 ? 1 : 0);
   }
   while (2 * c + 1 <= len) {
-    const uint4 kids = *reinterpret_cast<const uint4*>(&h[2 * c]);
+    const uint4 kids = lds128(&h[2 * c]);
     const bool right = !(__uint_as_float(kids.z) < __uint_as_float(kids.x));
     *reinterpret_cast<uint2*>(&h[c]) = right ? make_uint2(kids.z, kids.w) : make_uint2(kids.x, kids.y);
     c = 2 * c + (right ? 1 : 0);
@@ -142,38 +173,35 @@ __device__ inline int heap_pop(HeapEntry* h, int& len_ref) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Block-wide greedy NMS over candidates taken in pop order, 64 at a time:
+// Block-wide greedy NMS over candidates taken in pop order, 64 at a time, LAZILY: a chunk's 64
+// candidates are tested against the boxes selected so far (kept list in shared memory) only when
+// the chunk is reached, so the work is ~64 x |selected| per chunk and stops with the NMS itself
+// (TF stops at max_out picks) instead of pre-suppressing all n candidates for every pick.
 //   (0) if a heap is given, thread 0 pops the next 64 candidate ids (exact TF order under ties),
-//   (1) 64x64 intra-chunk suppression matrix in shared memory (all threads),
-//   (2) one thread resolves the chunk greedily against the `removed` bitmap,
-//   (3) all threads suppress later candidates against the boxes kept in this chunk: each thread
-//       keeps up to NMS_JB of its candidates in registers per pass and streams the kept boxes.
+//   (1) all threads: candidate k (16 threads each) vs the kept list -> suppressed flags, and the
+//       64x64 intra-chunk suppression matrix,
+//   (2) warp 0 gathers the alive mask; lane 0 resolves the chunk greedily,
+//   (3) the newly kept boxes are appended to the kept list.
 // Equivalent to TF's "pop best, suppress if IoU with any selected box > thr".
-// For later positions the heap has not been popped yet, so step (3) works on CANDIDATE IDS in
-// sorted order (pos == id when no heap is given): `removed` is indexed by candidate id.
 // boxes[id] = candidate box; order[p] = candidate id of pop position p; selected[] receives pop
-// positions.  Returns the number selected (<= max_out).
+// positions.  kept_box / kept_area: shared arrays of max_out entries.  Returns the number selected.
+// Requires blockDim.x == 1024.
 // ---------------------------------------------------------------------------------------------
 struct NmsScratch {
   unsigned long long M[64];
   NBox chunk[64];
-  float4 kept_box[64];
-  float kept_area[64];
+  unsigned char sup[64];
   unsigned long long kept_bits;
   int count;
   int heap_len;
 };
 
-constexpr int NMS_JB = 3;
-
 __device__ inline int block_nms(const Box4* boxes, uint16_t* order, int n, int max_out, float thr,
-                                uint32_t* removed /* ceil(n/32)+2 words, by candidate id */, uint16_t* selected,
-                                NmsScratch* sc, HeapEntry* lazy_heap) {
+                                float4* kept_box, float* kept_area, uint16_t* selected, NmsScratch* sc,
+                                HeapEntry* lazy_heap) {
   const int tid = threadIdx.x;
   const int nt = blockDim.x;
   const int lane = tid & 31;
-  const int nwords = (n + 31) / 32 + 2;
-  for (int i = tid; i < nwords; i += nt) removed[i] = 0;
   if (tid == 0) {
     sc->count = 0;
     sc->heap_len = n;
@@ -190,12 +218,10 @@ __device__ inline int block_nms(const Box4* boxes, uint16_t* order, int n, int m
       }
       __syncthreads();
     }
-    int my_id = -1;
     if (tid < 64) {
       NBox nb;
       if (tid < n_in) {
-        my_id = order[base + tid];
-        nb = normalise_box(boxes[my_id]);
+        nb = normalise_box(boxes[order[base + tid]]);
       } else {
         nb.ymin = nb.xmin = nb.ymax = nb.xmax = 0.f;
         nb.area = -1.f;
@@ -204,24 +230,42 @@ __device__ inline int block_nms(const Box4* boxes, uint16_t* order, int n, int m
       sc->M[tid] = 0ull;
     }
     __syncthreads();
+    {   // (1a) candidate k = tid/16 against the kept list, 16 threads striding over it
+      const int k = tid >> 4, sub = tid & 15;
+      const NBox cb = sc->chunk[k];
+      bool sup = false;
+      if (cb.area > 0.f) {
+        for (int r = sub; r < count; r += 16) {
+          const float4 kb = kept_box[r];
+          const float ih = __fsub_rn(fminf(kb.z, cb.ymax), fmaxf(kb.x, cb.ymin));
+          const float iw = __fsub_rn(fminf(kb.w, cb.xmax), fmaxf(kb.y, cb.xmin));
+          if (ih > 0.f && iw > 0.f) {
+            const float ka = kept_area[r];
+            const float inter = __fmul_rn(ih, iw);
+            if (ka > 0.f && inter != 0.0f) {
+              const float uni = __fsub_rn(__fadd_rn(ka, cb.area), inter);
+              if (__fdiv_rn(inter, uni) > thr) {
+                sup = true;
+                break;
+              }
+            }
+          }
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, sup);
+      if (sub == 0) sc->sup[k] = ((bal >> (lane & 16)) & 0xffffu) ? 1 : 0;
+    }
+    // (1b) intra-chunk suppression matrix
     for (int p = tid; p < 64 * 64; p += nt) {
       const int i = p >> 6, j = p & 63;
       if (j > i && j < n_in && iou_gt(sc->chunk[i], sc->chunk[j], thr)) atomicOr(&sc->M[i], 1ull << j);
     }
     __syncthreads();
-    if (tid < 32) {
-      // alive mask of this chunk: bit k = candidate order[base+k] not yet removed
-      unsigned long long alive = 0ull;
-      for (int k = lane; k < n_in; k += 32) {
-        const int id = order[base + k];
-        if (!((removed[id >> 5] >> (id & 31)) & 1u)) alive |= 1ull << k;
-      }
-      alive |= __shfl_xor_sync(0xffffffffu, alive, 16);
-      alive |= __shfl_xor_sync(0xffffffffu, alive, 8);
-      alive |= __shfl_xor_sync(0xffffffffu, alive, 4);
-      alive |= __shfl_xor_sync(0xffffffffu, alive, 2);
-      alive |= __shfl_xor_sync(0xffffffffu, alive, 1);
+    if (tid < 32) {   // (2)
+      const unsigned lo = __ballot_sync(0xffffffffu, lane < n_in && !sc->sup[lane]);
+      const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < n_in && !sc->sup[lane + 32]);
       if (lane == 0) {
+        unsigned long long alive = (unsigned long long)lo | ((unsigned long long)hi << 32);
         unsigned long long kept = 0ull;
         int c = sc->count;
         while (alive && c < max_out) {
@@ -237,64 +281,14 @@ __device__ inline int block_nms(const Box4* boxes, uint16_t* order, int n, int m
     }
     __syncthreads();
     const unsigned long long kept = sc->kept_bits;
-    count = sc->count;
-    const int nk = __popcll(kept);
-    if (tid < 64) {
-      // the chunk's own candidates are done: mark them removed so step (3) of later chunks skips them
-      if (my_id >= 0) atomicOr(&removed[my_id >> 5], 1u << (my_id & 31));
-      if ((kept >> tid) & 1ull) {
-        const int r = __popcll(kept & ((1ull << tid) - 1ull));
-        const NBox nb = sc->chunk[tid];
-        sc->kept_box[r] = make_float4(nb.ymin, nb.xmin, nb.ymax, nb.xmax);
-        sc->kept_area[r] = nb.area;
-      }
+    const int new_count = sc->count;
+    if (tid < 64 && ((kept >> tid) & 1ull)) {   // (3) append in selection order
+      const int r = count + __popcll(kept & ((1ull << tid) - 1ull));
+      const NBox nb = sc->chunk[tid];
+      kept_box[r] = make_float4(nb.ymin, nb.xmin, nb.ymax, nb.xmax);
+      kept_area[r] = nb.area;
     }
-    __syncthreads();
-    if (nk == 0 || count >= max_out || base + 64 >= n) continue;
-    // (3) suppress every not-yet-removed candidate id against the nk boxes kept in this chunk
-    for (int q0 = 0; q0 < n; q0 += nt * NMS_JB) {
-      NBox cand[NMS_JB];
-      bool live[NMS_JB], live0[NMS_JB];
-      bool any = false;
-#pragma unroll
-      for (int j = 0; j < NMS_JB; ++j) {
-        const int q = q0 + j * nt + tid;
-        live[j] = false;
-        if (q < n && !((removed[q >> 5] >> (q & 31)) & 1u)) {
-          cand[j] = normalise_box(boxes[q]);
-          live[j] = cand[j].area > 0.f;      // zero-area boxes are never suppressed
-        }
-        live0[j] = live[j];
-        any |= live[j];
-      }
-      if (__any_sync(0xffffffffu, any)) {
-        for (int r = 0; r < nk; ++r) {
-          const float4 kb = sc->kept_box[r];
-          const float ka = sc->kept_area[r];
-          if (!(ka > 0.f)) continue;
-#pragma unroll
-          for (int j = 0; j < NMS_JB; ++j) {
-            if (live[j]) {
-              const float ih = __fsub_rn(fminf(kb.z, cand[j].ymax), fmaxf(kb.x, cand[j].ymin));
-              const float iw = __fsub_rn(fminf(kb.w, cand[j].xmax), fmaxf(kb.y, cand[j].xmin));
-              if (ih > 0.f && iw > 0.f) {
-                const float inter = __fmul_rn(ih, iw);
-                if (inter != 0.0f) {
-                  const float uni = __fsub_rn(__fadd_rn(ka, cand[j].area), inter);
-                  if (__fdiv_rn(inter, uni) > thr) live[j] = false;   // suppressed
-                }
-              }
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NMS_JB; ++j) {
-        const int qw = q0 + j * nt + (tid & ~31);          // first candidate id of this warp's word
-        const unsigned bal = __ballot_sync(0xffffffffu, live0[j] && !live[j]);
-        if (lane == 0 && bal) removed[qw >> 5] |= bal;      // this warp owns word qw>>5 in this pass
-      }
-    }
+    count = new_count;
     __syncthreads();
   }
   return count;

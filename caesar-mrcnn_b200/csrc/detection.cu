@@ -39,7 +39,8 @@ struct DetSmem {
   uint16_t ixs[DET_MAX_N];
   uint16_t order[DET_MAX_N];
   uint16_t selected[DET_MAX_D];
-  uint32_t removed[DET_MAX_N / 32 + 2];
+  float4 kept_box[DET_MAX_D];
+  float kept_area[DET_MAX_D];
   unsigned char keepmask[DET_MAX_N];
   unsigned char nmskeep[DET_MAX_N];
   NmsScratch sc;
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(DET_THREADS, 1) detection_kernel(DetParams p) 
         s.order[r] = (uint16_t)(~(uint32_t)(s.sortbuf[r] & 0xffffffffull));
     }
     __syncthreads();
-    const int cnt = block_nms(s.cboxes, s.order, n_c, D, p.thr, s.removed, s.selected, &s.sc, any_tie ? s.heap : nullptr);
+    const int cnt = block_nms(s.cboxes, s.order, n_c, D, p.thr, s.kept_box, s.kept_area, s.selected, &s.sc, any_tie ? s.heap : nullptr);
     __syncthreads();
     for (int r = tid; r < cnt; r += nt) s.nmskeep[s.ixs[s.order[s.selected[r]]]] = 1;
     __syncthreads();

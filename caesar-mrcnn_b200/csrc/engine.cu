@@ -102,9 +102,17 @@ struct mrcnn_engine {
   // unmold scratch
   void* unmold_ws = nullptr;
   size_t unmold_ws_bytes = 0;
-  size_t mask_out_bytes = 0;
-  uint8_t* d_masks = nullptr;
   int32_t* d_windows = nullptr;
+  // result slots: unmold outputs are double-buffered so the D2H copy of step k (copy stream) can
+  // overlap the compute of step k+1 (main stream) in the asynchronous detect calls
+  struct ResultSlot {
+    void* masks = nullptr; size_t masks_bytes = 0;
+    int32_t* rois = nullptr; int32_t* class_ids = nullptr; float* scores = nullptr; int32_t* counts = nullptr;
+    cudaEvent_t computed = nullptr, copied = nullptr;
+    bool copy_pending = false;
+  } slots[2];
+  int cur_slot = 0;
+  cudaStream_t copy_stream = nullptr;
   // preprocessing scratch (detect_maps)
   void* pre_maps = nullptr; size_t pre_maps_bytes = 0;
   void* pre_rgb = nullptr; size_t pre_rgb_bytes = 0;
@@ -651,8 +659,13 @@ extern "C" void mrcnn_engine_destroy(mrcnn_engine* e) {
   for (auto ev : e->stage_events) cudaEventDestroy(ev);
   for (auto ev : e->step_events) cudaEventDestroy(ev);
   if (e->unmold_ws) cudaFree(e->unmold_ws);
-  if (e->d_masks) cudaFree(e->d_masks);
   if (e->d_windows) cudaFree(e->d_windows);
+  if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+  for (auto& sl : e->slots) {
+    if (sl.masks) cudaFree(sl.masks);
+    if (sl.computed) cudaEventDestroy(sl.computed);
+    if (sl.copied) cudaEventDestroy(sl.copied);
+  }
   if (e->pre_maps) cudaFree(e->pre_maps);
   if (e->pre_rgb) cudaFree(e->pre_rgb);
   if (e->pre_small) cudaFree(e->pre_small);
@@ -895,6 +908,7 @@ extern "C" int mrcnn_engine_kernel_times(mrcnn_engine* e, int max_kinds, const c
 
 // ---- unmold + result fetch (shared by detect_molded / detect_maps) ---------------------------------
 static int ensure_scratch(mrcnn_engine* e, void** ptr, size_t* have, size_t need) {
+  (void)e;
   if (*have >= need) return MRCNN_OK;
   if (*ptr) cudaFree(*ptr);
   *ptr = nullptr;
@@ -904,46 +918,85 @@ static int ensure_scratch(mrcnn_engine* e, void** ptr, size_t* have, size_t need
   return MRCNN_OK;
 }
 
-static int unmold_internal(mrcnn_engine* e, const int* orig_hw, const int32_t* windows_host) {
+static int unmold_internal(mrcnn_engine* e, int slot, const int* orig_hw, const int32_t* windows_host) {
   const mrcnn_engine_config& c = e->cfg;
   const int B = c.batch_size, D = c.detection_max_instances;
+  mrcnn_engine::ResultSlot& sl = e->slots[slot];
   RC(ensure_scratch(e, &e->unmold_ws, &e->unmold_ws_bytes, mrcnn_unmold_workspace_bytes(B, D)));
   const size_t mbytes = (size_t)B * orig_hw[0] * orig_hw[1] * D;
-  RC(ensure_scratch(e, (void**)&e->d_masks, &e->mask_out_bytes, mbytes));
+  if (sl.copy_pending) {                       // the slot's previous D2H must be complete before it is overwritten
+    MRCNN_CHECK_CUDA(cudaEventSynchronize(sl.copied));
+    sl.copy_pending = false;
+  }
+  RC(ensure_scratch(e, &sl.masks, &sl.masks_bytes, mbytes));
   if (!e->d_windows) MRCNN_CHECK_CUDA(cudaMalloc((void**)&e->d_windows, (size_t)B * 16));
-  if (e->tensors.find("unmold_rois") == e->tensors.end()) {
-    RC(new_tensor(e, "unmold_rois", DT_I32, (size_t)B * D * 4, nullptr, true));
-    RC(new_tensor(e, "unmold_class_ids", DT_I32, (size_t)B * D, nullptr, true));
-    RC(new_tensor(e, "unmold_scores", DT_F32, (size_t)B * D, nullptr, true));
-    RC(new_tensor(e, "unmold_counts", DT_I32, (size_t)B, nullptr, true));
+  if (!sl.rois) {
+    const std::string sfx = slot == 0 ? "" : "#1";
+    Tensor t;
+    RC(new_tensor(e, "unmold_rois" + sfx, DT_I32, (size_t)B * D * 4, &t, true)); sl.rois = static_cast<int32_t*>(t.ptr);
+    RC(new_tensor(e, "unmold_class_ids" + sfx, DT_I32, (size_t)B * D, &t, true)); sl.class_ids = static_cast<int32_t*>(t.ptr);
+    RC(new_tensor(e, "unmold_scores" + sfx, DT_F32, (size_t)B * D, &t, true)); sl.scores = static_cast<float*>(t.ptr);
+    RC(new_tensor(e, "unmold_counts" + sfx, DT_I32, (size_t)B, &t, true)); sl.counts = static_cast<int32_t*>(t.ptr);
+    MRCNN_CHECK_CUDA(cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming));
+    MRCNN_CHECK_CUDA(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
   }
   MRCNN_CHECK_CUDA(cudaMemcpyAsync(e->d_windows, windows_host, (size_t)B * 16, cudaMemcpyHostToDevice, e->stream));
   const int image_hw[2] = {c.image_size, c.image_size};
   return mrcnn_unmold_detections(static_cast<const float*>(e->tensors["detections"].ptr),
                                  static_cast<const float*>(e->tensors["mrcnn_mask"].ptr), B, D, 2 * c.mask_pool_size,
-                                 2 * c.mask_pool_size, c.num_classes, orig_hw, image_hw, e->d_windows,
-                                 static_cast<int32_t*>(e->tensors["unmold_rois"].ptr),
-                                 static_cast<int32_t*>(e->tensors["unmold_class_ids"].ptr),
-                                 static_cast<float*>(e->tensors["unmold_scores"].ptr),
-                                 static_cast<int32_t*>(e->tensors["unmold_counts"].ptr), e->d_masks, e->unmold_ws,
-                                 e->unmold_ws_bytes, e->stream);
+                                 2 * c.mask_pool_size, c.num_classes, orig_hw, image_hw, e->d_windows, sl.rois, sl.class_ids,
+                                 sl.scores, sl.counts, static_cast<uint8_t*>(sl.masks), e->unmold_ws, e->unmold_ws_bytes,
+                                 e->stream);
 }
 
-static int fetch_internal(mrcnn_engine* e, const int* orig_hw, int32_t* rois_host, int32_t* class_ids_host,
-                          float* scores_host, int32_t* counts_host, uint8_t* masks_host) {
+// D2H of one slot's results.  async: on the copy stream after the compute of this step (recorded event),
+// so the main stream is free to start the next step; otherwise on the main stream.
+static int fetch_internal(mrcnn_engine* e, int slot, bool async, const int* orig_hw, int32_t* rois_host,
+                          int32_t* class_ids_host, float* scores_host, int32_t* counts_host, uint8_t* masks_host) {
   const mrcnn_engine_config& c = e->cfg;
-  const size_t mbytes = (size_t)c.batch_size * orig_hw[0] * orig_hw[1] * c.detection_max_instances;
-  Tensor& tr = e->tensors["unmold_rois"];
-  Tensor& tc = e->tensors["unmold_class_ids"];
-  Tensor& ts = e->tensors["unmold_scores"];
-  Tensor& tn = e->tensors["unmold_counts"];
-  if (rois_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(rois_host, tr.ptr, tr.bytes, cudaMemcpyDeviceToHost, e->stream));
-  if (class_ids_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(class_ids_host, tc.ptr, tc.bytes, cudaMemcpyDeviceToHost, e->stream));
-  if (scores_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(scores_host, ts.ptr, ts.bytes, cudaMemcpyDeviceToHost, e->stream));
-  if (counts_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(counts_host, tn.ptr, tn.bytes, cudaMemcpyDeviceToHost, e->stream));
-  if (masks_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(masks_host, e->d_masks, mbytes, cudaMemcpyDeviceToHost, e->stream));
+  const int B = c.batch_size, D = c.detection_max_instances;
+  const size_t mbytes = (size_t)B * orig_hw[0] * orig_hw[1] * D;
+  mrcnn_engine::ResultSlot& sl = e->slots[slot];
+  cudaStream_t st = e->stream;
+  if (async) {
+    if (!e->copy_stream) MRCNN_CHECK_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    MRCNN_CHECK_CUDA(cudaEventRecord(sl.computed, e->stream));
+    MRCNN_CHECK_CUDA(cudaStreamWaitEvent(e->copy_stream, sl.computed, 0));
+    st = e->copy_stream;
+  }
+  if (rois_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(rois_host, sl.rois, (size_t)B * D * 16, cudaMemcpyDeviceToHost, st));
+  if (class_ids_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(class_ids_host, sl.class_ids, (size_t)B * D * 4, cudaMemcpyDeviceToHost, st));
+  if (scores_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(scores_host, sl.scores, (size_t)B * D * 4, cudaMemcpyDeviceToHost, st));
+  if (counts_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(counts_host, sl.counts, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (masks_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(masks_host, sl.masks, mbytes, cudaMemcpyDeviceToHost, st));
+  if (async) {
+    MRCNN_CHECK_CUDA(cudaEventRecord(sl.copied, e->copy_stream));
+    sl.copy_pending = true;
+  }
   return MRCNN_OK;
 }
+
+extern "C" int mrcnn_engine_wait(mrcnn_engine* e) {
+  MRCNN_REQUIRE(e, "engine_wait: null engine");
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+  if (e->copy_stream) MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->copy_stream));
+  for (auto& sl : e->slots) sl.copy_pending = false;
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_wait_slot(mrcnn_engine* e, int slot) {
+  MRCNN_REQUIRE(e && (slot == 0 || slot == 1), "engine_wait_slot: bad arguments");
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  mrcnn_engine::ResultSlot& sl = e->slots[slot];
+  if (sl.copy_pending) {
+    MRCNN_CHECK_CUDA(cudaEventSynchronize(sl.copied));
+    sl.copy_pending = false;
+  }
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_next_slot(const mrcnn_engine* e) { return e ? e->cur_slot : -1; }
 
 extern "C" int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, int molded_on_host,
                                           const float* metas_host, const int* orig_hw,
@@ -955,8 +1008,8 @@ extern "C" int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, 
   MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
   RC(predict_internal(e, molded, molded_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, metas_host,
                       cudaMemcpyHostToDevice));
-  RC(unmold_internal(e, orig_hw, windows_host));
-  RC(fetch_internal(e, orig_hw, rois_host, class_ids_host, scores_host, counts_host, masks_host));
+  RC(unmold_internal(e, 0, orig_hw, windows_host));
+  RC(fetch_internal(e, 0, false, orig_hw, rois_host, class_ids_host, scores_host, counts_host, masks_host));
   MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
   return MRCNN_OK;
 }
@@ -965,7 +1018,7 @@ extern "C" int mrcnn_engine_detect_maps(mrcnn_engine* e, const float* maps, int 
                                         const float* contrasts3, const float* mean_pixel3, int out_h, int out_w,
                                         int top, int left, const float* metas_host, const int32_t* windows_host,
                                         int32_t* rois_host, int32_t* class_ids_host, float* scores_host,
-                                        int32_t* counts_host, uint8_t* masks_host) {
+                                        int32_t* counts_host, uint8_t* masks_host, int async) {
   MRCNN_REQUIRE(e && e->finalized, "detect_maps: engine not finalized");
   MRCNN_REQUIRE(maps && contrasts3 && mean_pixel3 && metas_host && windows_host, "detect_maps: null pointer");
   MRCNN_REQUIRE(map_h > 0 && map_w > 0, "detect_maps: empty maps");
@@ -990,8 +1043,15 @@ extern "C" int mrcnn_engine_detect_maps(mrcnn_engine* e, const float* maps, int 
   RC(mrcnn_resize_pad_mold(d_rgb, d_minmax, B, map_h, map_w, out_h, out_w, c.image_size, top, left, mean_pixel3, d_img, e->stream));
   RC(predict_internal(e, d_img, cudaMemcpyDeviceToDevice, metas_host, cudaMemcpyHostToDevice));
   const int orig_hw[2] = {map_h, map_w};
-  RC(unmold_internal(e, orig_hw, windows_host));
-  RC(fetch_internal(e, orig_hw, rois_host, class_ids_host, scores_host, counts_host, masks_host));
+  const bool any_out = rois_host || class_ids_host || scores_host || counts_host || masks_host;
+  const int slot = (async && any_out) ? e->cur_slot : 0;
+  RC(unmold_internal(e, slot, orig_hw, windows_host));
+  if (async && any_out) {
+    RC(fetch_internal(e, slot, true, orig_hw, rois_host, class_ids_host, scores_host, counts_host, masks_host));
+    e->cur_slot ^= 1;
+    return MRCNN_OK;                 // caller collects with mrcnn_engine_wait()
+  }
+  RC(fetch_internal(e, slot, false, orig_hw, rois_host, class_ids_host, scores_host, counts_host, masks_host));
   MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
   return MRCNN_OK;
 }

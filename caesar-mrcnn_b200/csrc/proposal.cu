@@ -30,6 +30,7 @@ struct PropParams {
   int32_t* keep_idx;  // [B,R] or null (index into the top-k order, -1 padded)
   int32_t* keep_cnt;  // [B] or null
   int r0_bytes;
+  int kept_off;   // byte offset of the kept list inside region 0
 };
 
 __device__ __forceinline__ int block_excl_scan_flag(bool flag, int* warp_tot, int& total) {
@@ -162,7 +163,8 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
   HeapEntry* heap = reinterpret_cast<HeapEntry*>(r0);                  // 1-indexed: [K+2], 16-byte aligned
   uint16_t* order = reinterpret_cast<uint16_t*>(heap + ((K + 2 + 1) & ~1));   // [K]
   uint16_t* selected = order + ((K + 1) & ~1);                          // [R]
-  uint32_t* removed = reinterpret_cast<uint32_t*>(selected + ((R + 1) & ~1));
+  float4* kept_box = reinterpret_cast<float4*>(r0 + p.kept_off);         // [R]
+  float* kept_area = reinterpret_cast<float*>(kept_box + R);            // [R]
   bool tie = false;
   for (int q = tid; q + 1 < K; q += nt) tie |= (s_scores[q] == s_scores[q + 1]);
   const int any_tie = __syncthreads_or(tie ? 1 : 0);
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
   __syncthreads();
 
   // ---- 6. NMS + output ------------------------------------------------------------------------
-  const int count = block_nms(boxes, order, K, R, p.thr, removed, selected, sc, any_tie ? heap : nullptr);
+  const int count = block_nms(boxes, order, K, R, p.thr, kept_box, kept_area, selected, sc, any_tie ? heap : nullptr);
   __syncthreads();
   float4* out = reinterpret_cast<float4*>(p.rois + (size_t)b * R * 4);
   for (int r = tid; r < R; r += nt) {
@@ -203,11 +205,14 @@ int next_pow2(int v) {
   return p;
 }
 
-size_t prop_smem_bytes(int K, int R, int* r0_bytes) {
+size_t prop_smem_bytes(int K, int R, int* r0_bytes, int* kept_off) {
   const int Kpad = next_pow2(K);
   size_t a = (size_t)Kpad * 8;
-  size_t bsz = (size_t)((K + 2 + 1) & ~1) * sizeof(HeapEntry) + (size_t)((K + 1) & ~1) * 2 + (size_t)((R + 1) & ~1) * 2 +
-               (size_t)((K + 31) / 32 + 2) * 4 + 16;
+  // phase B of region 0: heap (1-indexed) | order | selected | kept boxes | kept areas
+  size_t bsz = (size_t)((K + 2 + 1) & ~1) * sizeof(HeapEntry) + (size_t)((K + 1) & ~1) * 2 + (size_t)((R + 1) & ~1) * 2;
+  bsz = (bsz + 15) & ~(size_t)15;
+  *kept_off = (int)bsz;
+  bsz += (size_t)R * 16 + (size_t)R * 4 + 16;
   size_t r0 = a > bsz ? a : bsz;
   r0 = (r0 + 15) & ~(size_t)15;
   *r0_bytes = (int)r0;
@@ -253,7 +258,7 @@ extern "C" int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbo
                   "proposal_layer: workspace too small");
     p.topk_idx = static_cast<int32_t*>(workspace);
   }
-  size_t smem = prop_smem_bytes(K, proposal_count, &p.r0_bytes);
+  size_t smem = prop_smem_bytes(K, proposal_count, &p.r0_bytes, &p.kept_off);
   MRCNN_REQUIRE(smem <= 227 * 1024, "proposal_layer: shared memory %zu exceeds 227 KB", smem);
   MRCNN_CHECK_CUDA(cudaFuncSetAttribute(proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   proposal_kernel<<<batch, PROP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);

@@ -68,24 +68,31 @@ template <> struct Vec<__nv_bfloat16> {
   }
 };
 
-// One CTA per ROI.  The P sample rows / columns of the crop are computed once per ROI into shared
-// memory (tf.image.crop_and_resize coordinates, float32, left-to-right evaluation); then each warp
-// takes output pixels round-robin with one lane per 16-byte channel vector, so a pixel is 4 coalesced
-// 512-byte reads (bf16, C=256) and one coalesced 512-byte streaming store.
+// One CTA per ROI.  Thread 0 computes the pyramid level; the P sample rows / columns of the crop are
+// then computed once per ROI into shared memory (tf.image.crop_and_resize coordinates, float32,
+// left-to-right evaluation) as element offsets + lerp weights; each warp takes output pixels
+// round-robin with one lane per 16-byte channel vector, so a pixel is 4 coalesced 512-byte reads
+// (bf16, C=256) and one coalesced 512-byte streaming store, with no per-pixel address arithmetic
+// beyond four integer adds.
 constexpr int ROI_MAX_P = 32;
 
 template <typename T>
 __global__ void __launch_bounds__(256) roialign_kernel(RoiParams p) {
   constexpr int VN = Vec<T>::N;
-  __shared__ int s_lo[2][ROI_MAX_P], s_hi[2][ROI_MAX_P];   // [0] = rows (top/bottom), [1] = cols (left/right); -1 = outside
+  __shared__ int s_lo[2][ROI_MAX_P], s_hi[2][ROI_MAX_P];   // element offsets: [0] rows (t*W*C, b*W*C), [1] cols (l*C, r*C); -1 = outside
   __shared__ float s_w[2][ROI_MAX_P];                      // lerp weights
+  __shared__ int s_level;
   const int roi = blockIdx.x;  // b*N + n
   const int b = roi / p.N;
   const float* bp = p.boxes + (size_t)roi * p.box_stride;
   const float y1 = bp[0], x1 = bp[1], y2 = bp[2], x2 = bp[3];
-  const int lvl = roi_level(y1, x1, y2, x2, p.image_area);
-  if (threadIdx.x == 0 && p.levels) p.levels[roi] = lvl;
-  const int li = lvl - 2;
+  if (threadIdx.x == 0) {
+    const int lv = roi_level(y1, x1, y2, x2, p.image_area);
+    s_level = lv;
+    if (p.levels) p.levels[roi] = lv;
+  }
+  __syncthreads();
+  const int li = s_level - 2;
   const int H = p.H[li], W = p.W[li], C = p.C, P = p.P;
   const T* feat = static_cast<const T*>(p.feat[li]) + (size_t)b * H * W * C;
   T* out = static_cast<T*>(p.out) + (size_t)roi * P * P * C;
@@ -101,8 +108,9 @@ __global__ void __launch_bounds__(256) roialign_kernel(RoiParams p) {
       float wgt = 0.f;
       if ((in >= 0.f) && (in <= Dm1)) {
         const float f = floorf(in);
-        lo = (int)f;
-        hi = (int)ceilf(in);
+        const int mul = axis == 0 ? W * C : C;
+        lo = (int)f * mul;
+        hi = (int)ceilf(in) * mul;
         wgt = __fsub_rn(in, f);
       }
       s_lo[axis][i] = lo;
@@ -112,24 +120,25 @@ __global__ void __launch_bounds__(256) roialign_kernel(RoiParams p) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  int iy = warp / P, ix = warp - iy * P;
   for (int pix = warp; pix < P * P; pix += nwarps) {
-    const int iy = pix / P, ix = pix - iy * P;
-    const int t = s_lo[0][iy], bt = s_hi[0][iy], l = s_lo[1][ix], r = s_hi[1][ix];
+    const int ro0 = s_lo[0][iy], ro1 = s_hi[0][iy], co0 = s_lo[1][ix], co1 = s_hi[1][ix];
     const float ly = s_w[0][iy], lx = s_w[1][ix];
-    const bool valid = (t >= 0) && (l >= 0);
-    const T* ptl = feat + ((size_t)t * W + l) * C;
-    const T* ptr_ = feat + ((size_t)t * W + r) * C;
-    const T* pbl = feat + ((size_t)bt * W + l) * C;
-    const T* pbr = feat + ((size_t)bt * W + r) * C;
-    T* po = out + (size_t)pix * C;
+    const bool valid = (ro0 >= 0) && (co0 >= 0);
+    T* po = out + pix * C;
     for (int c0 = lane * VN; c0 < C; c0 += 32 * VN) {
       float o[VN];
       if (valid) {
+        const T* fb = feat + c0;
+        const typename Vec<T>::Raw rtl = Vec<T>::load(fb + ro0 + co0);
+        const typename Vec<T>::Raw rtr = Vec<T>::load(fb + ro0 + co1);
+        const typename Vec<T>::Raw rbl = Vec<T>::load(fb + ro1 + co0);
+        const typename Vec<T>::Raw rbr = Vec<T>::load(fb + ro1 + co1);
         float a[VN], bq[VN], c[VN], d[VN];
-        Vec<T>::unpack(Vec<T>::load(ptl + c0), a);
-        Vec<T>::unpack(Vec<T>::load(ptr_ + c0), bq);
-        Vec<T>::unpack(Vec<T>::load(pbl + c0), c);
-        Vec<T>::unpack(Vec<T>::load(pbr + c0), d);
+        Vec<T>::unpack(rtl, a);
+        Vec<T>::unpack(rtr, bq);
+        Vec<T>::unpack(rbl, c);
+        Vec<T>::unpack(rbr, d);
 #pragma unroll
         for (int k = 0; k < VN; ++k) {
           const float top = __fadd_rn(a[k], __fmul_rn(__fsub_rn(bq[k], a[k]), lx));
@@ -141,6 +150,11 @@ __global__ void __launch_bounds__(256) roialign_kernel(RoiParams p) {
         for (int k = 0; k < VN; ++k) o[k] = 0.f;
       }
       Vec<T>::store(po + c0, o);
+    }
+    ix += nwarps;
+    while (ix >= P) {
+      ix -= P;
+      ++iy;
     }
   }
 }

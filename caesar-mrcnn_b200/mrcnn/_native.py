@@ -82,7 +82,10 @@ SIGNATURES = {
     "mrcnn_engine_detect_molded": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p]),
     "mrcnn_engine_detect_maps": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
-                                         c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                         c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "mrcnn_engine_wait": (c_int, [c_void_p]),
+    "mrcnn_engine_next_slot": (c_int, [c_void_p]),
+    "mrcnn_engine_wait_slot": (c_int, [c_void_p, c_int]),
     "mrcnn_engine_stream": (c_void_p, [c_void_p]),
     "mrcnn_engine_stage_times": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_float)]),
     "mrcnn_engine_flops": (ctypes.c_double, [c_void_p]),

@@ -67,6 +67,20 @@ def unmold_image(normalized_images, config):
 # MaskRCNN
 # --------------------------------------------------------------------------------------------
 
+class _PendingDetection(object):
+    """Handle of an asynchronous detect_maps call (keeps the pinned buffers and inputs alive)."""
+
+    def __init__(self, model, bufs, maps, slot):
+        self._model, self._bufs, self._maps, self._done, self._slot = model, bufs, maps, None, slot
+
+    def result(self):
+        if self._done is None:
+            _native.check(self._model._lib.mrcnn_engine_wait_slot(self._model._engine, self._slot), "engine_wait_slot")
+            self._done = MaskRCNN._results_from_buffers(self._bufs, self._model.config.BATCH_SIZE)
+            self._maps = None
+        return self._done
+
+
 class MaskRCNN(object):
     """Mask R-CNN inference model; drop-in for mrcnn.model.MaskRCNN(mode='inference')."""
 
@@ -337,9 +351,10 @@ class MaskRCNN(object):
         torch = utils._torch()
         c = self.config
         B, D = c.BATCH_SIZE, c.DETECTION_MAX_INSTANCES
-        return (torch.empty((B, D, 4), dtype=torch.int32).pin_memory(), torch.empty((B, D), dtype=torch.int32).pin_memory(),
-                torch.empty((B, D), dtype=torch.float32).pin_memory(), torch.empty((B,), dtype=torch.int32).pin_memory(),
-                torch.empty((B, H0, W0, D), dtype=torch.uint8).pin_memory())
+        # allocated pinned directly (tensor.pin_memory() would allocate pageable memory first and copy it)
+        return (torch.empty((B, D, 4), dtype=torch.int32, pin_memory=True), torch.empty((B, D), dtype=torch.int32, pin_memory=True),
+                torch.empty((B, D), dtype=torch.float32, pin_memory=True), torch.empty((B,), dtype=torch.int32, pin_memory=True),
+                torch.empty((B, H0, W0, D), dtype=torch.uint8, pin_memory=True))
 
     @staticmethod
     def _results_from_buffers(bufs, B):
@@ -370,7 +385,16 @@ class MaskRCNN(object):
                                                                wins.ctypes.data, *[_native.ptr(b) for b in bufs]), "detect")
         return self._results_from_buffers(bufs, self.config.BATCH_SIZE)
 
-    def detect_maps(self, maps, zscale_contrasts=(0.25, 0.25, 0.25), device_only=False):
+    def detect_maps_async(self, maps, zscale_contrasts=(0.25, 0.25, 0.25)):
+        """Queues detect_maps and returns a handle whose .result() gives the detect()-style dicts. The
+        device->host copy of this batch overlaps the compute of the next queued batch (at most two
+        batches in flight; call .result() on the older one before queueing a third)."""
+        return self.detect_maps(maps, zscale_contrasts, _async=True)
+
+    def wait(self):
+        _native.check(self._lib.mrcnn_engine_wait(self._engine), "engine_wait")
+
+    def detect_maps(self, maps, zscale_contrasts=(0.25, 0.25, 0.25), device_only=False, _async=False):
         """Fast path from FITS-like maps (extension; the numpy contract of detect() is unchanged):
         maps [BATCH_SIZE,H,W] float32 — numpy / pinned torch tensor (copied H2D) or a CUDA tensor —
         -> read_fits stretch + mold + graph + unmold in one C-ABI call. Returns detect()-style dicts,
@@ -397,11 +421,17 @@ class MaskRCNN(object):
         mean = _native.float_array([float(v) for v in np.asarray(c.MEAN_PIXEL).reshape(-1)[:3]])
         bufs = None if device_only else self._result_buffers(H0, W0)
         outs = [None] * 5 if device_only else [_native.ptr(b) for b in bufs]
+        slot = self._lib.mrcnn_engine_next_slot(self._engine)
         with torch.cuda.stream(self._stream):
             _native.check(self._lib.mrcnn_engine_detect_maps(self._engine, _native.ptr(maps), 0 if maps.is_cuda else 1, H0, W0, con, mean,
                                                              int(out_hw[0]), int(out_hw[1]), int(top_left[0]), int(top_left[1]),
-                                                             metas32.ctypes.data, wins.ctypes.data, *outs), "detect_maps")
-        return None if device_only else self._results_from_buffers(bufs, c.BATCH_SIZE)
+                                                             metas32.ctypes.data, wins.ctypes.data, *outs, 1 if _async else 0),
+                          "detect_maps")
+        if device_only:
+            return None
+        if _async:
+            return _PendingDetection(self, bufs, maps, slot)
+        return self._results_from_buffers(bufs, c.BATCH_SIZE)
 
     def kernel_times(self):
         """{family: (ms, launches)} of the last predict; needs set_profiling(True) beforehand."""

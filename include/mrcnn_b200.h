@@ -218,12 +218,20 @@ int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, int molded_
  * 1090-1208) -> resize to (out_h,out_w), pad at (top,left), minus mean (mold_inputs, mrcnn/model.py:
  * 2519-2556) -> graph -> unmold against the original (map_h,map_w) frame.  metas / windows: HOST.
  * Host result pointers may be NULL (all of them = results stay on the device, readable through
- * mrcnn_engine_tensor "unmold_rois"/"unmold_class_ids"/"unmold_scores"/"unmold_counts").  Blocking. */
+ * mrcnn_engine_tensor "unmold_rois"/"unmold_class_ids"/"unmold_scores"/"unmold_counts").  Blocking unless async. */
 int mrcnn_engine_detect_maps(mrcnn_engine* e, const float* maps, int maps_on_host, int map_h, int map_w,
                              const float* contrasts3, const float* mean_pixel3, int out_h, int out_w,
                              int top, int left, const float* metas_host, const int32_t* windows_host,
                              int32_t* rois_host, int32_t* class_ids_host, float* scores_host,
-                             int32_t* counts_host, uint8_t* masks_host);
+                             int32_t* counts_host, uint8_t* masks_host, int async);
+/* async != 0 (with host result pointers): returns once the work is queued; the device->host copies
+ * run on a second stream from double-buffered result slots, so the next call's compute overlaps
+ * them.  At most two calls may be in flight; mrcnn_engine_wait() blocks until every queued copy
+ * has landed in its host buffers (which must stay valid and pinned until then). */
+int mrcnn_engine_wait(mrcnn_engine* e);
+/* slot (0/1) the next async call will use, and a wait for the copies of one slot only */
+int mrcnn_engine_next_slot(const mrcnn_engine* e);
+int mrcnn_engine_wait_slot(mrcnn_engine* e, int slot);
 void* mrcnn_engine_stream(const mrcnn_engine* e);
 /* per-stage device time of the last predict in milliseconds (CUDA events); names via index */
 int mrcnn_engine_stage_times(const mrcnn_engine* e, int max_stages, const char** names, float* ms);

@@ -299,3 +299,20 @@ def test_detect_maps_equals_read_fits_plus_detect(model, weights):
     for a, b in zip(r_fast, r_slow):
         for k in ("rois", "class_ids", "scores", "masks"):
             assert np.array_equal(a[k], b[k]), k
+
+
+def test_async_pipelined_detect_maps_equals_sync(model):
+    """Two batches in flight (double-buffered result slots + copy stream) give the sync results."""
+    a = torch.from_numpy(synth.radio_maps(B, 132, start=21)).pin_memory()
+    b = torch.from_numpy(synth.radio_maps(B, 132, start=31)).pin_memory()
+    ref_a, ref_b = model.detect_maps(a), model.detect_maps(b)
+    h1 = model.detect_maps_async(a)
+    h2 = model.detect_maps_async(b)
+    r1 = h1.result()
+    h3 = model.detect_maps_async(a)          # reuses slot 0 after its copy completed
+    r2, r3 = h2.result(), h3.result()
+    for got, ref in ((r1, ref_a), (r2, ref_b), (r3, ref_a)):
+        for x, y in zip(got, ref):
+            for k in ("rois", "class_ids", "scores", "masks"):
+                assert np.array_equal(x[k], y[k]), k
+    model.wait()
