@@ -261,8 +261,16 @@ def main():
         if i == args.steps - 1:
             e2e_results[0] = pending[0].result()
             pending[0] = None
-    for i in range(2):
-        e2e_results[0] = model.detect_maps(host_sets[i % n_sets])
+    # warm-up with the same retention pattern (3 result sets alive: retained, draining, in flight) so the
+    # pinned-host caching allocator holds enough 420 MB blocks before the timed region (a fresh
+    # cudaHostAlloc of that size costs ~0.4 s)
+    for i in range(max(args.warmup, 4)):
+        h = model.detect_maps_async(host_sets[i % n_sets])
+        if pending[0] is not None:
+            e2e_results[0] = pending[0].result()
+        pending[0] = h
+    e2e_results[0] = pending[0].result()
+    pending[0] = None
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     D = 100

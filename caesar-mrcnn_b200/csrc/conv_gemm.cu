@@ -33,7 +33,8 @@ template <int BLOCK_N> struct TileCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = 2 * 2 * BLOCK_N * 4;   // [acc][scale|shift][BLOCK_N] floats
+  // [acc][scale|shift][BLOCK_N] floats + (fused mask logits) W2 [256][4] floats + partials [128][8] floats
+  static constexpr int EPI_BYTES = 2 * 2 * BLOCK_N * 4 + (BLOCK_N == 256 ? (256 * 4 * 4 + 128 * 8 * 4) : 0);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;   // double-buffered accumulator (64..512, power of two)
 };
@@ -253,7 +254,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     constexpr int COLS_PER_WARP = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
     const bool has_cols = (BLOCK_N >= 64) || (half == 0);
     const int c_begin = (BLOCK_N >= 64) ? half * COLS_PER_WARP : 0;
-    const int cout_store = p.out_mode == 1 ? p.cout : p.out_ld;   // pitch padding is written as zeros
+    const int cout_store = p.out_mode >= 1 ? p.cout : p.out_ld;   // pitch padding is written as zeros
+    const bool fused2 = (BLOCK_N == 256) && (p.out_mode == 2);
+    float* s_w2 = s_affine + 4 * BLOCK_N;          // [256][4] 1x1-conv weights (nc2 <= 4)
+    float* s_part = s_w2 + 256 * 4;                // [128][8] partial logits of the upper column half
+    if (fused2) {
+      for (int i = et; i < 256 * 4; i += EPI_THREADS) {
+        const int c = i >> 2, j = i & 3;
+        s_w2[i] = (j < p.nc2) ? __bfloat162float(p.w2[(size_t)j * p.cout + c]) : 0.f;
+      }
+    }
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1u;
@@ -263,7 +273,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       const int col_base = n_tile * BLOCK_N;
       int ch_base = col_base;          // channel index used for scale/shift and the store column
       int tap = 0;
-      if (p.out_mode == 1) {
+      if (p.out_mode >= 1) {
         tap = col_base / p.cout;
         ch_base = col_base - tap * p.cout;
       }
@@ -299,7 +309,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         row_ok = (row < per_img * p.nb) && (n < p.N) && (h < p.OH) && (w < p.OW);
       }
       size_t out_off;
-      if (p.out_mode == 1) {
+      if (p.out_mode >= 1) {
         const int oi = tap >> 1, oj = tap & 1;
         out_off = (((size_t)n * (2 * p.OH) + (2 * h + oi)) * (size_t)(2 * p.OW) + (2 * w + oj)) * (size_t)p.out_ld;
       } else {
@@ -317,6 +327,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       if (has_cols) {
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + (uint32_t)c_begin;
         uint32_t vbuf[2][32];
+        float logit[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         uint4 rbuf[2][4];     // residual of the chunk, fetched one chunk ahead (scattered 16-byte loads)
         const bool res_vec = (res_row != nullptr);
         auto load_residual = [&](int ci, uint4* r) {
@@ -373,7 +384,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 #pragma unroll
                   for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
                 }
-                if (p.out_f32) {
+                if (fused2) {
+                  // 1x1 conv on the bf16-rounded activation, fp32 accumulation; weights broadcast from smem
+                  float4 wv[8];
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) wv[k] = *reinterpret_cast<const float4*>(s_w2 + (size_t)(c + g * 8 + k) * 4);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const float xb = __bfloat162float(__float2bfloat16_rn(o[k]));
+                    logit[0] = fmaf(xb, wv[k].x, logit[0]);
+                    logit[1] = fmaf(xb, wv[k].y, logit[1]);
+                    logit[2] = fmaf(xb, wv[k].z, logit[2]);
+                    logit[3] = fmaf(xb, wv[k].w, logit[3]);
+                  }
+                } else if (p.out_f32) {
                   float* dst = static_cast<float*>(p.out) + out_off + ch;
                   *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
                   *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
@@ -385,6 +409,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
               }
             }
           }
+        }
+        if (fused2) {
+          // combine the two column halves of each row: half 1 -> smem, half 0 adds, bias, sigmoid, store
+          if (half == 1) {
+            *reinterpret_cast<float4*>(s_part + row * 8) = make_float4(logit[0], logit[1], logit[2], logit[3]);
+            *reinterpret_cast<float4*>(s_part + row * 8 + 4) = make_float4(logit[4], logit[5], logit[6], logit[7]);
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (half == 0 && row_ok) {
+            const float4 pa = *reinterpret_cast<const float4*>(s_part + row * 8);
+            const float4 pb = *reinterpret_cast<const float4*>(s_part + row * 8 + 4);
+            const float other[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+            float* dst = static_cast<float*>(p.out) + out_off;      // out_ld == nc2
+            float sg[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float z = logit[j] + other[j] + (j < p.nc2 ? __ldg(p.b2 + j) : 0.f);
+              sg[j] = 1.0f / (1.0f + expf(-z));
+            }
+            if (p.nc2 == 4) {
+              *reinterpret_cast<float4*>(dst) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j < p.nc2) dst[j] = sg[j];
+            }
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");            // s_part reusable by the next tile
         }
       } else {
         mbar_wait(tmem_full_bar(acc), aph);
@@ -625,12 +677,30 @@ int conv_plan_create(const mrcnn_conv_desc* d, const void* x, const void* w, con
   p.shift = shift;
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.out = out;
+  p.w2 = nullptr;
+  p.b2 = nullptr;
+  p.nc2 = 0;
   if (residual) MRCNN_REQUIRE(d->cout % 8 == 0, "conv2d: residual needs cout %% 8 == 0");
   p.n_tiles = ceil_div(cout_total, block_n);
   const long long ctas = (long long)p.n_tiles * p.tiles_w * p.tiles_h * p.tiles_nb;
   MRCNN_REQUIRE(ctas < 2147483647LL, "conv2d: grid too large");
   plan->grid = dim3((unsigned)ctas, 1, 1);
   plan->flops = 2.0 * (double)d->n * OH * OW * (double)cout_total * (double)K;
+  return MRCNN_OK;
+}
+
+int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, int nc2, void* out) {
+  MRCNN_REQUIRE(plan && w2 && b2 && out, "fuse_mask_logits: null pointer");
+  MRCNN_REQUIRE(plan->block_n == 256 && plan->p.out_mode == 1 && plan->p.cout == 256,
+                "fuse_mask_logits: needs a 256-channel transposed-conv plan with 256-wide tiles");
+  MRCNN_REQUIRE(nc2 >= 1 && nc2 <= 4, "fuse_mask_logits: nc2=%d outside [1,4]", nc2);
+  plan->p.out_mode = 2;
+  plan->p.w2 = static_cast<const __nv_bfloat16*>(w2);
+  plan->p.b2 = b2;
+  plan->p.nc2 = nc2;
+  plan->p.out = out;
+  plan->p.out_ld = nc2;
+  plan->flops += 2.0 * (double)plan->p.M * 4.0 * 256.0 * nc2;   // the fused 1x1 conv
   return MRCNN_OK;
 }
 
@@ -664,6 +734,7 @@ extern "C" int mrcnn_conv2d_bf16_simt(const mrcnn_conv_desc* d, const void* x, c
   p.scale = scale; p.shift = shift;
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.out = out;
+
   p.N = d->n; p.H = d->h; p.W = d->w; p.Cin = d->cin; p.KH = d->kh; p.KW = d->kw; p.stride = d->stride; p.pad = d->pad;
   p.OH = OH; p.OW = OW; p.cout = d->cout; p.cout_total = d->out_mode == 1 ? 4 * d->cout : d->cout;
   p.relu = d->relu; p.res_up2 = d->residual_upsample2; p.out_f32 = d->out_dtype == MRCNN_DTYPE_F32;

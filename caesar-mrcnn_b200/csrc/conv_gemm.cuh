@@ -20,6 +20,11 @@ struct ConvGemmParams {
   const float* shift;
   const __nv_bfloat16* residual;
   void* out;
+  // out_mode 2 (engine-internal): 2x2-s2 transposed conv + ReLU fused with the following 1x1 conv
+  // (cout -> nc2) + sigmoid; `out` is then float32 [N, 2*OH, 2*OW, nc2] (mrcnn_mask)
+  const __nv_bfloat16* w2;   // [nc2][cout] bf16
+  const float* b2;           // [nc2]
+  int nc2;
 };
 
 struct ConvPlan {
@@ -29,6 +34,7 @@ struct ConvPlan {
   int block_n;
   dim3 grid;
   double flops;
+  float* w2_table = nullptr;   // fused mask logits: [256][8] float expansion of w2 (device; freed by the owner)
 };
 
 // Builds the tensor maps + launch geometry for one layer.  x/w/out are device pointers that must
@@ -36,5 +42,7 @@ struct ConvPlan {
 int conv_plan_create(const mrcnn_conv_desc* d, const void* x, const void* w, const float* scale,
                      const float* shift, const void* residual, void* out, int block_n, ConvPlan* plan);
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);
+// turns a 256-channel deconv plan (block_n 256) into deconv + ReLU + 1x1 conv (nc2) + sigmoid -> float32 out
+int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, int nc2, void* out);
 
 void mrcnn_count_launch(unsigned long long n);

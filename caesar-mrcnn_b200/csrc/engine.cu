@@ -567,14 +567,30 @@ int build_graph(mrcnn_engine* e) {
                 "mrcnn_mask_conv" + std::to_string(i) + "_out", &o));
     m = o;
   }
-  Act dc;
-  RC(add_conv(e, "mask_head", "mrcnn_mask_deconv", m, 1, 1, 1, nullptr, 0, "mrcnn_mask_deconv_out", &dc, 0, 0, 1));
-  void* mlog = nullptr;
-  RC(add_conv(e, "mask_head", "mrcnn_mask", dc, 1, 1, 0, nullptr, 0, "mrcnn_mask_logits", nullptr, 1, 8, 0, &mlog));
   MRCNN_REQUIRE(NC <= 8, "engine: NUM_CLASSES=%d too large for the mask logits pitch (max 8)", NC);
   Tensor t_mask;
   RC(new_tensor(e, "mrcnn_mask", DT_F32, (size_t)B * D * 4 * MP * MP * NC, &t_mask, true));
-  {
+  if (PY == 256 && NC <= 4) {
+    // Conv2DTranspose(2x2, s2) + ReLU + Conv2D(1x1 -> NC) + sigmoid as ONE GEMM: the 1x1 conv runs in the
+    // epilogue on the bf16-rounded deconv output, so the [B*D,28,28,256] tensor never touches HBM
+    const GemmW& gd = e->gemm["mrcnn_mask_deconv"];
+    const GemmW& gm = e->gemm["mrcnn_mask"];
+    mrcnn_conv_desc d;
+    memset(&d, 0, sizeof(d));
+    d.n = m.n; d.h = m.h; d.w = m.w; d.cin = m.c; d.kh = 1; d.kw = 1; d.stride = 1; d.pad = 0;
+    d.cout = gd.cout; d.relu = 1; d.out_dtype = MRCNN_DTYPE_BF16; d.out_mode = 1;
+    ConvPlan* plan = new ConvPlan();
+    e->plans.push_back(plan);
+    RC(conv_plan_create(&d, m.p, gd.w, gd.scale, gd.shift, nullptr, t_mask.ptr, 256, plan));
+    RC(conv_plan_fuse_mask_logits(plan, gm.w, gm.shift, NC, t_mask.ptr));
+    e->flops += plan->flops;
+    e->steps.push_back({"mask_head", [plan](cudaStream_t st) { return conv_plan_launch(plan, st); }, "conv_gemm",
+                        "mrcnn_mask (deconv+1x1+sigmoid)", plan->flops});
+  } else {
+    Act dc;
+    RC(add_conv(e, "mask_head", "mrcnn_mask_deconv", m, 1, 1, 1, nullptr, 0, "mrcnn_mask_deconv_out", &dc, 0, 0, 1));
+    void* mlog = nullptr;
+    RC(add_conv(e, "mask_head", "mrcnn_mask", dc, 1, 1, 0, nullptr, 0, "mrcnn_mask_logits", nullptr, 1, 8, 0, &mlog));
     const float* lg = static_cast<const float*>(mlog);
     float* out = static_cast<float*>(t_mask.ptr);
     const size_t M = (size_t)B * D * 4 * MP * MP;
@@ -655,7 +671,10 @@ extern "C" void mrcnn_engine_destroy(mrcnn_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   for (void* p : e->allocs) cudaFree(p);
-  for (ConvPlan* p : e->plans) delete p;
+  for (ConvPlan* p : e->plans) {
+    if (p->w2_table) cudaFree(p->w2_table);
+    delete p;
+  }
   for (auto ev : e->stage_events) cudaEventDestroy(ev);
   for (auto ev : e->step_events) cudaEventDestroy(ev);
   if (e->unmold_ws) cudaFree(e->unmold_ws);
