@@ -7,6 +7,7 @@
 // needs ~12 GB of the 180 GB); weights are bf16 [Cout, KH*KW*Cin] (K-major GEMM-B operands) with
 // the frozen BatchNorm folded into per-channel fp32 (scale, shift) applied in the GEMM epilogue.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <functional>
 #include <map>
@@ -96,6 +97,7 @@ struct mrcnn_engine {
   // timing
   std::vector<std::string> stage_names;
   std::vector<cudaEvent_t> stage_events;  // stage_names.size() + 1
+  bool autotune = true;
   bool profiling = false;
   std::vector<cudaEvent_t> step_events;   // steps.size() + 1, recorded when profiling
   std::vector<std::string> kind_names;    // scratch for kernel_times()
@@ -333,6 +335,46 @@ int build_weights(mrcnn_engine* e) {
   return MRCNN_OK;
 }
 
+// Tile-width autotuning at build time: every legal BLOCK_N is timed on the layer's real shape (the result
+// is bit-identical for any width: the K order per output element does not depend on it) and the
+// fastest one is kept.  Small layers are dominated by wave quantisation / per-tile latency, which no
+// static heuristic predicts well.
+int autotune_block_n(mrcnn_engine* e, const mrcnn_conv_desc* d, const void* x, const GemmW& g, const void* residual,
+                     void* out, ConvPlan* plan) {
+  const int cout_total = d->out_mode == 1 ? 4 * d->cout : d->cout;
+  int cap = 32;
+  while (cap < cout_total && cap < 256) cap <<= 1;
+  cudaEvent_t e0, e1;
+  MRCNN_CHECK_CUDA(cudaEventCreate(&e0));
+  MRCNN_CHECK_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  int best_bn = plan->block_n;
+  for (int bn = 32; bn <= cap; bn <<= 1) {
+    if (d->out_mode == 1 && d->cout % bn != 0) continue;
+    ConvPlan trial;
+    if (conv_plan_create(d, x, g.w, g.scale, g.shift, residual, out, bn, &trial) != MRCNN_OK) continue;
+    float tmin = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+      MRCNN_CHECK_CUDA(cudaEventRecord(e0, e->stream));
+      int rc = conv_plan_launch(&trial, e->stream);
+      if (rc) return rc;
+      MRCNN_CHECK_CUDA(cudaEventRecord(e1, e->stream));
+      MRCNN_CHECK_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      MRCNN_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep >= 2 && ms < tmin) tmin = ms;
+    }
+    if (tmin < best * 0.97f) {   // prefer the narrower tile unless the wider one is clearly faster
+      best = tmin;
+      best_bn = bn;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (best_bn != plan->block_n) return conv_plan_create(d, x, g.w, g.scale, g.shift, residual, out, best_bn, plan);
+  return MRCNN_OK;
+}
+
 struct Act {   // NHWC bf16 activation
   __nv_bfloat16* p;
   int n, h, w, c;
@@ -367,6 +409,10 @@ int add_conv(mrcnn_engine* e, const std::string& stage, const std::string& wname
   e->plans.push_back(plan);
   rc = conv_plan_create(&d, in.p, g.w, g.scale, g.shift, residual, t.ptr, 0, plan);
   if (rc) return rc;
+  if (e->autotune) {
+    rc = autotune_block_n(e, &d, in.p, g, residual, t.ptr, plan);
+    if (rc) return rc;
+  }
   e->flops += plan->flops;
   e->steps.push_back({stage, [plan](cudaStream_t st) { return conv_plan_launch(plan, st); }, "conv_gemm", out_name, plan->flops});
   if (out) {
@@ -661,6 +707,8 @@ extern "C" int mrcnn_engine_create(const mrcnn_engine_config* cfg, int device, m
     mrcnn_set_error("engine_create: cudaStreamCreate failed");
     return MRCNN_ERR_CUDA;
   }
+  const char* at = getenv("MRCNN_B200_AUTOTUNE");
+  e->autotune = !(at && at[0] == '0');
   build_layer_table(e);
   *out = e;
   return MRCNN_OK;
