@@ -253,7 +253,11 @@ def main():
     e2e_results = [None]
     pending = [None]
 
+    dbg = [] if os.environ.get("BENCH_DEBUG") else None
+
     def e2e_step(i):
+        if dbg is not None:
+            dbg.append(time.perf_counter())
         h = model.detect_maps_async(host_sets[i % n_sets])
         if pending[0] is not None:
             e2e_results[0] = pending[0].result()
@@ -272,6 +276,8 @@ def main():
     e2e_results[0] = pending[0].result()
     pending[0] = None
     ms_e2e = timed(e2e_step, args.steps)
+    if dbg:
+        sys.stderr.write("e2e host ms between steps: " + " ".join("%.1f" % (1e3 * (b - a)) for a, b in zip(dbg, dbg[1:])) + "\n")
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     D = 100
     h2d = B * S * S * 4 + B * 16 * 4 + B * 16

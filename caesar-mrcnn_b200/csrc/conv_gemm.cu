@@ -17,6 +17,7 @@
 // tile i+1 overlap the epilogue of tile i — layers with K = 64..256 (1-4 k-blocks per tile) are
 // otherwise dominated by per-tile latency.
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include "conv_gemm.cuh"
 
@@ -77,6 +78,16 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// im2col-mode load (3x3 SAME convs whose output maps do not tile into 128-pixel rectangles): 128 consecutive
+// output pixels in (n, h, w) order starting at base pixel (w, h, n) of the padded bounding box, shifted by the
+// filter tap (off_w, off_h); pixels that fall into the padding are zero-filled by the TMA unit
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -197,7 +208,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         const int tw_i = m_tile % p.tiles_w;
         const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
         const int tn_i = m_tile / (p.tiles_w * p.tiles_h);
-        const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.nb;
+        int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.nb;
+        if (p.im2col) {                       // base output pixel of this M tile, in padded-box coordinates
+          const long long m0 = (long long)m_tile * BLOCK_M;
+          const int hw = p.OH * p.OW;
+          n0 = (int)(m0 / hw);
+          const int rem = (int)(m0 - (long long)n0 * hw);
+          h0 = rem / p.OW - p.pad;
+          w0 = rem - (rem / p.OW) * p.OW - p.pad;
+        }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
@@ -208,7 +227,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
           const uint32_t a_dst = base_addr + s * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + Cfg::A_BYTES;
           mbar_expect_tx(full_bar(s), a_bytes + Cfg::B_BYTES);
-          tma_load_4d(a_dst, &tmap_a, full_bar(s), cb * BLOCK_K, w0 + sx - p.pad, h0 + r - p.pad, n0);
+          if (p.im2col)
+            tma_load_im2col_4d(a_dst, &tmap_a, full_bar(s), cb * BLOCK_K, w0, h0, n0, (uint16_t)sx, (uint16_t)r);
+          else
+            tma_load_4d(a_dst, &tmap_a, full_bar(s), cb * BLOCK_K, w0 + sx - p.pad, h0 + r - p.pad, n0);
           tma_load_2d(b_dst, &tmap_b, full_bar(s), kb * BLOCK_K, n_tile * BLOCK_N);
         }
       }
@@ -538,6 +560,47 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+EncodeIm2colFn get_encode_im2col_fn() {
+  static EncodeIm2colFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(sym);
+  });
+  return fn;
+}
+
+// NHWC activation as (C, W, H, N); the base pixel traverses the W x H output positions of a SAME conv:
+// lower corner = -pad, upper corner = pad - (k - 1); 64 channels x 128 pixels per load
+int encode_map_im2col(CUtensorMap* map, const void* ptr, const cuuint64_t* dims, const cuuint64_t* strides_bytes, int pad,
+                      int ksize) {
+  EncodeIm2colFn fn = get_encode_im2col_fn();
+  if (!fn) {
+    mrcnn_set_error("cuTensorMapEncodeIm2col unavailable (no CUDA driver?)");
+    return MRCNN_ERR_CUDA;
+  }
+  const int lower[2] = {-pad, -pad};
+  const int upper[2] = {pad - (ksize - 1), pad - (ksize - 1)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides_bytes, lower, upper,
+                  (cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mrcnn_set_error("cuTensorMapEncodeIm2col failed (%d): dims [%llu,%llu,%llu,%llu]", (int)r, (unsigned long long)dims[0],
+                    (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3]);
+    return MRCNN_ERR_CUDA;
+  }
+  return MRCNN_OK;
+}
+
 int encode_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
@@ -652,8 +715,29 @@ int conv_plan_create(const mrcnn_conv_desc* d, const void* x, const void* w, con
   p.tiles_w = ceil_div(ext_w, p.tw);
   p.tiles_h = ceil_div(ext_h, p.th);
   p.tiles_nb = ceil_div(ext_n, p.nb);
-  box[0] = 64; box[1] = p.tw; box[2] = p.th; box[3] = p.nb;
-  rc = encode_map(&plan->tmap_a, x, 4, dims, strides, box);
+  // 3x3 convs whose maps do not tile into full 128-pixel rectangles (the 14x14 mask-head maps: 126 of 128 rows
+  // per tile and 18 tile rows for 14 map rows = 77 % useful MMA rows) switch to TMA im2col mode, where an M tile
+  // is 128 consecutive output pixels across row and image boundaries
+  p.im2col = 0;
+  if (d->kh == 3) {
+    const double useful = (double)p.M / ((double)p.tiles_w * p.tiles_h * p.tiles_nb * BLOCK_M);
+    const char* env = getenv("MRCNN_B200_IM2COL");          // "0" never, "1" every 3x3 conv, default: when it pays
+    const bool force_on = env && env[0] == '1', force_off = env && env[0] == '0';
+    if (!force_off && (force_on || useful < 0.95)) {
+      MRCNN_REQUIRE((unsigned long long)p.M < (1ull << 31), "conv2d: M too large");
+      p.im2col = 1;
+      p.flat = 1;                 // epilogue rows decode (n, h, w) from the flattened pixel index
+      p.tw = 128; p.th = 1; p.nb = 1;
+      p.tiles_w = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
+      p.tiles_h = 1; p.tiles_nb = 1;
+    }
+  }
+  if (p.im2col) {
+    rc = encode_map_im2col(&plan->tmap_a, x, dims, strides, d->pad, d->kh);
+  } else {
+    box[0] = 64; box[1] = p.tw; box[2] = p.th; box[3] = p.nb;
+    rc = encode_map(&plan->tmap_a, x, 4, dims, strides, box);
+  }
   if (rc) return rc;
 
   // ---- B: weights [cout_total, K] K-major; rows beyond cout_total are OOB -> zero fill --------

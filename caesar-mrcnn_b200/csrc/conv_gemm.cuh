@@ -9,7 +9,8 @@ struct ConvGemmParams {
   int tiles_w, tiles_h, tiles_nb, n_tiles;
   int tw, th, nb;
   int OW, OH, N;      // output spatial size and image count
-  int flat;           // 1x1 stride-1: M tiles run over the flattened pixel index
+  int flat;           // 1x1 stride-1 (and im2col mode): M tiles run over the flattened pixel index
+  int im2col;         // 3x3: A tiles are fetched with TMA im2col-mode loads (128 consecutive output pixels)
   long long M;        // N*OH*OW
   int kh, kw, pad;    // filter taps (stride is folded into the tensor-map view)
   int cin_blocks;     // Cin / 64

@@ -121,6 +121,21 @@ def test_conv_tcgen05_matches_cuda_core_reference(name):
     assert ((a - b).abs() <= (2.0 ** -7) * b.abs() + 1e-3).all()
 
 
+@pytest.mark.parametrize("name", [n for n in CASES if CASES[n]["k"] == 3])
+def test_conv_im2col_mode_every_3x3_shape(name, monkeypatch):
+    """TMA im2col-mode A loads forced on for every 3x3 shape (tile mode is the default where the map tiles
+    into full 128-pixel rectangles): same result as tile mode to the last bit (same K order per element)."""
+    x, w2, scale, shift, res, desc, oshape, odt, ref = make_case(11, **CASES[name])
+    monkeypatch.setenv("MRCNN_B200_IM2COL", "0")
+    a = run_conv(x, w2, scale, shift, res, desc, oshape, odt)
+    monkeypatch.setenv("MRCNN_B200_IM2COL", "1")
+    b = run_conv(x, w2, scale, shift, res, desc, oshape, odt)
+    assert torch.isfinite(b.float()).all()
+    assert torch.equal(a, b)
+    err = (b.float() - ref).abs()
+    assert (err <= (2.0 ** -7) * ref.abs() + 2e-2).all()
+
+
 def test_conv_rejects_unsupported():
     nat = _native()
     lib = nat.lib()
