@@ -141,6 +141,29 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// packed fp32 pairs (Blackwell FFMA2): two IEEE fp32 FMAs per issue slot
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float2 unpack_f32x2(uint64_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+// bf16x2 {hi, lo} = round-to-nearest-even of (max(hi,0), max(lo,0)): ReLU fused into the narrowing conversion
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -279,11 +302,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     const int cout_store = p.out_mode >= 1 ? p.cout : p.out_ld;   // pitch padding is written as zeros
     const bool fused2 = (BLOCK_N == 256) && (p.out_mode == 2);
     float* s_w2 = s_affine + 4 * BLOCK_N;          // [256][4] 1x1-conv weights (nc2 <= 4)
-    float* s_part = s_w2 + 256 * 4;                // [128][8] partial logits of the upper column half
+    float* s_part = s_w2 + 256 * 4;                // [128][4] partial logits of the upper column half
     if (fused2) {
+      // column-pair layout: s_w2[(c/2)*8 + 2*j + (c&1)] = w2[j][c], so one FFMA2 feeds class j from two columns
       for (int i = et; i < 256 * 4; i += EPI_THREADS) {
         const int c = i >> 2, j = i & 3;
-        s_w2[i] = (j < p.nc2) ? __bfloat162float(p.w2[(size_t)j * p.cout + c]) : 0.f;
+        s_w2[(c >> 1) * 8 + 2 * j + (c & 1)] = (j < p.nc2) ? __bfloat162float(p.w2[(size_t)j * p.cout + c]) : 0.f;
       }
     }
     uint32_t tcount = 0;
@@ -349,7 +373,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       if (has_cols) {
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + (uint32_t)c_begin;
         uint32_t vbuf[2][32];
-        float logit[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint64_t lacc[4] = {0ull, 0ull, 0ull, 0ull};   // fused 1x1: per class, (even-column, odd-column) partial sums
         uint4 rbuf[2][4];     // residual of the chunk, fetched one chunk ahead (scattered 16-byte loads)
         const bool res_vec = (res_row != nullptr);
         auto load_residual = [&](int ci, uint4* r) {
@@ -374,7 +398,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
           const uint32_t* v = vbuf[ci & 1];
           const uint4* rr4 = rbuf[ci & 1];
           const int c = c_begin + 32 * ci;                  // column inside the tile
-          if (row_ok) {
+          if (fused2) {
+            // transposed-conv epilogue fused with the 1x1 conv: affine (FFMA2) -> ReLU + bf16 rounding in one
+            // cvt -> 4 FFMA2 per column pair against smem-broadcast weights; nothing is stored per channel
+            if (row_ok) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {   // groups of 4 columns
+                const float4 s4 = *reinterpret_cast<const float4*>(t_scale + c + g * 4);
+                const float4 t4 = *reinterpret_cast<const float4*>(t_shift + c + g * 4);
+                const uint64_t o01 = ffma2(pack_f32x2(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1])),
+                                           pack_f32x2(s4.x, s4.y), pack_f32x2(t4.x, t4.y));
+                const uint64_t o23 = ffma2(pack_f32x2(__uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3])),
+                                           pack_f32x2(s4.z, s4.w), pack_f32x2(t4.z, t4.w));
+                const float2 f01 = unpack_f32x2(o01), f23 = unpack_f32x2(o23);
+                const uint32_t h01 = p.relu ? cvt_relu_bf16x2(f01.x, f01.y) : pack_bf16x2(f01.x, f01.y);
+                const uint32_t h23 = p.relu ? cvt_relu_bf16x2(f23.x, f23.y) : pack_bf16x2(f23.x, f23.y);
+                const uint64_t x01 = pack_f32x2(__uint_as_float(h01 << 16), __uint_as_float(h01 & 0xffff0000u));
+                const uint64_t x23 = pack_f32x2(__uint_as_float(h23 << 16), __uint_as_float(h23 & 0xffff0000u));
+                const float4* wp = reinterpret_cast<const float4*>(s_w2 + (size_t)((c + g * 4) >> 1) * 8);
+                const float4 wa = wp[0], wb = wp[1], wc = wp[2], wd = wp[3];
+                lacc[0] = ffma2(x01, pack_f32x2(wa.x, wa.y), lacc[0]);
+                lacc[1] = ffma2(x01, pack_f32x2(wa.z, wa.w), lacc[1]);
+                lacc[2] = ffma2(x01, pack_f32x2(wb.x, wb.y), lacc[2]);
+                lacc[3] = ffma2(x01, pack_f32x2(wb.z, wb.w), lacc[3]);
+                lacc[0] = ffma2(x23, pack_f32x2(wc.x, wc.y), lacc[0]);
+                lacc[1] = ffma2(x23, pack_f32x2(wc.z, wc.w), lacc[1]);
+                lacc[2] = ffma2(x23, pack_f32x2(wd.x, wd.y), lacc[2]);
+                lacc[3] = ffma2(x23, pack_f32x2(wd.z, wd.w), lacc[3]);
+              }
+            }
+          } else if (row_ok) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {   // groups of 8 columns
               const int ch = ch_base + c + g * 8;
@@ -406,20 +459,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 #pragma unroll
                   for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
                 }
-                if (fused2) {
-                  // 1x1 conv on the bf16-rounded activation, fp32 accumulation; weights broadcast from smem
-                  float4 wv[8];
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) wv[k] = *reinterpret_cast<const float4*>(s_w2 + (size_t)(c + g * 8 + k) * 4);
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) {
-                    const float xb = __bfloat162float(__float2bfloat16_rn(o[k]));
-                    logit[0] = fmaf(xb, wv[k].x, logit[0]);
-                    logit[1] = fmaf(xb, wv[k].y, logit[1]);
-                    logit[2] = fmaf(xb, wv[k].z, logit[2]);
-                    logit[3] = fmaf(xb, wv[k].w, logit[3]);
-                  }
-                } else if (p.out_f32) {
+                if (p.out_f32) {
                   float* dst = static_cast<float*>(p.out) + out_off + ch;
                   *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
                   *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
@@ -434,19 +474,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         }
         if (fused2) {
           // combine the two column halves of each row: half 1 -> smem, half 0 adds, bias, sigmoid, store
-          if (half == 1) {
-            *reinterpret_cast<float4*>(s_part + row * 8) = make_float4(logit[0], logit[1], logit[2], logit[3]);
-            *reinterpret_cast<float4*>(s_part + row * 8 + 4) = make_float4(logit[4], logit[5], logit[6], logit[7]);
+          float logit[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 pr = unpack_f32x2(lacc[j]);
+            logit[j] = pr.x + pr.y;
           }
+          if (half == 1) *reinterpret_cast<float4*>(s_part + row * 4) = make_float4(logit[0], logit[1], logit[2], logit[3]);
           asm volatile("bar.sync 2, 256;" ::: "memory");
           if (half == 0 && row_ok) {
-            const float4 pa = *reinterpret_cast<const float4*>(s_part + row * 8);
-            const float4 pb = *reinterpret_cast<const float4*>(s_part + row * 8 + 4);
-            const float other[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+            const float4 pa = *reinterpret_cast<const float4*>(s_part + row * 4);
+            const float other[4] = {pa.x, pa.y, pa.z, pa.w};
             float* dst = static_cast<float*>(p.out) + out_off;      // out_ld == nc2
-            float sg[8];
+            float sg[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               const float z = logit[j] + other[j] + (j < p.nc2 ? __ldg(p.b2 + j) : 0.f);
               sg[j] = 1.0f / (1.0f + expf(-z));
             }
@@ -454,7 +496,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
               *reinterpret_cast<float4*>(dst) = make_float4(sg[0], sg[1], sg[2], sg[3]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
+              for (int j = 0; j < 4; ++j)
                 if (j < p.nc2) dst[j] = sg[j];
             }
           }

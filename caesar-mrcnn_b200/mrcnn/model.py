@@ -67,6 +67,44 @@ def unmold_image(normalized_images, config):
 # MaskRCNN
 # --------------------------------------------------------------------------------------------
 
+class _PinnedSet(object):
+    """One batch worth of pinned host result buffers (rois, class ids, scores, counts, masks)."""
+
+    def __init__(self, torch, B, D, H0, W0, pin=True):
+        # allocated pinned directly (tensor.pin_memory() would allocate pageable memory first and copy it)
+        self.key = (B, D, H0, W0)
+        self.tensors = (torch.empty((B, D, 4), dtype=torch.int32, pin_memory=pin), torch.empty((B, D), dtype=torch.int32, pin_memory=pin),
+                        torch.empty((B, D), dtype=torch.float32, pin_memory=pin), torch.empty((B,), dtype=torch.int32, pin_memory=pin),
+                        torch.empty((B, H0, W0, D), dtype=torch.uint8, pin_memory=pin))
+
+
+class _Lease(object):
+    """Alive while any numpy array handed to the caller still views the set; returns it to the pool afterwards."""
+
+    def __init__(self, pool, pset):
+        self._pool, self._pset = pool, pset
+
+    def __del__(self):
+        try:
+            self._pool.setdefault(self._pset.key, []).append(self._pset)
+        except Exception:
+            pass
+
+
+class _LeasedArray(object):
+    """numpy-convertible window on one pinned tensor; np.asarray(...) keeps this object (and so the lease) as .base"""
+
+    def __init__(self, lease, tensor, typestr):
+        self._lease, self._tensor = lease, tensor
+        self.__array_interface__ = {"shape": tuple(tensor.shape), "typestr": typestr, "data": (tensor.data_ptr(), False), "version": 3}
+
+
+def _lease_arrays(pool, pset):
+    lease = _Lease(pool, pset)
+    types = ("<i4", "<i4", "<f4", "<i4", "|u1")
+    return tuple(np.asarray(_LeasedArray(lease, t, ts)) for t, ts in zip(pset.tensors, types))
+
+
 class _PendingDetection(object):
     """Handle of an asynchronous detect_maps call (keeps the pinned buffers and inputs alive)."""
 
@@ -141,6 +179,7 @@ class MaskRCNN(object):
         # everything this model launches (torch plumbing included) is ordered on the engine's stream
         self._stream = torch.cuda.ExternalStream(lib.mrcnn_engine_stream(handle), device=int(self._device))
         self._pinned = {}
+        self._result_pool = {}
         return self     # callers only use .predict() on it
 
     def __del__(self):
@@ -346,19 +385,24 @@ class MaskRCNN(object):
 
     # -- detection ------------------------------------------------------------------------------
     def _result_buffers(self, H0, W0):
-        """Pinned host buffers for one batch of results. Fresh per call: the arrays handed back to
-        the caller are views of them (torch's caching host allocator recycles the memory later)."""
+        """Pinned host buffers for one batch of results, as numpy arrays. The arrays handed back to the caller
+        are views of them; a set returns to this model's pool when the last such view is garbage-collected
+        (a fresh 420 MB cudaHostAlloc costs ~0.4 s, so sets are recycled, never freed)."""
         torch = utils._torch()
         c = self.config
-        B, D = c.BATCH_SIZE, c.DETECTION_MAX_INSTANCES
-        # allocated pinned directly (tensor.pin_memory() would allocate pageable memory first and copy it)
-        return (torch.empty((B, D, 4), dtype=torch.int32, pin_memory=True), torch.empty((B, D), dtype=torch.int32, pin_memory=True),
-                torch.empty((B, D), dtype=torch.float32, pin_memory=True), torch.empty((B,), dtype=torch.int32, pin_memory=True),
-                torch.empty((B, H0, W0, D), dtype=torch.uint8, pin_memory=True))
+        key = (c.BATCH_SIZE, c.DETECTION_MAX_INSTANCES, int(H0), int(W0))
+        free = self._result_pool.setdefault(key, [])
+        pset = free.pop() if free else _PinnedSet(torch, *key)
+        return _lease_arrays(self._result_pool, pset)
+
+    def reserve_result_buffers(self, count, H0, W0):
+        """Pre-allocates `count` pinned result sets for [H0, W0] frames (keeps the allocation out of the first calls)."""
+        sets = [self._result_buffers(H0, W0) for _ in range(count)]
+        del sets
 
     @staticmethod
     def _results_from_buffers(bufs, B):
-        rois_n, cls_n, sc_n, cnt_n, m_n = [b.numpy() for b in bufs]
+        rois_n, cls_n, sc_n, cnt_n, m_n = bufs
         out = []
         for i in range(B):
             n = int(cnt_n[i])
@@ -382,7 +426,7 @@ class MaskRCNN(object):
         on_host = 0 if molded.is_cuda else 1
         with torch.cuda.stream(self._stream):
             _native.check(self._lib.mrcnn_engine_detect_molded(self._engine, _native.ptr(molded), on_host, metas32.ctypes.data, orig,
-                                                               wins.ctypes.data, *[_native.ptr(b) for b in bufs]), "detect")
+                                                               wins.ctypes.data, *[b.ctypes.data for b in bufs]), "detect")
         return self._results_from_buffers(bufs, self.config.BATCH_SIZE)
 
     def detect_maps_async(self, maps, zscale_contrasts=(0.25, 0.25, 0.25)):
@@ -420,7 +464,7 @@ class MaskRCNN(object):
         con = _native.float_array(list(zscale_contrasts))
         mean = _native.float_array([float(v) for v in np.asarray(c.MEAN_PIXEL).reshape(-1)[:3]])
         bufs = None if device_only else self._result_buffers(H0, W0)
-        outs = [None] * 5 if device_only else [_native.ptr(b) for b in bufs]
+        outs = [None] * 5 if device_only else [b.ctypes.data for b in bufs]
         slot = self._lib.mrcnn_engine_next_slot(self._engine)
         with torch.cuda.stream(self._stream):
             _native.check(self._lib.mrcnn_engine_detect_maps(self._engine, _native.ptr(maps), 0 if maps.is_cuda else 1, H0, W0, con, mean,

@@ -149,3 +149,27 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
                 assert "oracle/" not in src or f.endswith((".cu", ".cuh")), os.path.join(dirpath, f)
+
+
+def test_result_buffer_sets_return_to_the_pool_when_the_last_view_dies():
+    """detect() hands out numpy views of pinned buffer sets; a set is recycled only after every view is gone."""
+    import gc
+    import torch
+    from mrcnn import model as M
+    pool = {}
+    pset = M._PinnedSet(torch, 2, 3, 4, 5, pin=False)
+    bufs = M._lease_arrays(pool, pset)
+    assert [b.shape for b in bufs] == [(2, 3, 4), (2, 3), (2, 3), (2,), (2, 4, 5, 3)]
+    assert [b.dtype for b in bufs] == [np.int32, np.int32, np.float32, np.int32, np.uint8]
+    bufs[4][:] = 7
+    assert int(pset.tensors[4].sum()) == 7 * 2 * 4 * 5 * 3          # same memory
+    bufs[3][:] = [1, 2]
+    res = M.MaskRCNN._results_from_buffers(bufs, 2)
+    assert res[1]["masks"].shape == (4, 5, 2) and res[1]["masks"].dtype == np.bool_
+    keep = res[1]["masks"]
+    del bufs, res
+    gc.collect()
+    assert not pool.get(pset.key)                                   # one view still alive
+    del keep
+    gc.collect()
+    assert pool[pset.key] == [pset]
