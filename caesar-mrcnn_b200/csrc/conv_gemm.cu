@@ -18,6 +18,7 @@
 // otherwise dominated by per-tile latency.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include <mutex>
 #include "conv_gemm.cuh"
 
@@ -29,15 +30,22 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 320;        // TMA warp + MMA warp + 8 epilogue warps
 constexpr int EPI_THREADS = 256;
 
-template <int BLOCK_N> struct TileCfg {
-  static constexpr int STAGES = (BLOCK_N <= 64) ? 8 : (BLOCK_N == 128 ? 6 : 4);
+// EPI_TMA: the epilogue goes through shared memory: the residual tile is fetched with TMA loads and the
+// bf16 output leaves with TMA stores ([128 rows x 32 channels] boxes, 64B swizzle), so global traffic is
+// full-line and asynchronous instead of one 16-byte piece per thread per row (32 sectors per request).
+template <int BLOCK_N, bool EPI_TMA> struct TileCfg {
+  static constexpr int STAGES = EPI_TMA ? ((BLOCK_N <= 32) ? 8 : (BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 5 : 3)))
+                                        : ((BLOCK_N <= 64) ? 8 : (BLOCK_N == 128 ? 6 : 4));
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_CHUNK_BYTES = BLOCK_M * 32 * 2;                   // 128 rows x 32 bf16
+  static constexpr int STAGING_BYTES = EPI_TMA ? 2 * 3 * EPI_CHUNK_BYTES : 0; // 2 column halves x 3 rotating buffers
   // [acc][scale|shift][BLOCK_N] floats + (fused mask logits) W2 [256][4] floats + partials [128][8] floats
-  static constexpr int EPI_BYTES = 2 * 2 * BLOCK_N * 4 + (BLOCK_N == 256 ? (256 * 4 * 4 + 128 * 8 * 4) : 0);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+  static constexpr int EPI_BYTES = 2 * 2 * BLOCK_N * 4 + ((BLOCK_N == 256 && !EPI_TMA) ? (256 * 4 * 4 + 128 * 8 * 4) : 0);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;   // double-buffered accumulator (64..512, power of two)
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -95,6 +103,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -171,24 +198,29 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool EPI_TMA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                      const __grid_constant__ CUtensorMap tmap_b,
+                                                                     const __grid_constant__ CUtensorMap tmap_out,
+                                                                     const __grid_constant__ CUtensorMap tmap_res,
                                                                      const ConvGemmParams p) {
-  using Cfg = TileCfg<BLOCK_N>;
+  using Cfg = TileCfg<BLOCK_N, EPI_TMA>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment required by the 128B swizzle
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_raw + (base_addr - raw_addr);
-  const uint32_t bar_base = base_addr + STAGES * Cfg::STAGE_BYTES;
+  constexpr int RING_BYTES = STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES;
+  const uint32_t staging_base = base_addr + STAGES * Cfg::STAGE_BYTES;        // [2 halves][3][128 rows x 64 B]
+  const uint32_t bar_base = base_addr + RING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
-  float* s_affine = reinterpret_cast<float*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 256);   // [2][2][BLOCK_N]
+  auto res_bar = [&](int half, int b) { return bar_base + 8u * (2 * STAGES + 4 + half * 3 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + RING_BYTES + 8 * (2 * STAGES + 10));
+  float* s_affine = reinterpret_cast<float*>(base_ptr + RING_BYTES + 256);   // [2][2][BLOCK_N]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -204,6 +236,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
       mbar_init(tmem_empty_bar(a), 8);   // one arrival per epilogue warp
+    }
+    if (EPI_TMA) {
+      for (int b = 0; b < 6; ++b) mbar_init(res_bar(b / 3, b % 3), 1);
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
+      if (p.residual != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_res) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -300,7 +337,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     const bool has_cols = (BLOCK_N >= 64) || (half == 0);
     const int c_begin = (BLOCK_N >= 64) ? half * COLS_PER_WARP : 0;
     const int cout_store = p.out_mode >= 1 ? p.cout : p.out_ld;   // pitch padding is written as zeros
-    const bool fused2 = (BLOCK_N == 256) && (p.out_mode == 2);
+    const bool fused2 = !EPI_TMA && (BLOCK_N == 256) && (p.out_mode == 2);
     float* s_w2 = s_affine + 4 * BLOCK_N;          // [256][4] 1x1-conv weights (nc2 <= 4)
     float* s_part = s_w2 + 256 * 4;                // [128][4] partial logits of the upper column half
     if (fused2) {
@@ -310,6 +347,118 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         s_w2[(c >> 1) * 8 + 2 * j + (c & 1)] = (j < p.nc2) ? __bfloat162float(p.w2[(size_t)j * p.cout + c]) : 0.f;
       }
     }
+    if constexpr (EPI_TMA) {
+      // ===== shared-memory epilogue (flat layers, bf16 out): per column half, 32-channel chunks rotate through
+      // three [128 x 64 B] buffers: TMA-load the residual chunk g+1, update chunk g in place (each thread owns
+      // one row: conflict-free 16-byte accesses under the 64B swizzle), TMA-store it; the store of chunk g-1 is
+      // still draining.  The elected thread of the half issues every bulk copy and owns the bulk groups.
+      constexpr int NCH = COLS_PER_WARP / 32;                 // chunks per tile for this half
+      const bool elected = ((ew & 3) == 0) && (lane == 0);
+      const bool has_res = p.residual != nullptr;
+      const uint32_t half_base = staging_base + (uint32_t)half * 3u * Cfg::EPI_CHUNK_BYTES;
+      const uint32_t row_off = (uint32_t)row * 64u;
+      const uint32_t sw = (uint32_t)((row >> 1) & 3);
+      uint32_t g = 0, tcount = 0;
+      if (has_cols && has_res && elected && (int)blockIdx.x < num_tiles) {   // residual of the very first chunk
+        const int t0 = blockIdx.x;
+        mbar_expect_tx(res_bar(half, 0), Cfg::EPI_CHUNK_BYTES);
+        tma_load_2d(half_base, &tmap_res, res_bar(half, 0), (t0 % p.n_tiles) * BLOCK_N + c_begin, (t0 / p.n_tiles) * BLOCK_M);
+      }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u;
+        const uint32_t aph = (tcount >> 1) & 1u;
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int col_base = n_tile * BLOCK_N;
+        float* t_scale = s_affine + acc * (2 * BLOCK_N);
+        float* t_shift = t_scale + BLOCK_N;
+        for (int c = et; c < BLOCK_N; c += EPI_THREADS) {
+          const int ch = col_base + c;
+          t_scale[c] = ch < p.cout ? __ldg(p.scale + ch) : 0.f;
+          t_shift[c] = ch < p.cout ? __ldg(p.shift + ch) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (has_cols) {
+          const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + (uint32_t)c_begin;
+          uint32_t vbuf[2][32];
+          mbar_wait(tmem_full_bar(acc), aph);
+          __syncwarp();
+          tcgen05_fence_after();
+          tmem_ld_32x32b_x32(t_addr, vbuf[0]);
+#pragma unroll
+          for (int ci = 0; ci < NCH; ++ci, ++g) {
+            const uint32_t b = g % 3u;
+            const uint32_t buf = half_base + b * Cfg::EPI_CHUNK_BYTES;
+            if (has_res) {
+              if (elected) {
+                // chunk g+1 (maybe of this CTA's next tile) -> buffer (g+1)%3, last read by the store of chunk g-2
+                int nt = tile, nci = ci + 1;
+                if (nci == NCH) { nt = tile + gridDim.x; nci = 0; }
+                if (nt < num_tiles) {
+                  bulk_wait_group_read<1>();
+                  const uint32_t nb = (g + 1u) % 3u;
+                  mbar_expect_tx(res_bar(half, nb), Cfg::EPI_CHUNK_BYTES);
+                  tma_load_2d(half_base + nb * Cfg::EPI_CHUNK_BYTES, &tmap_res, res_bar(half, nb),
+                              (nt % p.n_tiles) * BLOCK_N + c_begin + 32 * nci, (nt / p.n_tiles) * BLOCK_M);
+                }
+              }
+              mbar_wait(res_bar(half, b), (g / 3u) & 1u);
+            } else {
+              if (elected) bulk_wait_group_read<2>();          // the store of chunk g-3 has released this buffer
+              named_bar_sync(3 + half, 128);
+            }
+            tmem_ld_wait();                                     // chunk ci has landed
+            if (ci + 1 < NCH) tmem_ld_32x32b_x32(t_addr + (uint32_t)(32 * (ci + 1)), vbuf[(ci + 1) & 1]);
+            const uint32_t* v = vbuf[ci & 1];
+            const int c = c_begin + 32 * ci;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {   // 16-byte pieces = 8 channels
+              const uint32_t addr = buf + row_off + ((((uint32_t)j) ^ sw) << 4);
+              const float4 s0 = *reinterpret_cast<const float4*>(t_scale + c + j * 8);
+              const float4 s1 = *reinterpret_cast<const float4*>(t_scale + c + j * 8 + 4);
+              const float4 t0 = *reinterpret_cast<const float4*>(t_shift + c + j * 8);
+              const float4 t1 = *reinterpret_cast<const float4*>(t_shift + c + j * 8 + 4);
+              const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+              float o[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] = fmaf(__uint_as_float(v[j * 8 + k]), sc[k], sh[k]);
+              if (has_res) {
+                const uint4 r4 = lds128(addr);
+                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  o[2 * k] += __uint_as_float(rw[k] << 16);
+                  o[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
+                }
+              }
+              uint4 ov;
+              if (p.relu) {
+                ov = make_uint4(cvt_relu_bf16x2(o[0], o[1]), cvt_relu_bf16x2(o[2], o[3]), cvt_relu_bf16x2(o[4], o[5]),
+                                cvt_relu_bf16x2(o[6], o[7]));
+              } else {
+                ov = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+              }
+              sts128(addr, ov);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(3 + half, 128);
+            if (elected) {
+              tma_store_2d(&tmap_out, buf, col_base + c, m_tile * BLOCK_M);
+              bulk_commit_group();
+            }
+          }
+        } else {
+          mbar_wait(tmem_full_bar(acc), aph);
+          __syncwarp();
+          tcgen05_fence_after();
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+      }
+      if (elected) bulk_wait_group_all();     // smem must outlive the last store; results visible at kernel end
+    } else {
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1u;
@@ -512,6 +661,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
     }
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -644,7 +794,7 @@ int encode_map_im2col(CUtensorMap* map, const void* ptr, const cuuint64_t* dims,
 }
 
 int encode_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box) {
+               const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     mrcnn_set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -652,7 +802,7 @@ int encode_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* di
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     mrcnn_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r, rank,
@@ -663,20 +813,21 @@ int encode_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* di
   return MRCNN_OK;
 }
 
-template <int BN> int launch_tile(const ConvPlan* plan, cudaStream_t st) {
-  using Cfg = TileCfg<BN>;
+template <int BN, bool EPI> int launch_tile(const ConvPlan* plan, cudaStream_t st) {
+  using Cfg = TileCfg<BN, EPI>;
   static bool attr_done[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_done[dev]) {
-    MRCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MRCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done[dev] = true;
   }
   static int num_sms = 0;
   if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned tiles = plan->grid.x;
   const unsigned grid = tiles < (unsigned)num_sms ? tiles : (unsigned)num_sms;   // one persistent CTA per SM
-  conv_gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(plan->tmap_a, plan->tmap_b, plan->p);
+  conv_gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(plan->tmap_a, plan->tmap_b, plan->tmap_out,
+                                                                         plan->tmap_res, plan->p);
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;
@@ -705,6 +856,18 @@ int validate_desc(const mrcnn_conv_desc* d, int* OH, int* OW) {
 
 int conv_plan_create(const mrcnn_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
                      const void* residual, void* out, int block_n, ConvPlan* plan) {
+  return conv_plan_create_ex(d, x, w, scale, shift, residual, out, block_n, -1, plan);
+}
+
+bool conv_plan_epi_tma_eligible(const mrcnn_conv_desc* d) {
+  const int ld = d->out_ld ? d->out_ld : d->cout;
+  const bool flat = (d->kh == 1 && d->stride == 1) || d->kh == 3;     // 3x3 switches to im2col mode (flat M tiles)
+  return flat && d->out_mode == 0 && d->out_dtype == MRCNN_DTYPE_BF16 && ld == d->cout && d->cout % 8 == 0 &&
+         !d->residual_upsample2;
+}
+
+int conv_plan_create_ex(const mrcnn_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
+                        const void* residual, void* out, int block_n, int epi_tma, ConvPlan* plan) {
   int OH, OW;
   int rc = validate_desc(d, &OH, &OW);
   if (rc) return rc;
@@ -760,11 +923,21 @@ int conv_plan_create(const mrcnn_conv_desc* d, const void* x, const void* w, con
   // 3x3 convs whose maps do not tile into full 128-pixel rectangles (the 14x14 mask-head maps: 126 of 128 rows
   // per tile and 18 tile rows for 14 map rows = 77 % useful MMA rows) switch to TMA im2col mode, where an M tile
   // is 128 consecutive output pixels across row and image boundaries
+  // epilogue through shared memory + TMA (flat bf16 layers): -1 = policy (env MRCNN_B200_EPI_TMA=0/1 overrides;
+  // default on for layers with few k-blocks per tile, which are bound by the epilogue's global traffic)
+  {
+    const bool eligible = conv_plan_epi_tma_eligible(d);
+    const char* env = getenv("MRCNN_B200_EPI_TMA");
+    int want = epi_tma;
+    if (want < 0 && env && (env[0] == '0' || env[0] == '1')) want = env[0] - '0';
+    if (want < 0) want = (d->kh * d->kw * (d->cin / 64) <= 16) ? 1 : 0;
+    plan->epi_tma = (want && eligible) ? 1 : 0;
+  }
   p.im2col = 0;
   if (d->kh == 3) {
     const double useful = (double)p.M / ((double)p.tiles_w * p.tiles_h * p.tiles_nb * BLOCK_M);
     const char* env = getenv("MRCNN_B200_IM2COL");          // "0" never, "1" every 3x3 conv, default: when it pays
-    const bool force_on = env && env[0] == '1', force_off = env && env[0] == '0';
+    const bool force_on = (env && env[0] == '1') || plan->epi_tma, force_off = env && env[0] == '0' && !plan->epi_tma;
     if (!force_off && (force_on || useful < 0.95)) {
       MRCNN_REQUIRE((unsigned long long)p.M < (1ull << 31), "conv2d: M too large");
       p.im2col = 1;
@@ -789,6 +962,20 @@ int conv_plan_create(const mrcnn_conv_desc* d, const void* x, const void* w, con
   cuuint32_t bbox[2] = {64, (cuuint32_t)block_n};
   rc = encode_map(&plan->tmap_b, w, 2, bdims, bstr, bbox);
   if (rc) return rc;
+
+  memset(&plan->tmap_out, 0, sizeof(CUtensorMap));
+  memset(&plan->tmap_res, 0, sizeof(CUtensorMap));
+  if (plan->epi_tma) {
+    cuuint64_t odims[2] = {(cuuint64_t)d->cout, (cuuint64_t)p.M};
+    cuuint64_t ostr[1] = {(cuuint64_t)d->cout * 2};
+    cuuint32_t obox[2] = {32, (cuuint32_t)BLOCK_M};
+    rc = encode_map(&plan->tmap_out, out, 2, odims, ostr, obox, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    if (residual) {
+      rc = encode_map(&plan->tmap_res, residual, 2, odims, ostr, obox, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+  }
 
   p.kh = d->kh; p.kw = d->kw; p.pad = d->pad;
   p.cin_blocks = d->cin / 64;
@@ -817,7 +1004,7 @@ int conv_plan_create(const mrcnn_conv_desc* d, const void* x, const void* w, con
 
 int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, int nc2, void* out) {
   MRCNN_REQUIRE(plan && w2 && b2 && out, "fuse_mask_logits: null pointer");
-  MRCNN_REQUIRE(plan->block_n == 256 && plan->p.out_mode == 1 && plan->p.cout == 256,
+  MRCNN_REQUIRE(plan->block_n == 256 && plan->p.out_mode == 1 && plan->p.cout == 256 && !plan->epi_tma,
                 "fuse_mask_logits: needs a 256-channel transposed-conv plan with 256-wide tiles");
   MRCNN_REQUIRE(nc2 >= 1 && nc2 <= 4, "fuse_mask_logits: nc2=%d outside [1,4]", nc2);
   plan->p.out_mode = 2;
@@ -831,11 +1018,20 @@ int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, 
 }
 
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t st) {
-  switch (plan->block_n) {
-    case 32: return launch_tile<32>(plan, st);
-    case 64: return launch_tile<64>(plan, st);
-    case 128: return launch_tile<128>(plan, st);
-    case 256: return launch_tile<256>(plan, st);
+  if (plan->epi_tma) {
+    switch (plan->block_n) {
+      case 32: return launch_tile<32, true>(plan, st);
+      case 64: return launch_tile<64, true>(plan, st);
+      case 128: return launch_tile<128, true>(plan, st);
+      case 256: return launch_tile<256, true>(plan, st);
+    }
+  } else {
+    switch (plan->block_n) {
+      case 32: return launch_tile<32, false>(plan, st);
+      case 64: return launch_tile<64, false>(plan, st);
+      case 128: return launch_tile<128, false>(plan, st);
+      case 256: return launch_tile<256, false>(plan, st);
+    }
   }
   mrcnn_set_error("conv2d: bad block_n %d", plan->block_n);
   return MRCNN_ERR_INVALID;

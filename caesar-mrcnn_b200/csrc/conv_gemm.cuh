@@ -31,6 +31,9 @@ struct ConvGemmParams {
 struct ConvPlan {
   CUtensorMap tmap_a;
   CUtensorMap tmap_b;
+  CUtensorMap tmap_out;        // epi_tma: [M, cout] bf16 output, box 32 ch x 128 rows, 64B swizzle
+  CUtensorMap tmap_res;        // epi_tma: same geometry over the residual tensor
+  int epi_tma = 0;             // epilogue through shared memory with TMA residual loads / output stores
   ConvGemmParams p;
   int block_n;
   dim3 grid;
@@ -42,6 +45,10 @@ struct ConvPlan {
 // stay valid for the life of the plan.  block_n = 0 picks a tile width from cout.
 int conv_plan_create(const mrcnn_conv_desc* d, const void* x, const void* w, const float* scale,
                      const float* shift, const void* residual, void* out, int block_n, ConvPlan* plan);
+// epi_tma: -1 = policy, 0 = direct stores, 1 = TMA epilogue when the layer is eligible (results are bit-identical)
+int conv_plan_create_ex(const mrcnn_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
+                        const void* residual, void* out, int block_n, int epi_tma, ConvPlan* plan);
+bool conv_plan_epi_tma_eligible(const mrcnn_conv_desc* d);
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);
 // turns a 256-channel deconv plan (block_n 256) into deconv + ReLU + 1x1 conv (nc2) + sigmoid -> float32 out
 int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, int nc2, void* out);

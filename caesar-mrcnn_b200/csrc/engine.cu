@@ -348,30 +348,35 @@ int autotune_block_n(mrcnn_engine* e, const mrcnn_conv_desc* d, const void* x, c
   MRCNN_CHECK_CUDA(cudaEventCreate(&e0));
   MRCNN_CHECK_CUDA(cudaEventCreate(&e1));
   float best = 1e30f;
-  int best_bn = plan->block_n;
-  for (int bn = 32; bn <= cap; bn <<= 1) {
-    if (d->out_mode == 1 && d->cout % bn != 0) continue;
-    ConvPlan trial;
-    if (conv_plan_create(d, x, g.w, g.scale, g.shift, residual, out, bn, &trial) != MRCNN_OK) continue;
-    float tmin = 1e30f;
-    for (int rep = 0; rep < 6; ++rep) {
-      MRCNN_CHECK_CUDA(cudaEventRecord(e0, e->stream));
-      int rc = conv_plan_launch(&trial, e->stream);
-      if (rc) return rc;
-      MRCNN_CHECK_CUDA(cudaEventRecord(e1, e->stream));
-      MRCNN_CHECK_CUDA(cudaEventSynchronize(e1));
-      float ms = 0.f;
-      MRCNN_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-      if (rep >= 2 && ms < tmin) tmin = ms;
-    }
-    if (tmin < best * 0.97f) {   // prefer the narrower tile unless the wider one is clearly faster
-      best = tmin;
-      best_bn = bn;
+  int best_bn = plan->block_n, best_epi = plan->epi_tma;
+  const int n_epi = conv_plan_epi_tma_eligible(d) ? 2 : 1;
+  for (int epi = 0; epi < n_epi; ++epi) {
+    for (int bn = 32; bn <= cap; bn <<= 1) {
+      if (d->out_mode == 1 && d->cout % bn != 0) continue;
+      ConvPlan trial;
+      if (conv_plan_create_ex(d, x, g.w, g.scale, g.shift, residual, out, bn, epi, &trial) != MRCNN_OK) continue;
+      float tmin = 1e30f;
+      for (int rep = 0; rep < 6; ++rep) {
+        MRCNN_CHECK_CUDA(cudaEventRecord(e0, e->stream));
+        int rc = conv_plan_launch(&trial, e->stream);
+        if (rc) return rc;
+        MRCNN_CHECK_CUDA(cudaEventRecord(e1, e->stream));
+        MRCNN_CHECK_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        MRCNN_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep >= 2 && ms < tmin) tmin = ms;
+      }
+      if (tmin < best * 0.97f) {   // keep the earlier candidate unless the new one is clearly faster
+        best = tmin;
+        best_bn = bn;
+        best_epi = epi;
+      }
     }
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  if (best_bn != plan->block_n) return conv_plan_create(d, x, g.w, g.scale, g.shift, residual, out, best_bn, plan);
+  if (best_bn != plan->block_n || best_epi != plan->epi_tma)
+    return conv_plan_create_ex(d, x, g.w, g.scale, g.shift, residual, out, best_bn, best_epi, plan);
   return MRCNN_OK;
 }
 

@@ -136,6 +136,25 @@ def test_conv_im2col_mode_every_3x3_shape(name, monkeypatch):
     assert (err <= (2.0 ** -7) * ref.abs() + 2e-2).all()
 
 
+EPI_TMA_CASES = [n for n, c in CASES.items() if not c.get("deconv") and not c.get("out_f32") and not c.get("res_up2")
+                 and c.get("stride", 1) == 1 and c["cout"] % 8 == 0]
+
+
+@pytest.mark.parametrize("name", EPI_TMA_CASES)
+def test_conv_tma_epilogue_is_bit_identical(name, monkeypatch):
+    """Shared-memory epilogue (TMA residual loads + TMA output stores, 64B swizzle) against the direct-store
+    epilogue: the arithmetic per element is the same, so the bf16 outputs must be equal bit for bit."""
+    x, w2, scale, shift, res, desc, oshape, odt, ref = make_case(13, **CASES[name])
+    monkeypatch.setenv("MRCNN_B200_EPI_TMA", "0")
+    a = run_conv(x, w2, scale, shift, res, desc, oshape, odt)
+    monkeypatch.setenv("MRCNN_B200_EPI_TMA", "1")
+    b = run_conv(x, w2, scale, shift, res, desc, oshape, odt)
+    assert torch.isfinite(b.float()).all(), "non-finite output (unwritten rows?)"
+    assert torch.equal(a, b)
+    err = (b.float() - ref).abs()
+    assert (err <= (2.0 ** -7) * ref.abs() + 2e-2).all()
+
+
 def test_conv_rejects_unsupported():
     nat = _native()
     lib = nat.lib()
