@@ -14,32 +14,53 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// A[(b*OH+oh)*OW+ow][k], k = (r*7+s)*3+c for k < 147, zero for 147 <= k < KPAD (=192)
-__global__ void stem_im2col_kernel(const float* __restrict__ img, int B, int S, __nv_bfloat16* __restrict__ A) {
-  constexpr int KPAD = 192, VEC = 8, VPR = KPAD / VEC;   // 24 vectors per row
+// A[(b*OH+oh)*OW+ow][k], k = r*24 + s*3 + c (s*3+c < 21; the 3 tail entries of each 24-group and k >= 168 are
+// zero; KPAD = 192).  A filter row of a patch is 21 contiguous floats of the NHWC image, so one CTA stages the 7
+// zero-padded input rows of one output row in shared memory as bf16 (each pixel converted once) and every thread
+// then emits aligned 16-byte vectors: 4 x LDS.32 + one coalesced STG.128, no per-element index arithmetic.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, int B, int S, int RW,
+                                                          __nv_bfloat16* __restrict__ A) {
+  extern __shared__ uint32_t stem_smem[];                       // [7][RW] bf16, RW even
+  __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(stem_smem);
   const int OH = S / 2, OW = S / 2;
-  const size_t total = (size_t)B * OH * OW * VPR;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int v = (int)(idx % VPR);
-    size_t row = idx / VPR;
-    const int ow = (int)(row % OW);
-    const int oh = (int)((row / OW) % OH);
-    const int b = (int)(row / ((size_t)OW * OH));
-    float vals[VEC];
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const int k = v * VEC + j;
-      float x = 0.f;
-      if (k < 147) {
-        const int tap = k / 3, c = k - tap * 3;
-        const int r = tap / 7, s = tap - r * 7;
-        const int ih = oh * 2 + r - 3, iw = ow * 2 + s - 3;
-        if (ih >= 0 && ih < S && iw >= 0 && iw < S) x = __ldg(img + (((size_t)b * S + ih) * S + iw) * 3 + c);
+  const int b = blockIdx.x / OH, oh = blockIdx.x - b * OH;
+  const int n4 = S * 3 / 4;                                     // float4 chunks per image row
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  for (int i = threadIdx.x; i < 7 * RW; i += blockDim.x) {      // padding (and rows outside the image)
+    const int r = i / RW, q = i - r * RW;
+    const int ih = oh * 2 + r - 3;
+    if (q < 9 || q >= 9 + 3 * S || ih < 0 || ih >= S) srow[i] = zero;
+  }
+  for (int i = threadIdx.x; i < 7 * n4; i += blockDim.x) {
+    const int r = i / n4, c4 = i - r * n4;
+    const int ih = oh * 2 + r - 3;
+    if (ih < 0 || ih >= S) continue;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(img + ((size_t)b * S + ih) * S * 3) + c4);
+    __nv_bfloat16* d = srow + r * RW + 9 + c4 * 4;              // odd element offset: 2 + 4 + 2 byte stores
+    d[0] = __float2bfloat16_rn(v.x);
+    *reinterpret_cast<uint32_t*>(d + 1) = pack2(v.y, v.z);
+    d[3] = __float2bfloat16_rn(v.w);
+  }
+  __syncthreads();
+  const uint32_t* sw = stem_smem;
+  const int RW2 = RW / 2;
+  __nv_bfloat16* arow = A + (size_t)blockIdx.x * OW * 192;
+  for (int idx = threadIdx.x; idx < OW * 24; idx += blockDim.x) {
+    const int ow = idx / 24, v = idx - ow * 24;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (v < 21) {
+      const int r = v / 3, part = v - r * 3;
+      const uint32_t* src = sw + r * RW2 + ow * 3 + part * 4;   // element ow*6 + part*8
+      o.x = src[0];
+      o.y = src[1];
+      o.z = src[2];
+      o.w = src[3];
+      if (part == 2) {                                          // elements 21..23 of the group are padding
+        o.z &= 0x0000ffffu;
+        o.w = 0u;
       }
-      vals[j] = x;
     }
-    uint4 o = make_uint4(pack2(vals[0], vals[1]), pack2(vals[2], vals[3]), pack2(vals[4], vals[5]), pack2(vals[6], vals[7]));
-    *reinterpret_cast<uint4*>(A + row * KPAD + (size_t)v * VEC) = o;
+    *reinterpret_cast<uint4*>(arow + (size_t)idx * 8) = o;
   }
 }
 
@@ -147,8 +168,20 @@ int grid_for(size_t total, int threads) {
 }  // namespace
 
 int launch_stem_im2col(const float* img, int B, int S, __nv_bfloat16* A, cudaStream_t st) {
-  const size_t total = (size_t)B * (S / 2) * (S / 2) * 24;
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(img, B, S, A);
+  MRCNN_REQUIRE(S % 4 == 0, "stem_im2col: image size must be a multiple of 4");
+  const int RW = ((S + 6) * 3 + 7) & ~7;
+  const size_t smem = (size_t)7 * RW * 2;
+  MRCNN_REQUIRE(smem <= 200 * 1024, "stem_im2col: image rows of %d pixels do not fit in shared memory", S);
+  if (smem > 48 * 1024) {
+    static size_t attr_bytes[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && attr_bytes[dev] < smem) {
+      MRCNN_CHECK_CUDA(cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_bytes[dev] = smem;
+    }
+  }
+  stem_im2col_kernel<<<B * (S / 2), 256, smem, st>>>(img, B, S, RW, A);
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;

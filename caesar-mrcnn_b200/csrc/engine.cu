@@ -98,8 +98,14 @@ struct mrcnn_engine {
   std::vector<std::string> stage_names;
   std::vector<cudaEvent_t> stage_events;  // stage_names.size() + 1
   bool autotune = true;
-  bool profiling = false;
-  std::vector<cudaEvent_t> step_events;   // steps.size() + 1, recorded when profiling
+  int profiling = 0;                      // 0 off, 1 events around every launch, 2 events at kernel-family boundaries
+  std::vector<cudaEvent_t> step_events;   // steps.size() + 1, recorded when profiling == 1
+  // profiling == 2: a "run" is a maximal sequence of consecutive launches of one family; kRunSets event sets are
+  // cycled so the last kRunSets predicts can be read back after a timed loop without a sync inside it
+  static constexpr int kRunSets = 8;
+  std::vector<int> run_first;             // first step index of each run
+  std::vector<cudaEvent_t> run_events[kRunSets];   // runs + 1 per set
+  unsigned long long run_calls = 0;
   std::vector<std::string> kind_names;    // scratch for kernel_times()
   // unmold scratch
   void* unmold_ws = nullptr;
@@ -279,7 +285,18 @@ int build_weights(mrcnn_engine* e) {
     int kpad = kh * kw * cin;
     if (l.name == "conv1") kpad = 192;
     std::vector<uint16_t> w;
-    conv_to_gemm(l.host[0], kh, kw, cin, cout, kpad, &w);
+    if (l.name == "conv1") {
+      // stem im2col K order (elementwise.cu): k = r*24 + s*3 + c, 3 zero entries per filter row, zero tail
+      w.assign((size_t)cout * kpad, 0);
+      if (!l.host[0].empty())
+        for (int r = 0; r < kh; ++r)
+          for (int sx = 0; sx < kw; ++sx)
+            for (int c = 0; c < cin; ++c)
+              for (int o = 0; o < cout; ++o)
+                w[(size_t)o * kpad + r * 24 + sx * cin + c] = f2bf(l.host[0][(((size_t)r * kw + sx) * cin + c) * cout + o]);
+    } else {
+      conv_to_gemm(l.host[0], kh, kw, cin, cout, kpad, &w);
+    }
     // BN partner by naming convention
     std::string bn;
     if (l.name == "conv1") bn = "bn_conv1";
@@ -657,7 +674,7 @@ int build_graph(mrcnn_engine* e) {
 }
 
 int run_steps(mrcnn_engine* e, const char* only_stage, bool timed) {
-  size_t si = 0;
+  size_t si = 0, run_i = 0;
   std::string cur;
   for (const Step& s : e->steps) {
     if (only_stage && s.stage != only_stage) continue;
@@ -667,11 +684,19 @@ int run_steps(mrcnn_engine* e, const char* only_stage, bool timed) {
       cur = s.stage;
     }
     const size_t step_i = (size_t)(&s - &e->steps[0]);
-    if (e->profiling && !only_stage) MRCNN_CHECK_CUDA(cudaEventRecord(e->step_events[step_i], e->stream));
+    if (e->profiling == 1 && !only_stage) MRCNN_CHECK_CUDA(cudaEventRecord(e->step_events[step_i], e->stream));
+    if (e->profiling == 2 && !only_stage && run_i < e->run_first.size() && (size_t)e->run_first[run_i] == step_i) {
+      MRCNN_CHECK_CUDA(cudaEventRecord(e->run_events[e->run_calls % mrcnn_engine::kRunSets][run_i], e->stream));
+      ++run_i;
+    }
     int rc = s.run(e->stream);
     if (rc) return rc;
   }
-  if (e->profiling && !only_stage) MRCNN_CHECK_CUDA(cudaEventRecord(e->step_events[e->steps.size()], e->stream));
+  if (e->profiling == 1 && !only_stage) MRCNN_CHECK_CUDA(cudaEventRecord(e->step_events[e->steps.size()], e->stream));
+  if (e->profiling == 2 && !only_stage) {
+    MRCNN_CHECK_CUDA(cudaEventRecord(e->run_events[e->run_calls % mrcnn_engine::kRunSets][e->run_first.size()], e->stream));
+    ++e->run_calls;
+  }
   if (timed) MRCNN_CHECK_CUDA(cudaEventRecord(e->stage_events[e->stage_names.size()], e->stream));
   return MRCNN_OK;
 }
@@ -924,12 +949,24 @@ extern "C" double mrcnn_engine_flops(const mrcnn_engine* e) { return e ? e->flop
 
 extern "C" int mrcnn_engine_set_profiling(mrcnn_engine* e, int enable) {
   MRCNN_REQUIRE(e && e->finalized, "set_profiling: engine not finalized");
+  MRCNN_REQUIRE(enable >= 0 && enable <= 2, "set_profiling: mode must be 0, 1 or 2");
   MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
-  if (enable && e->step_events.empty()) {
+  if (enable == 1 && e->step_events.empty()) {
     e->step_events.resize(e->steps.size() + 1);
     for (auto& ev : e->step_events) MRCNN_CHECK_CUDA(cudaEventCreate(&ev));
   }
-  e->profiling = enable != 0;
+  if (enable == 2) {
+    if (e->run_first.empty()) {
+      for (size_t i = 0; i < e->steps.size(); ++i)
+        if (i == 0 || e->steps[i].kind != e->steps[i - 1].kind) e->run_first.push_back((int)i);
+      for (auto& set : e->run_events) {
+        set.resize(e->run_first.size() + 1);
+        for (auto& ev : set) MRCNN_CHECK_CUDA(cudaEventCreate(&ev));
+      }
+    }
+    e->run_calls = 0;
+  }
+  e->profiling = enable;
   return MRCNN_OK;
 }
 
@@ -951,12 +988,45 @@ extern "C" int mrcnn_engine_step_info(mrcnn_engine* e, int index, const char** l
 }
 
 extern "C" int mrcnn_engine_kernel_times(mrcnn_engine* e, int max_kinds, const char** names, float* ms, int* launches) {
-  MRCNN_REQUIRE(e && e->finalized && !e->step_events.empty(), "kernel_times: profiling was never enabled");
+  MRCNN_REQUIRE(e && e->finalized && (!e->step_events.empty() || !e->run_first.empty()), "kernel_times: profiling was never enabled");
   MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
   MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
   e->kind_names.clear();
   std::vector<float> tot;
   std::vector<int> cnt;
+  if (e->profiling == 2) {
+    // average over the predicts still held by the event ring (the last kRunSets of them)
+    const int nsets = (int)(e->run_calls < (unsigned long long)mrcnn_engine::kRunSets ? e->run_calls : mrcnn_engine::kRunSets);
+    MRCNN_REQUIRE(nsets > 0, "kernel_times: no profiled predict has completed yet");
+    const size_t nruns = e->run_first.size();
+    for (size_t r = 0; r < nruns; ++r) {
+      const size_t first = (size_t)e->run_first[r];
+      const size_t last = r + 1 < nruns ? (size_t)e->run_first[r + 1] : e->steps.size();
+      float sum = 0.f;
+      for (int sidx = 0; sidx < nsets; ++sidx) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, e->run_events[sidx][r], e->run_events[sidx][r + 1]) != cudaSuccess) {
+          mrcnn_set_error("kernel_times: profiled predict not complete");
+          return MRCNN_ERR_INVALID;
+        }
+        sum += t;
+      }
+      const std::string& kind = e->steps[first].kind;
+      size_t k = 0;
+      for (; k < e->kind_names.size(); ++k) if (e->kind_names[k] == kind) break;
+      if (k == e->kind_names.size()) { e->kind_names.push_back(kind); tot.push_back(0.f); cnt.push_back(0); }
+      tot[k] += sum / nsets;
+      cnt[k] += (int)(last - first);
+    }
+    const int n = (int)e->kind_names.size();
+    for (int k = 0; k < n && k < max_kinds; ++k) {
+      if (names) names[k] = e->kind_names[k].c_str();
+      if (ms) ms[k] = tot[k];
+      if (launches) launches[k] = cnt[k];
+    }
+    return n;
+  }
+  MRCNN_REQUIRE(!e->step_events.empty(), "kernel_times: per-launch profiling was never enabled");
   for (size_t i = 0; i < e->steps.size(); ++i) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, e->step_events[i], e->step_events[i + 1]) != cudaSuccess) {

@@ -21,6 +21,7 @@ struct RoiParams {
   float image_area;
   void* out;            // [B,N,P,P,C]
   int32_t* levels;      // [B,N] or null
+  unsigned long long one2;  // (1.0f, 1.0f) as a packed fp32 pair, see f2_add
 };
 
 // mrcnn/model.py:465-477 — level = min(5, max(2, 4 + int32(round(log2(sqrt(h*w)/(224/sqrt(area)))))))
@@ -68,6 +69,50 @@ template <> struct Vec<__nv_bfloat16> {
   }
 };
 
+// Packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): every lane of a pair is an IEEE round-to-nearest fp32
+// operation, so the samples are bit-identical to the scalar left-to-right evaluation.  ptxas contracts a packed
+// mul.rn + add.rn pair into one FFMA2 even under -fmad=false (it does not for scalar fp32), which would round
+// once instead of twice; the addition is therefore issued as fma(t, one, a) with `one` = (1.0f, 1.0f) taken
+// from the kernel parameters (opaque to the optimizer): t*1 is exact, so the result is exactly t + a.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b, uint64_t one) {   // a + b
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(b), "l"(one), "l"(a));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t b, uint64_t a) {   // b - a
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(b), "l"(a));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_from_bf16x2(uint32_t w) {
+  return f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(uint64_t v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// tf.image.crop_and_resize bilinear sample of two channels: top = tl + (tr - tl)*lx; bot likewise; top + (bot - top)*ly
+__device__ __forceinline__ uint32_t lerp_bf16x2(uint32_t tl, uint32_t tr, uint32_t bl, uint32_t br, uint64_t lx, uint64_t ly,
+                                                uint64_t one) {
+  const uint64_t a = f2_from_bf16x2(tl), b = f2_from_bf16x2(tr), c = f2_from_bf16x2(bl), d = f2_from_bf16x2(br);
+  const uint64_t top = f2_add(a, f2_mul(f2_sub(b, a), lx), one);
+  const uint64_t bot = f2_add(c, f2_mul(f2_sub(d, c), lx), one);
+  return f2_to_bf16x2(f2_add(top, f2_mul(f2_sub(bot, top), ly), one));
+}
+
 // One CTA per ROI.  Thread 0 computes the pyramid level; the P sample rows / columns of the crop are
 // then computed once per ROI into shared memory (tf.image.crop_and_resize coordinates, float32,
 // left-to-right evaluation) as element offsets + lerp weights; each warp takes output pixels
@@ -76,8 +121,11 @@ template <> struct Vec<__nv_bfloat16> {
 // beyond four integer adds.
 constexpr int ROI_MAX_P = 32;
 
+// 7 warps: the 49 (7x7) and 196 (14x14) output pixels of the two heads split evenly over them
+constexpr int ROI_THREADS = 224;
+
 template <typename T>
-__global__ void __launch_bounds__(256) roialign_kernel(RoiParams p) {
+__global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiParams p) {
   constexpr int VN = Vec<T>::N;
   __shared__ int s_lo[2][ROI_MAX_P], s_hi[2][ROI_MAX_P];   // element offsets: [0] rows (t*W*C, b*W*C), [1] cols (l*C, r*C); -1 = outside
   __shared__ float s_w[2][ROI_MAX_P];                      // lerp weights
@@ -120,6 +168,57 @@ __global__ void __launch_bounds__(256) roialign_kernel(RoiParams p) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if constexpr (sizeof(T) == 2) {
+    if (C == 256) {
+      // bf16, 256 channels (the engine's pyramid): one lane per 16-byte vector covers a pixel with one warp pass;
+      // two output pixels per iteration keep 8 independent 16-byte gathers in flight per lane
+      const T* fb = feat + lane * 8;
+      const int npix = P * P;
+      const uint64_t one2 = p.one2;
+      auto sample = [&](int pix, uint4& tl, uint4& tr, uint4& bl, uint4& br, uint64_t& lx2, uint64_t& ly2) -> bool {
+        const int iy = pix / P, ix = pix - iy * P;
+        const int ro0 = s_lo[0][iy], ro1 = s_hi[0][iy], co0 = s_lo[1][ix], co1 = s_hi[1][ix];
+        const float ly = s_w[0][iy], lx = s_w[1][ix];
+        lx2 = f2_pack(lx, lx);
+        ly2 = f2_pack(ly, ly);
+        const bool valid = (ro0 >= 0) && (co0 >= 0);
+        if (valid) {
+          tl = __ldg(reinterpret_cast<const uint4*>(fb + ro0 + co0));
+          tr = __ldg(reinterpret_cast<const uint4*>(fb + ro0 + co1));
+          bl = __ldg(reinterpret_cast<const uint4*>(fb + ro1 + co0));
+          br = __ldg(reinterpret_cast<const uint4*>(fb + ro1 + co1));
+        }
+        return valid;
+      };
+      auto finish = [&](int pix, bool valid, const uint4& tl, const uint4& tr, const uint4& bl, const uint4& br, uint64_t lx2,
+                        uint64_t ly2) {
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
+          o.x = lerp_bf16x2(tl.x, tr.x, bl.x, br.x, lx2, ly2, one2);
+          o.y = lerp_bf16x2(tl.y, tr.y, bl.y, br.y, lx2, ly2, one2);
+          o.z = lerp_bf16x2(tl.z, tr.z, bl.z, br.z, lx2, ly2, one2);
+          o.w = lerp_bf16x2(tl.w, tr.w, bl.w, br.w, lx2, ly2, one2);
+        }
+        __stcs(reinterpret_cast<uint4*>(out + (size_t)pix * 256 + lane * 8), o);
+      };
+      int pix = warp;
+      for (; pix + nwarps < npix; pix += 2 * nwarps) {
+        uint4 a0, b0, c0, d0, a1, b1, c1, d1;
+        uint64_t lx0, ly0, lx1, ly1;
+        const bool v0 = sample(pix, a0, b0, c0, d0, lx0, ly0);
+        const bool v1 = sample(pix + nwarps, a1, b1, c1, d1, lx1, ly1);
+        finish(pix, v0, a0, b0, c0, d0, lx0, ly0);
+        finish(pix + nwarps, v1, a1, b1, c1, d1, lx1, ly1);
+      }
+      if (pix < npix) {
+        uint4 a0, b0, c0, d0;
+        uint64_t lx0, ly0;
+        const bool v0 = sample(pix, a0, b0, c0, d0, lx0, ly0);
+        finish(pix, v0, a0, b0, c0, d0, lx0, ly0);
+      }
+      return;
+    }
+  }
   int iy = warp / P, ix = warp - iy * P;
   for (int pix = warp; pix < P * P; pix += nwarps) {
     const int ro0 = s_lo[0][iy], ro1 = s_hi[0][iy], co0 = s_lo[1][ix], co1 = s_hi[1][ix];
@@ -200,10 +299,11 @@ int launch_pyramid_roi_align(const void* const* feature_maps, const int* feat_h,
   p.image_area = image_area;
   p.out = pooled;
   p.levels = levels;
+  p.one2 = 0x3f8000003f800000ull;
   if (dtype == MRCNN_DTYPE_F32)
-    roialign_kernel<float><<<batch * num_boxes, 256, 0, st>>>(p);
+    roialign_kernel<float><<<batch * num_boxes, ROI_THREADS, 0, st>>>(p);
   else
-    roialign_kernel<__nv_bfloat16><<<batch * num_boxes, 256, 0, st>>>(p);
+    roialign_kernel<__nv_bfloat16><<<batch * num_boxes, ROI_THREADS, 0, st>>>(p);
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;

@@ -501,7 +501,9 @@ class MaskRCNN(object):
         return out
 
     def set_profiling(self, on=True):
-        _native.check(self._lib.mrcnn_engine_set_profiling(self._engine, 1 if on else 0), "set_profiling")
+        """False/0 off; True/1 CUDA events around every launch; 2 events at kernel-family boundaries only
+        (cheap; kernel_times() then averages the last <= 8 predicts)."""
+        _native.check(self._lib.mrcnn_engine_set_profiling(self._engine, int(on)), "set_profiling")
 
     def flops_per_predict(self):
         return float(self._lib.mrcnn_engine_flops(self._engine))

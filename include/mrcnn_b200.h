@@ -238,6 +238,10 @@ int mrcnn_engine_stage_times(const mrcnn_engine* e, int max_stages, const char**
 /* Per-kernel-family device time of the last predict (CUDA events recorded around every launch
  * on the engine stream while profiling is enabled): returns the number of families; names[k] in
  * {"conv_gemm","roialign","proposal","detection","stem_im2col","maxpool",...}. */
+/* enable: 0 off; 1 events around every launch (per-launch table via mrcnn_engine_step_info, times of the last
+ * predict); 2 events only where the kernel family changes between consecutive launches (~35 instead of ~150
+ * per predict), kept for the last 8 predicts so a timed loop needs no sync: kernel_times then returns the
+ * per-predict average over those. */
 int mrcnn_engine_set_profiling(mrcnn_engine* e, int enable);
 int mrcnn_engine_kernel_times(mrcnn_engine* e, int max_kinds, const char** names, float* ms, int* launches);
 /* one launch of the plan: label (output tensor), kernel family, device ms of the last profiled
