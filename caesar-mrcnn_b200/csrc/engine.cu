@@ -619,13 +619,15 @@ int build_graph(mrcnn_engine* e) {
   }
 
   // ---- mask head ---------------------------------------------------------------------------------
-  Tensor t_pm;
+  Tensor t_pm, t_lvl_mask;
   RC(new_tensor(e, "pooled_mask", DT_BF16, (size_t)B * D * MP * MP * PY, &t_pm));
+  RC(new_tensor(e, "roi_levels_mask", DT_I32, (size_t)B * D, &t_lvl_mask, true));
   {
     const float* det = static_cast<const float*>(t_det.ptr);
     void* pm = t_pm.ptr;
+    int32_t* lvm = static_cast<int32_t*>(t_lvl_mask.ptr);
     e->steps.push_back({"roialign_mask", [=](cudaStream_t st) {
-      return launch_pyramid_roi_align(fp.p, fp.h, fp.w, PY, MRCNN_DTYPE_BF16, det, 6, B, D, MP, image_area, pm, nullptr, st);
+      return launch_pyramid_roi_align(fp.p, fp.h, fp.w, PY, MRCNN_DTYPE_BF16, det, 6, B, D, MP, image_area, pm, lvm, st);
     }, "roialign"});
   }
   Act m = {static_cast<__nv_bfloat16*>(t_pm.ptr), B * D, MP, MP, PY};

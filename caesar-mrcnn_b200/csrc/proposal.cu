@@ -6,6 +6,8 @@
 // clip_boxes_graph) and the per-image Python unrolling of utils.batch_slice (utils.py:872-906).
 // Bit-exact contract: top-k indices, NMS keep indices and rois equal oracle/graph_layers.py
 // proposal_layer() for identical float32 inputs.
+#include <stdio.h>
+#include <stdlib.h>
 #include "box_ops.cuh"
 #include "mrcnn_b200.h"
 
@@ -31,6 +33,7 @@ struct PropParams {
   int32_t* keep_cnt;  // [B] or null
   int r0_bytes;
   int kept_off;   // byte offset of the kept list inside region 0
+  long long* phase_clocks;   // debug: [B][8] clock64() at the phase boundaries (null = off)
 };
 
 __device__ __forceinline__ int block_excl_scan_flag(bool flag, int* warp_tot, int& total) {
@@ -70,6 +73,7 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
   unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(r0);
   const float* scores = p.rpn_class + (size_t)b * A * 2 + 1;             // fg score, stride 2
 
+  if (p.phase_clocks && tid == 0) p.phase_clocks[(size_t)b * 8 + 0] = clock64();
   // ---- 1. radix select: key of the K-th largest score ---------------------------------------
   uint32_t prefix = 0, mask = 0;
   int need = K;
@@ -104,6 +108,7 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
   const uint32_t T = prefix;       // K-th largest key; `need` elements equal to T are taken,
   const int cnt_gt = K - need;     // lowest indices first (tf.nn.top_k tie rule)
 
+  if (p.phase_clocks && tid == 0) p.phase_clocks[(size_t)b * 8 + 1] = clock64();
   // ---- 2. compaction into the sort buffer -----------------------------------------------------
   if (tid == 0) misc[2] = 0;
   for (int i = K + tid; i < Kpad; i += nt) sortbuf[i] = 0ull;
@@ -124,6 +129,7 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
   }
   __syncthreads();
 
+  if (p.phase_clocks && tid == 0) p.phase_clocks[(size_t)b * 8 + 2] = clock64();
   // ---- 3. bitonic sort, descending on (key, ~index) ------------------------------------------
   for (int k = 2; k <= Kpad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -142,6 +148,7 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
     }
   }
 
+  if (p.phase_clocks && tid == 0) p.phase_clocks[(size_t)b * 8 + 3] = clock64();
   // ---- 4. gather + decode + clip --------------------------------------------------------------
   const float* deltas = p.rpn_bbox + (size_t)b * A * 4;
   const float* anch = p.anchors + (size_t)b * p.anchor_bstride;
@@ -159,6 +166,7 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
   }
   __syncthreads();
 
+  if (p.phase_clocks && tid == 0) p.phase_clocks[(size_t)b * 8 + 4] = clock64();
   // ---- 5. pop order: identity unless scores tie, else popped lazily from the emulated heap ------
   HeapEntry* heap = reinterpret_cast<HeapEntry*>(r0);                  // 1-indexed: [K+2], 16-byte aligned
   uint16_t* order = reinterpret_cast<uint16_t*>(heap + ((K + 2 + 1) & ~1));   // [K]
@@ -181,6 +189,7 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
   }
   __syncthreads();
 
+  if (p.phase_clocks && tid == 0) p.phase_clocks[(size_t)b * 8 + 5] = clock64();
   // ---- 6. NMS + output ------------------------------------------------------------------------
   const int count = block_nms(boxes, order, K, R, p.thr, kept_box, kept_area, selected, sc, any_tie ? heap : nullptr);
   __syncthreads();
@@ -197,6 +206,7 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
     if (p.keep_idx) p.keep_idx[(size_t)b * R + r] = cand;
   }
   if (tid == 0 && p.keep_cnt) p.keep_cnt[b] = count;
+  if (p.phase_clocks && tid == 0) p.phase_clocks[(size_t)b * 8 + 6] = clock64();
 }
 
 int next_pow2(int v) {
@@ -261,8 +271,19 @@ extern "C" int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbo
   size_t smem = prop_smem_bytes(K, proposal_count, &p.r0_bytes, &p.kept_off);
   MRCNN_REQUIRE(smem <= 227 * 1024, "proposal_layer: shared memory %zu exceeds 227 KB", smem);
   MRCNN_CHECK_CUDA(cudaFuncSetAttribute(proposal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  p.phase_clocks = nullptr;
+  const char* dbg = getenv("MRCNN_B200_PROPOSAL_CLOCKS");       // debug: per-phase SM clock counts of image 0 on stderr
+  if (dbg && dbg[0] == '1') MRCNN_CHECK_CUDA(cudaMalloc((void**)&p.phase_clocks, (size_t)batch * 8 * sizeof(long long)));
   proposal_kernel<<<batch, PROP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
+  if (p.phase_clocks) {
+    long long h[8];
+    MRCNN_CHECK_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    MRCNN_CHECK_CUDA(cudaMemcpy(h, p.phase_clocks, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "proposal phases (cycles, image 0): select %lld compact %lld sort %lld decode %lld heap-init %lld nms %lld total %lld\n",
+            h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[6] - h[0]);
+    cudaFree(p.phase_clocks);
+  }
   return MRCNN_OK;
 }

@@ -21,6 +21,7 @@ struct RoiParams {
   float image_area;
   void* out;            // [B,N,P,P,C]
   int32_t* levels;      // [B,N] or null
+  int levels_ready;     // levels[] was filled by roi_levels_kernel (all ROIs in parallel) before this launch
   unsigned long long one2;  // (1.0f, 1.0f) as a packed fp32 pair, see f2_add
 };
 
@@ -134,13 +135,19 @@ __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiParams p) {
   const int b = roi / p.N;
   const float* bp = p.boxes + (size_t)roi * p.box_stride;
   const float y1 = bp[0], x1 = bp[1], y2 = bp[2], x2 = bp[3];
-  if (threadIdx.x == 0) {
-    const int lv = roi_level(y1, x1, y2, x2, p.image_area);
-    s_level = lv;
-    if (p.levels) p.levels[roi] = lv;
+  int li;
+  if (p.levels_ready) {
+    li = p.levels[roi] - 2;
+  } else {
+    // one thread evaluates the double-precision log; the whole CTA waits (only used when no level buffer is given)
+    if (threadIdx.x == 0) {
+      const int lv = roi_level(y1, x1, y2, x2, p.image_area);
+      s_level = lv;
+      if (p.levels) p.levels[roi] = lv;
+    }
+    __syncthreads();
+    li = s_level - 2;
   }
-  __syncthreads();
-  const int li = s_level - 2;
   const int H = p.H[li], W = p.W[li], C = p.C, P = p.P;
   const T* feat = static_cast<const T*>(p.feat[li]) + (size_t)b * H * W * C;
   T* out = static_cast<T*>(p.out) + (size_t)roi * P * P * C;
@@ -258,11 +265,11 @@ __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiParams p) {
   }
 }
 
-__global__ void roi_levels_kernel(const float* boxes, int n, float image_area, int32_t* levels) {
+__global__ void roi_levels_kernel(const float* boxes, int box_stride, int n, float image_area, int32_t* levels) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const float4 bx = *reinterpret_cast<const float4*>(boxes + (size_t)i * 4);
-    levels[i] = roi_level(bx.x, bx.y, bx.z, bx.w, image_area);
+    const float* bx = boxes + (size_t)i * box_stride;
+    levels[i] = roi_level(bx[0], bx[1], bx[2], bx[3], image_area);
   }
 }
 
@@ -270,7 +277,7 @@ __global__ void roi_levels_kernel(const float* boxes, int n, float image_area, i
 
 extern "C" int mrcnn_roi_levels(const float* boxes, int num_boxes, float image_area, int32_t* levels, void* stream) {
   MRCNN_REQUIRE(boxes && levels && num_boxes > 0, "roi_levels: bad arguments");
-  roi_levels_kernel<<<ceil_div(num_boxes, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(boxes, num_boxes, image_area, levels);
+  roi_levels_kernel<<<ceil_div(num_boxes, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(boxes, 4, num_boxes, image_area, levels);
   MRCNN_CHECK_CUDA(cudaGetLastError());
   return MRCNN_OK;
 }
@@ -299,6 +306,13 @@ int launch_pyramid_roi_align(const void* const* feature_maps, const int* feat_h,
   p.image_area = image_area;
   p.out = pooled;
   p.levels = levels;
+  p.levels_ready = 0;
+  if (levels) {   // all levels in one parallel pass instead of one serial double-log per ROI CTA
+    roi_levels_kernel<<<ceil_div(batch * num_boxes, 256), 256, 0, st>>>(boxes, box_stride, batch * num_boxes, image_area, levels);
+    MRCNN_CHECK_CUDA(cudaGetLastError());
+    mrcnn_count_launch(1);
+    p.levels_ready = 1;
+  }
   p.one2 = 0x3f8000003f800000ull;
   if (dtype == MRCNN_DTYPE_F32)
     roialign_kernel<float><<<batch * num_boxes, ROI_THREADS, 0, st>>>(p);
