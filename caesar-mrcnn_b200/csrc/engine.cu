@@ -7,6 +7,7 @@
 // needs ~12 GB of the 180 GB); weights are bf16 [Cout, KH*KW*Cin] (K-major GEMM-B operands) with
 // the frozen BatchNorm folded into per-channel fp32 (scale, shift) applied in the GEMM epilogue.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <functional>
@@ -98,6 +99,9 @@ struct mrcnn_engine {
   std::vector<std::string> stage_names;
   std::vector<cudaEvent_t> stage_events;  // stage_names.size() + 1
   bool autotune = true;
+  std::map<std::string, std::pair<int, int>> tune_cache;   // layer key -> (BLOCK_N, epi_tma)
+  bool tune_cache_dirty = false;
+  std::string tune_cache_path;
   int profiling = 0;                      // 0 off, 1 events around every launch, 2 events at kernel-family boundaries
   std::vector<cudaEvent_t> step_events;   // steps.size() + 1, recorded when profiling == 1
   // profiling == 2: a "run" is a maximal sequence of consecutive launches of one family; kRunSets event sets are
@@ -432,8 +436,22 @@ int add_conv(mrcnn_engine* e, const std::string& stage, const std::string& wname
   rc = conv_plan_create(&d, in.p, g.w, g.scale, g.shift, residual, t.ptr, 0, plan);
   if (rc) return rc;
   if (e->autotune) {
-    rc = autotune_block_n(e, &d, in.p, g, residual, t.ptr, plan);
-    if (rc) return rc;
+    // optional on-disk cache of the choices (MRCNN_B200_AUTOTUNE_CACHE=<file>): a second process — e.g. the same
+    // workload under ncu — builds exactly the same launch plan without re-timing (and without the timing launches)
+    char key[160];
+    snprintf(key, sizeof(key), "%s:%d:%d:%d:%d:%d:%d:%d:%d", out_name.c_str(), d.n, d.h, d.w, d.cin, d.cout, k, stride, out_mode);
+    auto hit = e->tune_cache.find(key);
+    if (hit != e->tune_cache.end()) {
+      if (hit->second.first != plan->block_n || hit->second.second != plan->epi_tma) {
+        rc = conv_plan_create_ex(&d, in.p, g.w, g.scale, g.shift, residual, t.ptr, hit->second.first, hit->second.second, plan);
+        if (rc) return rc;
+      }
+    } else {
+      rc = autotune_block_n(e, &d, in.p, g, residual, t.ptr, plan);
+      if (rc) return rc;
+      e->tune_cache[key] = std::make_pair(plan->block_n, plan->epi_tma);
+      e->tune_cache_dirty = true;
+    }
   }
   e->flops += plan->flops;
   e->steps.push_back({stage, [plan](cudaStream_t st) { return conv_plan_launch(plan, st); }, "conv_gemm", out_name, plan->flops});
@@ -741,6 +759,15 @@ extern "C" int mrcnn_engine_create(const mrcnn_engine_config* cfg, int device, m
   }
   const char* at = getenv("MRCNN_B200_AUTOTUNE");
   e->autotune = !(at && at[0] == '0');
+  if (const char* cp = getenv("MRCNN_B200_AUTOTUNE_CACHE")) {
+    e->tune_cache_path = cp;
+    if (FILE* f = fopen(cp, "r")) {
+      char key[160];
+      int bn, epi;
+      while (fscanf(f, "%159s %d %d", key, &bn, &epi) == 3) e->tune_cache[key] = std::make_pair(bn, epi);
+      fclose(f);
+    }
+  }
   build_layer_table(e);
   *out = e;
   return MRCNN_OK;
@@ -824,6 +851,13 @@ extern "C" int mrcnn_engine_finalize(mrcnn_engine* e, int allow_missing) {
   int rc = build_weights(e);
   if (rc) return rc;
   rc = build_graph(e);
+  if (rc == MRCNN_OK && e->tune_cache_dirty && !e->tune_cache_path.empty()) {
+    if (FILE* f = fopen(e->tune_cache_path.c_str(), "w")) {
+      for (const auto& kv : e->tune_cache) fprintf(f, "%s %d %d\n", kv.first.c_str(), kv.second.first, kv.second.second);
+      fclose(f);
+    }
+    e->tune_cache_dirty = false;
+  }
   if (rc) return rc;
   for (LayerSpec& l : e->layers) { l.host.clear(); l.host.shrink_to_fit(); l.host.resize(l.nweights); }
   MRCNN_CHECK_CUDA(cudaDeviceSynchronize());
