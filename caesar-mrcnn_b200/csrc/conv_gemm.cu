@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + RING_BYTES + 8 * (2 * STAGES + 10));
   float* s_affine = reinterpret_cast<float*>(base_ptr + RING_BYTES + 256);   // [2][2][BLOCK_N]
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = p.kh * p.kw * p.cin_blocks;
@@ -256,6 +257,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barriers, TMEM, tensor-map prefetch) overlapped the tail of the previous kernel of the
+  // stream; from here on its outputs are read (A operand, residual) and this layer's output is written
+  pdl_wait();
 
   if (warp == 0) {
     // ===== TMA producer: runs ahead across tile boundaries, bounded only by the smem ring =====
@@ -826,9 +830,8 @@ template <int BN, bool EPI> int launch_tile(const ConvPlan* plan, cudaStream_t s
   if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned tiles = plan->grid.x;
   const unsigned grid = tiles < (unsigned)num_sms ? tiles : (unsigned)num_sms;   // one persistent CTA per SM
-  conv_gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(plan->tmap_a, plan->tmap_b, plan->tmap_out,
-                                                                         plan->tmap_res, plan->p);
-  MRCNN_CHECK_CUDA(cudaGetLastError());
+  MRCNN_CHECK_CUDA(mrcnn_launch(conv_gemm_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, plan->tmap_a,
+                                plan->tmap_b, plan->tmap_out, plan->tmap_res, plan->p));
   mrcnn_count_launch(1);
   return MRCNN_OK;
 }

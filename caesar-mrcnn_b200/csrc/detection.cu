@@ -87,6 +87,7 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long* buf, int n_pad)
 }
 
 __global__ void __launch_bounds__(DET_THREADS, 1) detection_kernel(DetParams p) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DetSmem& s = *reinterpret_cast<DetSmem*>(smem_raw);
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -238,7 +239,7 @@ extern "C" int mrcnn_detection_layer(const float* rois, const float* mrcnn_class
   p.thr = nms_threshold;
   p.det = detections;
   MRCNN_CHECK_CUDA(cudaFuncSetAttribute(detection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DetSmem)));
-  detection_kernel<<<batch, DET_THREADS, sizeof(DetSmem), static_cast<cudaStream_t>(stream)>>>(p);
+  MRCNN_CHECK_CUDA(mrcnn_launch(detection_kernel, dim3(batch), dim3(DET_THREADS), sizeof(DetSmem), static_cast<cudaStream_t>(stream), p));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;

@@ -20,6 +20,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // then emits aligned 16-byte vectors: 4 x LDS.32 + one coalesced STG.128, no per-element index arithmetic.
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, int B, int S, int RW,
                                                           __nv_bfloat16* __restrict__ A) {
+  pdl_prologue();
   extern __shared__ uint32_t stem_smem[];                       // [7][RW] bf16, RW even
   __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(stem_smem);
   const int OH = S / 2, OW = S / 2;
@@ -73,6 +74,7 @@ __device__ __forceinline__ void max8(uint4& acc, const uint4 v) {
 
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
                                     __nv_bfloat16* __restrict__ y) {
+  pdl_prologue();
   const int OH = (H + 1) / 2, OW = (W + 1) / 2;
   const int pt_h = max((OH - 1) * 2 + 3 - H, 0) / 2, pt_w = max((OW - 1) * 2 + 3 - W, 0) / 2;
   const int cv = C / 8;
@@ -101,6 +103,7 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int B, 
 
 __global__ void subsample2_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
                                   __nv_bfloat16* __restrict__ y) {
+  pdl_prologue();
   const int OH = (H + 1) / 2, OW = (W + 1) / 2, cv = C / 8;
   const size_t total = (size_t)B * OH * OW * cv;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -117,6 +120,7 @@ __global__ void subsample2_kernel(const __nv_bfloat16* __restrict__ x, int B, in
 // head [B*hw, ld] f32: cols [0, 2*apl) class logits (anchor a -> 2a,2a+1), cols [2*apl, 6*apl) deltas (4a+k)
 __global__ void rpn_post_kernel(const float* __restrict__ head, int ld, int B, int hw, int apl, int A, int level_off,
                                 float* __restrict__ rpn_class, float* __restrict__ rpn_bbox) {
+  pdl_prologue();
   const int total = B * hw * apl;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int a = idx % apl;
@@ -137,6 +141,7 @@ __global__ void rpn_post_kernel(const float* __restrict__ head, int ld, int B, i
 // head [M, ld] f32: cols [0,NC) logits, cols [NC, 5*NC) bbox deltas (4*cls+k)
 __global__ void class_post_kernel(const float* __restrict__ head, int ld, int M, int NC, float* __restrict__ probs,
                                   float* __restrict__ bbox) {
+  pdl_prologue();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
     const float* row = head + (size_t)i * ld;
     float m = row[0];
@@ -150,6 +155,7 @@ __global__ void class_post_kernel(const float* __restrict__ head, int ld, int M,
 }
 
 __global__ void mask_post_kernel(const float* __restrict__ logits, int ld, size_t M, int NC, float* __restrict__ out) {
+  pdl_prologue();
   const size_t total = M * NC;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const size_t r = idx / NC;
@@ -181,40 +187,40 @@ int launch_stem_im2col(const float* img, int B, int S, __nv_bfloat16* A, cudaStr
       attr_bytes[dev] = smem;
     }
   }
-  stem_im2col_kernel<<<B * (S / 2), 256, smem, st>>>(img, B, S, RW, A);
+  MRCNN_CHECK_CUDA(mrcnn_launch(stem_im2col_kernel, dim3(B * (S / 2)), dim3(256), smem, st, img, B, S, RW, A));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;
 }
 int launch_maxpool3x3s2(const __nv_bfloat16* x, int B, int H, int W, int C, __nv_bfloat16* y, cudaStream_t st) {
   const size_t total = (size_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, B, H, W, C, y);
+  MRCNN_CHECK_CUDA(mrcnn_launch(maxpool3x3s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, x, B, H, W, C, y));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;
 }
 int launch_subsample2(const __nv_bfloat16* x, int B, int H, int W, int C, __nv_bfloat16* y, cudaStream_t st) {
   const size_t total = (size_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  subsample2_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, B, H, W, C, y);
+  MRCNN_CHECK_CUDA(mrcnn_launch(subsample2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, x, B, H, W, C, y));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;
 }
 int launch_rpn_post(const float* head, int ld, int B, int hw, int apl, int A, int level_off, float* rpn_class,
                     float* rpn_bbox, cudaStream_t st) {
-  rpn_post_kernel<<<grid_for((size_t)B * hw * apl, 256), 256, 0, st>>>(head, ld, B, hw, apl, A, level_off, rpn_class, rpn_bbox);
+  MRCNN_CHECK_CUDA(mrcnn_launch(rpn_post_kernel, dim3(grid_for((size_t)B * hw * apl, 256)), dim3(256), 0, st, head, ld, B, hw, apl, A, level_off, rpn_class, rpn_bbox));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;
 }
 int launch_class_post(const float* head, int ld, int M, int NC, float* probs, float* bbox, cudaStream_t st) {
-  class_post_kernel<<<grid_for((size_t)M, 256), 256, 0, st>>>(head, ld, M, NC, probs, bbox);
+  MRCNN_CHECK_CUDA(mrcnn_launch(class_post_kernel, dim3(grid_for((size_t)M, 256)), dim3(256), 0, st, head, ld, M, NC, probs, bbox));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;
 }
 int launch_mask_post(const float* logits, int ld, size_t M, int NC, float* out, cudaStream_t st) {
-  mask_post_kernel<<<grid_for(M * NC, 256), 256, 0, st>>>(logits, ld, M, NC, out);
+  MRCNN_CHECK_CUDA(mrcnn_launch(mask_post_kernel, dim3(grid_for(M * NC, 256)), dim3(256), 0, st, logits, ld, M, NC, out));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;

@@ -1229,6 +1229,7 @@ extern "C" int mrcnn_engine_detect_maps(mrcnn_engine* e, const float* maps, int 
     e->cur_slot ^= 1;
     return MRCNN_OK;                 // caller collects with mrcnn_engine_wait()
   }
+  if (async) return MRCNN_OK;        // device-only and asynchronous: results stay in the unmold_* tensors, no sync
   RC(fetch_internal(e, slot, false, orig_hw, rois_host, class_ids_host, scores_host, counts_host, masks_host));
   MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
   return MRCNN_OK;

@@ -51,6 +51,7 @@ __device__ __forceinline__ float zscale_apply(float x, float vmin32, float rng32
 }
 
 __global__ void __launch_bounds__(ZS_THREADS, 1) zscale_params_kernel(ZParams p) {
+  pdl_prologue();
   __shared__ float s_samp[1024];
   __shared__ unsigned char s_bad[1024];
   __shared__ unsigned char s_bad2[1024];
@@ -213,12 +214,14 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zscale_params_kernel(ZParams p)
 }
 
 __global__ void init_minmax_kernel(int32_t* minmax, int n) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { minmax[2 * i] = 255; minmax[2 * i + 1] = 0; }
 }
 
 __global__ void stretch_rgb8_kernel(const float* __restrict__ maps, const float* __restrict__ params, int H, int W,
                                     uint8_t* __restrict__ rgb, int32_t* __restrict__ minmax) {
+  pdl_prologue();
   const int img = blockIdx.y;
   const size_t npx = (size_t)H * W;
   const float* pr = params + (size_t)img * 12;
@@ -262,6 +265,7 @@ __device__ __forceinline__ double px_or_zero(const uint8_t* img, int H, int W, i
 }
 
 __global__ void resize_pad_mold_kernel(MoldParams p) {
+  pdl_prologue();
   const int img = blockIdx.y;
   const size_t total = (size_t)p.SH * p.SW;
   const uint8_t* src = p.rgb + (size_t)img * p.H * p.W * 3;
@@ -315,7 +319,7 @@ extern "C" int mrcnn_zscale_params(const float* maps, int n_images, int height, 
   ZParams p;
   p.maps = maps; p.H = height; p.W = width; p.params = params;
   for (int i = 0; i < 3; ++i) p.contrast[i] = contrasts3[i];
-  zscale_params_kernel<<<n_images, ZS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MRCNN_CHECK_CUDA(mrcnn_launch(zscale_params_kernel, dim3(n_images), dim3(ZS_THREADS), 0, static_cast<cudaStream_t>(stream), p));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;
@@ -326,11 +330,11 @@ extern "C" int mrcnn_stretch_to_rgb8(const float* maps, const float* params, int
   MRCNN_REQUIRE(maps && params && rgb && minmax, "stretch_to_rgb8: null pointer");
   MRCNN_REQUIRE(n_images > 0 && height > 0 && width > 0, "stretch_to_rgb8: empty input");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  init_minmax_kernel<<<ceil_div(n_images, 128), 128, 0, st>>>(minmax, n_images);
+  MRCNN_CHECK_CUDA(mrcnn_launch(init_minmax_kernel, dim3(ceil_div(n_images, 128)), dim3(128), 0, st, minmax, n_images));
   const size_t npx = (size_t)height * width;
   int bx = (int)((npx + 255) / 256);
   if (bx > 148 * 4) bx = 148 * 4;
-  stretch_rgb8_kernel<<<dim3(bx, n_images), 256, 0, st>>>(maps, params, height, width, rgb, minmax);
+  MRCNN_CHECK_CUDA(mrcnn_launch(stretch_rgb8_kernel, dim3(dim3(bx, n_images)), dim3(256), 0, st, maps, params, height, width, rgb, minmax));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(2);
   return MRCNN_OK;
@@ -350,7 +354,7 @@ extern "C" int mrcnn_resize_pad_mold(const uint8_t* rgb, const int32_t* minmax, 
   const size_t total = (size_t)square * square;
   int bx = (int)((total + 255) / 256);
   if (bx > 148 * 4) bx = 148 * 4;
-  resize_pad_mold_kernel<<<dim3(bx, n_images), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MRCNN_CHECK_CUDA(mrcnn_launch(resize_pad_mold_kernel, dim3(dim3(bx, n_images)), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;

@@ -55,6 +55,7 @@ __device__ __forceinline__ int block_excl_scan_flag(bool flag, int* warp_tot, in
 }
 
 __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
@@ -274,7 +275,7 @@ extern "C" int mrcnn_proposal_layer(const float* rpn_class, const float* rpn_bbo
   p.phase_clocks = nullptr;
   const char* dbg = getenv("MRCNN_B200_PROPOSAL_CLOCKS");       // debug: per-phase SM clock counts of image 0 on stderr
   if (dbg && dbg[0] == '1') MRCNN_CHECK_CUDA(cudaMalloc((void**)&p.phase_clocks, (size_t)batch * 8 * sizeof(long long)));
-  proposal_kernel<<<batch, PROP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  MRCNN_CHECK_CUDA(mrcnn_launch(proposal_kernel, dim3(batch), dim3(PROP_THREADS), smem, static_cast<cudaStream_t>(stream), p));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   if (p.phase_clocks) {

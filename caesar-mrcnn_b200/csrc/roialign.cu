@@ -127,6 +127,7 @@ constexpr int ROI_THREADS = 224;
 
 template <typename T>
 __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiParams p) {
+  pdl_prologue();
   constexpr int VN = Vec<T>::N;
   __shared__ int s_lo[2][ROI_MAX_P], s_hi[2][ROI_MAX_P];   // element offsets: [0] rows (t*W*C, b*W*C), [1] cols (l*C, r*C); -1 = outside
   __shared__ float s_w[2][ROI_MAX_P];                      // lerp weights
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiParams p) {
 }
 
 __global__ void roi_levels_kernel(const float* boxes, int box_stride, int n, float image_area, int32_t* levels) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const float* bx = boxes + (size_t)i * box_stride;
@@ -277,7 +279,7 @@ __global__ void roi_levels_kernel(const float* boxes, int box_stride, int n, flo
 
 extern "C" int mrcnn_roi_levels(const float* boxes, int num_boxes, float image_area, int32_t* levels, void* stream) {
   MRCNN_REQUIRE(boxes && levels && num_boxes > 0, "roi_levels: bad arguments");
-  roi_levels_kernel<<<ceil_div(num_boxes, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(boxes, 4, num_boxes, image_area, levels);
+  MRCNN_CHECK_CUDA(mrcnn_launch(roi_levels_kernel, dim3(ceil_div(num_boxes, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), boxes, 4, num_boxes, image_area, levels));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   return MRCNN_OK;
 }
@@ -308,16 +310,16 @@ int launch_pyramid_roi_align(const void* const* feature_maps, const int* feat_h,
   p.levels = levels;
   p.levels_ready = 0;
   if (levels) {   // all levels in one parallel pass instead of one serial double-log per ROI CTA
-    roi_levels_kernel<<<ceil_div(batch * num_boxes, 256), 256, 0, st>>>(boxes, box_stride, batch * num_boxes, image_area, levels);
+    MRCNN_CHECK_CUDA(mrcnn_launch(roi_levels_kernel, dim3(ceil_div(batch * num_boxes, 256)), dim3(256), 0, st, boxes, box_stride, batch * num_boxes, image_area, levels));
     MRCNN_CHECK_CUDA(cudaGetLastError());
     mrcnn_count_launch(1);
     p.levels_ready = 1;
   }
   p.one2 = 0x3f8000003f800000ull;
   if (dtype == MRCNN_DTYPE_F32)
-    roialign_kernel<float><<<batch * num_boxes, ROI_THREADS, 0, st>>>(p);
+    MRCNN_CHECK_CUDA(mrcnn_launch(roialign_kernel<float>, dim3(batch * num_boxes), dim3(ROI_THREADS), 0, st, p));
   else
-    roialign_kernel<__nv_bfloat16><<<batch * num_boxes, ROI_THREADS, 0, st>>>(p);
+    MRCNN_CHECK_CUDA(mrcnn_launch(roialign_kernel<__nv_bfloat16>, dim3(batch * num_boxes), dim3(ROI_THREADS), 0, st, p));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;

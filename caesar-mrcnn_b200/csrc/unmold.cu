@@ -37,6 +37,7 @@ struct UnmoldParams {
 };
 
 __global__ void unmold_boxes_kernel(UnmoldParams p) {
+  pdl_prologue();
   extern __shared__ int s_int[];
   int* s_valid = s_int;            // [D]
   int* s_first0 = s_int + p.D;     // [1]
@@ -114,6 +115,7 @@ __global__ void unmold_boxes_kernel(UnmoldParams p) {
 constexpr int PAINT_THREADS = 128;
 
 __global__ void __launch_bounds__(PAINT_THREADS) unmold_paint_kernel(UnmoldParams p) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int D = p.D;
   DetRec* s_rec = reinterpret_cast<DetRec*>(s_raw);                         // [D]
@@ -195,12 +197,12 @@ extern "C" int mrcnn_unmold_detections(const float* detections, const float* mrc
   p.recs = static_cast<DetRec*>(workspace); p.out = masks;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int threads = ((max_instances + 31) / 32) * 32;
-  unmold_boxes_kernel<<<batch, threads, (max_instances + 1) * sizeof(int), st>>>(p);
+  MRCNN_CHECK_CUDA(mrcnn_launch(unmold_boxes_kernel, dim3(batch), dim3(threads), (max_instances + 1) * sizeof(int), st, p));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   const size_t npx = (size_t)p.H0 * p.W0;
   const size_t smem = (((size_t)max_instances * sizeof(DetRec) + 15) & ~(size_t)15) + (size_t)PAINT_THREADS * max_instances + 16;
   MRCNN_CHECK_CUDA(cudaFuncSetAttribute(unmold_paint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  unmold_paint_kernel<<<dim3((unsigned)((npx + PAINT_THREADS - 1) / PAINT_THREADS), batch), PAINT_THREADS, smem, st>>>(p);
+  MRCNN_CHECK_CUDA(mrcnn_launch(unmold_paint_kernel, dim3(dim3((unsigned)((npx + PAINT_THREADS - 1) / PAINT_THREADS), batch)), dim3(PAINT_THREADS), smem, st, p));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(2);
   return MRCNN_OK;

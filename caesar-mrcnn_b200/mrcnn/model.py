@@ -472,7 +472,7 @@ class MaskRCNN(object):
                                                              metas32.ctypes.data, wins.ctypes.data, *outs, 1 if _async else 0),
                           "detect_maps")
         if device_only:
-            return None
+            return None          # with _async=True nothing has been waited for: call wait() before reading tensors
         if _async:
             return _PendingDetection(self, bufs, maps, slot)
         return self._results_from_buffers(bufs, c.BATCH_SIZE)
