@@ -140,9 +140,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--image-size", type=int, default=S, help="IMAGE_MAX_DIM (256 = the run.py configuration the metric is "
+                    "quoted on; 1024 = base Config stress size, use --batch 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    global S, WORKLOAD
+    if args.image_size != S or args.batch != BATCH:
+        S = args.image_size
+        WORKLOAD = "batched detect, %d synthetic radio maps at IMAGE_MAX_DIM=%d (secondary size; BASELINE.json configs[1] is 64 maps at 256)" % (args.batch, S)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -306,7 +312,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "image_size": S, "num_classes": 4, "weights": "seeded random (LFS pointer unresolved)",
-                       "l2": "4 rotated input batches; per-step working set ~12 GB >> 126 MB L2", "parallelism": "batch-sharded, no collective"},
+                       "l2": "4 rotated input batches; per-step working set (activations) is GBs >> 126 MB L2", "parallelism": "batch-sharded, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_families": stages,
             "stage_ms_per_step": {k: v / nprof for k, v in st_acc.items()},

@@ -180,49 +180,68 @@ __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiParams p) {
     if (C == 256) {
       // bf16, 256 channels (the engine's pyramid): one lane per 16-byte vector covers a pixel with one warp pass;
       // two output pixels per iteration keep 8 independent 16-byte gathers in flight per lane
-      const T* fb = feat + lane * 8;
+      // 32-bit byte offsets from one 64-bit lane base, (iy, ix) advanced incrementally: no integer division and no
+      // 64-bit index arithmetic per gather
+      const char* fb = reinterpret_cast<const char*>(feat) + lane * 16;
+      char* ob = reinterpret_cast<char*>(out) + lane * 16;
       const int npix = P * P;
       const uint64_t one2 = p.one2;
-      auto sample = [&](int pix, uint4& tl, uint4& tr, uint4& bl, uint4& br, uint64_t& lx2, uint64_t& ly2) -> bool {
-        const int iy = pix / P, ix = pix - iy * P;
+      struct Px {
+        uint4 tl, tr, bl, br;
+        uint64_t lx2, ly2;
+        bool valid;
+      };
+      auto sample = [&](int iy, int ix, Px& q) {
         const int ro0 = s_lo[0][iy], ro1 = s_hi[0][iy], co0 = s_lo[1][ix], co1 = s_hi[1][ix];
         const float ly = s_w[0][iy], lx = s_w[1][ix];
-        lx2 = f2_pack(lx, lx);
-        ly2 = f2_pack(ly, ly);
-        const bool valid = (ro0 >= 0) && (co0 >= 0);
-        if (valid) {
-          tl = __ldg(reinterpret_cast<const uint4*>(fb + ro0 + co0));
-          tr = __ldg(reinterpret_cast<const uint4*>(fb + ro0 + co1));
-          bl = __ldg(reinterpret_cast<const uint4*>(fb + ro1 + co0));
-          br = __ldg(reinterpret_cast<const uint4*>(fb + ro1 + co1));
+        q.lx2 = f2_pack(lx, lx);
+        q.ly2 = f2_pack(ly, ly);
+        q.valid = (ro0 | co0) >= 0;
+        if (q.valid) {
+          q.tl = __ldg(reinterpret_cast<const uint4*>(fb + 2u * (uint32_t)(ro0 + co0)));
+          q.tr = __ldg(reinterpret_cast<const uint4*>(fb + 2u * (uint32_t)(ro0 + co1)));
+          q.bl = __ldg(reinterpret_cast<const uint4*>(fb + 2u * (uint32_t)(ro1 + co0)));
+          q.br = __ldg(reinterpret_cast<const uint4*>(fb + 2u * (uint32_t)(ro1 + co1)));
         }
-        return valid;
       };
-      auto finish = [&](int pix, bool valid, const uint4& tl, const uint4& tr, const uint4& bl, const uint4& br, uint64_t lx2,
-                        uint64_t ly2) {
+      auto finish = [&](int pix, const Px& q) {
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if (valid) {
-          o.x = lerp_bf16x2(tl.x, tr.x, bl.x, br.x, lx2, ly2, one2);
-          o.y = lerp_bf16x2(tl.y, tr.y, bl.y, br.y, lx2, ly2, one2);
-          o.z = lerp_bf16x2(tl.z, tr.z, bl.z, br.z, lx2, ly2, one2);
-          o.w = lerp_bf16x2(tl.w, tr.w, bl.w, br.w, lx2, ly2, one2);
+        if (q.valid) {
+          o.x = lerp_bf16x2(q.tl.x, q.tr.x, q.bl.x, q.br.x, q.lx2, q.ly2, one2);
+          o.y = lerp_bf16x2(q.tl.y, q.tr.y, q.bl.y, q.br.y, q.lx2, q.ly2, one2);
+          o.z = lerp_bf16x2(q.tl.z, q.tr.z, q.bl.z, q.br.z, q.lx2, q.ly2, one2);
+          o.w = lerp_bf16x2(q.tl.w, q.tr.w, q.bl.w, q.br.w, q.lx2, q.ly2, one2);
         }
-        __stcs(reinterpret_cast<uint4*>(out + (size_t)pix * 256 + lane * 8), o);
+        __stcs(reinterpret_cast<uint4*>(ob + 512u * (uint32_t)pix), o);
+      };
+      // pixel of this warp and the step to its next one (nwarps pixels further), as (row, column) pairs
+      int iy = warp / P, ix = warp - iy * P;
+      const int dy = nwarps / P, dx = nwarps - dy * P;
+      auto advance = [&](int& y, int& x) {
+        y += dy;
+        x += dx;
+        if (x >= P) {
+          x -= P;
+          ++y;
+        }
       };
       int pix = warp;
       for (; pix + nwarps < npix; pix += 2 * nwarps) {
-        uint4 a0, b0, c0, d0, a1, b1, c1, d1;
-        uint64_t lx0, ly0, lx1, ly1;
-        const bool v0 = sample(pix, a0, b0, c0, d0, lx0, ly0);
-        const bool v1 = sample(pix + nwarps, a1, b1, c1, d1, lx1, ly1);
-        finish(pix, v0, a0, b0, c0, d0, lx0, ly0);
-        finish(pix + nwarps, v1, a1, b1, c1, d1, lx1, ly1);
+        Px q0, q1;
+        int iy1 = iy, ix1 = ix;
+        advance(iy1, ix1);
+        sample(iy, ix, q0);
+        sample(iy1, ix1, q1);
+        finish(pix, q0);
+        finish(pix + nwarps, q1);
+        iy = iy1;
+        ix = ix1;
+        advance(iy, ix);
       }
       if (pix < npix) {
-        uint4 a0, b0, c0, d0;
-        uint64_t lx0, ly0;
-        const bool v0 = sample(pix, a0, b0, c0, d0, lx0, ly0);
-        finish(pix, v0, a0, b0, c0, d0, lx0, ly0);
+        Px q0;
+        sample(iy, ix, q0);
+        finish(pix, q0);
       }
       return;
     }

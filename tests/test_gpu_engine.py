@@ -316,3 +316,48 @@ def test_async_pipelined_detect_maps_equals_sync(model):
             for k in ("rois", "class_ids", "scores", "masks"):
                 assert np.array_equal(x[k], y[k]), k
     model.wait()
+
+
+def test_base_config_1024_chain_of_custody(weights):
+    """Largest configuration (base Config: IMAGE_MAX_DIM = 1024, 261 888 anchors): one full detect_maps, then every
+    index-producing stage bit-exact against the oracle fed with the engine's own tensors of that stage, ROIAlign
+    exact after bf16 rounding, unmolded boxes / masks exact.  (The dense stages are covered at S = 256 above.)"""
+    from mrcnn import model as modellib
+    from mrcnn.config import Config
+    S1 = 1024
+
+    class BaseSize(Config):
+        NAME = "base1024"
+        GPU_COUNT = 1
+        IMAGES_PER_GPU = 1
+        NUM_CLASSES = 4
+        IMAGE_MIN_DIM = S1
+        IMAGE_MAX_DIM = S1
+        RPN_ANCHOR_SCALES = (4, 8, 16, 32, 64)
+        MEAN_PIXEL = np.array([0, 0, 0])
+        DETECTION_MIN_CONFIDENCE = 0
+
+    m = modellib.MaskRCNN(mode="inference", config=BaseSize(), model_dir="/tmp/mrcnn_logs")
+    m.set_weights(weights)
+    maps = synth.radio_maps(1, 700)                          # 700x700 frame -> scaled to 1024
+    res = m.detect_maps(maps)[0]
+    anchors = m.get_anchors((S1, S1, 3))
+    assert anchors.shape[0] == 261888
+    rois, taps = GL.proposal_layer(m.read_tensor("rpn_class"), m.read_tensor("rpn_bbox"), anchors, return_taps=True)
+    assert np.array_equal(m.read_tensor("topk_idx")[0], taps[0]["topk"])
+    assert np.array_equal(m.read_tensor("rpn_rois").view(np.uint32), rois.view(np.uint32))
+    fmaps = [m.read_tensor(k) for k in ("P2", "P3", "P4", "P5")]
+    assert fmaps[0].shape == (1, 256, 256, 256)
+    ref, lv = GL.pyramid_roi_align(rois, (S1, S1, 3), fmaps, (7, 7), return_levels=True)
+    assert np.array_equal(m.read_tensor("roi_levels"), lv)
+    assert np.array_equal(m.read_tensor("pooled"), torch.from_numpy(ref).to(torch.bfloat16).float().numpy())
+    img = H.fits_to_rgb(maps[0])
+    _, metas, windows = H.mold_inputs([img], min_dim=S1, max_dim=S1, min_scale=0, mode="square",
+                                      mean_pixel=np.array([0, 0, 0]), num_classes=4)
+    det = m.read_tensor("detections")
+    refd = GL.detection_layer(rois, m.read_tensor("mrcnn_class"), m.read_tensor("mrcnn_bbox"), metas, min_confidence=0.0)
+    assert np.array_equal(det.view(np.uint32), refd.view(np.uint32))
+    boxes, cls, scores, full = H.unmold_detections(det[0], m.read_tensor("mrcnn_mask")[0], img.shape, (S1, S1, 3), windows[0])
+    assert np.array_equal(res["rois"], boxes) and np.array_equal(res["class_ids"], cls)
+    assert res["masks"].shape == full.shape == (700, 700, len(cls))
+    assert np.array_equal(res["masks"], full)

@@ -97,6 +97,14 @@ def test_proposal_all_ties_and_zero_area():
     _check_proposal(probs, bbox, anchors0)
 
 
+def test_proposal_1024_config_261888_anchors():
+    """Base-Config size (IMAGE_MAX_DIM = 1024): A = 261 888 anchors per image, top-6000 of them, with ties."""
+    rng = np.random.default_rng(5)
+    probs, bbox, anchors = _rpn_inputs(rng, 2, 261888, S=1024, sharp=3.0)
+    probs[1, 5::4001, 1] = probs[1, 7, 1]                     # a few exact ties among the top scores
+    _check_proposal(probs, bbox, anchors)
+
+
 def test_proposal_batched_anchors():
     rng = np.random.default_rng(4)
     probs, bbox, anchors = _rpn_inputs(rng, 2, 4092)
