@@ -134,6 +134,7 @@ def run_reference(args, rank, world):
 
 
 def main():
+    global S, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -145,7 +146,6 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    global S, WORKLOAD
     if args.image_size != S or args.batch != BATCH:
         S = args.image_size
         WORKLOAD = "batched detect, %d synthetic radio maps at IMAGE_MAX_DIM=%d (secondary size; BASELINE.json configs[1] is 64 maps at 256)" % (args.batch, S)

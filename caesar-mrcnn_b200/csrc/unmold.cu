@@ -20,6 +20,8 @@ struct DetRec {
   int y1, x1, y2, x2;
   int cls, src;       // class id, original detection row
   double mn, mx;      // min / max of the selected 28x28 mask
+  double rs, cs;      // MH / box height, MW / box width (skimage scale factors), hoisted out of the pixel loop
+  double ro, co;      // 0.5 * rs - 0.5, 0.5 * cs - 0.5
 };
 
 struct UnmoldParams {
@@ -93,22 +95,48 @@ __global__ void unmold_boxes_kernel(UnmoldParams p) {
       p.scores[(size_t)b * D + i] = 0.f;
     }
   }
+  int* s_slot = s_first0 + 1;      // [D] compacted slot of detection i, -1 = dropped
+  int* s_cls = s_slot + D;         // [D]
+  if (i < D) {
+    s_slot[i] = valid ? slot : -1;
+    s_cls[i] = cls;
+  }
   if (valid) {
     int32_t* r = p.rois + ((size_t)b * D + slot) * 4;
     r[0] = y1; r[1] = x1; r[2] = y2; r[3] = x2;
     p.class_ids[(size_t)b * D + slot] = cls;
     p.scores[(size_t)b * D + slot] = score;
-    // min / max of the class mask (skimage clip range)
-    const float* m = p.masks + (((size_t)b * D + i) * p.MH * p.MW) * p.NC + cls;
-    float mn = m[0], mx = m[0];
-    for (int k = 1; k < p.MH * p.MW; ++k) {
-      const float v = m[(size_t)k * p.NC];
-      mn = fminf(mn, v); mx = fmaxf(mx, v);
+    DetRec* rec = p.recs + (size_t)b * D + slot;
+    rec->y1 = y1; rec->x1 = x1; rec->y2 = y2; rec->x2 = x2; rec->cls = cls; rec->src = i;
+    const double rs = (double)p.MH / (double)(y2 - y1), cs = (double)p.MW / (double)(x2 - x1);
+    rec->rs = rs;
+    rec->cs = cs;
+    rec->ro = __dsub_rn(__dmul_rn(0.5, rs), 0.5);
+    rec->co = __dsub_rn(__dmul_rn(0.5, cs), 0.5);
+  }
+  __syncthreads();
+  // min / max of each kept detection's class mask (skimage clip range): one warp per detection, lanes stride
+  // over the MH*MW samples (min / max are order-independent, so the lane split is exact)
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int d = warp; d < D; d += nwarps) {
+    const int sl = s_slot[d];
+    if (sl < 0) continue;
+    const float* m = p.masks + (((size_t)b * D + d) * p.MH * p.MW) * p.NC + s_cls[d];
+    float mn = INFINITY, mx = -INFINITY;
+    for (int k = lane; k < p.MH * p.MW; k += 32) {
+      const float v = __ldg(m + (size_t)k * p.NC);
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
     }
-    DetRec rec;
-    rec.y1 = y1; rec.x1 = x1; rec.y2 = y2; rec.x2 = x2; rec.cls = cls; rec.src = i;
-    rec.mn = (double)mn; rec.mx = (double)mx;
-    p.recs[(size_t)b * D + slot] = rec;
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) {
+      DetRec* rec = p.recs + (size_t)b * D + sl;
+      rec->mn = (double)mn;
+      rec->mx = (double)mx;
+    }
   }
 }
 
@@ -136,10 +164,8 @@ __global__ void __launch_bounds__(PAINT_THREADS) unmold_paint_kernel(UnmoldParam
     for (int k = 0; k < cnt; ++k) {
       const DetRec& r = s_rec[k];
       if (y < r.y1 || y >= r.y2 || x < r.x1 || x >= r.x2) continue;
-      const int bh = r.y2 - r.y1, bw = r.x2 - r.x1;
-      const double rs = (double)p.MH / (double)bh, cs = (double)p.MW / (double)bw;
-      const double rr = __dadd_rn(__dmul_rn(rs, (double)(y - r.y1)), __dsub_rn(__dmul_rn(0.5, rs), 0.5));
-      const double cc = __dadd_rn(__dmul_rn(cs, (double)(x - r.x1)), __dsub_rn(__dmul_rn(0.5, cs), 0.5));
+      const double rr = __dadd_rn(__dmul_rn(r.rs, (double)(y - r.y1)), r.ro);
+      const double cc = __dadd_rn(__dmul_rn(r.cs, (double)(x - r.x1)), r.co);
       const double fr = floor(rr), fc = floor(cc);
       const int r0 = (int)fr, r1 = (int)ceil(rr), c0 = (int)fc, c1 = (int)ceil(cc);
       const double dr = __dsub_rn(rr, fr), dc = __dsub_rn(cc, fc);
@@ -196,8 +222,8 @@ extern "C" int mrcnn_unmold_detections(const float* detections, const float* mrc
   p.windows = windows; p.rois = rois; p.class_ids = class_ids; p.scores = scores; p.counts = counts;
   p.recs = static_cast<DetRec*>(workspace); p.out = masks;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int threads = ((max_instances + 31) / 32) * 32;
-  MRCNN_CHECK_CUDA(mrcnn_launch(unmold_boxes_kernel, dim3(batch), dim3(threads), (max_instances + 1) * sizeof(int), st, p));
+  const int threads = 1024;        // >= max_instances (<= 256): thread i = detection i, then one warp per detection
+  MRCNN_CHECK_CUDA(mrcnn_launch(unmold_boxes_kernel, dim3(batch), dim3(threads), (3 * max_instances + 1) * sizeof(int), st, p));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   const size_t npx = (size_t)p.H0 * p.W0;
   const size_t smem = (((size_t)max_instances * sizeof(DetRec) + 15) & ~(size_t)15) + (size_t)PAINT_THREADS * max_instances + 16;
