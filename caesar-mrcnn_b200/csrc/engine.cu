@@ -18,6 +18,8 @@
 #include "elementwise.cuh"
 #include "mrcnn_b200.h"
 
+void mrcnn_count_launch(unsigned long long n);
+
 int launch_pyramid_roi_align(const void* const* feature_maps, const int* feat_h, const int* feat_w, int channels,
                              int dtype, const float* boxes, int box_stride, int batch, int num_boxes, int pool_size,
                              float image_area, void* pooled, int32_t* levels, cudaStream_t st);
@@ -98,6 +100,10 @@ struct mrcnn_engine {
   // timing
   std::vector<std::string> stage_names;
   std::vector<cudaEvent_t> stage_events;  // stage_names.size() + 1
+  bool use_graph = false;                 // MRCNN_B200_GRAPH=1: replay the plan as a CUDA graph when not profiling
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_fresh = false;
+  unsigned long long launches_per_predict = 0;
   bool autotune = true;
   std::map<std::string, std::pair<int, int>> tune_cache;   // layer key -> (BLOCK_N, epi_tma)
   bool tune_cache_dirty = false;
@@ -757,6 +763,7 @@ extern "C" int mrcnn_engine_create(const mrcnn_engine_config* cfg, int device, m
     mrcnn_set_error("engine_create: cudaStreamCreate failed");
     return MRCNN_ERR_CUDA;
   }
+  if (const char* g = getenv("MRCNN_B200_GRAPH")) e->use_graph = g[0] == '1';
   const char* at = getenv("MRCNN_B200_AUTOTUNE");
   e->autotune = !(at && at[0] == '0');
   if (const char* cp = getenv("MRCNN_B200_AUTOTUNE_CACHE")) {
@@ -881,6 +888,37 @@ static int predict_internal(mrcnn_engine* e, const float* molded, cudaMemcpyKind
   const Tensor& tm = e->tensors["input_image_meta"];
   if (molded != ti.ptr) MRCNN_CHECK_CUDA(cudaMemcpyAsync(ti.ptr, molded, ti.bytes, molded_kind, e->stream));
   if (image_metas != tm.ptr) MRCNN_CHECK_CUDA(cudaMemcpyAsync(tm.ptr, image_metas, tm.bytes, metas_kind, e->stream));
+  // The launch plan is static (fixed pointers, fixed geometry): outside profiling it is captured once into a CUDA
+  // graph (programmatic-dependent-launch edges included) and replayed with one cudaGraphLaunch per predict.
+  if (e->use_graph && e->profiling == 0) {
+    if (!e->graph_exec) {
+      cudaGraph_t graph = nullptr;
+      MRCNN_CHECK_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+      const unsigned long long n0 = mrcnn_kernel_launch_count();
+      const int rc = run_steps(e, nullptr, false);
+      e->launches_per_predict = mrcnn_kernel_launch_count() - n0;
+      const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+      if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      MRCNN_CHECK_CUDA(ce);
+      const cudaError_t ie = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+      e->graph_fresh = true;
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) {            // fall back to stream launches for good
+        e->graph_exec = nullptr;
+        e->use_graph = false;
+        cudaGetLastError();
+        return run_steps(e, nullptr, true);
+      }
+    }
+    const bool first = e->graph_fresh;
+    e->graph_fresh = false;
+    MRCNN_CHECK_CUDA(cudaGraphLaunch(e->graph_exec, e->stream));
+    if (!first) mrcnn_count_launch(e->launches_per_predict);     // the capture pass already counted its launches
+    return MRCNN_OK;
+  }
   return run_steps(e, nullptr, true);
 }
 
