@@ -177,8 +177,9 @@ __device__ inline int heap_pop(HeapEntry* h, int& len_ref) {
 // candidates are tested against the boxes selected so far (kept list in shared memory) only when
 // the chunk is reached, so the work is ~64 x |selected| per chunk and stops with the NMS itself
 // (TF stops at max_out picks) instead of pre-suppressing all n candidates for every pick.
-//   (0) if a heap is given, thread 0 pops the next 64 candidate ids (exact TF order under ties),
-//   (1) all threads: candidate k (16 threads each) vs the kept list -> suppressed flags, and the
+//   (0) if a heap is given, the popper warp pops the NEXT chunk's 64 candidate ids (exact TF order under ties)
+//       while the workers do (1)-(3) on the current one,
+//   (1) workers: candidate k (15 threads each) vs the kept list -> suppressed flags, and the
 //       64x64 intra-chunk suppression matrix,
 //   (2) warp 0 gathers the alive mask; lane 0 resolves the chunk greedily,
 //   (3) the newly kept boxes are appended to the kept list.
@@ -196,100 +197,108 @@ struct NmsScratch {
   int heap_len;
 };
 
+// Warp 31 is the POPPER: while warps 0..30 (992 threads, named barrier 1) resolve chunk c, its lane 0 pops the
+// candidate ids of chunk c+1 from the emulated heap (the pops do not depend on the NMS outcome), so the serial
+// heap emulation and the NMS overlap instead of alternating; one __syncthreads per chunk hands over.  The chunk
+// popped after the last one consumed is wasted work only.
+constexpr int NMS_WORKERS = 992;
+__device__ __forceinline__ void nms_workers_sync() { asm volatile("bar.sync 1, 992;" ::: "memory"); }
+
 __device__ inline int block_nms(const Box4* boxes, uint16_t* order, int n, int max_out, float thr,
                                 float4* kept_box, float* kept_area, uint16_t* selected, NmsScratch* sc,
                                 HeapEntry* lazy_heap) {
   const int tid = threadIdx.x;
-  const int nt = blockDim.x;
   const int lane = tid & 31;
+  const bool worker = tid < NMS_WORKERS;
+  auto pop_chunk = [&](int base) {     // thread NMS_WORKERS only
+    int len = sc->heap_len;
+    const int cnt = min(64, n - base);
+    for (int k = 0; k < cnt; ++k) order[base + k] = (uint16_t)heap_pop(lazy_heap, len);
+    sc->heap_len = len;
+  };
   if (tid == 0) {
     sc->count = 0;
     sc->heap_len = n;
   }
   __syncthreads();
+  if (lazy_heap != nullptr && tid == NMS_WORKERS && n > 0) pop_chunk(0);
+  __syncthreads();
   int count = 0;
   for (int base = 0; base < n && count < max_out; base += 64) {
     const int n_in = min(64, n - base);
-    if (lazy_heap != nullptr) {
-      if (tid == 0) {
-        int len = sc->heap_len;
-        for (int k = 0; k < n_in; ++k) order[base + k] = (uint16_t)heap_pop(lazy_heap, len);
-        sc->heap_len = len;
+    if (!worker) {
+      if (lazy_heap != nullptr && tid == NMS_WORKERS && base + 64 < n) pop_chunk(base + 64);
+    } else {
+      if (tid < 64) {
+        NBox nb;
+        if (tid < n_in) {
+          nb = normalise_box(boxes[order[base + tid]]);
+        } else {
+          nb.ymin = nb.xmin = nb.ymax = nb.xmax = 0.f;
+          nb.area = -1.f;
+        }
+        sc->chunk[tid] = nb;
+        sc->M[tid] = 0ull;
+        sc->sup[tid] = 0;
       }
-      __syncthreads();
-    }
-    if (tid < 64) {
-      NBox nb;
-      if (tid < n_in) {
-        nb = normalise_box(boxes[order[base + tid]]);
-      } else {
-        nb.ymin = nb.xmin = nb.ymax = nb.xmax = 0.f;
-        nb.area = -1.f;
-      }
-      sc->chunk[tid] = nb;
-      sc->M[tid] = 0ull;
-    }
-    __syncthreads();
-    {   // (1a) candidate k = tid/16 against the kept list, 16 threads striding over it
-      const int k = tid >> 4, sub = tid & 15;
-      const NBox cb = sc->chunk[k];
-      bool sup = false;
-      if (cb.area > 0.f) {
-        for (int r = sub; r < count; r += 16) {
-          const float4 kb = kept_box[r];
-          const float ih = __fsub_rn(fminf(kb.z, cb.ymax), fmaxf(kb.x, cb.ymin));
-          const float iw = __fsub_rn(fminf(kb.w, cb.xmax), fmaxf(kb.y, cb.xmin));
-          if (ih > 0.f && iw > 0.f) {
-            const float ka = kept_area[r];
-            const float inter = __fmul_rn(ih, iw);
-            if (ka > 0.f && inter != 0.0f) {
-              const float uni = __fsub_rn(__fadd_rn(ka, cb.area), inter);
-              if (__fdiv_rn(inter, uni) > thr) {
-                sup = true;
-                break;
+      nms_workers_sync();
+      if (tid < 64 * 15) {   // (1a) candidate k = tid/15 against the kept list, 15 threads striding over it
+        const int k = tid / 15, sub = tid - k * 15;
+        const NBox cb = sc->chunk[k];
+        if (cb.area > 0.f) {
+          for (int r = sub; r < count; r += 15) {
+            const float4 kb = kept_box[r];
+            const float ih = __fsub_rn(fminf(kb.z, cb.ymax), fmaxf(kb.x, cb.ymin));
+            const float iw = __fsub_rn(fminf(kb.w, cb.xmax), fmaxf(kb.y, cb.xmin));
+            if (ih > 0.f && iw > 0.f) {
+              const float ka = kept_area[r];
+              const float inter = __fmul_rn(ih, iw);
+              if (ka > 0.f && inter != 0.0f) {
+                const float uni = __fsub_rn(__fadd_rn(ka, cb.area), inter);
+                if (__fdiv_rn(inter, uni) > thr) {
+                  sc->sup[k] = 1;      // any of the 15 threads; same value, benign race
+                  break;
+                }
               }
             }
           }
         }
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, sup);
-      if (sub == 0) sc->sup[k] = ((bal >> (lane & 16)) & 0xffffu) ? 1 : 0;
-    }
-    // (1b) intra-chunk suppression matrix
-    for (int p = tid; p < 64 * 64; p += nt) {
-      const int i = p >> 6, j = p & 63;
-      if (j > i && j < n_in && iou_gt(sc->chunk[i], sc->chunk[j], thr)) atomicOr(&sc->M[i], 1ull << j);
-    }
-    __syncthreads();
-    if (tid < 32) {   // (2)
-      const unsigned lo = __ballot_sync(0xffffffffu, lane < n_in && !sc->sup[lane]);
-      const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < n_in && !sc->sup[lane + 32]);
-      if (lane == 0) {
-        unsigned long long alive = (unsigned long long)lo | ((unsigned long long)hi << 32);
-        unsigned long long kept = 0ull;
-        int c = sc->count;
-        while (alive && c < max_out) {
-          const int i = __ffsll((long long)alive) - 1;
-          alive &= ~(1ull << i);
-          kept |= 1ull << i;
-          selected[c++] = (uint16_t)(base + i);
-          alive &= ~sc->M[i];
+      // (1b) intra-chunk suppression matrix
+      for (int p = tid; p < 64 * 64; p += NMS_WORKERS) {
+        const int i = p >> 6, j = p & 63;
+        if (j > i && j < n_in && iou_gt(sc->chunk[i], sc->chunk[j], thr)) atomicOr(&sc->M[i], 1ull << j);
+      }
+      nms_workers_sync();
+      if (tid < 32) {   // (2)
+        const unsigned lo = __ballot_sync(0xffffffffu, lane < n_in && !sc->sup[lane]);
+        const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < n_in && !sc->sup[lane + 32]);
+        if (lane == 0) {
+          unsigned long long alive = (unsigned long long)lo | ((unsigned long long)hi << 32);
+          unsigned long long kept = 0ull;
+          int c = sc->count;
+          while (alive && c < max_out) {
+            const int i = __ffsll((long long)alive) - 1;
+            alive &= ~(1ull << i);
+            kept |= 1ull << i;
+            selected[c++] = (uint16_t)(base + i);
+            alive &= ~sc->M[i];
+          }
+          sc->kept_bits = kept;
+          sc->count = c;
         }
-        sc->kept_bits = kept;
-        sc->count = c;
+      }
+      nms_workers_sync();
+      const unsigned long long kept = sc->kept_bits;
+      if (tid < 64 && ((kept >> tid) & 1ull)) {   // (3) append in selection order
+        const int r = count + __popcll(kept & ((1ull << tid) - 1ull));
+        const NBox nb = sc->chunk[tid];
+        kept_box[r] = make_float4(nb.ymin, nb.xmin, nb.ymax, nb.xmax);
+        kept_area[r] = nb.area;
       }
     }
-    __syncthreads();
-    const unsigned long long kept = sc->kept_bits;
-    const int new_count = sc->count;
-    if (tid < 64 && ((kept >> tid) & 1ull)) {   // (3) append in selection order
-      const int r = count + __popcll(kept & ((1ull << tid) - 1ull));
-      const NBox nb = sc->chunk[tid];
-      kept_box[r] = make_float4(nb.ymin, nb.xmin, nb.ymax, nb.xmax);
-      kept_area[r] = nb.area;
-    }
-    count = new_count;
-    __syncthreads();
+    __syncthreads();          // chunk handover: next order[] popped, kept list and count final
+    count = sc->count;
   }
   return count;
 }

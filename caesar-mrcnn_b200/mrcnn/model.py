@@ -414,10 +414,21 @@ class MaskRCNN(object):
         """engine predict + device unmold -> list of result dicts (numpy views of pinned buffers)."""
         torch = utils._torch()
         shapes = {tuple(s[:2]) for s in orig_shapes}
-        if len(shapes) != 1:
-            raise NotImplementedError("mrcnn (B200 build): detect() needs the images of one batch to share one original size")
         if not self._weights_loaded:
             raise RuntimeError("load_weights() / set_weights() must be called before predict/detect")
+        if len(shapes) != 1:
+            # images of different original sizes in one batch (allowed by the reference as long as the molded shapes
+            # agree, mrcnn/model.py:2655-2658): one graph pass, then the per-image GPU unmold
+            if not molded.is_cuda:
+                molded = molded.to("cuda:%d" % self._device)
+            self._predict_device(molded, metas)
+            det, masks = self.read_tensor("detections"), self.read_tensor("mrcnn_mask")
+            out = []
+            for i, shp in enumerate(orig_shapes):
+                rois, cls, scores, full = self.unmold_detections(det[i], masks[i], shp, tuple(int(v) for v in self.config.IMAGE_SHAPE),
+                                                                 windows[i])
+                out.append({"rois": rois, "class_ids": cls, "scores": scores, "masks": full})
+            return out
         H0, W0 = next(iter(shapes))
         metas32 = np.ascontiguousarray(metas, dtype=np.float32)
         wins = np.ascontiguousarray(windows, dtype=np.int32)

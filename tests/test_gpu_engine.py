@@ -318,6 +318,25 @@ def test_async_pipelined_detect_maps_equals_sync(model):
     model.wait()
 
 
+def test_detect_images_of_different_original_sizes(model):
+    """The reference only requires equal MOLDED shapes in a batch (mrcnn/model.py:2655-2658): two frames of
+    different size go through one graph pass and are unmolded per image, bit-exact against the oracle."""
+    maps = [synth.radio_maps(1, 132)[0], synth.radio_maps(1, 200, start=7)[0][:150, :]]
+    images = [H.fits_to_rgb(m) for m in maps]
+    assert images[0].shape != images[1].shape
+    results = model.detect(images)
+    det = model.read_tensor("detections")
+    masks = model.read_tensor("mrcnn_mask")
+    _, metas, windows = H.mold_inputs(images, min_dim=S, max_dim=S, min_scale=0, mode="square",
+                                      mean_pixel=np.array([0, 0, 0]), num_classes=4)
+    for i, im in enumerate(images):
+        boxes, class_ids, scores, full = H.unmold_detections(det[i], masks[i], im.shape, (S, S, 3), windows[i])
+        r = results[i]
+        assert r["masks"].shape[:2] == im.shape[:2]
+        assert np.array_equal(r["rois"], boxes) and np.array_equal(r["class_ids"], class_ids)
+        assert np.array_equal(r["scores"], scores) and np.array_equal(r["masks"], full)
+
+
 def test_base_config_1024_chain_of_custody(weights):
     """Largest configuration (base Config: IMAGE_MAX_DIM = 1024, 261 888 anchors): one full detect_maps, then every
     index-producing stage bit-exact against the oracle fed with the engine's own tensors of that stage, ROIAlign
