@@ -54,6 +54,72 @@ __device__ __forceinline__ int block_excl_scan_flag(bool flag, int* warp_tot, in
   return off + pre;
 }
 
+// Bitonic sort (descending) of 8192 64-bit keys by 1024 threads, 8 consecutive keys per thread.  The network is the
+// textbook one over the flat index i = 8*tid + r (partner i ^ j, direction by bit k of i); only WHERE the partner
+// lives changes the mechanics: j < 8 same thread (registers), 8 <= j < 256 same warp (shuffles), j >= 256 another
+// warp (shared memory, two barriers).  15 of the 91 stages touch shared memory instead of all of them.
+__device__ __forceinline__ void cmpx(unsigned long long& a, unsigned long long& b, bool desc) {
+  const bool sw = desc ? (a < b) : (a > b);
+  const unsigned long long t = a;
+  a = sw ? b : a;
+  b = sw ? t : b;
+}
+
+template <int J> __device__ __forceinline__ void sort_intra(unsigned long long (&e)[8], int k, bool desc) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    if ((r & J) == 0) {
+      const bool d = k >= 8 ? desc : ((r & k) == 0);     // k < 8: the direction bit is inside the thread's 8 keys
+      cmpx(e[r], e[r | J], d);
+    }
+  }
+}
+
+__device__ inline void sort_desc_regs(unsigned long long* buf) {
+  const int tid = threadIdx.x;
+  unsigned long long e[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) e[r] = buf[tid * 8 + r];
+  for (int k = 2; k <= 8192; k <<= 1) {
+    const bool desc = ((tid * 8) & k) == 0;          // k >= 8: same for the thread's 8 keys; k < 8 handled per key below
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 256) {
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) buf[tid * 8 + r] = e[r];
+        __syncthreads();
+        const int pt = tid ^ (j >> 3);
+        const bool lower = (tid & (j >> 3)) == 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const unsigned long long c = buf[pt * 8 + r];
+          const bool keep_max = lower == desc;
+          e[r] = keep_max ? (e[r] > c ? e[r] : c) : (e[r] < c ? e[r] : c);
+        }
+      } else if (j >= 8) {
+        const int m = j >> 3;                          // partner lane distance 1..16
+        const bool lower = (tid & m) == 0;
+        const bool keep_max = lower == desc;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const unsigned long long c = __shfl_xor_sync(0xffffffffu, e[r], m);
+          e[r] = keep_max ? (e[r] > c ? e[r] : c) : (e[r] < c ? e[r] : c);
+        }
+      } else if (j == 4) {
+        sort_intra<4>(e, k, desc);
+      } else if (j == 2) {
+        sort_intra<2>(e, k, desc);
+      } else {
+        sort_intra<1>(e, k, desc);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 8; ++r) buf[tid * 8 + r] = e[r];
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p) {
   pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem[];
@@ -132,6 +198,9 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
 
   if (p.phase_clocks && tid == 0) p.phase_clocks[(size_t)b * 8 + 2] = clock64();
   // ---- 3. bitonic sort, descending on (key, ~index) ------------------------------------------
+  if (Kpad == 8 * PROP_THREADS && nt == PROP_THREADS) {
+    sort_desc_regs(sortbuf);       // 8 keys per thread: registers / shuffles / shared memory by partner distance
+  } else
   for (int k = 2; k <= Kpad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int i = tid; i < Kpad; i += nt) {
