@@ -106,13 +106,42 @@ class ClockSampler(threading.Thread):
         return out
 
 
+def _bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI function) so that the
+    pinned result buffers (420 MB per step and rank) are allocated on, and copied into, the GPU's own NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:          # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return spec
+    except Exception:
+        pass
+    return None
+
+
 def run_reference(args, rank, world):
     """Reference arm: CPU restatement on the host cores; rank 0 only."""
     if rank != 0:
         return
     import torch
     import synth
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0)) or 1
     torch.set_num_threads(threads)
     weights = synth.make_random_weights(0, 4)
     per_step = 1                                   # bounded sample: 1 image per step
@@ -164,6 +193,8 @@ def main():
     from mrcnn.config import Config
 
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = _bind_to_gpu_numa_node(local_rank)      # before any pinned allocation: first touch lands on the GPU's node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.batch
@@ -312,7 +343,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "image_size": S, "num_classes": 4, "weights": "seeded random (LFS pointer unresolved)",
-                       "l2": "4 rotated input batches; per-step working set (activations) is GBs >> 126 MB L2", "parallelism": "batch-sharded, no collective"},
+                       "l2": "4 rotated input batches; per-step working set (activations) is GBs >> 126 MB L2", "parallelism": "batch-sharded, no collective", "cpu_affinity": numa},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_families": stages,
             "stage_ms_per_step": {k: v / nprof for k, v in st_acc.items()},
@@ -320,7 +351,9 @@ def main():
 
     # ---- CPU baseline: bounded sample of the same workload on the host cores (rank 0, N = 1) --------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        os.sched_setaffinity(0, all_cpus)          # the CPU baseline gets every host core again
+        threads = len(all_cpus) or 1
+        torch.set_num_threads(threads)
         sample = 4
         cpu_detect_images(base[:1], weights, threads)            # warm-up (page-in, thread pool)
         t = cpu_detect_images(base[:sample], weights, threads)
