@@ -39,11 +39,12 @@ template <int BLOCK_N, bool EPI_TMA> struct TileCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_CHUNK_BYTES = BLOCK_M * 32 * 2;                   // 128 rows x 32 bf16
-  static constexpr int STAGING_BYTES = EPI_TMA ? 2 * 3 * EPI_CHUNK_BYTES : 0; // 2 column halves x 3 rotating buffers
+  static constexpr int EPI_CHUNK_BYTES = 32 * 32 * 2;                        // one warp's chunk: 32 rows x 32 bf16
+  static constexpr int STAGING_BYTES = EPI_TMA ? 8 * 3 * EPI_CHUNK_BYTES : 0; // 8 epilogue warps x 3 rotating buffers
   // [acc][scale|shift][BLOCK_N] floats + (fused mask logits) W2 [256][4] floats + partials [128][8] floats
   static constexpr int EPI_BYTES = 2 * 2 * BLOCK_N * 4 + ((BLOCK_N == 256 && !EPI_TMA) ? (256 * 4 * 4 + 128 * 8 * 4) : 0);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+  static constexpr int BAR_BYTES = 512;                                      // mbarriers + TMEM slot
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + BAR_BYTES + EPI_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;   // double-buffered accumulator (64..512, power of two)
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -212,15 +213,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
   const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_raw + (base_addr - raw_addr);
   constexpr int RING_BYTES = STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES;
-  const uint32_t staging_base = base_addr + STAGES * Cfg::STAGE_BYTES;        // [2 halves][3][128 rows x 64 B]
+  const uint32_t staging_base = base_addr + STAGES * Cfg::STAGE_BYTES;        // [8 warps][3][32 rows x 64 B]
   const uint32_t bar_base = base_addr + RING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  auto res_bar = [&](int half, int b) { return bar_base + 8u * (2 * STAGES + 4 + half * 3 + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + RING_BYTES + 8 * (2 * STAGES + 10));
-  float* s_affine = reinterpret_cast<float*>(base_ptr + RING_BYTES + 256);   // [2][2][BLOCK_N]
+  auto res_bar = [&](int ew, int b) { return bar_base + 8u * (2 * STAGES + 4 + ew * 3 + b); };   // per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + RING_BYTES + 8 * (2 * STAGES + 4 + 24));
+  float* s_affine = reinterpret_cast<float*>(base_ptr + RING_BYTES + Cfg::BAR_BYTES);   // [2][2][BLOCK_N]
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       mbar_init(tmem_empty_bar(a), 8);   // one arrival per epilogue warp
     }
     if (EPI_TMA) {
-      for (int b = 0; b < 6; ++b) mbar_init(res_bar(b / 3, b % 3), 1);
+      for (int b = 0; b < 24; ++b) mbar_init(res_bar(b / 3, b % 3), 1);
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
       if (p.residual != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_res) : "memory");
     }
@@ -352,21 +353,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       }
     }
     if constexpr (EPI_TMA) {
-      // ===== shared-memory epilogue (flat layers, bf16 out): per column half, 32-channel chunks rotate through
-      // three [128 x 64 B] buffers: TMA-load the residual chunk g+1, update chunk g in place (each thread owns
-      // one row: conflict-free 16-byte accesses under the 64B swizzle), TMA-store it; the store of chunk g-1 is
-      // still draining.  The elected thread of the half issues every bulk copy and owns the bulk groups.
-      constexpr int NCH = COLS_PER_WARP / 32;                 // chunks per tile for this half
-      const bool elected = ((ew & 3) == 0) && (lane == 0);
+      // ===== shared-memory epilogue (flat layers, bf16 out), one independent pipeline PER WARP: the warp's
+      // [32 rows x 32 channels] chunks rotate through three 2 KB buffers: TMA-load the residual chunk g+1, update
+      // chunk g in place (each lane owns one row: conflict-free 16-byte accesses under the 64B swizzle), TMA-store
+      // it; the store of chunk g-1 is still draining.  Lane 0 issues the warp's bulk copies and owns its bulk
+      // groups; only __syncwarp() is needed, no cross-warp barrier inside a tile.
+      constexpr int NCH = COLS_PER_WARP / 32;                 // chunks per tile for this warp
+      const bool elected = lane == 0;
       const bool has_res = p.residual != nullptr;
-      const uint32_t half_base = staging_base + (uint32_t)half * 3u * Cfg::EPI_CHUNK_BYTES;
-      const uint32_t row_off = (uint32_t)row * 64u;
-      const uint32_t sw = (uint32_t)((row >> 1) & 3);
+      const uint32_t warp_base = staging_base + (uint32_t)ew * 3u * Cfg::EPI_CHUNK_BYTES;
+      const uint32_t row_off = (uint32_t)lane * 64u;
+      const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+      const int row0 = q * 32;                                // first tile row of this warp
       uint32_t g = 0, tcount = 0;
       if (has_cols && has_res && elected && (int)blockIdx.x < num_tiles) {   // residual of the very first chunk
         const int t0 = blockIdx.x;
-        mbar_expect_tx(res_bar(half, 0), Cfg::EPI_CHUNK_BYTES);
-        tma_load_2d(half_base, &tmap_res, res_bar(half, 0), (t0 % p.n_tiles) * BLOCK_N + c_begin, (t0 / p.n_tiles) * BLOCK_M);
+        mbar_expect_tx(res_bar(ew, 0), Cfg::EPI_CHUNK_BYTES);
+        tma_load_2d(warp_base, &tmap_res, res_bar(ew, 0), (t0 % p.n_tiles) * BLOCK_N + c_begin, (t0 / p.n_tiles) * BLOCK_M + row0);
       }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1u;
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci, ++g) {
             const uint32_t b = g % 3u;
-            const uint32_t buf = half_base + b * Cfg::EPI_CHUNK_BYTES;
+            const uint32_t buf = warp_base + b * Cfg::EPI_CHUNK_BYTES;
             if (has_res) {
               if (elected) {
                 // chunk g+1 (maybe of this CTA's next tile) -> buffer (g+1)%3, last read by the store of chunk g-2
@@ -401,15 +404,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 if (nt < num_tiles) {
                   bulk_wait_group_read<1>();
                   const uint32_t nb = (g + 1u) % 3u;
-                  mbar_expect_tx(res_bar(half, nb), Cfg::EPI_CHUNK_BYTES);
-                  tma_load_2d(half_base + nb * Cfg::EPI_CHUNK_BYTES, &tmap_res, res_bar(half, nb),
-                              (nt % p.n_tiles) * BLOCK_N + c_begin + 32 * nci, (nt / p.n_tiles) * BLOCK_M);
+                  mbar_expect_tx(res_bar(ew, nb), Cfg::EPI_CHUNK_BYTES);
+                  tma_load_2d(warp_base + nb * Cfg::EPI_CHUNK_BYTES, &tmap_res, res_bar(ew, nb),
+                              (nt % p.n_tiles) * BLOCK_N + c_begin + 32 * nci, (nt / p.n_tiles) * BLOCK_M + row0);
                 }
               }
-              mbar_wait(res_bar(half, b), (g / 3u) & 1u);
+              mbar_wait(res_bar(ew, b), (g / 3u) & 1u);
             } else {
               if (elected) bulk_wait_group_read<2>();          // the store of chunk g-3 has released this buffer
-              named_bar_sync(3 + half, 128);
+              __syncwarp();
             }
             tmem_ld_wait();                                     // chunk ci has landed
             if (ci + 1 < NCH) tmem_ld_32x32b_x32(t_addr + (uint32_t)(32 * (ci + 1)), vbuf[(ci + 1) & 1]);
@@ -446,9 +449,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
               sts128(addr, ov);
             }
             fence_proxy_async_smem();
-            named_bar_sync(3 + half, 128);
+            __syncwarp();
             if (elected) {
-              tma_store_2d(&tmap_out, buf, col_base + c, m_tile * BLOCK_M);
+              tma_store_2d(&tmap_out, buf, col_base + c, m_tile * BLOCK_M + row0);
               bulk_commit_group();
             }
           }
@@ -971,7 +974,7 @@ int conv_plan_create_ex(const mrcnn_conv_desc* d, const void* x, const void* w, 
   if (plan->epi_tma) {
     cuuint64_t odims[2] = {(cuuint64_t)d->cout, (cuuint64_t)p.M};
     cuuint64_t ostr[1] = {(cuuint64_t)d->cout * 2};
-    cuuint32_t obox[2] = {32, (cuuint32_t)BLOCK_M};
+    cuuint32_t obox[2] = {32, 32};      // one epilogue warp's chunk: 32 channels x 32 rows
     rc = encode_map(&plan->tmap_out, out, 2, odims, ostr, obox, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     if (residual) {

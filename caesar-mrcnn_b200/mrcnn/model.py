@@ -406,8 +406,9 @@ class MaskRCNN(object):
         out = []
         for i in range(B):
             n = int(cnt_n[i])
-            out.append({"rois": rois_n[i, :n], "class_ids": cls_n[i, :n], "scores": sc_n[i, :n],
-                        "masks": m_n[i, :, :, :n].view(np.bool_)})
+            # no detections: the reference returns np.empty(original_image_shape[:2] + (0,)) (float64), model.py:2618-2619
+            masks = m_n[i, :, :, :n].view(np.bool_) if n > 0 else np.empty(m_n.shape[1:3] + (0,))
+            out.append({"rois": rois_n[i, :n], "class_ids": cls_n[i, :n], "scores": sc_n[i, :n], "masks": masks})
         return out
 
     def _detect_device(self, molded, metas, windows, orig_shapes):
@@ -569,5 +570,5 @@ class MaskRCNN(object):
                                                   _native.ptr(masks), _native.ptr(ws), ws.numel(),
                                                   torch.cuda.current_stream().cuda_stream), "unmold_detections")
         n = int(cnt.item())
-        full = masks.cpu().numpy()[:, :, :n].view(np.bool_)
+        full = masks.cpu().numpy()[:, :, :n].view(np.bool_) if n > 0 else np.empty((H0, W0, 0))
         return rois.cpu().numpy()[:n], cls.cpu().numpy()[:n], sc.cpu().numpy()[:n], full

@@ -337,6 +337,28 @@ def test_detect_images_of_different_original_sizes(model):
         assert np.array_equal(r["scores"], scores) and np.array_equal(r["masks"], full)
 
 
+def test_no_detections_above_min_confidence(weights, images):
+    """DETECTION_MIN_CONFIDENCE so high that nothing survives: empty arrays with the reference's shapes / dtypes
+    (masks = np.empty([H, W, 0]), float64, mrcnn/model.py:2618-2619), detections all zero."""
+    from mrcnn import model as modellib
+
+    cfg = _config(B)
+    cfg.DETECTION_MIN_CONFIDENCE = 0.9999
+    m = modellib.MaskRCNN(mode="inference", config=cfg, model_dir="/tmp/mrcnn_logs")
+    m.set_weights(weights)
+    results = m.detect(images)
+    det = m.read_tensor("detections")
+    ref = GL.detection_layer(m.read_tensor("rpn_rois"), m.read_tensor("mrcnn_class"), m.read_tensor("mrcnn_bbox"),
+                             H.mold_inputs(images, min_dim=S, max_dim=S, min_scale=0, mode="square",
+                                           mean_pixel=np.array([0, 0, 0]), num_classes=4)[1], min_confidence=0.9999)
+    assert np.array_equal(det.view(np.uint32), ref.view(np.uint32))
+    assert not det.any()
+    for r, im in zip(results, images):
+        assert r["rois"].shape == (0, 4) and r["rois"].dtype == np.int32
+        assert r["class_ids"].shape == (0,) and r["scores"].shape == (0,) and r["scores"].dtype == np.float32
+        assert r["masks"].shape == im.shape[:2] + (0,) and r["masks"].dtype == np.float64
+
+
 def test_base_config_1024_chain_of_custody(weights):
     """Largest configuration (base Config: IMAGE_MAX_DIM = 1024, 261 888 anchors): one full detect_maps, then every
     index-producing stage bit-exact against the oracle fed with the engine's own tensors of that stage, ROIAlign
