@@ -265,38 +265,54 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
   if (warp == 0) {
     // ===== TMA producer: runs ahead across tile boundaries, bounded only by the smem ring =====
     if (lane == 0) {
-      const uint32_t a_bytes = (uint32_t)(p.tw * p.th * p.nb) * (BLOCK_K * 2);
-      uint32_t it = 0;
+      // This one thread paces every layer with few MMAs per k-block (a 128x128x64 k-block is 256 tensor cycles): the
+      // loop body is kept free of integer division / modulo — ring slot, phase, filter tap and channel block are
+      // running counters — so that issuing a k-block costs tens, not hundreds, of dependent instructions.
+      const uint32_t tx_bytes = (uint32_t)(p.tw * p.th * p.nb) * (BLOCK_K * 2) + (uint32_t)Cfg::B_BYTES;
+      const int cin_blocks = p.cin_blocks, kw = p.kw, pad = p.pad;
+      uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
-        const int tw_i = m_tile % p.tiles_w;
-        const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
-        const int tn_i = m_tile / (p.tiles_w * p.tiles_h);
-        int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.nb;
+        int w0, h0, n0;
         if (p.im2col) {                       // base output pixel of this M tile, in padded-box coordinates
           const long long m0 = (long long)m_tile * BLOCK_M;
           const int hw = p.OH * p.OW;
           n0 = (int)(m0 / hw);
           const int rem = (int)(m0 - (long long)n0 * hw);
-          h0 = rem / p.OW - p.pad;
-          w0 = rem - (rem / p.OW) * p.OW - p.pad;
+          h0 = rem / p.OW - pad;
+          w0 = rem - (rem / p.OW) * p.OW - pad;
+        } else if (p.flat) {
+          w0 = m_tile * BLOCK_M; h0 = 0; n0 = 0;
+        } else {
+          const int tw_i = m_tile % p.tiles_w;
+          const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
+          const int tn_i = m_tile / (p.tiles_w * p.tiles_h);
+          w0 = tw_i * p.tw - pad; h0 = th_i * p.th - pad; n0 = tn_i * p.nb;
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          const int tap = kb / p.cin_blocks;
-          const int cb = kb - tap * p.cin_blocks;
-          const int r = tap / p.kw, sx = tap - r * p.kw;
-          const uint32_t a_dst = base_addr + s * Cfg::STAGE_BYTES;
-          const uint32_t b_dst = a_dst + Cfg::A_BYTES;
-          mbar_expect_tx(full_bar(s), a_bytes + Cfg::B_BYTES);
+        const int b_row = n_tile * BLOCK_N;
+        int cb = 0, sx = 0, r = 0;            // channel block, filter column, filter row of the current k-block
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = base_addr + stage * Cfg::STAGE_BYTES;
+          const uint32_t fb = full_bar(stage);
+          mbar_expect_tx(fb, tx_bytes);
           if (p.im2col)
-            tma_load_im2col_4d(a_dst, &tmap_a, full_bar(s), cb * BLOCK_K, w0, h0, n0, (uint16_t)sx, (uint16_t)r);
+            tma_load_im2col_4d(a_dst, &tmap_a, fb, cb * BLOCK_K, w0, h0, n0, (uint16_t)sx, (uint16_t)r);
           else
-            tma_load_4d(a_dst, &tmap_a, full_bar(s), cb * BLOCK_K, w0 + sx - p.pad, h0 + r - p.pad, n0);
-          tma_load_2d(b_dst, &tmap_b, full_bar(s), kb * BLOCK_K, n_tile * BLOCK_N);
+            tma_load_4d(a_dst, &tmap_a, fb, cb * BLOCK_K, w0 + sx, h0 + r, n0);
+          tma_load_2d(a_dst + Cfg::A_BYTES, &tmap_b, fb, kb * BLOCK_K, b_row);
+          if (++cb == cin_blocks) {
+            cb = 0;
+            if (++sx == kw) {
+              sx = 0;
+              ++r;
+            }
+          }
+          if (++stage == (uint32_t)STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -306,17 +322,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BLOCK_N, M = 128
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                                  ((uint32_t)(BLOCK_M >> 4) << 24);
-      uint32_t it = 0, tcount = 0;
+      uint32_t stage = 0, phase = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1u;
         const uint32_t aph = (tcount >> 1) & 1u;
         mbar_wait(tmem_empty_bar(acc), aph ^ 1u);      // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(full_bar(s), ph);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const uint32_t s = stage;
+          mbar_wait(full_bar(s), phase);
+          if (++stage == (uint32_t)STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
           tcgen05_fence_after();
           const uint32_t a_addr = base_addr + s * Cfg::STAGE_BYTES;
           const uint64_t da = make_sw128_desc(a_addr);
