@@ -124,6 +124,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// one lane of a fully converged warp (the warp stays converged around it: the compiler can keep addresses,
+// coordinates and descriptors in uniform registers for the uniform-datapath TMA / MMA instructions)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -263,8 +274,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
   pdl_wait();
 
   if (warp == 0) {
-    // ===== TMA producer: runs ahead across tile boundaries, bounded only by the smem ring =====
-    if (lane == 0) {
+    // ===== TMA producer: runs ahead across tile boundaries, bounded only by the smem ring.  The whole warp walks
+    // the loop converged; one elected lane issues =====
+    {
       // This one thread paces every layer with few MMAs per k-block (a 128x128x64 k-block is 256 tensor cycles): the
       // loop body is kept free of integer division / modulo — ring slot, phase, filter tap and channel block are
       // running counters — so that issuing a k-block costs tens, not hundreds, of dependent instructions.
@@ -296,12 +308,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = base_addr + stage * Cfg::STAGE_BYTES;
           const uint32_t fb = full_bar(stage);
-          mbar_expect_tx(fb, tx_bytes);
-          if (p.im2col)
-            tma_load_im2col_4d(a_dst, &tmap_a, fb, cb * BLOCK_K, w0, h0, n0, (uint16_t)sx, (uint16_t)r);
-          else
-            tma_load_4d(a_dst, &tmap_a, fb, cb * BLOCK_K, w0 + sx, h0 + r, n0);
-          tma_load_2d(a_dst + Cfg::A_BYTES, &tmap_b, fb, kb * BLOCK_K, b_row);
+          if (elect_one()) {
+            mbar_expect_tx(fb, tx_bytes);
+            if (p.im2col)
+              tma_load_im2col_4d(a_dst, &tmap_a, fb, cb * BLOCK_K, w0, h0, n0, (uint16_t)sx, (uint16_t)r);
+            else
+              tma_load_4d(a_dst, &tmap_a, fb, cb * BLOCK_K, w0 + sx, h0 + r, n0);
+            tma_load_2d(a_dst + Cfg::A_BYTES, &tmap_b, fb, kb * BLOCK_K, b_row);
+          }
+          __syncwarp();
           if (++cb == cin_blocks) {
             cb = 0;
             if (++sx == kw) {
@@ -317,8 +332,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: alternates between the two TMEM accumulators =====
-    if (lane == 0) {
+    // ===== MMA issuer: alternates between the two TMEM accumulators (warp converged, one elected lane issues) =====
+    {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BLOCK_N, M = 128
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                                  ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -340,14 +355,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
           const uint32_t a_addr = base_addr + s * Cfg::STAGE_BYTES;
           const uint64_t da = make_sw128_desc(a_addr);
           const uint64_t db = make_sw128_desc(a_addr + Cfg::A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the >>4 address field
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the >>4 address field
+              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(s));          // frees the ring slot once these MMAs have read it
+            if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));      // accumulator complete
           }
-          umma_commit(empty_bar(s));          // frees the ring slot once these MMAs have read it
+          __syncwarp();
         }
-        umma_commit(tmem_full_bar(acc));      // accumulator complete
       }
     }
   } else {
