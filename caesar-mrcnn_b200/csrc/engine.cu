@@ -100,6 +100,8 @@ struct mrcnn_engine {
   // timing
   std::vector<std::string> stage_names;
   std::vector<cudaEvent_t> stage_events;  // stage_names.size() + 1
+  bool use_chain = false;                 // MRCNN_B200_CHAIN=1: ResNet stages as layer chains (one persistent launch each)
+  std::vector<ConvChain*> chains;
   bool use_graph = false;                 // MRCNN_B200_GRAPH=1: replay the plan as a CUDA graph when not profiling
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_fresh = false;
@@ -414,7 +416,7 @@ struct Act {   // NHWC bf16 activation
 
 int add_conv(mrcnn_engine* e, const std::string& stage, const std::string& wname, Act in, int k, int stride, int relu,
              const __nv_bfloat16* residual, int res_up2, const std::string& out_name, Act* out, int out_f32 = 0,
-             int out_ld = 0, int out_mode = 0, void** raw_out = nullptr) {
+             int out_ld = 0, int out_mode = 0, void** raw_out = nullptr, int force_bn = 0) {
   auto it = e->gemm.find(wname);
   if (it == e->gemm.end()) {
     mrcnn_set_error("engine: no GEMM weights for %s", wname.c_str());
@@ -439,9 +441,18 @@ int add_conv(mrcnn_engine* e, const std::string& stage, const std::string& wname
   if (rc) return rc;
   ConvPlan* plan = new ConvPlan();
   e->plans.push_back(plan);
+  if (force_bn > 0) {           // member of a layer chain: fixed tile width, shared-memory/TMA epilogue
+    rc = conv_plan_create_ex(&d, in.p, g.w, g.scale, g.shift, residual, t.ptr, force_bn, 1, plan);
+    if (rc) return rc;
+    if (!plan->epi_tma) {
+      mrcnn_set_error("engine: layer %s cannot join a chain", wname.c_str());
+      return MRCNN_ERR_INVALID;
+    }
+  } else {
   rc = conv_plan_create(&d, in.p, g.w, g.scale, g.shift, residual, t.ptr, 0, plan);
   if (rc) return rc;
-  if (e->autotune) {
+  }
+  if (e->autotune && force_bn == 0) {
     // optional on-disk cache of the choices (MRCNN_B200_AUTOTUNE_CACHE=<file>): a second process — e.g. the same
     // workload under ncu — builds exactly the same launch plan without re-timing (and without the timing launches)
     char key[160];
@@ -505,6 +516,9 @@ int build_graph(mrcnn_engine* e) {
 
   // ---- ResNet-101 stages 2..5 ----------------------------------------------------------------
   const int nblocks[4] = {3, 4, 23, 3};
+  const int chain_bn[4] = {64, 128, 128, 128};     // tile width shared by a stage's chain (res2 has 64-channel layers)
+  std::vector<ConvPlan*> chain_plans;
+  size_t chain_first_step = 0;
   Act C[6];
   for (int s = 0; s < 4; ++s) {
     for (int b = 0; b < nblocks[s]; ++b) {
@@ -512,14 +526,33 @@ int build_graph(mrcnn_engine* e) {
       const std::string base = "res" + std::to_string(s + 2) + blk + "_branch";
       const int stride = (b == 0 && s > 0) ? 2 : 1;
       Act y1, y2, sc, y3;
-      RC(add_conv(e, "backbone", base + "2a", x, 1, stride, 1, nullptr, 0, base + "2a_out", &y1));
-      RC(add_conv(e, "backbone", base + "2b", y1, 3, 1, 1, nullptr, 0, base + "2b_out", &y2));
+      // chain members (MRCNN_B200_CHAIN): everything of the stage after block a's strided 2a / shortcut convs runs
+      // in ONE persistent launch with per-M-tile dependency counters (conv_chain_kernel)
+      const int cbn = e->use_chain ? chain_bn[s] : 0;
+      RC(add_conv(e, "backbone", base + "2a", x, 1, stride, 1, nullptr, 0, base + "2a_out", &y1, 0, 0, 0, nullptr, b == 0 ? 0 : cbn));
+      if (b > 0 && cbn) chain_plans.push_back(e->plans.back());
       if (b == 0) RC(add_conv(e, "backbone", base + "1", x, 1, stride, 0, nullptr, 0, base + "1_out", &sc));
       else sc = x;
+      if (b == 0) chain_first_step = e->steps.size();
+      RC(add_conv(e, "backbone", base + "2b", y1, 3, 1, 1, nullptr, 0, base + "2b_out", &y2, 0, 0, 0, nullptr, cbn));
+      if (cbn) chain_plans.push_back(e->plans.back());
       const std::string oname = (b == nblocks[s] - 1) ? ("C" + std::to_string(s + 2)) : ("res" + std::to_string(s + 2) + blk + "_out");
-      RC(add_conv(e, "backbone", base + "2c", y2, 1, 1, 1, sc.p, 0, oname, &y3));
+      RC(add_conv(e, "backbone", base + "2c", y2, 1, 1, 1, sc.p, 0, oname, &y3, 0, 0, 0, nullptr, cbn));
+      if (cbn) chain_plans.push_back(e->plans.back());
       x = y3;
     }
+    if (e->use_chain && chain_plans.size() >= 2) {
+      ConvChain* chain = new ConvChain();
+      e->chains.push_back(chain);
+      RC(conv_chain_create(chain_plans.data(), (int)chain_plans.size(), chain));
+      // the members' own steps (contiguous from block a's 2b to the stage output) collapse into one chain step
+      e->steps.erase(e->steps.begin() + (long)chain_first_step, e->steps.end());
+      char label[96];
+      snprintf(label, sizeof(label), "res%d chain (%d layers, one launch)", s + 2, (int)chain_plans.size());
+      e->steps.push_back({"backbone", [chain](cudaStream_t st) { return conv_chain_launch(chain, st); }, "conv_gemm", label,
+                          chain->flops});
+    }
+    chain_plans.clear();
     C[s + 2] = x;
   }
 
@@ -764,6 +797,7 @@ extern "C" int mrcnn_engine_create(const mrcnn_engine_config* cfg, int device, m
     return MRCNN_ERR_CUDA;
   }
   if (const char* g = getenv("MRCNN_B200_GRAPH")) e->use_graph = g[0] == '1';
+  if (const char* c = getenv("MRCNN_B200_CHAIN")) e->use_chain = c[0] == '1';
   const char* at = getenv("MRCNN_B200_AUTOTUNE");
   e->autotune = !(at && at[0] == '0');
   if (const char* cp = getenv("MRCNN_B200_AUTOTUNE_CACHE")) {
@@ -788,6 +822,10 @@ extern "C" void mrcnn_engine_destroy(mrcnn_engine* e) {
   for (ConvPlan* p : e->plans) {
     if (p->w2_table) cudaFree(p->w2_table);
     delete p;
+  }
+  for (ConvChain* c : e->chains) {
+    conv_chain_destroy(c);
+    delete c;
   }
   for (auto ev : e->stage_events) cudaEventDestroy(ev);
   for (auto ev : e->step_events) cudaEventDestroy(ev);

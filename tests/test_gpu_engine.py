@@ -359,6 +359,23 @@ def test_no_detections_above_min_confidence(weights, images):
         assert r["masks"].shape == im.shape[:2] + (0,) and r["masks"].dtype == np.float64
 
 
+def test_layer_chain_launches_are_bit_identical(weights, images, run, monkeypatch):
+    """MRCNN_B200_CHAIN=1: each ResNet stage after its strided block-a convs runs as ONE persistent launch with
+    per-(layer, M tile) dependency counters (conv_chain_kernel). The K order per output element does not depend on
+    tiling or launch structure, so every tensor must equal the default per-layer plan bit for bit."""
+    from mrcnn import model as modellib
+    monkeypatch.setenv("MRCNN_B200_CHAIN", "1")
+    m = modellib.MaskRCNN(mode="inference", config=_config(B), model_dir="/tmp/mrcnn_logs")
+    monkeypatch.delenv("MRCNN_B200_CHAIN")
+    m.set_weights(weights)
+    labels = [t[0] for t in m.step_table()] if hasattr(m, "step_table") else []
+    assert any("chain" in lb for lb in labels), "chain steps missing from the launch plan"
+    m.predict([run["molded"], run["metas"], None])
+    for name in ("C2", "C5", "P2", "P5"):
+        assert np.array_equal(m.read_tensor(name), run[name]), name
+    assert np.array_equal(m.read_tensor("detections"), run["detections"])
+
+
 def test_base_config_1024_chain_of_custody(weights):
     """Largest configuration (base Config: IMAGE_MAX_DIM = 1024, 261 888 anchors): one full detect_maps, then every
     index-producing stage bit-exact against the oracle fed with the engine's own tensors of that stage, ROIAlign
