@@ -295,9 +295,21 @@ __global__ void stretch_rgb8_kernel(const float* __restrict__ maps, const float*
       }
     }
   }
+  // one pair of atomics per CTA (warp reduce -> shared -> thread 0): thousands of warps hammering the same two
+  // words per image used to dominate this kernel
+  __shared__ int s_lo[32], s_hi[32];
   lo = __reduce_min_sync(0xffffffffu, lo);
   hi = __reduce_max_sync(0xffffffffu, hi);
   if ((threadIdx.x & 31) == 0) {
+    s_lo[threadIdx.x >> 5] = lo;
+    s_hi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      lo = min(lo, s_lo[w]);
+      hi = max(hi, s_hi[w]);
+    }
     atomicMin(&minmax[2 * img], lo);
     atomicMax(&minmax[2 * img + 1], hi);
   }
@@ -384,8 +396,9 @@ extern "C" int mrcnn_stretch_to_rgb8(const float* maps, const float* params, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MRCNN_CHECK_CUDA(mrcnn_launch(init_minmax_kernel, dim3(ceil_div(n_images, 128)), dim3(128), 0, st, minmax, n_images));
   const size_t npx = (size_t)height * width;
-  int bx = (int)((npx + 255) / 256);
-  if (bx > 148 * 4) bx = 148 * 4;
+  int bx = (int)((npx / 4 + 255) / 256);          // 4 pixels per thread
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;                           // grid-stride beyond that: few CTAs per image, few atomics
   MRCNN_CHECK_CUDA(mrcnn_launch(stretch_rgb8_kernel, dim3(dim3(bx, n_images)), dim3(256), 0, st, maps, params, height, width, rgb, minmax));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(2);

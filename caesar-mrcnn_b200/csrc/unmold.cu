@@ -156,12 +156,31 @@ __global__ void __launch_bounds__(PAINT_THREADS) unmold_paint_kernel(UnmoldParam
   // zero the staging rows (D bytes per pixel)
   const int stage_words = (PAINT_THREADS * D + 3) / 4;
   for (int i = tid; i < stage_words; i += blockDim.x) reinterpret_cast<uint32_t*>(s_row)[i] = 0u;
+  // detections whose box intersects this CTA's pixel span (PAINT_THREADS consecutive pixels in raster order): most
+  // boxes cover a small part of the frame, so the per-pixel loop below runs over a short list instead of all cnt
+  int* s_list = reinterpret_cast<int*>(s_row + (size_t)PAINT_THREADS * D);          // [D]
+  int* s_nlist = s_list + D;
+  if (tid == 0) *s_nlist = 0;
   __syncthreads();
+  {
+    const size_t plast = min(p0 + PAINT_THREADS, npx) - 1;
+    const int ya = (int)(p0 / p.W0), yb = (int)(plast / p.W0);
+    const int xa = (int)(p0 % p.W0), xb = (int)(plast % p.W0);
+    for (int k = tid; k < cnt; k += blockDim.x) {
+      const DetRec& r = s_rec[k];
+      bool hit = r.y1 <= yb && r.y2 > ya;
+      if (hit && ya == yb) hit = r.x1 <= xb && r.x2 > xa;       // span inside one image row: clip in x as well
+      if (hit) s_list[atomicAdd(s_nlist, 1)] = k;
+    }
+  }
+  __syncthreads();
+  const int nlist = *s_nlist;
   const size_t pix = p0 + tid;
   if (pix < npx) {
     const int y = (int)(pix / p.W0), x = (int)(pix % p.W0);
     unsigned char* row = s_row + (size_t)tid * D;
-    for (int k = 0; k < cnt; ++k) {
+    for (int li = 0; li < nlist; ++li) {
+      const int k = s_list[li];                                  // order is irrelevant: each k writes its own byte
       const DetRec& r = s_rec[k];
       if (y < r.y1 || y >= r.y2 || x < r.x1 || x >= r.x2) continue;
       const double rr = __dadd_rn(__dmul_rn(r.rs, (double)(y - r.y1)), r.ro);
@@ -226,7 +245,8 @@ extern "C" int mrcnn_unmold_detections(const float* detections, const float* mrc
   MRCNN_CHECK_CUDA(mrcnn_launch(unmold_boxes_kernel, dim3(batch), dim3(threads), (3 * max_instances + 1) * sizeof(int), st, p));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   const size_t npx = (size_t)p.H0 * p.W0;
-  const size_t smem = (((size_t)max_instances * sizeof(DetRec) + 15) & ~(size_t)15) + (size_t)PAINT_THREADS * max_instances + 16;
+  const size_t smem = (((size_t)max_instances * sizeof(DetRec) + 15) & ~(size_t)15) + (size_t)PAINT_THREADS * max_instances +
+                      (size_t)(max_instances + 1) * sizeof(int) + 16;
   MRCNN_CHECK_CUDA(cudaFuncSetAttribute(unmold_paint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MRCNN_CHECK_CUDA(mrcnn_launch(unmold_paint_kernel, dim3(dim3((unsigned)((npx + PAINT_THREADS - 1) / PAINT_THREADS), batch)), dim3(PAINT_THREADS), smem, st, p));
   MRCNN_CHECK_CUDA(cudaGetLastError());
