@@ -596,17 +596,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             // transposed-conv epilogue fused with the 1x1 conv: affine (FFMA2) -> ReLU + bf16 rounding in one
             // cvt -> 4 FFMA2 per column pair against smem-broadcast weights; nothing is stored per channel
             if (row_ok) {
+              const bool unit_scale = p.unit_scale != 0;
 #pragma unroll
               for (int g = 0; g < 8; ++g) {   // groups of 4 columns
-                const float4 s4 = *reinterpret_cast<const float4*>(t_scale + c + g * 4);
+                // per-channel affine in scalar fp32 (the accumulator registers of tcgen05.ld are not pair-aligned:
+                // packing them for FFMA2 costs more moves than it saves); a unit BN scale (the transposed conv has
+                // no BN) is a plain add of the bias: acc*1 + b == acc + b exactly
                 const float4 t4 = *reinterpret_cast<const float4*>(t_shift + c + g * 4);
-                const uint64_t o01 = ffma2(pack_f32x2(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1])),
-                                           pack_f32x2(s4.x, s4.y), pack_f32x2(t4.x, t4.y));
-                const uint64_t o23 = ffma2(pack_f32x2(__uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3])),
-                                           pack_f32x2(s4.z, s4.w), pack_f32x2(t4.z, t4.w));
-                const float2 f01 = unpack_f32x2(o01), f23 = unpack_f32x2(o23);
-                const uint32_t h01 = p.relu ? cvt_relu_bf16x2(f01.x, f01.y) : pack_bf16x2(f01.x, f01.y);
-                const uint32_t h23 = p.relu ? cvt_relu_bf16x2(f23.x, f23.y) : pack_bf16x2(f23.x, f23.y);
+                float f0, f1, f2, f3;
+                if (unit_scale) {
+                  f0 = __uint_as_float(v[g * 4]) + t4.x;
+                  f1 = __uint_as_float(v[g * 4 + 1]) + t4.y;
+                  f2 = __uint_as_float(v[g * 4 + 2]) + t4.z;
+                  f3 = __uint_as_float(v[g * 4 + 3]) + t4.w;
+                } else {
+                  const float4 s4 = *reinterpret_cast<const float4*>(t_scale + c + g * 4);
+                  f0 = fmaf(__uint_as_float(v[g * 4]), s4.x, t4.x);
+                  f1 = fmaf(__uint_as_float(v[g * 4 + 1]), s4.y, t4.y);
+                  f2 = fmaf(__uint_as_float(v[g * 4 + 2]), s4.z, t4.z);
+                  f3 = fmaf(__uint_as_float(v[g * 4 + 3]), s4.w, t4.w);
+                }
+                const uint32_t h01 = p.relu ? cvt_relu_bf16x2(f0, f1) : pack_bf16x2(f0, f1);
+                const uint32_t h23 = p.relu ? cvt_relu_bf16x2(f2, f3) : pack_bf16x2(f2, f3);
                 const uint64_t x01 = pack_f32x2(__uint_as_float(h01 << 16), __uint_as_float(h01 & 0xffff0000u));
                 const uint64_t x23 = pack_f32x2(__uint_as_float(h23 << 16), __uint_as_float(h23 & 0xffff0000u));
                 const float4* wp = reinterpret_cast<const float4*>(s_w2 + (size_t)((c + g * 4) >> 1) * 8);
@@ -1386,6 +1397,7 @@ int conv_plan_create_ex(const mrcnn_conv_desc* d, const void* x, const void* w, 
   p.w2 = nullptr;
   p.b2 = nullptr;
   p.nc2 = 0;
+  p.unit_scale = 0;
   if (residual) MRCNN_REQUIRE(d->cout % 8 == 0, "conv2d: residual needs cout %% 8 == 0");
   p.n_tiles = ceil_div(cout_total, block_n);
   const long long ctas = (long long)p.n_tiles * p.tiles_w * p.tiles_h * p.tiles_nb;
@@ -1476,7 +1488,7 @@ int conv_chain_launch(const ConvChain* chain, cudaStream_t st) {
   return chain->block_n == 64 ? launch_chain<64>(chain, st) : launch_chain<128>(chain, st);
 }
 
-int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, int nc2, void* out) {
+int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, int nc2, void* out, int unit_scale) {
   MRCNN_REQUIRE(plan && w2 && b2 && out, "fuse_mask_logits: null pointer");
   MRCNN_REQUIRE(plan->block_n == 256 && plan->p.out_mode == 1 && plan->p.cout == 256 && !plan->epi_tma,
                 "fuse_mask_logits: needs a 256-channel transposed-conv plan with 256-wide tiles");
@@ -1485,6 +1497,7 @@ int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, 
   plan->p.w2 = static_cast<const __nv_bfloat16*>(w2);
   plan->p.b2 = b2;
   plan->p.nc2 = nc2;
+  plan->p.unit_scale = unit_scale;
   plan->p.out = out;
   plan->p.out_ld = nc2;
   plan->flops += 2.0 * (double)plan->p.M * 4.0 * 256.0 * nc2;   // the fused 1x1 conv

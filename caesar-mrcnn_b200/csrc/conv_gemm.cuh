@@ -26,6 +26,7 @@ struct ConvGemmParams {
   const __nv_bfloat16* w2;   // [nc2][cout] bf16
   const float* b2;           // [nc2]
   int nc2;
+  int unit_scale;            // out_mode 2: every per-channel scale is exactly 1 (no BN on the transposed conv)
 };
 
 struct ConvPlan {
@@ -51,7 +52,7 @@ int conv_plan_create_ex(const mrcnn_conv_desc* d, const void* x, const void* w, 
 bool conv_plan_epi_tma_eligible(const mrcnn_conv_desc* d);
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);
 // turns a 256-channel deconv plan (block_n 256) into deconv + ReLU + 1x1 conv (nc2) + sigmoid -> float32 out
-int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, int nc2, void* out);
+int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, int nc2, void* out, int unit_scale);
 
 // ---- chain of layers in one persistent launch (see conv_chain_kernel) -----------------------------------
 struct alignas(128) ChainLayerDev {

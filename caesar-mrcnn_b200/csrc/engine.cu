@@ -709,7 +709,7 @@ int build_graph(mrcnn_engine* e) {
     ConvPlan* plan = new ConvPlan();
     e->plans.push_back(plan);
     RC(conv_plan_create(&d, m.p, gd.w, gd.scale, gd.shift, nullptr, t_mask.ptr, 256, plan));
-    RC(conv_plan_fuse_mask_logits(plan, gm.w, gm.shift, NC, t_mask.ptr));
+    RC(conv_plan_fuse_mask_logits(plan, gm.w, gm.shift, NC, t_mask.ptr, /*unit_scale=*/1));   // Conv2DTranspose has no BN
     e->flops += plan->flops;
     e->steps.push_back({"mask_head", [plan](cudaStream_t st) { return conv_plan_launch(plan, st); }, "conv_gemm",
                         "mrcnn_mask (deconv+1x1+sigmoid)", plan->flops});

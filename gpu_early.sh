@@ -1,10 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_engine.py -q -m gpu -x > gpurun_out/tests.log 2>&1; echo "tests exit $?" >> gpurun_out/tests.log; tail -3 gpurun_out/tests.log
-timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"
-python - <<PY
-import json
-d=json.loads(open('gpurun_out/bench.log').read().strip().splitlines()[-1])
-print({k:d.get(k) for k in ('value','ms_per_step')}, d['e2e']['value'], d['roofline']['frac'])
-print(sum(d['stage_ms_per_step'].values()))
-PY
+timeout 900 python -m pytest tests/test_gpu_engine.py tests/test_gpu_conv.py -q -m gpu -x > gpurun_out/tests.log 2>&1; echo "tests exit $?" >> gpurun_out/tests.log; tail -3 gpurun_out/tests.log
+timeout 300 python tools/layer_table.py 64 > gpurun_out/layer_table.txt 2>&1
+grep "mrcnn_mask (\|total" gpurun_out/layer_table.txt | cut -c1-90
