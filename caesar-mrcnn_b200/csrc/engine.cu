@@ -385,7 +385,7 @@ int autotune_block_n(mrcnn_engine* e, const mrcnn_conv_desc* d, const void* x, c
       ConvPlan trial;
       if (conv_plan_create_ex(d, x, g.w, g.scale, g.shift, residual, out, bn, epi, &trial) != MRCNN_OK) continue;
       float tmin = 1e30f;
-      for (int rep = 0; rep < 6; ++rep) {
+      for (int rep = 0; rep < 10; ++rep) {       // 2 warm-up launches, minimum of 8
         MRCNN_CHECK_CUDA(cudaEventRecord(e0, e->stream));
         int rc = conv_plan_launch(&trial, e->stream);
         if (rc) return rc;
