@@ -973,6 +973,14 @@ extern "C" int mrcnn_engine_predict(mrcnn_engine* e, const float* molded, const 
 
 extern "C" int mrcnn_engine_tensor(const mrcnn_engine* e, const char* name, void** device_ptr, size_t* bytes) {
   MRCNN_REQUIRE(e && name, "engine_tensor: null pointer");
+  if (!strncmp(name, "unmold_masks", 12)) {   // [B,H0,W0,D] uint8 of result slot 0 / 1 (sized by the last detect call)
+    const int slot = !strcmp(name + 12, "#1") ? 1 : 0;
+    MRCNN_REQUIRE(name[12] == 0 || slot == 1, "engine_tensor: unknown tensor '%s'", name);
+    MRCNN_REQUIRE(e->slots[slot].masks, "engine_tensor: '%s' has not been produced yet", name);
+    if (device_ptr) *device_ptr = e->slots[slot].masks;
+    if (bytes) *bytes = e->slots[slot].masks_bytes;
+    return MRCNN_OK;
+  }
   auto it = e->tensors.find(name);
   if (it == e->tensors.end()) {
     mrcnn_set_error("engine_tensor: unknown tensor '%s'", name);

@@ -94,6 +94,16 @@ SIGNATURES = {
                                        ctypes.POINTER(c_float), ctypes.POINTER(ctypes.c_double)]),
     "mrcnn_engine_kernel_times": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_float),
                                           ctypes.POINTER(c_int)]),
+    "mrcnn_plane_words": (c_size_t, [c_int, c_int]),
+    "mrcnn_masks_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mrcnn_planes_area_bbox": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mrcnn_planes_pair_stats": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mrcnn_planes_union": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "mrcnn_planes_label_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mrcnn_planes_label": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mrcnn_labels_select": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "mrcnn_planes_pixels": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "mrcnn_planes_unpack": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

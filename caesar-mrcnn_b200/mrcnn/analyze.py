@@ -1,0 +1,641 @@
+"""Analyzer: detection post-processing of the reference (mrcnn/analyze.py:580-2173), detect side only.
+
+Mirrors the reference's `Analyzer` surface for the path that follows `model.detect()` on both CLI commands —
+`predict()` :833-904, `extract_det_masks()` :1162-1423, `make_json_results()` :1866-1942,
+`write_json_results()` :1945-1957, `merge_masks()` :2142, `extract_mask_connected_components()` :2148,
+`are_mask_connected()` :2154 — with the same attribute names, option flags and output structures.
+
+What runs where. The reference holds every detection as a full-frame numpy array and runs skimage labelling three
+times per mask pair plus sklearn's jaccard_score on the flattened frames. Here the masks stay in HBM as bit-planes
+(csrc/analyze.cu through the C ABI: mrcnn_masks_pack, mrcnn_planes_label, mrcnn_labels_select,
+mrcnn_planes_pair_stats, mrcnn_planes_union, mrcnn_planes_area_bbox, mrcnn_planes_pixels, mrcnn_planes_unpack);
+the host keeps only the tiny graph logic (score filter and ordering, the merge graph's DFS components, networkx
+maximal cliques, selection), written with the same numpy / networkx calls as the reference so ties and scalar
+types behave identically. `predict_maps()` is the device-resident extension: it runs `model.detect_maps(...,
+device_only=True)` and post-processes the whole batch without ever copying the [H,W,100] masks to the host.
+
+Not provided (SURVEY.md §8 marks them out of scope): ground-truth handling / performance metrics, drawing, DS9
+regions. The "vertexes" key of the JSON objects needs skimage.measure.find_contours: it is filled when scikit-image
+is importable and left as an empty list otherwise.
+There is no CPU fallback: every mask operation goes through libmrcnn_b200.so and needs a CUDA device.
+"""
+import ctypes
+import json
+import logging
+
+import numpy as np
+
+from . import _native, utils
+
+logger = logging.getLogger(__name__)
+
+# labels that extract_det_masks never splits into connected components (analyze.py:1223)
+_UNSPLIT_LABELS = ("galaxy_C2", "galaxy_C3", "galaxy", "extended-multisland")
+
+
+class Graph:
+    """Undirected graph with DFS connected components (reference: mrcnn/graph.py). Components come out in order
+    of their smallest vertex, members in pre-order of a depth-first walk that follows edges in insertion order."""
+
+    def __init__(self, V):
+        self.V = V
+        self.adj = [[] for _ in range(V)]
+
+    def addEdge(self, v, w):
+        self.adj[v].append(w)
+        self.adj[w].append(v)
+
+    def connectedComponents(self):
+        visited = [False] * self.V
+        components = []
+        for start in range(self.V):
+            if visited[start]:
+                continue
+            members, stack = [], [iter((start,))]
+            while stack:                       # explicit stack: same visiting order as the recursive walk
+                for v in stack[-1]:
+                    if not visited[v]:
+                        visited[v] = True
+                        members.append(v)
+                        stack.append(iter(self.adj[v]))
+                        break
+                else:
+                    stack.pop()
+            components.append(members)
+        return components
+
+
+class _Frame:
+    """One image's detections: device masks [H,W,depth] uint8 (address), host class ids / scores."""
+
+    def __init__(self, masks_ptr, depth, n, class_ids, scores, keepalive=None):
+        self.masks_ptr, self.depth, self.n = masks_ptr, depth, n
+        self.class_ids, self.scores = class_ids, scores
+        self.keepalive = keepalive
+
+
+class _FrameResult:
+    def __init__(self):
+        self.masks_final, self.class_ids_final, self.class_names_final = [], [], []
+        self.scores_final, self.bboxes, self.captions = [], [], []
+        self.pixels = []          # per final object: int32 [npix,2] (y,x) with the image origin already added
+
+
+class MaskPlaneOps:
+    """Thin host wrapper of the bit-plane entry points of the C ABI (device memory through torch)."""
+
+    def __init__(self, device=0, stream=None):
+        self.torch = utils._torch()
+        self.lib = _native.lib()
+        self.device = self.torch.device("cuda:%d" % int(device))
+        self.stream = stream
+
+    def _st(self):
+        return ctypes.c_void_p(self.stream.cuda_stream if self.stream is not None
+                               else self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ctx(self):
+        return self.torch.cuda.stream(self.stream) if self.stream is not None else self.torch.cuda.device(self.device)
+
+    def words(self, H, W):
+        return int(self.lib.mrcnn_plane_words(H, W))
+
+    def to_dev(self, array, dtype):
+        t = self.torch.from_numpy(np.ascontiguousarray(array, dtype=dtype))
+        with self._ctx():
+            return t.to(self.device, non_blocking=False)
+
+    def empty(self, shape, dtype):
+        with self._ctx():
+            return self.torch.empty(shape, dtype=dtype, device=self.device)
+
+    def pack(self, masks_ptr, n_images, H, W, depth, plane_of, n_planes):
+        """masks [n_images,H,W,depth] uint8 at device address masks_ptr; plane_of host int32 [n_images*depth]."""
+        planes = self.empty((max(n_planes, 1), self.words(H, W)), self.torch.int32)
+        d_map = self.to_dev(plane_of, np.int32)
+        _native.check(self.lib.mrcnn_masks_pack(ctypes.c_void_p(masks_ptr), n_images, H, W, depth, _native.ptr(d_map),
+                                                _native.ptr(planes), self._st()), "masks_pack")
+        return planes[:n_planes]
+
+    def area_bbox(self, planes, H, W):
+        n = int(planes.shape[0])
+        area = self.empty((max(n, 1),), self.torch.int32)
+        bbox = self.empty((max(n, 1), 4), self.torch.int32)
+        _native.check(self.lib.mrcnn_planes_area_bbox(_native.ptr(planes), n, H, W, _native.ptr(area), _native.ptr(bbox),
+                                                      self._st()), "planes_area_bbox")
+        return area[:n], bbox[:n]
+
+    def pair_stats(self, planes, H, W, pairs):
+        """pairs host int32 [P,2] -> device (inter [P], touch [P])."""
+        P = int(pairs.shape[0])
+        inter = self.empty((max(P, 1),), self.torch.int32)
+        touch = self.empty((max(P, 1),), self.torch.int32)
+        if P:
+            d_pairs = self.to_dev(pairs, np.int32)
+            _native.check(self.lib.mrcnn_planes_pair_stats(_native.ptr(planes), H, W, _native.ptr(d_pairs), P, _native.ptr(inter),
+                                                           _native.ptr(touch), self._st()), "planes_pair_stats")
+        return inter[:P], touch[:P]
+
+    def union(self, planes, H, W, groups):
+        """groups: list of lists of plane indices -> [len(groups), words] planes."""
+        G = len(groups)
+        out = self.empty((max(G, 1), self.words(H, W)), self.torch.int32)
+        if G:
+            members = np.concatenate([np.asarray(g, dtype=np.int32) for g in groups])
+            offsets = np.zeros(G + 1, dtype=np.int32)
+            offsets[1:] = np.cumsum([len(g) for g in groups])
+            d_m, d_o = self.to_dev(members, np.int32), self.to_dev(offsets, np.int32)
+            _native.check(self.lib.mrcnn_planes_union(_native.ptr(planes), H, W, _native.ptr(d_m), _native.ptr(d_o), G,
+                                                      _native.ptr(out), self._st()), "planes_union")
+        return out[:G]
+
+    def label(self, planes, H, W):
+        """-> (labels [n,H,W] int32 device, counts [n] int32 device)"""
+        n = int(planes.shape[0])
+        labels = self.empty((max(n, 1), H, W), self.torch.int32)
+        counts = self.empty((max(n, 1),), self.torch.int32)
+        if n:
+            ws_bytes = int(self.lib.mrcnn_planes_label_workspace_bytes(n, H, W))
+            ws = self.empty((ws_bytes,), self.torch.uint8)
+            _native.check(self.lib.mrcnn_planes_label(_native.ptr(planes), n, H, W, _native.ptr(labels), _native.ptr(counts),
+                                                      _native.ptr(ws), ws_bytes, self._st()), "planes_label")
+        return labels[:n], counts[:n]
+
+    def select(self, labels, H, W, src, comp):
+        K = len(src)
+        out = self.empty((max(K, 1), self.words(H, W)), self.torch.int32)
+        if K:
+            d_s, d_c = self.to_dev(src, np.int32), self.to_dev(comp, np.int32)
+            _native.check(self.lib.mrcnn_labels_select(_native.ptr(labels), H, W, _native.ptr(d_s), _native.ptr(d_c), K,
+                                                       _native.ptr(out), self._st()), "labels_select")
+        return out[:K]
+
+    def pixels(self, planes, H, W, areas, y0=0, x0=0):
+        """areas: host int array [n]; -> host int32 [sum(areas),2] and the int64 offsets [n+1]."""
+        n = int(planes.shape[0])
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        offsets[1:] = np.cumsum(np.asarray(areas, dtype=np.int64))
+        total = int(offsets[-1])
+        out = self.empty((max(total, 1), 2), self.torch.int32)
+        if n and total:
+            d_o = self.to_dev(offsets[:-1], np.int64)
+            _native.check(self.lib.mrcnn_planes_pixels(_native.ptr(planes), n, H, W, _native.ptr(d_o), int(y0), int(x0),
+                                                       _native.ptr(out), self._st()), "planes_pixels")
+        return self.host(out[:total]), offsets
+
+    def unpack(self, planes, H, W):
+        n = int(planes.shape[0])
+        out = self.empty((max(n, 1), H, W), self.torch.uint8)
+        if n:
+            _native.check(self.lib.mrcnn_planes_unpack(_native.ptr(planes), n, H, W, _native.ptr(out), self._st()), "planes_unpack")
+        return self.host(out[:n])
+
+    def gather(self, planes, index):
+        with self._ctx():
+            idx = self.torch.from_numpy(np.asarray(index, dtype=np.int64)).to(self.device)
+            return planes.index_select(0, idx).contiguous()
+
+    def host(self, t):
+        with self._ctx():
+            h = t.cpu()
+        return h.numpy()
+
+
+class Analyzer(object):
+    """Post-processes the detector output of one image into the final source list (reference: analyze.py:580)."""
+
+    def __init__(self, model, config, dataset=None):
+        self.model = model
+        self.config = config
+        self.n_classes = dataset.nclasses if dataset else self.config.NUM_CLASSES
+        self.dataset = dataset
+        # data
+        self.image = None
+        self.image_header = None
+        self.image_id = -1
+        self.image_xmin = 0
+        self.image_ymin = 0
+        # raw model output
+        self.class_names = None
+        self.masks = None
+        self.boxes = None
+        self.class_ids = None
+        self.scores = None
+        self.nobjects = 0
+        # processed detections
+        self.masks_final = []
+        self.class_ids_final = []
+        self.class_names_final = []
+        self.scores_final = []
+        self.bboxes = []
+        self.captions = []
+        self.split_masks = False
+        self.merge_overlapped_masks = True
+        self.select_best_overlapped_masks = True
+        self.split_source_sidelobe = True
+        self.merge_overlap_iou_thr = 0.3
+        self.results = {}
+        self.obj_name_tag = ""
+        # thresholds
+        self.score_thr = 0.7
+        self.iou_thr = 0.6
+        # outputs (drawing and DS9 regions are outside the rebuilt path: both default to off here)
+        self.outfile = ""
+        self.outfile_json = ""
+        self.outfile_ds9 = ""
+        self.draw = False
+        self.write_to_json = True
+        self.write_to_ds9 = False
+        self._final_pixels = None
+        self._ops = None
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _plane_ops(self):
+        if self._ops is None:
+            device = getattr(self.model, "_device", 0) if self.model is not None else 0
+            stream = getattr(self.model, "_stream", None) if self.model is not None else None
+            self._ops = MaskPlaneOps(device, stream)
+        return self._ops
+
+    def _options(self):
+        return dict(score_thr=self.score_thr, split_masks=self.split_masks, merge_overlapped_masks=self.merge_overlapped_masks,
+                    select_best_overlapped_masks=self.select_best_overlapped_masks,
+                    split_source_sidelobe=self.split_source_sidelobe, merge_overlap_iou_thr=self.merge_overlap_iou_thr)
+
+    # -- reference API ----------------------------------------------------------------------------
+    def predict(self, image, image_id='', bboxes_gt=[], header=None, xmin=0, ymin=0):
+        """reference: analyze.py:833-904 (drawing and DS9 output excluded)."""
+        if image is None:
+            logger.error("No input image given!")
+            return -1
+        self.image = image
+        self.image_xmin = xmin
+        self.image_ymin = ymin
+        if image_id:
+            self.image_id = image_id
+        if header:
+            self.image_header = header
+        r = self.model.detect([self.image], verbose=0)[0]
+        self.class_names = self.config.CLASS_NAMES
+        self.masks = r['masks']
+        self.boxes = r['rois']
+        self.class_ids = r['class_ids']
+        self.scores = r['scores']
+        self.nobjects = self.masks.shape[-1]
+        if self.nobjects > 0:
+            self.extract_det_masks()
+        else:
+            logger.warning("No detected object found for image %s ..." % self.image_id)
+            return 0
+        self.bboxes_gt = bboxes_gt
+        if self.draw or self.write_to_ds9:
+            raise NotImplementedError("drawing / DS9 regions are outside the rebuilt detect path (DESIGN.md §6)")
+        self.make_json_results()
+        if self.write_to_json:
+            self.write_json_results(self.outfile_json if self.outfile_json != "" else 'out_' + str(self.image_id) + '.json')
+        return 0
+
+    def extract_det_masks(self):
+        """reference: analyze.py:1162-1423, from self.masks [H,W,N] / self.boxes / self.class_ids / self.scores."""
+        ops = self._plane_ops()
+        masks = np.asarray(self.masks)
+        H, W, depth = masks.shape
+        N = int(np.asarray(self.boxes).shape[0])
+        d_masks = ops.to_dev(masks.view(np.uint8) if masks.dtype == np.bool_ else (masks != 0).view(np.uint8), np.uint8)
+        frame = _Frame(d_masks.data_ptr(), depth, N, self.class_ids, self.scores, keepalive=d_masks)
+        res = analyze_frames(ops, [frame], H, W, self.class_names, origins=[(self.image_ymin, self.image_xmin)],
+                             **self._options())[0]
+        self._publish(res)
+
+    def _publish(self, res):
+        self.masks_final = res.masks_final
+        self.class_ids_final = res.class_ids_final
+        self.class_names_final = res.class_names_final
+        self.scores_final = res.scores_final
+        self.bboxes = res.bboxes
+        self.captions = res.captions
+        self._final_pixels = res.pixels
+
+    def make_json_results(self):
+        """reference: analyze.py:1866-1942."""
+        shape = self.image.shape
+        self.results = build_json_results(self.image_id, self.obj_name_tag, self.class_names, shape[0], shape[1],
+                                          self.image_xmin, self.image_ymin, self.masks_final, self.class_ids_final,
+                                          self.scores_final, self.bboxes, self._final_pixels)
+
+    def write_json_results(self, outfile):
+        """reference: analyze.py:1945-1957 (numpy scalars are written as plain numbers)."""
+        if not self.results:
+            logger.warning("Result obj dictionary is empty, nothing to be written...")
+            return
+        with open(outfile, 'w') as fp:
+            json.dump(self.results, fp, indent=2, sort_keys=True, cls=NumpyEncoder)
+
+    def merge_masks(self, mask1, mask2):
+        """reference: analyze.py:2142-2146 — union of two masks (computed on the device)."""
+        ops = self._plane_ops()
+        H, W = np.asarray(mask1).shape
+        planes = _planes_from_host(ops, [mask1, mask2])
+        out = ops.unpack(ops.union(planes, H, W, [[0, 1]]), H, W)[0]
+        dt = np.result_type(np.asarray(mask1).dtype, np.asarray(mask2).dtype)
+        return out.view(np.bool_) if dt == np.bool_ else out.astype(dt)
+
+    def extract_mask_connected_components(self, mask):
+        """reference: analyze.py:2148-2151 — (labels [H,W], ncomponents), 4-connectivity, raster-order numbering."""
+        ops = self._plane_ops()
+        H, W = np.asarray(mask).shape
+        labels, counts = ops.label(_planes_from_host(ops, [mask]), H, W)
+        return ops.host(labels)[0].astype(np.int64), int(ops.host(counts)[0])
+
+    def are_mask_connected(self, mask1, mask2):
+        """reference: analyze.py:2154-2173."""
+        ops = self._plane_ops()
+        H, W = np.asarray(mask1).shape
+        _, touch = ops.pair_stats(_planes_from_host(ops, [mask1, mask2]), H, W, np.array([[0, 1]], dtype=np.int32))
+        return bool(ops.host(touch)[0])
+
+    # -- device-resident extension ---------------------------------------------------------------------
+    def predict_maps(self, maps, image_ids=None, origins=None, zscale_contrasts=(0.25, 0.25, 0.25)):
+        """maps [BATCH_SIZE,H,W] float32 -> one results dict (make_json_results layout) per image. The detector's
+        [B,H,W,100] masks never leave the GPU: only class ids, scores, boxes and the final pixel lists do."""
+        model, c = self.model, self.config
+        B, D = c.BATCH_SIZE, c.DETECTION_MAX_INSTANCES
+        H, W = int(maps.shape[1]), int(maps.shape[2])
+        lib, eng = model._lib, model._engine
+        slot = lib.mrcnn_engine_next_slot(eng)
+        sfx = b"" if slot == 0 else b"#1"
+        model.detect_maps(maps, zscale_contrasts, device_only=True)
+
+        def read(name, dtype, shape):
+            out = np.empty(shape, dtype=dtype)
+            _native.check(lib.mrcnn_engine_read(eng, name + sfx, out.ctypes.data, out.nbytes), "read")
+            return out
+
+        counts = read(b"unmold_counts", np.int32, (B,))
+        class_ids = read(b"unmold_class_ids", np.int32, (B, D))
+        scores = read(b"unmold_scores", np.float32, (B, D))
+        ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+        _native.check(lib.mrcnn_engine_tensor(eng, b"unmold_masks" + sfx, ctypes.byref(ptr), ctypes.byref(nbytes)), "unmold_masks")
+        frames = [_Frame(ptr.value + b * H * W * D, D, int(counts[b]), class_ids[b, :counts[b]], scores[b, :counts[b]])
+                  for b in range(B)]
+        origins = origins if origins is not None else [(0, 0)] * B
+        self.class_names = c.CLASS_NAMES
+        results = analyze_frames(self._plane_ops(), frames, H, W, self.class_names, origins=origins, want_masks=False,
+                                 **self._options())
+        out = []
+        for b, res in enumerate(results):
+            image_id = image_ids[b] if image_ids is not None else b
+            out.append(build_json_results(image_id, self.obj_name_tag, self.class_names, H, W, origins[b][1], origins[b][0],
+                                          res.masks_final, res.class_ids_final, res.scores_final, res.bboxes, res.pixels))
+        return out
+
+
+class NumpyEncoder(json.JSONEncoder):
+    def default(self, obj):
+        if isinstance(obj, np.integer):
+            return int(obj)
+        if isinstance(obj, np.floating):
+            return float(obj)
+        if isinstance(obj, np.ndarray):
+            return obj.tolist()
+        return json.JSONEncoder.default(self, obj)
+
+
+def _planes_from_host(ops, masks):
+    stack = np.stack([(np.asarray(m) != 0) for m in masks], axis=-1).view(np.uint8)      # [H,W,n]
+    H, W, n = stack.shape
+    d = ops.to_dev(stack, np.uint8)
+    return ops.pack(d.data_ptr(), 1, H, W, n, np.arange(n, dtype=np.int32), n)
+
+
+def _find_contours():
+    try:
+        from skimage.measure import find_contours
+        return find_contours
+    except ImportError:
+        return None
+
+
+def build_json_results(image_id, obj_name_tag, class_names, ny, nx, xmin, ymin, masks_final, class_ids_final, scores_final,
+                       bboxes, pixels):
+    """reference: analyze.py:1866-1942. `pixels`: per object int32 [npix,2] (y,x), image origin already added
+    (np.argwhere(mask==1) computed on the device)."""
+    results = {"image_id": image_id, "objs": []}
+    find_contours = _find_contours()
+    for i in range(len(class_ids_final)):
+        class_id = int(class_ids_final[i])
+        y1, x1, y2, x2 = (int(v) for v in bboxes[i])
+        at_edge = x1 <= 0 or x1 >= nx - 1 or x2 <= 0 or x2 >= nx - 1 or y1 <= 0 or y1 >= ny - 1 or y2 <= 0 or y2 >= ny - 1
+        vertex_list = []
+        if find_contours is not None and masks_final and masks_final[i] is not None:
+            mask = masks_final[i]
+            padded = np.zeros((mask.shape[0] + 2, mask.shape[1] + 2), dtype=np.uint8)
+            padded[1:-1, 1:-1] = mask
+            for verts in find_contours(padded, 0.5):
+                vertex_list.append((np.fliplr(verts) - 1 + np.array([xmin, ymin])).tolist() if (xmin != 0 or ymin != 0)
+                                   else (np.fliplr(verts) - 1).tolist())
+        results["objs"].append({
+            "name": 'S' + str(i + 1) + "_" + obj_name_tag,
+            "x1": xmin + x1, "x2": xmin + x2, "y1": ymin + y1, "y2": ymin + y2,
+            "class_id": class_id, "class_name": class_names[class_id], "score": scores_final[i],
+            "pixels": pixels[i].tolist(), "vertexes": vertex_list, "edge": at_edge,
+        })
+    return results
+
+
+def _all_pairs(counts):
+    """(i<j) pairs inside each frame, in the reference's loop order -> (pairs [P,2] global indices, per-frame slices)."""
+    chunks, slices, base, pos = [], [], 0, 0
+    for n in counts:
+        if n > 1:
+            i, j = np.triu_indices(n, k=1)
+            chunks.append(np.stack([i + base, j + base], axis=1))
+        npairs = n * (n - 1) // 2
+        slices.append((pos, pos + npairs, base))
+        pos += npairs
+        base += n
+    pairs = np.concatenate(chunks).astype(np.int32) if chunks else np.zeros((0, 2), dtype=np.int32)
+    return pairs, slices
+
+
+def _iou(inter, area_a, area_b):
+    """sklearn jaccard_score(average='binary'): tp / (tp + fp + fn) in float64, 0.0 for an empty union."""
+    union = area_a.astype(np.int64) + area_b.astype(np.int64) - inter.astype(np.int64)
+    out = np.zeros(inter.shape, dtype=np.float64)
+    np.divide(inter.astype(np.float64), union.astype(np.float64), out=out, where=union > 0)
+    return out
+
+
+def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True, score_thr=0.7, split_masks=False,
+                   merge_overlapped_masks=True, select_best_overlapped_masks=True, split_source_sidelobe=True,
+                   merge_overlap_iou_thr=0.3):
+    """extract_det_masks (+ the pixel lists of make_json_results) for a list of frames that share one [H,W] size.
+    All masks of one frame list must live in ONE device allocation laid out [n_frames,H,W,depth] when
+    len(frames) > 1 (the engine's result slot), or be a single frame."""
+    import networkx as nx
+
+    F = len(frames)
+    depth = frames[0].depth
+    base_ptr = frames[0].masks_ptr
+    for f, fr in enumerate(frames):
+        assert fr.depth == depth and fr.masks_ptr == base_ptr + f * H * W * depth, "frames must be one [F,H,W,depth] block"
+    origins = origins if origins is not None else [(0, 0)] * F
+
+    # -- score filter and descending-score order (analyze.py:1181-1203): host, the reference's own numpy calls
+    plane_of = np.full(F * depth, -1, dtype=np.int32)
+    sel_cls, sel_score, sel_count = [], [], []
+    m = 0
+    for f, fr in enumerate(frames):
+        picked = [i for i in range(fr.n) if not fr.scores[i] < score_thr]
+        scores_sel = [fr.scores[i] for i in picked]
+        order = np.argsort(scores_sel)[::-1]
+        for index in order:
+            plane_of[f * depth + picked[index]] = m
+            sel_cls.append(fr.class_ids[picked[index]])
+            sel_score.append(scores_sel[index])
+            m += 1
+        sel_count.append(len(picked))
+    planes = ops.pack(base_ptr, F, H, W, depth, plane_of, m)
+
+    # -- optional split into 4-connected components (analyze.py:1211-1255)
+    det_cls, det_score, det_int, det_count = sel_cls, sel_score, [False] * m, sel_count
+    if split_masks and m:
+        splittable = [class_names[c] not in _UNSPLIT_LABELS for c in sel_cls]
+        labels, counts = ops.label(planes, H, W)
+        ncomp = ops.host(counts)
+        src, comp, keep_src, keep_dst = [], [], [], []
+        det_cls, det_score, det_int, det_count = [], [], [], []
+        pos = 0
+        for f in range(F):
+            n_f = 0
+            for _ in range(sel_count[f]):
+                k = 1 if not splittable[pos] else int(ncomp[pos])
+                for c in range(k):
+                    if splittable[pos]:
+                        src.append(pos)
+                        comp.append(c + 1)
+                    else:
+                        keep_src.append(pos)
+                        keep_dst.append(len(det_cls))
+                    det_cls.append(sel_cls[pos])
+                    det_score.append(sel_score[pos])
+                    det_int.append(splittable[pos])      # np.where(labels == c + 1, [1], [0]) is an int64 array
+                n_f += k
+                pos += 1
+            det_count.append(n_f)
+        parts = ops.select(labels, H, W, src, comp)
+        if keep_src:
+            is_keep = np.zeros(len(det_cls), dtype=bool)
+            is_keep[keep_dst] = True
+            origin_idx = np.empty(len(det_cls), dtype=np.int64)     # row of cat([parts, planes]) for every det mask
+            origin_idx[~is_keep] = np.arange(len(src))
+            origin_idx[is_keep] = len(src) + np.asarray(keep_src, dtype=np.int64)
+            planes = ops.gather(ops.torch.cat([parts, planes], dim=0), origin_idx)
+        else:
+            planes = parts
+
+    # -- merge connected same-class masks above the IOU threshold (analyze.py:1258-1320)
+    merged_cls, merged_score, merged_int, merged_count = det_cls, det_score, det_int, det_count
+    if merge_overlapped_masks and len(det_cls):
+        pairs, slices = _all_pairs(det_count)
+        d_area, _ = ops.area_bbox(planes, H, W)
+        d_inter, d_touch = ops.pair_stats(planes, H, W, pairs)
+        area, inter, touch = ops.host(d_area), ops.host(d_inter), ops.host(d_touch)
+        cls_arr = np.asarray(det_cls)
+        iou = _iou(inter, area[pairs[:, 0]], area[pairs[:, 1]])
+        mergeable = (touch != 0) & (cls_arr[pairs[:, 0]] == cls_arr[pairs[:, 1]]) & (iou >= merge_overlap_iou_thr)
+        groups, merged_cls, merged_score, merged_int, merged_count = [], [], [], [], []
+        for f, (lo, hi, base) in enumerate(slices):
+            g = Graph(det_count[f])
+            for k in np.nonzero(mergeable[lo:hi])[0]:
+                g.addEdge(int(pairs[lo + k, 0]) - base, int(pairs[lo + k, 1]) - base)
+            cc = g.connectedComponents()
+            for members in cc:
+                score_avg = 0
+                for index in members:
+                    class_id = det_cls[base + index]
+                    score_avg += det_score[base + index]
+                score_avg *= 1. / len(members)
+                groups.append([base + index for index in members])
+                merged_cls.append(class_id)
+                merged_score.append(score_avg)
+                merged_int.append(any(det_int[base + index] for index in members))
+            merged_count.append(len(cc))
+        planes = ops.union(planes, H, W, groups)
+
+    results = [_FrameResult() for _ in range(F)]
+    if not select_best_overlapped_masks or not len(merged_cls):     # analyze.py:1324: nothing is published otherwise
+        return results
+
+    # -- best of overlapping objects through maximal cliques (analyze.py:1328-1395)
+    pairs, slices = _all_pairs(merged_count)
+    d_area, d_bbox = ops.area_bbox(planes, H, W)
+    d_inter, d_touch = ops.pair_stats(planes, H, W, pairs)
+    area, bbox, inter, touch = ops.host(d_area), ops.host(d_bbox), ops.host(d_inter), ops.host(d_touch)
+    spurious = np.array([class_names[c] == 'spurious' for c in merged_cls], dtype=bool)
+    linked = touch != 0
+    if split_source_sidelobe:
+        iou = _iou(inter, area[pairs[:, 0]], area[pairs[:, 1]])
+        linked &= ~((spurious[pairs[:, 0]] != spurious[pairs[:, 1]]) & (iou < merge_overlap_iou_thr))
+    final_planes, final_owner = [], []
+    for f, (lo, hi, base) in enumerate(slices):
+        g_final = nx.Graph()
+        for k in np.nonzero(linked[lo:hi])[0]:
+            g_final.add_edge(int(pairs[lo + k, 0]) - base, int(pairs[lo + k, 1]) - base)
+        cliques = list(nx.find_cliques(g_final))
+        clique_max_scores, clique_max_score_index = [], []
+        for item in cliques:
+            max_score, max_score_index = -1, -1
+            for index in item:
+                score = merged_score[base + index]
+                if score > max_score:
+                    max_score, max_score_index = score, index
+            clique_max_scores.append(max_score)
+            clique_max_score_index.append(max_score_index)
+        is_selected = [True] * merged_count[f]
+        for q in sorted(range(len(cliques)), key=lambda k: clique_max_scores[k], reverse=True):
+            for index in cliques[q]:
+                if index != clique_max_score_index[q] and is_selected[index]:
+                    is_selected[index] = False
+        res = results[f]
+        for index in range(merged_count[f]):
+            if not is_selected[index]:
+                continue
+            bb = bbox[base + index]
+            if bb[1] >= bb[3] or bb[0] >= bb[2]:
+                logger.warning("Invalid det bbox(%d,%d,%d,%d), skip it ..." % (bb[1], bb[3], bb[0], bb[2]))
+                continue
+            label = class_names[merged_cls[base + index]]
+            res.class_ids_final.append(merged_cls[base + index])
+            res.class_names_final.append(label)
+            res.scores_final.append(merged_score[base + index])
+            res.bboxes.append(bb.copy())
+            res.captions.append("{} {:.2f}".format(label, merged_score[base + index]))
+            final_planes.append(base + index)
+            final_owner.append(f)
+
+    # -- final masks and pixel lists (make_json_results: np.argwhere(mask == 1), analyze.py:1903-1909)
+    if final_planes:
+        fin = ops.gather(planes, final_planes)
+        unpacked = ops.unpack(fin, H, W) if want_masks else None
+        owner = np.asarray(final_owner)
+        fin_area = area[np.asarray(final_planes)]
+        same_origin = all(tuple(o) == tuple(origins[0]) for o in origins)
+        if same_origin:                                          # one launch and one copy for the whole batch
+            px_all, off_all = ops.pixels(fin, H, W, fin_area, origins[0][0], origins[0][1])
+        for f in range(F):
+            rows = np.nonzero(owner == f)[0]
+            if not len(rows):
+                continue
+            if same_origin:
+                px, offsets = px_all, off_all[int(rows[0]):int(rows[-1]) + 2]
+            else:                                                # a frame's final planes are contiguous
+                px, offsets = ops.pixels(fin[int(rows[0]):int(rows[-1]) + 1], H, W, fin_area[rows], origins[f][0], origins[f][1])
+            for k, row in enumerate(rows):
+                results[f].pixels.append(px[offsets[k]:offsets[k + 1]])
+                if want_masks:
+                    full = unpacked[row]
+                    results[f].masks_final.append(full.astype(np.int64) if merged_int[final_planes[row]] else full.view(np.bool_))
+                else:
+                    results[f].masks_final.append(None)
+    return results

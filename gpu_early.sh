@@ -1,6 +1,5 @@
 #!/bin/bash
-# scratch driver for one gpurun call: GPU tests, smoke, short bench
+# scratch driver for one gpurun call: analyzer GPU tests + analyzer bench
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu -x > gpurun_out/tests.log 2>&1; echo "tests exit $?" >> gpurun_out/tests.log; tail -3 gpurun_out/tests.log
-timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -1 gpurun_out/bench.log | cut -c1-300
+timeout 900 python -m pytest tests/test_gpu_analyzer.py -q -m gpu -x > gpurun_out/tests_an.log 2>&1; echo "tests exit $?" >> gpurun_out/tests_an.log; tail -25 gpurun_out/tests_an.log
+timeout 600 python tools/analyze_bench.py > gpurun_out/analyze_bench.log 2> gpurun_out/analyze_bench.err; echo "abench exit $?"; tail -1 gpurun_out/analyze_bench.log | cut -c1-1200; tail -5 gpurun_out/analyze_bench.err

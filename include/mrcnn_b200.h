@@ -218,7 +218,8 @@ int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, int molded_
  * 1090-1208) -> resize to (out_h,out_w), pad at (top,left), minus mean (mold_inputs, mrcnn/model.py:
  * 2519-2556) -> graph -> unmold against the original (map_h,map_w) frame.  metas / windows: HOST.
  * Host result pointers may be NULL (all of them = results stay on the device, readable through
- * mrcnn_engine_tensor "unmold_rois"/"unmold_class_ids"/"unmold_scores"/"unmold_counts").  Blocking unless async. */
+ * mrcnn_engine_tensor "unmold_rois"/"unmold_class_ids"/"unmold_scores"/"unmold_counts"/"unmold_masks"; the result
+ * slot of a call is mrcnn_engine_next_slot() read before it, slot 1 names carry the suffix "#1").  Blocking unless async. */
 int mrcnn_engine_detect_maps(mrcnn_engine* e, const float* maps, int maps_on_host, int map_h, int map_w,
                              const float* contrasts3, const float* mean_pixel3, int out_h, int out_w,
                              int top, int left, const float* metas_host, const int32_t* windows_host,
@@ -249,6 +250,46 @@ int mrcnn_engine_kernel_times(mrcnn_engine* e, int max_kinds, const char** names
 int mrcnn_engine_step_info(mrcnn_engine* e, int index, const char** label, const char** kind, float* ms, double* flops);
 /* FLOPs (2*M*N*K over all GEMM launches) of one predict at the configured batch */
 double mrcnn_engine_flops(const mrcnn_engine* e);
+
+/* ---- (f1) Analyzer source-mask post-processing on device-resident masks
+ *      (mrcnn/analyze.py: Analyzer.extract_det_masks :1162-1423, make_json_results :1866-1942,
+ *       merge_masks :2142-2146, extract_mask_connected_components :2148-2151, are_mask_connected
+ *       :2154-2173; utils.extract_bboxes mrcnn/utils.py:33-59).
+ * Masks are handled as bit-planes: plane[m] is [height][ceil(width/32)] uint32, bit k of word w is
+ * pixel x = 32*w + k, bits past `width` are zero.  mrcnn_plane_words() = words per plane.  All
+ * pointers are DEVICE pointers unless stated; calls are asynchronous on `stream`.  The graph logic
+ * between the calls (score filter, merge graph, cliques) is host logic in mrcnn/analyze.py. */
+size_t mrcnn_plane_words(int height, int width);
+/* masks [n_images,H,W,depth] uint8 (0 / non-zero; the [H,W,N] result layout of detect with N padded
+ * to depth); plane_of [n_images*depth] int32: destination plane of detection (b,d) or -1 = skip. */
+int mrcnn_masks_pack(const uint8_t* masks, int n_images, int height, int width, int depth,
+                     const int32_t* plane_of, uint32_t* planes, void* stream);
+/* area [n] = pixel count; bbox [n,4] = (y1,x1,y2,x2) of utils.extract_bboxes (y2/x2 exclusive; zeros
+ * for an empty mask). */
+int mrcnn_planes_area_bbox(const uint32_t* planes, int n_planes, int height, int width, int32_t* area,
+                           int32_t* bbox, void* stream);
+/* pairs [n_pairs,2] plane indices -> inter[p] = |a & b| (numerator of sklearn jaccard_score, the
+ * denominator is area[a]+area[b]-inter), touch[p] = 1 iff are_mask_connected(a,b) would be True
+ * (a pixel of a coincides with or is 4-adjacent to a pixel of b). */
+int mrcnn_planes_pair_stats(const uint32_t* planes, int height, int width, const int32_t* pairs, int n_pairs,
+                            int32_t* inter, int32_t* touch, void* stream);
+/* out[g] = OR of planes[members[offsets[g] .. offsets[g+1])]  (merge_masks folded over a group) */
+int mrcnn_planes_union(const uint32_t* planes, int height, int width, const int32_t* members,
+                       const int32_t* offsets, int n_groups, uint32_t* out, void* stream);
+/* skimage.measure.label(mask, background=0, connectivity=1): labels [n,H,W] int32 (0 = background,
+ * 1.. numbered in raster order of each component's first pixel), counts [n] = ncomponents. */
+size_t mrcnn_planes_label_workspace_bytes(int n_planes, int height, int width);
+int mrcnn_planes_label(const uint32_t* planes, int n_planes, int height, int width, int32_t* labels,
+                       int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+/* planes_out[k] = (labels[src[k]] == comp[k])  (np.where(component_labels == i+1, [1], [0])) */
+int mrcnn_labels_select(const int32_t* labels, int height, int width, const int32_t* src, const int32_t* comp,
+                        int n_out, uint32_t* planes_out, void* stream);
+/* np.argwhere(mask == 1) of every plane, row-major: pixels [total,2] int32 = (y + y_origin,
+ * x + x_origin); plane m writes rows offsets[m] .. offsets[m]+area[m] (offsets: int64 [n]). */
+int mrcnn_planes_pixels(const uint32_t* planes, int n_planes, int height, int width, const int64_t* offsets,
+                        int y_origin, int x_origin, int32_t* pixels, void* stream);
+/* out [n,H,W] uint8 0/1 */
+int mrcnn_planes_unpack(const uint32_t* planes, int n_planes, int height, int width, uint8_t* out, void* stream);
 
 #ifdef __cplusplus
 }

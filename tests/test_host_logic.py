@@ -173,3 +173,45 @@ def test_result_buffer_sets_return_to_the_pool_when_the_last_view_dies():
     del keep
     gc.collect()
     assert pool[pset.key] == [pset]
+
+
+def test_analyzer_host_logic_matches_oracle_graph_and_iou():
+    """Host pieces of mrcnn/analyze.py that need no GPU: DFS component order, pair enumeration, IOU arithmetic."""
+    from mrcnn import analyze as P
+    from oracle import analyze_ops as A
+    rng = np.random.default_rng(11)
+    for _ in range(50):
+        n = int(rng.integers(1, 14))
+        edges = [(int(a), int(b)) for a, b in rng.integers(0, n, size=(int(rng.integers(0, 2 * n)), 2)) if a != b]
+        gp, go = P.Graph(n), A.Graph(n)
+        for v, w in edges:
+            gp.addEdge(v, w)
+            go.add_edge(v, w)
+        assert gp.connectedComponents() == go.connected_components()
+    pairs, slices = P._all_pairs([3, 0, 1, 4])
+    assert pairs.tolist() == [[0, 1], [0, 2], [1, 2], [4, 5], [4, 6], [4, 7], [5, 6], [5, 7], [6, 7]]
+    assert slices == [(0, 3, 0), (3, 3, 3), (3, 3, 3), (3, 9, 4)]
+    a = rng.random((40, 33)) < 0.3
+    b = rng.random((40, 33)) < 0.3
+    z = np.zeros_like(a)
+    inter = np.array([np.count_nonzero(a & b), 0, 0], dtype=np.int32)
+    got = P._iou(inter, np.array([a.sum(), a.sum(), 0], np.int32), np.array([b.sum(), 0, 0], np.int32))
+    assert got.dtype == np.float64
+    assert got.tolist() == [float(A.jaccard_binary(a, b)), float(A.jaccard_binary(a, z)), float(A.jaccard_binary(z, z))]
+
+
+def test_analyzer_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mrcnn.analyze import Analyzer
+
+    class Cfg:
+        NUM_CLASSES = 4
+
+    an = Analyzer(None, Cfg())
+    an.class_names = ["bkg", "a", "b", "c"]
+    an.masks = np.ones((8, 8, 1), dtype=bool)
+    an.boxes, an.class_ids, an.scores = np.zeros((1, 4), np.int32), np.array([1], np.int32), np.array([0.9], np.float32)
+    with pytest.raises(Exception):
+        an.extract_det_masks()

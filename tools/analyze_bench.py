@@ -1,0 +1,130 @@
+#!/usr/bin/env python
+"""Timing of the Analyzer post-processing row on synthetic detections.
+
+Workload: F frames of S x S pixels with D detections each (unions of rectangles / discs, random classes and scores),
+resident in HBM in the detector's [F,S,S,D] uint8 layout — what `detect_maps(device_only=True)` leaves behind.
+Timed: `analyze_frames` (score filter -> bit-plane pack -> pair statistics -> merge -> cliques -> boxes -> pixel
+lists -> host results), CUDA events on the stream the kernels run on for the two streaming kernels that dominate
+(`masks_pack`, `planes_pair_stats`), wall clock for the whole call (it ends with host results, so it is e2e by
+construction). CPU baseline: the oracle (oracle/analyze_ops.py, a port of the reference's algorithm with the
+reference's own third-party calls) on a bounded sample of the same frames.
+
+Prints one JSON line. Not the round's headline bench (bench.py stays on BASELINE.json's metric)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "caesar-mrcnn_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CLASS_NAMES = ["bkg", "spurious", "compact", "extended", "extended-multisland", "flagged"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--dets", type=int, default=100)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--oracle-frames", type=int, default=1)
+    ap.add_argument("--split", action="store_true")
+    args = ap.parse_args()
+
+    import torch
+    import analyzer_cases as C
+    from mrcnn import analyze as P
+
+    F, S, D = args.frames, args.size, args.dets
+    rng = np.random.default_rng(0)
+    masks = np.zeros((F, S, S, D), dtype=np.uint8)
+    class_ids = np.zeros((F, D), dtype=np.int32)
+    scores = np.zeros((F, D), dtype=np.float32)
+    for f in range(F):
+        m, c, s = C.random_detections(rng, S, S, D, density=0.35)
+        masks[f], class_ids[f], scores[f] = m.view(np.uint8), c, s
+    ops = P.MaskPlaneOps(0)
+    d_masks = ops.to_dev(masks, np.uint8)
+    frames = [P._Frame(d_masks.data_ptr() + f * S * S * D, D, D, class_ids[f], scores[f]) for f in range(F)]
+    opts = dict(score_thr=0.7, split_masks=args.split)
+
+    def run():
+        return P.analyze_frames(ops, frames, S, S, CLASS_NAMES, want_masks=False, **opts)
+
+    res = run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.reps):
+        res = run()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / args.reps
+    n_final = sum(len(r.class_ids_final) for r in res)
+    n_pixels = sum(int(p.shape[0]) for r in res for p in r.pixels)
+
+    # the two streaming kernels, CUDA events on the current stream (the one MaskPlaneOps launches on)
+    plane_of = np.full(F * D, -1, dtype=np.int32)
+    sel = np.nonzero((scores >= 0.7).ravel())[0]
+    plane_of[sel] = np.arange(len(sel))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    planes = ops.pack(d_masks.data_ptr(), F, S, S, D, plane_of, len(sel))
+    counts = (scores >= 0.7).sum(axis=1).tolist()
+    pairs, _ = P._all_pairs(counts)
+    d_pairs = ops.to_dev(pairs, np.int32)
+    inter = ops.empty((len(pairs),), torch.int32)
+    touch = ops.empty((len(pairs),), torch.int32)
+    d_map = ops.to_dev(plane_of, np.int32)
+    lib, nat = ops.lib, P._native
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(args.reps):
+        nat.check(lib.mrcnn_masks_pack(d_masks.data_ptr(), F, S, S, D, nat.ptr(d_map), nat.ptr(planes), ops._st()), "pack")
+    ev[1].record()
+    for _ in range(args.reps):
+        nat.check(lib.mrcnn_planes_pair_stats(nat.ptr(planes), S, S, nat.ptr(d_pairs), len(pairs), nat.ptr(inter), nat.ptr(touch),
+                                              ops._st()), "pairs")
+    ev[2].record()
+    torch.cuda.synchronize()
+    pack_ms = ev[0].elapsed_time(ev[1]) / args.reps
+    pair_ms = ev[1].elapsed_time(ev[2]) / args.reps
+    words = ops.words(S, S)
+    pack_bytes = masks.nbytes + len(sel) * words * 4
+    pair_bytes = len(pairs) * 2 * words * 4           # both planes of every pair once (the neighbour rows hit L1/L2)
+    peak = 6538.3
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+
+    # CPU baseline: the oracle on a bounded sample of the same frames
+    from oracle import analyze_ops as A
+    t0 = time.perf_counter()
+    for f in range(args.oracle_frames):
+        det = A.extract_det_masks(masks[f].astype(bool), D, class_ids[f], scores[f], CLASS_NAMES, **opts)
+        ref = A.make_json_results(det, CLASS_NAMES, (S, S, 3))
+        got = res[f]
+        assert len(ref["objs"]) == len(got.class_ids_final)
+        for k, obj in enumerate(ref["objs"]):
+            assert obj["pixels"] == got.pixels[k].tolist()
+    cpu_s = (time.perf_counter() - t0) / max(args.oracle_frames, 1)
+
+    print(json.dumps({
+        "metric": "analyzed_images_per_sec", "value": F / wall, "unit": "images/s", "ms_per_batch": wall * 1e3,
+        "config": {"workload": "analyze_frames F=%d S=%d D=%d score_thr=0.7 split=%s" % (F, S, D, args.split),
+                   "selected_masks": int(len(sel)), "pairs": int(len(pairs)), "final_objects": n_final, "pixels": n_pixels},
+        "kernels": {
+            "masks_pack": {"ms": pack_ms, "bytes": pack_bytes, "GBps": pack_bytes / pack_ms / 1e6, "frac": pack_bytes / pack_ms / 1e6 / peak},
+            "planes_pair_stats": {"ms": pair_ms, "bytes": pair_bytes, "GBps": pair_bytes / max(pair_ms, 1e-9) / 1e6,
+                                  "frac": pair_bytes / max(pair_ms, 1e-9) / 1e6 / peak},
+        },
+        "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "images/s", "cores": 1, "kind": "port",
+                         "sample": "%d frame(s) of the same batch through oracle/analyze_ops.py, results compared" % args.oracle_frames},
+    }))
+
+
+if __name__ == "__main__":
+    main()
