@@ -60,17 +60,19 @@ __global__ void masks_pack_kernel(const uint8_t* __restrict__ masks, int H, int 
   }
 }
 
-// Fast variant for depth % 4 == 0 and 16-byte aligned rows: 64 pixels (two output words) per CTA, 16-byte loads,
-// and four detections per shared-memory word in the ballot phase (row stride depth/4 words: conflict-free when
-// odd, as for depth 100).  grid (ceil(W/64), H, B), 256 threads.
+// Fast variant for depth % 4 == 0 and 16-byte aligned rows: 256 pixels (eight output words) of one image row per
+// CTA, 16-byte loads (6 in flight per thread at depth 100), four detections per shared-memory word in the ballot
+// phase (row stride depth/4 words: conflict-free when odd, as for depth 100); lanes 0-3 of a warp each collect the
+// eight words of one detection and write them as one 32-byte run.  grid (ceil(W/256), H, B), 256 threads.
+constexpr int kPackPx = 256;
 __global__ void __launch_bounds__(256) masks_pack4_kernel(const uint8_t* __restrict__ masks, int H, int W, int D,
                                                           const int32_t* __restrict__ plane_of, uint32_t* __restrict__ planes) {
   pdl_prologue();
-  extern __shared__ __align__(16) uint8_t s_tile[];  // [64][D]
+  extern __shared__ __align__(16) uint8_t s_tile[];  // [kPackPx][D]
   const int y = blockIdx.y, b = blockIdx.z;
   const int WW = words_per_row(W);
-  const int x0 = blockIdx.x * 64;
-  const int npix = min(64, W - x0);
+  const int x0 = blockIdx.x * kPackPx;
+  const int npix = min(kPackPx, W - x0);
   const size_t base = (((size_t)b * H + y) * W + x0) * D;
   const int nbytes = npix * D;
   {
@@ -86,22 +88,33 @@ __global__ void __launch_bounds__(256) masks_pack4_kernel(const uint8_t* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int DQ = D >> 2;
   const uint32_t* s32 = reinterpret_cast<const uint32_t*>(s_tile);
-  const size_t plane_words = (size_t)H * WW;
+  const int nwords = (npix + 31) >> 5;
   for (int dq = warp; dq < DQ; dq += 8) {
     const int mk = lane < 4 ? plane_of[b * D + dq * 4 + lane] : -1;     // destination planes of these four detections
     if (__all_sync(0xffffffffu, mk < 0)) continue;
+    uint32_t mine[kPackPx / 32];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const int px = g * 32 + lane;
-      if (g * 32 >= npix) break;
-      const uint32_t v = px < npix ? s32[px * DQ + dq] : 0u;
-      const uint32_t b0 = __ballot_sync(0xffffffffu, (v & 0x000000ffu) != 0);
-      const uint32_t b1 = __ballot_sync(0xffffffffu, (v & 0x0000ff00u) != 0);
-      const uint32_t b2 = __ballot_sync(0xffffffffu, (v & 0x00ff0000u) != 0);
-      const uint32_t b3 = __ballot_sync(0xffffffffu, (v & 0xff000000u) != 0);
-      if (mk >= 0) {
-        const uint32_t word = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : b3;
-        planes[(size_t)mk * plane_words + (size_t)y * WW + blockIdx.x * 2 + g] = word;
+    for (int g = 0; g < kPackPx / 32; ++g) {
+      mine[g] = 0;
+      if (g < nwords) {
+        const int px = g * 32 + lane;
+        const uint32_t v = px < npix ? s32[px * DQ + dq] : 0u;
+        const uint32_t b0 = __ballot_sync(0xffffffffu, (v & 0x000000ffu) != 0);
+        const uint32_t b1 = __ballot_sync(0xffffffffu, (v & 0x0000ff00u) != 0);
+        const uint32_t b2 = __ballot_sync(0xffffffffu, (v & 0x00ff0000u) != 0);
+        const uint32_t b3 = __ballot_sync(0xffffffffu, (v & 0xff000000u) != 0);
+        mine[g] = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : b3;
+      }
+    }
+    if (mk >= 0) {
+      uint32_t* dst = planes + ((size_t)mk * H + y) * WW + blockIdx.x * (kPackPx / 32);
+      if (nwords == kPackPx / 32 && (WW & 3) == 0) {
+        reinterpret_cast<uint4*>(dst)[0] = make_uint4(mine[0], mine[1], mine[2], mine[3]);
+        reinterpret_cast<uint4*>(dst)[1] = make_uint4(mine[4], mine[5], mine[6], mine[7]);
+      } else {
+#pragma unroll
+        for (int g = 0; g < kPackPx / 32; ++g)
+          if (g < nwords) dst[g] = mine[g];
       }
     }
   }
@@ -415,11 +428,11 @@ extern "C" int mrcnn_masks_pack(const uint8_t* masks, int n_images, int height, 
   MRCNN_REQUIRE(n_images > 0 && n_images <= 65535 && height <= 65535 && depth > 0 && depth * 32 <= 200 * 1024,
                 "masks_pack: bad sizes (n_images %d, depth %d)", n_images, depth);
   const bool fast = (depth & 3) == 0 && ((size_t)width * depth) % 16 == 0 && (reinterpret_cast<uintptr_t>(masks) & 15) == 0 &&
-                    (size_t)64 * depth <= 48 * 1024;
+                    (reinterpret_cast<uintptr_t>(planes) & 15) == 0 && (size_t)kPackPx * depth <= 48 * 1024;
   if (fast) {
-    dim3 grid((width + 63) / 64, height, n_images);
-    MRCNN_CHECK_CUDA(mrcnn_launch(masks_pack4_kernel, grid, dim3(256), (size_t)64 * depth, (cudaStream_t)stream, masks, height,
-                                  width, depth, plane_of, planes));
+    dim3 grid((width + kPackPx - 1) / kPackPx, height, n_images);
+    MRCNN_CHECK_CUDA(mrcnn_launch(masks_pack4_kernel, grid, dim3(256), (size_t)kPackPx * depth, (cudaStream_t)stream, masks,
+                                  height, width, depth, plane_of, planes));
   } else {
     const size_t smem = (size_t)32 * depth;
     if (smem > 48 * 1024)

@@ -20,6 +20,7 @@ is importable and left as an empty list otherwise.
 There is no CPU fallback: every mask operation goes through libmrcnn_b200.so and needs a CUDA device.
 """
 import ctypes
+import itertools
 import json
 import logging
 
@@ -141,9 +142,10 @@ class MaskPlaneOps:
         G = len(groups)
         out = self.empty((max(G, 1), self.words(H, W)), self.torch.int32)
         if G:
-            members = np.concatenate([np.asarray(g, dtype=np.int32) for g in groups])
+            lens = np.fromiter(map(len, groups), dtype=np.int64, count=G)
+            members = np.fromiter(itertools.chain.from_iterable(groups), dtype=np.int32, count=int(lens.sum()))
             offsets = np.zeros(G + 1, dtype=np.int32)
-            offsets[1:] = np.cumsum([len(g) for g in groups])
+            offsets[1:] = np.cumsum(lens)
             d_m, d_o = self.to_dev(members, np.int32), self.to_dev(offsets, np.int32)
             _native.check(self.lib.mrcnn_planes_union(_native.ptr(planes), H, W, _native.ptr(d_m), _native.ptr(d_o), G,
                                                       _native.ptr(out), self._st()), "planes_union")
@@ -443,18 +445,23 @@ def build_json_results(image_id, obj_name_tag, class_names, ny, nx, xmin, ymin, 
     return results
 
 
+_TRIU = {}
+
+
 def _all_pairs(counts):
     """(i<j) pairs inside each frame, in the reference's loop order -> (pairs [P,2] global indices, per-frame slices)."""
     chunks, slices, base, pos = [], [], 0, 0
     for n in counts:
         if n > 1:
-            i, j = np.triu_indices(n, k=1)
-            chunks.append(np.stack([i + base, j + base], axis=1))
+            if n not in _TRIU:
+                i, j = np.triu_indices(n, k=1)
+                _TRIU[n] = np.stack([i, j], axis=1).astype(np.int32)
+            chunks.append(_TRIU[n] + np.int32(base))
         npairs = n * (n - 1) // 2
         slices.append((pos, pos + npairs, base))
         pos += npairs
         base += n
-    pairs = np.concatenate(chunks).astype(np.int32) if chunks else np.zeros((0, 2), dtype=np.int32)
+    pairs = np.concatenate(chunks) if chunks else np.zeros((0, 2), dtype=np.int32)
     return pairs, slices
 
 
@@ -468,11 +475,20 @@ def _iou(inter, area_a, area_b):
 
 def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True, score_thr=0.7, split_masks=False,
                    merge_overlapped_masks=True, select_best_overlapped_masks=True, split_source_sidelobe=True,
-                   merge_overlap_iou_thr=0.3):
+                   merge_overlap_iou_thr=0.3, timings=None):
     """extract_det_masks (+ the pixel lists of make_json_results) for a list of frames that share one [H,W] size.
     All masks of one frame list must live in ONE device allocation laid out [n_frames,H,W,depth] when
     len(frames) > 1 (the engine's result slot), or be a single frame."""
     import networkx as nx
+    import time
+
+    def mark(stage):          # development aid: cumulative wall time per stage (device drained at every mark)
+        if timings is not None:
+            ops.torch.cuda.synchronize()
+            now = time.perf_counter()
+            timings[stage] = timings.get(stage, 0.0) + now - mark.t
+            mark.t = now
+    mark.t = time.perf_counter()
 
     F = len(frames)
     depth = frames[0].depth
@@ -495,7 +511,9 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
             sel_score.append(scores_sel[index])
             m += 1
         sel_count.append(len(picked))
+    mark("host: score filter + order")
     planes = ops.pack(base_ptr, F, H, W, depth, plane_of, m)
+    mark("gpu: pack")
 
     # -- optional split into 4-connected components (analyze.py:1211-1255)
     det_cls, det_score, det_int, det_count = sel_cls, sel_score, [False] * m, sel_count
@@ -538,18 +556,25 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
     merged_cls, merged_score, merged_int, merged_count = det_cls, det_score, det_int, det_count
     if merge_overlapped_masks and len(det_cls):
         pairs, slices = _all_pairs(det_count)
+        mark("host: pair lists")
         d_area, _ = ops.area_bbox(planes, H, W)
         d_inter, d_touch = ops.pair_stats(planes, H, W, pairs)
         area, inter, touch = ops.host(d_area), ops.host(d_inter), ops.host(d_touch)
+        mark("gpu: merge pair stats (+pairs H2D, results D2H)")
         cls_arr = np.asarray(det_cls)
         iou = _iou(inter, area[pairs[:, 0]], area[pairs[:, 1]])
         mergeable = (touch != 0) & (cls_arr[pairs[:, 0]] == cls_arr[pairs[:, 1]]) & (iou >= merge_overlap_iou_thr)
         groups, merged_cls, merged_score, merged_int, merged_count = [], [], [], [], []
+        any_int = any(det_int)
         for f, (lo, hi, base) in enumerate(slices):
-            g = Graph(det_count[f])
-            for k in np.nonzero(mergeable[lo:hi])[0]:
-                g.addEdge(int(pairs[lo + k, 0]) - base, int(pairs[lo + k, 1]) - base)
-            cc = g.connectedComponents()
+            edges = np.nonzero(mergeable[lo:hi])[0]
+            if len(edges):
+                g = Graph(det_count[f])
+                for a, b in (pairs[lo + edges] - base).tolist():
+                    g.addEdge(a, b)
+                cc = g.connectedComponents()
+            else:
+                cc = [[v] for v in range(det_count[f])]        # what the DFS returns for a graph without edges
             for members in cc:
                 score_avg = 0
                 for index in members:
@@ -559,9 +584,11 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
                 groups.append([base + index for index in members])
                 merged_cls.append(class_id)
                 merged_score.append(score_avg)
-                merged_int.append(any(det_int[base + index] for index in members))
+                merged_int.append(any_int and any(det_int[base + index] for index in members))
             merged_count.append(len(cc))
+        mark("host: merge graph")
         planes = ops.union(planes, H, W, groups)
+        mark("gpu: union")
 
     results = [_FrameResult() for _ in range(F)]
     if not select_best_overlapped_masks or not len(merged_cls):     # analyze.py:1324: nothing is published otherwise
@@ -569,51 +596,57 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
 
     # -- best of overlapping objects through maximal cliques (analyze.py:1328-1395)
     pairs, slices = _all_pairs(merged_count)
+    mark("host: pair lists")
     d_area, d_bbox = ops.area_bbox(planes, H, W)
     d_inter, d_touch = ops.pair_stats(planes, H, W, pairs)
     area, bbox, inter, touch = ops.host(d_area), ops.host(d_bbox), ops.host(d_inter), ops.host(d_touch)
+    mark("gpu: select pair stats + bbox (+H2D/D2H)")
     spurious = np.array([class_names[c] == 'spurious' for c in merged_cls], dtype=bool)
     linked = touch != 0
     if split_source_sidelobe:
         iou = _iou(inter, area[pairs[:, 0]], area[pairs[:, 1]])
         linked &= ~((spurious[pairs[:, 0]] != spurious[pairs[:, 1]]) & (iou < merge_overlap_iou_thr))
     final_planes, final_owner = [], []
+    bbox_ok = ((bbox[:, 1] < bbox[:, 3]) & (bbox[:, 0] < bbox[:, 2])).tolist()
     for f, (lo, hi, base) in enumerate(slices):
-        g_final = nx.Graph()
-        for k in np.nonzero(linked[lo:hi])[0]:
-            g_final.add_edge(int(pairs[lo + k, 0]) - base, int(pairs[lo + k, 1]) - base)
-        cliques = list(nx.find_cliques(g_final))
-        clique_max_scores, clique_max_score_index = [], []
-        for item in cliques:
-            max_score, max_score_index = -1, -1
-            for index in item:
-                score = merged_score[base + index]
-                if score > max_score:
-                    max_score, max_score_index = score, index
-            clique_max_scores.append(max_score)
-            clique_max_score_index.append(max_score_index)
         is_selected = [True] * merged_count[f]
-        for q in sorted(range(len(cliques)), key=lambda k: clique_max_scores[k], reverse=True):
-            for index in cliques[q]:
-                if index != clique_max_score_index[q] and is_selected[index]:
-                    is_selected[index] = False
+        edges = np.nonzero(linked[lo:hi])[0]
+        if len(edges):
+            g_final = nx.Graph()
+            g_final.add_edges_from((pairs[lo + edges] - base).tolist())     # same insertion order as the pair loop
+            cliques = list(nx.find_cliques(g_final))
+            clique_max_scores, clique_max_score_index = [], []
+            for item in cliques:
+                max_score, max_score_index = -1, -1
+                for index in item:
+                    score = merged_score[base + index]
+                    if score > max_score:
+                        max_score, max_score_index = score, index
+                clique_max_scores.append(max_score)
+                clique_max_score_index.append(max_score_index)
+            for q in sorted(range(len(cliques)), key=lambda k: clique_max_scores[k], reverse=True):
+                for index in cliques[q]:
+                    if index != clique_max_score_index[q] and is_selected[index]:
+                        is_selected[index] = False
         res = results[f]
         for index in range(merged_count[f]):
             if not is_selected[index]:
                 continue
-            bb = bbox[base + index]
-            if bb[1] >= bb[3] or bb[0] >= bb[2]:
+            k = base + index
+            if not bbox_ok[k]:
+                bb = bbox[k]
                 logger.warning("Invalid det bbox(%d,%d,%d,%d), skip it ..." % (bb[1], bb[3], bb[0], bb[2]))
                 continue
-            label = class_names[merged_cls[base + index]]
-            res.class_ids_final.append(merged_cls[base + index])
+            label = class_names[merged_cls[k]]
+            res.class_ids_final.append(merged_cls[k])
             res.class_names_final.append(label)
-            res.scores_final.append(merged_score[base + index])
-            res.bboxes.append(bb.copy())
-            res.captions.append("{} {:.2f}".format(label, merged_score[base + index]))
-            final_planes.append(base + index)
+            res.scores_final.append(merged_score[k])
+            res.bboxes.append(bbox[k])
+            res.captions.append("{} {:.2f}".format(label, merged_score[k]))
+            final_planes.append(k)
             final_owner.append(f)
 
+    mark("host: cliques + selection")
     # -- final masks and pixel lists (make_json_results: np.argwhere(mask == 1), analyze.py:1903-1909)
     if final_planes:
         fin = ops.gather(planes, final_planes)
@@ -638,4 +671,5 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
                     results[f].masks_final.append(full.astype(np.int64) if merged_int[final_planes[row]] else full.view(np.bool_))
                 else:
                     results[f].masks_final.append(None)
+    mark("gpu+host: pixel lists / final masks")
     return results

@@ -5,10 +5,13 @@ reference's scripts/run.py (parse_args :1263-1384, InferenceConfig :1652-1706, d
   run.py detect --image data/galaxy0002.fits --weights share/mrcnn_weights.h5 [--imgsize 256 ...]
   run.py test   --datalist images.txt        --weights share/mrcnn_weights.h5
 
-`detect` reads the FITS image (zscale + uint8 RGB on the GPU), runs MaskRCNN.detect and writes the raw
-detections with score >= --scoreThr as JSON.  `test` does the same for every FITS file of a list
-(batched by --nimg_per_gpu).  The reference's post-processing (`Analyzer`: mask merging, metrics,
-PNG / DS9 output) and `train` are outside the hot path rebuilt here and are rejected.
+`detect` reads the FITS image (zscale + uint8 RGB on the GPU) and hands it to `Analyzer.predict` exactly as the
+reference's SFinder.run does (mrcnn/sfinder.py:485-493): MaskRCNN.detect, then extract_det_masks (score filter,
+merging of connected same-class masks, best-of-overlapping selection) on the GPU, then the reference's JSON catalogue
+(`out_<image>.json` or --detect_outfile_json; keys name,x1,x2,y1,y2,class_id,class_name,score,pixels,vertexes,edge).
+`test` writes the raw detections with score >= --scoreThr of every FITS file of a list (batched by --nimg_per_gpu).
+PNG / DS9 output, the ground-truth metrics of `test`, tiling (--split_img_in_tiles) and `train` are outside the path
+rebuilt here and are rejected.
 Returns exit code 0 on success, 1 on failure, like the reference's main().
 """
 import argparse
@@ -24,6 +27,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 from mrcnn import logger  # noqa: E402
 from mrcnn import model as modellib, utils  # noqa: E402
+from mrcnn.analyze import Analyzer  # noqa: E402
 from mrcnn.config import Config  # noqa: E402
 
 
@@ -173,13 +177,34 @@ def detect(args, model, config):
     if res is None:
         logger.error("Failed to read image %s!" % args.image)
         return -1
-    image, _header = res
-    out = result_to_json(os.path.basename(args.image), model.detect([image] * config.BATCH_SIZE)[0], config)
-    path = args.detect_outfile_json or ("out_" + os.path.splitext(os.path.basename(args.image))[0] + ".json")
-    with open(path, "w") as f:
-        json.dump(out, f, indent=1)
-    logger.info("#%d objects above score %.2f (%d raw detections) written to %s" % (len(out["objs"]), config.SCORE_THR, out["ndet_raw"], path))
+    image, header = res
+    image_id = os.path.splitext(os.path.basename(args.image))[0]
+    analyzer = Analyzer(_FirstOfBatch(model, config.BATCH_SIZE), config)
+    analyzer.draw = False
+    analyzer.write_to_ds9 = False
+    analyzer.write_to_json = True
+    analyzer.outfile_json = args.detect_outfile_json
+    analyzer.iou_thr = config.IOU_THR
+    analyzer.score_thr = config.SCORE_THR
+    if analyzer.predict(image, image_id, header=header) < 0:
+        logger.error("Failed to run model prediction on image %s!" % args.image)
+        return -1
+    if not analyzer.bboxes:
+        logger.info("No object detected in image %s ..." % args.image)
+        return 0
+    logger.info("#%d objects found in image %s ..." % (len(analyzer.bboxes), args.image))
     return 0
+
+
+class _FirstOfBatch:
+    """detect([image]) for a model built with BATCH_SIZE > 1: the image fills the batch, the first result is returned."""
+
+    def __init__(self, model, batch):
+        self._model, self._batch = model, batch
+        self._device, self._stream = model._device, model._stream
+
+    def detect(self, images, verbose=0):
+        return self._model.detect(list(images) * self._batch, verbose=verbose)[:1]
 
 
 def test(args, model, config):

@@ -74,3 +74,76 @@ def random_detections(rng, H, W, n, n_classes=6, density=1.0):
     class_ids = rng.integers(1, n_classes, size=n).astype(np.int32)
     scores = rng.uniform(0.5, 1.0, size=n).astype(np.float32)
     return masks, class_ids, scores
+
+
+class _Arr:
+    """Minimal stand-in for a device tensor (shape + slicing) used by NumpyPlaneOps."""
+
+    def __init__(self, a):
+        self.a = a
+
+    @property
+    def shape(self):
+        return self.a.shape
+
+    def __getitem__(self, k):
+        return _Arr(self.a[k])
+
+
+class NumpyPlaneOps:
+    """TEST DOUBLE of mrcnn.analyze.MaskPlaneOps: the same method contract computed with numpy on full-frame bool
+    arrays, so the host logic of mrcnn/analyze.py (ordering, graphs, cliques, selection, result assembly) can be
+    exercised by the CPU suite. Never used by the product."""
+
+    class torch:                       # only what analyze_frames touches for its timing marks
+        class cuda:
+            @staticmethod
+            def synchronize():
+                pass
+
+    def __init__(self, masks):
+        self.masks = masks             # [F,H,W,D] bool, addressed through plane_of exactly like the device block
+
+    def pack(self, ptr, F, H, W, D, plane_of, n):
+        out = np.zeros((n, H, W), bool)
+        for flat in np.nonzero(plane_of >= 0)[0]:
+            out[plane_of[flat]] = self.masks[flat // D, :, :, flat % D]
+        return _Arr(out)
+
+    def area_bbox(self, pl, H, W):
+        area = pl.a.reshape(len(pl.a), -1).sum(1).astype(np.int32)
+        bbox = np.zeros((len(pl.a), 4), np.int32)
+        for i, m in enumerate(pl.a):
+            ys, xs = np.nonzero(m.any(1))[0], np.nonzero(m.any(0))[0]
+            if len(ys):
+                bbox[i] = [ys[0], xs[0], ys[-1] + 1, xs[-1] + 1]
+        return _Arr(area), _Arr(bbox)
+
+    def pair_stats(self, pl, H, W, pairs):
+        a = pl.a
+        grown = a.copy()
+        grown[:, 1:] |= a[:, :-1]
+        grown[:, :-1] |= a[:, 1:]
+        grown[:, :, 1:] |= a[:, :, :-1]
+        grown[:, :, :-1] |= a[:, :, 1:]
+        inter = np.array([np.count_nonzero(a[i] & a[j]) for i, j in pairs], dtype=np.int32).reshape(-1)
+        touch = np.array([np.any(a[i] & grown[j]) for i, j in pairs], dtype=np.int32).reshape(-1)
+        return _Arr(inter), _Arr(touch)
+
+    def union(self, pl, H, W, groups):
+        return _Arr(np.stack([np.any(pl.a[g], axis=0) for g in groups]) if groups else np.zeros((0, H, W), bool))
+
+    def gather(self, pl, index):
+        return _Arr(pl.a[np.asarray(index, dtype=np.int64)])
+
+    def pixels(self, pl, H, W, areas, y0=0, x0=0):
+        offsets = np.zeros(len(areas) + 1, np.int64)
+        offsets[1:] = np.cumsum(areas)
+        px = np.concatenate([np.argwhere(m) for m in pl.a] + [np.zeros((0, 2), np.int64)]).astype(np.int32)
+        return px + np.array([y0, x0], dtype=np.int32), offsets
+
+    def unpack(self, pl, H, W):
+        return pl.a.astype(np.uint8)
+
+    def host(self, t):
+        return t.a

@@ -283,9 +283,21 @@ def test_load_weights_from_keras_h5_and_cli(tmp_path, weights, golden_dir):
                    "--detect_outfile_json", out])
     assert rc == 0
     d = json.load(open(out))
-    assert d["image"] == "galaxy0002.fits" and d["ndet_raw"] == len(d["objs"]) and d["ndet_raw"] > 0
-    o = d["objs"][0]
-    assert 0 <= o["y1"] < o["y2"] <= 132 and 0 <= o["x1"] < o["x2"] <= 132 and o["class_name"] in ("sidelobe", "source", "galaxy")
+    # the reference's catalogue layout (analyze.py:1866-1942), produced by Analyzer.predict on the GPU
+    assert d["image_id"] == "galaxy0002" and len(d["objs"]) > 0
+    from oracle import analyze_ops as A
+    image = run.utils.read_fits(os.path.join(golden_dir, "galaxy0002.fits"), zscale_contrasts=[0.25, 0.25, 0.25])[0]
+    r = m.detect([image])[0]
+    names = ["bkg", "sidelobe", "source", "galaxy"]
+    det = A.extract_det_masks(np.asarray(r["masks"]), r["rois"].shape[0], r["class_ids"], r["scores"], names, score_thr=0.0)
+    ref = A.make_json_results(det, names, image.shape, image_id="galaxy0002")
+    assert len(ref["objs"]) == len(d["objs"])
+    for o, want in zip(d["objs"], ref["objs"]):
+        assert set(o) == {"name", "x1", "x2", "y1", "y2", "class_id", "class_name", "score", "pixels", "vertexes", "edge"}
+        for k in ("name", "x1", "x2", "y1", "y2", "class_id", "class_name", "pixels", "edge"):
+            assert o[k] == want[k], k
+        assert o["score"] == float(want["score"])
+        assert 0 <= o["y1"] < o["y2"] <= 132 and 0 <= o["x1"] < o["x2"] <= 132
 
 
 def test_detect_maps_equals_read_fits_plus_detect(model, weights):

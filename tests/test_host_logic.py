@@ -215,3 +215,38 @@ def test_analyzer_fails_loudly_without_gpu():
     an.boxes, an.class_ids, an.scores = np.zeros((1, 4), np.int32), np.array([1], np.int32), np.array([0.9], np.float32)
     with pytest.raises(Exception):
         an.extract_det_masks()
+
+
+def test_analyzer_host_pipeline_matches_oracle_with_numpy_backend():
+    """analyze_frames (the product's host logic: ordering, merge graph, cliques, selection, result assembly) driven
+    by a numpy test double of the device primitives == the oracle, for several frames at once."""
+    import analyzer_cases as C
+    from mrcnn import analyze as P
+    from oracle import analyze_ops as A
+    names = ["bkg", "spurious", "compact", "extended", "extended-multisland", "flagged"]
+    rng = np.random.default_rng(1)
+    F, S, D = 4, 48, 24
+    masks = np.zeros((F, S, S, D), bool)
+    cls, sc = np.zeros((F, D), np.int32), np.zeros((F, D), np.float32)
+    for f in range(F):
+        masks[f], cls[f], sc[f] = C.random_detections(rng, S, S, D, density=0.6)
+    masks[2] = False                                     # a frame whose detections are all empty masks
+    sc[1, ::3] = sc[1, 0]                                # score ties
+    ops = C.NumpyPlaneOps(masks)
+    frames = [P._Frame(4096 + f * S * S * D, D, D, cls[f], sc[f]) for f in range(F)]
+    origins = [(0, 0), (5, 9), (0, 0), (100, 200)]
+    for opts in (dict(), dict(split_source_sidelobe=False, merge_overlap_iou_thr=0.05, score_thr=0.6),
+                 dict(merge_overlapped_masks=False), dict(select_best_overlapped_masks=False)):
+        res = P.analyze_frames(ops, frames, S, S, names, origins=origins, want_masks=True, **opts)
+        for f in range(F):
+            det = A.extract_det_masks(masks[f], D, cls[f], sc[f], names, **opts)
+            ref = A.make_json_results(det, names, (S, S, 3), xmin=origins[f][1], ymin=origins[f][0])
+            got = res[f]
+            assert len(ref["objs"]) == len(got.class_ids_final), (f, opts)
+            for k, o in enumerate(ref["objs"]):
+                assert o["pixels"] == got.pixels[k].tolist()
+                assert o["score"] == got.scores_final[k] and type(o["score"]) is type(got.scores_final[k])
+                assert o["class_id"] == int(got.class_ids_final[k])
+                assert list(det["bboxes"][k]) == list(got.bboxes[k])
+                assert det["captions"][k] == got.captions[k]
+                assert np.array_equal(np.asarray(det["masks_final"][k]) != 0, got.masks_final[k] != 0)

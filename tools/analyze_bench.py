@@ -63,6 +63,10 @@ def main():
         res = run()
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / args.reps
+    stages = {}
+    for _ in range(3):
+        P.analyze_frames(ops, frames, S, S, CLASS_NAMES, want_masks=False, timings=stages, **opts)
+    stages = {k: round(v / 3 * 1e3, 3) for k, v in stages.items()}
     n_final = sum(len(r.class_ids_final) for r in res)
     n_pixels = sum(int(p.shape[0]) for r in res for p in r.pixels)
 
@@ -116,6 +120,7 @@ def main():
         "metric": "analyzed_images_per_sec", "value": F / wall, "unit": "images/s", "ms_per_batch": wall * 1e3,
         "config": {"workload": "analyze_frames F=%d S=%d D=%d score_thr=0.7 split=%s" % (F, S, D, args.split),
                    "selected_masks": int(len(sel)), "pairs": int(len(pairs)), "final_objects": n_final, "pixels": n_pixels},
+        "stages_ms": stages,
         "kernels": {
             "masks_pack": {"ms": pack_ms, "bytes": pack_bytes, "GBps": pack_bytes / pack_ms / 1e6, "frac": pack_bytes / pack_ms / 1e6 / peak},
             "planes_pair_stats": {"ms": pair_ms, "bytes": pair_bytes, "GBps": pair_bytes / max(pair_ms, 1e-9) / 1e6,
