@@ -23,6 +23,7 @@ import ctypes
 import itertools
 import json
 import logging
+import time
 
 import numpy as np
 
@@ -360,35 +361,58 @@ class Analyzer(object):
     def predict_maps(self, maps, image_ids=None, origins=None, zscale_contrasts=(0.25, 0.25, 0.25)):
         """maps [BATCH_SIZE,H,W] float32 -> one results dict (make_json_results layout) per image. The detector's
         [B,H,W,100] masks never leave the GPU: only class ids, scores, boxes and the final pixel lists do."""
-        model, c = self.model, self.config
-        B, D = c.BATCH_SIZE, c.DETECTION_MAX_INSTANCES
-        H, W = int(maps.shape[1]), int(maps.shape[2])
-        lib, eng = model._lib, model._engine
-        slot = lib.mrcnn_engine_next_slot(eng)
-        sfx = b"" if slot == 0 else b"#1"
-        model.detect_maps(maps, zscale_contrasts, device_only=True)
+        return self._finish_maps(self.model.detect_maps(maps, zscale_contrasts, masks_on_device=True), image_ids, origins)
 
-        def read(name, dtype, shape):
-            out = np.empty(shape, dtype=dtype)
-            _native.check(lib.mrcnn_engine_read(eng, name + sfx, out.ctypes.data, out.nbytes), "read")
-            return out
+    def predict_maps_stream(self, batches, zscale_contrasts=(0.25, 0.25, 0.25)):
+        """Generator over an iterable of maps batches ([BATCH_SIZE,H,W] float32 each, or (maps, image_ids, origins)
+        tuples): yields predict_maps() results batch by batch, with the detector already working on batch k+1 while
+        the post-processing of batch k (its few small kernels, on a stream of their own, and the host graph logic)
+        runs. Two result slots exist in the engine, so at most two batches are ever in flight."""
+        pending = None
+        for item in batches:
+            maps, image_ids, origins = item if isinstance(item, tuple) else (item, None, None)
+            handle = (self.model.detect_maps(maps, zscale_contrasts, masks_on_device=True), image_ids, origins)
+            if pending is not None:
+                yield self._finish_maps(*pending)
+            pending = handle
+        if pending is not None:
+            yield self._finish_maps(*pending)
 
-        counts = read(b"unmold_counts", np.int32, (B,))
-        class_ids = read(b"unmold_class_ids", np.int32, (B, D))
-        scores = read(b"unmold_scores", np.float32, (B, D))
-        ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
-        _native.check(lib.mrcnn_engine_tensor(eng, b"unmold_masks" + sfx, ctypes.byref(ptr), ctypes.byref(nbytes)), "unmold_masks")
-        frames = [_Frame(ptr.value + b * H * W * D, D, int(counts[b]), class_ids[b, :counts[b]], scores[b, :counts[b]])
-                  for b in range(B)]
+    def _side_stream_ops(self):
+        """Plane ops on a stream of their own, so they do not queue behind the next batch's detect kernels."""
+        if getattr(self, "_side_ops", None) is None:
+            torch = utils._torch()
+            device = getattr(self.model, "_device", 0)
+            with torch.cuda.device(int(device)):
+                self._side_ops = MaskPlaneOps(device, torch.cuda.Stream())
+        return self._side_ops
+
+    def _finish_maps(self, handle, image_ids, origins):
+        c = self.config
+        B = c.BATCH_SIZE
+        H, W = handle.frame_hw
+        tw = time.perf_counter()
+        r = handle.result()                  # waits for this batch's small copies only (=> its masks are complete)
+        if getattr(self, "_timings", None) is not None:
+            self._timings["wait for detect"] = self._timings.get("wait for detect", 0.0) + time.perf_counter() - tw
+        D, counts = r["depth"], r["counts"]
+        frames = [_Frame(r["masks_ptr"] + b * H * W * D, D, int(counts[b]), r["class_ids"][b, :counts[b]],
+                         r["scores"][b, :counts[b]]) for b in range(B)]
         origins = origins if origins is not None else [(0, 0)] * B
         self.class_names = c.CLASS_NAMES
-        results = analyze_frames(self._plane_ops(), frames, H, W, self.class_names, origins=origins, want_masks=False,
-                                 **self._options())
+        timings = getattr(self, "_timings", None)            # development aid (tools/catalog_bench.py)
+        t0 = time.perf_counter()
+        results = analyze_frames(self._side_stream_ops(), frames, H, W, self.class_names, origins=origins, want_masks=False,
+                                 timings=timings, **self._options())
+        t1 = time.perf_counter()
         out = []
         for b, res in enumerate(results):
             image_id = image_ids[b] if image_ids is not None else b
             out.append(build_json_results(image_id, self.obj_name_tag, self.class_names, H, W, origins[b][1], origins[b][0],
                                           res.masks_final, res.class_ids_final, res.scores_final, res.bboxes, res.pixels))
+        if timings is not None:
+            timings["analyze_frames total"] = timings.get("analyze_frames total", 0.0) + t1 - t0
+            timings["host: catalogue dicts"] = timings.get("host: catalogue dicts", 0.0) + time.perf_counter() - t1
         return out
 
 
@@ -410,12 +434,19 @@ def _planes_from_host(ops, masks):
     return ops.pack(d.data_ptr(), 1, H, W, n, np.arange(n, dtype=np.int32), n)
 
 
+_FIND_CONTOURS = []
+
+
 def _find_contours():
-    try:
-        from skimage.measure import find_contours
-        return find_contours
-    except ImportError:
-        return None
+    """skimage.measure.find_contours if scikit-image is installed, else None (looked up once: a failed import is
+    not cached by Python and would be retried for every image)."""
+    if not _FIND_CONTOURS:
+        try:
+            from skimage.measure import find_contours
+            _FIND_CONTOURS.append(find_contours)
+        except ImportError:
+            _FIND_CONTOURS.append(None)
+    return _FIND_CONTOURS[0]
 
 
 def build_json_results(image_id, obj_name_tag, class_names, ny, nx, xmin, ymin, masks_final, class_ids_final, scores_final,
@@ -463,6 +494,18 @@ def _all_pairs(counts):
         base += n
     pairs = np.concatenate(chunks) if chunks else np.zeros((0, 2), dtype=np.int32)
     return pairs, slices
+
+
+def _probe_f32_average():
+    score_avg = 0
+    score_avg += np.float32(0.8125)
+    score_avg *= 1. / 1
+    return type(score_avg) is np.float32 and score_avg == np.float32(0.8125)
+
+
+# True when the reference's `score_avg = 0; score_avg += s; score_avg *= 1./1` leaves a float32 scalar unchanged
+# (numpy >= 2 scalar promotion); otherwise the expression is always evaluated literally
+_F32_AVG_IS_IDENTITY = _probe_f32_average()
 
 
 def _iou(inter, area_a, area_b):
@@ -576,6 +619,14 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
             else:
                 cc = [[v] for v in range(det_count[f])]        # what the DFS returns for a graph without edges
             for members in cc:
+                if len(members) == 1 and _F32_AVG_IS_IDENTITY and type(det_score[base + members[0]]) is np.float32:
+                    # (0 + s) * (1. / 1) is s itself, same scalar type, under this numpy's promotion rules
+                    k = base + members[0]
+                    groups.append([k])
+                    merged_cls.append(det_cls[k])
+                    merged_score.append(det_score[k])
+                    merged_int.append(any_int and det_int[k])
+                    continue
                 score_avg = 0
                 for index in members:
                     class_id = det_cls[base + index]
@@ -608,9 +659,27 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
         linked &= ~((spurious[pairs[:, 0]] != spurious[pairs[:, 1]]) & (iou < merge_overlap_iou_thr))
     final_planes, final_owner = [], []
     bbox_ok = ((bbox[:, 1] < bbox[:, 3]) & (bbox[:, 0] < bbox[:, 2])).tolist()
+    # A mask survives iff it has the best score in every maximal clique it belongs to. Without score ties between
+    # linked masks that is "no linked mask has a higher score" (any linked pair extends to a maximal clique that holds
+    # both), which needs no clique enumeration; frames with a tie between linked masks take the reference's
+    # networkx route below, where the winner depends on the order networkx lists a clique's members.
+    score_arr = np.asarray(merged_score)
+    li, lj = pairs[linked, 0], pairs[linked, 1]
+    si, sj = score_arr[li], score_arr[lj]
+    loses = np.zeros(len(merged_score), dtype=bool)
+    loses[li[si < sj]] = True
+    loses[lj[sj < si]] = True
+    tie_frame = np.zeros(F, dtype=bool)
+    if len(li):
+        frame_of = np.repeat(np.arange(F), merged_count)
+        tie_frame[frame_of[li[si == sj]]] = True
     for f, (lo, hi, base) in enumerate(slices):
-        is_selected = [True] * merged_count[f]
-        edges = np.nonzero(linked[lo:hi])[0]
+        if not tie_frame[f]:
+            is_selected = (~loses[base:base + merged_count[f]]).tolist()
+            edges = ()
+        else:
+            is_selected = [True] * merged_count[f]
+            edges = np.nonzero(linked[lo:hi])[0]
         if len(edges):
             g_final = nx.Graph()
             g_final.add_edges_from((pairs[lo + edges] - base).tolist())     # same insertion order as the pair loop

@@ -119,6 +119,30 @@ class _PendingDetection(object):
         return self._done
 
 
+class _PendingDeviceDetection(object):
+    """Handle of detect_maps(..., masks_on_device=True): boxes / class ids / scores / counts arrive in small pinned
+    buffers through the copy stream, the [B,H,W,D] uint8 masks stay in the engine's result slot on the device
+    (valid until the second next detect call reuses the slot)."""
+
+    def __init__(self, model, bufs, maps, slot, H0, W0):
+        self._model, self._bufs, self._maps, self._slot, self._done = model, bufs, maps, slot, None
+        self.frame_hw = (H0, W0)
+
+    def result(self):
+        """-> dict(rois [B,D,4], class_ids [B,D], scores [B,D], counts [B] (host), masks_ptr (device address), depth)"""
+        if self._done is None:
+            m = self._model
+            _native.check(m._lib.mrcnn_engine_wait_slot(m._engine, self._slot), "engine_wait_slot")
+            ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+            name = b"unmold_masks" if self._slot == 0 else b"unmold_masks#1"
+            _native.check(m._lib.mrcnn_engine_tensor(m._engine, name, ctypes.byref(ptr), ctypes.byref(nbytes)), "unmold_masks")
+            rois, cls, scores, counts, _ = self._bufs
+            self._done = {"rois": rois, "class_ids": cls, "scores": scores, "counts": counts, "masks_ptr": ptr.value,
+                          "depth": m.config.DETECTION_MAX_INSTANCES}
+            self._maps = None
+        return self._done
+
+
 class MaskRCNN(object):
     """Mask R-CNN inference model; drop-in for mrcnn.model.MaskRCNN(mode='inference')."""
 
@@ -450,11 +474,13 @@ class MaskRCNN(object):
     def wait(self):
         _native.check(self._lib.mrcnn_engine_wait(self._engine), "engine_wait")
 
-    def detect_maps(self, maps, zscale_contrasts=(0.25, 0.25, 0.25), device_only=False, _async=False):
+    def detect_maps(self, maps, zscale_contrasts=(0.25, 0.25, 0.25), device_only=False, _async=False, masks_on_device=False):
         """Fast path from FITS-like maps (extension; the numpy contract of detect() is unchanged):
         maps [BATCH_SIZE,H,W] float32 — numpy / pinned torch tensor (copied H2D) or a CUDA tensor —
         -> read_fits stretch + mold + graph + unmold in one C-ABI call. Returns detect()-style dicts,
-        or None with device_only=True (results stay in the engine's 'unmold_*' tensors)."""
+        or None with device_only=True (results stay in the engine's 'unmold_*' tensors). masks_on_device=True queues
+        the call and returns a _PendingDeviceDetection: only boxes / class ids / scores / counts are copied to the host,
+        the full-frame masks stay in HBM for mrcnn.analyze (no [B,H,W,100] transfer)."""
         torch = utils._torch()
         c = self.config
         if not self._weights_loaded:
@@ -475,14 +501,21 @@ class MaskRCNN(object):
         out_hw, top_left, metas32, wins = self._pinned[key]
         con = _native.float_array(list(zscale_contrasts))
         mean = _native.float_array([float(v) for v in np.asarray(c.MEAN_PIXEL).reshape(-1)[:3]])
-        bufs = None if device_only else self._result_buffers(H0, W0)
-        outs = [None] * 5 if device_only else [b.ctypes.data for b in bufs]
+        if masks_on_device:
+            bufs = self._result_buffers(1, 1)                  # small pinned set: its 1x1 mask buffer is not used
+            outs = [b.ctypes.data for b in bufs[:4]] + [None]
+            _async = True
+        else:
+            bufs = None if device_only else self._result_buffers(H0, W0)
+            outs = [None] * 5 if device_only else [b.ctypes.data for b in bufs]
         slot = self._lib.mrcnn_engine_next_slot(self._engine)
         with torch.cuda.stream(self._stream):
             _native.check(self._lib.mrcnn_engine_detect_maps(self._engine, _native.ptr(maps), 0 if maps.is_cuda else 1, H0, W0, con, mean,
                                                              int(out_hw[0]), int(out_hw[1]), int(top_left[0]), int(top_left[1]),
                                                              metas32.ctypes.data, wins.ctypes.data, *outs, 1 if _async else 0),
                           "detect_maps")
+        if masks_on_device:
+            return _PendingDeviceDetection(self, bufs, maps, slot, H0, W0)
         if device_only:
             return None          # with _async=True nothing has been waited for: call wait() before reading tensors
         if _async:

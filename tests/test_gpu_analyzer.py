@@ -248,3 +248,26 @@ def test_predict_maps_device_path_matches_host_path():
         assert ref == one.results
         total += len(ref["objs"])
     assert total > 0
+
+
+def test_predict_maps_stream_overlapped_equals_batch_by_batch():
+    """Three batches through the overlapped generator (two result slots in flight) == one predict_maps() per batch."""
+    import synth
+    from mrcnn import model as modellib
+    from mrcnn.analyze import Analyzer
+    from oracle import network as N
+    from test_gpu_engine import _config
+
+    B = 2
+    cfg = _config(B)
+    cfg.CLASS_NAMES = ["bkg", "spurious", "compact", "extended"]
+    m = modellib.MaskRCNN(mode="inference", config=cfg, model_dir="/tmp/mrcnn_logs")
+    m.set_weights(N.make_random_weights(0, 4))
+    batches = [np.stack(synth.radio_maps(B, 132, start=s)) for s in (0, 40, 80)]
+    an = Analyzer(m, cfg)
+    scores = np.concatenate([r["scores"] for r in m.detect_maps(batches[0])])
+    an.score_thr = float(np.sort(scores)[len(scores) // 3])
+    want = [an.predict_maps(b, image_ids=["x%d" % k, "y%d" % k], origins=[(0, 0), (7, 3)]) for k, b in enumerate(batches)]
+    got = list(an.predict_maps_stream((b, ["x%d" % k, "y%d" % k], [(0, 0), (7, 3)]) for k, b in enumerate(batches)))
+    assert got == want
+    assert sum(len(c["objs"]) for cats in got for c in cats) > 0
