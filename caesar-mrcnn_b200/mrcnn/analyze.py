@@ -20,6 +20,7 @@ is importable and left as an empty list otherwise.
 There is no CPU fallback: every mask operation goes through libmrcnn_b200.so and needs a CUDA device.
 """
 import ctypes
+import gc
 import itertools
 import json
 import logging
@@ -251,6 +252,9 @@ class Analyzer(object):
         self.write_to_ds9 = False
         self._final_pixels = None
         self._ops = None
+        # predict_maps / predict_maps_stream only: False returns each object's "pixels" as an int32 [npix,2] array
+        # (same JSON through write_json_results / NumpyEncoder, far fewer Python objects per batch)
+        self.pixels_as_lists = False
 
     # -- plumbing -------------------------------------------------------------------------------
     def _plane_ops(self):
@@ -360,7 +364,8 @@ class Analyzer(object):
     # -- device-resident extension ---------------------------------------------------------------------
     def predict_maps(self, maps, image_ids=None, origins=None, zscale_contrasts=(0.25, 0.25, 0.25)):
         """maps [BATCH_SIZE,H,W] float32 -> one results dict (make_json_results layout) per image. The detector's
-        [B,H,W,100] masks never leave the GPU: only class ids, scores, boxes and the final pixel lists do."""
+        [B,H,W,100] masks never leave the GPU: only class ids, scores, boxes and the final pixel lists do.
+        "pixels" is an int32 [npix,2] array per object unless self.pixels_as_lists is set."""
         return self._finish_maps(self.model.detect_maps(maps, zscale_contrasts, masks_on_device=True), image_ids, origins)
 
     def predict_maps_stream(self, batches, zscale_contrasts=(0.25, 0.25, 0.25)):
@@ -388,6 +393,18 @@ class Analyzer(object):
         return self._side_ops
 
     def _finish_maps(self, handle, image_ids, origins):
+        # The batch builds ~10^4 short-lived lists / scalars; with a large heap (torch, networkx) every generation-2
+        # pass of the cyclic collector they trigger costs tens of ms. Nothing here creates reference cycles, so the
+        # collector is paused for the duration (plain reference counting still frees everything).
+        was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            return self._finish_maps_impl(handle, image_ids, origins)
+        finally:
+            if was_enabled:
+                gc.enable()
+
+    def _finish_maps_impl(self, handle, image_ids, origins):
         c = self.config
         B = c.BATCH_SIZE
         H, W = handle.frame_hw
@@ -409,7 +426,8 @@ class Analyzer(object):
         for b, res in enumerate(results):
             image_id = image_ids[b] if image_ids is not None else b
             out.append(build_json_results(image_id, self.obj_name_tag, self.class_names, H, W, origins[b][1], origins[b][0],
-                                          res.masks_final, res.class_ids_final, res.scores_final, res.bboxes, res.pixels))
+                                          res.masks_final, res.class_ids_final, res.scores_final, res.bboxes, res.pixels,
+                                          pixels_as_lists=self.pixels_as_lists))
         if timings is not None:
             timings["analyze_frames total"] = timings.get("analyze_frames total", 0.0) + t1 - t0
             timings["host: catalogue dicts"] = timings.get("host: catalogue dicts", 0.0) + time.perf_counter() - t1
@@ -450,9 +468,11 @@ def _find_contours():
 
 
 def build_json_results(image_id, obj_name_tag, class_names, ny, nx, xmin, ymin, masks_final, class_ids_final, scores_final,
-                       bboxes, pixels):
+                       bboxes, pixels, pixels_as_lists=True):
     """reference: analyze.py:1866-1942. `pixels`: per object int32 [npix,2] (y,x), image origin already added
-    (np.argwhere(mask==1) computed on the device)."""
+    (np.argwhere(mask==1) computed on the device). pixels_as_lists=False keeps each object's "pixels" as that int32
+    array instead of a list of [y, x] lists (NumpyEncoder writes the same JSON): a batch of 64 images otherwise
+    allocates ~10^5 small lists, which costs more in Python's garbage collector than the whole GPU step."""
     results = {"image_id": image_id, "objs": []}
     find_contours = _find_contours()
     for i in range(len(class_ids_final)):
@@ -471,7 +491,7 @@ def build_json_results(image_id, obj_name_tag, class_names, ny, nx, xmin, ymin, 
             "name": 'S' + str(i + 1) + "_" + obj_name_tag,
             "x1": xmin + x1, "x2": xmin + x2, "y1": ymin + y1, "y2": ymin + y2,
             "class_id": class_id, "class_name": class_names[class_id], "score": scores_final[i],
-            "pixels": pixels[i].tolist(), "vertexes": vertex_list, "edge": at_edge,
+            "pixels": pixels[i].tolist() if pixels_as_lists else pixels[i], "vertexes": vertex_list, "edge": at_edge,
         })
     return results
 

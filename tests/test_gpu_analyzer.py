@@ -226,7 +226,9 @@ def test_predict_maps_device_path_matches_host_path():
     an.score_thr = thr
     an.obj_name_tag = "tile"
     batch = an.predict_maps(np.stack(maps), image_ids=["a", "b"])
-    assert len(batch) == B
+    assert len(batch) == B and all(isinstance(o["pixels"], np.ndarray) for cat in batch for o in cat["objs"])
+    an.pixels_as_lists = True
+    batch = an.predict_maps(np.stack(maps), image_ids=["a", "b"])
     total = 0
     for b in range(B):
         r = host[b]
@@ -265,6 +267,7 @@ def test_predict_maps_stream_overlapped_equals_batch_by_batch():
     m.set_weights(N.make_random_weights(0, 4))
     batches = [np.stack(synth.radio_maps(B, 132, start=s)) for s in (0, 40, 80)]
     an = Analyzer(m, cfg)
+    an.pixels_as_lists = True
     scores = np.concatenate([r["scores"] for r in m.detect_maps(batches[0])])
     an.score_thr = float(np.sort(scores)[len(scores) // 3])
     want = [an.predict_maps(b, image_ids=["x%d" % k, "y%d" % k], origins=[(0, 0), (7, 3)]) for k, b in enumerate(batches)]

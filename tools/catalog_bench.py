@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """End-to-end detect + Analyzer throughput: pinned host maps in, source catalogues (the reference's JSON objects
-minus 'vertexes') out, through `Analyzer.predict_maps_stream` (detect of batch k+1 overlaps the post-processing of
+minus 'vertexes'; "pixels" as one int32 array per object) out, through `Analyzer.predict_maps_stream` (detect of batch k+1 overlaps the post-processing of
 batch k; the [B,H,W,100] masks never leave the GPU).
 
 Same workload as bench.py (BASELINE.json configs[1]: 64 synthetic maps at IMAGE_MAX_DIM=256, random weights). The
