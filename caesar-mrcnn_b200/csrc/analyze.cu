@@ -404,6 +404,41 @@ __global__ void planes_unpack_kernel(const uint32_t* __restrict__ planes, int H,
   out[(size_t)m * H * W + p] = (planes[((size_t)m * H + y) * WW + (x >> 5)] >> (x & 31)) & 1u;
 }
 
+// ---- 8-connected adjacency of two pixel lists (SFinder.merge_edge_sources, mrcnn/sfinder.py:787-808) ----
+// One CTA per candidate pair: the second list streams through shared memory in chunks, every thread walks its share
+// of the first list against the chunk; the CTA stops at the first hit (checked once per chunk).
+constexpr int kAdjChunk = 2048;
+__global__ void __launch_bounds__(256) pixel_lists_adjacent_kernel(const int32_t* __restrict__ pixels,
+                                                                   const int64_t* __restrict__ offsets,
+                                                                   const int32_t* __restrict__ pairs, int32_t* __restrict__ out) {
+  pdl_prologue();
+  __shared__ int2 s_b[kAdjChunk];
+  __shared__ int s_hit;
+  const int p = blockIdx.x;
+  const int64_t a0 = offsets[pairs[2 * p]], a1 = offsets[pairs[2 * p] + 1];
+  const int64_t b0 = offsets[pairs[2 * p + 1]], b1 = offsets[pairs[2 * p + 1] + 1];
+  const int2* px = reinterpret_cast<const int2*>(pixels);
+  if (threadIdx.x == 0) s_hit = 0;
+  __syncthreads();
+  for (int64_t cb = b0; cb < b1; cb += kAdjChunk) {
+    const int nb = (int)min((int64_t)kAdjChunk, b1 - cb);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_b[i] = px[cb + i];
+    __syncthreads();
+    bool hit = false;
+    for (int64_t ia = a0 + threadIdx.x; ia < a1 && !hit; ia += blockDim.x) {
+      const int2 a = px[ia];
+      for (int i = 0; i < nb; ++i) {
+        const int2 b = s_b[i];
+        if (abs(a.x - b.x) <= 1 && abs(a.y - b.y) <= 1) { hit = true; break; }
+      }
+    }
+    if (hit) s_hit = 1;
+    __syncthreads();
+    if (s_hit) break;
+  }
+  if (threadIdx.x == 0) out[p] = s_hit;
+}
+
 inline int check_frame(int H, int W, const char* who) {
   MRCNN_REQUIRE(H > 0 && W > 0 && (long long)H * W < (1ll << 31), "%s: bad frame %dx%d", who, H, W);
   return MRCNN_OK;
@@ -547,6 +582,17 @@ extern "C" int mrcnn_planes_unpack(const uint32_t* planes, int n_planes, int hei
   const int n = height * width;
   MRCNN_CHECK_CUDA(mrcnn_launch(planes_unpack_kernel, dim3((n + kThreads - 1) / kThreads, n_planes), dim3(kThreads), 0,
                                 (cudaStream_t)stream, planes, height, width, out));
+  mrcnn_count_launch(1);
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_pixel_lists_adjacent(const int32_t* pixels, const int64_t* offsets, const int32_t* pairs, int n_pairs,
+                                          int32_t* adjacent, void* stream) {
+  MRCNN_REQUIRE(n_pairs >= 0, "pixel_lists_adjacent: negative count");
+  if (n_pairs == 0) return MRCNN_OK;
+  MRCNN_REQUIRE(pixels && offsets && pairs && adjacent, "pixel_lists_adjacent: null pointer");
+  MRCNN_CHECK_CUDA(mrcnn_launch(pixel_lists_adjacent_kernel, dim3(n_pairs), dim3(256), 0, (cudaStream_t)stream, pixels, offsets,
+                                pairs, adjacent));
   mrcnn_count_launch(1);
   return MRCNN_OK;
 }

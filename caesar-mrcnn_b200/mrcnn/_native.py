@@ -104,6 +104,7 @@ SIGNATURES = {
     "mrcnn_labels_select": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mrcnn_planes_pixels": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mrcnn_planes_unpack": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mrcnn_pixel_lists_adjacent": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -366,17 +366,17 @@ class Analyzer(object):
         """maps [BATCH_SIZE,H,W] float32 -> one results dict (make_json_results layout) per image. The detector's
         [B,H,W,100] masks never leave the GPU: only class ids, scores, boxes and the final pixel lists do.
         "pixels" is an int32 [npix,2] array per object unless self.pixels_as_lists is set."""
-        return self._finish_maps(self.model.detect_maps(maps, zscale_contrasts, masks_on_device=True), image_ids, origins)
+        return self._finish_maps(self.model.detect_maps(maps, zscale_contrasts, masks_on_device=True), image_ids, origins, None)
 
     def predict_maps_stream(self, batches, zscale_contrasts=(0.25, 0.25, 0.25)):
-        """Generator over an iterable of maps batches ([BATCH_SIZE,H,W] float32 each, or (maps, image_ids, origins)
-        tuples): yields predict_maps() results batch by batch, with the detector already working on batch k+1 while
+        """Generator over an iterable of maps batches ([BATCH_SIZE,H,W] float32 each, or (maps, image_ids, origins[,
+        name_tags]) tuples; name_tags = one obj_name_tag per image): yields predict_maps() results batch by batch, with the detector already working on batch k+1 while
         the post-processing of batch k (its few small kernels, on a stream of their own, and the host graph logic)
         runs. Two result slots exist in the engine, so at most two batches are ever in flight."""
         pending = None
         for item in batches:
-            maps, image_ids, origins = item if isinstance(item, tuple) else (item, None, None)
-            handle = (self.model.detect_maps(maps, zscale_contrasts, masks_on_device=True), image_ids, origins)
+            maps, image_ids, origins, name_tags = (tuple(item) + (None,))[:4] if isinstance(item, tuple) else (item, None, None, None)
+            handle = (self.model.detect_maps(maps, zscale_contrasts, masks_on_device=True), image_ids, origins, name_tags)
             if pending is not None:
                 yield self._finish_maps(*pending)
             pending = handle
@@ -392,19 +392,19 @@ class Analyzer(object):
                 self._side_ops = MaskPlaneOps(device, torch.cuda.Stream())
         return self._side_ops
 
-    def _finish_maps(self, handle, image_ids, origins):
+    def _finish_maps(self, handle, image_ids, origins, name_tags=None):
         # The batch builds ~10^4 short-lived lists / scalars; with a large heap (torch, networkx) every generation-2
         # pass of the cyclic collector they trigger costs tens of ms. Nothing here creates reference cycles, so the
         # collector is paused for the duration (plain reference counting still frees everything).
         was_enabled = gc.isenabled()
         gc.disable()
         try:
-            return self._finish_maps_impl(handle, image_ids, origins)
+            return self._finish_maps_impl(handle, image_ids, origins, name_tags)
         finally:
             if was_enabled:
                 gc.enable()
 
-    def _finish_maps_impl(self, handle, image_ids, origins):
+    def _finish_maps_impl(self, handle, image_ids, origins, name_tags):
         c = self.config
         B = c.BATCH_SIZE
         H, W = handle.frame_hw
@@ -425,7 +425,8 @@ class Analyzer(object):
         out = []
         for b, res in enumerate(results):
             image_id = image_ids[b] if image_ids is not None else b
-            out.append(build_json_results(image_id, self.obj_name_tag, self.class_names, H, W, origins[b][1], origins[b][0],
+            tag = name_tags[b] if name_tags is not None else self.obj_name_tag
+            out.append(build_json_results(image_id, tag, self.class_names, H, W, origins[b][1], origins[b][0],
                                           res.masks_final, res.class_ids_final, res.scores_final, res.bboxes, res.pixels,
                                           pixels_as_lists=self.pixels_as_lists))
         if timings is not None:

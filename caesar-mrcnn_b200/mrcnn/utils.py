@@ -209,3 +209,44 @@ def norm_boxes(boxes, shape):
 def denorm_boxes(boxes, shape):
     h, w = shape
     return np.around(np.multiply(boxes, np.array([h - 1, w - 1, h - 1, w - 1])) + np.array([0, 0, 1, 1])).astype(np.int32)
+
+
+# --------------------------------------------------------------------------------------------
+# tiles (reference: mrcnn/utils.py:1254-1328)
+# --------------------------------------------------------------------------------------------
+
+def generate_tiles(img_xmin, img_xmax, img_ymin, img_ymax, tileSizeX, tileSizeY, gridStepSizeX, gridStepSizeY):
+    """Tile coordinates (xmin, xmax, ymin, ymax) with exclusive maxima, row-major over the image range; None when the
+    arguments are invalid. (The reference's error branches call an undefined `logger` and raise NameError; the
+    intended `return None` is what is implemented here.)"""
+    if img_xmax <= img_xmin:
+        logger.error("xmax must be > xmin!")
+        return None
+    if img_ymax <= img_ymin:
+        logger.error("ymax must be > ymin!")
+        return None
+    if tileSizeX <= 0 or tileSizeY <= 0:
+        logger.error("Invalid box size given!")
+        return None
+    if gridStepSizeX <= 0 or gridStepSizeY <= 0 or gridStepSizeX > 1 or gridStepSizeY > 1:
+        logger.error("Invalid grid step size given (null or negative)!")
+        return None
+    Nx = img_xmax - img_xmin + 1
+    Ny = img_ymax - img_ymin + 1
+    if tileSizeX > Nx or tileSizeY > Ny:
+        logger.warning("Invalid box size given (too small or larger than image size)!")
+        return None
+    stepSizeX = int(np.round(gridStepSizeX * tileSizeX))
+    stepSizeY = int(np.round(gridStepSizeY * tileSizeY))
+    if stepSizeX < 1 or stepSizeY < 1:          # the reference would loop forever here
+        logger.error("Grid step rounds to zero pixels!")
+        return None
+    spans = []
+    for n, size, step in ((Nx, tileSizeX, stepSizeX), (Ny, tileSizeY, stepSizeY)):
+        lo_hi, index = [], 0
+        while index < n:                      # a tile starts at every step until the range is exhausted
+            lo_hi.append((index, index + min(size, n - index)))
+            index += step
+        spans.append(lo_hi)
+    return [(img_xmin + x0, img_xmin + x1, img_ymin + y0, img_ymin + y1) for (y0, y1) in spans[1] for (x0, x1) in spans[0]]
+

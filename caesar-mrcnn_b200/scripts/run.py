@@ -10,8 +10,11 @@ reference's SFinder.run does (mrcnn/sfinder.py:485-493): MaskRCNN.detect, then e
 merging of connected same-class masks, best-of-overlapping selection) on the GPU, then the reference's JSON catalogue
 (`out_<image>.json` or --detect_outfile_json; keys name,x1,x2,y1,y2,class_id,class_name,score,pixels,vertexes,edge).
 `test` writes the raw detections with score >= --scoreThr of every FITS file of a list (batched by --nimg_per_gpu).
-PNG / DS9 output, the ground-truth metrics of `test`, tiling (--split_img_in_tiles) and `train` are outside the path
-rebuilt here and are rejected.
+With --split_img_in_tiles the image is cut into --tile_xsize x --tile_ysize tiles (SFinder.run_parallel,
+mrcnn/sfinder.py:549-640): the tiles go through the detector in batches of --nimg_per_gpu, sources cut by tile borders
+are merged, and `catalog_<image>.json` is written; launched under torchrun, every rank (GPU) takes the tiles the
+reference's MPI ranks would. PNG / DS9 output, the ground-truth metrics of `test`, source parameters (WCS / flux) and
+`train` are outside the path rebuilt here and are rejected or skipped.
 Returns exit code 0 on success, 1 on failure, like the reference's main().
 """
 import argparse
@@ -28,6 +31,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 from mrcnn import logger  # noqa: E402
 from mrcnn import model as modellib, utils  # noqa: E402
 from mrcnn.analyze import Analyzer  # noqa: E402
+from mrcnn.sfinder import SFinder  # noqa: E402
 from mrcnn.config import Config  # noqa: E402
 
 
@@ -93,6 +97,10 @@ def parse_args(argv=None):
     p.add_argument("--ymax", type=int, default=-1)
     p.add_argument("--detect_outfile_json", type=str, default="")
     p.add_argument("--split_img_in_tiles", action="store_true")
+    p.add_argument("--tile_xsize", type=int, default=512, help="Sub image size in pixel along x")
+    p.add_argument("--tile_ysize", type=int, default=512, help="Sub image size in pixel along y")
+    p.add_argument("--tile_xstep", type=float, default=1.0, help="Sub image step fraction along x (=1 means no overlap)")
+    p.add_argument("--tile_ystep", type=float, default=1.0, help="Sub image step fraction along y (=1 means no overlap)")
     return p.parse_args(argv)
 
 
@@ -116,7 +124,7 @@ def validate_args(args):
         return -1
     for flag, ok in (("--grayimg", not args.grayimg), ("--no_uint8", args.to_uint8), ("--no_zscale", args.zscale),
                      ("--biascontrast", not args.biascontrast), ("--no_norm_img", args.norm_img),
-                     ("--split_img_in_tiles", not args.split_img_in_tiles), ("--backbone != resnet101", args.backbone == "resnet101"),
+                     ("--backbone != resnet101", args.backbone == "resnet101"),
                      ("--ngpu > 1 (run one process per GPU instead)", args.ngpu == 1)):
         if not ok:
             logger.error("Option %s is not supported by the B200 build (SURVEY.md §8a row a17)" % flag)
@@ -143,11 +151,18 @@ def make_config(args):
     config.ZSCALE_CONTRASTS = [float(x) for x in args.zscale_contrasts.split(",")]
     config.IOU_THR = args.iouThr
     config.SCORE_THR = args.scoreThr
+    config.IMG_PATH = args.image
+    config.IMG_XMIN, config.IMG_XMAX, config.IMG_YMIN, config.IMG_YMAX = args.xmin, args.xmax, args.ymin, args.ymax
+    config.SPLIT_IMG_IN_TILES = args.split_img_in_tiles
+    config.TILE_XSIZE, config.TILE_YSIZE = args.tile_xsize, args.tile_ysize
+    config.TILE_XSTEP, config.TILE_YSTEP = args.tile_xstep, args.tile_ystep
+    config.MAX_NTASKS_PER_WORKER = 100000
+    config.OUTFILE_JSON = args.detect_outfile_json
     return config
 
 
 def load_model(args, config):
-    model = modellib.MaskRCNN(mode="inference", config=config, model_dir=args.logs)
+    model = modellib.MaskRCNN(mode="inference", config=config, model_dir=args.logs, device=int(os.environ.get("LOCAL_RANK", "0")))
     if args.random_weights is not None:
         sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
         import synth
@@ -173,6 +188,18 @@ def result_to_json(name, r, config):
 
 
 def detect(args, model, config):
+    if args.split_img_in_tiles:
+        # scripts/run.py:1176-1183: SFinder.run_parallel(); the workers are the torch.distributed ranks (one per GPU)
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                dist.init_process_group("gloo")          # catalogues only (all_gather_object); no data-path collective
+        sfinder = SFinder(model, config)
+        sfinder.outfile_json = args.detect_outfile_json
+        if sfinder.run_parallel() < 0:
+            logger.error("sfinder run failed, see logs...")
+            return -1
+        return 0
     res = utils.read_fits(args.image, args.xmin, args.xmax, args.ymin, args.ymax, zscale_contrasts=config.ZSCALE_CONTRASTS)
     if res is None:
         logger.error("Failed to read image %s!" % args.image)

@@ -291,6 +291,14 @@ int mrcnn_planes_pixels(const uint32_t* planes, int n_planes, int height, int wi
 /* out [n,H,W] uint8 0/1 */
 int mrcnn_planes_unpack(const uint32_t* planes, int n_planes, int height, int width, uint8_t* out, void* stream);
 
+/* ---- (f2) tile driver: merging of sources across tile edges (mrcnn/sfinder.py: SFinder.merge_edge_sources
+ *      :711-935, pixel test :787-808).  pixels [total,2] int32 (y,x) = the concatenated pixel lists of all edge sources
+ *      in one global frame, offsets int64 [n_lists+1]; pairs [n_pairs,2] list indices (candidates that already passed
+ *      the neighbour-tile and bounding-box tests) -> adjacent[p] = 1 iff some pixel of list a and some pixel of list b
+ *      satisfy |dx| <= 1 and |dy| <= 1 (8-connected, the reference's double loop). */
+int mrcnn_pixel_lists_adjacent(const int32_t* pixels, const int64_t* offsets, const int32_t* pairs, int n_pairs,
+                               int32_t* adjacent, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
