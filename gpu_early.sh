@@ -1,4 +1,3 @@
 #!/bin/bash
-# scratch driver for one gpurun call: tile-driver GPU tests
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_sfinder.py -q -m gpu -x > gpurun_out/tests_sf.log 2>&1; echo "tests exit $?" >> gpurun_out/tests_sf.log; grep -v "Invalid det bbox" gpurun_out/tests_sf.log | tail -40
+timeout 900 python tools/tile_bench.py > gpurun_out/tile_bench.log 2> gpurun_out/tile_bench.err; echo "tbench exit $?"; tail -1 gpurun_out/tile_bench.log | cut -c1-1500; grep -v "Invalid det bbox\|No object detected" gpurun_out/tile_bench.err | tail -8
