@@ -1,6 +1,5 @@
 #!/bin/bash
-# scratch driver for one gpurun call: GPU tests, smoke, short bench
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/tests.log 2>&1; echo "tests exit $?" >> gpurun_out/tests.log; grep -v "Invalid det bbox" gpurun_out/tests.log | tail -4
-timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -1 gpurun_out/bench.log | cut -c1-400
+timeout 900 python -m pytest tests/test_gpu_analyzer.py -q -m gpu -x -k "pack or goldens or predict_maps_device" > gpurun_out/tests_an.log 2>&1; echo "tests exit $?" >> gpurun_out/tests_an.log; grep -v "Invalid det" gpurun_out/tests_an.log | tail -5
+timeout 600 python tools/analyze_bench.py --oracle-frames 0 > gpurun_out/analyze_bench2.log 2> gpurun_out/analyze_bench2.err; echo "abench exit $?"; python -c "
+import json; d=json.loads(open('gpurun_out/analyze_bench2.log').read().strip().splitlines()[-1]); print(d['kernels'], d['ms_per_batch'])"
