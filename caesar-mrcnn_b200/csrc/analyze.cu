@@ -85,37 +85,41 @@ __global__ void __launch_bounds__(256) masks_pack4_kernel(const uint8_t* __restr
     for (int i = (n16 << 2) + threadIdx.x; i < (nbytes >> 2); i += 256) dst4[i] = __ldg(src4 + i);
   }
   __syncthreads();
+  // ballot phase: warp w owns pixels 32w..32w+31; a lane reads the DQ words of its pixel (row stride DQ words:
+  // conflict-free when odd) and every byte costs one test + one vote + one lane-0 store into the [D][8] staging
+  // table, which then leaves as 32-byte runs per detection (no per-lane select chains)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int DQ = D >> 2;
   const uint32_t* s32 = reinterpret_cast<const uint32_t*>(s_tile);
+  uint32_t* s_out = reinterpret_cast<uint32_t*>(s_tile + (size_t)kPackPx * D);   // [D][8]
   const int nwords = (npix + 31) >> 5;
-  for (int dq = warp; dq < DQ; dq += 8) {
-    const int mk = lane < 4 ? plane_of[b * D + dq * 4 + lane] : -1;     // destination planes of these four detections
-    if (__all_sync(0xffffffffu, mk < 0)) continue;
-    uint32_t mine[kPackPx / 32];
+  if (warp < nwords) {
+    const int px = warp * 32 + lane;
+    const uint32_t* row = s32 + (px < npix ? px : 0) * DQ;
+#pragma unroll 4
+    for (int w = 0; w < DQ; ++w) {
+      const uint32_t v = px < npix ? row[w] : 0u;
 #pragma unroll
-    for (int g = 0; g < kPackPx / 32; ++g) {
-      mine[g] = 0;
-      if (g < nwords) {
-        const int px = g * 32 + lane;
-        const uint32_t v = px < npix ? s32[px * DQ + dq] : 0u;
-        const uint32_t b0 = __ballot_sync(0xffffffffu, (v & 0x000000ffu) != 0);
-        const uint32_t b1 = __ballot_sync(0xffffffffu, (v & 0x0000ff00u) != 0);
-        const uint32_t b2 = __ballot_sync(0xffffffffu, (v & 0x00ff0000u) != 0);
-        const uint32_t b3 = __ballot_sync(0xffffffffu, (v & 0xff000000u) != 0);
-        mine[g] = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : b3;
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, (v & (0xffu << (8 * q))) != 0);
+        if (lane == 0) s_out[(w * 4 + q) * 8 + warp] = bits;
       }
     }
-    if (mk >= 0) {
-      uint32_t* dst = planes + ((size_t)mk * H + y) * WW + blockIdx.x * (kPackPx / 32);
-      if (nwords == kPackPx / 32 && (WW & 3) == 0) {
-        reinterpret_cast<uint4*>(dst)[0] = make_uint4(mine[0], mine[1], mine[2], mine[3]);
-        reinterpret_cast<uint4*>(dst)[1] = make_uint4(mine[4], mine[5], mine[6], mine[7]);
-      } else {
-#pragma unroll
-        for (int g = 0; g < kPackPx / 32; ++g)
-          if (g < nwords) dst[g] = mine[g];
-      }
+  }
+  __syncthreads();
+  if (nwords == 8 && (WW & 3) == 0) {
+    for (int i = threadIdx.x; i < D * 2; i += 256) {       // two 16-byte halves per detection
+      const int d = i >> 1, h = i & 1;
+      const int m = plane_of[b * D + d];
+      if (m >= 0)
+        reinterpret_cast<uint4*>(planes + ((size_t)m * H + y) * WW + blockIdx.x * 8)[h] =
+            reinterpret_cast<const uint4*>(s_out + d * 8)[h];
+    }
+  } else {
+    for (int i = threadIdx.x; i < D * 8; i += 256) {
+      const int d = i >> 3, g = i & 7;
+      const int m = plane_of[b * D + d];
+      if (m >= 0 && g < nwords) planes[((size_t)m * H + y) * WW + blockIdx.x * 8 + g] = s_out[d * 8 + g];
     }
   }
 }
@@ -463,11 +467,11 @@ extern "C" int mrcnn_masks_pack(const uint8_t* masks, int n_images, int height, 
   MRCNN_REQUIRE(n_images > 0 && n_images <= 65535 && height <= 65535 && depth > 0 && depth * 32 <= 200 * 1024,
                 "masks_pack: bad sizes (n_images %d, depth %d)", n_images, depth);
   const bool fast = (depth & 3) == 0 && ((size_t)width * depth) % 16 == 0 && (reinterpret_cast<uintptr_t>(masks) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(planes) & 15) == 0 && (size_t)kPackPx * depth <= 48 * 1024;
+                    (reinterpret_cast<uintptr_t>(planes) & 15) == 0 && (size_t)(kPackPx + 32) * depth <= 48 * 1024;
   if (fast) {
     dim3 grid((width + kPackPx - 1) / kPackPx, height, n_images);
-    MRCNN_CHECK_CUDA(mrcnn_launch(masks_pack4_kernel, grid, dim3(256), (size_t)kPackPx * depth, (cudaStream_t)stream, masks,
-                                  height, width, depth, plane_of, planes));
+    MRCNN_CHECK_CUDA(mrcnn_launch(masks_pack4_kernel, grid, dim3(256), (size_t)(kPackPx + 32) * depth, (cudaStream_t)stream,
+                                  masks, height, width, depth, plane_of, planes));
   } else {
     const size_t smem = (size_t)32 * depth;
     if (smem > 48 * 1024)
