@@ -171,14 +171,29 @@ __global__ void planes_area_bbox_kernel(const uint32_t* __restrict__ planes, int
 
 // ---- pair statistics: |a & b| and the 4-neighbourhood touch test, one CTA per pair ----
 __global__ void planes_pair_stats_kernel(const uint32_t* __restrict__ planes, int H, int W, const int32_t* __restrict__ pairs,
-                                         int32_t* __restrict__ inter, int32_t* __restrict__ touch) {
+                                         const int32_t* __restrict__ bbox, int32_t* __restrict__ inter,
+                                         int32_t* __restrict__ touch) {
   pdl_prologue();
   const int p = blockIdx.x, WW = words_per_row(W);
-  const uint32_t* A = planes + (size_t)pairs[2 * p] * H * WW;
-  const uint32_t* B = planes + (size_t)pairs[2 * p + 1] * H * WW;
+  const int ia = pairs[2 * p], ib = pairs[2 * p + 1];
+  int row_lo = 0, row_hi = H;
+  if (bbox) {
+    // (y1,x1,y2,x2), y2/x2 exclusive, zeros for an empty mask: masks whose boxes are more than one pixel apart can
+    // neither intersect nor touch; otherwise only the rows of a's box can contribute
+    const int ay1 = bbox[4 * ia], ax1 = bbox[4 * ia + 1], ay2 = bbox[4 * ia + 2], ax2 = bbox[4 * ia + 3];
+    const int by1 = bbox[4 * ib], bx1 = bbox[4 * ib + 1], by2 = bbox[4 * ib + 2], bx2 = bbox[4 * ib + 3];
+    if (ay2 < by1 || by2 < ay1 || ax2 < bx1 || bx2 < ax1 || ay2 <= ay1 || by2 <= by1) {
+      if (threadIdx.x == 0) { inter[p] = 0; touch[p] = 0; }
+      return;
+    }
+    row_lo = ay1;
+    row_hi = ay2;
+  }
+  const uint32_t* A = planes + (size_t)ia * H * WW;
+  const uint32_t* B = planes + (size_t)ib * H * WW;
   int cnt = 0;
   uint32_t hit = 0;
-  for (int i = threadIdx.x; i < H * WW; i += blockDim.x) {
+  for (int i = row_lo * WW + threadIdx.x; i < row_hi * WW; i += blockDim.x) {
     const uint32_t a = A[i];
     if (!a) continue;
     const int y = i / WW, wx = i - y * WW;
@@ -497,13 +512,13 @@ extern "C" int mrcnn_planes_area_bbox(const uint32_t* planes, int n_planes, int 
 }
 
 extern "C" int mrcnn_planes_pair_stats(const uint32_t* planes, int height, int width, const int32_t* pairs, int n_pairs,
-                                       int32_t* inter, int32_t* touch, void* stream) {
+                                       const int32_t* bbox, int32_t* inter, int32_t* touch, void* stream) {
   MRCNN_REQUIRE(n_pairs >= 0, "planes_pair_stats: negative count");
   if (n_pairs == 0) return MRCNN_OK;
   MRCNN_REQUIRE(planes && pairs && inter && touch, "planes_pair_stats: null pointer");
   RC(check_frame(height, width, "planes_pair_stats"));
   MRCNN_CHECK_CUDA(mrcnn_launch(planes_pair_stats_kernel, dim3(n_pairs), dim3(kThreads), 0, (cudaStream_t)stream, planes,
-                                height, width, pairs, inter, touch));
+                                height, width, pairs, bbox, inter, touch));
   mrcnn_count_launch(1);
   return MRCNN_OK;
 }

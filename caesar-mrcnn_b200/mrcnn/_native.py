@@ -97,7 +97,7 @@ SIGNATURES = {
     "mrcnn_plane_words": (c_size_t, [c_int, c_int]),
     "mrcnn_masks_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mrcnn_planes_area_bbox": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "mrcnn_planes_pair_stats": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mrcnn_planes_pair_stats": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mrcnn_planes_union": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mrcnn_planes_label_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mrcnn_planes_label": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

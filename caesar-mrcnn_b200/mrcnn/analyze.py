@@ -128,15 +128,15 @@ class MaskPlaneOps:
                                                       self._st()), "planes_area_bbox")
         return area[:n], bbox[:n]
 
-    def pair_stats(self, planes, H, W, pairs):
-        """pairs host int32 [P,2] -> device (inter [P], touch [P])."""
+    def pair_stats(self, planes, H, W, pairs, bbox=None):
+        """pairs host int32 [P,2] -> device (inter [P], touch [P]); bbox: optional device [n,4] from area_bbox."""
         P = int(pairs.shape[0])
         inter = self.empty((max(P, 1),), self.torch.int32)
         touch = self.empty((max(P, 1),), self.torch.int32)
         if P:
             d_pairs = self.to_dev(pairs, np.int32)
-            _native.check(self.lib.mrcnn_planes_pair_stats(_native.ptr(planes), H, W, _native.ptr(d_pairs), P, _native.ptr(inter),
-                                                           _native.ptr(touch), self._st()), "planes_pair_stats")
+            _native.check(self.lib.mrcnn_planes_pair_stats(_native.ptr(planes), H, W, _native.ptr(d_pairs), P, _native.ptr(bbox),
+                                                           _native.ptr(inter), _native.ptr(touch), self._st()), "planes_pair_stats")
         return inter[:P], touch[:P]
 
     def union(self, planes, H, W, groups):
@@ -529,6 +529,16 @@ def _probe_f32_average():
 _F32_AVG_IS_IDENTITY = _probe_f32_average()
 
 
+def _probe_scalar_compare():
+    x = np.float32(0.7)
+    return bool(x < 0.7) == bool((np.array([x]) < 0.7)[0]) and bool(x < 0.7000000001) == bool((np.array([x]) < 0.7000000001)[0])
+
+
+# True when `np.float32 scalar < python float` and `float32 array < python float` compare the same way (numpy >= 2:
+# both in float32); numpy 1.x compares the scalar in float64, and then the reference's scalar loop is kept
+_SCALAR_LT_IS_ARRAY_LT = _probe_scalar_compare()
+
+
 def _iou(inter, area_a, area_b):
     """sklearn jaccard_score(average='binary'): tp / (tp + fp + fn) in float64, 0.0 for an empty union."""
     union = area_a.astype(np.int64) + area_b.astype(np.int64) - inter.astype(np.int64)
@@ -566,7 +576,10 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
     sel_cls, sel_score, sel_count = [], [], []
     m = 0
     for f, fr in enumerate(frames):
-        picked = [i for i in range(fr.n) if not fr.scores[i] < score_thr]
+        if _SCALAR_LT_IS_ARRAY_LT and isinstance(fr.scores, np.ndarray) and fr.scores.dtype == np.float32:
+            picked = np.nonzero(~(fr.scores[:fr.n] < score_thr))[0].tolist()     # same comparisons, one numpy call
+        else:
+            picked = [i for i in range(fr.n) if not fr.scores[i] < score_thr]
         scores_sel = [fr.scores[i] for i in picked]
         order = np.argsort(scores_sel)[::-1]
         for index in order:
@@ -621,8 +634,8 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
     if merge_overlapped_masks and len(det_cls):
         pairs, slices = _all_pairs(det_count)
         mark("host: pair lists")
-        d_area, _ = ops.area_bbox(planes, H, W)
-        d_inter, d_touch = ops.pair_stats(planes, H, W, pairs)
+        d_area, d_bbox = ops.area_bbox(planes, H, W)
+        d_inter, d_touch = ops.pair_stats(planes, H, W, pairs, d_bbox)
         area, inter, touch = ops.host(d_area), ops.host(d_inter), ops.host(d_touch)
         mark("gpu: merge pair stats (+pairs H2D, results D2H)")
         cls_arr = np.asarray(det_cls)
@@ -670,7 +683,7 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
     pairs, slices = _all_pairs(merged_count)
     mark("host: pair lists")
     d_area, d_bbox = ops.area_bbox(planes, H, W)
-    d_inter, d_touch = ops.pair_stats(planes, H, W, pairs)
+    d_inter, d_touch = ops.pair_stats(planes, H, W, pairs, d_bbox)
     area, bbox, inter, touch = ops.host(d_area), ops.host(d_bbox), ops.host(d_inter), ops.host(d_touch)
     mark("gpu: select pair stats + bbox (+H2D/D2H)")
     spurious = np.array([class_names[c] == 'spurious' for c in merged_cls], dtype=bool)

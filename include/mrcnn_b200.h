@@ -270,9 +270,11 @@ int mrcnn_planes_area_bbox(const uint32_t* planes, int n_planes, int height, int
                            int32_t* bbox, void* stream);
 /* pairs [n_pairs,2] plane indices -> inter[p] = |a & b| (numerator of sklearn jaccard_score, the
  * denominator is area[a]+area[b]-inter), touch[p] = 1 iff are_mask_connected(a,b) would be True
- * (a pixel of a coincides with or is 4-adjacent to a pixel of b). */
+ * (a pixel of a coincides with or is 4-adjacent to a pixel of b).  bbox: optional [n_planes,4] from
+ * mrcnn_planes_area_bbox (NULL = none): pairs whose boxes are more than one pixel apart are answered without
+ * reading the planes, the others scan only the rows of a's box. */
 int mrcnn_planes_pair_stats(const uint32_t* planes, int height, int width, const int32_t* pairs, int n_pairs,
-                            int32_t* inter, int32_t* touch, void* stream);
+                            const int32_t* bbox, int32_t* inter, int32_t* touch, void* stream);
 /* out[g] = OR of planes[members[offsets[g] .. offsets[g+1])]  (merge_masks folded over a group) */
 int mrcnn_planes_union(const uint32_t* planes, int height, int width, const int32_t* members,
                        const int32_t* offsets, int n_groups, uint32_t* out, void* stream);

@@ -119,7 +119,7 @@ class NumpyPlaneOps:
                 bbox[i] = [ys[0], xs[0], ys[-1] + 1, xs[-1] + 1]
         return _Arr(area), _Arr(bbox)
 
-    def pair_stats(self, pl, H, W, pairs):
+    def pair_stats(self, pl, H, W, pairs, bbox=None):
         a = pl.a
         grown = a.copy()
         grown[:, 1:] |= a[:, :-1]

@@ -85,6 +85,9 @@ def test_pair_stats_and_union(ops, H, W):
     pairs = np.stack([i, j], axis=1).astype(np.int32)
     inter, touch = ops.pair_stats(planes, H, W, pairs)
     inter, touch = ops.host(inter), ops.host(touch)
+    _, d_bbox = ops.area_bbox(planes, H, W)                    # bounding-box prefilter: same answers
+    inter_b, touch_b = ops.pair_stats(planes, H, W, pairs, d_bbox)
+    assert np.array_equal(ops.host(inter_b), inter) and np.array_equal(ops.host(touch_b), touch)
     for p, (a, b) in enumerate(pairs):
         ma, mb = masks[:, :, a], masks[:, :, b]
         assert inter[p] == np.count_nonzero(ma & mb)

@@ -82,6 +82,7 @@ def main():
     inter = ops.empty((len(pairs),), torch.int32)
     touch = ops.empty((len(pairs),), torch.int32)
     d_map = ops.to_dev(plane_of, np.int32)
+    _, d_bbox = ops.area_bbox(planes, S, S)
     lib, nat = ops.lib, P._native
     torch.cuda.synchronize()
     ev[0].record()
@@ -89,15 +90,15 @@ def main():
         nat.check(lib.mrcnn_masks_pack(d_masks.data_ptr(), F, S, S, D, nat.ptr(d_map), nat.ptr(planes), ops._st()), "pack")
     ev[1].record()
     for _ in range(args.reps):
-        nat.check(lib.mrcnn_planes_pair_stats(nat.ptr(planes), S, S, nat.ptr(d_pairs), len(pairs), nat.ptr(inter), nat.ptr(touch),
-                                              ops._st()), "pairs")
+        nat.check(lib.mrcnn_planes_pair_stats(nat.ptr(planes), S, S, nat.ptr(d_pairs), len(pairs), nat.ptr(d_bbox), nat.ptr(inter),
+                                              nat.ptr(touch), ops._st()), "pairs")
     ev[2].record()
     torch.cuda.synchronize()
     pack_ms = ev[0].elapsed_time(ev[1]) / args.reps
     pair_ms = ev[1].elapsed_time(ev[2]) / args.reps
     words = ops.words(S, S)
     pack_bytes = masks.nbytes + len(sel) * words * 4
-    pair_bytes = len(pairs) * 2 * words * 4           # both planes of every pair once (the neighbour rows hit L1/L2)
+    pair_bytes = len(pairs) * 2 * words * 4           # nominal: both planes of every pair once (box-disjoint pairs are skipped)
     peak = 6538.3
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
