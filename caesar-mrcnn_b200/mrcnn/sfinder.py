@@ -232,19 +232,26 @@ class SFinder(object):
             return -1
         plane = data[0, 0] if data.ndim == 4 else data
         B = self.config.BATCH_SIZE
+        # the image goes to the GPU once (native-endian float32); tiles are cut there, on the detector's stream, so
+        # the per-batch host work is a handful of slice objects instead of a 16 MB byte-swapping copy
+        torch = utils._torch()
+        stream = self.model._stream
+        with torch.cuda.stream(stream):
+            d_plane = torch.from_numpy(np.ascontiguousarray(plane, dtype=np.float32)).to("cuda:%d" % int(self.model._device))
         by_shape = {}
         for j, task in enumerate(mine):
-            tile = plane[task.iy_min:task.iy_max, task.ix_min:task.ix_max]
-            by_shape.setdefault(tile.shape, []).append((j, tile))
+            shape = (min(task.iy_max, d_plane.shape[0]) - task.iy_min, min(task.ix_max, d_plane.shape[1]) - task.ix_min)
+            by_shape.setdefault(shape, []).append(j)
 
         def batches():
             for shape, items in by_shape.items():
                 for lo in range(0, len(items), B):
                     chunk = items[lo:lo + B]
                     padded = chunk + [chunk[-1]] * (B - len(chunk))          # the tail batch repeats its last tile
-                    maps = np.ascontiguousarray(np.stack([t for _, t in padded]), dtype=np.float32)
-                    tasks = [mine[j] for j, _ in padded]
-                    order.append([j for j, _ in chunk])
+                    tasks = [mine[j] for j in padded]
+                    with torch.cuda.stream(stream):
+                        maps = torch.stack([d_plane[t.iy_min:t.iy_max, t.ix_min:t.ix_max] for t in tasks]).contiguous()
+                    order.append(list(chunk))
                     yield (maps, [self.image_id] * B, [(t.iy_min, t.ix_min) for t in tasks], [t.sname_tag for t in tasks])
 
         order = []
