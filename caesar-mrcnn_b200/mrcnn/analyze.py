@@ -650,6 +650,15 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
                 for a, b in (pairs[lo + edges] - base).tolist():
                     g.addEdge(a, b)
                 cc = g.connectedComponents()
+            elif _F32_AVG_IS_IDENTITY and all(type(x) is np.float32 for x in det_score[base:base + det_count[f]]):
+                # no edges: every mask is its own component and (0 + s) * (1. / 1) is s itself -> bulk copy
+                n_f = det_count[f]
+                groups.extend([k] for k in range(base, base + n_f))
+                merged_cls.extend(det_cls[base:base + n_f])
+                merged_score.extend(det_score[base:base + n_f])
+                merged_int.extend(det_int[base:base + n_f] if any_int else [False] * n_f)
+                merged_count.append(n_f)
+                continue
             else:
                 cc = [[v] for v in range(det_count[f])]        # what the DFS returns for a graph without edges
             for members in cc:
@@ -732,6 +741,7 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
                     if index != clique_max_score_index[q] and is_selected[index]:
                         is_selected[index] = False
         res = results[f]
+        keep = []
         for index in range(merged_count[f]):
             if not is_selected[index]:
                 continue
@@ -740,14 +750,14 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
                 bb = bbox[k]
                 logger.warning("Invalid det bbox(%d,%d,%d,%d), skip it ..." % (bb[1], bb[3], bb[0], bb[2]))
                 continue
-            label = class_names[merged_cls[k]]
-            res.class_ids_final.append(merged_cls[k])
-            res.class_names_final.append(label)
-            res.scores_final.append(merged_score[k])
-            res.bboxes.append(bbox[k])
-            res.captions.append("{} {:.2f}".format(label, merged_score[k]))
-            final_planes.append(k)
-            final_owner.append(f)
+            keep.append(k)
+        res.class_ids_final = [merged_cls[k] for k in keep]
+        res.class_names_final = [class_names[c] for c in res.class_ids_final]
+        res.scores_final = [merged_score[k] for k in keep]
+        res.bboxes = [bbox[k] for k in keep]
+        res.captions = ["{} {:.2f}".format(n, sc) for n, sc in zip(res.class_names_final, res.scores_final)]
+        final_planes.extend(keep)
+        final_owner.extend([f] * len(keep))
 
     mark("host: cliques + selection")
     # -- final masks and pixel lists (make_json_results: np.argwhere(mask == 1), analyze.py:1903-1909)
