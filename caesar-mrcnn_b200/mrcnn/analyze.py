@@ -275,6 +275,9 @@ class Analyzer(object):
         if image is None:
             logger.error("No input image given!")
             return -1
+        if self.draw or self.write_to_ds9:
+            raise NotImplementedError("drawing / DS9 regions are outside the rebuilt detect path (DESIGN.md §6): "
+                                      "set analyzer.draw = False and analyzer.write_to_ds9 = False")
         self.image = image
         self.image_xmin = xmin
         self.image_ymin = ymin
@@ -295,8 +298,6 @@ class Analyzer(object):
             logger.warning("No detected object found for image %s ..." % self.image_id)
             return 0
         self.bboxes_gt = bboxes_gt
-        if self.draw or self.write_to_ds9:
-            raise NotImplementedError("drawing / DS9 regions are outside the rebuilt detect path (DESIGN.md §6)")
         self.make_json_results()
         if self.write_to_json:
             self.write_json_results(self.outfile_json if self.outfile_json != "" else 'out_' + str(self.image_id) + '.json')
@@ -304,10 +305,13 @@ class Analyzer(object):
 
     def extract_det_masks(self):
         """reference: analyze.py:1162-1423, from self.masks [H,W,N] / self.boxes / self.class_ids / self.scores."""
-        ops = self._plane_ops()
         masks = np.asarray(self.masks)
         H, W, depth = masks.shape
         N = int(np.asarray(self.boxes).shape[0])
+        if depth == 0 or N == 0:                         # nothing detected: empty result lists, as in the reference
+            self._publish(_FrameResult())
+            return
+        ops = self._plane_ops()
         d_masks = ops.to_dev(masks.view(np.uint8) if masks.dtype == np.bool_ else (masks != 0).view(np.uint8), np.uint8)
         frame = _Frame(d_masks.data_ptr(), depth, N, self.class_ids, self.scores, keepalive=d_masks)
         res = analyze_frames(ops, [frame], H, W, self.class_names, origins=[(self.image_ymin, self.image_xmin)],

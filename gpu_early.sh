@@ -1,4 +1,6 @@
 #!/bin/bash
+# scratch driver for one gpurun call: GPU tests, smoke, short bench
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_sfinder.py -q -m gpu -x > gpurun_out/tests_sf.log 2>&1; echo "tests exit $?" >> gpurun_out/tests_sf.log; grep -v "Invalid det bbox" gpurun_out/tests_sf.log | tail -4
-timeout 600 python tools/tile_bench.py > gpurun_out/tile_bench.log 2> gpurun_out/tile_bench.err; echo "tbench exit $?"; tail -1 gpurun_out/tile_bench.log | cut -c1-600
+timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/tests.log 2>&1; echo "tests exit $?" >> gpurun_out/tests.log; grep -v "Invalid det bbox" gpurun_out/tests.log | tail -4
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -1 gpurun_out/bench.log | cut -c1-400

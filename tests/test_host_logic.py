@@ -250,3 +250,27 @@ def test_analyzer_host_pipeline_matches_oracle_with_numpy_backend():
                 assert list(det["bboxes"][k]) == list(got.bboxes[k])
                 assert det["captions"][k] == got.captions[k]
                 assert np.array_equal(np.asarray(det["masks_final"][k]) != 0, got.masks_final[k] != 0)
+
+
+def test_analyzer_rejects_drawing_before_any_work_and_handles_no_detections():
+    from mrcnn.analyze import Analyzer
+
+    class Cfg:
+        NUM_CLASSES = 4
+
+    class Boom:
+        def detect(self, images, verbose=0):
+            raise AssertionError("detect must not be reached")
+
+    an = Analyzer(Boom(), Cfg())
+    an.draw = True
+    with pytest.raises(NotImplementedError):
+        an.predict(np.zeros((8, 8, 3), np.uint8), "img")
+    an = Analyzer(None, Cfg())                       # no detections: no device work, empty lists
+    an.class_names = ["bkg", "a", "b", "c"]
+    an.masks, an.boxes = np.empty((8, 8, 0)), np.zeros((0, 4), np.int32)
+    an.class_ids, an.scores = np.zeros((0,), np.int32), np.zeros((0,), np.float32)
+    an.image = np.zeros((8, 8, 3), np.uint8)
+    an.extract_det_masks()
+    an.make_json_results()
+    assert an.masks_final == [] and an.bboxes == [] and an.results == {"image_id": -1, "objs": []}
