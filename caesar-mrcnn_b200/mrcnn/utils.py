@@ -93,7 +93,7 @@ def mold_rgb8_device(rgb, minmax, out_hw, square, top_left, mean_pixel, out=None
 
 def get_fits_header(filename):
     try:
-        _, header = fitsio.read_primary(filename)
+        header, _ = fitsio.read_header_only(filename)         # header blocks only: survey images are GBs
     except Exception:
         logger.error("ERROR: Cannot read image file: " + str(filename))
         return None

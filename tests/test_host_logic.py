@@ -274,3 +274,43 @@ def test_analyzer_rejects_drawing_before_any_work_and_handles_no_detections():
     an.extract_det_masks()
     an.make_json_results()
     assert an.masks_final == [] and an.bboxes == [] and an.results == {"image_id": -1, "objs": []}
+
+
+def test_fits_header_only_memmap_subimage_and_writer(golden_dir, tmp_path):
+    """Survey-sized access paths of mrcnn/fitsio.py against read_primary on the shipped files and on written ones."""
+    from mrcnn import fitsio, utils
+    for name in ("galaxy0002.fits", "sidelobe0001.fits"):
+        path = os.path.join(golden_dir, name)
+        full, hdr = fitsio.read_primary(path)
+        hdr2, pos = fitsio.read_header_only(path)
+        assert dict(hdr2) == dict(hdr) and pos % 2880 == 0
+        plane = full[0, 0] if full.ndim == 4 else full
+        sub, _ = fitsio.read_subimage(path, 5, 77, 11, 40)
+        assert sub.dtype == plane.dtype and np.array_equal(sub, plane[11:40, 5:77], equal_nan=True)
+        mm, _ = fitsio.open_primary(path)
+        assert mm.shape == full.shape and not mm.flags.writeable
+        assert utils.get_fits_size(path) == (hdr["NAXIS1"], hdr["NAXIS2"])
+    rng = np.random.default_rng(3)
+    cases = [(rng.normal(size=(37, 53)).astype(np.float32), ()), (rng.normal(size=(1, 1, 20, 31)), ()),
+             (rng.integers(-3000, 3000, size=(25, 40)).astype(np.int16), (("BSCALE", 0.5), ("BZERO", 100.0), ("BLANK", -7))),
+             (rng.integers(0, 255, size=(16, 16)).astype(np.uint8), ()), (rng.integers(-9, 9, size=(9, 70)).astype(np.int32), ())]
+    for k, (arr, cards) in enumerate(cases):
+        path = str(tmp_path / ("w%d.fits" % k))
+        if cards:
+            arr[3, 4] = -7
+        fitsio.write_primary(path, arr, cards + (("OBJECT", "it's a test"), ("BMAJ", 1.25e-3)))
+        full, hdr = fitsio.read_primary(path)
+        assert hdr["OBJECT"] == "it's a test" and hdr["BMAJ"] == 1.25e-3 and hdr["NAXIS"] == arr.ndim
+        if cards:
+            want = arr.astype(np.float64) * 0.5 + 100.0
+            want[arr == -7] = np.nan
+            assert np.array_equal(full, want.astype(np.float32), equal_nan=True)
+        else:
+            assert np.array_equal(full, arr) and full.dtype == arr.dtype
+        plane = full[0, 0] if full.ndim == 4 else full
+        sub, _ = fitsio.read_subimage(path, 2, 13, 1, 8)
+        assert np.array_equal(sub, plane[1:8, 2:13], equal_nan=True) and sub.dtype == plane.dtype
+    with pytest.raises(fitsio.FitsError):
+        fitsio.read_header_only(__file__)
+    with pytest.raises(fitsio.FitsError):
+        fitsio.write_primary(str(tmp_path / "bad.fits"), np.zeros((3,), np.float32))
