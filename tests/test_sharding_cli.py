@@ -68,3 +68,27 @@ def test_cli_argument_validation(tmp_path, golden_dir):
     assert run.main(["detect", "--image", fits, "--random_weights", "0", "--grayimg"]) == 1
     assert run.main(["detect", "--image", fits, "--random_weights", "0", "--backbone", "resnet50"]) == 1
     assert run.main(["test", "--weights", "w.h5"]) == 1                            # no datalist
+
+
+def test_cli_tile_options_reach_the_tile_driver(golden_dir):
+    """--split_img_in_tiles and the tile geometry flags land in the config and produce the reference's tile grid
+    for the shipped 132 x 132 image (header-only FITS access: no GPU involved)."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "caesar-mrcnn_b200", "scripts", "run.py")
+    spec = importlib.util.spec_from_file_location("b200_run_tiles", path)
+    run = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(run)
+    fits = os.path.join(golden_dir, "galaxy0002.fits")
+    args = run.parse_args(["detect", "--image", fits, "--random_weights", "0", "--split_img_in_tiles", "--tile_xsize", "66",
+                           "--tile_ysize", "50", "--tile_xstep", "1.0", "--tile_ystep", "0.5", "--nimg_per_gpu", "4"])
+    assert run.validate_args(args) == 0
+    cfg = run.make_config(args)
+    assert (cfg.SPLIT_IMG_IN_TILES, cfg.TILE_XSIZE, cfg.TILE_YSIZE, cfg.TILE_XSTEP, cfg.TILE_YSTEP) == (True, 66, 50, 1.0, 0.5)
+    assert cfg.IMG_PATH == fits and cfg.BATCH_SIZE == 4
+    sf = run.SFinder(None, cfg)
+    assert sf.set_img_size_params() == 0
+    assert (sf.nx, sf.ny, sf.xmin, sf.xmax, sf.ymin, sf.ymax, sf.image_id) == (132, 132, 0, 131, 0, 131, "galaxy0002")
+    assert sf.create_tile_tasks() == 0
+    coords = [t.coords for t in sf.tasks_per_worker[0]]
+    assert coords[:2] == [(0, 66, 0, 50), (66, 132, 0, 50)] and coords[-1] == (66, 132, 125, 132) and len(coords) == 12
+    assert sf.tasks_per_worker[0][0].neighborTaskId[:2] == [1, 2]
