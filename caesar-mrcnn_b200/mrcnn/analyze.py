@@ -602,6 +602,7 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
         splittable = [class_names[c] not in _UNSPLIT_LABELS for c in sel_cls]
         labels, counts = ops.label(planes, H, W)
         ncomp = ops.host(counts)
+        mark("gpu: label components (+counts D2H)")
         src, comp, keep_src, keep_dst = [], [], [], []
         det_cls, det_score, det_int, det_count = [], [], [], []
         pos = 0
@@ -632,6 +633,7 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
             planes = ops.gather(ops.torch.cat([parts, planes], dim=0), origin_idx)
         else:
             planes = parts
+        mark("host+gpu: component planes")
 
     # -- merge connected same-class masks above the IOU threshold (analyze.py:1258-1320)
     merged_cls, merged_score, merged_int, merged_count = det_cls, det_score, det_int, det_count
