@@ -105,6 +105,8 @@ SIGNATURES = {
     "mrcnn_planes_pixels": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mrcnn_planes_unpack": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mrcnn_pixel_lists_adjacent": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "mrcnn_host_merge_components": (c_int, [c_int, c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p,
+                                            c_void_p]),
 }
 
 _lib = None

@@ -24,6 +24,7 @@ import gc
 import itertools
 import json
 import logging
+import os
 import time
 
 import numpy as np
@@ -140,14 +141,18 @@ class MaskPlaneOps:
         return inter[:P], touch[:P]
 
     def union(self, planes, H, W, groups):
-        """groups: list of lists of plane indices -> [len(groups), words] planes."""
-        G = len(groups)
-        out = self.empty((max(G, 1), self.words(H, W)), self.torch.int32)
-        if G:
+        """groups: list of lists of plane indices, or (members int32 [M], offsets int32 [G+1]) -> [G, words] planes."""
+        if isinstance(groups, tuple):
+            members, offsets = groups
+            G = len(offsets) - 1
+        else:
+            G = len(groups)
             lens = np.fromiter(map(len, groups), dtype=np.int64, count=G)
             members = np.fromiter(itertools.chain.from_iterable(groups), dtype=np.int32, count=int(lens.sum()))
             offsets = np.zeros(G + 1, dtype=np.int32)
             offsets[1:] = np.cumsum(lens)
+        out = self.empty((max(G, 1), self.words(H, W)), self.torch.int32)
+        if G:
             d_m, d_o = self.to_dev(members, np.int32), self.to_dev(offsets, np.int32)
             _native.check(self.lib.mrcnn_planes_union(_native.ptr(planes), H, W, _native.ptr(d_m), _native.ptr(d_o), G,
                                                       _native.ptr(out), self._st()), "planes_union")
@@ -521,6 +526,49 @@ def _all_pairs(counts):
     return pairs, slices
 
 
+# MRCNN_B200_NATIVE_GRAPH=1: the merge graph of a whole batch through the host-only C++ routine
+# mrcnn_host_merge_components instead of the per-frame Python walk (same component order; CPU-tested against the
+# reference goldens; off by default until its effect has been measured on the GPU box)
+_USE_NATIVE_GRAPH = os.environ.get("MRCNN_B200_NATIVE_GRAPH", "0") == "1"
+
+
+def _native_merge(det_count, pairs, mergeable, det_cls, det_score, det_int, any_int):
+    """Merge stage of extract_det_masks for all frames at once -> (groups as (members, offsets), merged_cls,
+    merged_score, merged_int, merged_count), or None when the score shortcut does not apply to this numpy."""
+    if not (_F32_AVG_IS_IDENTITY and all(type(x) is np.float32 for x in det_score)):
+        return None
+    lib = _native.lib()
+    n, F = len(det_cls), len(det_count)
+    counts = np.asarray(det_count, dtype=np.int32)
+    flags = np.ascontiguousarray(mergeable, dtype=np.uint8)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32)
+    members = np.empty(n, dtype=np.int32)
+    offsets = np.empty(n + 1, dtype=np.int32)
+    frame_comps = np.empty(F, dtype=np.int32)
+    ncomp = ctypes.c_int32(0)
+    _native.check(lib.mrcnn_host_merge_components(F, counts.ctypes.data, pairs.ctypes.data if len(pairs) else None,
+                                                  flags.ctypes.data if len(pairs) else None, len(pairs), members.ctypes.data,
+                                                  offsets.ctypes.data, frame_comps.ctypes.data, ctypes.byref(ncomp)),
+                  "host_merge_components")
+    G = ncomp.value
+    offsets = offsets[:G + 1]
+    last = members[offsets[1:] - 1]                     # class of the LAST member, as in the reference
+    merged_cls = [det_cls[k] for k in last.tolist()]
+    merged_score = [det_score[k] for k in members[offsets[:-1]].tolist()]      # (0 + s) * (1. / 1) is s for singletons
+    merged_int = [False] * G
+    sizes = np.diff(offsets)
+    if any_int:
+        int_arr = np.asarray(det_int, dtype=bool)
+        merged_int = np.logical_or.reduceat(int_arr[members], offsets[:-1]).tolist() if G else []
+    for g in np.nonzero(sizes > 1)[0].tolist():         # real merges: the reference's scalar arithmetic, literally
+        score_avg = 0
+        for k in members[offsets[g]:offsets[g + 1]].tolist():
+            score_avg += det_score[k]
+        score_avg *= 1. / int(sizes[g])
+        merged_score[g] = score_avg
+    return (members, offsets), merged_cls, merged_score, merged_int, frame_comps.tolist()
+
+
 def _probe_f32_average():
     score_avg = 0
     score_avg += np.float32(0.8125)
@@ -649,6 +697,10 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
         mergeable = (touch != 0) & (cls_arr[pairs[:, 0]] == cls_arr[pairs[:, 1]]) & (iou >= merge_overlap_iou_thr)
         groups, merged_cls, merged_score, merged_int, merged_count = [], [], [], [], []
         any_int = any(det_int)
+        native = _native_merge(det_count, pairs, mergeable, det_cls, det_score, det_int, any_int) if _USE_NATIVE_GRAPH else None
+        if native is not None:
+            groups, merged_cls, merged_score, merged_int, merged_count = native
+            slices = ()
         for f, (lo, hi, base) in enumerate(slices):
             edges = np.nonzero(mergeable[lo:hi])[0]
             if len(edges):

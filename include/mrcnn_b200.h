@@ -301,6 +301,16 @@ int mrcnn_planes_unpack(const uint32_t* planes, int n_planes, int height, int wi
 int mrcnn_pixel_lists_adjacent(const int32_t* pixels, const int64_t* offsets, const int32_t* pairs, int n_pairs,
                                int32_t* adjacent, void* stream);
 
+/* HOST-ONLY (no device work): the merge graph of Analyzer.extract_det_masks (mrcnn/analyze.py:1258-1320, mrcnn/graph.py)
+ * for a batch of frames.  det_count [n_frames] masks per frame (global indices are frame-major); pairs [n_pairs,2]
+ * global indices in the reference's pair-loop order, mergeable [n_pairs] (0/1).  Output, all HOST: members [sum
+ * det_count] and offsets [sum det_count + 1] = the connected components in the reference's order (by smallest vertex;
+ * members in recursive depth-first pre-order over insertion-ordered adjacency lists), frame_components [n_frames] =
+ * components per frame, *n_components. */
+int mrcnn_host_merge_components(int n_frames, const int32_t* det_count, const int32_t* pairs, const uint8_t* mergeable,
+                                int64_t n_pairs, int32_t* members, int32_t* offsets, int32_t* frame_components,
+                                int32_t* n_components);
+
 #ifdef __cplusplus
 }
 #endif

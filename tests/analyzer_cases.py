@@ -131,6 +131,9 @@ class NumpyPlaneOps:
         return _Arr(inter), _Arr(touch)
 
     def union(self, pl, H, W, groups):
+        if isinstance(groups, tuple):
+            members, offsets = groups
+            groups = [members[offsets[i]:offsets[i + 1]] for i in range(len(offsets) - 1)]
         return _Arr(np.stack([np.any(pl.a[g], axis=0) for g in groups]) if groups else np.zeros((0, H, W), bool))
 
     def gather(self, pl, index):

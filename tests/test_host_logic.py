@@ -345,3 +345,54 @@ def test_analyzer_host_logic_reproduces_reference_goldens_with_numpy_backend():
         assert got == want, (case["name"], case["options"], case["origin"])
         done += 1
     assert done >= 30
+
+
+def test_native_merge_components_reproduces_the_reference_graph_order():
+    """mrcnn_host_merge_components (host-only C++) == mrcnn/graph.py semantics (oracle Graph) on random multi-frame
+    graphs: component order, member pre-order, components per frame."""
+    import ctypes
+    from mrcnn import _native, analyze as P
+    from oracle import analyze_ops as A
+    lib = _native.lib()
+    rng = np.random.default_rng(21)
+    for trial in range(60):
+        F = int(rng.integers(1, 6))
+        counts = [int(rng.integers(0, 15)) for _ in range(F)]
+        pairs, _ = P._all_pairs(counts)
+        mergeable = (rng.random(len(pairs)) < rng.choice([0.0, 0.05, 0.3, 1.0])).astype(np.uint8)
+        n = sum(counts)
+        members = np.full(n, -1, np.int32)
+        offsets = np.full(n + 1, -1, np.int32)
+        frame_comps = np.zeros(F, np.int32)
+        ncomp = ctypes.c_int32(-1)
+        counts_arr = np.asarray(counts, np.int32)
+        _native.check(lib.mrcnn_host_merge_components(F, counts_arr.ctypes.data, pairs.ctypes.data if len(pairs) else None,
+                                                      mergeable.ctypes.data if len(pairs) else None, len(pairs),
+                                                      members.ctypes.data, offsets.ctypes.data, frame_comps.ctypes.data,
+                                                      ctypes.byref(ncomp)), "merge_components")
+        want, want_frames, base, pos = [], [], 0, 0
+        for c in counts:
+            g = A.Graph(c)
+            npairs = c * (c - 1) // 2
+            for k in np.nonzero(mergeable[pos:pos + npairs])[0]:
+                g.add_edge(int(pairs[pos + k, 0]) - base, int(pairs[pos + k, 1]) - base)
+            cc = g.connected_components()
+            want += [[base + v for v in comp] for comp in cc]
+            want_frames.append(len(cc))
+            base += c
+            pos += npairs
+        got = [members[offsets[i]:offsets[i + 1]].tolist() for i in range(ncomp.value)]
+        assert got == want and frame_comps.tolist() == want_frames and ncomp.value == len(want)
+
+
+def test_native_graph_mode_gives_the_same_catalogues(monkeypatch):
+    """MRCNN_B200_NATIVE_GRAPH=1 (merge graph in C++) == the default Python walk: reference goldens and the random
+    multi-frame comparison against the oracle are replayed with the switch on."""
+    from mrcnn import analyze as P
+    monkeypatch.setattr(P, "_USE_NATIVE_GRAPH", True)
+    calls = []
+    real = P._native_merge
+    monkeypatch.setattr(P, "_native_merge", lambda *a: (calls.append(1), real(*a))[1])
+    test_analyzer_host_logic_reproduces_reference_goldens_with_numpy_backend()
+    test_analyzer_host_pipeline_matches_oracle_with_numpy_backend()
+    assert len(calls) > 30
