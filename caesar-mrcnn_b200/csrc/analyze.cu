@@ -16,6 +16,8 @@
 // each component's first pixel) is a union-find over pixels with the smallest raster index as the root,
 // followed by a raster-order ranking of the roots.  Everything is bit-exact integer work; all kernels
 // are HBM/L2-bound streaming passes over words.
+// Also here: the 8-connected pixel-list adjacency test of the tile driver (SFinder.merge_edge_sources,
+// mrcnn/sfinder.py:787-808).  The host-only merge-graph routine lives in host_graph.cu.
 #include <climits>
 
 #include "common.cuh"
