@@ -52,8 +52,9 @@ def _oracle_cfg():
                 DETECTION_NMS_THRESHOLD=0.3, DETECTION_MAX_INSTANCES=100, POOL_SIZE=7, MASK_POOL_SIZE=14)
 
 
-def cpu_detect_images(maps, weights, threads):
-    """The reference detect path restated on the CPU (oracle): read_fits stretch -> mold -> graph -> unmold."""
+def cpu_detect_images(maps, weights, threads, keep=None):
+    """The reference detect path restated on the CPU (oracle): read_fits stretch -> mold -> graph -> unmold.
+    keep: optional list that receives (detections [D,6], detect()-style dict) per image (parity check)."""
     from oracle import host_ops as H, network as N
     net = N.OracleNet(weights, 4, emulate_bf16=False, threads=threads)
     anchors = H.get_anchors((S, S, 3), (4, 8, 16, 32, 64))
@@ -63,8 +64,37 @@ def cpu_detect_images(maps, weights, threads):
         molded, metas, windows = H.mold_inputs([img], min_dim=S, max_dim=S, min_scale=0, mode="square",
                                                mean_pixel=np.array([0, 0, 0]), num_classes=4)
         out = net.predict(molded, metas, anchors, _oracle_cfg())
-        H.unmold_detections(out["detections"][0], out["mrcnn_mask"][0], img.shape, (S, S, 3), windows[0])
+        b, c, sc, mk = H.unmold_detections(out["detections"][0], out["mrcnn_mask"][0], img.shape, (S, S, 3), windows[0])
+        if keep is not None:
+            keep.append((out["detections"][0], {"rois": b, "class_ids": c, "scores": sc, "masks": mk}))
     return time.perf_counter() - t0
+
+
+MAPS_TOTAL = 4096          # BASELINE.json configs[3]: the multi-GPU job is 4096 maps in contiguous shards
+
+
+def job_maps(first, count):
+    """Maps [first, first+count) of the 4096-map job: 256 generated radio maps x 16 rigid variants (8 dihedral x
+    a half-frame roll) — all distinct frames with the same source statistics, without 68 s of map synthesis."""
+    import synth
+    base = {}
+    out = np.empty((count, S, S), dtype=np.float32)
+    for k in range(count):
+        g = first + k
+        b, v = g % 256, g // 256
+        if b not in base:
+            base[b] = synth.radio_map(b, S)
+        m = base[b]
+        if v & 1:
+            m = m[::-1, :]
+        if v & 2:
+            m = m[:, ::-1]
+        if v & 4:
+            m = m.T
+        if v & 8:
+            m = np.roll(m, S // 2, axis=1)
+        out[k] = m
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -217,17 +247,34 @@ def main():
     model.set_profiling(2)          # CUDA events where the kernel family changes (~35 per step), read after the timed loop
     lib = _native.lib()
 
-    # distinct input batches per step (rotated) so no step re-reads the previous step's inputs from L2;
+    # distinct input batches per step so no step re-reads the previous step's inputs from L2;
     # the per-step working set (~12 GB of activations) is ~100x the 126 MB L2 anyway
-    n_sets = 4
-    base = synth.radio_maps(B, S, start=1000 * rank)
     host_sets, dev_sets = [], []
-    for k in range(n_sets):
-        arr = np.roll(base, k * 7, axis=0).copy()
-        if k % 2:
-            arr = arr[:, ::-1, :].copy()
-        t = torch.from_numpy(arr).pin_memory()
-        host_sets.append(t)
+    if world == 1:
+        # configs[1]: 64 maps; 4 rotated / mirrored copies of the batch are cycled
+        n_sets = 4
+        base = synth.radio_maps(B, S, start=0)
+        for k in range(n_sets):
+            arr = np.roll(base, k * 7, axis=0).copy()
+            if k % 2:
+                arr = arr[:, ::-1, :].copy()
+            host_sets.append(torch.from_numpy(arr).pin_memory())
+        shard = (0, B)
+    else:
+        # configs[3]: rank r owns the contiguous shard [start, stop) of the 4096-map job and walks its batches
+        # (cyclically when --steps exceeds the shard's batch count); no collective on the data path
+        from mrcnn import sharding
+        shard = sharding.shard_range(MAPS_TOTAL, rank, world)
+        plan = [bt for bt in sharding.batches(shard[0], shard[1], B) if bt[1] == B]
+        plan = plan[:max(4, min(len(plan), args.steps))]
+        base = None
+        for first, count in plan:
+            arr = job_maps(first, count)
+            if base is None:
+                base = arr
+            host_sets.append(torch.from_numpy(arr).pin_memory())
+        n_sets = len(host_sets)
+    for t in host_sets:
         dev_sets.append(t.cuda())
     stream = model._stream
 
@@ -308,7 +355,9 @@ def main():
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     D = 100
     h2d = B * S * S * 4 + B * 16 * 4 + B * 16
-    d2h = B * (D * 4 * 4 + D * 4 + D * 4 + 4) + B * S * S * D
+    # boxes / class ids / scores / counts + the pixel-major mask bits (16 B per pixel for D = 100); the [H,W,N] bool
+    # arrays of the reference contract are expanded from the bits on the host inside the timed region
+    d2h = B * (D * 4 * 4 + D * 4 + D * 4 + 4) + B * S * S * 4 * lib.mrcnn_mask_bits_words(D)
 
     # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM convolutions) ---------------
     peaks = _peaks()
@@ -343,8 +392,13 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "image_size": S, "num_classes": 4, "weights": "seeded random (LFS pointer unresolved)",
-                       "l2": "4 rotated input batches; per-step working set (activations) is GBs >> 126 MB L2", "parallelism": "batch-sharded, no collective", "cpu_affinity": numa},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                       "l2": "%d distinct input batches cycled; per-step working set (activations) is GBs >> 126 MB L2" % n_sets,
+                       "parallelism": "batch-sharded, no collective", "cpu_affinity": numa,
+                       "maps_total": B if world == 1 else MAPS_TOTAL, "shard_of_rank0": list(shard),
+                       "host_threads": int(lib.mrcnn_host_threads())},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "masks": "shipped as pixel-major bits, expanded to [H,W,N] bool on the host (%d threads) inside the timed region"
+                             % int(lib.mrcnn_host_threads())},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_families": stages,
             "stage_ms_per_step": {k: v / nprof for k, v in st_acc.items()},
             "detections_in_last_batch": int(sum(len(r["class_ids"]) for r in e2e_results[0]))}
@@ -356,9 +410,22 @@ def main():
         torch.set_num_threads(threads)
         sample = 4
         cpu_detect_images(base[:1], weights, threads)            # warm-up (page-in, thread pool)
-        t = cpu_detect_images(base[:sample], weights, threads)
+        kept = []
+        t = cpu_detect_images(base[:sample], weights, threads, keep=kept)
         line["cpu_baseline"] = {"value": sample / t, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "%d of the 64 maps, fp32 oracle restatement of the reference path (TF1 unavailable)" % sample}
+        # the same 4 maps through the engine (bf16) against the fp32 oracle run just timed: final detections
+        import parity_metrics as PM
+        res = model.detect_maps(base)
+        det = model.read_tensor("detections")
+        m_det = [PM.match_detections_tensor(det[i], kept[i][0], S) for i in range(sample)]
+        m_res = [PM.match_results(res[i], kept[i][1]) for i in range(sample)]
+        sd, sr = PM.summarize(m_det), PM.summarize(m_res)
+        line["parity_vs_fp32"] = {"images": sample, "matched_frac": sd["matched_frac"], "dbox_px_median": sd.get("dbox_px_median"),
+                                  "dbox_px_p95": sd.get("dbox_px_p95"), "dscore_median": sd.get("dscore_median"),
+                                  "dscore_p95": sd.get("dscore_p95"), "mask_iou_median": sr.get("mask_iou_median"),
+                                  "mask_iou_ge_0.9_frac": sr.get("mask_iou_ge_0.9_frac"),
+                                  "note": "bf16 engine vs fp32 CPU oracle, same maps and weights (tests/test_gpu_e2e_parity.py asserts the bounds)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

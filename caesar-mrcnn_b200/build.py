@@ -30,8 +30,12 @@ PER_FILE = {
 }
 
 
+LAST_BUILD = {}
+
+
 def _sources():
-    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    """*.cu: device + host code through nvcc; *.cpp: host-only translation units (nvcc hands them to g++ unchanged)."""
+    return sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
 
 
 def _stamp(src, flags):
@@ -50,7 +54,7 @@ def _stamp(src, flags):
 
 def _compile(src, verbose):
     flags = ARCH + COMMON + PER_FILE.get(src, [])
-    obj = os.path.join(OBJDIR, src[:-3] + ".o")
+    obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
     stamp_file = obj + ".stamp"
     stamp = _stamp(src, flags)
     if os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
@@ -77,9 +81,16 @@ def build(verbose=False, force=False):
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         results = list(ex.map(lambda s: _compile(s, verbose), srcs))
     objs = [o for o, _ in results]
-    if any(changed for _, changed in results) or not os.path.exists(LIB):
+    compiled = sum(1 for _, changed in results if changed)
+    relinked = False
+    if compiled or not os.path.exists(LIB):
         cmd = ["nvcc"] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
         subprocess.check_call(cmd)
+        relinked = True
+    # what this call actually did (objects are content-stamped: source + headers + flags)
+    LAST_BUILD.update({"sources": len(srcs), "compiled": compiled, "reused": len(srcs) - compiled, "relinked": relinked})
+    print("mrcnn_b200 build: %d sources, compiled %d / reused %d, %s %s" % (
+        len(srcs), compiled, len(srcs) - compiled, "linked" if relinked else "kept", os.path.relpath(LIB, ROOT)), file=sys.stderr)
     return LIB
 
 

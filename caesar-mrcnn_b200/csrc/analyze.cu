@@ -28,10 +28,12 @@ void mrcnn_count_launch(unsigned long long n);
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kMaxGridY = 65535;   // per-plane / per-group work rides on gridDim.y; the launchers chunk beyond this
 
 __device__ __forceinline__ int words_per_row(int W) { return (W + 31) >> 5; }
 
 // ---- pack: [B,H,W,D] uint8 (the [H,W,N] layout of detect(), N padded to D) -> selected bit-planes ----
+// General-shape variant (any depth / alignment; masks_pack4_kernel below is the fast path for depth % 4 == 0).
 // grid (WW, H, B).  The CTA stages the 32-pixel x D-byte tile with coalesced loads, then each warp
 // ballots one detection at a time (row stride D bytes: conflict-free for odd D/4, 2-way at worst).
 __global__ void masks_pack_kernel(const uint8_t* __restrict__ masks, int H, int W, int D,
@@ -531,8 +533,13 @@ extern "C" int mrcnn_planes_union(const uint32_t* planes, int height, int width,
   if (n_groups == 0) return MRCNN_OK;
   MRCNN_REQUIRE(planes && members && offsets && out, "planes_union: null pointer");
   RC(check_frame(height, width, "planes_union"));
-  MRCNN_REQUIRE(n_groups <= 65535, "planes_union: too many groups (%d)", n_groups);
   const size_t words = mrcnn_plane_words(height, width);
+  if (n_groups > kMaxGridY) {            // groups ride on gridDim.y: larger batches go in chunks
+    for (int g0 = 0; g0 < n_groups; g0 += kMaxGridY)
+      RC(mrcnn_planes_union(planes, height, width, members, offsets + g0, n_groups - g0 < kMaxGridY ? n_groups - g0 : kMaxGridY,
+                            out + (size_t)g0 * words, stream));
+    return MRCNN_OK;
+  }
   const int bx = (int)((words + kThreads - 1) / kThreads < 1024 ? (words + kThreads - 1) / kThreads : 1024);
   MRCNN_CHECK_CUDA(mrcnn_launch(planes_union_kernel, dim3(bx, n_groups), dim3(kThreads), 0, (cudaStream_t)stream, planes,
                                 words, members, offsets, out));
@@ -550,9 +557,17 @@ extern "C" int mrcnn_planes_label(const uint32_t* planes, int n_planes, int heig
   if (n_planes == 0) return MRCNN_OK;
   MRCNN_REQUIRE(planes && labels && counts && workspace, "planes_label: null pointer");
   RC(check_frame(height, width, "planes_label"));
-  MRCNN_REQUIRE(n_planes <= 65535, "planes_label: too many planes (%d)", n_planes);
   MRCNN_REQUIRE(workspace_bytes >= mrcnn_planes_label_workspace_bytes(n_planes, height, width),
                 "planes_label: workspace too small");
+  if (n_planes > kMaxGridY) {
+    const size_t words = mrcnn_plane_words(height, width), npix = (size_t)height * width;
+    for (int m0 = 0; m0 < n_planes; m0 += kMaxGridY) {
+      const int cnt = n_planes - m0 < kMaxGridY ? n_planes - m0 : kMaxGridY;
+      RC(mrcnn_planes_label(planes + (size_t)m0 * words, cnt, height, width, labels + (size_t)m0 * npix, counts + m0,
+                            static_cast<int32_t*>(workspace) + (size_t)m0 * npix, (size_t)cnt * npix * sizeof(int32_t), stream));
+    }
+    return MRCNN_OK;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const int n = height * width, WW = (width + 31) / 32;
   dim3 gpix((n + kThreads - 1) / kThreads, n_planes), gword((height * WW + kThreads - 1) / kThreads, n_planes);
@@ -573,8 +588,13 @@ extern "C" int mrcnn_labels_select(const int32_t* labels, int height, int width,
   if (n_out == 0) return MRCNN_OK;
   MRCNN_REQUIRE(labels && src && comp && planes_out, "labels_select: null pointer");
   RC(check_frame(height, width, "labels_select"));
-  MRCNN_REQUIRE(n_out <= 65535, "labels_select: too many components (%d)", n_out);
   const int words = (int)mrcnn_plane_words(height, width);
+  if (n_out > kMaxGridY) {
+    for (int k0 = 0; k0 < n_out; k0 += kMaxGridY)
+      RC(mrcnn_labels_select(labels, height, width, src + k0, comp + k0, n_out - k0 < kMaxGridY ? n_out - k0 : kMaxGridY,
+                             planes_out + (size_t)k0 * words, stream));
+    return MRCNN_OK;
+  }
   const int wpb = kThreads / 32;
   MRCNN_CHECK_CUDA(mrcnn_launch(labels_select_kernel, dim3((words + wpb - 1) / wpb, n_out), dim3(kThreads), 0,
                                 (cudaStream_t)stream, labels, height, width, src, comp, planes_out));
@@ -599,8 +619,14 @@ extern "C" int mrcnn_planes_unpack(const uint32_t* planes, int n_planes, int hei
   if (n_planes == 0) return MRCNN_OK;
   MRCNN_REQUIRE(planes && out, "planes_unpack: null pointer");
   RC(check_frame(height, width, "planes_unpack"));
-  MRCNN_REQUIRE(n_planes <= 65535, "planes_unpack: too many planes (%d)", n_planes);
   const int n = height * width;
+  if (n_planes > kMaxGridY) {
+    const size_t words = mrcnn_plane_words(height, width);
+    for (int m0 = 0; m0 < n_planes; m0 += kMaxGridY)
+      RC(mrcnn_planes_unpack(planes + (size_t)m0 * words, n_planes - m0 < kMaxGridY ? n_planes - m0 : kMaxGridY, height, width,
+                             out + (size_t)m0 * n, stream));
+    return MRCNN_OK;
+  }
   MRCNN_CHECK_CUDA(mrcnn_launch(planes_unpack_kernel, dim3((n + kThreads - 1) / kThreads, n_planes), dim3(kThreads), 0,
                                 (cudaStream_t)stream, planes, height, width, out));
   mrcnn_count_launch(1);

@@ -731,354 +731,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 
 
 // ---------------------------------------------------------------------------------------------
-// CHAIN kernel: one persistent launch runs a whole sequence of layers that share the same M (the
-// bottleneck blocks b.. of a ResNet stage: 1x1 -> 3x3 -> 1x1 + residual, repeated), so the per-launch
-// fill / drain / wave-quantisation bubbles of ~20 us layers disappear: every CTA walks one global work
-// list (layer-major, then N-fastest tiles) and never idles at a layer boundary.  Correctness comes from
-// per-(layer, M tile) completion counters in global memory: the epilogue bumps done[l][m] once the tile's
-// TMA stores have completed (wait_group 0 + fence), and the producer of a tile of layer l+1 first waits
-// for the M tiles of layer l it reads (itself for a 1x1, itself +- radius for a 3x3 in im2col order).
-// All CTAs are co-resident (grid <= #SMs, one CTA per SM) and dependencies only point to earlier work
-// of the list, so the waits cannot deadlock; they are bounded (trap) like every other wait here.
-// Same tile machinery as conv_gemm_kernel<BLOCK_N, true>: TMA -> smem ring -> tcgen05.mma -> TMEM ->
-// shared-memory epilogue with TMA residual loads / output stores.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-template <int BLOCK_N>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) conv_chain_kernel(const ChainLayerDev* __restrict__ layers, int num_layers,
-                                                                      int m_tiles, int total_tiles, int* __restrict__ done) {
-  using Cfg = TileCfg<BLOCK_N, true>;
-  constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
-  unsigned char* base_ptr = smem_raw + (base_addr - raw_addr);
-  constexpr int RING_BYTES = STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES;
-  const uint32_t staging_base = base_addr + STAGES * Cfg::STAGE_BYTES;        // [8 warps][3][32 rows x 64 B]
-  const uint32_t bar_base = base_addr + RING_BYTES;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  auto res_bar = [&](int ew, int b) { return bar_base + 8u * (2 * STAGES + 4 + ew * 3 + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + RING_BYTES + 8 * (2 * STAGES + 4 + 24));
-  float* s_affine = reinterpret_cast<float*>(base_ptr + RING_BYTES + Cfg::BAR_BYTES);   // [2][2][BLOCK_N]
-
-  pdl_launch_dependents();
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 8);
-    }
-    for (int b = 0; b < 24; ++b) mbar_init(res_bar(b / 3, b % 3), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)Cfg::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
-
-  // work index w -> layer l (layers[l].tile_start is the prefix sum of tiles); l only ever moves forward
-  auto locate = [&](int w, int& l) {
-    while (l + 1 < num_layers && w >= __ldg(&layers[l + 1].tile_start)) ++l;
-  };
-  // bounded acquire-wait until counter[mm] >= need for mm in [lo, hi]
-  auto wait_done = [&](const int* cnt, int lo, int hi, int need, int l_dbg) {
-    for (int mm = lo; mm <= hi; ++mm) {
-      uint32_t spins = 0;
-      while (ld_acquire_gpu(cnt + mm) < need) {
-        if (++spins > 200000000u) {
-          printf("conv_chain: dependency timeout block %d layer %d m %d (have %d need %d)\n", blockIdx.x, l_dbg, mm,
-                 ld_acquire_gpu(cnt + mm), need);
-          __trap();
-        }
-      }
-    }
-    asm volatile("fence.proxy.async.global;" ::: "memory");   // TMA reads issued after this see the published tiles
-  };
-
-  if (warp == 0) {
-    // ===== TMA producer (warp converged, one elected lane issues) =====
-    uint32_t stage = 0, phase = 0;
-    int l = 0;
-    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
-      locate(w, l);
-      const ChainLayerDev& L = layers[l];
-      const int tile = w - L.tile_start;
-      const int n_tile = tile % L.n_tiles;
-      const int m_tile = tile / L.n_tiles;
-      // the M tiles of the previous layer this tile reads
-      if (L.dep_need > 0)
-        wait_done(done + (size_t)(l - 1) * m_tiles, max(0, m_tile - L.dep_radius), min(m_tiles - 1, m_tile + L.dep_radius),
-                  L.dep_need, l);
-      int w0 = m_tile * BLOCK_M, h0 = 0, n0 = 0;
-      const int im2col = L.im2col, pad = L.pad, kw = L.kw, cin_blocks = L.cin_blocks;
-      if (im2col) {
-        const long long m0 = (long long)m_tile * BLOCK_M;
-        const int hw = L.OH * L.OW;
-        n0 = (int)(m0 / hw);
-        const int rem = (int)(m0 - (long long)n0 * hw);
-        h0 = rem / L.OW - pad;
-        w0 = rem - (rem / L.OW) * L.OW - pad;
-      }
-      const int num_kb = L.taps * cin_blocks;
-      const int b_row = n_tile * BLOCK_N;
-      int cb = 0, sx = 0, r = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t a_dst = base_addr + stage * Cfg::STAGE_BYTES;
-        const uint32_t fb = full_bar(stage);
-        if (elect_one()) {
-          mbar_expect_tx(fb, Cfg::A_BYTES + Cfg::B_BYTES);
-          if (im2col)
-            tma_load_im2col_4d(a_dst, &L.tmap_a, fb, cb * BLOCK_K, w0, h0, n0, (uint16_t)sx, (uint16_t)r);
-          else
-            tma_load_4d(a_dst, &L.tmap_a, fb, cb * BLOCK_K, w0, 0, 0);
-          tma_load_2d(a_dst + Cfg::A_BYTES, &L.tmap_b, fb, kb * BLOCK_K, b_row);
-        }
-        __syncwarp();
-        if (++cb == cin_blocks) {
-          cb = 0;
-          if (++sx == kw) {
-            sx = 0;
-            ++r;
-          }
-        }
-        if (++stage == (uint32_t)STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                               ((uint32_t)(BLOCK_M >> 4) << 24);
-    uint32_t stage = 0, phase = 0, tcount = 0;
-    int l = 0;
-    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tcount) {
-      locate(w, l);
-      const int num_kb = __ldg(&layers[l].taps) * __ldg(&layers[l].cin_blocks);
-      const uint32_t acc = tcount & 1u;
-      const uint32_t aph = (tcount >> 1) & 1u;
-      mbar_wait(tmem_empty_bar(acc), aph ^ 1u);
-      tcgen05_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const uint32_t s = stage;
-        mbar_wait(full_bar(s), phase);
-        if (++stage == (uint32_t)STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
-        tcgen05_fence_after();
-        const uint32_t a_addr = base_addr + s * Cfg::STAGE_BYTES;
-        const uint64_t da = make_sw128_desc(a_addr);
-        const uint64_t db = make_sw128_desc(a_addr + Cfg::A_BYTES);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(s));
-          if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ===== epilogue: one shared-memory / TMA pipeline per warp (see conv_gemm_kernel<BLOCK_N, true>) =====
-    const int ew = warp - 2;
-    const int q = warp & 3;
-    const int half = ew >> 2;
-    const int et = threadIdx.x - 64;
-    constexpr int COLS_PER_WARP = BLOCK_N / 2;
-    constexpr int NCH = COLS_PER_WARP / 32;
-    const int c_begin = half * COLS_PER_WARP;
-    const bool elected = lane == 0;
-    const uint32_t warp_base = staging_base + (uint32_t)ew * 3u * Cfg::EPI_CHUNK_BYTES;
-    const uint32_t row_off = (uint32_t)lane * 64u;
-    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
-    const int row0 = q * 32;
-    uint32_t g = 0, tcount = 0;
-    uint32_t nl0 = 0u, nl1 = 0u, nl2 = 0u;   // residual loads consumed per staging buffer so far (mbarrier parity)
-    int l = 0;
-    // residual chunk loader (lane 0): the residual's producer tiles must have been published first
-    // `blocking` = false: only if the producer tiles are already published (a warp must never block on a tile it
-    // has itself not published yet: the prefetch for the next tile runs before this tile's publication)
-    auto load_residual = [&](const ChainLayerDev& LL, int ll, int m_t, int col, uint32_t nb, bool blocking) -> bool {
-      if (LL.res_layer >= 0) {
-        const int* cnt = done + (size_t)LL.res_layer * m_tiles;
-        if (blocking) {
-          wait_done(cnt, m_t, m_t, LL.res_need, ll);
-        } else {
-          if (ld_acquire_gpu(cnt + m_t) < LL.res_need) return false;
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-        }
-      }
-      mbar_expect_tx(res_bar(ew, nb), Cfg::EPI_CHUNK_BYTES);
-      tma_load_2d(warp_base + nb * Cfg::EPI_CHUNK_BYTES, &LL.tmap_res, res_bar(ew, nb), col, m_t * BLOCK_M + row0);
-      return true;
-    };
-    bool deferred = false;                    // lane 0: the first residual chunk of the coming tile is still to be loaded
-    if ((int)blockIdx.x < total_tiles) {      // residual of the very first chunk of this warp
-      int l0 = 0;
-      locate((int)blockIdx.x, l0);
-      const ChainLayerDev& L0 = layers[l0];
-      if (L0.has_res && elected) {
-        const int t0 = (int)blockIdx.x - L0.tile_start;
-        load_residual(L0, l0, t0 / L0.n_tiles, (t0 % L0.n_tiles) * BLOCK_N + c_begin, 0u, true);
-      }
-    }
-    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tcount) {
-      locate(w, l);
-      const ChainLayerDev& L = layers[l];
-      const int tile = w - L.tile_start;
-      const uint32_t acc = tcount & 1u;
-      const uint32_t aph = (tcount >> 1) & 1u;
-      const int n_tile = tile % L.n_tiles;
-      const int m_tile = tile / L.n_tiles;
-      const int col_base = n_tile * BLOCK_N;
-      const bool has_res = L.has_res != 0;
-      const bool relu = L.relu != 0;
-      // the next tile of this CTA: its first residual chunk is prefetched during this tile's last chunk
-      const int wn = w + gridDim.x;
-      int ln = l;
-      bool next_res = false;
-      int next_col = 0, next_m = 0;
-      if (wn < total_tiles) {
-        locate(wn, ln);
-        const ChainLayerDev& LN = layers[ln];
-        next_res = LN.has_res != 0;
-        const int tn = wn - LN.tile_start;
-        next_col = (tn % LN.n_tiles) * BLOCK_N + c_begin;
-        next_m = tn / LN.n_tiles;
-      }
-      if (deferred) {                         // lane 0 only: everything of the previous tile is published by now
-        load_residual(L, l, m_tile, col_base + c_begin, g % 3u, true);
-        deferred = false;
-      }
-      float* t_scale = s_affine + acc * (2 * BLOCK_N);
-      float* t_shift = t_scale + BLOCK_N;
-      for (int c = et; c < BLOCK_N; c += EPI_THREADS) {
-        const int ch = col_base + c;
-        t_scale[c] = ch < L.cout ? __ldg(L.scale + ch) : 0.f;
-        t_shift[c] = ch < L.cout ? __ldg(L.shift + ch) : 0.f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + (uint32_t)c_begin;
-      uint32_t vbuf[2][32];
-      mbar_wait(tmem_full_bar(acc), aph);
-      __syncwarp();
-      tcgen05_fence_after();
-      tmem_ld_32x32b_x32(t_addr, vbuf[0]);
-#pragma unroll
-      for (int ci = 0; ci < NCH; ++ci, ++g) {
-        const uint32_t b = g % 3u;
-        const uint32_t buf = warp_base + b * Cfg::EPI_CHUNK_BYTES;
-        // residual of chunk g+1 -> buffer (g+1)%3 (last read by the store of chunk g-2)
-        const bool last_ci = (ci + 1 == NCH);
-        const bool res_next = last_ci ? next_res : has_res;
-        const bool have_next = last_ci ? (wn < total_tiles) : true;
-        if (have_next && res_next && elected) {
-          bulk_wait_group_read<1>();
-          const uint32_t nb = (g + 1u) % 3u;
-          if (last_ci)
-            deferred = !load_residual(layers[ln], ln, next_m, next_col, nb, false);
-          else
-            load_residual(L, l, m_tile, col_base + c_begin + 32 * (ci + 1), nb, true);   // own tile: producers long done
-        }
-        if (has_res) {
-          const uint32_t cnt = b == 0u ? nl0 : (b == 1u ? nl1 : nl2);
-          mbar_wait(res_bar(ew, b), cnt & 1u);
-          nl0 += b == 0u ? 1u : 0u;            // identical bookkeeping in every lane
-          nl1 += b == 1u ? 1u : 0u;
-          nl2 += b == 2u ? 1u : 0u;
-        } else {
-          if (elected) bulk_wait_group_read<2>();          // the store of chunk g-3 has released this buffer
-          __syncwarp();
-        }
-        tmem_ld_wait();
-        if (ci + 1 < NCH) tmem_ld_32x32b_x32(t_addr + (uint32_t)(32 * (ci + 1)), vbuf[(ci + 1) & 1]);
-        const uint32_t* v = vbuf[ci & 1];
-        const int c = c_begin + 32 * ci;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t addr = buf + row_off + ((((uint32_t)j) ^ sw) << 4);
-          const float4 s0 = *reinterpret_cast<const float4*>(t_scale + c + j * 8);
-          const float4 s1 = *reinterpret_cast<const float4*>(t_scale + c + j * 8 + 4);
-          const float4 t0 = *reinterpret_cast<const float4*>(t_shift + c + j * 8);
-          const float4 t1 = *reinterpret_cast<const float4*>(t_shift + c + j * 8 + 4);
-          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-          float o[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] = fmaf(__uint_as_float(v[j * 8 + k]), sc[k], sh[k]);
-          if (has_res) {
-            const uint4 r4 = lds128(addr);
-            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              o[2 * k] += __uint_as_float(rw[k] << 16);
-              o[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
-            }
-          }
-          uint4 ov;
-          if (relu) {
-            ov = make_uint4(cvt_relu_bf16x2(o[0], o[1]), cvt_relu_bf16x2(o[2], o[3]), cvt_relu_bf16x2(o[4], o[5]),
-                            cvt_relu_bf16x2(o[6], o[7]));
-          } else {
-            ov = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-          }
-          sts128(addr, ov);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (elected) {
-          tma_store_2d(&L.tmap_out, buf, col_base + c, m_tile * BLOCK_M + row0);
-          bulk_commit_group();
-        }
-      }
-      // the accumulator is drained: hand it back to the MMA warp
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-      // publish this warp's part of the tile: its stores must have completed (not just been read from smem)
-      if (elected) {
-        bulk_wait_group_all();
-        __threadfence();
-        atomicAdd(done + (size_t)l * m_tiles + m_tile, 1);
-      }
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
-                 : "memory");
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // CUDA-core reference (tests only): same descriptor semantics, fp32 accumulation
 // ---------------------------------------------------------------------------------------------
 struct SimtParams {
@@ -1407,86 +1059,6 @@ int conv_plan_create_ex(const mrcnn_conv_desc* d, const void* x, const void* w, 
   return MRCNN_OK;
 }
 
-
-int conv_chain_create(ConvPlan* const* plans, int n, ConvChain* chain) {
-  MRCNN_REQUIRE(plans && chain && n >= 2, "conv_chain: need at least two layers");
-  const int bn = plans[0]->block_n;
-  MRCNN_REQUIRE(bn == 64 || bn == 128, "conv_chain: block_n must be 64 or 128");
-  const long long M = plans[0]->p.M;
-  std::vector<ChainLayerDev> h((size_t)n);
-  int start = 0;
-  double flops = 0.0;
-  for (int i = 0; i < n; ++i) {
-    const ConvPlan* pl = plans[i];
-    const ConvGemmParams& p = pl->p;
-    MRCNN_REQUIRE(pl->epi_tma && p.flat && pl->block_n == bn && p.out_mode == 0 && !p.out_f32 && p.M == M && !p.res_up2,
-                  "conv_chain: layer %d is not chainable", i);
-    ChainLayerDev& L = h[(size_t)i];
-    memset(&L, 0, sizeof(L));
-    L.tmap_a = pl->tmap_a; L.tmap_b = pl->tmap_b; L.tmap_out = pl->tmap_out; L.tmap_res = pl->tmap_res;
-    L.scale = p.scale; L.shift = p.shift;
-    L.taps = p.kh * p.kw; L.kw = p.kw; L.pad = p.pad; L.cin_blocks = p.cin_blocks;
-    L.n_tiles = p.n_tiles; L.im2col = p.im2col; L.relu = p.relu; L.has_res = p.residual != nullptr;
-    L.OH = p.OH; L.OW = p.OW; L.cout = p.cout;
-    L.dep_need = i == 0 ? 0 : 8 * plans[i - 1]->p.n_tiles;     // eight epilogue warps publish every (m, n) tile
-    L.res_layer = -1;                                           // residual produced inside the chain?
-    L.res_need = 0;
-    if (p.residual != nullptr)
-      for (int jj = 0; jj < i; ++jj)
-        if (plans[jj]->p.out == (void*)p.residual) {
-          L.res_layer = jj;
-          L.res_need = 8 * plans[jj]->p.n_tiles;
-        }
-    L.dep_radius = p.kh == 3 ? (p.OW + 1 + BLOCK_M - 1) / BLOCK_M : 0;
-    L.tile_start = start;
-    start += (int)((M + BLOCK_M - 1) / BLOCK_M) * p.n_tiles;
-    flops += pl->flops;
-  }
-  chain->num_layers = n;
-  chain->m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
-  chain->total_tiles = start;
-  chain->block_n = bn;
-  chain->flops = flops;
-  MRCNN_CHECK_CUDA(cudaMalloc((void**)&chain->d_layers, sizeof(ChainLayerDev) * (size_t)n));
-  MRCNN_CHECK_CUDA(cudaMemcpy(chain->d_layers, h.data(), sizeof(ChainLayerDev) * (size_t)n, cudaMemcpyHostToDevice));
-  MRCNN_CHECK_CUDA(cudaMalloc((void**)&chain->d_done, sizeof(int) * (size_t)n * chain->m_tiles));
-  return MRCNN_OK;
-}
-
-void conv_chain_destroy(ConvChain* chain) {
-  if (!chain) return;
-  if (chain->d_layers) cudaFree(chain->d_layers);
-  if (chain->d_done) cudaFree(chain->d_done);
-  chain->d_layers = nullptr;
-  chain->d_done = nullptr;
-}
-
-namespace {
-template <int BN> int launch_chain(const ConvChain* c, cudaStream_t st) {
-  using Cfg = TileCfg<BN, true>;
-  static bool attr_done[16] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 16 && !attr_done[dev]) {
-    MRCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_chain_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done[dev] = true;
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  // every CTA must be resident at once (the dependency waits rely on it): one CTA per SM, at most #SMs CTAs
-  const int grid = c->total_tiles < num_sms ? c->total_tiles : num_sms;
-  MRCNN_CHECK_CUDA(cudaMemsetAsync(c->d_done, 0, sizeof(int) * (size_t)c->num_layers * c->m_tiles, st));
-  MRCNN_CHECK_CUDA(mrcnn_launch(conv_chain_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st,
-                                (const ChainLayerDev*)c->d_layers, c->num_layers, c->m_tiles, c->total_tiles, c->d_done));
-  mrcnn_count_launch(1);
-  return MRCNN_OK;
-}
-}  // namespace
-
-int conv_chain_launch(const ConvChain* chain, cudaStream_t st) {
-  MRCNN_REQUIRE(chain && chain->d_layers, "conv_chain_launch: chain not created");
-  return chain->block_n == 64 ? launch_chain<64>(chain, st) : launch_chain<128>(chain, st);
-}
 
 int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, int nc2, void* out, int unit_scale) {
   MRCNN_REQUIRE(plan && w2 && b2 && out, "fuse_mask_logits: null pointer");

@@ -54,30 +54,4 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);
 // turns a 256-channel deconv plan (block_n 256) into deconv + ReLU + 1x1 conv (nc2) + sigmoid -> float32 out
 int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, int nc2, void* out, int unit_scale);
 
-// ---- chain of layers in one persistent launch (see conv_chain_kernel) -----------------------------------
-struct alignas(128) ChainLayerDev {
-  CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res;
-  const float* scale;
-  const float* shift;
-  int taps, kw, pad, cin_blocks;   // filter taps (kh*kw), filter width, padding, Cin / 64
-  int n_tiles, im2col, relu, has_res;
-  int OH, OW, cout;
-  int dep_need, dep_radius;        // wait until done[l-1][m-radius..m+radius] >= dep_need (0 = no wait)
-  int res_layer, res_need;         // residual = output of chain layer res_layer (-1: produced before the chain)
-  int tile_start;                  // first index of this layer in the global work list
-};
-
-struct ConvChain {
-  ChainLayerDev* d_layers = nullptr;
-  int* d_done = nullptr;           // [num_layers][m_tiles] completion counters, zeroed before every launch
-  int num_layers = 0, m_tiles = 0, total_tiles = 0, block_n = 128;
-  double flops = 0.0;
-};
-
-// plans: consecutive layers (each reads the previous one's output; a residual may come from any earlier layer or
-// from outside the chain), all created with the same block_n and the shared-memory/TMA epilogue, same M
-int conv_chain_create(ConvPlan* const* plans, int n, ConvChain* chain);
-int conv_chain_launch(const ConvChain* chain, cudaStream_t stream);
-void conv_chain_destroy(ConvChain* chain);
-
 void mrcnn_count_launch(unsigned long long n);

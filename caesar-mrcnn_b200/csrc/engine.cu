@@ -100,8 +100,6 @@ struct mrcnn_engine {
   // timing
   std::vector<std::string> stage_names;
   std::vector<cudaEvent_t> stage_events;  // stage_names.size() + 1
-  bool use_chain = false;                 // MRCNN_B200_CHAIN=1: ResNet stages as layer chains (one persistent launch each)
-  std::vector<ConvChain*> chains;
   bool use_graph = false;                 // replay the plan as a CUDA graph when not profiling (default: batch <= 16)
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_fresh = false;
@@ -126,7 +124,8 @@ struct mrcnn_engine {
   // result slots: unmold outputs are double-buffered so the D2H copy of step k (copy stream) can
   // overlap the compute of step k+1 (main stream) in the asynchronous detect calls
   struct ResultSlot {
-    void* masks = nullptr; size_t masks_bytes = 0;
+    void* masks = nullptr; size_t masks_bytes = 0;     // [B,H0,W0,D] uint8 (mask_format 0: device consumers, mrcnn.analyze)
+    void* bits = nullptr; size_t bits_bytes = 0;       // [B,H0*W0,DW] uint32 pixel-major bits (mask_format 1: host results)
     int32_t* rois = nullptr; int32_t* class_ids = nullptr; float* scores = nullptr; int32_t* counts = nullptr;
     cudaEvent_t computed = nullptr, copied = nullptr;
     bool copy_pending = false;
@@ -416,7 +415,7 @@ struct Act {   // NHWC bf16 activation
 
 int add_conv(mrcnn_engine* e, const std::string& stage, const std::string& wname, Act in, int k, int stride, int relu,
              const __nv_bfloat16* residual, int res_up2, const std::string& out_name, Act* out, int out_f32 = 0,
-             int out_ld = 0, int out_mode = 0, void** raw_out = nullptr, int force_bn = 0) {
+             int out_ld = 0, int out_mode = 0, void** raw_out = nullptr) {
   auto it = e->gemm.find(wname);
   if (it == e->gemm.end()) {
     mrcnn_set_error("engine: no GEMM weights for %s", wname.c_str());
@@ -441,18 +440,9 @@ int add_conv(mrcnn_engine* e, const std::string& stage, const std::string& wname
   if (rc) return rc;
   ConvPlan* plan = new ConvPlan();
   e->plans.push_back(plan);
-  if (force_bn > 0) {           // member of a layer chain: fixed tile width, shared-memory/TMA epilogue
-    rc = conv_plan_create_ex(&d, in.p, g.w, g.scale, g.shift, residual, t.ptr, force_bn, 1, plan);
-    if (rc) return rc;
-    if (!plan->epi_tma) {
-      mrcnn_set_error("engine: layer %s cannot join a chain", wname.c_str());
-      return MRCNN_ERR_INVALID;
-    }
-  } else {
   rc = conv_plan_create(&d, in.p, g.w, g.scale, g.shift, residual, t.ptr, 0, plan);
   if (rc) return rc;
-  }
-  if (e->autotune && force_bn == 0) {
+  if (e->autotune) {
     // optional on-disk cache of the choices (MRCNN_B200_AUTOTUNE_CACHE=<file>): a second process — e.g. the same
     // workload under ncu — builds exactly the same launch plan without re-timing (and without the timing launches)
     char key[160];
@@ -516,9 +506,6 @@ int build_graph(mrcnn_engine* e) {
 
   // ---- ResNet-101 stages 2..5 ----------------------------------------------------------------
   const int nblocks[4] = {3, 4, 23, 3};
-  const int chain_bn[4] = {64, 128, 128, 128};     // tile width shared by a stage's chain (res2 has 64-channel layers)
-  std::vector<ConvPlan*> chain_plans;
-  size_t chain_first_step = 0;
   Act C[6];
   for (int s = 0; s < 4; ++s) {
     for (int b = 0; b < nblocks[s]; ++b) {
@@ -526,33 +513,14 @@ int build_graph(mrcnn_engine* e) {
       const std::string base = "res" + std::to_string(s + 2) + blk + "_branch";
       const int stride = (b == 0 && s > 0) ? 2 : 1;
       Act y1, y2, sc, y3;
-      // chain members (MRCNN_B200_CHAIN): everything of the stage after block a's strided 2a / shortcut convs runs
-      // in ONE persistent launch with per-M-tile dependency counters (conv_chain_kernel)
-      const int cbn = e->use_chain ? chain_bn[s] : 0;
-      RC(add_conv(e, "backbone", base + "2a", x, 1, stride, 1, nullptr, 0, base + "2a_out", &y1, 0, 0, 0, nullptr, b == 0 ? 0 : cbn));
-      if (b > 0 && cbn) chain_plans.push_back(e->plans.back());
+      RC(add_conv(e, "backbone", base + "2a", x, 1, stride, 1, nullptr, 0, base + "2a_out", &y1));
       if (b == 0) RC(add_conv(e, "backbone", base + "1", x, 1, stride, 0, nullptr, 0, base + "1_out", &sc));
       else sc = x;
-      if (b == 0) chain_first_step = e->steps.size();
-      RC(add_conv(e, "backbone", base + "2b", y1, 3, 1, 1, nullptr, 0, base + "2b_out", &y2, 0, 0, 0, nullptr, cbn));
-      if (cbn) chain_plans.push_back(e->plans.back());
+      RC(add_conv(e, "backbone", base + "2b", y1, 3, 1, 1, nullptr, 0, base + "2b_out", &y2));
       const std::string oname = (b == nblocks[s] - 1) ? ("C" + std::to_string(s + 2)) : ("res" + std::to_string(s + 2) + blk + "_out");
-      RC(add_conv(e, "backbone", base + "2c", y2, 1, 1, 1, sc.p, 0, oname, &y3, 0, 0, 0, nullptr, cbn));
-      if (cbn) chain_plans.push_back(e->plans.back());
+      RC(add_conv(e, "backbone", base + "2c", y2, 1, 1, 1, sc.p, 0, oname, &y3));
       x = y3;
     }
-    if (e->use_chain && chain_plans.size() >= 2) {
-      ConvChain* chain = new ConvChain();
-      e->chains.push_back(chain);
-      RC(conv_chain_create(chain_plans.data(), (int)chain_plans.size(), chain));
-      // the members' own steps (contiguous from block a's 2b to the stage output) collapse into one chain step
-      e->steps.erase(e->steps.begin() + (long)chain_first_step, e->steps.end());
-      char label[96];
-      snprintf(label, sizeof(label), "res%d chain (%d layers, one launch)", s + 2, (int)chain_plans.size());
-      e->steps.push_back({"backbone", [chain](cudaStream_t st) { return conv_chain_launch(chain, st); }, "conv_gemm", label,
-                          chain->flops});
-    }
-    chain_plans.clear();
     C[s + 2] = x;
   }
 
@@ -800,7 +768,6 @@ extern "C" int mrcnn_engine_create(const mrcnn_engine_config* cfg, int device, m
   // (measured: B=1 2.07 -> 1.96 ms, B=8 3.05 -> 2.94 ms, B=64 neutral); MRCNN_B200_GRAPH=0/1 overrides
   e->use_graph = cfg->batch_size <= 16;
   if (const char* g = getenv("MRCNN_B200_GRAPH")) e->use_graph = g[0] == '1';
-  if (const char* c = getenv("MRCNN_B200_CHAIN")) e->use_chain = c[0] == '1';
   const char* at = getenv("MRCNN_B200_AUTOTUNE");
   e->autotune = !(at && at[0] == '0');
   if (const char* cp = getenv("MRCNN_B200_AUTOTUNE_CACHE")) {
@@ -826,10 +793,6 @@ extern "C" void mrcnn_engine_destroy(mrcnn_engine* e) {
     if (p->w2_table) cudaFree(p->w2_table);
     delete p;
   }
-  for (ConvChain* c : e->chains) {
-    conv_chain_destroy(c);
-    delete c;
-  }
   for (auto ev : e->stage_events) cudaEventDestroy(ev);
   for (auto ev : e->step_events) cudaEventDestroy(ev);
   if (e->unmold_ws) cudaFree(e->unmold_ws);
@@ -837,6 +800,7 @@ extern "C" void mrcnn_engine_destroy(mrcnn_engine* e) {
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   for (auto& sl : e->slots) {
     if (sl.masks) cudaFree(sl.masks);
+    if (sl.bits) cudaFree(sl.bits);
     if (sl.computed) cudaEventDestroy(sl.computed);
     if (sl.copied) cudaEventDestroy(sl.copied);
   }
@@ -979,6 +943,14 @@ extern "C" int mrcnn_engine_tensor(const mrcnn_engine* e, const char* name, void
     MRCNN_REQUIRE(e->slots[slot].masks, "engine_tensor: '%s' has not been produced yet", name);
     if (device_ptr) *device_ptr = e->slots[slot].masks;
     if (bytes) *bytes = e->slots[slot].masks_bytes;
+    return MRCNN_OK;
+  }
+  if (!strncmp(name, "unmold_mask_bits", 16)) {   // [B,H0*W0,DW] uint32 of result slot 0 / 1
+    const int slot = !strcmp(name + 16, "#1") ? 1 : 0;
+    MRCNN_REQUIRE(name[16] == 0 || slot == 1, "engine_tensor: unknown tensor '%s'", name);
+    MRCNN_REQUIRE(e->slots[slot].bits, "engine_tensor: '%s' has not been produced yet", name);
+    if (device_ptr) *device_ptr = e->slots[slot].bits;
+    if (bytes) *bytes = e->slots[slot].bits_bytes;
     return MRCNN_OK;
   }
   auto it = e->tensors.find(name);
@@ -1183,17 +1155,18 @@ static int ensure_scratch(mrcnn_engine* e, void** ptr, size_t* have, size_t need
   return MRCNN_OK;
 }
 
-static int unmold_internal(mrcnn_engine* e, int slot, const int* orig_hw, const int32_t* windows_host) {
+static int unmold_internal(mrcnn_engine* e, int slot, const int* orig_hw, const int32_t* windows_host, int mask_format) {
   const mrcnn_engine_config& c = e->cfg;
   const int B = c.batch_size, D = c.detection_max_instances;
   mrcnn_engine::ResultSlot& sl = e->slots[slot];
   RC(ensure_scratch(e, &e->unmold_ws, &e->unmold_ws_bytes, mrcnn_unmold_workspace_bytes(B, D)));
-  const size_t mbytes = (size_t)B * orig_hw[0] * orig_hw[1] * D;
   if (sl.copy_pending) {                       // the slot's previous D2H must be complete before it is overwritten
     MRCNN_CHECK_CUDA(cudaEventSynchronize(sl.copied));
     sl.copy_pending = false;
   }
-  RC(ensure_scratch(e, &sl.masks, &sl.masks_bytes, mbytes));
+  const size_t npx = (size_t)orig_hw[0] * orig_hw[1];
+  if (mask_format == 0) RC(ensure_scratch(e, &sl.masks, &sl.masks_bytes, (size_t)B * npx * D));
+  else RC(ensure_scratch(e, &sl.bits, &sl.bits_bytes, (size_t)B * npx * mrcnn_mask_bits_words(D) * 4));
   if (!e->d_windows) MRCNN_CHECK_CUDA(cudaMalloc((void**)&e->d_windows, (size_t)B * 16));
   if (!sl.rois) {
     const std::string sfx = slot == 0 ? "" : "#1";
@@ -1207,20 +1180,24 @@ static int unmold_internal(mrcnn_engine* e, int slot, const int* orig_hw, const 
   }
   MRCNN_CHECK_CUDA(cudaMemcpyAsync(e->d_windows, windows_host, (size_t)B * 16, cudaMemcpyHostToDevice, e->stream));
   const int image_hw[2] = {c.image_size, c.image_size};
-  return mrcnn_unmold_detections(static_cast<const float*>(e->tensors["detections"].ptr),
-                                 static_cast<const float*>(e->tensors["mrcnn_mask"].ptr), B, D, 2 * c.mask_pool_size,
-                                 2 * c.mask_pool_size, c.num_classes, orig_hw, image_hw, e->d_windows, sl.rois, sl.class_ids,
-                                 sl.scores, sl.counts, static_cast<uint8_t*>(sl.masks), e->unmold_ws, e->unmold_ws_bytes,
-                                 e->stream);
+  const float* det = static_cast<const float*>(e->tensors["detections"].ptr);
+  const float* mm = static_cast<const float*>(e->tensors["mrcnn_mask"].ptr);
+  if (mask_format == 0)
+    return mrcnn_unmold_detections(det, mm, B, D, 2 * c.mask_pool_size, 2 * c.mask_pool_size, c.num_classes, orig_hw, image_hw,
+                                   e->d_windows, sl.rois, sl.class_ids, sl.scores, sl.counts, static_cast<uint8_t*>(sl.masks),
+                                   e->unmold_ws, e->unmold_ws_bytes, e->stream);
+  return mrcnn_unmold_detections_bits(det, mm, B, D, 2 * c.mask_pool_size, 2 * c.mask_pool_size, c.num_classes, orig_hw, image_hw,
+                                      e->d_windows, sl.rois, sl.class_ids, sl.scores, sl.counts, static_cast<uint32_t*>(sl.bits),
+                                      e->unmold_ws, e->unmold_ws_bytes, e->stream);
 }
 
 // D2H of one slot's results.  async: on the copy stream after the compute of this step (recorded event),
 // so the main stream is free to start the next step; otherwise on the main stream.
 static int fetch_internal(mrcnn_engine* e, int slot, bool async, const int* orig_hw, int32_t* rois_host,
-                          int32_t* class_ids_host, float* scores_host, int32_t* counts_host, uint8_t* masks_host) {
+                          int32_t* class_ids_host, float* scores_host, int32_t* counts_host, uint32_t* mask_bits_host) {
   const mrcnn_engine_config& c = e->cfg;
   const int B = c.batch_size, D = c.detection_max_instances;
-  const size_t mbytes = (size_t)B * orig_hw[0] * orig_hw[1] * D;
+  const size_t mbytes = (size_t)B * orig_hw[0] * orig_hw[1] * mrcnn_mask_bits_words(D) * 4;
   mrcnn_engine::ResultSlot& sl = e->slots[slot];
   cudaStream_t st = e->stream;
   if (async) {
@@ -1233,7 +1210,7 @@ static int fetch_internal(mrcnn_engine* e, int slot, bool async, const int* orig
   if (class_ids_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(class_ids_host, sl.class_ids, (size_t)B * D * 4, cudaMemcpyDeviceToHost, st));
   if (scores_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(scores_host, sl.scores, (size_t)B * D * 4, cudaMemcpyDeviceToHost, st));
   if (counts_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(counts_host, sl.counts, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  if (masks_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(masks_host, sl.masks, mbytes, cudaMemcpyDeviceToHost, st));
+  if (mask_bits_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(mask_bits_host, sl.bits, mbytes, cudaMemcpyDeviceToHost, st));
   if (async) {
     MRCNN_CHECK_CUDA(cudaEventRecord(sl.copied, e->copy_stream));
     sl.copy_pending = true;
@@ -1267,14 +1244,14 @@ extern "C" int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, 
                                           const float* metas_host, const int* orig_hw,
                                           const int32_t* windows_host, int32_t* rois_host,
                                           int32_t* class_ids_host, float* scores_host, int32_t* counts_host,
-                                          uint8_t* masks_host) {
+                                          uint32_t* mask_bits_host) {
   MRCNN_REQUIRE(e && e->finalized, "detect_molded: engine not finalized");
   MRCNN_REQUIRE(molded && metas_host && orig_hw && windows_host, "detect_molded: null pointer");
   MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
   RC(predict_internal(e, molded, molded_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, metas_host,
                       cudaMemcpyHostToDevice));
-  RC(unmold_internal(e, 0, orig_hw, windows_host));
-  RC(fetch_internal(e, 0, false, orig_hw, rois_host, class_ids_host, scores_host, counts_host, masks_host));
+  RC(unmold_internal(e, 0, orig_hw, windows_host, 1));
+  RC(fetch_internal(e, 0, false, orig_hw, rois_host, class_ids_host, scores_host, counts_host, mask_bits_host));
   MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
   return MRCNN_OK;
 }
@@ -1283,8 +1260,10 @@ extern "C" int mrcnn_engine_detect_maps(mrcnn_engine* e, const float* maps, int 
                                         const float* contrasts3, const float* mean_pixel3, int out_h, int out_w,
                                         int top, int left, const float* metas_host, const int32_t* windows_host,
                                         int32_t* rois_host, int32_t* class_ids_host, float* scores_host,
-                                        int32_t* counts_host, uint8_t* masks_host, int async) {
+                                        int32_t* counts_host, uint32_t* mask_bits_host, int mask_format, int async) {
   MRCNN_REQUIRE(e && e->finalized, "detect_maps: engine not finalized");
+  MRCNN_REQUIRE(mask_format == 0 || mask_format == 1, "detect_maps: mask_format must be 0 (bytes, device only) or 1 (bits)");
+  MRCNN_REQUIRE(mask_format == 1 || !mask_bits_host, "detect_maps: host masks are shipped as bits (mask_format 1)");
   MRCNN_REQUIRE(maps && contrasts3 && mean_pixel3 && metas_host && windows_host, "detect_maps: null pointer");
   MRCNN_REQUIRE(map_h > 0 && map_w > 0, "detect_maps: empty maps");
   MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
@@ -1308,16 +1287,16 @@ extern "C" int mrcnn_engine_detect_maps(mrcnn_engine* e, const float* maps, int 
   RC(mrcnn_resize_pad_mold(d_rgb, d_minmax, B, map_h, map_w, out_h, out_w, c.image_size, top, left, mean_pixel3, d_img, e->stream));
   RC(predict_internal(e, d_img, cudaMemcpyDeviceToDevice, metas_host, cudaMemcpyHostToDevice));
   const int orig_hw[2] = {map_h, map_w};
-  const bool any_out = rois_host || class_ids_host || scores_host || counts_host || masks_host;
+  const bool any_out = rois_host || class_ids_host || scores_host || counts_host || mask_bits_host;
   const int slot = (async && any_out) ? e->cur_slot : 0;
-  RC(unmold_internal(e, slot, orig_hw, windows_host));
+  RC(unmold_internal(e, slot, orig_hw, windows_host, mask_format));
   if (async && any_out) {
-    RC(fetch_internal(e, slot, true, orig_hw, rois_host, class_ids_host, scores_host, counts_host, masks_host));
+    RC(fetch_internal(e, slot, true, orig_hw, rois_host, class_ids_host, scores_host, counts_host, mask_bits_host));
     e->cur_slot ^= 1;
     return MRCNN_OK;                 // caller collects with mrcnn_engine_wait()
   }
   if (async) return MRCNN_OK;        // device-only and asynchronous: results stay in the unmold_* tensors, no sync
-  RC(fetch_internal(e, slot, false, orig_hw, rois_host, class_ids_host, scores_host, counts_host, masks_host));
+  RC(fetch_internal(e, slot, false, orig_hw, rois_host, class_ids_host, scores_host, counts_host, mask_bits_host));
   MRCNN_CHECK_CUDA(cudaStreamSynchronize(e->stream));
   return MRCNN_OK;
 }

@@ -373,6 +373,47 @@ __global__ void resize_pad_mold_kernel(MoldParams p) {
   }
 }
 
+
+// skimage.transform.resize(order=1, mode='constant', cval=0, clip=True, anti_aliasing=False) for a float64 [H,W,C]
+// image (scikit-image <= 0.15 affine warp; same arithmetic, op for op, as resize_pad_mold_kernel / unmold_paint_kernel)
+struct ResizeParams {
+  const double* src;
+  double* dst;
+  int H, W, C, out_h, out_w;
+  double mn, mx;
+};
+
+__global__ void skimage_resize_kernel(ResizeParams p) {
+  pdl_prologue();
+  const size_t total = (size_t)p.out_h * p.out_w * p.C;
+  const double row_scale = (double)p.H / (double)p.out_h;
+  const double col_scale = (double)p.W / (double)p.out_w;
+  const bool single = (p.out_h == 1 && p.out_w == 1);        // skimage uses a translation-only transform for a 1x1 output
+  const double row_off = __dsub_rn(__dmul_rn(0.5, row_scale), 0.5);
+  const double col_off = __dsub_rn(__dmul_rn(0.5, col_scale), 0.5);
+  const bool preserve_cval = !(p.mn <= 0.0 && 0.0 <= p.mx);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % p.C);
+    const size_t px = i / p.C;
+    const int x = (int)(px % p.out_w), y = (int)(px / p.out_w);
+    const double r = single ? __dsub_rn((double)p.H / 2.0, 0.5) : __dadd_rn(__dmul_rn(row_scale, (double)y), row_off);
+    const double cc = single ? __dsub_rn((double)p.W / 2.0, 0.5) : __dadd_rn(__dmul_rn(col_scale, (double)x), col_off);
+    const double fr = floor(r), fc = floor(cc);
+    const int r0 = (int)fr, r1 = (int)ceil(r), c0 = (int)fc, c1 = (int)ceil(cc);
+    const double dr = __dsub_rn(r, fr), dc = __dsub_rn(cc, fc);
+    const double wr = __dsub_rn(1.0, dr), wc = __dsub_rn(1.0, dc);
+    auto at = [&](int ri, int ci) -> double {
+      if (ri < 0 || ri >= p.H || ci < 0 || ci >= p.W) return 0.0;
+      return p.src[((size_t)ri * p.W + ci) * p.C + ch];
+    };
+    const double t = __dadd_rn(__dmul_rn(wc, at(r0, c0)), __dmul_rn(dc, at(r0, c1)));
+    const double b = __dadd_rn(__dmul_rn(wc, at(r1, c0)), __dmul_rn(dc, at(r1, c1)));
+    double v = __dadd_rn(__dmul_rn(wr, t), __dmul_rn(dr, b));
+    if (!(preserve_cval && v == 0.0)) v = fmin(fmax(v, p.mn), p.mx);
+    p.dst[i] = v;
+  }
+}
+
 }  // namespace
 
 extern "C" int mrcnn_zscale_params(const float* maps, int n_images, int height, int width, const float* contrasts3,
@@ -420,6 +461,22 @@ extern "C" int mrcnn_resize_pad_mold(const uint8_t* rgb, const int32_t* minmax, 
   int bx = (int)((total + 255) / 256);
   if (bx > 148 * 4) bx = 148 * 4;
   MRCNN_CHECK_CUDA(mrcnn_launch(resize_pad_mold_kernel, dim3(dim3(bx, n_images)), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
+  MRCNN_CHECK_CUDA(cudaGetLastError());
+  mrcnn_count_launch(1);
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_skimage_resize_f64(const double* image, int height, int width, int channels, int out_h, int out_w,
+                                        double image_min, double image_max, double* out, void* stream) {
+  MRCNN_REQUIRE(image && out, "skimage_resize: null pointer");
+  MRCNN_REQUIRE(height > 0 && width > 0 && channels > 0 && out_h > 0 && out_w > 0, "skimage_resize: empty input / output");
+  ResizeParams p;
+  p.src = image; p.dst = out; p.H = height; p.W = width; p.C = channels; p.out_h = out_h; p.out_w = out_w;
+  p.mn = image_min; p.mx = image_max;
+  const size_t total = (size_t)out_h * out_w * channels;
+  int bx = (int)((total + 255) / 256);
+  if (bx > 148 * 8) bx = 148 * 8;
+  MRCNN_CHECK_CUDA(mrcnn_launch(skimage_resize_kernel, dim3(bx), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;

@@ -18,7 +18,7 @@ void mrcnn_set_error(const char* fmt, ...) {
 void mrcnn_count_launch(unsigned long long n) { g_mrcnn_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" const char* mrcnn_last_error(void) { return g_err; }
-extern "C" int mrcnn_abi_version(void) { return 1; }
+extern "C" int mrcnn_abi_version(void) { return 2; }
 extern "C" unsigned long long mrcnn_kernel_launch_count(void) { return g_mrcnn_launches.load(); }
 
 // programmatic dependent launch is on unless MRCNN_B200_PDL=0 (read once)

@@ -217,6 +217,84 @@ __global__ void __launch_bounds__(PAINT_THREADS) unmold_paint_kernel(UnmoldParam
   }
 }
 
+
+// Same per-pixel arithmetic as unmold_paint_kernel, but the result leaves as PIXEL-MAJOR BITS: out[b][pixel][DW] uint32,
+// bit k of word w = detection 32*w + k of image b (compacted order), DW = mask_bits_words(D) in {1,2,4,8}.  One thread per
+// pixel keeps its DW words in registers and stores them as one aligned vector: 16 bytes per pixel for D = 100 instead
+// of 100, which is what crosses PCIe on the host-result path (the [H,W,N] bool arrays of the reference contract are
+// expanded from these bits on the host, host_expand.cu).
+template <int DW>
+__global__ void __launch_bounds__(PAINT_THREADS) unmold_paint_bits_kernel(UnmoldParams p, uint32_t* __restrict__ out_bits) {
+  pdl_prologue();
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int D = p.D;
+  DetRec* s_rec = reinterpret_cast<DetRec*>(s_raw);                                  // [D]
+  int* s_list = reinterpret_cast<int*>(s_raw + (((size_t)D * sizeof(DetRec) + 15) & ~(size_t)15));   // [D]
+  int* s_nlist = s_list + D;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int cnt = p.counts[b];
+  for (int i = tid; i < cnt; i += blockDim.x) s_rec[i] = p.recs[(size_t)b * D + i];
+  const size_t npx = (size_t)p.H0 * p.W0;
+  const size_t p0 = (size_t)blockIdx.x * PAINT_THREADS;
+  if (tid == 0) *s_nlist = 0;
+  __syncthreads();
+  {
+    const size_t plast = min(p0 + PAINT_THREADS, npx) - 1;
+    const int ya = (int)(p0 / p.W0), yb = (int)(plast / p.W0);
+    const int xa = (int)(p0 % p.W0), xb = (int)(plast % p.W0);
+    for (int k = tid; k < cnt; k += blockDim.x) {
+      const DetRec& r = s_rec[k];
+      bool hit = r.y1 <= yb && r.y2 > ya;
+      if (hit && ya == yb) hit = r.x1 <= xb && r.x2 > xa;
+      if (hit) s_list[atomicAdd(s_nlist, 1)] = k;
+    }
+  }
+  __syncthreads();
+  const int nlist = *s_nlist;
+  const size_t pix = p0 + tid;
+  if (pix >= npx) return;
+  uint32_t words[DW];
+#pragma unroll
+  for (int w = 0; w < DW; ++w) words[w] = 0u;
+  const int y = (int)(pix / p.W0), x = (int)(pix % p.W0);
+  for (int li = 0; li < nlist; ++li) {
+    const int k = s_list[li];
+    const DetRec& r = s_rec[k];
+    if (y < r.y1 || y >= r.y2 || x < r.x1 || x >= r.x2) continue;
+    const double rr = __dadd_rn(__dmul_rn(r.rs, (double)(y - r.y1)), r.ro);
+    const double cc = __dadd_rn(__dmul_rn(r.cs, (double)(x - r.x1)), r.co);
+    const double fr = floor(rr), fc = floor(cc);
+    const int r0 = (int)fr, r1 = (int)ceil(rr), c0 = (int)fc, c1 = (int)ceil(cc);
+    const double dr = __dsub_rn(rr, fr), dc = __dsub_rn(cc, fc);
+    const double wr = __dsub_rn(1.0, dr), wc = __dsub_rn(1.0, dc);
+    const float* m = p.masks + (((size_t)b * D + r.src) * p.MH * p.MW) * p.NC + r.cls;
+    auto px = [&](int ri, int ci) -> double {
+      if (ri < 0 || ri >= p.MH || ci < 0 || ci >= p.MW) return 0.0;
+      return (double)__ldg(m + ((size_t)ri * p.MW + ci) * p.NC);
+    };
+    const double t = __dadd_rn(__dmul_rn(wc, px(r0, c0)), __dmul_rn(dc, px(r0, c1)));
+    const double bo = __dadd_rn(__dmul_rn(wc, px(r1, c0)), __dmul_rn(dc, px(r1, c1)));
+    double v = __dadd_rn(__dmul_rn(wr, t), __dmul_rn(dr, bo));
+    const bool preserve_cval = !(r.mn <= 0.0 && 0.0 <= r.mx);
+    if (!(preserve_cval && v == 0.0)) v = fmin(fmax(v, r.mn), r.mx);
+    if (v >= 0.5) {
+#pragma unroll
+      for (int w = 0; w < DW; ++w)
+        if ((k >> 5) == w) words[w] |= 1u << (k & 31);
+    }
+  }
+  uint32_t* dst = out_bits + ((size_t)b * npx + pix) * DW;
+  if constexpr (DW == 1) {
+    __stcs(dst, words[0]);
+  } else if constexpr (DW == 2) {
+    __stcs(reinterpret_cast<uint2*>(dst), make_uint2(words[0], words[1]));
+  } else {
+#pragma unroll
+    for (int w = 0; w < DW; w += 4)
+      __stcs(reinterpret_cast<uint4*>(dst + w), make_uint4(words[w], words[w + 1], words[w + 2], words[w + 3]));
+  }
+}
+
 }  // namespace
 
 extern "C" size_t mrcnn_unmold_workspace_bytes(int batch, int max_instances) {
@@ -249,6 +327,46 @@ extern "C" int mrcnn_unmold_detections(const float* detections, const float* mrc
                       (size_t)(max_instances + 1) * sizeof(int) + 16;
   MRCNN_CHECK_CUDA(cudaFuncSetAttribute(unmold_paint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MRCNN_CHECK_CUDA(mrcnn_launch(unmold_paint_kernel, dim3(dim3((unsigned)((npx + PAINT_THREADS - 1) / PAINT_THREADS), batch)), dim3(PAINT_THREADS), smem, st, p));
+  MRCNN_CHECK_CUDA(cudaGetLastError());
+  mrcnn_count_launch(2);
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_mask_bits_words(int max_instances) {
+  const int need = (max_instances + 31) / 32;
+  int dw = 1;
+  while (dw < need) dw <<= 1;
+  return dw;
+}
+
+extern "C" int mrcnn_unmold_detections_bits(const float* detections, const float* mrcnn_mask, int batch, int max_instances,
+                                            int mask_h, int mask_w, int num_classes, const int* orig_hw, const int* image_hw,
+                                            const int32_t* windows, int32_t* rois, int32_t* class_ids, float* scores,
+                                            int32_t* counts, uint32_t* mask_bits, void* workspace, size_t workspace_bytes,
+                                            void* stream) {
+  MRCNN_REQUIRE(detections && mrcnn_mask && orig_hw && image_hw && windows && rois && class_ids && scores && counts && mask_bits,
+                "unmold_detections_bits: null pointer");
+  MRCNN_REQUIRE(batch > 0 && max_instances > 0 && max_instances <= 256, "unmold_detections_bits: batch/max_instances out of range");
+  MRCNN_REQUIRE(mask_h > 0 && mask_w > 0 && num_classes > 0, "unmold_detections_bits: bad mask shape");
+  MRCNN_REQUIRE(orig_hw[0] > 1 && orig_hw[1] > 1 && image_hw[0] > 1 && image_hw[1] > 1, "unmold_detections_bits: bad image size");
+  MRCNN_REQUIRE(workspace && workspace_bytes >= mrcnn_unmold_workspace_bytes(batch, max_instances),
+                "unmold_detections_bits: workspace too small");
+  UnmoldParams p;
+  p.det = detections; p.masks = mrcnn_mask; p.D = max_instances; p.MH = mask_h; p.MW = mask_w; p.NC = num_classes;
+  p.H0 = orig_hw[0]; p.W0 = orig_hw[1]; p.IH = image_hw[0]; p.IW = image_hw[1];
+  p.windows = windows; p.rois = rois; p.class_ids = class_ids; p.scores = scores; p.counts = counts;
+  p.recs = static_cast<DetRec*>(workspace); p.out = nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MRCNN_CHECK_CUDA(mrcnn_launch(unmold_boxes_kernel, dim3(batch), dim3(1024), (3 * max_instances + 1) * sizeof(int), st, p));
+  const size_t npx = (size_t)p.H0 * p.W0;
+  const size_t smem = (((size_t)max_instances * sizeof(DetRec) + 15) & ~(size_t)15) + (size_t)(max_instances + 1) * sizeof(int) + 16;
+  const dim3 grid((unsigned)((npx + PAINT_THREADS - 1) / PAINT_THREADS), batch);
+  switch (mrcnn_mask_bits_words(max_instances)) {
+    case 1: MRCNN_CHECK_CUDA(mrcnn_launch(unmold_paint_bits_kernel<1>, grid, dim3(PAINT_THREADS), smem, st, p, mask_bits)); break;
+    case 2: MRCNN_CHECK_CUDA(mrcnn_launch(unmold_paint_bits_kernel<2>, grid, dim3(PAINT_THREADS), smem, st, p, mask_bits)); break;
+    case 4: MRCNN_CHECK_CUDA(mrcnn_launch(unmold_paint_bits_kernel<4>, grid, dim3(PAINT_THREADS), smem, st, p, mask_bits)); break;
+    default: MRCNN_CHECK_CUDA(mrcnn_launch(unmold_paint_bits_kernel<8>, grid, dim3(PAINT_THREADS), smem, st, p, mask_bits)); break;
+  }
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(2);
   return MRCNN_OK;

@@ -50,6 +50,8 @@ SIGNATURES = {
     "mrcnn_stretch_to_rgb8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mrcnn_resize_pad_mold": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_void_p, c_void_p, c_void_p]),
+    "mrcnn_skimage_resize_f64": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_double, ctypes.c_double,
+                                         c_void_p, c_void_p]),
     "mrcnn_proposal_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mrcnn_proposal_layer": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -62,6 +64,12 @@ SIGNATURES = {
     "mrcnn_unmold_detections": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_size_t, c_void_p]),
+    "mrcnn_mask_bits_words": (c_int, [c_int]),
+    "mrcnn_unmold_detections_bits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_size_t, c_void_p]),
+    "mrcnn_host_threads": (c_int, []),
+    "mrcnn_host_expand_mask_bits": (c_int, [c_void_p, c_int, ctypes.c_int64, c_int, c_void_p, c_void_p, c_int]),
     "mrcnn_conv2d_bf16": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
     "mrcnn_conv2d_bf16_simt": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -82,7 +90,7 @@ SIGNATURES = {
     "mrcnn_engine_detect_molded": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p]),
     "mrcnn_engine_detect_maps": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
-                                         c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+                                         c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "mrcnn_engine_wait": (c_int, [c_void_p]),
     "mrcnn_engine_next_slot": (c_int, [c_void_p]),
     "mrcnn_engine_wait_slot": (c_int, [c_void_p, c_int]),

@@ -101,6 +101,12 @@ class MaskPlaneOps:
     def _ctx(self):
         return self.torch.cuda.stream(self.stream) if self.stream is not None else self.torch.cuda.device(self.device)
 
+    def _call(self, fn, *args, what=""):
+        """Every native launch happens with this object's device current (the C entry points launch on the stream they
+        are given and never switch devices themselves): a model on cuda:1 works while cuda:0 is the process default."""
+        with self.torch.cuda.device(self.device):
+            _native.check(fn(*args), what)
+
     def words(self, H, W):
         return int(self.lib.mrcnn_plane_words(H, W))
 
@@ -117,16 +123,16 @@ class MaskPlaneOps:
         """masks [n_images,H,W,depth] uint8 at device address masks_ptr; plane_of host int32 [n_images*depth]."""
         planes = self.empty((max(n_planes, 1), self.words(H, W)), self.torch.int32)
         d_map = self.to_dev(plane_of, np.int32)
-        _native.check(self.lib.mrcnn_masks_pack(ctypes.c_void_p(masks_ptr), n_images, H, W, depth, _native.ptr(d_map),
-                                                _native.ptr(planes), self._st()), "masks_pack")
+        self._call(self.lib.mrcnn_masks_pack, ctypes.c_void_p(masks_ptr), n_images, H, W, depth, _native.ptr(d_map),
+                                                _native.ptr(planes), self._st(), what="masks_pack")
         return planes[:n_planes]
 
     def area_bbox(self, planes, H, W):
         n = int(planes.shape[0])
         area = self.empty((max(n, 1),), self.torch.int32)
         bbox = self.empty((max(n, 1), 4), self.torch.int32)
-        _native.check(self.lib.mrcnn_planes_area_bbox(_native.ptr(planes), n, H, W, _native.ptr(area), _native.ptr(bbox),
-                                                      self._st()), "planes_area_bbox")
+        self._call(self.lib.mrcnn_planes_area_bbox, _native.ptr(planes), n, H, W, _native.ptr(area), _native.ptr(bbox),
+                                                      self._st(), what="planes_area_bbox")
         return area[:n], bbox[:n]
 
     def pair_stats(self, planes, H, W, pairs, bbox=None):
@@ -136,8 +142,8 @@ class MaskPlaneOps:
         touch = self.empty((max(P, 1),), self.torch.int32)
         if P:
             d_pairs = self.to_dev(pairs, np.int32)
-            _native.check(self.lib.mrcnn_planes_pair_stats(_native.ptr(planes), H, W, _native.ptr(d_pairs), P, _native.ptr(bbox),
-                                                           _native.ptr(inter), _native.ptr(touch), self._st()), "planes_pair_stats")
+            self._call(self.lib.mrcnn_planes_pair_stats, _native.ptr(planes), H, W, _native.ptr(d_pairs), P, _native.ptr(bbox),
+                                                           _native.ptr(inter), _native.ptr(touch), self._st(), what="planes_pair_stats")
         return inter[:P], touch[:P]
 
     def union(self, planes, H, W, groups):
@@ -154,8 +160,8 @@ class MaskPlaneOps:
         out = self.empty((max(G, 1), self.words(H, W)), self.torch.int32)
         if G:
             d_m, d_o = self.to_dev(members, np.int32), self.to_dev(offsets, np.int32)
-            _native.check(self.lib.mrcnn_planes_union(_native.ptr(planes), H, W, _native.ptr(d_m), _native.ptr(d_o), G,
-                                                      _native.ptr(out), self._st()), "planes_union")
+            self._call(self.lib.mrcnn_planes_union, _native.ptr(planes), H, W, _native.ptr(d_m), _native.ptr(d_o), G,
+                                                      _native.ptr(out), self._st(), what="planes_union")
         return out[:G]
 
     def label(self, planes, H, W):
@@ -166,8 +172,8 @@ class MaskPlaneOps:
         if n:
             ws_bytes = int(self.lib.mrcnn_planes_label_workspace_bytes(n, H, W))
             ws = self.empty((ws_bytes,), self.torch.uint8)
-            _native.check(self.lib.mrcnn_planes_label(_native.ptr(planes), n, H, W, _native.ptr(labels), _native.ptr(counts),
-                                                      _native.ptr(ws), ws_bytes, self._st()), "planes_label")
+            self._call(self.lib.mrcnn_planes_label, _native.ptr(planes), n, H, W, _native.ptr(labels), _native.ptr(counts),
+                                                      _native.ptr(ws), ws_bytes, self._st(), what="planes_label")
         return labels[:n], counts[:n]
 
     def select(self, labels, H, W, src, comp):
@@ -175,8 +181,8 @@ class MaskPlaneOps:
         out = self.empty((max(K, 1), self.words(H, W)), self.torch.int32)
         if K:
             d_s, d_c = self.to_dev(src, np.int32), self.to_dev(comp, np.int32)
-            _native.check(self.lib.mrcnn_labels_select(_native.ptr(labels), H, W, _native.ptr(d_s), _native.ptr(d_c), K,
-                                                       _native.ptr(out), self._st()), "labels_select")
+            self._call(self.lib.mrcnn_labels_select, _native.ptr(labels), H, W, _native.ptr(d_s), _native.ptr(d_c), K,
+                                                       _native.ptr(out), self._st(), what="labels_select")
         return out[:K]
 
     def pixels(self, planes, H, W, areas, y0=0, x0=0):
@@ -188,15 +194,15 @@ class MaskPlaneOps:
         out = self.empty((max(total, 1), 2), self.torch.int32)
         if n and total:
             d_o = self.to_dev(offsets[:-1], np.int64)
-            _native.check(self.lib.mrcnn_planes_pixels(_native.ptr(planes), n, H, W, _native.ptr(d_o), int(y0), int(x0),
-                                                       _native.ptr(out), self._st()), "planes_pixels")
+            self._call(self.lib.mrcnn_planes_pixels, _native.ptr(planes), n, H, W, _native.ptr(d_o), int(y0), int(x0),
+                                                       _native.ptr(out), self._st(), what="planes_pixels")
         return self.host(out[:total]), offsets
 
     def unpack(self, planes, H, W):
         n = int(planes.shape[0])
         out = self.empty((max(n, 1), H, W), self.torch.uint8)
         if n:
-            _native.check(self.lib.mrcnn_planes_unpack(_native.ptr(planes), n, H, W, _native.ptr(out), self._st()), "planes_unpack")
+            self._call(self.lib.mrcnn_planes_unpack, _native.ptr(planes), n, H, W, _native.ptr(out), self._st(), what="planes_unpack")
         return self.host(out[:n])
 
     def gather(self, planes, index):

@@ -63,19 +63,52 @@ def unmold_image(normalized_images, config):
     return (normalized_images + config.MEAN_PIXEL).astype(np.uint8)
 
 
+def graph_limit_problems(config):
+    """Hard limits of the fused sm_100a kernels, checked when the model is built (not at first predict):
+    -> list of messages, empty when the configuration fits."""
+    out = []
+    if not 1 <= int(config.NUM_CLASSES) <= 6:
+        out.append("NUM_CLASSES=%d: the fused class/bbox head packs 5*NUM_CLASSES outputs into one 32-wide tile (max 6 "
+                   "classes including background)" % config.NUM_CLASSES)
+    if not 1 <= len(config.RPN_ANCHOR_RATIOS) <= 5:
+        out.append("len(RPN_ANCHOR_RATIOS)=%d: the fused RPN head packs 6*anchors_per_location outputs into one 32-wide "
+                   "tile (max 5)" % len(config.RPN_ANCHOR_RATIOS))
+    if int(config.POST_NMS_ROIS_INFERENCE) > 1024:
+        out.append("POST_NMS_ROIS_INFERENCE=%d: DetectionLayer kernel handles at most 1024 ROIs per image" % config.POST_NMS_ROIS_INFERENCE)
+    if int(config.DETECTION_MAX_INSTANCES) > 256:
+        out.append("DETECTION_MAX_INSTANCES=%d: at most 256 detections per image" % config.DETECTION_MAX_INSTANCES)
+    if int(config.TOP_DOWN_PYRAMID_SIZE) % 64 or int(config.FPN_CLASSIF_FC_LAYERS_SIZE) % 64:
+        out.append("TOP_DOWN_PYRAMID_SIZE and FPN_CLASSIF_FC_LAYERS_SIZE must be multiples of 64")
+    if list(config.BACKBONE_STRIDES) != [4, 8, 16, 32, 64]:
+        out.append("BACKBONE_STRIDES must be [4, 8, 16, 32, 64]")
+    return out
+
+
+def load_image_gt(dataset, config, image_id, augment=False, augmentation=None, use_mini_mask=False):
+    """reference: mrcnn/model.py:1277-1381 (ground-truth loading for training / ModelTester, used by
+    mrcnn/analyze.py:440-442 when ground truth is available).  The B200 build covers the detect path only:
+    importing the name works, calling it says so."""
+    raise NotImplementedError("mrcnn (B200 build): load_image_gt belongs to the training / ground-truth evaluation path, "
+                              "which is outside the detect hot path (SURVEY.md §8f rank 4)")
+
+
 # --------------------------------------------------------------------------------------------
 # MaskRCNN
 # --------------------------------------------------------------------------------------------
 
 class _PinnedSet(object):
-    """One batch worth of pinned host result buffers (rois, class ids, scores, counts, masks)."""
+    """One batch worth of host result buffers: rois, class ids, scores, counts and the pixel-major mask bits
+    [B, H0*W0, DW] uint32 land in PINNED memory (device->host copies); `dense` is the plain host buffer the
+    reference-contract [H0,W0,N] bool masks are expanded into (mrcnn_host_expand_mask_bits)."""
 
-    def __init__(self, torch, B, D, H0, W0, pin=True):
+    def __init__(self, torch, B, D, H0, W0, dw, pin=True):
         # allocated pinned directly (tensor.pin_memory() would allocate pageable memory first and copy it)
         self.key = (B, D, H0, W0)
+        self.dw = dw
         self.tensors = (torch.empty((B, D, 4), dtype=torch.int32, pin_memory=pin), torch.empty((B, D), dtype=torch.int32, pin_memory=pin),
                         torch.empty((B, D), dtype=torch.float32, pin_memory=pin), torch.empty((B,), dtype=torch.int32, pin_memory=pin),
-                        torch.empty((B, H0, W0, D), dtype=torch.uint8, pin_memory=pin))
+                        torch.empty((B, H0 * W0, dw), dtype=torch.int32, pin_memory=pin))
+        self.dense = torch.empty((B, H0 * W0 * D), dtype=torch.uint8)
 
 
 class _Lease(object):
@@ -92,7 +125,7 @@ class _Lease(object):
 
 
 class _LeasedArray(object):
-    """numpy-convertible window on one pinned tensor; np.asarray(...) keeps this object (and so the lease) as .base"""
+    """numpy-convertible window on one host tensor; np.asarray(...) keeps this object (and so the lease) as .base"""
 
     def __init__(self, lease, tensor, typestr):
         self._lease, self._tensor = lease, tensor
@@ -100,9 +133,10 @@ class _LeasedArray(object):
 
 
 def _lease_arrays(pool, pset):
+    """-> (rois, class_ids, scores, counts, mask_bits, dense, (H0, W0)): numpy views sharing one lease"""
     lease = _Lease(pool, pset)
-    types = ("<i4", "<i4", "<f4", "<i4", "|u1")
-    return tuple(np.asarray(_LeasedArray(lease, t, ts)) for t, ts in zip(pset.tensors, types))
+    types = ("<i4", "<i4", "<f4", "<i4", "<u4", "|u1")
+    return tuple(np.asarray(_LeasedArray(lease, t, ts)) for t, ts in zip(pset.tensors + (pset.dense,), types)) + (pset.key[2:],)
 
 
 class _PendingDetection(object):
@@ -114,7 +148,7 @@ class _PendingDetection(object):
     def result(self):
         if self._done is None:
             _native.check(self._model._lib.mrcnn_engine_wait_slot(self._model._engine, self._slot), "engine_wait_slot")
-            self._done = MaskRCNN._results_from_buffers(self._bufs, self._model.config.BATCH_SIZE)
+            self._done = self._model._results_from_buffers(self._bufs)
             self._maps = None
         return self._done
 
@@ -136,7 +170,7 @@ class _PendingDeviceDetection(object):
             ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
             name = b"unmold_masks" if self._slot == 0 else b"unmold_masks#1"
             _native.check(m._lib.mrcnn_engine_tensor(m._engine, name, ctypes.byref(ptr), ctypes.byref(nbytes)), "unmold_masks")
-            rois, cls, scores, counts, _ = self._bufs
+            rois, cls, scores, counts = self._bufs[:4]
             self._done = {"rois": rois, "class_ids": cls, "scores": scores, "counts": counts, "masks_ptr": ptr.value,
                           "depth": m.config.DETECTION_MAX_INSTANCES}
             self._maps = None
@@ -172,6 +206,9 @@ class MaskRCNN(object):
             raise NotImplementedError("mrcnn (B200 build): BACKBONE must be 'resnet101' (SURVEY.md §8a row a17)")
         if config.IMAGE_CHANNEL_COUNT != 3:
             raise NotImplementedError("mrcnn (B200 build): IMAGE_CHANNEL_COUNT must be 3 (SURVEY.md §8a row a17)")
+        problems = graph_limit_problems(config)
+        if problems:
+            raise NotImplementedError("mrcnn (B200 build): " + "; ".join(problems))
         torch = utils._torch()
         lib = _native.lib()
         if self._device is None:
@@ -409,29 +446,41 @@ class MaskRCNN(object):
 
     # -- detection ------------------------------------------------------------------------------
     def _result_buffers(self, H0, W0):
-        """Pinned host buffers for one batch of results, as numpy arrays. The arrays handed back to the caller
-        are views of them; a set returns to this model's pool when the last such view is garbage-collected
-        (a fresh 420 MB cudaHostAlloc costs ~0.4 s, so sets are recycled, never freed)."""
+        """Host buffers for one batch of results, as numpy arrays (pinned: boxes / ids / scores / counts / mask bits;
+        plain: the dense mask buffer). The arrays handed back to the caller are views of them; a set returns to this
+        model's pool when the last such view is garbage-collected (page-faulting in a fresh 420 MB buffer costs more
+        than a whole detect step, so sets are recycled, never freed)."""
         torch = utils._torch()
         c = self.config
         key = (c.BATCH_SIZE, c.DETECTION_MAX_INSTANCES, int(H0), int(W0))
         free = self._result_pool.setdefault(key, [])
-        pset = free.pop() if free else _PinnedSet(torch, *key)
+        pset = free.pop() if free else _PinnedSet(torch, *key, dw=self._lib.mrcnn_mask_bits_words(c.DETECTION_MAX_INSTANCES))
         return _lease_arrays(self._result_pool, pset)
 
     def reserve_result_buffers(self, count, H0, W0):
-        """Pre-allocates `count` pinned result sets for [H0, W0] frames (keeps the allocation out of the first calls)."""
+        """Pre-allocates `count` result sets for [H0, W0] frames (keeps the allocation and the first-touch page faults
+        out of the first calls)."""
         sets = [self._result_buffers(H0, W0) for _ in range(count)]
+        for bufs in sets:
+            bufs[5].fill(0)
         del sets
 
     @staticmethod
-    def _results_from_buffers(bufs, B):
-        rois_n, cls_n, sc_n, cnt_n, m_n = bufs
+    def _results_from_buffers(bufs):
+        """Expands the mask bits of one batch into the reference's [H0,W0,N] bool arrays (multi-threaded C++ behind the
+        C ABI) and builds the detect()-style dicts (mrcnn/model.py:2697-2703)."""
+        rois_n, cls_n, sc_n, cnt_n, bits_n, dense_n, (H0, W0) = bufs
+        B, D = cls_n.shape
+        npx, dw = bits_n.shape[1], bits_n.shape[2]
+        base = dense_n.ctypes.data
+        dst = (ctypes.c_void_p * B)(*[base + i * npx * D for i in range(B)])
+        _native.check(_native.lib().mrcnn_host_expand_mask_bits(bits_n.ctypes.data, B, npx, dw, cnt_n.ctypes.data, dst, 0),
+                      "host_expand_mask_bits")
         out = []
         for i in range(B):
             n = int(cnt_n[i])
             # no detections: the reference returns np.empty(original_image_shape[:2] + (0,)) (float64), model.py:2618-2619
-            masks = m_n[i, :, :, :n].view(np.bool_) if n > 0 else np.empty(m_n.shape[1:3] + (0,))
+            masks = dense_n[i, :npx * n].reshape(H0, W0, n).view(np.bool_) if n > 0 else np.empty((H0, W0, 0))
             out.append({"rois": rois_n[i, :n], "class_ids": cls_n[i, :n], "scores": sc_n[i, :n], "masks": masks})
         return out
 
@@ -462,8 +511,8 @@ class MaskRCNN(object):
         on_host = 0 if molded.is_cuda else 1
         with torch.cuda.stream(self._stream):
             _native.check(self._lib.mrcnn_engine_detect_molded(self._engine, _native.ptr(molded), on_host, metas32.ctypes.data, orig,
-                                                               wins.ctypes.data, *[b.ctypes.data for b in bufs]), "detect")
-        return self._results_from_buffers(bufs, self.config.BATCH_SIZE)
+                                                               wins.ctypes.data, *[b.ctypes.data for b in bufs[:5]]), "detect")
+        return self._results_from_buffers(bufs)
 
     def detect_maps_async(self, maps, zscale_contrasts=(0.25, 0.25, 0.25)):
         """Queues detect_maps and returns a handle whose .result() gives the detect()-style dicts. The
@@ -474,13 +523,17 @@ class MaskRCNN(object):
     def wait(self):
         _native.check(self._lib.mrcnn_engine_wait(self._engine), "engine_wait")
 
-    def detect_maps(self, maps, zscale_contrasts=(0.25, 0.25, 0.25), device_only=False, _async=False, masks_on_device=False):
+    def detect_maps(self, maps, zscale_contrasts=(0.25, 0.25, 0.25), device_only=False, _async=False, masks_on_device=False,
+                    mask_format=None):
         """Fast path from FITS-like maps (extension; the numpy contract of detect() is unchanged):
         maps [BATCH_SIZE,H,W] float32 — numpy / pinned torch tensor (copied H2D) or a CUDA tensor —
         -> read_fits stretch + mold + graph + unmold in one C-ABI call. Returns detect()-style dicts,
         or None with device_only=True (results stay in the engine's 'unmold_*' tensors). masks_on_device=True queues
         the call and returns a _PendingDeviceDetection: only boxes / class ids / scores / counts are copied to the host,
-        the full-frame masks stay in HBM for mrcnn.analyze (no [B,H,W,100] transfer)."""
+        the full-frame masks stay in HBM for mrcnn.analyze (no [B,H,W,100] transfer).
+        Host results travel as pixel-major mask bits (16 bytes per pixel for 100 detections) and are expanded to the
+        reference's [H,W,N] bool arrays on the host; mask_format=0 with device_only leaves [B,H,W,D] uint8 masks in
+        the engine tensor "unmold_masks" instead of the bits in "unmold_mask_bits"."""
         torch = utils._torch()
         c = self.config
         if not self._weights_loaded:
@@ -502,17 +555,20 @@ class MaskRCNN(object):
         con = _native.float_array(list(zscale_contrasts))
         mean = _native.float_array([float(v) for v in np.asarray(c.MEAN_PIXEL).reshape(-1)[:3]])
         if masks_on_device:
-            bufs = self._result_buffers(1, 1)                  # small pinned set: its 1x1 mask buffer is not used
+            bufs = self._result_buffers(1, 1)                  # small pinned set: its 1x1 mask buffers are not used
             outs = [b.ctypes.data for b in bufs[:4]] + [None]
             _async = True
         else:
             bufs = None if device_only else self._result_buffers(H0, W0)
-            outs = [None] * 5 if device_only else [b.ctypes.data for b in bufs]
+            outs = [None] * 5 if device_only else [b.ctypes.data for b in bufs[:5]]
+        if mask_format is None:
+            mask_format = 0 if masks_on_device else 1          # device consumers read bytes, host results travel as bits
+        assert mask_format == 1 or masks_on_device or device_only, "host results are shipped as mask bits (mask_format=1)"
         slot = self._lib.mrcnn_engine_next_slot(self._engine)
         with torch.cuda.stream(self._stream):
             _native.check(self._lib.mrcnn_engine_detect_maps(self._engine, _native.ptr(maps), 0 if maps.is_cuda else 1, H0, W0, con, mean,
                                                              int(out_hw[0]), int(out_hw[1]), int(top_left[0]), int(top_left[1]),
-                                                             metas32.ctypes.data, wins.ctypes.data, *outs, 1 if _async else 0),
+                                                             metas32.ctypes.data, wins.ctypes.data, *outs, mask_format, 1 if _async else 0),
                           "detect_maps")
         if masks_on_device:
             return _PendingDeviceDetection(self, bufs, maps, slot, H0, W0)
@@ -520,7 +576,7 @@ class MaskRCNN(object):
             return None          # with _async=True nothing has been waited for: call wait() before reading tensors
         if _async:
             return _PendingDetection(self, bufs, maps, slot)
-        return self._results_from_buffers(bufs, c.BATCH_SIZE)
+        return self._results_from_buffers(bufs)
 
     def kernel_times(self):
         """{family: (ms, launches)} of the last predict; needs set_profiling(True) beforehand."""
@@ -580,28 +636,29 @@ class MaskRCNN(object):
                                    [image_shape] * len(molded_images))
 
     def unmold_detections(self, detections, mrcnn_mask, original_image_shape, image_shape, window):
-        """reference: mrcnn/model.py:2558-2621, for one image, computed on the GPU."""
+        """reference: mrcnn/model.py:2558-2621, for one image, computed on the GPU (this model's device and stream)."""
         torch = utils._torch()
         lib = self._lib
         D = detections.shape[0]
         dev = "cuda:%d" % self._device
-        d_det = torch.from_numpy(np.ascontiguousarray(detections, dtype=np.float32)).to(dev)
-        d_mask = torch.from_numpy(np.ascontiguousarray(mrcnn_mask, dtype=np.float32)).to(dev)
-        d_win = torch.from_numpy(np.ascontiguousarray(window, dtype=np.int32).reshape(1, 4)).to(dev)
         H0, W0 = int(original_image_shape[0]), int(original_image_shape[1])
-        rois = torch.empty((D, 4), dtype=torch.int32, device=dev)
-        cls = torch.empty((D,), dtype=torch.int32, device=dev)
-        sc = torch.empty((D,), dtype=torch.float32, device=dev)
-        cnt = torch.empty((1,), dtype=torch.int32, device=dev)
-        masks = torch.empty((H0, W0, D), dtype=torch.uint8, device=dev)
-        ws = torch.empty((lib.mrcnn_unmold_workspace_bytes(1, D),), dtype=torch.uint8, device=dev)
-        orig = (ctypes.c_int * 2)(H0, W0)
-        img = (ctypes.c_int * 2)(int(image_shape[0]), int(image_shape[1]))
-        _native.check(lib.mrcnn_unmold_detections(_native.ptr(d_det), _native.ptr(d_mask), 1, D, mrcnn_mask.shape[1],
-                                                  mrcnn_mask.shape[2], mrcnn_mask.shape[3], orig, img, _native.ptr(d_win),
-                                                  _native.ptr(rois), _native.ptr(cls), _native.ptr(sc), _native.ptr(cnt),
-                                                  _native.ptr(masks), _native.ptr(ws), ws.numel(),
-                                                  torch.cuda.current_stream().cuda_stream), "unmold_detections")
-        n = int(cnt.item())
-        full = masks.cpu().numpy()[:, :, :n].view(np.bool_) if n > 0 else np.empty((H0, W0, 0))
-        return rois.cpu().numpy()[:n], cls.cpu().numpy()[:n], sc.cpu().numpy()[:n], full
+        with torch.cuda.stream(self._stream):
+            d_det = torch.from_numpy(np.ascontiguousarray(detections, dtype=np.float32)).to(dev)
+            d_mask = torch.from_numpy(np.ascontiguousarray(mrcnn_mask, dtype=np.float32)).to(dev)
+            d_win = torch.from_numpy(np.ascontiguousarray(window, dtype=np.int32).reshape(1, 4)).to(dev)
+            rois = torch.empty((D, 4), dtype=torch.int32, device=dev)
+            cls = torch.empty((D,), dtype=torch.int32, device=dev)
+            sc = torch.empty((D,), dtype=torch.float32, device=dev)
+            cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+            masks = torch.empty((H0, W0, D), dtype=torch.uint8, device=dev)
+            ws = torch.empty((lib.mrcnn_unmold_workspace_bytes(1, D),), dtype=torch.uint8, device=dev)
+            orig = (ctypes.c_int * 2)(H0, W0)
+            img = (ctypes.c_int * 2)(int(image_shape[0]), int(image_shape[1]))
+            _native.check(lib.mrcnn_unmold_detections(_native.ptr(d_det), _native.ptr(d_mask), 1, D, mrcnn_mask.shape[1],
+                                                      mrcnn_mask.shape[2], mrcnn_mask.shape[3], orig, img, _native.ptr(d_win),
+                                                      _native.ptr(rois), _native.ptr(cls), _native.ptr(sc), _native.ptr(cnt),
+                                                      _native.ptr(masks), _native.ptr(ws), ws.numel(),
+                                                      self._stream.cuda_stream), "unmold_detections")
+            n = int(cnt.item())
+            full = masks.cpu().numpy()[:, :, :n].view(np.bool_) if n > 0 else np.empty((H0, W0, 0))
+            return rois.cpu().numpy()[:n], cls.cpu().numpy()[:n], sc.cpu().numpy()[:n], full

@@ -404,9 +404,10 @@ class SFinder(object):
         d_off = torch.from_numpy(offsets).to(device)
         d_pairs = torch.from_numpy(np.array([[slot[i], slot[j]] for i, j in pairs], dtype=np.int32)).to(device)
         d_out = torch.empty((len(pairs),), dtype=torch.int32, device=device)
-        _native.check(lib.mrcnn_pixel_lists_adjacent(_native.ptr(d_px), _native.ptr(d_off), _native.ptr(d_pairs), len(pairs),
-                                                     _native.ptr(d_out), ctypes.c_void_p(torch.cuda.current_stream(d_out.device).cuda_stream)),
-                      "pixel_lists_adjacent")
+        with torch.cuda.device(d_out.device):
+            _native.check(lib.mrcnn_pixel_lists_adjacent(_native.ptr(d_px), _native.ptr(d_off), _native.ptr(d_pairs), len(pairs),
+                                                         _native.ptr(d_out), ctypes.c_void_p(torch.cuda.current_stream(d_out.device).cuda_stream)),
+                          "pixel_lists_adjacent")
         return d_out.cpu().numpy().astype(bool).tolist()
 
     # -- output ------------------------------------------------------------------------------------

@@ -38,11 +38,12 @@ def maps_to_rgb8_device(maps, zscale_contrasts=(0.25, 0.25, 0.25)):
     params = torch.empty((n, 3, 4), dtype=torch.float32, device=maps.device)
     rgb = torch.empty((n, H, W, 3), dtype=torch.uint8, device=maps.device)
     minmax = torch.empty((n, 2), dtype=torch.int32, device=maps.device)
-    stream = torch.cuda.current_stream().cuda_stream
     con = _native.float_array(list(zscale_contrasts))
-    _native.check(lib.mrcnn_zscale_params(_native.ptr(maps), n, H, W, con, _native.ptr(params), stream), "zscale_params")
-    _native.check(lib.mrcnn_stretch_to_rgb8(_native.ptr(maps), _native.ptr(params), n, H, W, _native.ptr(rgb),
-                                            _native.ptr(minmax), stream), "stretch_to_rgb8")
+    with torch.cuda.device(maps.device):        # launch on the tensor's device, whatever the process default is
+        stream = torch.cuda.current_stream(maps.device).cuda_stream
+        _native.check(lib.mrcnn_zscale_params(_native.ptr(maps), n, H, W, con, _native.ptr(params), stream), "zscale_params")
+        _native.check(lib.mrcnn_stretch_to_rgb8(_native.ptr(maps), _native.ptr(params), n, H, W, _native.ptr(rgb),
+                                                _native.ptr(minmax), stream), "stretch_to_rgb8")
     return rgb, minmax, params
 
 
@@ -80,10 +81,11 @@ def mold_rgb8_device(rgb, minmax, out_hw, square, top_left, mean_pixel, out=None
     if out is None:
         out = torch.empty((n, square, square, 3), dtype=torch.float32, device=rgb.device)
     mean = _native.float_array([float(v) for v in np.asarray(mean_pixel).reshape(-1)[:3]])
-    stream = torch.cuda.current_stream().cuda_stream
-    _native.check(lib.mrcnn_resize_pad_mold(_native.ptr(rgb), _native.ptr(minmax), n, H, W, int(out_hw[0]), int(out_hw[1]),
-                                            int(square), int(top_left[0]), int(top_left[1]), mean, _native.ptr(out), stream),
-                  "resize_pad_mold")
+    with torch.cuda.device(rgb.device):
+        stream = torch.cuda.current_stream(rgb.device).cuda_stream
+        _native.check(lib.mrcnn_resize_pad_mold(_native.ptr(rgb), _native.ptr(minmax), n, H, W, int(out_hw[0]), int(out_hw[1]),
+                                                int(square), int(top_left[0]), int(top_left[1]), mean, _native.ptr(out), stream),
+                      "resize_pad_mold")
     return out
 
 
@@ -163,6 +165,143 @@ def resize_image(image, min_dim=None, max_dim=None, min_scale=None, mode="square
     rgb = torch.from_numpy(np.ascontiguousarray(image)).cuda().unsqueeze(0)
     molded = mold_rgb8_device(rgb, None, out_hw, max_dim, top_left, (0.0, 0.0, 0.0))
     return molded[0].to(torch.uint8).cpu().numpy(), window, scale, padding, None
+
+
+def resize(image, output_shape, order=1, mode='constant', cval=0, clip=True, preserve_range=False, anti_aliasing=False,
+           anti_aliasing_sigma=None):
+    """reference: mrcnn/utils.py:957-978 — the wrapper around skimage.transform.resize; here the scikit-image <= 0.15
+    bilinear warp runs on the GPU (float64, same operation order). Only the argument values the reference itself uses
+    are implemented (order=1, mode='constant', cval=0, clip=True, no anti-aliasing). Returns float64 like skimage:
+    float inputs keep their range, uint8 / bool inputs are scaled to [0,1] unless preserve_range."""
+    if order != 1 or mode != 'constant' or cval != 0 or not clip or anti_aliasing:
+        raise NotImplementedError("resize (B200 build): only order=1, mode='constant', cval=0, clip=True, anti_aliasing=False")
+    image = np.asarray(image)
+    if preserve_range or image.dtype.kind == "f" or image.dtype == np.bool_:
+        img = image.astype(np.float64)
+    elif image.dtype == np.uint8:
+        img = image.astype(np.float64) / 255.0
+    else:
+        raise NotImplementedError("resize (B200 build): dtype %s" % image.dtype)
+    rows, cols = int(output_shape[0]), int(output_shape[1])
+    squeeze = img.ndim == 2
+    if squeeze:
+        img = img[:, :, None]
+    if img.ndim != 3:
+        raise NotImplementedError("resize (B200 build): [H,W] or [H,W,C] images only")
+    if rows == 0 or cols == 0 or img.size == 0:
+        out = np.zeros((rows, cols, img.shape[2]), dtype=np.float64)
+        return out[:, :, 0] if squeeze else out
+    torch = _torch()
+    lib = _native.lib()
+    d_in = torch.from_numpy(np.ascontiguousarray(img)).cuda()
+    d_out = torch.empty((rows, cols, img.shape[2]), dtype=torch.float64, device=d_in.device)
+    with torch.cuda.device(d_in.device):
+        _native.check(lib.mrcnn_skimage_resize_f64(_native.ptr(d_in), img.shape[0], img.shape[1], img.shape[2], rows, cols,
+                                                   float(img.min()), float(img.max()), _native.ptr(d_out),
+                                                   torch.cuda.current_stream(d_in.device).cuda_stream), "skimage_resize")
+    out = d_out.cpu().numpy()
+    return out[:, :, 0] if squeeze else out
+
+
+def unmold_mask(mask, bbox, image_shape):
+    """reference: mrcnn/utils.py:629-645 — one [h,w] float mask (28x28) resized to its box, thresholded at 0.5 and pasted
+    into a full-size boolean image. (MaskRCNN.detect does this for a whole batch in one kernel, csrc/unmold.cu.)"""
+    threshold = 0.5
+    y1, x1, y2, x2 = bbox
+    mask = resize(mask, (y2 - y1, x2 - x1))
+    mask = np.where(mask >= threshold, 1, 0).astype(bool)
+    full_mask = np.zeros(image_shape[:2], dtype=bool)
+    full_mask[y1:y2, x1:x2] = mask
+    return full_mask
+
+
+def extract_bboxes(mask):
+    """reference: mrcnn/utils.py:49-77 — mask [H,W,N] (0/1) -> int32 [N,(y1,x1,y2,x2)], y2 / x2 exclusive, zeros for an
+    empty mask. Host numpy like the reference (the Analyzer path gets its boxes from mrcnn_planes_area_bbox on the
+    device-resident bit-planes instead)."""
+    mask = np.asarray(mask)
+    n = mask.shape[-1]
+    boxes = np.zeros([n, 4], dtype=np.int32)
+    if n == 0 or mask.shape[0] == 0 or mask.shape[1] == 0:
+        return boxes
+    m = mask.astype(bool)
+    cols = m.any(axis=0)          # [W,N]
+    rows = m.any(axis=1)          # [H,N]
+    has = cols.any(axis=0)
+    x1 = cols.argmax(axis=0)
+    x2 = cols.shape[0] - cols[::-1].argmax(axis=0)
+    y1 = rows.argmax(axis=0)
+    y2 = rows.shape[0] - rows[::-1].argmax(axis=0)
+    boxes[has] = np.stack([y1, x1, y2, x2], axis=1)[has]
+    return boxes
+
+
+class Dataset(object):
+    """reference: mrcnn/utils.py:305-440 — the dataset bookkeeping base class (class / image registries and id maps).
+    Subclasses provide load_image / load_mask; nothing here touches the GPU."""
+
+    def __init__(self, class_map=None):
+        self._image_ids = []
+        self.image_info = []
+        self.class_info = [{"source": "", "id": 0, "name": "BG"}]      # background is always class 0
+        self.source_class_ids = {}
+
+    def add_class(self, source, class_id, class_name):
+        assert "." not in source, "Source name cannot contain a dot"
+        if any(info["source"] == source and info["id"] == class_id for info in self.class_info):
+            return
+        self.class_info.append({"source": source, "id": class_id, "name": class_name})
+
+    def add_image(self, source, image_id, path, **kwargs):
+        info = {"id": image_id, "source": source, "path": path}
+        info.update(kwargs)
+        self.image_info.append(info)
+
+    def image_reference(self, image_id):
+        return ""
+
+    def prepare(self, class_map=None):
+        self.num_classes = len(self.class_info)
+        self.class_ids = np.arange(self.num_classes)
+        self.class_names = [",".join(c["name"].split(",")[:1]) for c in self.class_info]
+        self.num_images = len(self.image_info)
+        self._image_ids = np.arange(self.num_images)
+        self.class_from_source_map = {"{}.{}".format(info["source"], info["id"]): i
+                                      for info, i in zip(self.class_info, self.class_ids)}
+        self.image_from_source_map = {"{}.{}".format(info["source"], info["id"]): i
+                                      for info, i in zip(self.image_info, self.image_ids)}
+        self.sources = list(set(i["source"] for i in self.class_info))
+        self.source_class_ids = {}
+        for source in self.sources:
+            self.source_class_ids[source] = [i for i, info in enumerate(self.class_info) if i == 0 or source == info["source"]]
+
+    def map_source_class_id(self, source_class_id):
+        return self.class_from_source_map[source_class_id]
+
+    def get_source_class_id(self, class_id, source):
+        info = self.class_info[class_id]
+        assert info["source"] == source
+        return info["id"]
+
+    @property
+    def image_ids(self):
+        return self._image_ids
+
+    def source_image_link(self, image_id):
+        return self.image_info[image_id]["path"]
+
+    def load_image(self, image_id):
+        """[H,W,3] array of the image. The reference reads any raster file through skimage.io; this build reads FITS
+        (the data format of the detect path) through read_fits."""
+        path = self.image_info[image_id]["path"]
+        res = read_fits(path)
+        if res is None:
+            raise IOError("cannot read image " + str(path))
+        return res[0]
+
+    def load_mask(self, image_id):
+        logging.warning("You are using the default load_mask(), maybe you need to define your own one.")
+        return np.empty([0, 0, 0]), np.empty([0], np.int32)
 
 
 # --------------------------------------------------------------------------------------------

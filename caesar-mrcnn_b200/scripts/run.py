@@ -129,6 +129,14 @@ def validate_args(args):
         if not ok:
             logger.error("Option %s is not supported by the B200 build (SURVEY.md §8a row a17)" % flag)
             return -1
+    try:
+        nclasses = len(json.loads(args.classdict_model or args.classdict)) + 1
+    except Exception:
+        logger.error("Cannot parse --classdict / --classdict_model as a JSON dictionary")
+        return -1
+    if nclasses > 6:
+        logger.error("%d classes (+ background) given: the B200 build supports at most 6 classes including background" % (nclasses - 1))
+        return -1
     return 0
 
 
@@ -162,7 +170,11 @@ def make_config(args):
 
 
 def load_model(args, config):
-    model = modellib.MaskRCNN(mode="inference", config=config, model_dir=args.logs, device=int(os.environ.get("LOCAL_RANK", "0")))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)      # one process per GPU: everything of this rank (read_fits included) on its GPU
+    model = modellib.MaskRCNN(mode="inference", config=config, model_dir=args.logs, device=local_rank)
     if args.random_weights is not None:
         sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
         import synth

@@ -66,6 +66,12 @@ int mrcnn_resize_pad_mold(const uint8_t* rgb, const int32_t* minmax, int n_image
                           int width, int out_h, int out_w, int square, int top, int left,
                           const float* mean_pixel3, float* molded, void* stream);
 
+/* utils.resize (mrcnn/utils.py:957-978 = skimage.transform.resize(order=1, mode='constant', cval=0, clip=True,
+ * anti_aliasing=False), scikit-image <= 0.15) for one float64 image [H,W,C] -> out [out_h,out_w,C] float64;
+ * image_min / image_max = the clip range (min / max of the input).  Used by utils.resize / utils.unmold_mask. */
+int mrcnn_skimage_resize_f64(const double* image, int height, int width, int channels, int out_h, int out_w,
+                             double image_min, double image_max, double* out, void* stream);
+
 /* ---- a7: ProposalLayer  (mrcnn/model.py:329-406, apply_box_deltas_graph :287-308,
  *      clip_boxes_graph :311-326, utils.batch_slice mrcnn/utils.py:872-906)
  * rpn_class [B,A,2], rpn_bbox [B,A,4], anchors [A,4] (anchors_batched=0) or [B,A,4] -> rpn_rois
@@ -116,6 +122,23 @@ int mrcnn_unmold_detections(const float* detections, const float* mrcnn_mask, in
                             int32_t* rois, int32_t* class_ids, float* scores, int32_t* counts,
                             uint8_t* masks, void* workspace, size_t workspace_bytes, void* stream);
 size_t mrcnn_unmold_workspace_bytes(int batch, int max_instances);
+/* Same computation, masks as PIXEL-MAJOR BITS: mask_bits [B, H0*W0, DW] uint32, bit k of word w of a pixel = that
+ * pixel of detection 32*w+k of the image (compacted order), DW = mrcnn_mask_bits_words(D) in {1,2,4,8}.  This is what the
+ * engine ships over PCIe for host results (16 bytes per pixel for D = 100 instead of 100). */
+int mrcnn_mask_bits_words(int max_instances);
+int mrcnn_unmold_detections_bits(const float* detections, const float* mrcnn_mask, int batch,
+                                 int max_instances, int mask_h, int mask_w, int num_classes,
+                                 const int* orig_hw, const int* image_hw, const int32_t* windows,
+                                 int32_t* rois, int32_t* class_ids, float* scores, int32_t* counts,
+                                 uint32_t* mask_bits, void* workspace, size_t workspace_bytes, void* stream);
+/* HOST-ONLY: expands pixel-major mask bits (HOST memory, as copied back from the device) into the reference's
+ * result contract (mrcnn/model.py:2613-2619): for image b, dst[b] receives a dense C-order [pixels_per_image, counts[b]]
+ * uint8 array (0/1) = masks [H0, W0, N] bool.  dst: HOST array of n_images HOST pointers (may be NULL where
+ * counts[b] == 0).  n_threads <= 0: mrcnn_host_threads() workers (min(16, CPUs of the affinity mask),
+ * env MRCNN_B200_HOST_THREADS overrides).  AVX-512BW when the CPU has it (env MRCNN_B200_HOST_SIMD=0 disables). */
+int mrcnn_host_threads(void);
+int mrcnn_host_expand_mask_bits(const uint32_t* bits, int n_images, int64_t pixels_per_image, int words_per_pixel,
+                                const int32_t* counts, uint8_t* const* dst, int n_threads);
 
 /* ---- a4-a6, a9, a11: the dense contractions — one bf16 tcgen05/TMEM implicit-GEMM family
  * (KL.Conv2D / TimeDistributed(Conv2D|Dense) / Conv2DTranspose call sites:
@@ -207,24 +230,29 @@ int mrcnn_engine_write(mrcnn_engine* e, const char* name, const void* host_src, 
 /* whole detect(): predict + unmold, results to HOST buffers (pinned recommended).
  * molded [B,S,S,3] float32 (MaskRCNN.mold_inputs output): HOST pointer when molded_on_host != 0,
  * else DEVICE; metas / windows (int32 [B,4]) / orig_hw: HOST.  Outputs as for
- * mrcnn_unmold_detections, written to HOST buffers; masks [B,H0,W0,D] uint8.  Blocking. */
+ * mrcnn_unmold_detections_bits, written to HOST buffers; mask_bits [B,H0*W0,DW] uint32 (expand with
+ * mrcnn_host_expand_mask_bits).  Blocking. */
 int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, int molded_on_host,
                                const float* metas_host, const int* orig_hw,
                                const int32_t* windows_host, int32_t* rois_host,
                                int32_t* class_ids_host, float* scores_host, int32_t* counts_host,
-                               uint8_t* masks_host);
+                               uint32_t* mask_bits_host);
 /* The whole hot path from FITS-like maps in ONE call: maps [B,map_h,map_w] float32 (HOST when
  * maps_on_host != 0, else DEVICE; NaN allowed) -> zscale/uint8 RGB (read_fits, mrcnn/utils.py:
  * 1090-1208) -> resize to (out_h,out_w), pad at (top,left), minus mean (mold_inputs, mrcnn/model.py:
  * 2519-2556) -> graph -> unmold against the original (map_h,map_w) frame.  metas / windows: HOST.
+ * mask_format: 1 = full-frame masks as pixel-major bits (device tensor "unmold_mask_bits", copied to mask_bits_host
+ * [B,H0*W0,DW] uint32 when that pointer is given); 0 = [B,H0,W0,D] uint8 kept on the device only (tensor "unmold_masks",
+ * consumed by the mrcnn.analyze bit-plane kernels; mask_bits_host must be NULL).
  * Host result pointers may be NULL (all of them = results stay on the device, readable through
- * mrcnn_engine_tensor "unmold_rois"/"unmold_class_ids"/"unmold_scores"/"unmold_counts"/"unmold_masks"; the result
- * slot of a call is mrcnn_engine_next_slot() read before it, slot 1 names carry the suffix "#1").  Blocking unless async. */
+ * mrcnn_engine_tensor "unmold_rois"/"unmold_class_ids"/"unmold_scores"/"unmold_counts"/"unmold_masks"|"unmold_mask_bits";
+ * the result slot of a call is mrcnn_engine_next_slot() read before it, slot 1 names carry the suffix "#1").
+ * Blocking unless async. */
 int mrcnn_engine_detect_maps(mrcnn_engine* e, const float* maps, int maps_on_host, int map_h, int map_w,
                              const float* contrasts3, const float* mean_pixel3, int out_h, int out_w,
                              int top, int left, const float* metas_host, const int32_t* windows_host,
                              int32_t* rois_host, int32_t* class_ids_host, float* scores_host,
-                             int32_t* counts_host, uint8_t* masks_host, int async);
+                             int32_t* counts_host, uint32_t* mask_bits_host, int mask_format, int async);
 /* async != 0 (with host result pointers): returns once the work is queued; the device->host copies
  * run on a second stream from double-buffered result slots, so the next call's compute overlaps
  * them.  At most two calls may be in flight; mrcnn_engine_wait() blocks until every queued copy

@@ -40,25 +40,38 @@ def _bf16(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+SECTIONS = ("backbone", "fpn", "rpn", "class", "mask")
+
+
 class OracleNet:
-    def __init__(self, weights, num_classes=4, emulate_bf16=False, threads=None):
+    def __init__(self, weights, num_classes=4, emulate_bf16=False, threads=None, trunk_fp32=False):
+        """emulate_bf16: False (fp32 everywhere), True (the engine's arithmetic everywhere) or a set of SECTIONS that
+        use the engine's arithmetic while the others stay fp32 (precision studies, tools/e2e_parity_cpu.py).
+        trunk_fp32: study variant — the ResNet residual trunk (block outputs) is stored in fp32 and only rounded to
+        bf16 where it is consumed as a GEMM operand."""
         self.w = weights
         self.nc = num_classes
-        self.emu = emulate_bf16
+        self._emu_sections = set(SECTIONS) if emulate_bf16 is True else set(emulate_bf16 or ())
+        self.emu = bool(self._emu_sections)
+        self.trunk_fp32 = trunk_fp32
         if threads:
             torch.set_num_threads(threads)
         self._cache = {}
 
     # -- parameter helpers ------------------------------------------------------------------
+    def _section(self, name):
+        self.emu = name in self._emu_sections
+
     def _kernel(self, name):
-        if name not in self._cache:
+        key = (name, self.emu)
+        if key not in self._cache:
             k = torch.from_numpy(np.ascontiguousarray(self.w[name][0]))
             if k.ndim == 4:
                 k = k.permute(3, 2, 0, 1).contiguous()    # [kh,kw,Cin,Cout] -> [Cout,Cin,kh,kw]
             if self.emu:
                 k = _bf16(k)
-            self._cache[name] = k
-        return self._cache[name]
+            self._cache[key] = k
+        return self._cache[key]
 
     def _bias(self, name):
         return torch.from_numpy(self.w[name][1])
@@ -73,7 +86,7 @@ class OracleNet:
         t = (b - mu) * s + be
         return s.float(), t.float()
 
-    def _finish(self, acc, conv, bn, relu, residual=None):
+    def _finish(self, acc, conv, bn, relu, residual=None, keep_f32=False):
         if self.emu:
             s, t = self._affine(conv, bn)
             y = acc * s.view(1, -1, 1, 1) + t.view(1, -1, 1, 1)
@@ -86,11 +99,13 @@ class OracleNet:
             y = y + residual
         if relu:
             y = F.relu(y)
-        return _bf16(y) if self.emu else y
+        return _bf16(y) if (self.emu and not keep_f32) else y
 
-    def conv(self, x, name, bn=None, relu=False, stride=1, pad=0, residual=None):
+    def conv(self, x, name, bn=None, relu=False, stride=1, pad=0, residual=None, keep_f32=False):
+        if self.emu:
+            x = _bf16(x)          # GEMM operands are bf16 (a no-op for activations that were stored as bf16)
         acc = F.conv2d(x, self._kernel(name), None, stride=stride, padding=pad)
-        return self._finish(acc, name, bn, relu, residual)
+        return self._finish(acc, name, bn, relu, residual, keep_f32)
 
     # -- backbone + FPN ---------------------------------------------------------------------
     def _block(self, x, stage, blk, first, stride):
@@ -99,13 +114,14 @@ class OracleNet:
         y = self.conv(x, base + "2a", bnb + "2a", relu=True, stride=stride)
         y = self.conv(y, base + "2b", bnb + "2b", relu=True, pad=1)
         if first:
-            sc = self.conv(x, base + "1", bnb + "1", relu=False, stride=stride)
+            sc = self.conv(x, base + "1", bnb + "1", relu=False, stride=stride, keep_f32=self.trunk_fp32)
         else:
             sc = x
-        return self.conv(y, base + "2c", bnb + "2c", relu=True, residual=sc)
+        return self.conv(y, base + "2c", bnb + "2c", relu=True, residual=sc, keep_f32=self.trunk_fp32)
 
     def backbone_fpn(self, molded):
         """molded [B,S,S,3] float32 NHWC -> dict with C2..C5, P2..P6 (NCHW torch tensors)."""
+        self._section("backbone")
         x = torch.from_numpy(np.ascontiguousarray(molded, dtype=np.float32)).permute(0, 3, 1, 2)
         if self.emu:
             x = _bf16(x)
@@ -125,6 +141,7 @@ class OracleNet:
                 stride = 2 if (first and stage > 2) else 1
                 x = self._block(x, stage, blk, first, stride)
             feats["C%d" % stage] = x
+        self._section("fpn")
         p5 = self.conv(feats["C5"], "fpn_c5p5")
         p4 = self.conv(feats["C4"], "fpn_c4p4", residual=F.interpolate(p5, scale_factor=2, mode="nearest"))
         p3 = self.conv(feats["C3"], "fpn_c3p3", residual=F.interpolate(p4, scale_factor=2, mode="nearest"))
@@ -139,6 +156,7 @@ class OracleNet:
     # -- RPN --------------------------------------------------------------------------------
     def rpn(self, feats):
         """-> rpn_class [B,A,2], rpn_bbox [B,A,4] float32 numpy (level-major anchor order)."""
+        self._section("rpn")
         cls, box = [], []
         for lv in ("P2", "P3", "P4", "P5", "P6"):
             shared = self.conv(feats[lv], "rpn_conv_shared", relu=True, pad=1)
@@ -156,6 +174,7 @@ class OracleNet:
     # -- heads ------------------------------------------------------------------------------
     def class_head(self, pooled):
         """pooled [B,N,7,7,C] float32 -> mrcnn_class [B,N,NC], mrcnn_bbox [B,N,NC,4]."""
+        self._section("class")
         B, N = pooled.shape[:2]
         x = torch.from_numpy(np.ascontiguousarray(pooled, dtype=np.float32))
         x = x.reshape(B * N, *pooled.shape[2:]).permute(0, 3, 1, 2)
@@ -176,6 +195,7 @@ class OracleNet:
 
     def mask_head(self, pooled):
         """pooled [B,N,14,14,C] float32 -> mrcnn_mask [B,N,28,28,NC]."""
+        self._section("mask")
         B, N = pooled.shape[:2]
         x = torch.from_numpy(np.ascontiguousarray(pooled, dtype=np.float32))
         x = x.reshape(B * N, *pooled.shape[2:]).permute(0, 3, 1, 2)

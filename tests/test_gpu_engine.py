@@ -371,23 +371,6 @@ def test_no_detections_above_min_confidence(weights, images):
         assert r["masks"].shape == im.shape[:2] + (0,) and r["masks"].dtype == np.float64
 
 
-def test_layer_chain_launches_are_bit_identical(weights, images, run, monkeypatch):
-    """MRCNN_B200_CHAIN=1: each ResNet stage after its strided block-a convs runs as ONE persistent launch with
-    per-(layer, M tile) dependency counters (conv_chain_kernel). The K order per output element does not depend on
-    tiling or launch structure, so every tensor must equal the default per-layer plan bit for bit."""
-    from mrcnn import model as modellib
-    monkeypatch.setenv("MRCNN_B200_CHAIN", "1")
-    m = modellib.MaskRCNN(mode="inference", config=_config(B), model_dir="/tmp/mrcnn_logs")
-    monkeypatch.delenv("MRCNN_B200_CHAIN")
-    m.set_weights(weights)
-    labels = [t[0] for t in m.step_table()] if hasattr(m, "step_table") else []
-    assert any("chain" in lb for lb in labels), "chain steps missing from the launch plan"
-    m.predict([run["molded"], run["metas"], None])
-    for name in ("C2", "C5", "P2", "P5"):
-        assert np.array_equal(m.read_tensor(name), run[name]), name
-    assert np.array_equal(m.read_tensor("detections"), run["detections"])
-
-
 def test_base_config_1024_chain_of_custody(weights):
     """Largest configuration (base Config: IMAGE_MAX_DIM = 1024, 261 888 anchors): one full detect_maps, then every
     index-producing stage bit-exact against the oracle fed with the engine's own tensors of that stage, ROIAlign
@@ -431,3 +414,56 @@ def test_base_config_1024_chain_of_custody(weights):
     assert np.array_equal(res["rois"], boxes) and np.array_equal(res["class_ids"], cls)
     assert res["masks"].shape == full.shape == (700, 700, len(cls))
     assert np.array_equal(res["masks"], full)
+
+
+def test_utils_resize_and_unmold_mask_match_oracle():
+    """utils.resize (reference wrapper mrcnn/utils.py:957-978) and utils.unmold_mask (:629-645) on the GPU, bit-exact against
+    the oracle's skimage <= 0.15 restatement: float mask up/down-scaling, uint8 RGB (scaled to [0,1]), preserve_range,
+    1x1 and empty outputs."""
+    from mrcnn import utils
+    rng = np.random.default_rng(9)
+    m = rng.uniform(0, 1, (28, 28)).astype(np.float32)
+    for shape in ((57, 41), (7, 90), (28, 28), (1, 1), (3, 1)):
+        got, want = utils.resize(m, shape), H.skimage_resize(m, shape)
+        assert got.dtype == np.float64 and got.shape == want.shape and np.array_equal(got, want), shape
+    img = rng.integers(3, 250, (33, 47, 3), dtype=np.uint8)
+    assert np.array_equal(utils.resize(img, (64, 64)), H.skimage_resize(img, (64, 64)))
+    assert np.array_equal(utils.resize(img, (20, 95), preserve_range=True), H.skimage_resize(img, (20, 95), preserve_range=True))
+    assert utils.resize(m, (0, 5)).shape == (0, 5)
+    with pytest.raises(NotImplementedError):
+        utils.resize(m, (5, 5), order=3)
+    for bbox in ((3, 4, 60, 50), (0, 0, 1, 1), (10, 10, 10, 30)):
+        got, want = utils.unmold_mask(m, bbox, (64, 64, 3)), H.unmold_mask(m, bbox, (64, 64, 3))
+        assert got.dtype == np.bool_ and np.array_equal(got, want), bbox
+
+
+def test_model_on_second_device_while_first_is_current(weights):
+    """every launch must land on the model's device / stream whatever the process-wide current device is."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from mrcnn import model as modellib
+    from mrcnn.analyze import Analyzer
+    torch.cuda.set_device(0)
+    m1 = modellib.MaskRCNN(mode="inference", config=_config(1), model_dir="/tmp/mrcnn_logs", device=1)
+    m1.set_weights(weights)
+    m0 = modellib.MaskRCNN(mode="inference", config=_config(1), model_dir="/tmp/mrcnn_logs", device=0)
+    m0.set_weights(weights)
+    torch.cuda.set_device(0)
+    maps = synth.radio_maps(1, 132)
+    r1, r0 = m1.detect_maps(maps)[0], m0.detect_maps(maps)[0]
+    assert torch.cuda.current_device() == 0
+    for k in ("rois", "class_ids", "scores", "masks"):
+        assert np.array_equal(r1[k], r0[k]), k
+    img = H.fits_to_rgb(maps[0])
+    d1, d0 = m1.detect([img])[0], m0.detect([img])[0]
+    assert np.array_equal(d1["masks"], d0["masks"]) and np.array_equal(d1["rois"], d0["rois"])
+    outs = []
+    for m in (m1, m0):
+        an = Analyzer(m, m.config)
+        an.class_names, an.score_thr, an.image, an.image_id = ["bkg", "sidelobe", "source", "galaxy"], 0.3, img, "x"
+        r = m.detect([img])[0]
+        an.masks, an.boxes, an.class_ids, an.scores = r["masks"], r["rois"], r["class_ids"], r["scores"]
+        an.extract_det_masks()
+        an.make_json_results()
+        outs.append(an.results)
+    assert outs[0] == outs[1]

@@ -111,7 +111,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     lib = _native.lib()                       # loads without a GPU (static cudart, no driver needed)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mrcnn_abi_version() == 1
+    assert lib.mrcnn_abi_version() == 2
     assert ctypes.sizeof(_native.ConvDesc) == 14 * 4
     assert ctypes.sizeof(_native.EngineConfig) == (11 + 3 + 8 + 5) * 4
 
@@ -157,15 +157,17 @@ def test_result_buffer_sets_return_to_the_pool_when_the_last_view_dies():
     import torch
     from mrcnn import model as M
     pool = {}
-    pset = M._PinnedSet(torch, 2, 3, 4, 5, pin=False)
+    pset = M._PinnedSet(torch, 2, 3, 4, 5, dw=1, pin=False)
     bufs = M._lease_arrays(pool, pset)
-    assert [b.shape for b in bufs] == [(2, 3, 4), (2, 3), (2, 3), (2,), (2, 4, 5, 3)]
-    assert [b.dtype for b in bufs] == [np.int32, np.int32, np.float32, np.int32, np.uint8]
-    bufs[4][:] = 7
-    assert int(pset.tensors[4].sum()) == 7 * 2 * 4 * 5 * 3          # same memory
+    assert [b.shape for b in bufs[:6]] == [(2, 3, 4), (2, 3), (2, 3), (2,), (2, 20, 1), (2, 60)] and bufs[6] == (4, 5)
+    assert [b.dtype for b in bufs[:6]] == [np.int32, np.int32, np.float32, np.int32, np.uint32, np.uint8]
+    bufs[4][:] = 5                                                  # every pixel: detections 0 and 2
+    assert int(pset.tensors[4].sum()) == 5 * 2 * 20                 # same memory
     bufs[3][:] = [1, 2]
-    res = M.MaskRCNN._results_from_buffers(bufs, 2)
+    res = M.MaskRCNN._results_from_buffers(bufs)                    # host-only C++ expansion, no GPU needed
     assert res[1]["masks"].shape == (4, 5, 2) and res[1]["masks"].dtype == np.bool_
+    assert res[1]["masks"].flags["C_CONTIGUOUS"] and res[0]["masks"].shape == (4, 5, 1)
+    assert res[1]["masks"][:, :, 0].all() and not res[1]["masks"][:, :, 1].any() and res[0]["masks"].all()
     keep = res[1]["masks"]
     del bufs, res
     gc.collect()
@@ -173,6 +175,42 @@ def test_result_buffer_sets_return_to_the_pool_when_the_last_view_dies():
     del keep
     gc.collect()
     assert pool[pset.key] == [pset]
+
+
+def test_host_expand_mask_bits_matches_numpy():
+    """mrcnn_host_expand_mask_bits (host-only C++, SIMD and portable paths, 1..n threads) against a numpy unpack:
+    ragged detection counts incl. 0, 1, 63..65 and the maximum, odd pixel counts."""
+    import ctypes
+    import subprocess
+    import sys
+    from mrcnn import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(3)
+    for D, npx in ((100, 4099), (64, 257), (256, 1000), (7, 33)):
+        dw = lib.mrcnn_mask_bits_words(D)
+        assert dw * 32 >= D and (dw & (dw - 1)) == 0
+        counts = np.array([0, 1, min(D, 63), min(D, 64), min(D, 65), D, int(rng.integers(1, D + 1))], dtype=np.int32)
+        B = len(counts)
+        bits = rng.integers(0, 2 ** 32, size=(B, npx, dw), dtype=np.uint64).astype(np.uint32)
+        want = np.unpackbits(bits.view(np.uint8).reshape(B, npx, dw * 4), axis=2, bitorder="little")
+        for threads in (1, 3, 0):
+            dense = np.full((B, npx * D + 64), 0xAB, dtype=np.uint8)
+            dst = (ctypes.c_void_p * B)(*[dense[i].ctypes.data for i in range(B)])
+            _native.check(lib.mrcnn_host_expand_mask_bits(bits.ctypes.data, B, npx, dw, counts.ctypes.data, dst, threads))
+            for i, n in enumerate(counts):
+                assert np.array_equal(dense[i, :npx * n].reshape(npx, n), want[i, :, :n]), (D, npx, i, n, threads)
+                assert (dense[i, npx * n:] == 0xAB).all(), "wrote past the image's [npx, n] block"
+    # the portable path (what a CPU without AVX-512BW runs) in a fresh process
+    code = ("import os, sys, ctypes, numpy as np; sys.path.insert(0, %r); from mrcnn import _native; lib = _native.lib();"
+            "bits = (np.arange(3 * 50 * 4, dtype=np.uint64).reshape(3, 50, 4) * 2654435761 %% 2**32).astype(np.uint32);"
+            "counts = np.array([100, 37, 8], dtype=np.int32); dense = np.zeros((3, 5000), np.uint8);"
+            "dst = (ctypes.c_void_p * 3)(*[dense[i].ctypes.data for i in range(3)]);"
+            "assert lib.mrcnn_host_expand_mask_bits(bits.ctypes.data, 3, 50, 4, counts.ctypes.data, dst, 2) == 0;"
+            "want = np.unpackbits(bits.view(np.uint8).reshape(3, 50, 16), axis=2, bitorder='little');"
+            "assert all(np.array_equal(dense[i, :50 * n].reshape(50, n), want[i, :, :n]) for i, n in enumerate(counts)); print('ok')"
+            % os.path.join(ROOT, "caesar-mrcnn_b200"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MRCNN_B200_HOST_SIMD="0"), capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr
 
 
 def test_analyzer_host_logic_matches_oracle_graph_and_iou():
@@ -396,3 +434,66 @@ def test_native_graph_mode_gives_the_same_catalogues(monkeypatch):
     test_analyzer_host_logic_reproduces_reference_goldens_with_numpy_backend()
     test_analyzer_host_pipeline_matches_oracle_with_numpy_backend()
     assert len(calls) > 30
+
+
+def test_drop_in_exports_of_survey_8b_exist():
+    """SURVEY.md §8(b) 'must export' list: code written against the reference imports these names."""
+    from mrcnn import model as M, utils as U
+    for name in ("read_fits", "get_fits_header", "resize_image", "resize", "norm_boxes", "denorm_boxes",
+                 "generate_pyramid_anchors", "unmold_mask", "extract_bboxes", "generate_tiles", "Dataset"):
+        assert hasattr(U, name), name
+    for name in ("MaskRCNN", "mold_image", "unmold_image", "compose_image_meta", "parse_image_meta", "load_image_gt"):
+        assert hasattr(M, name), name
+    with pytest.raises(NotImplementedError):
+        M.load_image_gt(None, None, 0)
+
+
+def test_extract_bboxes_matches_reference_loop():
+    """utils.extract_bboxes (vectorised) against the reference's per-instance loop (mrcnn/utils.py:49-77) restated in
+    oracle/analyze_ops.py: random masks, empty instances, single pixels, full frames, zero instances."""
+    from mrcnn import utils as U
+    from oracle import analyze_ops as A
+    rng = np.random.default_rng(2)
+    for H_, W_, n in ((17, 23, 6), (1, 9, 3), (32, 32, 0), (8, 5, 4)):
+        m = np.zeros((H_, W_, n), dtype=np.uint8)
+        for i in range(n):
+            if i % 3 == 0:
+                continue                                     # empty instance -> zeros
+            y1, x1 = int(rng.integers(0, H_)), int(rng.integers(0, W_))
+            y2, x2 = int(rng.integers(y1, H_)) + 1, int(rng.integers(x1, W_)) + 1
+            m[y1:y2, x1:x2, i] = rng.integers(0, 2, (y2 - y1, x2 - x1))
+            m[y1, x1, i] = 1
+        got = U.extract_bboxes(m)
+        assert got.dtype == np.int32 and got.shape == (n, 4)
+        want = np.array([A.extract_bbox(m[:, :, i]) for i in range(n)], dtype=np.int32).reshape(n, 4)
+        assert np.array_equal(got, want), (H_, W_, n)
+    full = np.ones((4, 6, 1), bool)
+    assert U.extract_bboxes(full).tolist() == [[0, 0, 4, 6]]
+
+
+def test_dataset_bookkeeping():
+    from mrcnn import utils as U
+    ds = U.Dataset()
+    ds.add_class("rg", 1, "sidelobe")
+    ds.add_class("rg", 2, "source, compact")
+    ds.add_class("rg", 1, "duplicate ignored")
+    ds.add_image("rg", "img7", "/data/a.fits", extra=3)
+    ds.prepare()
+    assert ds.num_classes == 3 and ds.class_names == ["BG", "sidelobe", "source"] and ds.num_images == 1
+    assert ds.map_source_class_id("rg.2") == 2 and ds.get_source_class_id(2, "rg") == 2
+    assert ds.image_from_source_map == {"rg.img7": 0} and ds.source_image_link(0) == "/data/a.fits"
+    assert sorted(ds.source_class_ids["rg"]) == [0, 1, 2] and ds.image_info[0]["extra"] == 3
+    mask, ids = ds.load_mask(0)
+    assert mask.shape == (0, 0, 0) and ids.shape == (0,)
+
+
+def test_graph_limits_are_reported_at_build_time():
+    from mrcnn import model as M
+    from mrcnn.config import Config
+
+    class Big(Config):
+        NUM_CLASSES = 9
+        DETECTION_MAX_INSTANCES = 300
+    msgs = M.graph_limit_problems(Big())
+    assert len(msgs) == 2 and "NUM_CLASSES=9" in msgs[0] and "DETECTION_MAX_INSTANCES=300" in msgs[1]
+    assert M.graph_limit_problems(Config()) == []
