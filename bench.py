@@ -216,6 +216,10 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # host threads of the result expansion: this rank's share of the cores (the ranks of one box share them)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    if "MRCNN_B200_HOST_THREADS" not in os.environ:
+        os.environ["MRCNN_B200_HOST_THREADS"] = str(max(1, min(16, (len(os.sched_getaffinity(0)) or 1) // max(1, local_world))))
     import torch
     import torch.distributed as dist
     import synth

@@ -132,8 +132,14 @@ struct mrcnn_engine {
   } slots[2];
   int cur_slot = 0;
   cudaStream_t copy_stream = nullptr;
-  // preprocessing scratch (detect_maps)
+  // preprocessing scratch (detect_maps).  Host maps of asynchronous calls are uploaded on their own stream into one
+  // of two buffers, so the H2D copy of step k+1 overlaps the compute of step k
   void* pre_maps = nullptr; size_t pre_maps_bytes = 0;
+  void* up_maps[2] = {nullptr, nullptr}; size_t up_maps_bytes[2] = {0, 0};
+  cudaEvent_t up_done[2] = {nullptr, nullptr}, up_consumed[2] = {nullptr, nullptr};
+  bool up_used[2] = {false, false};
+  int up_next = 0;
+  cudaStream_t upload_stream = nullptr;
   void* pre_rgb = nullptr; size_t pre_rgb_bytes = 0;
   void* pre_small = nullptr; size_t pre_small_bytes = 0;
 
@@ -805,6 +811,12 @@ extern "C" void mrcnn_engine_destroy(mrcnn_engine* e) {
     if (sl.copied) cudaEventDestroy(sl.copied);
   }
   if (e->pre_maps) cudaFree(e->pre_maps);
+  if (e->upload_stream) { cudaStreamSynchronize(e->upload_stream); cudaStreamDestroy(e->upload_stream); }
+  for (int k = 0; k < 2; ++k) {
+    if (e->up_maps[k]) cudaFree(e->up_maps[k]);
+    if (e->up_done[k]) cudaEventDestroy(e->up_done[k]);
+    if (e->up_consumed[k]) cudaEventDestroy(e->up_consumed[k]);
+  }
   if (e->pre_rgb) cudaFree(e->pre_rgb);
   if (e->pre_small) cudaFree(e->pre_small);
   cudaStreamDestroy(e->stream);
@@ -1270,11 +1282,32 @@ extern "C" int mrcnn_engine_detect_maps(mrcnn_engine* e, const float* maps, int 
   const mrcnn_engine_config& c = e->cfg;
   const int B = c.batch_size;
   const size_t npx = (size_t)map_h * map_w;
-  RC(ensure_scratch(e, &e->pre_maps, &e->pre_maps_bytes, (size_t)B * npx * 4));
   RC(ensure_scratch(e, &e->pre_rgb, &e->pre_rgb_bytes, (size_t)B * npx * 3));
   RC(ensure_scratch(e, &e->pre_small, &e->pre_small_bytes, (size_t)B * (12 * 4 + 2 * 4)));
   const float* d_maps = maps;
-  if (maps_on_host) {
+  int up = -1;
+  if (maps_on_host && async) {
+    // upload on the side stream into buffer `up`; the main stream only waits for the copy's event.  The buffer is
+    // recycled two calls later: the copy first waits until the preprocessing kernels that read it have run.
+    up = e->up_next;
+    e->up_next ^= 1;
+    if (!e->upload_stream) MRCNN_CHECK_CUDA(cudaStreamCreateWithFlags(&e->upload_stream, cudaStreamNonBlocking));
+    if (!e->up_done[up]) {
+      MRCNN_CHECK_CUDA(cudaEventCreateWithFlags(&e->up_done[up], cudaEventDisableTiming));
+      MRCNN_CHECK_CUDA(cudaEventCreateWithFlags(&e->up_consumed[up], cudaEventDisableTiming));
+    }
+    if (e->up_maps_bytes[up] < (size_t)B * npx * 4) {
+      if (e->up_used[up]) MRCNN_CHECK_CUDA(cudaEventSynchronize(e->up_consumed[up]));
+      RC(ensure_scratch(e, &e->up_maps[up], &e->up_maps_bytes[up], (size_t)B * npx * 4));
+      e->up_used[up] = false;
+    }
+    if (e->up_used[up]) MRCNN_CHECK_CUDA(cudaStreamWaitEvent(e->upload_stream, e->up_consumed[up], 0));
+    MRCNN_CHECK_CUDA(cudaMemcpyAsync(e->up_maps[up], maps, (size_t)B * npx * 4, cudaMemcpyHostToDevice, e->upload_stream));
+    MRCNN_CHECK_CUDA(cudaEventRecord(e->up_done[up], e->upload_stream));
+    MRCNN_CHECK_CUDA(cudaStreamWaitEvent(e->stream, e->up_done[up], 0));
+    d_maps = static_cast<const float*>(e->up_maps[up]);
+  } else if (maps_on_host) {
+    RC(ensure_scratch(e, &e->pre_maps, &e->pre_maps_bytes, (size_t)B * npx * 4));
     MRCNN_CHECK_CUDA(cudaMemcpyAsync(e->pre_maps, maps, (size_t)B * npx * 4, cudaMemcpyHostToDevice, e->stream));
     d_maps = static_cast<const float*>(e->pre_maps);
   }
@@ -1283,6 +1316,10 @@ extern "C" int mrcnn_engine_detect_maps(mrcnn_engine* e, const float* maps, int 
   uint8_t* d_rgb = static_cast<uint8_t*>(e->pre_rgb);
   RC(mrcnn_zscale_params(d_maps, B, map_h, map_w, contrasts3, d_params, e->stream));
   RC(mrcnn_stretch_to_rgb8(d_maps, d_params, B, map_h, map_w, d_rgb, d_minmax, e->stream));
+  if (up >= 0) {                     // the uploaded maps have been consumed: the buffer may be overwritten after this point
+    MRCNN_CHECK_CUDA(cudaEventRecord(e->up_consumed[up], e->stream));
+    e->up_used[up] = true;
+  }
   float* d_img = static_cast<float*>(e->tensors["input_image"].ptr);
   RC(mrcnn_resize_pad_mold(d_rgb, d_minmax, B, map_h, map_w, out_h, out_w, c.image_size, top, left, mean_pixel3, d_img, e->stream));
   RC(predict_internal(e, d_img, cudaMemcpyDeviceToDevice, metas_host, cudaMemcpyHostToDevice));

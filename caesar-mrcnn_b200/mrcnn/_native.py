@@ -115,6 +115,8 @@ SIGNATURES = {
     "mrcnn_pixel_lists_adjacent": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mrcnn_host_merge_components": (c_int, [c_int, c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p,
                                             c_void_p]),
+    "mrcnn_host_contours": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "mrcnn_host_contours_fetch": (c_int, [c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -15,8 +15,9 @@ types behave identically. `predict_maps()` is the device-resident extension: it 
 device_only=True)` and post-processes the whole batch without ever copying the [H,W,100] masks to the host.
 
 Not provided (SURVEY.md §8 marks them out of scope): ground-truth handling / performance metrics, drawing, DS9
-regions. The "vertexes" key of the JSON objects needs skimage.measure.find_contours: it is filled when scikit-image
-is importable and left as an empty list otherwise.
+regions. The "vertexes" key of the JSON objects (skimage.measure.find_contours in the reference) is computed from each
+object's pixel list by a host-only C++ restatement of the scikit-image 0.15 algorithm (csrc/host_contours.cpp; parity
+unpinned: scikit-image is absent here).
 There is no CPU fallback: every mask operation goes through libmrcnn_b200.so and needs a CUDA device.
 """
 import ctypes
@@ -468,41 +469,44 @@ def _planes_from_host(ops, masks):
     return ops.pack(d.data_ptr(), 1, H, W, n, np.arange(n, dtype=np.int32), n)
 
 
-_FIND_CONTOURS = []
-
-
-def _find_contours():
-    """skimage.measure.find_contours if scikit-image is installed, else None (looked up once: a failed import is
-    not cached by Python and would be retried for every image)."""
-    if not _FIND_CONTOURS:
-        try:
-            from skimage.measure import find_contours
-            _FIND_CONTOURS.append(find_contours)
-        except ImportError:
-            _FIND_CONTOURS.append(None)
-    return _FIND_CONTOURS[0]
+def contours_of_pixel_lists(pixel_lists):
+    """`vertexes` of a list of objects given as pixel lists (int [npix,2] (y,x) in image coordinates, origin included):
+    per object the list of contours of find_contours(zero-padded mask, 0.5), each a list of [x, y] floats — reference
+    mrcnn/analyze.py:1908-1927.  Host-only C++ behind the C ABI (csrc/host_contours.cpp: the scikit-image 0.15 algorithm
+    restated; scikit-image itself is absent here, so this key is parity-UNPINNED)."""
+    n = len(pixel_lists)
+    if n == 0:
+        return []
+    arrays = [np.ascontiguousarray(np.asarray(p, dtype=np.int32).reshape(-1, 2)) for p in pixel_lists]
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    offsets[1:] = np.cumsum([len(a) for a in arrays])
+    flat = np.ascontiguousarray(np.concatenate(arrays)) if offsets[-1] else np.zeros((0, 2), dtype=np.int32)
+    lib = _native.lib()
+    nv, nc = ctypes.c_int64(0), ctypes.c_int64(0)
+    _native.check(lib.mrcnn_host_contours(flat.ctypes.data, offsets.ctypes.data, n, ctypes.byref(nv), ctypes.byref(nc)), "host_contours")
+    verts = np.empty((nv.value, 2), dtype=np.float64)
+    c_off = np.empty(nc.value + 1, dtype=np.int64)
+    o_off = np.empty(n + 1, dtype=np.int64)
+    _native.check(lib.mrcnn_host_contours_fetch(verts.ctypes.data, c_off.ctypes.data, o_off.ctypes.data), "host_contours_fetch")
+    out = []
+    for o in range(n):
+        out.append([verts[c_off[k]:c_off[k + 1]].tolist() for k in range(o_off[o], o_off[o + 1])])
+    return out
 
 
 def build_json_results(image_id, obj_name_tag, class_names, ny, nx, xmin, ymin, masks_final, class_ids_final, scores_final,
-                       bboxes, pixels, pixels_as_lists=True):
+                       bboxes, pixels, pixels_as_lists=True, compute_vertexes=True):
     """reference: analyze.py:1866-1942. `pixels`: per object int32 [npix,2] (y,x), image origin already added
     (np.argwhere(mask==1) computed on the device). pixels_as_lists=False keeps each object's "pixels" as that int32
     array instead of a list of [y, x] lists (NumpyEncoder writes the same JSON): a batch of 64 images otherwise
     allocates ~10^5 small lists, which costs more in Python's garbage collector than the whole GPU step."""
     results = {"image_id": image_id, "objs": []}
-    find_contours = _find_contours()
+    vertexes = contours_of_pixel_lists([pixels[i] for i in range(len(class_ids_final))]) if compute_vertexes else None
     for i in range(len(class_ids_final)):
         class_id = int(class_ids_final[i])
         y1, x1, y2, x2 = (int(v) for v in bboxes[i])
         at_edge = x1 <= 0 or x1 >= nx - 1 or x2 <= 0 or x2 >= nx - 1 or y1 <= 0 or y1 >= ny - 1 or y2 <= 0 or y2 >= ny - 1
-        vertex_list = []
-        if find_contours is not None and masks_final and masks_final[i] is not None:
-            mask = masks_final[i]
-            padded = np.zeros((mask.shape[0] + 2, mask.shape[1] + 2), dtype=np.uint8)
-            padded[1:-1, 1:-1] = mask
-            for verts in find_contours(padded, 0.5):
-                vertex_list.append((np.fliplr(verts) - 1 + np.array([xmin, ymin])).tolist() if (xmin != 0 or ymin != 0)
-                                   else (np.fliplr(verts) - 1).tolist())
+        vertex_list = vertexes[i] if vertexes is not None else []
         results["objs"].append({
             "name": 'S' + str(i + 1) + "_" + obj_name_tag,
             "x1": xmin + x1, "x2": xmin + x2, "y1": ymin + y1, "y2": ymin + y2,

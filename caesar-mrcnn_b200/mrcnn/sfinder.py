@@ -28,7 +28,7 @@ import os
 import numpy as np
 
 from . import _native, fitsio, logger, utils
-from .analyze import Analyzer, Graph, NumpyEncoder, _find_contours
+from .analyze import Analyzer, Graph, NumpyEncoder, contours_of_pixel_lists
 
 
 class TileTask(object):
@@ -357,7 +357,6 @@ class SFinder(object):
             for (i, j), hit in zip(pairs, self._adjacent_on_device(srcs, pairs)):
                 if hit:
                     g.addEdge(i, j)
-        find_contours = _find_contours()
         for i, members in enumerate(g.connectedComponents()):
             sname_merged = "S" + str(i + 1) + "_merged"
             if len(members) == 1:
@@ -374,13 +373,9 @@ class SFinder(object):
             last = srcs[members[-1]]       # sic: the reference indexes with its loop variable, not with index_largest
             ymin, xmin = pixels_merged.min(axis=0)
             ymax, xmax = pixels_merged.max(axis=0)
-            vertex_list = []
-            if find_contours is not None:
-                offset = 10
-                padded = np.zeros((ymax - ymin + 1 + 2 * offset, xmax - xmin + 1 + 2 * offset), dtype=np.uint8)
-                padded[pixels_merged[:, 0] - ymin + offset, pixels_merged[:, 1] - xmin + offset] = 1
-                for verts in find_contours(padded, 0.5):
-                    vertex_list.append((np.fliplr(verts) + np.array([xmin - offset, ymin - offset])).tolist())
+            # contours of the merged mask (sfinder.py:885-910): the reference pads by 10 pixels and shifts back, which
+            # gives the same image coordinates as the unit padding of the analyzer path
+            vertex_list = contours_of_pixel_lists([pixels_merged])[0]
             self.sources["sources"].append({
                 "name": sname_merged, "x1": xmin, "x2": xmax, "y1": ymin, "y2": ymax, "edge": True, "merged": True,
                 "score": last["score"], "class_name": last["class_name"], "class_id": last["class_id"],

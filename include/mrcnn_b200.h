@@ -339,6 +339,17 @@ int mrcnn_host_merge_components(int n_frames, const int32_t* det_count, const in
                                 int64_t n_pairs, int32_t* members, int32_t* offsets, int32_t* frame_components,
                                 int32_t* n_components);
 
+/* HOST-ONLY: the `vertexes` of catalogue objects (mrcnn/analyze.py:1908-1927, mrcnn/sfinder.py:885-910):
+ * skimage.measure.find_contours(zero-padded mask, 0.5) [scikit-image 0.15 algorithm, third-party, restated; parity
+ * unpinned] computed from each object's pixel list.  pixels_yx [total,2] int32 (y, x) in image coordinates,
+ * pixel_offsets int64 [n_objects+1].  The result stays in thread-local storage: n_vertices / n_contours give its size,
+ * mrcnn_host_contours_fetch copies it out: vertices_xy [n_vertices,2] float64 (x, y) in the same coordinates
+ * (= pixel +- 0.5), contour_offsets int64 [n_contours+1] (vertex ranges, contours in skimage's order),
+ * object_offsets int64 [n_objects+1] (contour ranges). */
+int mrcnn_host_contours(const int32_t* pixels_yx, const int64_t* pixel_offsets, int n_objects, int64_t* n_vertices,
+                        int64_t* n_contours);
+int mrcnn_host_contours_fetch(double* vertices_xy, int64_t* contour_offsets, int64_t* object_offsets);
+
 #ifdef __cplusplus
 }
 #endif
