@@ -5,6 +5,7 @@
 // is the identity out[b,n] = crop(P_level(b,n)[b], boxes[b,n]), which is what is computed here.
 // Contract: ROI levels bit-exact; float32 features -> bit-exact samples (no FMA contraction);
 // bf16 features -> float32 lerp of the bf16 values, one rounding to bf16 on store.
+#include <stdlib.h>
 #include "box_ops.cuh"
 #include "mrcnn_b200.h"
 
@@ -285,6 +286,100 @@ __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiParams p) {
   }
 }
 
+// ---- row-per-warp variant for the engine's case (bf16, C = 256, P = 7 | 14) ----------------------------------------
+// The generic kernel above spends ~146 SASS instructions per output pixel and lane, of which only 72 are the
+// bilinear arithmetic (32 bf16->f32 unpacks, 36 packed fp32 ops that must not be contracted, 4 packs): the rest is
+// per-pixel table lookups, 64-bit address assembly and loop bookkeeping, and the kernel is issue-bound (ncu: 70-77 %
+// issue-slot utilisation, DRAM traffic = the algorithmic bytes).  Here one warp owns a whole output ROW of the crop:
+// the two source-row pointers and the y weight are set up once per row, the column loop is fully unrolled (P is a
+// template parameter) with one 16-byte table entry per column, every gather address is one 64-bit add of a
+// precomputed BYTE offset, the store offset is an immediate, and the loads of pixel ix+1 are issued before the
+// arithmetic of pixel ix.  Same operations in the same order on the same values: bit-identical output.
+struct __align__(16) AxisEnt {
+  uint32_t lo, hi;      // byte offsets of the floor / ceil source row (x W*C*2) or column (x C*2); valid only if ok
+  float w;              // lerp weight
+  int ok;               // sample lies inside [0, D-1] (tf.image.crop_and_resize extrapolates to 0 outside)
+};
+
+template <int P>
+__global__ void __launch_bounds__(ROI_THREADS) roialign_rows_kernel(RoiParams p) {
+  pdl_prologue();
+  __shared__ AxisEnt s_ax[2][P];      // [0] rows, [1] columns
+  const int roi = blockIdx.x;         // b*N + n
+  const int b = roi / p.N;
+  const float* bp = p.boxes + (size_t)roi * p.box_stride;
+  const int li = p.levels[roi] - 2;
+  const int H = p.H[li], W = p.W[li];
+  constexpr int C = 256;
+  if (threadIdx.x < 2 * P) {
+    const int axis = threadIdx.x / P, i = threadIdx.x - axis * P;
+    const float a1 = axis == 0 ? bp[0] : bp[1], a2 = axis == 0 ? bp[2] : bp[3];
+    const float Dm1 = (float)((axis == 0 ? H : W) - 1);
+    const float sc = __fdiv_rn(__fmul_rn(__fsub_rn(a2, a1), Dm1), (float)(P - 1));
+    const float in = __fadd_rn(__fmul_rn(a1, Dm1), __fmul_rn((float)i, sc));
+    AxisEnt e;
+    e.lo = 0u; e.hi = 0u; e.w = 0.f; e.ok = 0;
+    if ((in >= 0.f) && (in <= Dm1)) {
+      const float f = floorf(in);
+      const uint32_t mul = (axis == 0 ? (uint32_t)W * C : (uint32_t)C) * 2u;
+      e.lo = (uint32_t)(int)f * mul;
+      e.hi = (uint32_t)(int)ceilf(in) * mul;
+      e.w = __fsub_rn(in, f);
+      e.ok = 1;
+    }
+    s_ax[axis][i] = e;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const char* fb = reinterpret_cast<const char*>(p.feat[li]) + ((size_t)b * H * W * C) * 2 + lane * 16;
+  char* ob = reinterpret_cast<char*>(p.out) + ((size_t)roi * P * P * C) * 2 + lane * 16;
+  const uint64_t one2 = p.one2;
+  for (int iy = warp; iy < P; iy += ROI_THREADS / 32) {
+    const AxisEnt re = s_ax[0][iy];
+    char* orow = ob + (size_t)iy * (P * C * 2);
+    if (!re.ok) {
+#pragma unroll
+      for (int ix = 0; ix < P; ++ix) __stcs(reinterpret_cast<uint4*>(orow + ix * (C * 2)), make_uint4(0u, 0u, 0u, 0u));
+      continue;
+    }
+    const char* r0 = fb + re.lo;
+    const char* r1 = fb + re.hi;
+    const uint64_t ly2 = f2_pack(re.w, re.w);
+    // gathers are unconditional (a column outside the map has offsets 0: a valid address whose data is ignored), so
+    // the loads of the next pixel need no predicate and the compiler can rename registers instead of copying them
+    AxisEnt ce = s_ax[1][0];
+    uint4 tl = __ldg(reinterpret_cast<const uint4*>(r0 + ce.lo));
+    uint4 tr = __ldg(reinterpret_cast<const uint4*>(r0 + ce.hi));
+    uint4 bl = __ldg(reinterpret_cast<const uint4*>(r1 + ce.lo));
+    uint4 br = __ldg(reinterpret_cast<const uint4*>(r1 + ce.hi));
+#pragma unroll
+    for (int ix = 0; ix < P; ++ix) {
+      uint4 ntl, ntr, nbl, nbr;
+      AxisEnt ne;
+      if (ix + 1 < P) {
+        ne = s_ax[1][ix + 1];
+        ntl = __ldg(reinterpret_cast<const uint4*>(r0 + ne.lo));
+        ntr = __ldg(reinterpret_cast<const uint4*>(r0 + ne.hi));
+        nbl = __ldg(reinterpret_cast<const uint4*>(r1 + ne.lo));
+        nbr = __ldg(reinterpret_cast<const uint4*>(r1 + ne.hi));
+      }
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (ce.ok) {
+        const uint64_t lx2 = f2_pack(ce.w, ce.w);
+        o.x = lerp_bf16x2(tl.x, tr.x, bl.x, br.x, lx2, ly2, one2);
+        o.y = lerp_bf16x2(tl.y, tr.y, bl.y, br.y, lx2, ly2, one2);
+        o.z = lerp_bf16x2(tl.z, tr.z, bl.z, br.z, lx2, ly2, one2);
+        o.w = lerp_bf16x2(tl.w, tr.w, bl.w, br.w, lx2, ly2, one2);
+      }
+      __stcs(reinterpret_cast<uint4*>(orow + ix * (C * 2)), o);
+      if (ix + 1 < P) {
+        ce = ne;
+        tl = ntl; tr = ntr; bl = nbl; br = nbr;
+      }
+    }
+  }
+}
+
 __global__ void roi_levels_kernel(const float* boxes, int box_stride, int n, float image_area, int32_t* levels) {
   pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,7 +430,13 @@ int launch_pyramid_roi_align(const void* const* feature_maps, const int* feat_h,
     p.levels_ready = 1;
   }
   p.one2 = 0x3f8000003f800000ull;
-  if (dtype == MRCNN_DTYPE_F32)
+  static const bool rows_variant = !(getenv("MRCNN_B200_ROIALIGN_ROWS") && getenv("MRCNN_B200_ROIALIGN_ROWS")[0] == '0');
+  if (dtype == MRCNN_DTYPE_BF16 && channels == 256 && p.levels_ready && rows_variant && (pool_size == 7 || pool_size == 14)) {
+    if (pool_size == 7)
+      MRCNN_CHECK_CUDA(mrcnn_launch(roialign_rows_kernel<7>, dim3(batch * num_boxes), dim3(ROI_THREADS), 0, st, p));
+    else
+      MRCNN_CHECK_CUDA(mrcnn_launch(roialign_rows_kernel<14>, dim3(batch * num_boxes), dim3(ROI_THREADS), 0, st, p));
+  } else if (dtype == MRCNN_DTYPE_F32)
     MRCNN_CHECK_CUDA(mrcnn_launch(roialign_kernel<float>, dim3(batch * num_boxes), dim3(ROI_THREADS), 0, st, p));
   else
     MRCNN_CHECK_CUDA(mrcnn_launch(roialign_kernel<__nv_bfloat16>, dim3(batch * num_boxes), dim3(ROI_THREADS), 0, st, p));

@@ -164,13 +164,15 @@ def test_roialign_fp32_bit_exact_and_levels(pool):
     assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), "fp32 ROIAlign not bit-exact"
 
 
-def test_roialign_bf16_within_one_rounding():
-    rng = np.random.default_rng(20)
-    B, S, C, N = 2, 128, 256, 100
+@pytest.mark.parametrize("pool,C", [(7, 256), (14, 256), (5, 256), (7, 64)])
+def test_roialign_bf16_within_one_rounding(pool, C):
+    """pool 7 / 14 with 256 channels = the engine's case (row-per-warp kernel); the others take the generic kernel"""
+    rng = np.random.default_rng(20 + pool + C)
+    B, S, N = 2, 128, 100
     fm = [torch.from_numpy(f).to(torch.bfloat16).float().numpy() for f in _pyramid(rng, B, S, C)]
     boxes = _mixed_boxes(rng, B, N)
-    out, lv = run_roialign(fm, boxes, 7, S * S, "bf16")
-    ref, rlv = GL.pyramid_roi_align(boxes, (S, S, 3), fm, (7, 7), return_levels=True)
+    out, lv = run_roialign(fm, boxes, pool, S * S, "bf16")
+    ref, rlv = GL.pyramid_roi_align(boxes, (S, S, 3), fm, (pool, pool), return_levels=True)
     assert np.array_equal(lv, rlv)
     ref_bf = torch.from_numpy(ref).to(torch.bfloat16).float().numpy()
     assert np.array_equal(out, ref_bf), "bf16 ROIAlign != bf16(round(fp32 oracle))"
