@@ -13,17 +13,14 @@
 // exactly representable: the result equals the reference's float64 arithmetic bit for bit.
 #include <stdint.h>
 #include <string.h>
-#include <deque>
-#include <unordered_map>
+#include <atomic>
 #include <vector>
+#include "host_pool.h"
 #include "mrcnn_b200.h"
 
 void mrcnn_set_error(const char* fmt, ...);
 
 namespace {
-
-typedef uint64_t Pt;   // (2*row) << 32 | (2*col) in the zero-padded local frame of the object's bounding box
-inline Pt mk(int64_t r2, int64_t c2) { return ((uint64_t)(uint32_t)r2 << 32) | (uint64_t)(uint32_t)c2; }
 
 struct Result {
   std::vector<double> verts;            // (x, y) pairs
@@ -32,65 +29,92 @@ struct Result {
 };
 thread_local Result g_res;
 
+// _assemble_contours with the dictionaries replaced by direct-indexed tables over the doubled-coordinate grid of the
+// object's padded bounding box (point key = 2*row * stride + 2*col) and the deques by singly linked point lists
+// (append / prepend / concatenate are O(1)); same decisions in the same order as the Python original.
 struct Assembler {
-  std::vector<std::deque<Pt>> contours;   // index = creation number - 1
+  int stride = 0;
+  std::vector<int> starts, ends;          // point key -> contour id, -1 = absent
+  std::vector<int> touched;               // keys to reset for the next object
+  std::vector<int> pt, nxt;               // linked point nodes
+  std::vector<int> first, last;           // per contour (index = creation order)
   std::vector<char> alive;
-  std::unordered_map<Pt, int> starts, ends;
 
-  void segment(Pt from, Pt to) {
+  void reset(int64_t PH, int64_t PW) {
+    stride = (int)(2 * PW + 1);
+    const size_t need = (size_t)(2 * PH + 1) * (size_t)stride;
+    if (starts.size() < need) {
+      starts.assign(need, -1);
+      ends.assign(need, -1);
+    } else {
+      for (int k : touched) starts[(size_t)k] = ends[(size_t)k] = -1;
+    }
+    touched.clear();
+    pt.clear(); nxt.clear(); first.clear(); last.clear(); alive.clear();
+  }
+  int node(int key) {
+    pt.push_back(key);
+    nxt.push_back(-1);
+    return (int)pt.size() - 1;
+  }
+  void segment(int from, int to) {
     if (from == to) return;
-    auto ts = starts.find(to);
-    auto he = ends.find(from);
-    const bool has_tail = ts != starts.end(), has_head = he != ends.end();
-    if (has_tail && has_head) {
-      const int tail = ts->second, head = he->second;
+    touched.push_back(from);
+    touched.push_back(to);
+    const int tail = starts[(size_t)to], head = ends[(size_t)from];
+    if (tail >= 0 && head >= 0) {
       if (tail == head) {                       // close the contour
-        contours[head].push_back(to);
-        starts.erase(to);
-        ends.erase(from);
-      } else if (tail > head) {                 // tail was created second: append it to head
-        std::deque<Pt>& h = contours[head];
-        std::deque<Pt>& t = contours[tail];
-        h.insert(h.end(), t.begin(), t.end());
-        starts.erase(to);
-        ends.erase(t.back());
-        alive[tail] = 0;
-        ends.erase(from);
-        ends[h.back()] = head;
-        t.clear();
-      } else {                                  // head was created second: prepend it to tail
-        std::deque<Pt>& h = contours[head];
-        std::deque<Pt>& t = contours[tail];
-        const Pt head_first = h.front();
-        t.insert(t.begin(), h.begin(), h.end());
-        starts.erase(head_first);
-        ends.erase(from);
-        alive[head] = 0;
-        starts.erase(to);
-        starts[t.front()] = tail;
-        h.clear();
+        const int n = node(to);
+        nxt[(size_t)last[(size_t)head]] = n;
+        last[(size_t)head] = n;
+        starts[(size_t)to] = -1;
+        ends[(size_t)from] = -1;
+      } else {
+        // head's points followed by tail's points; the contour created first keeps its identity
+        const int tail_last = pt[(size_t)last[(size_t)tail]], head_first = pt[(size_t)first[(size_t)head]];
+        nxt[(size_t)last[(size_t)head]] = first[(size_t)tail];
+        if (tail > head) {                      // tail was created second: append it to head
+          starts[(size_t)to] = -1;
+          ends[(size_t)tail_last] = -1;
+          alive[(size_t)tail] = 0;
+          ends[(size_t)from] = -1;
+          last[(size_t)head] = last[(size_t)tail];
+          ends[(size_t)tail_last] = head;
+        } else {                                // head was created second: prepend it to tail
+          starts[(size_t)head_first] = -1;
+          ends[(size_t)from] = -1;
+          alive[(size_t)head] = 0;
+          starts[(size_t)to] = -1;
+          first[(size_t)tail] = first[(size_t)head];
+          starts[(size_t)head_first] = tail;
+        }
       }
-    } else if (!has_tail && !has_head) {
-      const int id = (int)contours.size();
-      contours.emplace_back();
-      contours.back().push_back(from);
-      contours.back().push_back(to);
+    } else if (tail < 0 && head < 0) {
+      const int id = (int)first.size();
+      const int n1 = node(from), n2 = node(to);
+      nxt[(size_t)n1] = n2;
+      first.push_back(n1);
+      last.push_back(n2);
       alive.push_back(1);
-      starts[from] = id;
-      ends[to] = id;
-    } else if (has_tail) {                      // prepend to the contour that starts at `to`
-      const int tail = ts->second;
-      contours[tail].push_front(from);
-      starts.erase(to);
-      starts[from] = tail;
+      starts[(size_t)from] = id;
+      ends[(size_t)to] = id;
+    } else if (tail >= 0) {                     // prepend to the contour that starts at `to`
+      const int n = node(from);
+      nxt[(size_t)n] = first[(size_t)tail];
+      first[(size_t)tail] = n;
+      starts[(size_t)to] = -1;
+      starts[(size_t)from] = tail;
     } else {                                    // append to the contour that ends at `from`
-      const int head = he->second;
-      contours[head].push_back(to);
-      ends.erase(from);
-      ends[to] = head;
+      const int n = node(to);
+      nxt[(size_t)last[(size_t)head]] = n;
+      last[(size_t)head] = n;
+      ends[(size_t)from] = -1;
+      ends[(size_t)to] = head;
     }
   }
 };
+thread_local Assembler g_as;
+thread_local std::vector<uint8_t> g_bm;
 
 void object_contours(const int32_t* px, int64_t n, Result* out) {
   if (n <= 0) return;
@@ -102,17 +126,20 @@ void object_contours(const int32_t* px, int64_t n, Result* out) {
   }
   const int64_t h = (int64_t)y1 - y0 + 1, w = (int64_t)x1 - x0 + 1;
   const int64_t PH = h + 2, PW = w + 2;           // zero border of one pixel, as the reference pads the whole mask
-  std::vector<uint8_t> bm((size_t)(PH * PW), 0);
+  std::vector<uint8_t>& bm = g_bm;
+  bm.assign((size_t)(PH * PW), 0);
   for (int64_t i = 0; i < n; ++i) bm[(size_t)(((int64_t)px[2 * i] - y0 + 1) * PW + ((int64_t)px[2 * i + 1] - x0 + 1))] = 1;
-  Assembler as;
+  Assembler& as = g_as;
+  as.reset(PH, PW);
+  const int st = as.stride;
   for (int64_t r0 = 0; r0 + 1 < PH; ++r0) {
     const uint8_t* a = &bm[(size_t)(r0 * PW)];
     const uint8_t* b = a + PW;
     for (int64_t c0 = 0; c0 + 1 < PW; ++c0) {
       const int sq = a[c0] | (a[c0 + 1] << 1) | (b[c0] << 2) | (b[c0 + 1] << 3);
       if (sq == 0 || sq == 15) continue;
-      const Pt top = mk(2 * r0, 2 * c0 + 1), bottom = mk(2 * r0 + 2, 2 * c0 + 1);
-      const Pt left = mk(2 * r0 + 1, 2 * c0), right = mk(2 * r0 + 1, 2 * c0 + 2);
+      const int top = (int)(2 * r0) * st + (int)(2 * c0 + 1), bottom = (int)(2 * r0 + 2) * st + (int)(2 * c0 + 1);
+      const int left = (int)(2 * r0 + 1) * st + (int)(2 * c0), right = (int)(2 * r0 + 1) * st + (int)(2 * c0 + 2);
       switch (sq) {
         case 1: as.segment(top, left); break;
         case 2: as.segment(right, top); break;
@@ -131,10 +158,11 @@ void object_contours(const int32_t* px, int64_t n, Result* out) {
       }
     }
   }
-  for (size_t k = 0; k < as.contours.size(); ++k) {
+  for (size_t k = 0; k < as.first.size(); ++k) {
     if (!as.alive[k]) continue;
-    for (Pt p : as.contours[k]) {
-      const double r = (double)(uint32_t)(p >> 32) * 0.5, c = (double)(uint32_t)(p & 0xffffffffu) * 0.5;
+    for (int nd = as.first[k]; nd >= 0; nd = as.nxt[(size_t)nd]) {
+      const int key = as.pt[(size_t)nd];
+      const double r = (double)(key / st) * 0.5, c = (double)(key % st) * 0.5;
       out->verts.push_back(c - 1.0 + (double)x0);      // np.fliplr(verts) - 1 (+ origin, already part of the pixel list)
       out->verts.push_back(r - 1.0 + (double)y0);
     }
@@ -150,18 +178,43 @@ extern "C" int mrcnn_host_contours(const int32_t* pixels_yx, const int64_t* pixe
     mrcnn_set_error("host_contours: bad arguments");
     return MRCNN_STATUS_INVALID;
   }
+  for (int o = 0; o < n_objects; ++o)
+    if (pixel_offsets[o + 1] < pixel_offsets[o]) {
+      mrcnn_set_error("host_contours: pixel_offsets must be non-decreasing");
+      return MRCNN_STATUS_INVALID;
+    }
+  // objects are independent: chunks of 32 objects are handed out dynamically to the worker pool, each chunk fills its
+  // own partial result (offsets relative to the chunk), and the partials are stitched together in object order
+  constexpr int kChunk = 32;
+  const int n_chunks = (n_objects + kChunk - 1) / kChunk;
+  std::vector<Result> part((size_t)n_chunks);
+  std::atomic<int> next(0);
+  auto work = [&](int) {
+    for (;;) {
+      const int c = next.fetch_add(1, std::memory_order_relaxed);
+      if (c >= n_chunks) break;
+      Result& pr = part[(size_t)c];
+      pr.contour_off.assign(1, 0);
+      pr.object_off.assign(1, 0);
+      const int o1 = (c + 1) * kChunk < n_objects ? (c + 1) * kChunk : n_objects;
+      for (int o = c * kChunk; o < o1; ++o) {
+        object_contours(pixels_yx + 2 * pixel_offsets[o], pixel_offsets[o + 1] - pixel_offsets[o], &pr);
+        pr.object_off.push_back((int64_t)pr.contour_off.size() - 1);
+      }
+    }
+  };
+  int nt = mrcnn_host::default_threads();
+  if (nt > n_chunks) nt = n_chunks;
+  if (n_chunks > 0) mrcnn_host::Pool::get().run(nt, work);
   Result& r = g_res;
   r.verts.clear();
   r.contour_off.assign(1, 0);
   r.object_off.assign(1, 0);
-  for (int o = 0; o < n_objects; ++o) {
-    const int64_t a = pixel_offsets[o], b = pixel_offsets[o + 1];
-    if (b < a) {
-      mrcnn_set_error("host_contours: pixel_offsets must be non-decreasing");
-      return MRCNN_STATUS_INVALID;
-    }
-    object_contours(pixels_yx + 2 * a, b - a, &r);
-    r.object_off.push_back((int64_t)r.contour_off.size() - 1);
+  for (const Result& pr : part) {
+    const int64_t v0 = (int64_t)(r.verts.size() / 2), c0 = (int64_t)r.contour_off.size() - 1;
+    r.verts.insert(r.verts.end(), pr.verts.begin(), pr.verts.end());
+    for (size_t k = 1; k < pr.contour_off.size(); ++k) r.contour_off.push_back(v0 + pr.contour_off[k]);
+    for (size_t k = 1; k < pr.object_off.size(); ++k) r.object_off.push_back(c0 + pr.object_off[k]);
   }
   *n_vertices = (int64_t)(r.verts.size() / 2);
   *n_contours = (int64_t)r.contour_off.size() - 1;

@@ -18,104 +18,12 @@
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
+#include "host_pool.h"
 #include "mrcnn_b200.h"
 
 void mrcnn_set_error(const char* fmt, ...);
 
 namespace {
-
-// ---- persistent worker pool -------------------------------------------------------------------
-class Pool {
- public:
-  static Pool& get() {
-    static Pool p;
-    return p;
-  }
-  // runs fn(worker_index) on `n` threads (the caller is worker 0) and returns when all are done
-  void run(int n, const std::function<void(int)>& fn) {
-    std::lock_guard<std::mutex> serial(run_mu_);      // one parallel region at a time
-    if (n <= 1) {
-      fn(0);
-      return;
-    }
-    ensure(n - 1);
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      fn_ = &fn;
-      want_ = n - 1;
-      pending_ = n - 1;
-      ++epoch_;
-    }
-    cv_.notify_all();
-    fn(0);
-    std::unique_lock<std::mutex> lk(mu_);
-    done_cv_.wait(lk, [&] { return pending_ == 0; });
-    fn_ = nullptr;
-  }
-
- private:
-  Pool() = default;
-  ~Pool() {
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      stop_ = true;
-      ++epoch_;
-    }
-    cv_.notify_all();
-    for (auto& t : threads_) t.join();
-  }
-  void ensure(int n) {
-    while ((int)threads_.size() < n) {
-      const int id = (int)threads_.size();
-      uint64_t start_epoch;
-      {
-        std::lock_guard<std::mutex> lk(mu_);
-        start_epoch = epoch_;
-      }
-      threads_.emplace_back([this, id, start_epoch] { worker(id, start_epoch); });
-    }
-  }
-  void worker(int id, uint64_t seen) {
-    for (;;) {
-      const std::function<void(int)>* fn = nullptr;
-      {
-        std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return epoch_ != seen; });
-        seen = epoch_;
-        if (stop_) return;
-        if (id < want_) fn = fn_;
-      }
-      if (fn) {
-        (*fn)(id + 1);
-        std::lock_guard<std::mutex> lk(mu_);
-        if (--pending_ == 0) done_cv_.notify_one();
-      }
-    }
-  }
-  std::mutex run_mu_, mu_;
-  std::condition_variable cv_, done_cv_;
-  std::vector<std::thread> threads_;
-  const std::function<void(int)>* fn_ = nullptr;
-  int want_ = 0, pending_ = 0;
-  uint64_t epoch_ = 0;
-  bool stop_ = false;
-};
-
-int default_threads() {
-  static int n = 0;
-  if (n == 0) {
-    int avail = 1;
-    cpu_set_t set;
-    if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = CPU_COUNT(&set);
-    if (avail < 1) avail = 1;
-    n = avail > 16 ? 16 : avail;
-    if (const char* e = getenv("MRCNN_B200_HOST_THREADS")) {
-      const int v = atoi(e);
-      if (v >= 1 && v <= 256) n = v;
-    }
-  }
-  return n;
-}
 
 // ---- expansion kernels ------------------------------------------------------------------------
 struct Lut {
@@ -217,7 +125,7 @@ ExpandFn pick_expand() {
 
 }  // namespace
 
-extern "C" int mrcnn_host_threads(void) { return default_threads(); }
+extern "C" int mrcnn_host_threads(void) { return mrcnn_host::default_threads(); }
 
 extern "C" int mrcnn_host_expand_mask_bits(const uint32_t* bits, int n_images, int64_t pixels_per_image, int words_per_pixel,
                                            const int32_t* counts, uint8_t* const* dst, int n_threads) {
@@ -237,7 +145,7 @@ extern "C" int mrcnn_host_expand_mask_bits(const uint32_t* bits, int n_images, i
   const int64_t chunks_per_image = (pixels_per_image + chunk - 1) / chunk;
   const int64_t total = chunks_per_image * n_images;
   if (total == 0) return MRCNN_STATUS_OK;
-  int nt = n_threads > 0 ? n_threads : default_threads();
+  int nt = n_threads > 0 ? n_threads : mrcnn_host::default_threads();
   if ((int64_t)nt > total) nt = (int)total;
   std::atomic<int64_t> next(0);
   auto work = [&](int) {
@@ -252,6 +160,6 @@ extern "C" int mrcnn_host_expand_mask_bits(const uint32_t* bits, int n_images, i
       fn(bits + (size_t)b * pixels_per_image * words_per_pixel, words_per_pixel, n, p0, p1, dst[b]);
     }
   };
-  Pool::get().run(nt, work);
+  mrcnn_host::Pool::get().run(nt, work);
   return MRCNN_STATUS_OK;
 }

@@ -84,6 +84,7 @@ class _FrameResult:
         self.masks_final, self.class_ids_final, self.class_names_final = [], [], []
         self.scores_final, self.bboxes, self.captions = [], [], []
         self.pixels = []          # per final object: int32 [npix,2] (y,x) with the image origin already added
+        self.vertexes = None      # per final object: list of contours (filled by the batched path, else by build_json_results)
 
 
 class MaskPlaneOps:
@@ -267,6 +268,8 @@ class Analyzer(object):
         # predict_maps / predict_maps_stream only: False returns each object's "pixels" as an int32 [npix,2] array
         # (same JSON through write_json_results / NumpyEncoder, far fewer Python objects per batch)
         self.pixels_as_lists = False
+        # the "vertexes" key (contours of every catalogued object, mrcnn/analyze.py:1908-1927); False leaves it empty
+        self.compute_vertexes = True
 
     # -- plumbing -------------------------------------------------------------------------------
     def _plane_ops(self):
@@ -344,7 +347,8 @@ class Analyzer(object):
         shape = self.image.shape
         self.results = build_json_results(self.image_id, self.obj_name_tag, self.class_names, shape[0], shape[1],
                                           self.image_xmin, self.image_ymin, self.masks_final, self.class_ids_final,
-                                          self.scores_final, self.bboxes, self._final_pixels)
+                                          self.scores_final, self.bboxes, self._final_pixels,
+                                          compute_vertexes=self.compute_vertexes)
 
     def write_json_results(self, outfile):
         """reference: analyze.py:1945-1957 (numpy scalars are written as plain numbers)."""
@@ -435,8 +439,9 @@ class Analyzer(object):
         self.class_names = c.CLASS_NAMES
         timings = getattr(self, "_timings", None)            # development aid (tools/catalog_bench.py)
         t0 = time.perf_counter()
+        vmode = None if not self.compute_vertexes else ("lists" if self.pixels_as_lists else "arrays")
         results = analyze_frames(self._side_stream_ops(), frames, H, W, self.class_names, origins=origins, want_masks=False,
-                                 timings=timings, **self._options())
+                                 timings=timings, vertexes=vmode, **self._options())
         t1 = time.perf_counter()
         out = []
         for b, res in enumerate(results):
@@ -444,7 +449,8 @@ class Analyzer(object):
             tag = name_tags[b] if name_tags is not None else self.obj_name_tag
             out.append(build_json_results(image_id, tag, self.class_names, H, W, origins[b][1], origins[b][0],
                                           res.masks_final, res.class_ids_final, res.scores_final, res.bboxes, res.pixels,
-                                          pixels_as_lists=self.pixels_as_lists))
+                                          pixels_as_lists=self.pixels_as_lists, compute_vertexes=self.compute_vertexes,
+                                          vertexes=res.vertexes))
         if timings is not None:
             timings["analyze_frames total"] = timings.get("analyze_frames total", 0.0) + t1 - t0
             timings["host: catalogue dicts"] = timings.get("host: catalogue dicts", 0.0) + time.perf_counter() - t1
@@ -469,18 +475,17 @@ def _planes_from_host(ops, masks):
     return ops.pack(d.data_ptr(), 1, H, W, n, np.arange(n, dtype=np.int32), n)
 
 
-def contours_of_pixel_lists(pixel_lists):
-    """`vertexes` of a list of objects given as pixel lists (int [npix,2] (y,x) in image coordinates, origin included):
-    per object the list of contours of find_contours(zero-padded mask, 0.5), each a list of [x, y] floats — reference
-    mrcnn/analyze.py:1908-1927.  Host-only C++ behind the C ABI (csrc/host_contours.cpp: the scikit-image 0.15 algorithm
-    restated; scikit-image itself is absent here, so this key is parity-UNPINNED)."""
-    n = len(pixel_lists)
-    if n == 0:
+def contours_of_flat_pixels(flat, offsets, as_lists=True):
+    """`vertexes` of objects whose pixel lists are slices flat[offsets[o]:offsets[o+1]] of ONE int32 [total,2] (y,x)
+    array (image coordinates, origin included): per object the contours of find_contours(zero-padded mask, 0.5), each
+    a list of [x, y] floats (as_lists) or a float64 [n,2] array view — reference mrcnn/analyze.py:1908-1927.  Host-only
+    multi-threaded C++ behind the C ABI (csrc/host_contours.cpp: the scikit-image 0.15 algorithm restated;
+    scikit-image itself is absent here, so this key is parity-UNPINNED)."""
+    n = len(offsets) - 1
+    if n <= 0:
         return []
-    arrays = [np.ascontiguousarray(np.asarray(p, dtype=np.int32).reshape(-1, 2)) for p in pixel_lists]
-    offsets = np.zeros(n + 1, dtype=np.int64)
-    offsets[1:] = np.cumsum([len(a) for a in arrays])
-    flat = np.ascontiguousarray(np.concatenate(arrays)) if offsets[-1] else np.zeros((0, 2), dtype=np.int32)
+    flat = np.ascontiguousarray(flat, dtype=np.int32).reshape(-1, 2)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     lib = _native.lib()
     nv, nc = ctypes.c_int64(0), ctypes.c_int64(0)
     _native.check(lib.mrcnn_host_contours(flat.ctypes.data, offsets.ctypes.data, n, ctypes.byref(nv), ctypes.byref(nc)), "host_contours")
@@ -488,20 +493,34 @@ def contours_of_pixel_lists(pixel_lists):
     c_off = np.empty(nc.value + 1, dtype=np.int64)
     o_off = np.empty(n + 1, dtype=np.int64)
     _native.check(lib.mrcnn_host_contours_fetch(verts.ctypes.data, c_off.ctypes.data, o_off.ctypes.data), "host_contours_fetch")
-    out = []
-    for o in range(n):
-        out.append([verts[c_off[k]:c_off[k + 1]].tolist() for k in range(o_off[o], o_off[o + 1])])
-    return out
+    c_off, o_off = c_off.tolist(), o_off.tolist()
+    if as_lists:
+        return [[verts[c_off[k]:c_off[k + 1]].tolist() for k in range(o_off[o], o_off[o + 1])] for o in range(n)]
+    return [[verts[c_off[k]:c_off[k + 1]] for k in range(o_off[o], o_off[o + 1])] for o in range(n)]
+
+
+def contours_of_pixel_lists(pixel_lists, as_lists=True):
+    """same for a list of separate pixel lists / arrays"""
+    n = len(pixel_lists)
+    if n == 0:
+        return []
+    arrays = [p if (isinstance(p, np.ndarray) and p.dtype == np.int32 and p.ndim == 2) else
+              np.asarray(p, dtype=np.int32).reshape(-1, 2) for p in pixel_lists]
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    offsets[1:] = np.cumsum([len(a) for a in arrays])
+    flat = np.concatenate(arrays) if offsets[-1] else np.zeros((0, 2), dtype=np.int32)
+    return contours_of_flat_pixels(flat, offsets, as_lists)
 
 
 def build_json_results(image_id, obj_name_tag, class_names, ny, nx, xmin, ymin, masks_final, class_ids_final, scores_final,
-                       bboxes, pixels, pixels_as_lists=True, compute_vertexes=True):
+                       bboxes, pixels, pixels_as_lists=True, compute_vertexes=True, vertexes=None):
     """reference: analyze.py:1866-1942. `pixels`: per object int32 [npix,2] (y,x), image origin already added
     (np.argwhere(mask==1) computed on the device). pixels_as_lists=False keeps each object's "pixels" as that int32
     array instead of a list of [y, x] lists (NumpyEncoder writes the same JSON): a batch of 64 images otherwise
     allocates ~10^5 small lists, which costs more in Python's garbage collector than the whole GPU step."""
     results = {"image_id": image_id, "objs": []}
-    vertexes = contours_of_pixel_lists([pixels[i] for i in range(len(class_ids_final))]) if compute_vertexes else None
+    if vertexes is None and compute_vertexes:       # (the batched path computes them for all frames in one call)
+        vertexes = contours_of_pixel_lists([pixels[i] for i in range(len(class_ids_final))], as_lists=pixels_as_lists)
     for i in range(len(class_ids_final)):
         class_id = int(class_ids_final[i])
         y1, x1, y2, x2 = (int(v) for v in bboxes[i])
@@ -611,7 +630,7 @@ def _iou(inter, area_a, area_b):
 
 def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True, score_thr=0.7, split_masks=False,
                    merge_overlapped_masks=True, select_best_overlapped_masks=True, split_source_sidelobe=True,
-                   merge_overlap_iou_thr=0.3, timings=None):
+                   merge_overlap_iou_thr=0.3, timings=None, vertexes=None):
     """extract_det_masks (+ the pixel lists of make_json_results) for a list of frames that share one [H,W] size.
     All masks of one frame list must live in ONE device allocation laid out [n_frames,H,W,depth] when
     len(frames) > 1 (the engine's result slot), or be a single frame."""
@@ -835,8 +854,11 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
         owner = np.asarray(final_owner)
         fin_area = area[np.asarray(final_planes)]
         same_origin = all(tuple(o) == tuple(origins[0]) for o in origins)
+        vx_all = None
         if same_origin:                                          # one launch and one copy for the whole batch
             px_all, off_all = ops.pixels(fin, H, W, fin_area, origins[0][0], origins[0][1])
+            if vertexes is not None:                             # contours of every final object, one threaded C++ call
+                vx_all = contours_of_flat_pixels(px_all, off_all, as_lists=(vertexes == "lists"))
         for f in range(F):
             rows = np.nonzero(owner == f)[0]
             if not len(rows):
@@ -845,6 +867,8 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
                 px, offsets = px_all, off_all[int(rows[0]):int(rows[-1]) + 2]
             else:                                                # a frame's final planes are contiguous
                 px, offsets = ops.pixels(fin[int(rows[0]):int(rows[-1]) + 1], H, W, fin_area[rows], origins[f][0], origins[f][1])
+            if vx_all is not None:
+                results[f].vertexes = vx_all[int(rows[0]):int(rows[-1]) + 1]
             for k, row in enumerate(rows):
                 results[f].pixels.append(px[offsets[k]:offsets[k + 1]])
                 if want_masks:
