@@ -173,6 +173,257 @@ __device__ inline int heap_pop(HeapEntry* h, int& len_ref) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Pipelined exact heap pops (ProposalLayer).  std::pop_heap's bottom-up __adjust_heap (hole to a leaf,
+// then the former last element v sifts up) leaves the same array as a TOP-DOWN sift of v that stops at the
+// first level whose chosen child (the larger one, the right one on a tie) is strictly smaller than v: the
+// chosen children along a path are non-increasing, so "sift up while parent < v" ends exactly there and
+// restores every promotion below it.  A top-down pop never re-reads a level it has left, so pop j+1 can
+// run two levels behind pop j: in a round every in-flight pop loads the children of its hole, decides,
+// and fills the hole; lanes 0..7 of one warp each own one pop (a pop lasts <= 13 rounds for heaps below
+// 8192 entries, a new one starts every second round).  What the sequential order fixes and the pipeline
+// must re-establish:
+//   * v of pop j is h[n-j] AFTER all older pops: an older in-flight pop that ends at that index rewrites
+//     it.  A pop therefore re-reads its v source every round; the decisions taken with a stale v were all
+//     "continue" (chosen child >= stale v) and stay valid iff the smallest child promoted so far is still
+//     >= the new v (`xlast`, checked at every change; a violation raises `hazard`);
+//   * a pop may STOP only when no older pop is in flight (its v is final then); otherwise it and every
+//     younger pop freeze for the round while the older ones advance (lags only grow);
+//   * the last 32 pops run sequentially (for tiny heaps a v source may still have children).
+// On `hazard` (never observed; kept for rigour) the heap is rebuilt and popped sequentially from the start;
+// entries are published to the consumers only once every older pop has ended hazard-free, so nothing
+// already consumed can change.  tests/test_heap_pipeline_sim.py runs the same round-synchronous algorithm
+// on the CPU against libstdc++'s std::pop_heap.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint2 lds64(const void* p) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+__device__ __forceinline__ int ld_volatile_shared(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_shared(int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+struct PopperShared {
+  int popped;    // order[0 .. popped) is final (written by the popper warp, read by the consumers)
+  int stop;      // consumers are done: the popper may leave
+};
+
+constexpr int POP_TAIL = 32;
+
+// Whole warp (32 lanes converged).  h: valid 1-indexed max-heap of n entries whose initial array is sorted (entry q+1 =
+// {sorted_scores[q], q}); order[k] receives the id of the k-th pop.  Lane (j & 7) owns pop j; the pops in flight are
+// [jnext-8, jnext), so "the oldest active pop" and "the oldest pop that wants to stop too early" are a rotate + find-first
+// on the vote masks (uniform datapath, in the shadow of the loads).  The id of pop j+1 is the entry pop j puts into the
+// root, so nobody has to read the root.
+__device__ inline void popper_warp(HeapEntry* h, const int n, uint16_t* order, PopperShared* ps, const float* sorted_scores) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int npipe = n > POP_TAIL ? n - POP_TAIL : 0;
+  const float INF = __int_as_float(0x7f800000);
+  int c = 1, len = 0, vsrc = 1, vid = -1, pop = -1;
+  float vs = 0.f, xlast = INF;
+  bool active = false, hazard = false;
+  int jnext = 0, since = 2, round = 0, published = 0;     // warp-uniform
+  unsigned act = 0u;                                       // lanes with a pop in flight
+  bool stopped = false;
+  if (npipe > 0) {
+    if (lane == 0) {                                       // pop 0
+      order[0] = (uint16_t)h[1].id;
+      len = n - 1;
+      vsrc = n;
+      pop = 0;
+      active = true;
+    }
+  }
+  // ---- fast mode: fixed schedule (pop j starts in round 2j on lane j & 7, a lane is free again after <= 13 rounds),
+  // no freeze logic.  Valid while every pop that stops is the oldest one in flight (pops normally end in order: a pop
+  // reaches its leaf after the older ones); the first stop that comes earlier — a v larger than a child high up,
+  // which starts around pop 1200 of 6000 — is not committed: nobody stores in that round and the careful loop below
+  // takes over from the same state.
+  if (npipe > 0) {
+    int r = 0;                                             // rounds done; lane 0 holds pop 0 (started "in round 0")
+    int mystart = lane < 8 ? 2 * (lane == 0 ? 8 : lane) : INT_MAX;
+    bool handover = false;
+    while (true) {
+      if ((r & 15) == 0 && r > 0) {
+        if (__any_sync(FULL, hazard)) break;
+        const int fin = min(npipe, r >= 12 ? (r - 12) / 2 + 1 : 0);
+        if (fin > published) {
+          published = fin;
+          if (lane == 0) {
+            __threadfence_block();
+            st_volatile_shared(&ps->popped, fin);
+          }
+        }
+        if (__any_sync(FULL, ld_volatile_shared(&ps->stop) != 0)) {
+          stopped = true;
+          break;
+        }
+        if (r >= 2 * npipe + 16) break;                    // every pipelined pop has started and ended
+      }
+      if (r == mystart) {                                  // my next pop (pops lane, lane+8, ...)
+        hazard |= active;
+        pop = r >> 1;
+        if (pop < npipe) {
+          c = 1;
+          len = n - pop - 1;
+          vsrc = n - pop;
+          vid = -1;
+          xlast = INF;
+          active = true;
+        }
+        mystart += 16;
+      }
+      const int l = 2 * c;
+      const bool in = active && l <= len;
+      const uint4 kids = lds128(&h[in ? l : 2]);
+      const uint2 u = lds64(&h[vsrc]);
+      const unsigned a0 = __ballot_sync(FULL, active);
+      const int jn = min(npipe, (r >> 1) + 1);             // pops started so far: in flight are [jn-8, jn)
+      const unsigned rot0 = ((a0 | (a0 << 8)) >> (jn & 7)) & 0xffu;
+      const bool oldest = pop == jn - 9 + __ffs(rot0);     // no older pop in flight: my v is final
+      if (active && (int)u.y != vid) {
+        vs = __uint_as_float(u.x);
+        vid = (int)u.y;
+        hazard |= xlast < vs;
+      }
+      const float ls = __uint_as_float(kids.x), rs = __uint_as_float(kids.z);
+      const bool right = l < len && !(rs < ls);
+      const float xs = right ? rs : ls;
+      const int xid = (int)(right ? kids.w : kids.y);
+      const bool stop = !in || xs < vs;
+      if (__any_sync(FULL, active && stop && !oldest)) {
+        handover = true;
+        break;
+      }
+      if (active) {
+        const float ss = stop ? vs : xs;
+        const int sid = stop ? vid : xid;
+        *reinterpret_cast<uint2*>(&h[c]) = make_uint2(__float_as_uint(ss), (uint32_t)sid);
+        if (c == 1) order[pop + 1] = (uint16_t)sid;
+        xlast = stop ? xlast : xs;
+        c = stop ? c : l + (right ? 1 : 0);
+        active = !stop;
+      }
+      ++r;
+      __syncwarp();
+    }
+    // state for the careful loop: pops [0, jnext) have started, the youngest one `since` rounds ago
+    act = __ballot_sync(FULL, active);
+    jnext = min(npipe, handover ? (r >> 1) + 1 : npipe);
+    since = handover ? (r & 1) : 2;
+    if (!handover) act = stopped ? 0u : act;
+  }
+  while (!stopped && (act != 0u || jnext < npipe)) {
+    if ((++round & 15) == 0) {                             // checkpoint: publish, look for the consumers' stop flag
+      if (__any_sync(FULL, hazard)) break;
+      const unsigned rot = ((act | (act << 8)) >> (jnext & 7)) & 0xffu;
+      const int fin = rot ? jnext - 8 + __ffs(rot) : jnext;      // oldest active pop + 1: every older pop has ended
+      if (fin > published) {
+        published = fin;
+        if (lane == 0) {
+          __threadfence_block();
+          st_volatile_shared(&ps->popped, fin);
+        }
+      }
+      if (__any_sync(FULL, ld_volatile_shared(&ps->stop) != 0)) {
+        stopped = true;
+        break;
+      }
+    }
+    const int l = 2 * c;
+    const bool in = active && l <= len;                    // the hole has at least a left child
+    const uint4 kids = lds128(&h[in ? l : 2]);
+    const uint2 u = lds64(&h[vsrc]);
+    const unsigned rot = ((act | (act << 8)) >> (jnext & 7)) & 0xffu;
+    const int minpop = jnext - 9 + __ffs(rot);             // oldest pop in flight (act != 0 whenever a lane is active)
+    if (active && (int)u.y != vid) {                       // v source (re)read: first read, or an older pop ended there
+      vs = __uint_as_float(u.x);
+      vid = (int)u.y;
+      hazard |= xlast < vs;
+    }
+    const float ls = __uint_as_float(kids.x), rs = __uint_as_float(kids.z);
+    const bool right = l < len && !(rs < ls);
+    const float xs = right ? rs : ls;
+    const int xid = (int)(right ? kids.w : kids.y);
+    const bool stop = !in || xs < vs;
+    const unsigned ub = __ballot_sync(FULL, active && stop && pop != minpop);   // stop wanted, but v is not final yet
+    int stall_pop = INT_MAX;
+    if (ub != 0u) {
+      const unsigned urot = ((ub | (ub << 8)) >> (jnext & 7)) & 0xffu;
+      stall_pop = jnext - 9 + __ffs(urot);
+    }
+    if (active && pop < stall_pop) {                       // advance one level
+      const float ss = stop ? vs : xs;
+      const int sid = stop ? vid : xid;
+      *reinterpret_cast<uint2*>(&h[c]) = make_uint2(__float_as_uint(ss), (uint32_t)sid);
+      if (c == 1) order[pop + 1] = (uint16_t)sid;          // the new root is the next pop's result
+      xlast = stop ? xlast : xs;
+      c = stop ? c : l + (right ? 1 : 0);
+      active = !stop;
+    }
+    act = __ballot_sync(FULL, active);
+    if (ub == 0u) ++since;
+    const int sl = jnext & 7;
+    if (jnext < npipe && since >= 2 && !((act >> sl) & 1u)) {   // next pop: two levels behind the previous one
+      if (lane == sl) {
+        c = 1;
+        len = n - jnext - 1;
+        vsrc = n - jnext;
+        vid = -1;
+        xlast = INF;
+        pop = jnext;
+        active = true;
+      }
+      act |= 1u << sl;
+      ++jnext;
+      since = 0;
+    }
+    __syncwarp();
+  }
+  if (stopped) return;
+  hazard = __any_sync(FULL, hazard);
+  int k0 = npipe, hl = n - npipe;
+  if (hazard) {                               // rebuild the initial heap (the sorted array) and pop it sequentially
+    for (int q = lane; q < n; q += 32) {
+      HeapEntry e;
+      e.score = sorted_scores[q];
+      e.id = q;
+      h[q + 1] = e;
+    }
+    k0 = 0;
+    hl = n;
+  } else if (npipe > published) {             // every pipelined pop has ended hazard-free
+    published = npipe;
+    if (lane == 0) {
+      __threadfence_block();
+      st_volatile_shared(&ps->popped, npipe);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    for (int k = k0; k < n; ++k) {
+      const int id = heap_pop(h, hl);
+      if (k >= published) order[k] = (uint16_t)id;
+      if ((k & 63) == 63 || k == n - 1) {
+        if (k + 1 > published) {
+          published = k + 1;
+          __threadfence_block();
+          st_volatile_shared(&ps->popped, k + 1);
+        }
+        if (ld_volatile_shared(&ps->stop) != 0) break;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Block-wide greedy NMS over candidates taken in pop order, 64 at a time, LAZILY: a chunk's 64
 // candidates are tested against the boxes selected so far (kept list in shared memory) only when
 // the chunk is reached, so the work is ~64 x |selected| per chunk and stops with the NMS itself
@@ -300,5 +551,108 @@ __device__ inline int block_nms(const Box4* boxes, uint16_t* order, int n, int m
     __syncthreads();          // chunk handover: next order[] popped, kept list and count final
     count = sc->count;
   }
+  return count;
+}
+
+// block_nms for the ProposalLayer: same chunk resolution, but the popper warp runs `popper_warp` on its own and the
+// 992 workers never wait for it at a block barrier: pop positions below `first_tie` are the sorted order itself
+// (order[] pre-filled with the identity; the heap pops the unique maximum until the first equal pair reaches the
+// root), later positions are consumed as soon as the popper has published them.  `heap` == nullptr: no ties at all.
+__device__ inline int block_nms_async(const Box4* boxes, uint16_t* order, int n, int max_out, float thr,
+                                      float4* kept_box, float* kept_area, uint16_t* selected, NmsScratch* sc,
+                                      PopperShared* ps, HeapEntry* heap, const float* sorted_scores, int first_tie) {
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  if (tid == 0) {
+    sc->count = 0;
+    ps->popped = 0;
+    ps->stop = 0;
+  }
+  __syncthreads();
+  if (tid >= NMS_WORKERS) {
+    if (heap != nullptr && n > 0) popper_warp(heap, n, order, ps, sorted_scores);
+    return 0;                                  // the caller's __syncthreads() joins the warps again
+  }
+  int count = 0;
+  for (int base = 0; base < n && count < max_out; base += 64) {
+    const int n_in = min(64, n - base);
+    if (heap != nullptr && base + n_in > first_tie) {
+      if (tid == 0) {
+        while (ld_volatile_shared(&ps->popped) < base + n_in) {
+        }
+        __threadfence_block();
+      }
+      nms_workers_sync();
+    }
+    if (tid < 64) {
+      NBox nb;
+      if (tid < n_in) {
+        nb = normalise_box(boxes[order[base + tid]]);
+      } else {
+        nb.ymin = nb.xmin = nb.ymax = nb.xmax = 0.f;
+        nb.area = -1.f;
+      }
+      sc->chunk[tid] = nb;
+      sc->M[tid] = 0ull;
+      sc->sup[tid] = 0;
+    }
+    nms_workers_sync();
+    if (tid < 64 * 15) {   // candidate k = tid/15 against the kept list, 15 threads striding over it
+      const int k = tid / 15, sub = tid - k * 15;
+      const NBox cb = sc->chunk[k];
+      if (cb.area > 0.f) {
+        for (int r = sub; r < count; r += 15) {
+          const float4 kb = kept_box[r];
+          const float ih = __fsub_rn(fminf(kb.z, cb.ymax), fmaxf(kb.x, cb.ymin));
+          const float iw = __fsub_rn(fminf(kb.w, cb.xmax), fmaxf(kb.y, cb.xmin));
+          if (ih > 0.f && iw > 0.f) {
+            const float ka = kept_area[r];
+            const float inter = __fmul_rn(ih, iw);
+            if (ka > 0.f && inter != 0.0f) {
+              const float uni = __fsub_rn(__fadd_rn(ka, cb.area), inter);
+              if (__fdiv_rn(inter, uni) > thr) {
+                sc->sup[k] = 1;
+                break;
+              }
+            }
+          }
+        }
+      }
+    }
+    for (int p = tid; p < 64 * 64; p += NMS_WORKERS) {   // intra-chunk suppression matrix
+      const int i = p >> 6, j = p & 63;
+      if (j > i && j < n_in && iou_gt(sc->chunk[i], sc->chunk[j], thr)) atomicOr(&sc->M[i], 1ull << j);
+    }
+    nms_workers_sync();
+    if (tid < 32) {
+      const unsigned lo = __ballot_sync(0xffffffffu, lane < n_in && !sc->sup[lane]);
+      const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < n_in && !sc->sup[lane + 32]);
+      if (lane == 0) {
+        unsigned long long alive = (unsigned long long)lo | ((unsigned long long)hi << 32);
+        unsigned long long kept = 0ull;
+        int c = count;
+        while (alive && c < max_out) {
+          const int i = __ffsll((long long)alive) - 1;
+          alive &= ~(1ull << i);
+          kept |= 1ull << i;
+          selected[c++] = (uint16_t)(base + i);
+          alive &= ~sc->M[i];
+        }
+        sc->kept_bits = kept;
+        sc->count = c;
+      }
+    }
+    nms_workers_sync();
+    const unsigned long long kept = sc->kept_bits;
+    if (tid < 64 && ((kept >> tid) & 1ull)) {   // append in selection order
+      const int r = count + __popcll(kept & ((1ull << tid) - 1ull));
+      const NBox nb = sc->chunk[tid];
+      kept_box[r] = make_float4(nb.ymin, nb.xmin, nb.ymax, nb.xmax);
+      kept_area[r] = nb.area;
+    }
+    count = sc->count;
+    nms_workers_sync();          // kept list complete; chunk scratch free for the next round
+  }
+  if (tid == 0) st_volatile_shared(&ps->stop, 1);
   return count;
 }

@@ -243,9 +243,14 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
   uint16_t* selected = order + ((K + 1) & ~1);                          // [R]
   float4* kept_box = reinterpret_cast<float4*>(r0 + p.kept_off);         // [R]
   float* kept_area = reinterpret_cast<float*>(kept_box + R);            // [R]
-  bool tie = false;
-  for (int q = tid; q + 1 < K; q += nt) tie |= (s_scores[q] == s_scores[q + 1]);
-  const int any_tie = __syncthreads_or(tie ? 1 : 0);
+  // first pop position whose order the heap decides (first pair of equal adjacent scores); K = no ties at all
+  if (tid == 0) misc[3] = K;
+  __syncthreads();
+  for (int q = tid; q + 1 < K; q += nt)
+    if (s_scores[q] == s_scores[q + 1]) atomicMin(&misc[3], q);
+  __syncthreads();
+  const int first_tie = misc[3];
+  const bool any_tie = first_tie < K;
   if (any_tie) {
     // pushing the (already sorted) scores in order never sifts up: the array IS the initial heap
     for (int q = tid; q < K; q += nt) {
@@ -254,15 +259,16 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
       e.id = q;
       heap[q + 1] = e;
     }
-  } else {
-    for (int q = tid; q < K; q += nt) order[q] = (uint16_t)q;
   }
+  for (int q = tid; q < K; q += nt) order[q] = (uint16_t)q;      // pop order below first_tie, and everywhere without ties
   __syncthreads();
 
   if (p.phase_clocks && tid == 0) p.phase_clocks[(size_t)b * 8 + 5] = clock64();
   // ---- 6. NMS + output ------------------------------------------------------------------------
-  const int count = block_nms(boxes, order, K, R, p.thr, kept_box, kept_area, selected, sc, any_tie ? heap : nullptr);
+  PopperShared* ps = reinterpret_cast<PopperShared*>(misc + 4);
+  block_nms_async(boxes, order, K, R, p.thr, kept_box, kept_area, selected, sc, ps, any_tie ? heap : nullptr, s_scores, first_tie);
   __syncthreads();
+  const int count = sc->count;
   float4* out = reinterpret_cast<float4*>(p.rois + (size_t)b * R * 4);
   for (int r = tid; r < R; r += nt) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);

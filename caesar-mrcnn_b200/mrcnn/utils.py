@@ -161,6 +161,8 @@ def resize_image(image, min_dim=None, max_dim=None, min_scale=None, mode="square
     if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
         raise NotImplementedError("resize_image (B200 build): uint8 [H,W,3] images only")
     scale, out_hw, top_left, window, padding = square_geometry(h, w, min_dim, max_dim, min_scale, mode)
+    if scale == 1:          # no resampling (reference utils.py:514): zero padding only, on the host like the reference
+        return np.pad(image, padding, mode='constant', constant_values=0), window, scale, padding, None
     torch = _torch()
     rgb = torch.from_numpy(np.ascontiguousarray(image)).cuda().unsqueeze(0)
     molded = mold_rgb8_device(rgb, None, out_hw, max_dim, top_left, (0.0, 0.0, 0.0))
@@ -234,6 +236,79 @@ def extract_bboxes(mask):
     y2 = rows.shape[0] - rows[::-1].argmax(axis=0)
     boxes[has] = np.stack([y1, x1, y2, x2], axis=1)[has]
     return boxes
+
+
+# --------------------------------------------------------------------------------------------
+# training-path host helpers (reference: mrcnn/utils.py:147-163, 275-298, 564-622, 715-722)
+# --------------------------------------------------------------------------------------------
+
+def compute_overlaps(boxes1, boxes2):
+    """IoU matrix [len(boxes1), len(boxes2)] of pixel boxes (y1,x1,y2,x2); reference utils.compute_overlaps / compute_iou
+    (:75-97, :147-163): float64 arithmetic on whatever dtype comes in, intersection clipped at 0, no epsilon."""
+    b1 = np.asarray(boxes1)
+    b2 = np.asarray(boxes2)
+    area1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    area2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    y1 = np.maximum(b1[:, None, 0], b2[None, :, 0])
+    y2 = np.minimum(b1[:, None, 2], b2[None, :, 2])
+    x1 = np.maximum(b1[:, None, 1], b2[None, :, 1])
+    x2 = np.minimum(b1[:, None, 3], b2[None, :, 3])
+    inter = np.maximum(x2 - x1, 0) * np.maximum(y2 - y1, 0)
+    union = area1[:, None] + area2[None, :] - inter
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (inter / union).astype(np.float64)
+
+
+def box_refinement(box, gt_box):
+    """(dy, dx, log dh, log dw) that turns box into gt_box, float32 like the reference (utils.py:275-298)."""
+    box = np.asarray(box).astype(np.float32)
+    gt = np.asarray(gt_box).astype(np.float32)
+    h, w = box[:, 2] - box[:, 0], box[:, 3] - box[:, 1]
+    cy, cx = box[:, 0] + 0.5 * h, box[:, 1] + 0.5 * w
+    gh, gw = gt[:, 2] - gt[:, 0], gt[:, 3] - gt[:, 1]
+    gcy, gcx = gt[:, 0] + 0.5 * gh, gt[:, 1] + 0.5 * gw
+    return np.stack([(gcy - cy) / h, (gcx - cx) / w, np.log(gh / h), np.log(gw / w)], axis=1)
+
+
+def resize_mask(mask, scale, padding, crop=None):
+    """Instance masks [H,W,N] follow their image through resize_image: nearest-neighbour zoom (scipy, order 0, as the
+    reference calls it, utils.py:564-583), then the same crop or zero padding."""
+    import warnings
+    import scipy.ndimage
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mask = scipy.ndimage.zoom(mask, zoom=[scale, scale, 1], order=0)
+    if crop is not None:
+        y, x, h, w = crop
+        return mask[y:y + h, x:x + w]
+    return np.pad(mask, padding, mode='constant', constant_values=0)
+
+
+def minimize_mask(bbox, mask, mini_shape):
+    """Each instance mask cropped to its box and resized (bilinear, rounded) to mini_shape (utils.py:586-603)."""
+    mini = np.zeros(tuple(mini_shape) + (mask.shape[-1],), dtype=bool)
+    for i in range(mask.shape[-1]):
+        y1, x1, y2, x2 = bbox[i][:4]
+        m = mask[:, :, i].astype(bool)[y1:y2, x1:x2]
+        if m.size == 0:
+            raise Exception("Invalid bounding box with area of zero")
+        mini[:, :, i] = np.around(resize(m, mini_shape)).astype(bool)
+    return mini
+
+
+def expand_mask(bbox, mini_mask, image_shape):
+    """Inverse of minimize_mask (utils.py:606-622)."""
+    mask = np.zeros(tuple(image_shape[:2]) + (mini_mask.shape[-1],), dtype=bool)
+    for i in range(mask.shape[-1]):
+        y1, x1, y2, x2 = bbox[i][:4]
+        mask[y1:y2, x1:x2, i] = np.around(resize(mini_mask[:, :, i], (y2 - y1, x2 - x1))).astype(bool)
+    return mask
+
+
+def trim_zeros(x):
+    """Rows that are not all zero (utils.py:715-722)."""
+    assert len(x.shape) == 2
+    return x[~np.all(x == 0, axis=1)]
 
 
 class Dataset(object):

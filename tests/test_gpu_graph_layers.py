@@ -97,6 +97,44 @@ def test_proposal_all_ties_and_zero_area():
     _check_proposal(probs, bbox, anchors0)
 
 
+TIE_KINDS = ["sparse_pairs", "many_pairs", "few_values", "quantised", "saturated_head", "triples"]
+
+
+@pytest.mark.parametrize("kind", TIE_KINDS)
+def test_proposal_tie_patterns_consumed_to_the_end(kind):
+    """Differential test of the pipelined heap popper: tie patterns of every kind, and a low NMS threshold on heavily
+    overlapping boxes so the NMS pops (almost) all K candidates instead of stopping at 1000 kept after ~1100 pops.
+    The oracle's pop order is libstdc++'s std::priority_queue (oracle/nms_ref.cpp)."""
+    rng = np.random.default_rng(40 + TIE_KINDS.index(kind))
+    for A, K, R, thr in ((8184, 6000, 1000, 0.2), (16368, 6000, 1000, 0.05), (5000, 4097, 300, 0.3), (700, 6000, 1000, 0.1)):
+        probs, bbox, anchors = _rpn_inputs(rng, 2, A)
+        if thr < 0.25:                                          # big random boxes: nearly every pair overlaps
+            cy, cx = rng.random((2, A)).astype(np.float32)
+            hh, ww = (rng.random((2, A)) * 0.3 + 0.15).astype(np.float32)
+            anchors = np.stack([cy - hh, cx - ww, cy + hh, cx + ww], 1).astype(np.float32)
+        fg = rng.random((2, A)).astype(np.float32) * np.float32(0.98) + np.float32(0.01)
+        if kind == "sparse_pairs":
+            for b in range(2):
+                idx = rng.integers(0, A - 1, 12)
+                fg[b, idx] = fg[b, idx + 1]
+        elif kind == "many_pairs":
+            fg = (rng.integers(1, A // 3, (2, A)) / np.float32(A // 3 + 1)).astype(np.float32)
+        elif kind == "few_values":
+            fg = (rng.integers(1, 6, (2, A)) / np.float32(8)).astype(np.float32)
+        elif kind == "quantised":
+            fg = np.round(fg, 2).astype(np.float32) + np.float32(0.001)
+        elif kind == "saturated_head":
+            fg[:, rng.integers(0, A, A // 4)] = np.float32(1.0)
+        elif kind == "triples":
+            for b in range(2):
+                idx = rng.integers(0, A - 2, 40)
+                fg[b, idx] = fg[b, idx + 1] = fg[b, idx + 2]
+        probs[..., 1] = fg
+        probs[..., 0] = np.float32(1.0) - fg
+        bbox *= np.float32(0.3)                                # boxes stay near their anchors: dense overlaps
+        _check_proposal(probs, bbox, anchors, K=K, R=R, thr=thr)
+
+
 def test_proposal_1024_config_261888_anchors():
     """Base-Config size (IMAGE_MAX_DIM = 1024): A = 261 888 anchors per image, top-6000 of them, with ties."""
     rng = np.random.default_rng(5)
