@@ -17,7 +17,7 @@ namespace {
 
 constexpr int PROP_THREADS = 1024;
 constexpr int PROP_MAX_K = 6144;
-constexpr int PROP_MAX_R = 1024;
+constexpr int PROP_MAX_R = 2048;     // POST_NMS_ROIS_TRAINING = 2000 (mrcnn/config.py:98)
 
 struct PropParams {
   const float* rpn_class;  // [B,A,2]

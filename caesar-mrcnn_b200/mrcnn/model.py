@@ -84,12 +84,8 @@ def graph_limit_problems(config):
     return out
 
 
-def load_image_gt(dataset, config, image_id, augment=False, augmentation=None, use_mini_mask=False):
-    """reference: mrcnn/model.py:1277-1381 (ground-truth loading for training / ModelTester, used by
-    mrcnn/analyze.py:440-442 when ground truth is available).  The B200 build covers the detect path only:
-    importing the name works, calling it says so."""
-    raise NotImplementedError("mrcnn (B200 build): load_image_gt belongs to the training / ground-truth evaluation path, "
-                              "which is outside the detect hot path (SURVEY.md §8f rank 4)")
+# training-path functions of the reference's mrcnn.model namespace (mrcnn/model.py:1277-1381, 1536-1644, 1721-1904)
+from .training import build_rpn_targets, data_generator, load_image_gt  # noqa: E402,F401
 
 
 # --------------------------------------------------------------------------------------------
@@ -189,12 +185,17 @@ class MaskRCNN(object):
         self._engine = None
         self._weights_loaded = False
         self._device = device
+        self._graph = None
         self.keras_model = self.build(mode=mode, config=config)
 
     # -- construction ---------------------------------------------------------------------------
     def build(self, mode, config):
-        if mode != "inference":
-            raise NotImplementedError("mrcnn (B200 build): only mode='inference' is implemented (SURVEY.md §8f)")
+        if mode == "training":
+            # the training graph (mrcnn/model.py:2068-2132) lives in mrcnn/training.py; it owns its own parameters
+            from . import training
+            self._graph = training.TrainGraph(config, device=self._device)
+            self._device = self._graph.device.index
+            return self
         h, w = config.IMAGE_SHAPE[:2]
         if h / 2 ** 6 != int(h / 2 ** 6) or w / 2 ** 6 != int(w / 2 ** 6):
             raise Exception("Image size must be dividable by 2 at least 6 times "
@@ -272,6 +273,10 @@ class MaskRCNN(object):
     # -- weights --------------------------------------------------------------------------------
     def set_weights(self, weights, exclude=None, allow_missing=False):
         """weights: {layer_name: [arrays in Keras layer.weights order]}."""
+        if self.mode == "training":
+            self._graph.params.set_weights(weights, exclude=exclude)
+            self._weights_loaded = True
+            return
         if self._weights_loaded:
             raise RuntimeError("weights already loaded into this engine; create a new MaskRCNN")
         lib = self._lib
@@ -296,6 +301,89 @@ class MaskRCNN(object):
         weights = h5weights.read_keras_weights(filepath)
         self.set_weights(weights, exclude=exclude)
         self.set_log_dir(filepath)
+
+    def get_weights(self):
+        """{layer_name: [arrays in Keras layer.weights order]} of the training graph."""
+        assert self.mode == "training", "Create model in training mode."
+        return self._graph.params.get_weights()
+
+    def save_weights(self, filepath):
+        """Keras `save_weights` layout (what ModelCheckpoint(save_weights_only=True) writes, mrcnn/model.py:2452-2453)."""
+        from . import h5weights
+        w = self.get_weights()
+        h5weights.write_keras_weights(filepath, w, layer_order=[n for n, _, _ in self._graph.params.specs])
+
+    def compile(self, learning_rate, momentum):
+        """reference: mrcnn/model.py:2259-2330 — SGD(lr, momentum, clipnorm=GRADIENT_CLIP_NORM), the five weighted losses
+        and the L2 regulariser; here it creates the Trainer (bucketed all-reduce + fused optimiser kernels)."""
+        from . import training
+        assert self.mode == "training", "Create model in training mode."
+        self._trainer = training.Trainer(self._graph, learning_rate=learning_rate, momentum=momentum)
+        return self._trainer
+
+    def set_trainable(self, layer_regex, keras_model=None, indent=0, verbose=1):
+        assert self.mode == "training", "Create model in training mode."
+        self._graph.set_trainable(layer_regex)
+        if verbose > 0:
+            log("Selecting layers to train")
+            for (name, role), t in self._graph.masters.items():
+                if role == "kernel" and t.requires_grad:
+                    log("{}{:20}".format(" " * indent, name))
+
+    def train(self, train_dataset, val_dataset, learning_rate, epochs, layers, augmentation=None, custom_callbacks=None,
+              no_augmentation_sources=None, n_worker_threads=-1, class_weights=None, draw_loss=False):
+        """reference: mrcnn/model.py:2395-2517.  Same arguments; `epochs` is the total epoch count (earlier epochs of a
+        resumed run count), STEPS_PER_EPOCH batches per epoch, VALIDATION_STEPS validation batches (losses only) and one
+        weights file per epoch at `checkpoint_path` (rank 0).  Under torchrun every rank trains on its own generator and the
+        gradients are averaged over NVLink (training.GradReducer) — the replacement of ParallelModel.  TensorBoard,
+        Keras callbacks, multiprocessing loaders and the loss plot are not part of this build; returns the history dict."""
+        from . import training
+        assert self.mode == "training", "Create model in training mode."
+        if augmentation is not None or custom_callbacks or class_weights is not None:
+            raise NotImplementedError("mrcnn (B200 build): augmentation / custom_callbacks / class_weights")
+        cfg, g = self.config, self._graph
+        torch = g.torch
+        layers = training.LAYER_REGEX.get(layers, layers)
+        train_gen = training.data_generator(train_dataset, cfg, shuffle=True, batch_size=cfg.BATCH_SIZE,
+                                            no_augmentation_sources=no_augmentation_sources)
+        val_gen = training.data_generator(val_dataset, cfg, shuffle=True, batch_size=cfg.BATCH_SIZE) if val_dataset is not None else None
+        log("\nStarting at epoch {}. LR={}\n".format(self.epoch, learning_rate))
+        log("Checkpoint Path: {}".format(self.checkpoint_path))
+        self.set_trainable(layers, verbose=0)
+        trainer = self.compile(learning_rate, cfg.LEARNING_MOMENTUM)
+        trainer.broadcast_parameters()
+        rank = trainer.reducer.dist.get_rank() if trainer.reducer.world > 1 else 0
+        history = {"loss": [], "val_loss": []}
+        for n in training.LOSS_NAMES:
+            history[n] = []
+            history["val_" + n] = []
+        for epoch in range(self.epoch, epochs):
+            sums = {}
+            for _ in range(int(cfg.STEPS_PER_EPOCH)):
+                inputs, _unused = next(train_gen)
+                ls = trainer.train_step(g.to_device(inputs))
+                for k, v in ls.items():
+                    sums[k] = sums.get(k, 0.0) + float(v)
+            for k, v in sums.items():
+                history[k].append(v / max(1, int(cfg.STEPS_PER_EPOCH)))
+            if val_gen is not None and int(cfg.VALIDATION_STEPS) > 0:
+                vs = {}
+                with torch.no_grad():
+                    for _ in range(int(cfg.VALIDATION_STEPS)):
+                        inputs, _unused = next(val_gen)
+                        total, ls = g.forward(g.to_device(inputs))
+                        ls = dict(ls)
+                        ls["loss"] = total
+                        for k, v in ls.items():
+                            vs[k] = vs.get(k, 0.0) + float(v)
+                for k, v in vs.items():
+                    history["val_" + k].append(v / int(cfg.VALIDATION_STEPS))
+            log("Epoch {}/{}: ".format(epoch + 1, epochs) + " ".join("{}={:.4f}".format(k, history[k][-1]) for k in history if history[k]))
+            if rank == 0:
+                os.makedirs(self.log_dir, exist_ok=True)
+                self.save_weights(self.checkpoint_path.format(epoch=epoch + 1))
+        self.epoch = max(self.epoch, epochs)
+        return history
 
     def find_last(self):
         dir_names = next(os.walk(self.model_dir))[1]

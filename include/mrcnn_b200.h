@@ -350,6 +350,43 @@ int mrcnn_host_contours(const int32_t* pixels_yx, const int64_t* pixel_offsets, 
                         int64_t* n_contours);
 int mrcnn_host_contours_fetch(double* vertices_xy, int64_t* contour_offsets, int64_t* object_offsets);
 
+/* ---- train mode (BASELINE.json configs[4]; reference MaskRCNN(mode='training'), mrcnn/model.py:2068-2132) -----------
+ * The dense layers of the training graph are driven from mrcnn/training.py; these are its graph layers that are not
+ * contractions, plus the optimiser. */
+
+/* DetectionTargetLayer (mrcnn/model.py:570-763): per image, trim zero proposals / GT rows, IoU proposals x GT,
+ * positives (IoU >= 0.5) and negatives (< 0.5, not in a crowd box), shuffle + sub-sample to
+ * int(train_rois * roi_positive_ratio) positives and the matching negatives, box refinement targets / bbox_std_dev, and the
+ * mask_h x mask_w crop_and_resize (rounded) of the assigned GT mask.  gt_masks [B, mask_src_h, mask_src_w, max_gt] 0/1
+ * bytes (full-size masks, or mini masks with use_mini_mask = 1).  tf.random.shuffle is replaced by ascending
+ * mrcnn_shuffle_key(seed, image, stream 0 positives / 1 negatives, trimmed proposal index).  Outputs are zero padded to
+ * train_rois rows: rois [B,T,4], target_class_ids [B,T], target_bbox [B,T,4], target_mask [B,T,mask_h,mask_w];
+ * counts (optional) [B,2] = positives, negatives. */
+uint32_t mrcnn_shuffle_key(unsigned long long seed, uint32_t image, uint32_t stream, uint32_t index);
+int mrcnn_detection_targets(const float* proposals, const int32_t* gt_class_ids, const float* gt_boxes,
+                            const uint8_t* gt_masks, int batch, int num_proposals, int max_gt, int mask_src_h,
+                            int mask_src_w, int use_mini_mask, int train_rois, float roi_positive_ratio,
+                            const float* bbox_std_dev, int mask_h, int mask_w, unsigned long long seed, float* rois,
+                            int32_t* target_class_ids, float* target_bbox, float* target_mask, int32_t* counts,
+                            void* stream);
+
+/* Gradient of mrcnn_pyramid_roi_align (mrcnn/model.py:428-534) with respect to the pyramid: dpooled [B,N,P,P,C] bf16 is
+ * scattered with the forward's bilinear weights into dfeature_maps[l] [B,H_l,W_l,C] float32 (accumulated: clear them
+ * first); levels [B,N] are the forward's ROI levels. */
+int mrcnn_pyramid_roi_align_backward(float* const* dfeature_maps, const int* feat_h, const int* feat_w, int channels,
+                                     const float* boxes, const int32_t* levels, int batch, int num_boxes, int pool_size,
+                                     const void* dpooled_bf16, void* stream);
+
+/* One optimiser step over flat float32 buffers of n elements (mrcnn/model.py:2259-2297: keras SGD(lr, momentum,
+ * clipnorm=GRADIENT_CLIP_NORM) on loss + sum_w l2(WEIGHT_DECAY)(w) / size(w)):
+ *   g = grad * grad_scale + segment_reg_coef[s] * w      (s = segment of the element; coef = 2*WEIGHT_DECAY/size(w), 0 for BN)
+ *   g *= clipnorm / max(||g||_2 over ALL n elements, clipnorm)      (clipnorm <= 0: no clipping)
+ *   velocity = momentum * velocity - learning_rate * g ;  weights += velocity ;  weights_bf16 (optional) = bf16(weights)
+ * segment_start int64 [num_segments + 1] (device), sumsq_scratch: one device double. */
+int mrcnn_sgd_step(float* grad, float* weights, float* velocity, void* weights_bf16, long long n,
+                   const long long* segment_start, const float* segment_reg_coef, int num_segments, float grad_scale,
+                   float clipnorm, float learning_rate, float momentum, double* sumsq_scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
