@@ -203,6 +203,9 @@ def main():
     ap.add_argument("--image-size", type=int, default=S, help="IMAGE_MAX_DIM (256 = the run.py configuration the metric is "
                     "quoted on; 1024 = base Config stress size, use --batch 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="detect", choices=["detect", "train"], help="train: BASELINE.json configs[4] (train_bench.py)")
+    ap.add_argument("--bucket-mb", type=float, default=25.0, help="--mode train: gradient all-reduce bucket size")
+    ap.add_argument("--no-graph", action="store_true", help="--mode train: do not capture the step in a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.image_size != S or args.batch != BATCH:
@@ -214,6 +217,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.mode == "train":
+        import train_bench
+        train_bench.run_train(args, rank, world, local_rank)
         return
 
     # host threads of the result expansion: this rank's share of the cores (the ranks of one box share them)

@@ -830,7 +830,7 @@ EncodeIm2colFn get_encode_im2col_fn() {
 // NHWC activation as (C, W, H, N); the base pixel traverses the W x H output positions of a SAME conv:
 // lower corner = -pad, upper corner = pad - (k - 1); 64 channels x 128 pixels per load
 int encode_map_im2col(CUtensorMap* map, const void* ptr, const cuuint64_t* dims, const cuuint64_t* strides_bytes, int pad,
-                      int ksize) {
+                      int ksize, int pixels_per_column = BLOCK_M) {
   EncodeIm2colFn fn = get_encode_im2col_fn();
   if (!fn) {
     mrcnn_set_error("cuTensorMapEncodeIm2col unavailable (no CUDA driver?)");
@@ -840,7 +840,7 @@ int encode_map_im2col(CUtensorMap* map, const void* ptr, const cuuint64_t* dims,
   const int upper[2] = {pad - (ksize - 1), pad - (ksize - 1)};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides_bytes, lower, upper,
-                  (cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  (cuuint32_t)BLOCK_K, (cuuint32_t)pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     mrcnn_set_error("cuTensorMapEncodeIm2col failed (%d): dims [%llu,%llu,%llu,%llu]", (int)r, (unsigned long long)dims[0],
@@ -867,6 +867,201 @@ int encode_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* di
                     (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
     return MRCNN_ERR_CUDA;
   }
+  return MRCNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight gradient (train mode): dW[co, tap, ci] += sum_p dY[p, co] * X[p + tap, ci]
+//
+// GEMM with M = Cout, N = Cin (one filter tap per tile), K = pixels.  Both operands are read straight from the NHWC
+// tensors, whose contiguous dimension is the GEMM's M (dY) or N (X): MN-major UMMA operands.  A TMA box of 64 pixels x
+// 64 channels lands as 64 rows of 128 B (128B swizzle, 8-row atoms of 1024 B): exactly the canonical MN-major SW128
+// layout ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units with SBO = 1024 B between 8-pixel groups and LBO = 8192 B
+// between 64-channel chunks.  X is fetched per tap with the same im2col-mode loads as the forward pass (pixels that
+// fall into the SAME padding arrive as zeros), 64 consecutive pixels per load.  K is split over CTAs (the pixel count
+// is 10^3..10^5, the tile count 4..300) and partial tiles are accumulated with float32 red.add into dW, which has the
+// layout of the parameter itself, [Cout, KH, KW, Cin].
+//   warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2-5: TMEM -> red.global.add.f32
+// ---------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 192;
+constexpr int WG_BLOCK_K = 64;          // pixels per stage
+constexpr int WG_CHUNK_BYTES = 64 * 128;   // 64 pixels x 64 channels bf16
+
+struct WgradParams {
+  int cout, cin, taps, kw, pad, OH, OW;
+  int im2col;             // 3x3: X through im2col-mode loads
+  int k_chunks;           // ceil(P / 64)
+  int chunks_per_split;   // K partition
+  int m_tiles, n_tiles, ksplit;
+  float* out;             // [cout, taps*cin] float32
+  int out_ld;
+};
+
+template <int BLOCK_N> struct WgradCfg {
+  static constexpr int A_BYTES = 2 * WG_CHUNK_BYTES;                 // M = 128 channels of dY
+  static constexpr int B_BYTES = (BLOCK_N / 64) * WG_CHUNK_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BLOCK_N == 128 ? 6 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+// MN-major, 128B-swizzled operand: start>>4 | LBO>>4 (distance between 64-element chunks along M/N) | SBO>>4 (distance
+// between 8-row groups along K) | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
+                                                               const __grid_constant__ CUtensorMap tmap_x, const WgradParams p) {
+  using Cfg = WgradCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+  unsigned char* base_ptr = smem_raw + (base_addr - raw_addr);
+  const uint32_t bar_base = base_addr + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile of this CTA: (split, tap, n_tile, m_tile), m fastest
+  int t = blockIdx.x;
+  const int m_tile = t % p.m_tiles; t /= p.m_tiles;
+  const int n_tile = t % p.n_tiles; t /= p.n_tiles;
+  const int tap = t % p.taps;
+  const int split = t / p.taps;
+  const int kc0 = split * p.chunks_per_split;
+  const int kc1 = min(p.k_chunks, kc0 + p.chunks_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_dy) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)BLOCK_N)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    const int r = tap / p.kw, sx = tap - r * p.kw;
+    const int hw = p.OH * p.OW;
+    uint32_t stage = 0, phase = 0;
+    for (int kc = kc0; kc < kc1; ++kc) {
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t a_dst = base_addr + stage * Cfg::STAGE_BYTES;
+      const uint32_t fb = full_bar(stage);
+      if (elect_one()) {
+        mbar_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
+        const int p0 = kc * WG_BLOCK_K;
+#pragma unroll
+        for (int mc = 0; mc < 2; ++mc) tma_load_2d(a_dst + mc * WG_CHUNK_BYTES, &tmap_dy, fb, m_tile * BLOCK_M + mc * 64, p0);
+        if (p.im2col) {
+          const int n0 = p0 / hw, rem = p0 - n0 * hw;
+          const int h0 = rem / p.OW - p.pad, w0 = rem - (rem / p.OW) * p.OW - p.pad;
+#pragma unroll
+          for (int nc = 0; nc < BLOCK_N / 64; ++nc)
+            tma_load_im2col_4d(a_dst + Cfg::A_BYTES + nc * WG_CHUNK_BYTES, &tmap_x, fb, n_tile * BLOCK_N + nc * 64, w0, h0, n0,
+                               (uint16_t)sx, (uint16_t)r);
+        } else {
+#pragma unroll
+          for (int nc = 0; nc < BLOCK_N / 64; ++nc)
+            tma_load_2d(a_dst + Cfg::A_BYTES + nc * WG_CHUNK_BYTES, &tmap_x, fb, n_tile * BLOCK_N + nc * 64, p0);
+        }
+      }
+      __syncwarp();
+      if (++stage == (uint32_t)STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 1) {
+    // D = f32, A = B = bf16, both MN-major (bits 15 / 16), N = BLOCK_N, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                               ((uint32_t)(BLOCK_M >> 4) << 24);
+    uint32_t stage = 0, phase = 0;
+    for (int kc = kc0; kc < kc1; ++kc) {
+      mbar_wait(full_bar(stage), phase);
+      tcgen05_fence_after();
+      const uint32_t a_addr = base_addr + stage * Cfg::STAGE_BYTES;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < WG_BLOCK_K / UMMA_K; ++k) {
+          // 16 pixels further along K = 16 rows of 128 B
+          const uint64_t da = make_sw128_mn_desc(a_addr + k * 2048, WG_CHUNK_BYTES, 1024);
+          const uint64_t db = make_sw128_mn_desc(a_addr + Cfg::A_BYTES + k * 2048, WG_CHUNK_BYTES, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (kc == kc1 - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+      if (++stage == (uint32_t)STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (kc1 > kc0) {
+    // epilogue: warp w may read TMEM lanes 32*(w % 4)..+31 = rows (output channels) of the tile
+    const int q = warp & 3;
+    const int co = m_tile * BLOCK_M + q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tcgen05_fence_after();
+    float* orow = p.out + (size_t)co * p.out_ld + (size_t)tap * p.cin + (size_t)n_tile * BLOCK_N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (co < p.cout) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n_tile * BLOCK_N + c0 + j < p.cin) atomicAdd(orow + c0 + j, __uint_as_float(v[j]));
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
+  }
+}
+
+template <int BN> int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, cudaStream_t st) {
+  using Cfg = WgradCfg<BN>;
+  static bool attr_done[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_done[dev]) {
+    MRCNN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done[dev] = true;
+  }
+  const unsigned grid = (unsigned)(p.m_tiles * p.n_tiles * p.taps * p.ksplit);
+  MRCNN_CHECK_CUDA(mrcnn_launch(wgrad_kernel<BN>, dim3(grid), dim3(WG_THREADS), Cfg::SMEM_BYTES, st, tdy, tx, p));
+  mrcnn_count_launch(1);
   return MRCNN_OK;
 }
 
@@ -1126,4 +1321,62 @@ extern "C" int mrcnn_conv2d_bf16_simt(const mrcnn_conv_desc* d, const void* x, c
   conv_simt_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   MRCNN_CHECK_CUDA(cudaGetLastError());
   return MRCNN_OK;
+}
+
+extern "C" int mrcnn_conv2d_wgrad_bf16(const mrcnn_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
+  MRCNN_REQUIRE(d && x && dy && dw, "conv2d_wgrad: null pointer");
+  const bool k1 = d->kh == 1 && d->kw == 1 && d->pad == 0 && d->stride == 1;
+  const bool k3 = d->kh == 3 && d->kw == 3 && d->pad == 1 && d->stride == 1;
+  MRCNN_REQUIRE(k1 || k3, "conv2d_wgrad: 1x1 stride 1 or 3x3 stride 1 pad 1 only (got %dx%d stride %d pad %d)", d->kh, d->kw,
+                d->stride, d->pad);
+  MRCNN_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0, "conv2d_wgrad: empty tensor");
+  MRCNN_REQUIRE(d->cin % 64 == 0 && d->cout % 8 == 0, "conv2d_wgrad: Cin %% 64 and Cout %% 8 (got %d, %d)", d->cin, d->cout);
+  const long long P = (long long)d->n * d->h * d->w;
+  MRCNN_REQUIRE(P < (1ll << 31), "conv2d_wgrad: too many pixels");
+  CUtensorMap tdy, tx;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->cout, (cuuint64_t)P};
+    cuuint64_t strides[1] = {(cuuint64_t)d->cout * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)WG_BLOCK_K};
+    int rc = encode_map(&tdy, dy, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (k3) {
+    cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)d->cin * 2 * d->w, (cuuint64_t)d->cin * 2 * d->w * d->h};
+    int rc = encode_map_im2col(&tx, x, dims, strides, d->pad, d->kh, WG_BLOCK_K);
+    if (rc) return rc;
+  } else {
+    cuuint64_t dims[2] = {(cuuint64_t)d->cin, (cuuint64_t)P};
+    cuuint64_t strides[1] = {(cuuint64_t)d->cin * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)WG_BLOCK_K};
+    int rc = encode_map(&tx, x, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  WgradParams p;
+  p.cout = d->cout;
+  p.cin = d->cin;
+  p.taps = d->kh * d->kw;
+  p.kw = d->kw;
+  p.pad = d->pad;
+  p.OH = d->h;
+  p.OW = d->w;
+  p.im2col = k3 ? 1 : 0;
+  p.k_chunks = (int)((P + WG_BLOCK_K - 1) / WG_BLOCK_K);
+  const int bn = d->cin % 128 == 0 ? 128 : 64;
+  p.m_tiles = ceil_div(d->cout, BLOCK_M);
+  p.n_tiles = d->cin / bn;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = p.m_tiles * p.n_tiles * p.taps;
+  int ksplit = ceil_div(2 * sms, tiles);                     // about two waves of CTAs ...
+  const int max_split = p.k_chunks >= 8 ? p.k_chunks / 4 : 1;   // ... of at least 4 k-chunks each
+  if (ksplit > max_split) ksplit = max_split;
+  if (ksplit < 1) ksplit = 1;
+  p.chunks_per_split = ceil_div(p.k_chunks, ksplit);
+  p.ksplit = ceil_div(p.k_chunks, p.chunks_per_split);
+  p.out = dw;
+  p.out_ld = p.taps * d->cin;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return bn == 128 ? launch_wgrad<128>(tdy, tx, p, st) : launch_wgrad<64>(tdy, tx, p, st);
 }

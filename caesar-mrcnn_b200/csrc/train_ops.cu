@@ -33,6 +33,7 @@ struct DetTargetParams {
   float inv_ratio;               // float32(1 / ROI_POSITIVE_RATIO)
   float std_dev[4];
   unsigned long long seed;
+  const unsigned long long* seed_device;   // optional: added to seed (a replayed CUDA graph advances it on the device)
   float* rois;                   // [B,T,4]
   int32_t* target_class_ids;     // [B,T]
   float* target_bbox;            // [B,T,4]
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(DT_THREADS) detection_targets_kernel(DetTarget
   short* assign = reinterpret_cast<short*>(gsrc + DT_MAX_G);                   // [N] argmax GT of each trimmed proposal
   __shared__ int s_np, s_ng, s_nc, s_npos, s_nneg, s_warp[DT_THREADS / 32];
   const int b = blockIdx.x, tid = threadIdx.x;
+  const unsigned long long seed = p.seed + (p.seed_device ? *p.seed_device : 0ull);
   const float4* props = reinterpret_cast<const float4*>(p.proposals) + (size_t)b * p.N;
   const float4* gtb = reinterpret_cast<const float4*>(p.gt_boxes) + (size_t)b * p.G;
   const int32_t* gtc = p.gt_class_ids + (size_t)b * p.G;
@@ -163,9 +165,9 @@ __global__ void __launch_bounds__(DT_THREADS) detection_targets_kernel(DetTarget
     for (int g = 0; g < nc; ++g) crowd = fmaxf(crowd, iou_tf(bx, cbox[g]));
     assign[i] = (short)arg;
     if (best >= 0.5f) {
-      pos[atomicAdd(&s_npos, 1)] = ((unsigned long long)shuffle_key(p.seed, b, 0, i) << 32) | (unsigned)i;
+      pos[atomicAdd(&s_npos, 1)] = ((unsigned long long)shuffle_key(seed, b, 0, i) << 32) | (unsigned)i;
     } else if (best < 0.5f && crowd < 0.001f) {
-      neg[atomicAdd(&s_nneg, 1)] = ((unsigned long long)shuffle_key(p.seed, b, 1, i) << 32) | (unsigned)i;
+      neg[atomicAdd(&s_nneg, 1)] = ((unsigned long long)shuffle_key(seed, b, 1, i) << 32) | (unsigned)i;
     }
   }
   __syncthreads();
@@ -417,7 +419,8 @@ extern "C" uint32_t mrcnn_shuffle_key(unsigned long long seed, uint32_t image, u
 extern "C" int mrcnn_detection_targets(const float* proposals, const int32_t* gt_class_ids, const float* gt_boxes,
                                        const uint8_t* gt_masks, int batch, int num_proposals, int max_gt, int mask_src_h,
                                        int mask_src_w, int use_mini_mask, int train_rois, float roi_positive_ratio,
-                                       const float* bbox_std_dev, int mask_h, int mask_w, unsigned long long seed, float* rois,
+                                       const float* bbox_std_dev, int mask_h, int mask_w, unsigned long long seed,
+                                       const unsigned long long* seed_device, float* rois,
                                        int32_t* target_class_ids, float* target_bbox, float* target_mask, int32_t* counts,
                                        void* stream) {
   MRCNN_REQUIRE(proposals && gt_class_ids && gt_boxes && gt_masks && rois && target_class_ids && target_bbox && target_mask &&
@@ -443,6 +446,7 @@ extern "C" int mrcnn_detection_targets(const float* proposals, const int32_t* gt
   p.inv_ratio = (float)(1.0 / (double)roi_positive_ratio);
   for (int i = 0; i < 4; ++i) p.std_dev[i] = bbox_std_dev[i];
   p.seed = seed;
+  p.seed_device = seed_device;
   p.rois = rois;
   p.target_class_ids = target_class_ids;
   p.target_bbox = target_bbox;

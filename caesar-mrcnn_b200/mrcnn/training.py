@@ -232,8 +232,12 @@ class ParamStore(object):
                 elif kind != "bn" and role == "bias":
                     shp = (shape[2] if kind == "deconv" else shape[-1],)
                 elif kind != "bn" and role == "kernel":
-                    shp = {"conv": (shape[3], shape[0], shape[1], shape[2]), "dense": (shape[1], shape[0]),
-                           "deconv": tuple(shape)}[kind]
+                    if kind == "conv":
+                        shp = (shape[3], shape[0], shape[1], shape[2])
+                    elif kind == "dense":
+                        shp = (shape[1], shape[0])
+                    else:
+                        shp = tuple(shape)
                 else:
                     continue
                 self.entries[(name, role)] = (off, shp)
@@ -429,6 +433,8 @@ class TrainGraph(object):
                                            config.BACKBONE_STRIDES, config.RPN_ANCHOR_STRIDE)
         self.anchors_px = a
         self.anchors = torch.from_numpy(np.ascontiguousarray(utils.norm_boxes(a, config.IMAGE_SHAPE[:2]), dtype=np.float32)).to(self.device)
+        self._box_shift = torch.tensor([0., 0., 1., 1.], device=self.device)
+        self.seed_device = torch.zeros(1, dtype=torch.int64, device=self.device)     # advanced on the device every step
         self.taps = {}
 
     # -- trainable layers --------------------------------------------------------------------------------------
@@ -535,7 +541,7 @@ class TrainGraph(object):
                                                         torch.cuda.current_stream(self.device).cuda_stream), "proposal_layer")
         return rois
 
-    def detection_targets(self, rpn_rois, gt_class_ids, gt_boxes_norm, gt_masks, seed):
+    def detection_targets(self, rpn_rois, gt_class_ids, gt_boxes_norm, gt_masks, seed, seed_device=None):
         """DetectionTargetLayer (mrcnn/model.py:570-763) -> rois [B,T,4], target_class_ids [B,T] int32, target_bbox
         [B,T,4], target_mask [B,T,mh,mw] float32, counts [B,2]."""
         torch, cfg = self.torch, self.config
@@ -554,7 +560,8 @@ class TrainGraph(object):
             _native.check(self.lib.mrcnn_detection_targets(
                 _native.ptr(rpn_rois), _native.ptr(gt_class_ids), _native.ptr(gt_boxes_norm), _native.ptr(gm), B, N, G,
                 gm.shape[1], gm.shape[2], 1 if cfg.USE_MINI_MASK else 0, T, float(cfg.ROI_POSITIVE_RATIO), sd, mh, mw,
-                int(seed), _native.ptr(rois), _native.ptr(tcls), _native.ptr(tbox), _native.ptr(tmask), _native.ptr(counts),
+                int(seed), _native.ptr(seed_device), _native.ptr(rois), _native.ptr(tcls), _native.ptr(tbox), _native.ptr(tmask),
+                _native.ptr(counts),
                 torch.cuda.current_stream(self.device).cuda_stream), "detection_targets")
         return rois, tcls, tbox, tmask, counts
 
@@ -594,44 +601,44 @@ class TrainGraph(object):
     # -- losses (mrcnn/model.py:1098-1270), float32 ------------------------------------------------------------------
     def losses(self, rpn_match, rpn_bbox_t, rpn_class_logits, rpn_bbox, target_class_ids, target_bbox, target_mask,
                mrcnn_class_logits, mrcnn_bbox, mrcnn_mask, active_class_ids):
+        """The five loss graphs as masked sums: a mean over the gathered rows of the reference is sum(mask * loss) /
+        count, and "no rows -> 0" falls out of count clamped to 1 — no host decision anywhere, so the step can be
+        captured in a CUDA graph."""
         torch, F = self.torch, self.F
-        zero = torch.zeros((), dtype=torch.float32, device=self.device)
 
         def smooth_l1(t, p):
             d = (t - p).abs()
             return torch.where(d < 1.0, 0.5 * d * d, d - 0.5)
 
-        match = rpn_match.view(rpn_match.shape[0], -1)
-        used = match != 0
         out = {}
-        out["rpn_class_loss"] = F.cross_entropy(rpn_class_logits[used], (match[used] == 1).long()) if bool(used.any()) else zero
+        match = rpn_match.view(rpn_match.shape[0], -1)
+        used = (match != 0).float()
+        ce = F.cross_entropy(rpn_class_logits.reshape(-1, 2), (match == 1).long().reshape(-1), reduction="none")
+        out["rpn_class_loss"] = (ce * used.reshape(-1)).sum() / used.sum().clamp(min=1.0)
         posm = match == 1
-        if bool(posm.any()):
-            counts = posm.sum(1)
-            # batch_pack_graph: the first counts[b] target rows of image b, in image order
-            rows = torch.arange(rpn_bbox_t.shape[1], device=self.device).view(1, -1) < counts.view(-1, 1)
-            out["rpn_bbox_loss"] = smooth_l1(rpn_bbox_t[rows].float(), rpn_bbox[posm]).mean()
-        else:
-            out["rpn_bbox_loss"] = zero
-        tci = target_class_ids.long()
-        ce = F.cross_entropy(mrcnn_class_logits.reshape(-1, mrcnn_class_logits.shape[-1]), tci.reshape(-1), reduction="none")
+        # batch_pack_graph: the k-th positive anchor of image b (anchor order) goes with target row k of image b
+        row = (posm.long().cumsum(1) - 1).clamp(0, rpn_bbox_t.shape[1] - 1)
+        tgt = rpn_bbox_t.float().gather(1, row.unsqueeze(-1).expand(-1, -1, 4))
+        pf = posm.float()
+        out["rpn_bbox_loss"] = (smooth_l1(tgt, rpn_bbox) * pf.unsqueeze(-1)).sum() / (4.0 * pf.sum()).clamp(min=1.0)
+        tci = target_class_ids.long().reshape(-1)
+        nc = mrcnn_class_logits.shape[-1]
+        ce = F.cross_entropy(mrcnn_class_logits.reshape(-1, nc), tci, reduction="none")
         pred_active = active_class_ids[0].float()[mrcnn_class_logits.argmax(-1).reshape(-1)]
         out["mrcnn_class_loss"] = (ce * pred_active).sum() / pred_active.sum()
-        pos = (tci > 0).reshape(-1)
-        if bool(pos.any()):
-            ix = torch.nonzero(pos)[:, 0]
-            cls = tci.reshape(-1)[ix]
-            out["mrcnn_bbox_loss"] = smooth_l1(target_bbox.reshape(-1, 4)[ix], mrcnn_bbox.reshape(-1, mrcnn_bbox.shape[2], 4)[ix, cls]).mean()
-            mm = mrcnn_mask.reshape((-1,) + tuple(mrcnn_mask.shape[2:]))
-            y_pred = mm[ix, :, :, cls]
-            y_true = target_mask.reshape((-1,) + tuple(target_mask.shape[2:]))[ix]
-            # K.binary_crossentropy of Keras 2.2.4 / TF backend: clip to [eps, 1-eps], back to logits, sigmoid CE
-            o = y_pred.clamp(1e-7, 1.0 - 1e-7)
-            z = torch.log(o / (1.0 - o))
-            out["mrcnn_mask_loss"] = F.binary_cross_entropy_with_logits(z, y_true)
-        else:
-            out["mrcnn_bbox_loss"] = zero
-            out["mrcnn_mask_loss"] = zero
+        pos = (tci > 0).float()
+        npos = pos.sum()
+        pred = mrcnn_bbox.reshape(-1, nc, 4).gather(1, tci.view(-1, 1, 1).expand(-1, 1, 4)).squeeze(1)
+        out["mrcnn_bbox_loss"] = (smooth_l1(target_bbox.reshape(-1, 4), pred) * pos.unsqueeze(-1)).sum() / (4.0 * npos).clamp(min=1.0)
+        mm = mrcnn_mask.reshape((-1,) + tuple(mrcnn_mask.shape[2:]))
+        mh, mw = mm.shape[1], mm.shape[2]
+        y_pred = mm.gather(3, tci.view(-1, 1, 1, 1).expand(-1, mh, mw, 1)).squeeze(3)
+        y_true = target_mask.reshape(-1, mh, mw)
+        # K.binary_crossentropy of Keras 2.2.4 / TF backend: clip to [eps, 1-eps], back to logits, sigmoid CE
+        o = y_pred.clamp(1e-7, 1.0 - 1e-7)
+        z = torch.log(o / (1.0 - o))
+        bce = F.binary_cross_entropy_with_logits(z, y_true, reduction="none")
+        out["mrcnn_mask_loss"] = (bce * pos.view(-1, 1, 1)).sum() / (float(mh * mw) * npos).clamp(min=1.0)
         return out
 
     # -- one replica step -----------------------------------------------------------------------------------------------
@@ -641,16 +648,19 @@ class TrainGraph(object):
         images, image_meta, rpn_match, rpn_bbox_t, gt_class_ids, gt_boxes, gt_masks = inputs
         S = float(cfg.IMAGE_SHAPE[0])
         # norm_boxes_graph (mrcnn/model.py:3003-3017): (boxes - [0,0,1,1]) / (S-1)
-        shift = torch.tensor([0., 0., 1., 1.], device=self.device)
-        gt_norm = ((gt_boxes.float() - shift) / (S - 1.0)).contiguous()
+        gt_norm = ((gt_boxes.float() - self._box_shift) / (S - 1.0)).contiguous()
         P = self.backbone_fpn(images)
         rpn_class_logits, rpn_class, rpn_bbox = self.rpn(P)
         rpn_rois = self.proposals(rpn_class, rpn_bbox)
+        # shuffle seed of the DetectionTargetLayer: an explicit one (tests), else base + a device counter that the step
+        # advances itself (so a replayed CUDA graph draws new samples every step)
+        seed_dev = None
         if seed is None:
-            seed = self.step_seed
-            self.step_seed += 1
+            seed, seed_dev = self.step_seed, self.seed_device
         rois, tcls, tbox, tmask, counts = self.detection_targets(rpn_rois, gt_class_ids.to(torch.int32).contiguous(), gt_norm,
-                                                                 gt_masks.to(torch.uint8), seed)
+                                                                 gt_masks.to(torch.uint8), seed, seed_dev)
+        if seed_dev is not None:
+            seed_dev.add_(1)
         logits, probs, bbox = self.class_head(rois, P)
         masks = self.mask_head(rois, P)
         active = image_meta[:, 12:].to(torch.int32)
@@ -787,6 +797,8 @@ class Trainer(object):
         self.opt = SGD(graph, cfg.LEARNING_RATE if learning_rate is None else learning_rate,
                        cfg.LEARNING_MOMENTUM if momentum is None else momentum, cfg.GRADIENT_CLIP_NORM, cfg.WEIGHT_DECAY,
                        world=self.reducer.world)
+        self.timing = False            # record CUDA events around backward / all-reduce wait / optimiser
+        self._events = []
 
     def broadcast_parameters(self):
         if self.reducer.world > 1:
@@ -795,14 +807,78 @@ class Trainer(object):
                 self.reducer.dist.broadcast(buf, src=0, group=self.reducer.group)
             p.wb.copy_(p.w)
 
+    def capture(self, example_inputs):
+        """Records the whole step (forward, backward with the bucket all-reduces launched from the hooks, optimiser) into a
+        CUDA graph over static input tensors; train_step then copies a batch in and replays ~1 000 launches with one
+        call.  Parameters and the shuffle counter are restored after the warm-up runs a capture needs.  Returns False (and
+        stays eager) if the capture fails, e.g. a process-group backend that cannot be captured."""
+        g = self.graph
+        torch, p = g.torch, g.params
+        self._static = [t.clone() for t in example_inputs]
+        keep = [p.w.clone(), p.v.clone(), p.wb.clone(), g.seed_device.clone()]
+        cur = torch.cuda.current_stream(g.device)
+        side = torch.cuda.Stream(device=g.device)
+        side.wait_stream(cur)
+        ok = True
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self._eager_step(self._static, None)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(g.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                self._static_losses = self._eager_step(self._static, None)
+            self._graph = graph
+        except Exception as e:            # noqa: BLE001 — stay eager, say why
+            logging.warning("CUDA-graph capture of the training step failed (%s); running eagerly", e)
+            self._graph, ok = None, False
+            torch.cuda.synchronize(g.device)
+        for dst, src in zip((p.w, p.v, p.wb, g.seed_device), keep):
+            dst.copy_(src)
+        return ok
+
     def train_step(self, inputs, seed=None):
         """-> {loss name: float tensor (this replica)}; gradients averaged over the replicas, parameters updated."""
+        if getattr(self, "_graph", None) is not None and seed is None:
+            for dst, src in zip(self._static, inputs):
+                dst.copy_(src, non_blocking=True)
+            self._graph.replay()
+            return self._static_losses
+        return self._eager_step(inputs, seed)
+
+    def _eager_step(self, inputs, seed):
         g = self.graph
+        torch = g.torch
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if self.timing else None
+        if ev:
+            ev[0].record()
         g.params.g.zero_()
         total, ls = g.forward(inputs, seed=seed)
+        if ev:
+            ev[1].record()
         total.backward()
+        if ev:
+            ev[2].record()
         self.reducer.finish()
+        if ev:
+            ev[3].record()
         self.opt.step()
+        if ev:
+            ev[4].record()
+            self._events.append(ev)
         ls = dict(ls)
         ls["loss"] = total.detach()
         return ls
+
+    def phase_ms(self):
+        """mean ms of (forward, backward incl. the overlapped all-reduce launches, exposed all-reduce wait, optimiser) over
+        the steps recorded with timing=True; call after torch.cuda.synchronize()."""
+        if not self._events:
+            return None
+        names = ["forward", "backward", "allreduce_exposed", "optimizer"]
+        out = {n: 0.0 for n in names}
+        for ev in self._events:
+            for k, n in enumerate(names):
+                out[n] += ev[k].elapsed_time(ev[k + 1])
+        return {n: v / len(self._events) for n, v in out.items()}

@@ -163,6 +163,12 @@ typedef struct mrcnn_conv_desc {
 } mrcnn_conv_desc;
 int mrcnn_conv2d_bf16(const mrcnn_conv_desc* desc, const void* x, const void* w, const float* scale,
                       const float* shift, const void* residual, void* out, void* stream);
+/* Weight gradient of mrcnn_conv2d_bf16 for the training graph: dw[co, r, s, ci] += sum over pixels of
+ * dy[n, oh, ow, co] * x[n, oh + r - pad, ow + s - pad, ci]  (float32 accumulation into dw, which is NOT cleared: it has
+ * the [Cout, KH, KW, Cin] layout of the parameter and its gradient buffer).  x [N,H,W,Cin] bf16, dy [N,H,W,Cout] bf16;
+ * 1x1 stride 1 or 3x3 stride 1 pad 1; Cin % 64 == 0, Cout % 8 == 0.  tcgen05 GEMM over MN-major operands, K (pixels)
+ * split across CTAs.  Only n, h, w, cin, cout, kh, kw, stride, pad of the descriptor are read. */
+int mrcnn_conv2d_wgrad_bf16(const mrcnn_conv_desc* desc, const void* x, const void* dy, float* dw, void* stream);
 /* reference implementation on CUDA cores (fp32 accumulate) used only by the tests to check the
  * tcgen05 path on the device at full size */
 int mrcnn_conv2d_bf16_simt(const mrcnn_conv_desc* desc, const void* x, const void* w, const float* scale,
@@ -359,14 +365,16 @@ int mrcnn_host_contours_fetch(double* vertices_xy, int64_t* contour_offsets, int
  * int(train_rois * roi_positive_ratio) positives and the matching negatives, box refinement targets / bbox_std_dev, and the
  * mask_h x mask_w crop_and_resize (rounded) of the assigned GT mask.  gt_masks [B, mask_src_h, mask_src_w, max_gt] 0/1
  * bytes (full-size masks, or mini masks with use_mini_mask = 1).  tf.random.shuffle is replaced by ascending
- * mrcnn_shuffle_key(seed, image, stream 0 positives / 1 negatives, trimmed proposal index).  Outputs are zero padded to
+ * mrcnn_shuffle_key(seed, image, stream 0 positives / 1 negatives, trimmed proposal index); seed_device (optional, device
+ * memory) is added to seed when the kernel runs, so a replayed CUDA graph can advance it.  Outputs are zero padded to
  * train_rois rows: rois [B,T,4], target_class_ids [B,T], target_bbox [B,T,4], target_mask [B,T,mask_h,mask_w];
  * counts (optional) [B,2] = positives, negatives. */
 uint32_t mrcnn_shuffle_key(unsigned long long seed, uint32_t image, uint32_t stream, uint32_t index);
 int mrcnn_detection_targets(const float* proposals, const int32_t* gt_class_ids, const float* gt_boxes,
                             const uint8_t* gt_masks, int batch, int num_proposals, int max_gt, int mask_src_h,
                             int mask_src_w, int use_mini_mask, int train_rois, float roi_positive_ratio,
-                            const float* bbox_std_dev, int mask_h, int mask_w, unsigned long long seed, float* rois,
+                            const float* bbox_std_dev, int mask_h, int mask_w, unsigned long long seed,
+                            const unsigned long long* seed_device, float* rois,
                             int32_t* target_class_ids, float* target_bbox, float* target_mask, int32_t* counts,
                             void* stream);
 

@@ -135,3 +135,46 @@ def make_random_weights(seed=0, num_classes=4):
     return out
 
 
+# --------------------------------------------------------------------------------------------
+# training samples (BASELINE.json configs[4]: synthetic GT from the generator's own source list)
+# --------------------------------------------------------------------------------------------
+
+def training_sample(i, S=256):
+    """-> (map [S,S] float32, masks [S,S,n] bool, class_ids [n] int32).  Sources are drawn like radio_map's (compact
+    sources = class 2 'source', double-lobe sources = class 3 'galaxy', a faint ring artefact around the brightest compact
+    source = class 1 'sidelobe'); the mask of a source is where its own flux exceeds 3 sigma of the noise."""
+    rng = np.random.default_rng(99000 + i)
+    sigma = 3e-4
+    img = rng.normal(0.0, sigma, size=(S, S))
+    yy, xx = np.mgrid[0:S, 0:S].astype(np.float64)
+    bmaj, bmin, bpa = rng.uniform(3, 6), rng.uniform(3, 6), rng.uniform(0, np.pi)
+    masks, cls, peaks = [], [], []
+    for _ in range(int(rng.integers(6, 20))):
+        peak = 10 ** rng.uniform(-2.6, np.log10(5e-2))
+        y0, x0 = rng.uniform(8, S - 8, 2)
+        src = _gauss2d(S, y0, x0, bmaj, bmin, bpa, peak, yy, xx)
+        img += src
+        masks.append(src > 3 * sigma)
+        cls.append(2)
+        peaks.append((peak, y0, x0))
+    for _ in range(int(rng.integers(1, 4))):
+        y0, x0 = rng.uniform(0.2 * S, 0.8 * S, 2)
+        sep, ang = rng.uniform(6, 0.1 * S), rng.uniform(0, np.pi)
+        peak = 10 ** rng.uniform(-2.5, -1.5)
+        src = np.zeros((S, S))
+        for sgn in (-1, 1):
+            src += _gauss2d(S, y0 + sgn * sep * np.sin(ang), x0 + sgn * sep * np.cos(ang), rng.uniform(6, 12), rng.uniform(4, 8),
+                            ang, peak, yy, xx)
+        img += src
+        masks.append(src > 3 * sigma)
+        cls.append(3)
+    peak, y0, x0 = max(peaks)
+    rr = np.hypot(yy - y0, xx - x0)
+    ring = 0.02 * peak * np.exp(-0.5 * ((rr - 4 * max(bmaj, bmin)) / 1.5) ** 2)
+    img += ring
+    if (ring > 2 * sigma).any():
+        masks.append(ring > 2 * sigma)
+        cls.append(1)
+    masks = np.stack(masks, axis=-1)
+    keep = masks.sum(axis=(0, 1)) > 0
+    return img.astype(np.float32), masks[:, :, keep], np.asarray(cls, dtype=np.int32)[keep]

@@ -84,7 +84,7 @@ def run_detection_targets(props, gt_cls, gt_boxes, gt_masks, T, ratio, mask_shap
     counts = torch.empty((B, 2), dtype=torch.int32, device="cuda")
     sd = nat.float_array([0.1, 0.1, 0.2, 0.2])
     nat.check(lib.mrcnn_detection_targets(nat.ptr(d[0]), nat.ptr(d[1]), nat.ptr(d[2]), nat.ptr(d[3]), B, N, G, gt_masks.shape[1],
-                                          gt_masks.shape[2], int(mini), T, ratio, sd, mask_shape[0], mask_shape[1], seed,
+                                          gt_masks.shape[2], int(mini), T, ratio, sd, mask_shape[0], mask_shape[1], seed, None,
                                           nat.ptr(rois), nat.ptr(tcls), nat.ptr(tbox), nat.ptr(tmask), nat.ptr(counts), None),
               "detection_targets")
     torch.cuda.synchronize()
@@ -185,8 +185,9 @@ def test_sgd_step_matches_keras_restatement():
     dw, dg, dv = _dev(w), _dev(g), _dev(v)
     wb = torch.zeros(off, dtype=torch.bfloat16, device="cuda")
     sumsq = torch.zeros(1, dtype=torch.float64, device="cuda")
-    nat.check(lib.mrcnn_sgd_step(nat.ptr(dg), nat.ptr(dw), nat.ptr(dv), nat.ptr(wb), off, nat.ptr(_dev(np.array(starts, np.int64))),
-                                 nat.ptr(_dev(coefs)), len(sizes), 1.0 / world, clip, lr, mom, nat.ptr(sumsq), None), "sgd_step")
+    d_starts, d_coefs = _dev(np.array(starts, np.int64)), _dev(coefs)
+    nat.check(lib.mrcnn_sgd_step(nat.ptr(dg), nat.ptr(dw), nat.ptr(dv), nat.ptr(wb), off, nat.ptr(d_starts),
+                                 nat.ptr(d_coefs), len(sizes), 1.0 / world, clip, lr, mom, nat.ptr(sumsq), None), "sgd_step")
     torch.cuda.synchronize()
     norm = TO.sgd_step(W, G, V, lr, mom, clip, wd, world=world)
     assert norm > clip                                # the clipping branch is exercised
@@ -196,6 +197,32 @@ def test_sgd_step_matches_keras_restatement():
         assert np.allclose(gw[s:s + n], W[(name, role)], rtol=0, atol=2e-6), (name, role)
         assert np.allclose(gv[s:s + n], V[(name, role)], rtol=0, atol=2e-6), (name, role)
     assert torch.equal(wb, dw.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("case", ["1x1_small", "1x1_fc1", "3x3_mask", "3x3_backbone", "1x1_cout_ragged"])
+def test_conv_wgrad_tcgen05_vs_torch(case):
+    """mrcnn_conv2d_wgrad_bf16 (MN-major tcgen05 GEMM, split K, float32 atomics) against torch's float32 weight gradient
+    of the same bf16 tensors; dw is accumulated on top of what the buffer held."""
+    nat = _native()
+    lib = nat.lib()
+    n, h, w, cin, cout, k = {"1x1_small": (2, 16, 16, 64, 128, 1), "1x1_fc1": (1, 25, 8, 1024, 256, 1),
+                             "3x3_mask": (37, 14, 14, 256, 256, 3), "3x3_backbone": (2, 32, 32, 128, 128, 3),
+                             "1x1_cout_ragged": (3, 9, 11, 192, 72, 1)}[case]
+    rng = np.random.default_rng(len(case))
+    x = torch.from_numpy(rng.normal(0, 1, (n, h, w, cin)).astype(np.float32)).cuda().to(torch.bfloat16)
+    dy = torch.from_numpy(rng.normal(0, 1, (n, h, w, cout)).astype(np.float32)).cuda().to(torch.bfloat16)
+    base = torch.from_numpy(rng.normal(0, 1, (cout, k, k, cin)).astype(np.float32)).cuda()
+    dw = base.clone()
+    desc = nat.ConvDesc(n=n, h=h, w=w, cin=cin, kh=k, kw=k, stride=1, pad=k // 2, cout=cout, relu=0, residual_upsample2=0,
+                        out_dtype=nat.DTYPE_F32, out_mode=0, out_ld=0)
+    nat.check(lib.mrcnn_conv2d_wgrad_bf16(ctypes.byref(desc), nat.ptr(x), nat.ptr(dy), nat.ptr(dw), None), "conv2d_wgrad")
+    torch.cuda.synchronize()
+    want = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, k, k), dy.float().permute(0, 3, 1, 2),
+                                       stride=1, padding=k // 2).permute(0, 2, 3, 1)
+    got = (dw - base).cpu().numpy()
+    want = want.cpu().numpy()
+    err = np.abs(got - want).max()
+    assert err <= 2e-3 * np.abs(want).max() + 1e-3, (case, err, np.abs(want).max())
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -222,11 +249,18 @@ def _tiny_config():
     return C()
 
 
-def _tiny_inputs(cfg, seed=0):
+def _tiny_inputs(cfg, seed=0, gt_boxes_px=None):
+    """gt_boxes_px: rectangles to use as ground truth (filled-rectangle masks) instead of random blobs — the tests pass a
+    few of the graph's own proposals, which guarantees positive ROIs whatever the random weights propose."""
     from mrcnn import model as modellib, utils
     rng = np.random.default_rng(seed)
     S = 128
-    masks = _blobs(rng, S, 6)
+    if gt_boxes_px is None:
+        masks = _blobs(rng, S, 6)
+    else:
+        masks = np.zeros((S, S, len(gt_boxes_px)), bool)
+        for i, (y1, x1, y2, x2) in enumerate(gt_boxes_px):
+            masks[y1:y2, x1:x2, i] = True
     masks = masks[:, :, masks.sum((0, 1)) > 0]
     cls = rng.integers(1, 4, masks.shape[-1]).astype(np.int32)
     boxes = utils.extract_bboxes(masks)
@@ -245,6 +279,18 @@ def _tiny_inputs(cfg, seed=0):
     return [img[None], meta, match[None, :, None], bbox[None], gcls, gbox, gm]
 
 
+def _inputs_with_positive_rois(g, cfg):
+    with torch.no_grad():
+        g.forward(g.to_device(_tiny_inputs(cfg)), seed=1)
+    rois = g.taps["rpn_rois"][0].cpu().numpy()
+    px = np.round(rois * 127.0 + np.array([0, 0, 1, 1])).astype(int)
+    px = np.clip(px, 0, 128)
+    ok = [tuple(b) for b in px if b[2] - b[0] >= 3 and b[3] - b[1] >= 3]
+    ok = sorted(set(ok), key=lambda b: -(b[2] - b[0]) * (b[3] - b[1]))       # the largest distinct proposals
+    assert len(ok) >= 3, "the random network proposed no usable box: %s" % px[:8].tolist()
+    return _tiny_inputs(cfg, gt_boxes_px=ok[:5])
+
+
 def test_training_graph_losses_and_gradients_vs_fp32_oracle():
     """bf16 graph on the GPU vs the fp32 torch-CPU oracle fed with the product's own ROIs and targets (chain of custody:
     proposals and targets are index stages checked bit-exactly elsewhere).  Tolerances: every loss within 3 % + 0.02 abs,
@@ -254,7 +300,7 @@ def test_training_graph_losses_and_gradients_vs_fp32_oracle():
     weights = synth.make_random_weights(0, 4)
     g = training.TrainGraph(cfg, layers="all", seed=11)
     g.params.set_weights(weights)
-    inputs = _tiny_inputs(cfg)
+    inputs = _inputs_with_positive_rois(g, cfg)
     dev = g.to_device(inputs)
     g.params.g.zero_()
     total, ls = g.forward(dev, seed=11)
@@ -274,7 +320,7 @@ def test_training_graph_losses_and_gradients_vs_fp32_oracle():
     ototal = sum(ols.values())
     ototal.backward()
     for k in training.LOSS_NAMES:
-        a, b = float(ls[k]), float(ols[k])
+        a, b = float(ls[k].detach()), float(ols[k].detach())
         assert abs(a - b) <= 0.03 * abs(b) + 0.02, (k, a, b)
     checked = 0
     for (name, role), t in g.masters.items():
@@ -284,10 +330,15 @@ def test_training_graph_losses_and_gradients_vs_fp32_oracle():
         kind = g.params.kinds[name]
         want = net.p[(name, "kernel")].grad.numpy()
         want = {"conv": lambda a: a.transpose(3, 0, 1, 2), "dense": lambda a: a.T, "deconv": lambda a: a}[kind](want)
+        if np.linalg.norm(want) == 0.0:             # e.g. fpn_p5 at 128x128: no ROI on level 5, no RPN sample on P5 / P6
+            assert np.linalg.norm(got) == 0.0, name
+            continue
         cos = float((got * want).sum() / (np.linalg.norm(got) * np.linalg.norm(want) + 1e-30))
         assert cos >= 0.97, (name, cos)
+        ratio = float(np.linalg.norm(got) / np.linalg.norm(want))
+        assert 0.9 <= ratio <= 1.1, (name, ratio)
         checked += 1
-    assert checked >= 20
+    assert checked >= 18
 
 
 def test_train_steps_reduce_the_loss_on_a_fixed_batch():
@@ -296,7 +347,7 @@ def test_train_steps_reduce_the_loss_on_a_fixed_batch():
     g = training.TrainGraph(cfg, layers="all", seed=3)
     g.params.set_weights(synth.make_random_weights(0, 4))
     tr = training.Trainer(g, learning_rate=0.002, momentum=0.9)
-    dev = g.to_device(_tiny_inputs(cfg))
+    dev = g.to_device(_inputs_with_positive_rois(g, cfg))
     first = last = None
     for i in range(12):
         ls = tr.train_step(dev, seed=3)
