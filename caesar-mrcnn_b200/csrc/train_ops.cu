@@ -276,16 +276,32 @@ struct RoiBwdParams {
   int N, C, P;
 };
 
-// One CTA per ROI; a thread owns (pixel, 4-channel group) items.  The sample coordinates repeat the forward
-// (csrc/roialign.cu: in = a1*(D-1) + i*((a2-a1)*(D-1)/(P-1)), outside [0, D-1] -> no contribution).
+// One CTA per ROI.  The bilinear weights are separable, so the scatter is done in two steps inside shared memory:
+//   T[iy][x][c]  = sum over ix of wx(ix -> x) * dout[iy][ix][c]        (thread = (iy, channel group): owns its row of T)
+//   dF[y][x][c] += sum over iy of wy(iy -> y) * T[iy][x][c]            (thread = (y, x, channel group): ONE atomic each)
+// over the ROI's footprint (the input pixels its samples touch), 64 channels at a time: an ROI costs fh*fw*C/4 float4
+// atomics instead of 4*P*P*C/4 (a 14x14 crop of a 6x6-pixel footprint: 36 instead of 784 per channel group).  ROIs
+// whose footprint exceeds 16x16 pixels (long thin boxes on level 2) take the direct path: one atomic per sample corner.
+// The sample coordinates repeat the forward (csrc/roialign.cu: in = a1*(D-1) + i*((a2-a1)*(D-1)/(P-1)), outside
+// [0, D-1] -> no contribution).
+constexpr int RB_FMAX = 16;      // footprint limit of the shared-memory path
+constexpr int RB_CH = 64;        // channels per pass
+
 __global__ void __launch_bounds__(256) roialign_backward_kernel(RoiBwdParams p) {
   pdl_prologue();
+  extern __shared__ __align__(16) float s_T[];        // [P][RB_FMAX][RB_CH]
   __shared__ int s_lo[2][32], s_hi[2][32];
   __shared__ float s_w[2][32];
+  __shared__ int s_min[2], s_max[2];
   const int roi = blockIdx.x, b = roi / p.N;
   const int li = p.levels[roi] - 2;
   const int H = p.H[li], W = p.W[li], C = p.C, P = p.P;
   const float* bp = p.boxes + (size_t)roi * 4;
+  if (threadIdx.x < 2) {
+    s_min[threadIdx.x] = INT_MAX;
+    s_max[threadIdx.x] = -1;
+  }
+  __syncthreads();
   if (threadIdx.x < 64) {
     const int axis = threadIdx.x >> 5, i = threadIdx.x & 31;
     if (i < P) {
@@ -301,6 +317,8 @@ __global__ void __launch_bounds__(256) roialign_backward_kernel(RoiBwdParams p) 
         lo = (int)f;
         hi = (int)ceilf(in);
         wgt = __fsub_rn(in, f);
+        atomicMin(&s_min[axis], lo);
+        atomicMax(&s_max[axis], hi);
       }
       s_lo[axis][i] = lo;
       s_hi[axis][i] = hi;
@@ -308,27 +326,147 @@ __global__ void __launch_bounds__(256) roialign_backward_kernel(RoiBwdParams p) 
     }
   }
   __syncthreads();
+  if (s_max[0] < 0 || s_max[1] < 0) return;          // every sample lies outside the map
+  const int y0f = s_min[0], x0f = s_min[1];
+  const int fh = s_max[0] - y0f + 1, fw = s_max[1] - x0f + 1;
   float* df = p.dfeat[li] + (size_t)b * H * W * C;
   const __nv_bfloat16* g = p.dout + (size_t)roi * P * P * C;
-  const int cg = C / 4, items = P * P * cg;
-  for (int e = threadIdx.x; e < items; e += blockDim.x) {
-    const int pix = e / cg, c4 = (e - pix * cg) * 4, iy = pix / P, ix = pix - iy * P;
-    const int y0 = s_lo[0][iy], y1 = s_hi[0][iy], x0 = s_lo[1][ix], x1 = s_hi[1][ix];
-    if ((y0 | x0) < 0) continue;
-    const float ly = s_w[0][iy], lx = s_w[1][ix];
-    const uint2 raw = *reinterpret_cast<const uint2*>(g + (size_t)pix * C + c4);
-    const float g0 = __uint_as_float(raw.x << 16), g1 = __uint_as_float(raw.x & 0xffff0000u);
-    const float g2 = __uint_as_float(raw.y << 16), g3 = __uint_as_float(raw.y & 0xffff0000u);
-    const float wtl = (1.f - lx) * (1.f - ly), wtr = lx * (1.f - ly), wbl = (1.f - lx) * ly, wbr = lx * ly;
-    float4* a = reinterpret_cast<float4*>(df + ((size_t)y0 * W + x0) * C + c4);
-    float4* bq = reinterpret_cast<float4*>(df + ((size_t)y0 * W + x1) * C + c4);
-    float4* cq = reinterpret_cast<float4*>(df + ((size_t)y1 * W + x0) * C + c4);
-    float4* dq = reinterpret_cast<float4*>(df + ((size_t)y1 * W + x1) * C + c4);
-    atomicAdd(a, make_float4(g0 * wtl, g1 * wtl, g2 * wtl, g3 * wtl));
-    atomicAdd(bq, make_float4(g0 * wtr, g1 * wtr, g2 * wtr, g3 * wtr));
-    atomicAdd(cq, make_float4(g0 * wbl, g1 * wbl, g2 * wbl, g3 * wbl));
-    atomicAdd(dq, make_float4(g0 * wbr, g1 * wbr, g2 * wbr, g3 * wbr));
+  if (fh > RB_FMAX || fw > RB_FMAX || (C % RB_CH) != 0) {
+    // direct path: a thread owns (pixel, 4-channel group) items
+    const int cg = C / 4, items = P * P * cg;
+    for (int e = threadIdx.x; e < items; e += blockDim.x) {
+      const int pix = e / cg, c4 = (e - pix * cg) * 4, iy = pix / P, ix = pix - iy * P;
+      const int ya = s_lo[0][iy], yb = s_hi[0][iy], xa = s_lo[1][ix], xb = s_hi[1][ix];
+      if ((ya | xa) < 0) continue;
+      const float ly = s_w[0][iy], lx = s_w[1][ix];
+      const uint2 raw = *reinterpret_cast<const uint2*>(g + (size_t)pix * C + c4);
+      const float g0 = __uint_as_float(raw.x << 16), g1 = __uint_as_float(raw.x & 0xffff0000u);
+      const float g2 = __uint_as_float(raw.y << 16), g3 = __uint_as_float(raw.y & 0xffff0000u);
+      const float wtl = (1.f - lx) * (1.f - ly), wtr = lx * (1.f - ly), wbl = (1.f - lx) * ly, wbr = lx * ly;
+      atomicAdd(reinterpret_cast<float4*>(df + ((size_t)ya * W + xa) * C + c4), make_float4(g0 * wtl, g1 * wtl, g2 * wtl, g3 * wtl));
+      atomicAdd(reinterpret_cast<float4*>(df + ((size_t)ya * W + xb) * C + c4), make_float4(g0 * wtr, g1 * wtr, g2 * wtr, g3 * wtr));
+      atomicAdd(reinterpret_cast<float4*>(df + ((size_t)yb * W + xa) * C + c4), make_float4(g0 * wbl, g1 * wbl, g2 * wbl, g3 * wbl));
+      atomicAdd(reinterpret_cast<float4*>(df + ((size_t)yb * W + xb) * C + c4), make_float4(g0 * wbr, g1 * wbr, g2 * wbr, g3 * wbr));
+    }
+    return;
   }
+  constexpr int CG = RB_CH / 4;                     // float4 groups per pass
+  float4* T4 = reinterpret_cast<float4*>(s_T);      // [P][RB_FMAX][CG]
+  for (int c0 = 0; c0 < C; c0 += RB_CH) {
+    // phase 1: row iy of T, one thread per (iy, group)
+    for (int e = threadIdx.x; e < P * CG; e += blockDim.x) {
+      const int iy = e / CG, cgi = e - iy * CG;
+      float4* row = T4 + (size_t)iy * RB_FMAX * CG + cgi;
+      for (int x = 0; x < fw; ++x) row[x * CG] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s_lo[0][iy] < 0) continue;
+      const __nv_bfloat16* gp = g + (size_t)iy * P * C + c0 + cgi * 4;
+      for (int ix = 0; ix < P; ++ix) {
+        const int xa = s_lo[1][ix];
+        if (xa < 0) continue;
+        const int xb = s_hi[1][ix];
+        const float lx = s_w[1][ix];
+        const uint2 raw = *reinterpret_cast<const uint2*>(gp + (size_t)ix * C);
+        const float g0 = __uint_as_float(raw.x << 16), g1 = __uint_as_float(raw.x & 0xffff0000u);
+        const float g2 = __uint_as_float(raw.y << 16), g3 = __uint_as_float(raw.y & 0xffff0000u);
+        const float wa = 1.f - lx;
+        float4 ta = row[(xa - x0f) * CG];
+        ta.x += wa * g0; ta.y += wa * g1; ta.z += wa * g2; ta.w += wa * g3;
+        row[(xa - x0f) * CG] = ta;
+        float4 tb = row[(xb - x0f) * CG];
+        tb.x += lx * g0; tb.y += lx * g1; tb.z += lx * g2; tb.w += lx * g3;
+        row[(xb - x0f) * CG] = tb;
+      }
+    }
+    __syncthreads();
+    // phase 2: one atomic per touched input pixel and channel group
+    for (int e = threadIdx.x; e < fh * fw * CG; e += blockDim.x) {
+      const int cgi = e % CG, x = (e / CG) % fw, y = e / (CG * fw);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool any = false;
+      for (int iy = 0; iy < P; ++iy) {
+        const int ya = s_lo[0][iy];
+        if (ya < 0) continue;
+        const int yb = s_hi[0][iy];
+        const float ly = s_w[0][iy];
+        float wy = 0.f;
+        if (ya - y0f == y) wy += 1.f - ly;
+        if (yb - y0f == y) wy += ly;
+        if (ya - y0f == y || yb - y0f == y) {
+          const float4 t = T4[((size_t)iy * RB_FMAX + x) * CG + cgi];
+          acc.x += wy * t.x; acc.y += wy * t.y; acc.z += wy * t.z; acc.w += wy * t.w;
+          any = true;
+        }
+      }
+      if (any) atomicAdd(reinterpret_cast<float4*>(df + ((size_t)(y + y0f) * W + (x + x0f)) * C + c0 + cgi * 4), acc);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward "prologue" of a fused conv + BN-affine (+ residual) + ReLU layer: one pass over the incoming gradient
+//   dz  = dout * (out > 0)            (gradient before the affine = gradient of the residual input)
+//   dzs = dz * scale[c]               (operand of the data- and weight-gradient GEMMs)
+//   colsum[c] += sum over rows of dz  (gradient of the shift: bias / beta)
+// dout / out / dz / dzs: [rows, C] bf16 (NHWC flattened), C % 8 == 0, C <= 2048.
+// ------------------------------------------------------------------------------------------------------------------
+struct BwdPrepParams {
+  const __nv_bfloat16* dout;
+  const __nv_bfloat16* out;      // forward output (post-ReLU) or null: no ReLU
+  const float* scale;            // or null
+  __nv_bfloat16* dz;             // or null
+  __nv_bfloat16* dzs;            // or null
+  float* colsum;                 // or null
+  long long rows;
+  int C;
+};
+
+__global__ void __launch_bounds__(256) conv_backward_prep_kernel(BwdPrepParams p) {
+  pdl_prologue();
+  __shared__ float s_sum[2048];
+  const int groups = p.C >> 3;                 // 16-byte channel groups per row
+  const int rows_par = 256 / groups;           // rows handled in parallel by the block (>= 1)
+  const int cg = threadIdx.x % groups, r0 = threadIdx.x / groups;
+  const bool worker = r0 < rows_par;
+  for (int c = threadIdx.x; c < p.C; c += 256) s_sum[c] = 0.f;
+  __syncthreads();
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+  if (worker && p.scale) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sc[k] = p.scale[cg * 8 + k];
+  }
+  if (worker) {
+    for (long long r = (long long)blockIdx.x * rows_par + r0; r < p.rows; r += (long long)gridDim.x * rows_par) {
+      const size_t off = (size_t)r * p.C + (size_t)cg * 8;
+      const uint4 g = *reinterpret_cast<const uint4*>(p.dout + off);
+      uint4 o = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);     // "positive" when there is no ReLU
+      if (p.out) o = *reinterpret_cast<const uint4*>(p.out + off);
+      const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, ow[4] = {o.x, o.y, o.z, o.w};
+      uint32_t zw[4], sw[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float g0 = __uint_as_float(gw[k] << 16), g1 = __uint_as_float(gw[k] & 0xffff0000u);
+        const float o0 = __uint_as_float(ow[k] << 16), o1 = __uint_as_float(ow[k] & 0xffff0000u);
+        g0 = o0 > 0.f ? g0 : 0.f;
+        g1 = o1 > 0.f ? g1 : 0.f;
+        acc[2 * k] += g0;
+        acc[2 * k + 1] += g1;
+        __nv_bfloat162 z = __floats2bfloat162_rn(g0, g1), zs = __floats2bfloat162_rn(g0 * sc[2 * k], g1 * sc[2 * k + 1]);
+        zw[k] = *reinterpret_cast<uint32_t*>(&z);
+        sw[k] = *reinterpret_cast<uint32_t*>(&zs);
+      }
+      if (p.dz) *reinterpret_cast<uint4*>(p.dz + off) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+      if (p.dzs) *reinterpret_cast<uint4*>(p.dzs + off) = make_uint4(sw[0], sw[1], sw[2], sw[3]);
+    }
+    if (p.colsum) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&s_sum[cg * 8 + k], acc[k]);
+    }
+  }
+  __syncthreads();
+  if (p.colsum)
+    for (int c = threadIdx.x; c < p.C; c += 256) atomicAdd(p.colsum + c, s_sum[c]);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -478,7 +616,10 @@ extern "C" int mrcnn_pyramid_roi_align_backward(float* const* dfeature_maps, con
   p.N = num_boxes;
   p.C = channels;
   p.P = pool_size;
-  MRCNN_CHECK_CUDA(mrcnn_launch(roialign_backward_kernel, dim3(batch * num_boxes), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
+  const size_t smem = (size_t)pool_size * RB_FMAX * RB_CH * sizeof(float);
+  MRCNN_REQUIRE(smem <= 200 * 1024, "roi_align_backward: pool size %d too large", pool_size);
+  MRCNN_CHECK_CUDA(cudaFuncSetAttribute(roialign_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MRCNN_CHECK_CUDA(mrcnn_launch(roialign_backward_kernel, dim3(batch * num_boxes), dim3(256), smem, static_cast<cudaStream_t>(stream), p));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;
@@ -500,5 +641,28 @@ extern "C" int mrcnn_sgd_step(float* grad, float* weights, float* velocity, void
                                 learning_rate, momentum));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(2);
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_conv_backward_prep(const void* dout, const void* out, const float* scale, void* dz, void* dzs, float* colsum,
+                                        long long rows, int channels, void* stream) {
+  MRCNN_REQUIRE(dout && rows > 0, "conv_backward_prep: empty input");
+  MRCNN_REQUIRE(channels % 8 == 0 && channels >= 8 && channels <= 2048, "conv_backward_prep: channels %d outside 8..2048 (multiple of 8)",
+                channels);
+  BwdPrepParams p;
+  p.dout = static_cast<const __nv_bfloat16*>(dout);
+  p.out = static_cast<const __nv_bfloat16*>(out);
+  p.scale = scale;
+  p.dz = static_cast<__nv_bfloat16*>(dz);
+  p.dzs = static_cast<__nv_bfloat16*>(dzs);
+  p.colsum = colsum;
+  p.rows = rows;
+  p.C = channels;
+  const int rows_par = 256 / (channels / 8);
+  long long blocks = (rows + rows_par - 1) / rows_par;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  MRCNN_CHECK_CUDA(mrcnn_launch(conv_backward_prep_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
+  MRCNN_CHECK_CUDA(cudaGetLastError());
+  mrcnn_count_launch(1);
   return MRCNN_OK;
 }

@@ -124,6 +124,8 @@ SIGNATURES = {
                                         c_void_p, c_void_p, c_void_p]),
     "mrcnn_pyramid_roi_align_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                                  c_void_p, c_void_p]),
+    "mrcnn_conv_backward_prep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int,
+                                         c_void_p]),
     "mrcnn_sgd_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_float,
                                c_float, c_float, c_float, c_void_p, c_void_p]),
 }

@@ -212,53 +212,81 @@ def _round8(n):
 
 class ParamStore(object):
     """Flat parameter storage.  Layout of `w` (float32; `g` gradient, `v` momentum, `wb` bf16 copy share it):
-        [ biases of every conv/dense/deconv layer | BN gammas | BN betas | kernels in forward layer order ]
-    every tensor starting at a multiple of 8 elements.  Gradients of the kernels become available in reverse layer order,
-    so all-reduce buckets are cut from the END of the buffer; the small vectors at the front complete last.  BatchNorm
-    moving statistics (never trained: TRAIN_BN=False, mrcnn/config.py:216) live in `stats`.
-    kernel storage: conv [Cout,KH,KW,Cin], dense [out,in], deconv [KH,KW,Cout,Cin] (its Keras layout)."""
+        [ biases of the convs followed by a BatchNorm | BN gammas | BN betas | other biases | kernels in forward layer order ]
+    every tensor starting at a multiple of 8 elements.  The first three groups (and the moving means / variances in
+    `stats`, never trained: TRAIN_BN=False, mrcnn/config.py:216) list the BatchNorm layers in the same order with the same
+    offsets, so the folded affine of EVERY layer (scale = gamma / sqrt(var + eps), shift = (bias - mean) * scale + beta)
+    and its backward are a handful of vector operations over whole groups.  Gradients of the kernels become available
+    in reverse layer order, so all-reduce buckets are cut from the END of the buffer; the small vectors at the front
+    complete last.  kernel storage: conv [Cout,KH,KW,Cin], dense [out,in], deconv [KH,KW,Cout,Cin] (its Keras layout)."""
 
     def __init__(self, config, torch, device):
         self.torch, self.device = torch, device
         self.specs = layer_specs(config)
         self.entries = {}                    # (layer, role) -> (offset, shape) in w;  role: kernel bias gamma beta
         self.stat_entries = {}               # (layer, role) -> (offset, shape) in stats;  role: mean var
+        self.bn_of = {}                      # conv layer -> its BatchNorm layer
+        self.bn_rel = {}                     # BatchNorm layer -> (offset inside a BN group, channels)
+        rel = 0
+        for i, (name, kind, shape) in enumerate(self.specs):
+            if kind == "bn":
+                self.bn_of[self.specs[i - 1][0]] = name
+                self.bn_rel[name] = (rel, int(shape[0]))
+                rel += _round8(shape[0])
+        self.bn_elements = rel
         off = 0
         order = []
-        for role in ("bias", "gamma", "beta", "kernel"):
+        self.group = {}
+
+        def add(name, role, shp):
+            nonlocal off
+            self.entries[(name, role)] = (off, shp)
+            order.append((name, role, off, int(np.prod(shp))))
+            off += _round8(np.prod(shp))
+
+        def cout_of(kind, shape):
+            return shape[2] if kind == "deconv" else shape[-1]
+
+        self.group["bias_bn"] = off
+        for name, kind, shape in self.specs:
+            if kind != "bn" and name in self.bn_of:
+                add(name, "bias", (cout_of(kind, shape),))
+        for role in ("gamma", "beta"):
+            self.group[role] = off
             for name, kind, shape in self.specs:
-                if kind == "bn" and role in ("gamma", "beta"):
-                    shp = (shape[0],)
-                elif kind != "bn" and role == "bias":
-                    shp = (shape[2] if kind == "deconv" else shape[-1],)
-                elif kind != "bn" and role == "kernel":
-                    if kind == "conv":
-                        shp = (shape[3], shape[0], shape[1], shape[2])
-                    elif kind == "dense":
-                        shp = (shape[1], shape[0])
-                    else:
-                        shp = tuple(shape)
-                else:
-                    continue
-                self.entries[(name, role)] = (off, shp)
-                order.append((name, role, off, int(np.prod(shp))))
-                off += _round8(np.prod(shp))
+                if kind == "bn":
+                    add(name, role, (shape[0],))
+        for name, kind, shape in self.specs:
+            if kind != "bn" and name not in self.bn_of:
+                add(name, "bias", (cout_of(kind, shape),))
+        for name, kind, shape in self.specs:
+            if kind == "conv":
+                add(name, "kernel", (shape[3], shape[0], shape[1], shape[2]))
+            elif kind == "dense":
+                add(name, "kernel", (shape[1], shape[0]))
+            elif kind == "deconv":
+                add(name, "kernel", tuple(shape))
         self.order = order
         self.n = off
-        soff = 0
-        for name, kind, shape in self.specs:
-            if kind == "bn":
-                for role in ("mean", "var"):
-                    self.stat_entries[(name, role)] = (soff, (shape[0],))
-                    soff += _round8(shape[0])
+        for k, role in enumerate(("mean", "var")):
+            for name, (r, c) in self.bn_rel.items():
+                self.stat_entries[(name, role)] = (k * self.bn_elements + r, (c,))
         self.w = torch.zeros(self.n, dtype=torch.float32, device=device)
         self.g = torch.zeros(self.n, dtype=torch.float32, device=device)
         self.v = torch.zeros(self.n, dtype=torch.float32, device=device)
         self.wb = torch.zeros(self.n, dtype=torch.bfloat16, device=device)
-        self.stats = torch.zeros(max(soff, 8), dtype=torch.float32, device=device)
+        self.stats = torch.zeros(max(2 * self.bn_elements, 8), dtype=torch.float32, device=device)
         self.kinds = {name: kind for name, kind, _ in self.specs}
         self.keras_shapes = {name: shape for name, _, shape in self.specs}
         self.trainable_elements = sum(sz for _, _, _, sz in order)
+
+    def bn_group(self, buf, role):
+        """whole-group view (all BatchNorm layers) of `role` in bias_bn | gamma | beta (buf = w, g, ...) or mean | var (stats)"""
+        if role in ("mean", "var"):
+            o = 0 if role == "mean" else self.bn_elements
+            return self.stats[o:o + self.bn_elements]
+        o = self.group[role]
+        return buf[o:o + self.bn_elements]
 
     # -- views ------------------------------------------------------------------------------------------------
     def view(self, buf, name, role):
@@ -393,7 +421,115 @@ def _functions(torch):
             outs = [gd.to(torch.bfloat16).permute(0, 3, 1, 2) for gd in grads]
             return (None, None, None) + tuple(outs)
 
-    return UseParam, RoiAlign
+    class ConvTC(torch.autograd.Function):
+        """conv + folded BN affine + residual (+ nearest-2x upsampled residual) + ReLU as ONE tcgen05 implicit-GEMM launch
+        (csrc/conv_gemm.cu, the detect path's kernel).  Backward: one pass over the incoming gradient
+        (mrcnn_conv_backward_prep: ReLU mask, scale, shift gradient), the same GEMM kernel on the flipped / transposed
+        weights for the data gradient, the MN-major tcgen05 GEMM (mrcnn_conv2d_wgrad_bf16) for the weight gradient.
+        x, residual, result: NCHW-logical channels-last bf16 (= NHWC memory).  `L` carries the layer: w_op (bf16
+        [Cout,KH,KW,Cin]), scale (or None) / shift float32 [Cout] WITHOUT autograd history, and where the parameter
+        gradients go: g_kernel (float32 view of the flat gradient buffer; the weight gradient is accumulated there by the
+        kernel itself), d_scale / d_shift (views of the graph's affine-gradient buffers), notify(key) for the reducer.
+        With L.g_kernel None the weight gradient is returned to autograd for `w_master` instead (layers used several
+        times per step)."""
+        @staticmethod
+        def forward(ctx, x, residual, w_master, L):
+            lib = _native.lib()
+            xn = x.permute(0, 2, 3, 1)
+            assert xn.is_contiguous() and xn.dtype == torch.bfloat16
+            N, H, W, Cin = xn.shape
+            Cout, KH, KW, _ = L.w_op.shape
+            stride, pad = L.stride, L.pad
+            OH, OW = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+            out = torch.empty((N, OH, OW, Cout), dtype=torch.bfloat16, device=x.device)
+            sc = L.scale if L.scale is not None else L.const(Cout, 1.0)
+            rn = None
+            if residual is not None:
+                rn = residual.permute(0, 2, 3, 1)
+                assert rn.is_contiguous()
+            desc = _native.ConvDesc(n=N, h=H, w=W, cin=Cin, kh=KH, kw=KW, stride=stride, pad=pad, cout=Cout, relu=int(L.relu),
+                                    residual_upsample2=int(L.res_up2), out_dtype=_native.DTYPE_BF16, out_mode=0, out_ld=0)
+            st = torch.cuda.current_stream(x.device).cuda_stream
+            with torch.cuda.device(x.device):
+                _native.check(lib.mrcnn_conv2d_bf16(ctypes.byref(desc), _native.ptr(xn), _native.ptr(L.w_op), _native.ptr(sc),
+                                                    _native.ptr(L.shift), _native.ptr(rn), _native.ptr(out), st), "conv2d")
+            ctx.save_for_backward(xn, out if L.relu else None)
+            ctx.L = L
+            ctx.has_res = residual is not None
+            ctx.in_shape = (N, H, W, Cin)
+            return out.permute(0, 3, 1, 2)
+
+        @staticmethod
+        def backward(ctx, dout):
+            lib = _native.lib()
+            xn, out = ctx.saved_tensors
+            L = ctx.L
+            N, H, W, Cin = ctx.in_shape
+            Cout, KH, KW, _ = L.w_op.shape
+            stride, pad = L.stride, L.pad
+            has_scale = L.scale is not None
+            dev = xn.device
+            dn = dout.permute(0, 2, 3, 1)
+            if not dn.is_contiguous():
+                dn = dn.contiguous()
+            OH, OW = dn.shape[1], dn.shape[2]
+            rows = N * OH * OW
+            st = torch.cuda.current_stream(dev).cuda_stream
+            need_dz = ctx.has_res or not has_scale
+            plain = out is None and not has_scale            # no ReLU, no scale: dz is dout itself
+            dz = dn if plain else (torch.empty_like(dn) if need_dz else None)
+            dzs = torch.empty_like(dn) if has_scale else None
+            d_shift = L.d_shift if L.d_shift is not None else torch.zeros(Cout, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _native.check(lib.mrcnn_conv_backward_prep(_native.ptr(dn), _native.ptr(out), _native.ptr(L.scale),
+                                                           None if plain else _native.ptr(dz), _native.ptr(dzs), _native.ptr(d_shift),
+                                                           rows, Cout, st), "conv_backward_prep")
+            op = dzs if has_scale else dz
+            d_res = None
+            if ctx.has_res:
+                d_res = dz.permute(0, 3, 1, 2)
+                if L.res_up2:
+                    d_res = (torch.nn.functional.avg_pool2d(d_res.float(), 2) * 4.0).to(torch.bfloat16)
+            # weight gradient, accumulated by the kernel into the flat gradient buffer (or a scratch buffer for autograd)
+            xs = xn if stride == 1 else xn[:, ::stride, ::stride, :].contiguous()
+            G = L.g_kernel if L.g_kernel is not None else torch.zeros((Cout, KH, KW, Cin), dtype=torch.float32, device=dev)
+            desc = _native.ConvDesc(n=N, h=OH, w=OW, cin=Cin, kh=KH, kw=KW, stride=1, pad=pad, cout=Cout, relu=0,
+                                    residual_upsample2=0, out_dtype=_native.DTYPE_F32, out_mode=0, out_ld=0)
+            with torch.cuda.device(dev):
+                _native.check(lib.mrcnn_conv2d_wgrad_bf16(ctypes.byref(desc), _native.ptr(xs), _native.ptr(op), _native.ptr(G), st),
+                              "conv2d_wgrad")
+            if has_scale and L.d_scale is not None:
+                # d scale[c] = sum dz * (conv output before the affine) = <W[c], dW[c]> / scale[c]   (dW already carries scale)
+                ds = (L.w_op.float() * G).sum((1, 2, 3))
+                L.d_scale.add_(torch.where(L.scale != 0, ds / L.scale, torch.zeros_like(ds)))
+            if L.notify is not None:
+                L.notify()
+            # data gradient: correlation of (dz * scale) with the flipped, transposed filter — the forward kernel again
+            d_x = None
+            if ctx.needs_input_grad[0]:
+                wt = L.w_op if KH == 1 else L.w_op.flip(1, 2)
+                wt = wt.permute(3, 1, 2, 0).contiguous()                       # [Cin, KH, KW, Cout]
+                dsub = torch.empty((N, OH, OW, Cin), dtype=torch.bfloat16, device=dev)
+                desc = _native.ConvDesc(n=N, h=OH, w=OW, cin=Cout, kh=KH, kw=KW, stride=1, pad=pad, cout=Cin, relu=0,
+                                        residual_upsample2=0, out_dtype=_native.DTYPE_BF16, out_mode=0, out_ld=0)
+                with torch.cuda.device(dev):
+                    _native.check(lib.mrcnn_conv2d_bf16(ctypes.byref(desc), _native.ptr(op), _native.ptr(wt), _native.ptr(L.const(Cin, 1.0)),
+                                                        _native.ptr(L.const(Cin, 0.0)), None, _native.ptr(dsub), st), "conv2d (dgrad)")
+                if stride == 1:
+                    d_x = dsub.permute(0, 3, 1, 2)
+                else:
+                    full = torch.zeros((N, H, W, Cin), dtype=torch.bfloat16, device=dev)
+                    full[:, ::stride, ::stride, :] = dsub
+                    d_x = full.permute(0, 3, 1, 2)
+            d_w = G if L.g_kernel is None else None
+            return d_x, d_res, d_w, None
+
+    return UseParam, RoiAlign, ConvTC
+
+
+class _Layer(object):
+    """what ConvTC needs to know about one layer (see ConvTC)"""
+    __slots__ = ("w_op", "scale", "shift", "stride", "pad", "relu", "res_up2", "g_kernel", "d_scale", "d_shift", "notify", "const")
 
 
 class TrainGraph(object):
@@ -425,7 +561,9 @@ class TrainGraph(object):
         if int(config.POST_NMS_ROIS_TRAINING) > 2048 or int(config.MAX_GT_INSTANCES) > 512:
             raise NotImplementedError("mrcnn (B200 build): POST_NMS_ROIS_TRAINING <= 2048 and MAX_GT_INSTANCES <= 512")
         self.params = ParamStore(config, torch, self.device)
-        self.UseParam, self.RoiAlign = _functions(torch)
+        self.UseParam, self.RoiAlign, self.ConvTC = _functions(torch)
+        import os
+        self.backend = os.environ.get("MRCNN_B200_TRAIN_BACKEND", "tcgen05")       # "torch": library convolutions everywhere
         self.step_seed = int(seed)
         self.set_trainable(layers)
         a = utils.generate_pyramid_anchors(config.RPN_ANCHOR_SCALES, config.RPN_ANCHOR_RATIOS,
@@ -433,6 +571,13 @@ class TrainGraph(object):
                                            config.BACKBONE_STRIDES, config.RPN_ANCHOR_STRIDE)
         self.anchors_px = a
         self.anchors = torch.from_numpy(np.ascontiguousarray(utils.norm_boxes(a, config.IMAGE_SHAPE[:2]), dtype=np.float32)).to(self.device)
+        self._consts = {}
+        self.reducer = None                  # set by GradReducer: told when a gradient was deposited outside autograd
+        nb = self.params.bn_elements
+        self._S = torch.zeros(nb, dtype=torch.float32, device=self.device)      # folded affine of every BN layer (per step)
+        self._T = torch.zeros(nb, dtype=torch.float32, device=self.device)
+        self._dS = torch.zeros(nb, dtype=torch.float32, device=self.device)     # and its gradient, filled by ConvTC.backward
+        self._dT = torch.zeros(nb, dtype=torch.float32, device=self.device)
         self._box_shift = torch.tensor([0., 0., 1., 1.], device=self.device)
         self.seed_device = torch.zeros(1, dtype=torch.int64, device=self.device)     # advanced on the device every step
         self.taps = {}
@@ -450,6 +595,44 @@ class TrainGraph(object):
                 t.requires_grad_(True)
                 t.grad = p.view(p.g, name, role)
             self.masters[(name, role)] = t
+        mask = self.torch.zeros(p.bn_elements, dtype=self.torch.float32, device=self.device)
+        cmask = self.torch.zeros(p.bn_elements, dtype=self.torch.float32, device=self.device)
+        for conv, bn in p.bn_of.items():
+            r, c = p.bn_rel[bn]
+            mask[r:r + c] = 1.0 if self.trainable(bn) else 0.0
+            cmask[r:r + c] = 1.0 if self.trainable(conv) else 0.0
+        self._bn_trainable, self._bnconv_trainable = mask, cmask
+
+    def const(self, n, value):
+        """cached float32 vector of n copies of value (scale 1 / shift 0 of the plain GEMM launches)"""
+        key = (int(n), float(value))
+        if key not in self._consts:
+            self._consts[key] = self.torch.full((int(n),), float(value), dtype=self.torch.float32, device=self.device)
+        return self._consts[key]
+
+    def begin_step(self):
+        """Folded affine of every BatchNorm layer in five vector operations (no autograd: ConvTC deposits its gradient in
+        _dS / _dT and finish_backward turns those into the gamma / beta / bias gradients)."""
+        p, torch = self.params, self.torch
+        with torch.no_grad():
+            torch.rsqrt(p.bn_group(None, "var") + BN_EPS, out=self._S)
+            self._S.mul_(p.bn_group(p.w, "gamma"))
+            torch.sub(p.bn_group(p.w, "bias_bn"), p.bn_group(None, "mean"), out=self._T)
+            self._T.mul_(self._S).add_(p.bn_group(p.w, "beta"))
+            self._dS.zero_()
+            self._dT.zero_()
+
+    def finish_backward(self):
+        """After loss.backward(): gradients of gamma, beta and the BN'd convolutions' biases from the affine gradients the
+        fused layers left in _dS / _dT:  scale = gamma*inv, shift = (bias - mean)*scale + beta, inv = rsqrt(var + eps)
+          d gamma = (dS + dT*(bias - mean)) * inv ;  d beta = dT ;  d bias = dT * scale."""
+        p, torch = self.params, self.torch
+        with torch.no_grad():
+            inv = torch.rsqrt(p.bn_group(None, "var") + BN_EPS)
+            centred = p.bn_group(p.w, "bias_bn") - p.bn_group(None, "mean")
+            p.bn_group(p.g, "gamma").add_((self._dS + self._dT * centred) * inv * self._bn_trainable)
+            p.bn_group(p.g, "beta").add_(self._dT * self._bn_trainable)
+            p.bn_group(p.g, "bias_bn").add_(self._dT * self._S * self._bnconv_trainable)
 
     def trainable_parameters(self):
         return [(k, t) for k, t in self.masters.items() if t.requires_grad]
@@ -479,11 +662,46 @@ class TrainGraph(object):
             y = self.F.relu(y)
         return y.to(self.torch.bfloat16).contiguous(memory_format=self.torch.channels_last)
 
-    def conv(self, x, name, bn=None, relu=False, stride=1, pad=0, residual=None):
+    def _layer(self, name, bn, w_shape, relu, stride, pad, res_up2, shared):
+        """the _Layer record of ConvTC for layer `name` (kernel seen as w_shape = [Cout,KH,KW,Cin])"""
+        p = self.params
+        L = _Layer()
+        L.w_op = p.view(p.wb, name, "kernel").view(w_shape)
+        L.stride, L.pad, L.relu, L.res_up2, L.const = stride, pad, relu, res_up2, self.const
+        train_k = self.masters[(name, "kernel")].requires_grad
+        if bn is not None:
+            r, c = p.bn_rel[bn]
+            L.scale, L.shift = self._S[r:r + c], self._T[r:r + c]
+            L.d_scale, L.d_shift = self._dS[r:r + c], self._dT[r:r + c]
+        else:
+            L.scale, L.shift = None, p.view(p.w, name, "bias")
+            L.d_scale = None
+            L.d_shift = p.view(p.g, name, "bias") if self.masters[(name, "bias")].requires_grad else None
+        # single-use layers: the weight-gradient kernel accumulates straight into the flat gradient buffer
+        L.g_kernel = p.view(p.g, name, "kernel").view(w_shape) if (train_k and not shared) else None
+        key = (name, "kernel")
+        L.notify = (lambda: self.reducer.mark_ready(key)) if (self.reducer is not None and L.g_kernel is not None) else None
+        if not train_k and not shared:            # frozen layer: its gradient goes to a scratch buffer nobody reads
+            L.g_kernel = self.torch.zeros(w_shape, dtype=self.torch.float32, device=self.device)
+        return L
+
+    def conv(self, x, name, bn=None, relu=False, stride=1, pad=0, residual=None, residual_up2=False, shared=False):
+        """One convolution layer with its folded BatchNorm, optional residual (nearest-2x upsampled for the FPN laterals)
+        and ReLU.  tcgen05 backend: one fused launch (ConvTC) for 1x1 / 3x3 layers whose channel counts fit the
+        implicit GEMM (Cin and Cout multiples of 64); everything else — the 7x7 stem with 3 input channels, the 6 / 12
+        channel RPN outputs — goes through torch.  shared: the layer is applied several times per step (the RPN on five
+        pyramid levels), its weight gradient is summed by autograd."""
+        m = self.masters[(name, "kernel")]
+        cout, kh, kw, cin = m.shape
+        if (self.backend == "tcgen05" and cin % 64 == 0 and cout % 64 == 0 and (kh, kw, pad) in ((1, 1, 0), (3, 3, 1))
+                and (stride == 1 or kh == 1)):
+            L = self._layer(name, bn, (cout, kh, kw, cin), relu, stride, pad, residual_up2, shared)
+            return self.ConvTC.apply(x, residual, m if (shared and m.requires_grad) else None, L)
+        if residual is not None and residual_up2:
+            residual = self.F.interpolate(residual, scale_factor=2, mode="nearest")
         w = self._operand(name).permute(0, 3, 1, 2)           # [Cout,KH,KW,Cin] storage seen as channels-last OIHW
         return self._finish(self.F.conv2d(x, w, None, stride=stride, padding=pad), name, bn, relu, residual)
 
-    # -- graph ------------------------------------------------------------------------------------------------------
     def _block(self, x, stage, blk, first, stride):
         base, bnb = "res%d%s_branch" % (stage, blk), "bn%d%s_branch" % (stage, blk)
         y = self.conv(x, base + "2a", bnb + "2a", relu=True, stride=stride)
@@ -503,9 +721,9 @@ class TrainGraph(object):
                 x = self._block(x, stage, chr(97 + i), i == 0, 2 if (i == 0 and stage > 2) else 1)
             feats["C%d" % stage] = x
         p5 = self.conv(feats["C5"], "fpn_c5p5")
-        p4 = self.conv(feats["C4"], "fpn_c4p4", residual=F.interpolate(p5, scale_factor=2, mode="nearest"))
-        p3 = self.conv(feats["C3"], "fpn_c3p3", residual=F.interpolate(p4, scale_factor=2, mode="nearest"))
-        p2 = self.conv(feats["C2"], "fpn_c2p2", residual=F.interpolate(p3, scale_factor=2, mode="nearest"))
+        p4 = self.conv(feats["C4"], "fpn_c4p4", residual=p5, residual_up2=True)
+        p3 = self.conv(feats["C3"], "fpn_c3p3", residual=p4, residual_up2=True)
+        p2 = self.conv(feats["C2"], "fpn_c2p2", residual=p3, residual_up2=True)
         P = {"P2": self.conv(p2, "fpn_p2", pad=1), "P3": self.conv(p3, "fpn_p3", pad=1),
              "P4": self.conv(p4, "fpn_p4", pad=1), "P5": self.conv(p5, "fpn_p5", pad=1)}
         P["P6"] = F.max_pool2d(P["P5"], 1, 2)
@@ -516,7 +734,7 @@ class TrainGraph(object):
         torch = self.torch
         logits, boxes = [], []
         for lvl in ("P2", "P3", "P4", "P5", "P6"):
-            s = self.conv(P[lvl], "rpn_conv_shared", relu=True, pad=1)
+            s = self.conv(P[lvl], "rpn_conv_shared", relu=True, pad=1, shared=True)
             c = self.conv(s, "rpn_class_raw").permute(0, 2, 3, 1)
             d = self.conv(s, "rpn_bbox_pred").permute(0, 2, 3, 1)
             logits.append(c.reshape(c.shape[0], -1, 2).float())
@@ -572,7 +790,7 @@ class TrainGraph(object):
         area = float(cfg.IMAGE_SHAPE[0] * cfg.IMAGE_SHAPE[1])
         x = self.RoiAlign.apply(rois, int(cfg.POOL_SIZE), area, P["P2"], P["P3"], P["P4"], P["P5"])
         x = x.view(B * T, cfg.POOL_SIZE, cfg.POOL_SIZE, -1).permute(0, 3, 1, 2)
-        x = self.conv(x, "mrcnn_class_conv1", "mrcnn_class_bn1", relu=True)
+        x = self._fc1(x)
         x = self.conv(x, "mrcnn_class_conv2", "mrcnn_class_bn2", relu=True)
         shared = x.reshape(B * T, -1)
         logits = (shared @ self._operand("mrcnn_class_logits").t()).float() + self.masters[("mrcnn_class_logits", "bias")]
@@ -580,6 +798,18 @@ class TrainGraph(object):
         nc = int(cfg.NUM_CLASSES)
         logits = logits.view(B, T, nc)
         return logits, torch.softmax(logits, -1), bbox.view(B, T, nc, 4)
+
+    def _fc1(self, x):
+        """mrcnn_class_conv1: a POOL x POOL VALID convolution over a POOL x POOL map = one dense layer over K = POOL*POOL*C;
+        the pooled tensor [n, P, P, C] and the kernel [Cout, P, P, C] are already laid out as that GEMM's operands."""
+        name, bn = "mrcnn_class_conv1", "mrcnn_class_bn1"
+        cout, kh, kw, cin = self.masters[(name, "kernel")].shape
+        k = kh * kw * cin
+        if self.backend == "tcgen05" and k % 64 == 0 and cout % 64 == 0:
+            xf = x.permute(0, 2, 3, 1).reshape(x.shape[0], 1, 1, k).permute(0, 3, 1, 2)
+            L = self._layer(name, bn, (cout, 1, 1, k), True, 1, 0, False, False)
+            return self.ConvTC.apply(xf, None, None, L)
+        return self.conv(x, name, bn, relu=True)
 
     def mask_head(self, rois, P):
         """build_fpn_mask_graph (mrcnn/model.py:1042-1091) -> masks [B,T,2*MASK_POOL,2*MASK_POOL,NC] float32 in (0,1)."""
@@ -591,11 +821,11 @@ class TrainGraph(object):
         x = x.view(B * T, mp, mp, -1).permute(0, 3, 1, 2)
         for i in range(1, 5):
             x = self.conv(x, "mrcnn_mask_conv%d" % i, "mrcnn_mask_bn%d" % i, relu=True, pad=1)
+        # transposed convolution + ReLU and the NUM_CLASSES-channel 1x1 through torch (library), bias added in the call
         wd = self._operand("mrcnn_mask_deconv").permute(3, 2, 0, 1)          # [KH,KW,Cout,Cin] -> [Cin,Cout,KH,KW]
-        x = F.conv_transpose2d(x, wd, None, stride=2)
-        x = F.relu(x.float() + self.masters[("mrcnn_mask_deconv", "bias")].view(1, -1, 1, 1)).to(torch.bfloat16)
-        x = F.conv2d(x, self._operand("mrcnn_mask").permute(0, 3, 1, 2))
-        x = torch.sigmoid(x.float() + self.masters[("mrcnn_mask", "bias")].view(1, -1, 1, 1))
+        x = F.relu(F.conv_transpose2d(x, wd, self.masters[("mrcnn_mask_deconv", "bias")].to(torch.bfloat16), stride=2))
+        x = F.conv2d(x, self._operand("mrcnn_mask").permute(0, 3, 1, 2), self.masters[("mrcnn_mask", "bias")].to(torch.bfloat16))
+        x = torch.sigmoid(x.float())
         return x.permute(0, 2, 3, 1).reshape(B, T, 2 * mp, 2 * mp, int(cfg.NUM_CLASSES))
 
     # -- losses (mrcnn/model.py:1098-1270), float32 ------------------------------------------------------------------
@@ -649,6 +879,7 @@ class TrainGraph(object):
         S = float(cfg.IMAGE_SHAPE[0])
         # norm_boxes_graph (mrcnn/model.py:3003-3017): (boxes - [0,0,1,1]) / (S-1)
         gt_norm = ((gt_boxes.float() - self._box_shift) / (S - 1.0)).contiguous()
+        self.begin_step()
         P = self.backbone_fpn(images)
         rpn_class_logits, rpn_class, rpn_bbox = self.rpn(P)
         rpn_rois = self.proposals(rpn_class, rpn_bbox)
@@ -726,15 +957,26 @@ class GradReducer(object):
         self._left = list(self._need)
         self._works = []
         self.enabled = True
+        graph.reducer = self
 
     def _make_hook(self, bi):
         def hook(_param):
-            if not self.enabled:
-                return
-            self._left[bi] -= 1
-            if self._left[bi] == 0:
-                self._launch(bi)
+            self._ready(bi)
         return hook
+
+    def _ready(self, bi):
+        if not self.enabled:
+            return
+        self._left[bi] -= 1
+        if self._left[bi] == 0:
+            self._launch(bi)
+
+    def mark_ready(self, key):
+        """a gradient that did not come through autograd (ConvTC lets the weight-gradient kernel accumulate straight into
+        the flat buffer) is complete"""
+        bi = self._bucket_of.get(key)
+        if bi is not None:
+            self._ready(bi)
 
     def _launch(self, bi):
         if self.world > 1:
@@ -858,6 +1100,7 @@ class Trainer(object):
         if ev:
             ev[1].record()
         total.backward()
+        g.finish_backward()
         if ev:
             ev[2].record()
         self.reducer.finish()

@@ -385,6 +385,12 @@ int mrcnn_pyramid_roi_align_backward(float* const* dfeature_maps, const int* fea
                                      const float* boxes, const int32_t* levels, int batch, int num_boxes, int pool_size,
                                      const void* dpooled_bf16, void* stream);
 
+/* First step of the backward pass of a fused conv + affine (+ residual) + ReLU layer, one pass over the gradient:
+ * dz = dout * (out > 0) (out = the layer's forward output; NULL: no ReLU), dzs = dz * scale[c] (scale NULL: dzs = dz),
+ * colsum[c] += sum over rows of dz.  [rows, channels] bf16 row-major, channels % 8 == 0, <= 2048; dz / dzs / colsum optional. */
+int mrcnn_conv_backward_prep(const void* dout, const void* out, const float* scale, void* dz, void* dzs, float* colsum,
+                             long long rows, int channels, void* stream);
+
 /* One optimiser step over flat float32 buffers of n elements (mrcnn/model.py:2259-2297: keras SGD(lr, momentum,
  * clipnorm=GRADIENT_CLIP_NORM) on loss + sum_w l2(WEIGHT_DECAY)(w) / size(w)):
  *   g = grad * grad_scale + segment_reg_coef[s] * w      (s = segment of the element; coef = 2*WEIGHT_DECAY/size(w), 0 for BN)

@@ -305,6 +305,7 @@ def test_training_graph_losses_and_gradients_vs_fp32_oracle():
     g.params.g.zero_()
     total, ls = g.forward(dev, seed=11)
     total.backward()
+    g.finish_backward()
     torch.cuda.synchronize()
     taps = {k: v.detach().cpu() for k, v in g.taps.items()}
     assert int(taps["counts"][0, 0]) > 0, "no positive ROI in the tiny case"
@@ -339,6 +340,14 @@ def test_training_graph_losses_and_gradients_vs_fp32_oracle():
         assert 0.9 <= ratio <= 1.1, (name, ratio)
         checked += 1
     assert checked >= 18
+    # BatchNorm gamma / beta and bias gradients (batched affine backward of the fused layers)
+    for name, role in (("bn4f_branch2b", "gamma"), ("bn4f_branch2b", "beta"), ("res4f_branch2b", "bias"), ("mrcnn_mask_bn2", "gamma"),
+                       ("mrcnn_class_bn1", "beta"), ("fpn_p3", "bias"), ("rpn_conv_shared", "bias"), ("bn_conv1", "gamma")):
+        got = g.params.view(g.params.g, name, role).cpu().numpy()
+        want = net.p[(name, role)].grad.numpy()
+        cos = float((got * want).sum() / (np.linalg.norm(got) * np.linalg.norm(want) + 1e-30))
+        assert cos >= 0.95, (name, role, cos)
+        assert 0.85 <= np.linalg.norm(got) / np.linalg.norm(want) <= 1.15, (name, role)
 
 
 def test_train_steps_reduce_the_loss_on_a_fixed_batch():
