@@ -895,6 +895,8 @@ struct WgradParams {
   int m_tiles, n_tiles, ksplit;
   float* out;             // [cout, taps*cin] float32
   int out_ld;
+  const __nv_bfloat16* w; // optional: the layer's weights [cout, taps*cin] ...
+  float* wdot;            // ... and wdot[co] += <w[co, :], dW tile> (gradient of a per-channel scale folded behind the conv)
 };
 
 template <int BLOCK_N> struct WgradCfg {
@@ -1029,18 +1031,35 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     const int co = m_tile * BLOCK_M + q * 32 + lane;
     mbar_wait(done_bar, 0);
     tcgen05_fence_after();
-    float* orow = p.out + (size_t)co * p.out_ld + (size_t)tap * p.cin + (size_t)n_tile * BLOCK_N;
+    const size_t roff = (size_t)co * p.out_ld + (size_t)tap * p.cin + (size_t)n_tile * BLOCK_N;
+    float* orow = p.out + roff;
+    float dot = 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (co < p.cout) {
+      if (co < p.cout) {       // cin is a multiple of 64: the 32 columns of a chunk are all real
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n_tile * BLOCK_N + c0 + j < p.cin) atomicAdd(orow + c0 + j, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; j += 4)
+          atomicAdd(reinterpret_cast<float4*>(orow + c0 + j), make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+        if (p.wdot) {
+          const uint4* wr = reinterpret_cast<const uint4*>(p.w + roff + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 ww = __ldg(wr + j);
+            const uint32_t wv[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              dot += __uint_as_float(v[8 * j + 2 * k]) * __uint_as_float(wv[k] << 16);
+              dot += __uint_as_float(v[8 * j + 2 * k + 1]) * __uint_as_float(wv[k] & 0xffff0000u);
+            }
+          }
+        }
       }
     }
+    if (p.wdot && co < p.cout) atomicAdd(p.wdot + co, dot);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -1323,8 +1342,10 @@ extern "C" int mrcnn_conv2d_bf16_simt(const mrcnn_conv_desc* d, const void* x, c
   return MRCNN_OK;
 }
 
-extern "C" int mrcnn_conv2d_wgrad_bf16(const mrcnn_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
+extern "C" int mrcnn_conv2d_wgrad_bf16(const mrcnn_conv_desc* d, const void* x, const void* dy, float* dw, const void* w,
+                                       float* wdot, void* stream) {
   MRCNN_REQUIRE(d && x && dy && dw, "conv2d_wgrad: null pointer");
+  MRCNN_REQUIRE((w == nullptr) == (wdot == nullptr), "conv2d_wgrad: w and wdot go together");
   const bool k1 = d->kh == 1 && d->kw == 1 && d->pad == 0 && d->stride == 1;
   const bool k3 = d->kh == 3 && d->kw == 3 && d->pad == 1 && d->stride == 1;
   MRCNN_REQUIRE(k1 || k3, "conv2d_wgrad: 1x1 stride 1 or 3x3 stride 1 pad 1 only (got %dx%d stride %d pad %d)", d->kh, d->kw,
@@ -1377,6 +1398,8 @@ extern "C" int mrcnn_conv2d_wgrad_bf16(const mrcnn_conv_desc* d, const void* x, 
   p.ksplit = ceil_div(p.k_chunks, p.chunks_per_split);
   p.out = dw;
   p.out_ld = p.taps * d->cin;
+  p.w = static_cast<const __nv_bfloat16*>(w);
+  p.wdot = wdot;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return bn == 128 ? launch_wgrad<128>(tdy, tx, p, st) : launch_wgrad<64>(tdy, tx, p, st);
 }

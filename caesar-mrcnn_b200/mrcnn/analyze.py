@@ -518,19 +518,29 @@ def build_json_results(image_id, obj_name_tag, class_names, ny, nx, xmin, ymin, 
     (np.argwhere(mask==1) computed on the device). pixels_as_lists=False keeps each object's "pixels" as that int32
     array instead of a list of [y, x] lists (NumpyEncoder writes the same JSON): a batch of 64 images otherwise
     allocates ~10^5 small lists, which costs more in Python's garbage collector than the whole GPU step."""
+    n = len(class_ids_final)
     results = {"image_id": image_id, "objs": []}
+    if n == 0:
+        return results
     if vertexes is None and compute_vertexes:       # (the batched path computes them for all frames in one call)
-        vertexes = contours_of_pixel_lists([pixels[i] for i in range(len(class_ids_final))], as_lists=pixels_as_lists)
-    for i in range(len(class_ids_final)):
-        class_id = int(class_ids_final[i])
-        y1, x1, y2, x2 = (int(v) for v in bboxes[i])
-        at_edge = x1 <= 0 or x1 >= nx - 1 or x2 <= 0 or x2 >= nx - 1 or y1 <= 0 or y1 >= ny - 1 or y2 <= 0 or y2 >= ny - 1
-        vertex_list = vertexes[i] if vertexes is not None else []
-        results["objs"].append({
-            "name": 'S' + str(i + 1) + "_" + obj_name_tag,
-            "x1": xmin + x1, "x2": xmin + x2, "y1": ymin + y1, "y2": ymin + y2,
+        vertexes = contours_of_pixel_lists([pixels[i] for i in range(n)], as_lists=pixels_as_lists)
+    # per-frame conversions in one go (a 64-frame batch holds ~2 500 objects: per-object numpy scalar handling was the
+    # largest host item of the catalogue path)
+    bb = np.asarray(bboxes, dtype=np.int64).reshape(n, 4)
+    edge = ((bb[:, [1, 3]] <= 0) | (bb[:, [1, 3]] >= nx - 1)).any(axis=1) | ((bb[:, [0, 2]] <= 0) | (bb[:, [0, 2]] >= ny - 1)).any(axis=1)
+    edge = edge.tolist()
+    bb = (bb + np.array([ymin, xmin, ymin, xmin], dtype=np.int64)).tolist()
+    cids = [int(c) for c in class_ids_final]
+    objs = results["objs"]
+    for i in range(n):
+        y1, x1, y2, x2 = bb[i]
+        class_id = cids[i]
+        objs.append({
+            "name": "S%d_%s" % (i + 1, obj_name_tag),
+            "x1": x1, "x2": x2, "y1": y1, "y2": y2,
             "class_id": class_id, "class_name": class_names[class_id], "score": scores_final[i],
-            "pixels": pixels[i].tolist() if pixels_as_lists else pixels[i], "vertexes": vertex_list, "edge": at_edge,
+            "pixels": pixels[i].tolist() if pixels_as_lists else pixels[i],
+            "vertexes": vertexes[i] if vertexes is not None else [], "edge": edge[i],
         })
     return results
 

@@ -299,6 +299,14 @@ class MaskRCNN(object):
         by layer name (the inference graph has no positional layer list)."""
         from . import h5weights
         weights = h5weights.read_keras_weights(filepath)
+        # make a mis-parsed or foreign file visible: how many of the graph's weighted layers the file provides
+        known = [n for n, _, _ in self._graph.params.specs] if self.mode == "training" else [n for n, _, _, _ in self.layer_table()]
+        found = [n for n in known if n in weights and not (exclude and n in exclude)]
+        missing = [n for n in known if n not in weights]
+        log("load_weights(%s): %d of %d weighted layers loaded, %d missing%s, %d entries of the file unused" % (
+            os.path.basename(str(filepath)), len(found), len(known), len(missing),
+            (" (" + ", ".join(missing[:6]) + (" ..." if len(missing) > 6 else "") + ")") if missing else "",
+            len([n for n in weights if n not in known])))
         self.set_weights(weights, exclude=exclude)
         self.set_log_dir(filepath)
 
@@ -357,11 +365,16 @@ class MaskRCNN(object):
         for n in training.LOSS_NAMES:
             history[n] = []
             history["val_" + n] = []
+        captured = False
         for epoch in range(self.epoch, epochs):
             sums = {}
             for _ in range(int(cfg.STEPS_PER_EPOCH)):
                 inputs, _unused = next(train_gen)
-                ls = trainer.train_step(g.to_device(inputs))
+                dev = g.to_device(inputs)
+                if not captured and os.environ.get("MRCNN_B200_TRAIN_GRAPH", "1") != "0":
+                    trainer.capture(dev)           # the whole step as one CUDA graph from here on (eager if that fails)
+                captured = True
+                ls = trainer.train_step(dev)
                 for k, v in ls.items():
                     sums[k] = sums.get(k, 0.0) + float(v)
             for k, v in sums.items():

@@ -496,12 +496,12 @@ def _functions(torch):
             desc = _native.ConvDesc(n=N, h=OH, w=OW, cin=Cin, kh=KH, kw=KW, stride=1, pad=pad, cout=Cout, relu=0,
                                     residual_upsample2=0, out_dtype=_native.DTYPE_F32, out_mode=0, out_ld=0)
             with torch.cuda.device(dev):
-                _native.check(lib.mrcnn_conv2d_wgrad_bf16(ctypes.byref(desc), _native.ptr(xs), _native.ptr(op), _native.ptr(G), st),
-                              "conv2d_wgrad")
-            if has_scale and L.d_scale is not None:
-                # d scale[c] = sum dz * (conv output before the affine) = <W[c], dW[c]> / scale[c]   (dW already carries scale)
-                ds = (L.w_op.float() * G).sum((1, 2, 3))
-                L.d_scale.add_(torch.where(L.scale != 0, ds / L.scale, torch.zeros_like(ds)))
+                # d scale[c] = sum dz * (conv output before the affine) = <W[c], dW[c]> / scale[c] (dW already carries the
+                # scale): the GEMM's epilogue leaves <W[c], dW[c]> in d_scale, finish_backward divides all layers at once
+                fold = has_scale and L.d_scale is not None
+                _native.check(lib.mrcnn_conv2d_wgrad_bf16(ctypes.byref(desc), _native.ptr(xs), _native.ptr(op), _native.ptr(G),
+                                                          _native.ptr(L.w_op) if fold else None,
+                                                          _native.ptr(L.d_scale) if fold else None, st), "conv2d_wgrad")
             if L.notify is not None:
                 L.notify()
             # data gradient: correlation of (dz * scale) with the flipped, transposed filter — the forward kernel again
@@ -630,6 +630,8 @@ class TrainGraph(object):
         with torch.no_grad():
             inv = torch.rsqrt(p.bn_group(None, "var") + BN_EPS)
             centred = p.bn_group(p.w, "bias_bn") - p.bn_group(None, "mean")
+            # _dS holds <W, dW> per channel (weight-gradient epilogue); dW carries the scale once too often
+            self._dS.copy_(torch.where(self._S != 0, self._dS / self._S, torch.zeros_like(self._dS)))
             p.bn_group(p.g, "gamma").add_((self._dS + self._dT * centred) * inv * self._bn_trainable)
             p.bn_group(p.g, "beta").add_(self._dT * self._bn_trainable)
             p.bn_group(p.g, "bias_bn").add_(self._dT * self._S * self._bnconv_trainable)
@@ -985,6 +987,8 @@ class GradReducer(object):
 
     def finish(self):
         """After backward: launch buckets whose parameters produced no gradient this step, wait for everything."""
+        if not self.enabled:
+            return
         for bi, left in enumerate(self._left):
             if left > 0:
                 self._launch(bi)

@@ -140,6 +140,13 @@ def read_fits(filename, xmin=-1, xmax=-1, ymin=-1, ymax=-1, stretch=True, normal
     plane = data[0, 0] if data.ndim == 4 else data
     if read_tile:
         plane = plane[ymin:ymax, xmin:xmax]
+    if not stretch and not normalize and not convertToRGB and not stretch_biascontrast:
+        # the raw plane (ground-truth mask files of the training datasets, scripts/run.py:641-727): float32, NaN -> minimum
+        out = np.array(plane, dtype=np.float32)
+        bad = np.isnan(out)
+        if bad.any():
+            out[bad] = np.nanmin(out)
+        return out, header
     if not (stretch and normalize and convertToRGB and to_uint8) or stretch_biascontrast:
         raise NotImplementedError("read_fits (B200 build): only stretch=True, normalize=True, convertToRGB=True, "
                                   "to_uint8=True, stretch_biascontrast=False is implemented (SURVEY.md §8a row a17)")

@@ -1,9 +1,13 @@
 #!/usr/bin/env python
-"""run.py — detect/test CLI of the B200 build, flag-compatible with the detect-path subset of the
-reference's scripts/run.py (parse_args :1263-1384, InferenceConfig :1652-1706, detect :1172-1189).
+"""run.py — detect/test/train CLI of the B200 build, flag-compatible with the corresponding subset of the
+reference's scripts/run.py (parse_args :1263-1384, InferenceConfig :1652-1706, detect :1172-1189, train :1052-1125,
+SourceDataset :246-818).
 
   run.py detect --image data/galaxy0002.fits --weights share/mrcnn_weights.h5 [--imgsize 256 ...]
   run.py test   --datalist images.txt        --weights share/mrcnn_weights.h5
+  run.py train  --datalist train.txt [--dataloader datalist|datalist_json] --nepochs 10 --nimg_per_gpu 2 [--weights w.h5]
+                (one process per GPU under torchrun: every rank trains on its own shuffled stream of the dataset and the
+                 gradients are averaged over NVLink — the replacement of --ngpu N / ParallelModel)
 
 `detect` reads the FITS image (zscale + uint8 RGB on the GPU) and hands it to `Analyzer.predict` exactly as the
 reference's SFinder.run does (mrcnn/sfinder.py:485-493): MaskRCNN.detect, then extract_det_masks (score filter,
@@ -13,8 +17,10 @@ merging of connected same-class masks, best-of-overlapping selection) on the GPU
 With --split_img_in_tiles the image is cut into --tile_xsize x --tile_ysize tiles (SFinder.run_parallel,
 mrcnn/sfinder.py:549-640): the tiles go through the detector in batches of --nimg_per_gpu, sources cut by tile borders
 are merged, and `catalog_<image>.json` is written; launched under torchrun, every rank (GPU) takes the tiles the
-reference's MPI ranks would. PNG / DS9 output, the ground-truth metrics of `test`, source parameters (WCS / flux) and
-`train` are outside the path rebuilt here and are rejected or skipped.
+reference's MPI ranks would. `train` builds the reference's SourceDataset (image,mask,label lists or per-image JSON files),
+splits it into training / cross-validation sets and calls MaskRCNN.train(layers='all') (mrcnn/training.py).  PNG / DS9
+output, the ground-truth metrics of `test`, source parameters (WCS / flux), imgaug augmentation and class weights are
+outside the path rebuilt here and are rejected or skipped.
 Returns exit code 0 on success, 1 on failure, like the reference's main().
 """
 import argparse
@@ -62,9 +68,240 @@ class SDetectorConfig(Config):
     SCORE_THR = 0.7
 
 
+class SourceDataset(utils.Dataset):
+    """reference: scripts/run.py:246-818 — radio-source dataset: one FITS image + one FITS mask file per object.
+    Loaders: `image.fits,mask.fits,class_name` lines (load_data_from_list) or per-image JSON files listing the object
+    masks (load_data_from_json_file / _list).  Images go through read_fits (zscale + uint8 RGB on the GPU), masks are read
+    raw and cast to bool."""
+
+    def __init__(self):
+        utils.Dataset.__init__(self)
+        self.class_id_map = {}
+        self.nclasses = 0
+        self.loaded_imgs = 0
+        self.zscale_contrasts = [0.25, 0.25, 0.25]
+        self.nobjs_per_class = {}
+
+    def set_class_dict(self, class_dict_str):
+        if class_dict_str == "":
+            logger.error("Empty string given!")
+            return -1
+        try:
+            class_dict = json.loads(class_dict_str)
+        except Exception:
+            logger.error("Failed to get dictionary from string!")
+            return -1
+        self.class_id_map = class_dict
+        for class_name in self.class_id_map:
+            class_id = self.class_id_map[class_name]
+            self.add_class("rg-dataset", class_id, class_name)
+            self.nobjs_per_class[class_id] = 0
+        self.class_id_map['bkg'] = 0
+        self.nobjs_per_class[0] = 0
+        self.nclasses = len(self.class_id_map)
+        return 0
+
+    def _add(self, image_path, mask_paths, class_ids, **extra):
+        import uuid
+        self.add_image("rg-dataset", image_id=str(uuid.uuid1()), path=image_path, path_masks=mask_paths, class_ids=class_ids, **extra)
+        for cid in class_ids:
+            self.nobjs_per_class[cid] = self.nobjs_per_class.get(cid, 0) + 1
+        self.loaded_imgs += 1
+
+    def load_data_from_list(self, dataset, nmaximgs=-1):
+        img_counter, status = 0, 0
+        with open(dataset, 'r') as f:
+            for line in f:
+                if not line.strip():
+                    continue
+                filename, filename_mask, class_name = line.strip().split(',')
+                fp, mp = os.path.abspath(filename), os.path.abspath(filename_mask)
+                if not (os.path.isfile(fp) and fp.endswith('.fits')):
+                    logger.warning("Image file %s does not exist or has unexpected extension (.fits required)" % filename)
+                    status = -1
+                    continue
+                if not (os.path.isfile(mp) and mp.endswith('.fits')):
+                    logger.warning("Mask file %s does not exist or has unexpected extension (.fits required)" % filename_mask)
+                    status = -1
+                    continue
+                if class_name not in self.class_id_map:
+                    logger.warning("Image file %s class name (%s) is not present in dictionary, skip it..." % (filename, class_name))
+                    status = -1
+                    continue
+                self._add(fp, [mp], [self.class_id_map.get(class_name)])
+                img_counter += 1
+                if nmaximgs != -1 and img_counter >= nmaximgs:
+                    logger.info("Max number (%d) of desired images reached, stop loading ..." % nmaximgs)
+                    break
+        if status < 0:
+            logger.warning("One or more files have been skipped...")
+        if img_counter <= 0:
+            logger.error("All files in list have been skipped!")
+            return -1
+        logger.info("#%d images added in dataset..." % img_counter)
+        return 0
+
+    def load_data_from_json_file(self, filename, rootdir='', modify_class_names=True):
+        try:
+            with open(filename, "r") as jf:
+                d = json.load(jf)
+        except IOError:
+            logger.error("Failed to open file %s, skip it..." % filename)
+            return -1
+        img_fullpath = os.path.abspath(os.path.join(rootdir, d['img']))
+        if not (os.path.isfile(img_fullpath) and img_fullpath.endswith('.fits')):
+            logger.warning("Image file %s does not exist or has unexpected extension (.fits required)" % img_fullpath)
+            return -1
+        metadata = {k: d.get(k) for k in ("telescope", "bkg", "rms", "bmaj", "bmin", "dx", "dy", "nx", "ny")}
+        mask_paths, class_ids, near = [], [], []
+        for obj in d['objs']:
+            mask_fullpath = os.path.abspath(os.path.join(rootdir, obj['mask']))
+            if not (os.path.isfile(mask_fullpath) and mask_fullpath.endswith('.fits')):
+                logger.error("One or more mask of file %s does not exist or have unexpected extension (.fits required)" % img_fullpath)
+                return -1
+            class_name = obj['class']
+            if modify_class_names:
+                if obj.get('nislands', 1) > 1 and class_name == "extended":
+                    class_name = 'extended-multisland'
+                if obj.get('sidelobe-mixed'):
+                    class_name = 'flagged'
+                obj['class'] = class_name
+            if class_name not in self.class_id_map:
+                logger.warning("Image file %s class name (%s) is not present in dictionary, skip it..." % (img_fullpath, class_name))
+                continue
+            mask_paths.append(mask_fullpath)
+            class_ids.append(self.class_id_map.get(class_name))
+            near.append(1 if (obj.get('sidelobe-mixed') == 1 or obj.get('sidelobe-near') == 1) else 0)
+        self._add(img_fullpath, mask_paths, class_ids, sidelobes_mixed_or_near=near, objs=d['objs'], metadata=metadata)
+        return 0
+
+    def load_data_from_json_list(self, filelist, nmaximgs):
+        img_counter, status = 0, 0
+        with open(filelist, 'r') as f:
+            for line in f:
+                fn = line.strip()
+                if not fn:
+                    continue
+                if self.load_data_from_json_file(fn, os.path.dirname(fn)) < 0:
+                    status = -1
+                    continue
+                img_counter += 1
+                if nmaximgs != -1 and img_counter >= nmaximgs:
+                    break
+        if status < 0:
+            logger.warning("One or more files have been skipped...")
+        if img_counter <= 0:
+            logger.error("All files in list have been skipped!")
+            return -1
+        return 0
+
+    def load_gt_masks(self, image_id, binary=True):
+        info = self.image_info[image_id]
+        mask = None
+        for k, filename in enumerate(info["path_masks"]):
+            data, _ = utils.read_fits(filename, stretch=False, normalize=False, convertToRGB=False)
+            if mask is None:
+                mask = np.zeros([data.shape[0], data.shape[1], len(info["path_masks"])], dtype=bool if binary else int)
+            mask[:, :, k] = data.astype(bool) if binary else data
+        return mask
+
+    def load_mask(self, image_id):
+        if self.image_info[image_id]["source"] != "rg-dataset":
+            return super(SourceDataset, self).load_mask(image_id)
+        mask = self.load_gt_masks(image_id, binary=True)
+        return mask, np.full([mask.shape[-1]], self.image_info[image_id]["class_ids"], dtype=np.int32)
+
+    def load_image(self, image_id):
+        res = utils.read_fits(self.image_info[image_id]['path'], zscale_contrasts=self.zscale_contrasts)
+        if res is None:
+            raise IOError("cannot read image " + str(self.image_info[image_id]['path']))
+        return res[0]
+
+    def image_reference(self, image_id):
+        return self.image_info[image_id]["path"]
+
+
+def create_train_val_sets_from_filelist(filelist, crossval_size=0.1, train_filename='train.dat', crossval_filename='crossval.dat'):
+    """reference: scripts/run.py:821-864 — shuffle the list (Python `random`) and split off the cross-validation part
+    (sklearn.model_selection.train_test_split there: ceil(test_size * n) shuffled test samples; here the tail of the
+    already shuffled list, which is the same kind of split without the dependency)."""
+    import math
+    import random
+    with open(filelist, 'r') as f:
+        data = [ln.strip() for ln in f if ln.strip()]
+    if not data:
+        logger.error("Given filelist is empty!")
+        return []
+    if len(data) < 10:
+        logger.warning("Given filelist contains less than 10 entries ...")
+    random.shuffle(data)
+    n_val = max(1, int(math.ceil(float(crossval_size) * len(data)))) if len(data) > 1 else 0
+    x_train, x_val = data[:len(data) - n_val], data[len(data) - n_val:]
+    for fn, items in ((train_filename, x_train), (crossval_filename, x_val)):
+        with open(fn, 'w') as f:
+            for item in items:
+                f.write("%s\n" % item)
+    return [train_filename, crossval_filename]
+
+
+def create_train_val_datasets(args, train_filename='train.dat', crossval_filename='crossval.dat'):
+    """reference: scripts/run.py:893-989"""
+    if args.datalist_train and args.datalist_val:
+        datalist_train, datalist_val = args.datalist_train, args.datalist_val
+    elif args.dataloader in ('datalist', 'datalist_json'):
+        lists = create_train_val_sets_from_filelist(args.datalist, args.validation_data_fract, train_filename, crossval_filename)
+        if len(lists) != 2:
+            return []
+        datalist_train, datalist_val = lists
+    else:
+        logger.error("Invalid/unknown dataloader (%s)!" % args.dataloader)
+        return []
+    out = []
+    for path in (datalist_train, datalist_val):
+        ds = SourceDataset()
+        ds.set_class_dict(args.classdict)
+        ds.zscale_contrasts = [float(x) for x in args.zscale_contrasts.split(',')]
+        rc = ds.load_data_from_list(path, args.maxnimgs) if args.dataloader == 'datalist' else ds.load_data_from_json_list(path, args.maxnimgs)
+        if rc < 0:
+            logger.error("Failed to load dataset from file %s (see logs)..." % path)
+            return []
+        ds.prepare()
+        out.append(ds)
+    logger.info("#%d/%d entries in the training/validation sets ..." % (out[0].loaded_imgs, out[1].loaded_imgs))
+    return out
+
+
+def train(args, model, config, datasets):
+    """reference: scripts/run.py:1052-1125"""
+    if len(datasets) != 2 or datasets[0] is None or datasets[1] is None:
+        logger.error("Given dataset list must have size=2!")
+        return -1
+    logger.info("Training without augmentation steps ...")
+    logger.info("Start training ...")
+    model.train(datasets[0], datasets[1], learning_rate=config.LEARNING_RATE, epochs=args.nepochs, layers='all',
+                n_worker_threads=args.nthreads)
+    return 0
+
+
 def parse_args(argv=None):
-    p = argparse.ArgumentParser(description="Mask R-CNN detect on radio maps (B200 build)")
-    p.add_argument("command", metavar="<command>", help="'detect' or 'test' ('train' is not part of this build)")
+    p = argparse.ArgumentParser(description="Mask R-CNN detect / train on radio maps (B200 build)")
+    p.add_argument("command", metavar="<command>", help="'detect', 'test' or 'train'")
+    p.add_argument("--dataloader", type=str, default="datalist", help="train: datalist (img,mask,label lines) | datalist_json")
+    p.add_argument("--datalist_train", default=None)
+    p.add_argument("--datalist_val", default=None)
+    p.add_argument("--validation_data_fract", type=float, default=0.1)
+    p.add_argument("--nthreads", type=int, default=1)
+    p.add_argument("--nepochs", type=int, default=1)
+    p.add_argument("--epoch_length", type=int, default=None)
+    p.add_argument("--nvalidation_steps", type=int, default=None)
+    p.add_argument("--max_gt_instances", type=int, default=300)
+    p.add_argument("--rpn_train_anchors_per_image", type=int, default=512)
+    p.add_argument("--train_rois_per_image", type=int, default=512)
+    for name in ("rpn_class", "rpn_bbox", "mrcnn_class", "mrcnn_bbox", "mrcnn_mask"):
+        p.add_argument("--%s_loss_weight" % name, type=float, default=1.0)
+        p.add_argument("--no_%s_loss" % name, dest="%s_loss" % name, action="store_false")
+    p.add_argument("--no_augmentation", dest="use_augmentation", action="store_false")
+    p.add_argument("--weight_classes", action="store_true")
     p.add_argument("--imgsize", dest="imgsize", type=int, default=256)
     p.add_argument("--grayimg", dest="grayimg", action="store_true")
     p.add_argument("--no_uint8", dest="to_uint8", action="store_false")
@@ -106,9 +343,18 @@ def parse_args(argv=None):
 
 def validate_args(args):
     """scripts/run.py:1387-1443 for the commands kept here."""
-    if args.command not in ("detect", "test"):
-        logger.error("Command '%s' is not available in the B200 build (only detect/test)." % args.command)
+    if args.command not in ("detect", "test", "train"):
+        logger.error("Command '%s' is not available in the B200 build (detect / test / train)." % args.command)
         return -1
+    if args.command == "train":
+        has_split = args.datalist_train and args.datalist_val
+        if not has_split and not (args.datalist and os.path.isfile(args.datalist)):
+            logger.error("Argument --datalist (or --datalist_train and --datalist_val) is required for train task!")
+            return -1
+        if args.weight_classes:
+            logger.error("Option --weight_classes is not supported by the B200 build")
+            return -1
+        args.use_augmentation = False        # imgaug is not part of this build: training runs without augmentation
     if args.command == "detect":
         if not args.image:
             logger.error("Argument --image is required for detect task!")
@@ -119,7 +365,7 @@ def validate_args(args):
     if args.command == "test" and not (args.datalist and os.path.isfile(args.datalist)):
         logger.error("Argument --datalist (existing file) is required for test task!")
         return -1
-    if not args.weights and args.random_weights is None:
+    if args.command != "train" and not args.weights and args.random_weights is None:
         logger.error("Argument --weights is required (or --random_weights SEED)")
         return -1
     for flag, ok in (("--grayimg", not args.grayimg), ("--no_uint8", args.to_uint8), ("--no_zscale", args.zscale),
@@ -166,6 +412,16 @@ def make_config(args):
     config.TILE_XSTEP, config.TILE_YSTEP = args.tile_xstep, args.tile_ystep
     config.MAX_NTASKS_PER_WORKER = 100000
     config.OUTFILE_JSON = args.detect_outfile_json
+    if args.command == "train":          # scripts/run.py:1627-1672 (training values of SDetectorConfig + CLI overrides)
+        config.MAX_GT_INSTANCES = args.max_gt_instances
+        config.RPN_TRAIN_ANCHORS_PER_IMAGE = args.rpn_train_anchors_per_image
+        config.TRAIN_ROIS_PER_IMAGE = args.train_rois_per_image
+        config.LEARNING_RATE = 0.0005
+        config.USE_MINI_MASK = False
+        config.LOSS_WEIGHTS = {"%s_loss" % n: getattr(args, "%s_loss_weight" % n) for n in
+                               ("rpn_class", "rpn_bbox", "mrcnn_class", "mrcnn_bbox", "mrcnn_mask")}
+        config.USE_LOSSES = {"%s_loss" % n: getattr(args, "%s_loss" % n) for n in
+                             ("rpn_class", "rpn_bbox", "mrcnn_class", "mrcnn_bbox", "mrcnn_mask")}
     return config
 
 
@@ -174,7 +430,10 @@ def load_model(args, config):
     import torch
     if torch.cuda.is_available():
         torch.cuda.set_device(local_rank)      # one process per GPU: everything of this rank (read_fits included) on its GPU
-    model = modellib.MaskRCNN(mode="inference", config=config, model_dir=args.logs, device=local_rank)
+    mode = "training" if args.command == "train" else "inference"
+    model = modellib.MaskRCNN(mode=mode, config=config, model_dir=args.logs, device=local_rank)
+    if mode == "training" and not args.weights and args.random_weights is None:
+        args.random_weights = 0                  # training from scratch: seeded random initialisation
     if args.random_weights is not None:
         sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
         import synth
@@ -279,6 +538,27 @@ def main(argv=None):
         return 1
     config = make_config(args)
     try:
+        if args.command == "train":
+            world = int(os.environ.get("WORLD_SIZE", "1"))
+            if world > 1:
+                import torch
+                import torch.distributed as dist
+                torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+                if not dist.is_initialized():
+                    dist.init_process_group("nccl")
+            datasets = create_train_val_datasets(args, "train_%d.dat" % os.getpid(), "crossval_%d.dat" % os.getpid())
+            if not datasets:
+                logger.error("Failed to create train/validation datasets!")
+                return 1
+            if args.epoch_length is not None:
+                config.STEPS_PER_EPOCH = args.epoch_length
+            else:
+                config.STEPS_PER_EPOCH = max(1, datasets[0].loaded_imgs // (config.BATCH_SIZE * world))
+            config.VALIDATION_STEPS = args.nvalidation_steps if args.nvalidation_steps is not None else \
+                max(1, datasets[1].loaded_imgs // (config.BATCH_SIZE * world))
+            model = load_model(args, config)
+            status = train(args, model, config, datasets)
+            return 0 if status == 0 else 1
         model = load_model(args, config)
         status = detect(args, model, config) if args.command == "detect" else test(args, model, config)
     except Exception as e:      # noqa: BLE001 — the reference's main() turns failures into exit code 1

@@ -167,8 +167,11 @@ int mrcnn_conv2d_bf16(const mrcnn_conv_desc* desc, const void* x, const void* w,
  * dy[n, oh, ow, co] * x[n, oh + r - pad, ow + s - pad, ci]  (float32 accumulation into dw, which is NOT cleared: it has
  * the [Cout, KH, KW, Cin] layout of the parameter and its gradient buffer).  x [N,H,W,Cin] bf16, dy [N,H,W,Cout] bf16;
  * 1x1 stride 1 or 3x3 stride 1 pad 1; Cin % 64 == 0, Cout % 8 == 0.  tcgen05 GEMM over MN-major operands, K (pixels)
- * split across CTAs.  Only n, h, w, cin, cout, kh, kw, stride, pad of the descriptor are read. */
-int mrcnn_conv2d_wgrad_bf16(const mrcnn_conv_desc* desc, const void* x, const void* dy, float* dw, void* stream);
+ * split across CTAs.  Only n, h, w, cin, cout, kh, kw, stride, pad of the descriptor are read.  Optional (both or none):
+ * w = the layer's bf16 weights [Cout, KH, KW, Cin] and wdot [Cout] float32, wdot[co] += <w[co], this call's dw[co]> — the
+ * gradient of a per-channel scale applied behind the convolution (folded BatchNorm) times that scale. */
+int mrcnn_conv2d_wgrad_bf16(const mrcnn_conv_desc* desc, const void* x, const void* dy, float* dw, const void* w,
+                            float* wdot, void* stream);
 /* reference implementation on CUDA cores (fp32 accumulate) used only by the tests to check the
  * tcgen05 path on the device at full size */
 int mrcnn_conv2d_bf16_simt(const mrcnn_conv_desc* desc, const void* x, const void* w, const float* scale,

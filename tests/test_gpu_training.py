@@ -215,7 +215,10 @@ def test_conv_wgrad_tcgen05_vs_torch(case):
     dw = base.clone()
     desc = nat.ConvDesc(n=n, h=h, w=w, cin=cin, kh=k, kw=k, stride=1, pad=k // 2, cout=cout, relu=0, residual_upsample2=0,
                         out_dtype=nat.DTYPE_F32, out_mode=0, out_ld=0)
-    nat.check(lib.mrcnn_conv2d_wgrad_bf16(ctypes.byref(desc), nat.ptr(x), nat.ptr(dy), nat.ptr(dw), None), "conv2d_wgrad")
+    wts = torch.from_numpy(rng.normal(0, 1, (cout, k, k, cin)).astype(np.float32)).cuda().to(torch.bfloat16)
+    wdot = torch.zeros(cout, dtype=torch.float32, device="cuda")
+    nat.check(lib.mrcnn_conv2d_wgrad_bf16(ctypes.byref(desc), nat.ptr(x), nat.ptr(dy), nat.ptr(dw), nat.ptr(wts), nat.ptr(wdot), None),
+              "conv2d_wgrad")
     torch.cuda.synchronize()
     want = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, k, k), dy.float().permute(0, 3, 1, 2),
                                        stride=1, padding=k // 2).permute(0, 2, 3, 1)
@@ -223,6 +226,8 @@ def test_conv_wgrad_tcgen05_vs_torch(case):
     want = want.cpu().numpy()
     err = np.abs(got - want).max()
     assert err <= 2e-3 * np.abs(want).max() + 1e-3, (case, err, np.abs(want).max())
+    want_dot = (wts.float().cpu().numpy() * want).sum((1, 2, 3))
+    assert np.abs(wdot.cpu().numpy() - want_dot).max() <= 2e-3 * np.abs(want_dot).max() + 1e-2, case
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -368,3 +373,43 @@ def test_train_steps_reduce_the_loss_on_a_fixed_batch():
     assert tr.opt.grad_norm() > 0
     # the bf16 operand copy follows the master weights
     assert torch.equal(g.params.wb, g.params.w.to(torch.bfloat16))
+
+
+def test_run_py_train_writes_a_checkpoint_the_detector_loads(tmp_path):
+    """`run.py train` end to end on a tiny FITS dataset (reference scripts/run.py train -> MaskRCNN.train): one epoch of two
+    steps + one validation step, a Keras-layout weights file per epoch, and that file loads into the inference engine."""
+    import glob
+    import importlib.util
+    import os
+    from mrcnn import fitsio
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "caesar-mrcnn_b200", "scripts", "run.py")
+    spec = importlib.util.spec_from_file_location("run_b200_train_gpu", path)
+    run = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(run)
+    rng = np.random.default_rng(2)
+    lines = []
+    for i in range(6):
+        m, masks, cls = synth.training_sample(i, 128)
+        ipath = str(tmp_path / ("img%d.fits" % i))
+        fitsio.write_primary(ipath, m)
+        k = int(np.argmax(masks.sum((0, 1))))
+        mpath = str(tmp_path / ("mask%d.fits" % i))
+        fitsio.write_primary(mpath, masks[:, :, k].astype(np.float32))
+        lines.append("%s,%s,%s" % (ipath, mpath, ["sidelobe", "source", "galaxy"][int(cls[k]) - 1]))
+    lst = str(tmp_path / "list.dat")
+    open(lst, "w").write("\n".join(lines) + "\n")
+    logs = str(tmp_path / "logs")
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path))
+    try:
+        rc = run.main(["train", "--datalist", lst, "--imgsize", "128", "--nimg_per_gpu", "1", "--nepochs", "1", "--epoch_length", "2",
+                       "--nvalidation_steps", "1", "--validation_data_fract", "0.34", "--logs", logs,
+                       "--train_rois_per_image", "32", "--rpn_train_anchors_per_image", "64", "--max_gt_instances", "8"])
+    finally:
+        os.chdir(cwd)
+    assert rc == 0
+    files = glob.glob(os.path.join(logs, "*", "mask_rcnn_rg-dataset_0001.h5"))
+    assert len(files) == 1, os.listdir(logs)
+    rc = run.main(["detect", "--image", lines[0].split(",")[0], "--weights", files[0], "--imgsize", "128",
+                   "--detect_outfile_json", str(tmp_path / "det.json"), "--logs", logs])
+    assert rc == 0
