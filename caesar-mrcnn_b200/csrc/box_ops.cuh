@@ -242,12 +242,13 @@ __device__ inline void popper_warp(HeapEntry* h, const int n, uint16_t* order, P
   }
   // ---- fast mode: fixed schedule (pop j starts in round 2j on lane j & 7, a lane is free again after <= 13 rounds),
   // no freeze logic.  Valid while every pop that stops is the oldest one in flight (pops normally end in order: a pop
-  // reaches its leaf after the older ones); the first stop that comes earlier — a v larger than a child high up,
+  // reaches its leaf after the older ones; the oldest is then a counter, not a search); the first stop that comes earlier — a v larger than a child high up,
   // which starts around pop 1200 of 6000 — is not committed: nobody stores in that round and the careful loop below
   // takes over from the same state.
   if (npipe > 0) {
     int r = 0;                                             // rounds done; lane 0 holds pop 0 (started "in round 0")
     int mystart = lane < 8 ? 2 * (lane == 0 ? 8 : lane) : INT_MAX;
+    int jo = 0;                                            // oldest pop in flight (every pop below it has ended)
     bool handover = false;
     while (true) {
       if ((r & 15) == 0 && r > 0) {
@@ -283,10 +284,6 @@ __device__ inline void popper_warp(HeapEntry* h, const int n, uint16_t* order, P
       const bool in = active && l <= len;
       const uint4 kids = lds128(&h[in ? l : 2]);
       const uint2 u = lds64(&h[vsrc]);
-      const unsigned a0 = __ballot_sync(FULL, active);
-      const int jn = min(npipe, (r >> 1) + 1);             // pops started so far: in flight are [jn-8, jn)
-      const unsigned rot0 = ((a0 | (a0 << 8)) >> (jn & 7)) & 0xffu;
-      const bool oldest = pop == jn - 9 + __ffs(rot0);     // no older pop in flight: my v is final
       if (active && (int)u.y != vid) {
         vs = __uint_as_float(u.x);
         vid = (int)u.y;
@@ -297,10 +294,15 @@ __device__ inline void popper_warp(HeapEntry* h, const int n, uint16_t* order, P
       const float xs = right ? rs : ls;
       const int xid = (int)(right ? kids.w : kids.y);
       const bool stop = !in || xs < vs;
-      if (__any_sync(FULL, active && stop && !oldest)) {
+      // in this mode pops end in order, so "the oldest pop in flight" is a warp-uniform counter jo: ONE vote per round says
+      // who wants to stop; anybody but lane jo & 7 doing so is the early stop that hands over to the careful loop
+      const unsigned sb = __ballot_sync(FULL, active && stop);
+      const unsigned ob = 1u << (jo & 7);
+      if (sb & ~ob) {
         handover = true;
         break;
       }
+      jo += (sb & ob) ? 1 : 0;
       if (active) {
         const float ss = stop ? vs : xs;
         const int sid = stop ? vid : xid;

@@ -59,6 +59,21 @@ def mold_image(images, config):
     return images.astype(np.float32) - config.MEAN_PIXEL
 
 
+def expand_mask_bits(mask_bits, mask_shape):
+    """One image's packed detection masks (result(expand=False): uint32 [H*W, words]) -> the reference's [H, W, N] bool array
+    (mrcnn/model.py:2613-2619); same host routine as the default path, one image at a time."""
+    H, W, n = mask_shape
+    if n == 0:
+        return np.empty((H, W, 0))
+    bits = np.ascontiguousarray(mask_bits).view(np.uint32)
+    dense = np.empty((H * W * n,), dtype=np.uint8)
+    cnt = np.array([n], dtype=np.int32)
+    dst = (ctypes.c_void_p * 1)(dense.ctypes.data)
+    _native.check(_native.lib().mrcnn_host_expand_mask_bits(bits.ctypes.data, 1, H * W, bits.shape[1], cnt.ctypes.data, dst, 0),
+                  "host_expand_mask_bits")
+    return dense.reshape(H, W, n).view(np.bool_)
+
+
 def unmold_image(normalized_images, config):
     return (normalized_images + config.MEAN_PIXEL).astype(np.uint8)
 
@@ -141,10 +156,13 @@ class _PendingDetection(object):
     def __init__(self, model, bufs, maps, slot):
         self._model, self._bufs, self._maps, self._done, self._slot = model, bufs, maps, None, slot
 
-    def result(self):
+    def result(self, expand=True):
+        """expand=False (extension): leave each image's masks as the packed bits that crossed PCIe — dict keys rois,
+        class_ids, scores, mask_bits (uint32 [H*W, words], bit k of word j = detection 32*j + k), mask_shape (H, W, N) —
+        for consumers that do not need the dense [H,W,N] bool arrays at once (expand_mask_bits makes them on demand)."""
         if self._done is None:
             _native.check(self._model._lib.mrcnn_engine_wait_slot(self._model._engine, self._slot), "engine_wait_slot")
-            self._done = self._model._results_from_buffers(self._bufs)
+            self._done = self._model._results_from_buffers(self._bufs, expand)
             self._maps = None
         return self._done
 
@@ -567,12 +585,15 @@ class MaskRCNN(object):
         del sets
 
     @staticmethod
-    def _results_from_buffers(bufs):
+    def _results_from_buffers(bufs, expand=True):
         """Expands the mask bits of one batch into the reference's [H0,W0,N] bool arrays (multi-threaded C++ behind the
         C ABI) and builds the detect()-style dicts (mrcnn/model.py:2697-2703)."""
         rois_n, cls_n, sc_n, cnt_n, bits_n, dense_n, (H0, W0) = bufs
         B, D = cls_n.shape
         npx, dw = bits_n.shape[1], bits_n.shape[2]
+        if not expand:
+            return [{"rois": rois_n[i, :int(cnt_n[i])], "class_ids": cls_n[i, :int(cnt_n[i])], "scores": sc_n[i, :int(cnt_n[i])],
+                     "mask_bits": bits_n[i], "mask_shape": (H0, W0, int(cnt_n[i]))} for i in range(B)]
         base = dense_n.ctypes.data
         dst = (ctypes.c_void_p * B)(*[base + i * npx * D for i in range(B)])
         _native.check(_native.lib().mrcnn_host_expand_mask_bits(bits_n.ctypes.data, B, npx, dw, cnt_n.ctypes.data, dst, 0),

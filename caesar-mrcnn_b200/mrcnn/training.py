@@ -579,6 +579,7 @@ class TrainGraph(object):
         self._dS = torch.zeros(nb, dtype=torch.float32, device=self.device)     # and its gradient, filled by ConvTC.backward
         self._dT = torch.zeros(nb, dtype=torch.float32, device=self.device)
         self._box_shift = torch.tensor([0., 0., 1., 1.], device=self.device)
+        self._box_scale = torch.full((4,), float(config.IMAGE_SHAPE[0]) - 1.0, device=self.device)
         self.seed_device = torch.zeros(1, dtype=torch.int64, device=self.device)     # advanced on the device every step
         self.taps = {}
 
@@ -880,7 +881,9 @@ class TrainGraph(object):
         images, image_meta, rpn_match, rpn_bbox_t, gt_class_ids, gt_boxes, gt_masks = inputs
         S = float(cfg.IMAGE_SHAPE[0])
         # norm_boxes_graph (mrcnn/model.py:3003-3017): (boxes - [0,0,1,1]) / (S-1)
-        gt_norm = ((gt_boxes.float() - self._box_shift) / (S - 1.0)).contiguous()
+        # divisor as a TENSOR: torch turns division by a Python scalar into a multiplication by its reciprocal (1 ulp off
+        # the reference's tf.divide)
+        gt_norm = ((gt_boxes.float() - self._box_shift) / self._box_scale).contiguous()
         self.begin_step()
         P = self.backbone_fpn(images)
         rpn_class_logits, rpn_class, rpn_bbox = self.rpn(P)

@@ -330,6 +330,22 @@ def test_async_pipelined_detect_maps_equals_sync(model):
     model.wait()
 
 
+def test_packed_mask_results_expand_to_the_same_masks(model):
+    """result(expand=False) leaves the masks as the packed bits that crossed PCIe; expand_mask_bits turns one image's bits
+    into exactly the [H,W,N] bool array the default path returns."""
+    from mrcnn import model as modellib
+    a = torch.from_numpy(synth.radio_maps(B, 132, start=41)).pin_memory()
+    ref = model.detect_maps(a)
+    packed = model.detect_maps_async(a).result(expand=False)
+    for x, y in zip(packed, ref):
+        assert "masks" not in x and x["mask_shape"] == y["masks"].shape
+        for k in ("rois", "class_ids", "scores"):
+            assert np.array_equal(x[k], y[k]), k
+        full = modellib.expand_mask_bits(x["mask_bits"], x["mask_shape"])
+        assert full.dtype == y["masks"].dtype and np.array_equal(full, y["masks"])
+    model.wait()
+
+
 def test_detect_images_of_different_original_sizes(model):
     """The reference only requires equal MOLDED shapes in a batch (mrcnn/model.py:2655-2658): two frames of
     different size go through one graph pass and are unmolded per image, bit-exact against the oracle."""

@@ -314,6 +314,14 @@ def test_training_graph_losses_and_gradients_vs_fp32_oracle():
     torch.cuda.synchronize()
     taps = {k: v.detach().cpu() for k, v in g.taps.items()}
     assert int(taps["counts"][0, 0]) > 0, "no positive ROI in the tiny case"
+    # the graph's own DetectionTargetLayer call (GT boxes normalised inside the graph) against the oracle, bit for bit
+    gt_norm = ((inputs[5][0].astype(np.float32) - np.array([0, 0, 1, 1], np.float32)) / np.float32(127)).astype(np.float32)
+    o = TO.detection_targets(taps["rpn_rois"][0].numpy(), inputs[4][0], gt_norm, inputs[6][0], cfg.TRAIN_ROIS_PER_IMAGE, cfg.ROI_POSITIVE_RATIO,
+                             (0.1, 0.1, 0.2, 0.2), (28, 28), False, 11, 0)
+    assert np.array_equal(taps["rois"][0].numpy().view(np.uint32), o[0].view(np.uint32))
+    assert np.array_equal(taps["target_class_ids"][0].numpy(), o[1])
+    assert np.array_equal(taps["target_bbox"][0].numpy().view(np.uint32), o[2].view(np.uint32))
+    assert np.array_equal(taps["target_mask"][0].numpy(), o[3])
     # the oracle on the same ROIs / targets
     net = TO.TrainNet(weights, cfg)
     P = net.backbone_fpn(inputs[0])

@@ -55,7 +55,7 @@ def popper_warp_model(sorted_scores, stats=None, ref=None):
         order[0] = h[1][1]
         L[0].update(len=n - 1, vsrc=n, pop=0, active=True)
         # ---- fast mode: fixed schedule, no freeze logic, hands over at the first stop that comes too early
-        r, handover = 0, False
+        r, handover, jo = 0, False, 0
         mystart = [2 * (8 if lane == 0 else lane) if lane < 8 else INT_MAX for lane in range(32)]
         while True:
             if (r & 15) == 0 and r > 0:
@@ -75,28 +75,27 @@ def popper_warp_model(sorted_scores, stats=None, ref=None):
                     if x["pop"] < npipe:
                         x.update(c=1, len=n - x["pop"] - 1, vsrc=n - x["pop"], vid=-1, xlast=INF, active=True)
                     mystart[lane] += 16
-            T, early = [], False
-            a0 = sum(1 << i for i in range(32) if L[i]["active"])
-            jn = min(npipe, (r >> 1) + 1)
-            rot0 = ((a0 | (a0 << 8)) >> (jn & 7)) & 0xFF
+            T, sb = [], 0
             for lane in range(32):
                 x = L[lane]
                 l = 2 * x["c"]
                 inn = x["active"] and l <= x["len"]
                 kl, kr = (h[l], h[l + 1]) if inn else (h[2], h[3])
                 u = h[x["vsrc"]]
-                safe = x["pop"] == jn - 9 + _ffs(rot0)
                 if x["active"] and u[1] != x["vid"]:
                     x["vs"], x["vid"] = u
                     x["hazard"] |= x["xlast"] < x["vs"]
                 right = l < x["len"] and not (kr[0] < kl[0])
                 xs, xid = kr if right else kl
                 stop = (not inn) or xs < x["vs"]
-                early |= x["active"] and stop and not safe
+                if x["active"] and stop:
+                    sb |= 1 << lane
                 T.append((l, right, xs, xid, stop))
-            if early:
+            ob = 1 << (jo & 7)
+            if sb & ~ob:
                 handover = True
                 break
+            jo += 1 if (sb & ob) else 0
             for lane in range(32):
                 l, right, xs, xid, stop = T[lane]
                 x = L[lane]
