@@ -176,6 +176,18 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major, 128B-swizzled operand: start>>4 | LBO>>4 (distance between 64-element chunks along M/N) | SBO>>4 (distance
+// between 8-row groups along K) | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -211,7 +223,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BLOCK_N, bool EPI_TMA>
+// B_MN (train mode, data gradient): the B operand is read MN-major straight from the FORWARD layer's weights
+// [Cout_f, KH, KW, Cin_f] — this GEMM's K runs over (flipped tap, Cout_f) and its N over Cin_f, which is the weights'
+// contiguous dimension — so no transposed copy of the weights is ever made: a k-block is BLOCK_N/64 TMA boxes of
+// 64 Cout_f rows x 64 Cin_f columns (the canonical MN-major SW128 layout, see wgrad_kernel).
+template <int BLOCK_N, bool EPI_TMA, bool B_MN = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                      const __grid_constant__ CUtensorMap tmap_b,
                                                                      const __grid_constant__ CUtensorMap tmap_out,
@@ -315,7 +331,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
               tma_load_im2col_4d(a_dst, &tmap_a, fb, cb * BLOCK_K, w0, h0, n0, (uint16_t)sx, (uint16_t)r);
             else
               tma_load_4d(a_dst, &tmap_a, fb, cb * BLOCK_K, w0 + sx, h0 + r, n0);
-            tma_load_2d(a_dst + Cfg::A_BYTES, &tmap_b, fb, kb * BLOCK_K, b_row);
+            if constexpr (B_MN) {
+              const int ftap = (p.kh - 1 - r) * kw + (kw - 1 - sx);      // correlation with the flipped filter
+#pragma unroll
+              for (int nc = 0; nc < BLOCK_N / 64; ++nc)
+                tma_load_2d(a_dst + Cfg::A_BYTES + nc * 8192, &tmap_b, fb, ftap * p.cout + b_row + nc * 64, cb * BLOCK_K);
+            } else {
+              tma_load_2d(a_dst + Cfg::A_BYTES, &tmap_b, fb, kb * BLOCK_K, b_row);
+            }
           }
           __syncwarp();
           if (++cb == cin_blocks) {
@@ -336,7 +359,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     // ===== MMA issuer: alternates between the two TMEM accumulators (warp converged, one elected lane issues) =====
     {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BLOCK_N, M = 128
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (B_MN ? (1u << 16) : 0u) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                                  ((uint32_t)(BLOCK_M >> 4) << 24);
       uint32_t stage = 0, phase = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
@@ -360,7 +383,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the >>4 address field
-              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              const uint64_t dbk = B_MN ? make_sw128_mn_desc(a_addr + Cfg::A_BYTES + k * 2048, 8192, 1024) : db + (uint64_t)(2 * k);
+              umma_bf16(d_tmem, da + (uint64_t)(2 * k), dbk, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit(empty_bar(s));          // frees the ring slot once these MMAs have read it
             if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));      // accumulator complete
@@ -907,18 +931,6 @@ template <int BLOCK_N> struct WgradCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-// MN-major, 128B-swizzled operand: start>>4 | LBO>>4 (distance between 64-element chunks along M/N) | SBO>>4 (distance
-// between 8-row groups along K) | version 1 | SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(lbo_bytes >> 4) << 16;
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
 template <int BLOCK_N>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
                                                                const __grid_constant__ CUtensorMap tmap_x, const WgradParams p) {
@@ -1084,20 +1096,20 @@ template <int BN> int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx
   return MRCNN_OK;
 }
 
-template <int BN, bool EPI> int launch_tile(const ConvPlan* plan, cudaStream_t st) {
+template <int BN, bool EPI, bool BMN = false> int launch_tile(const ConvPlan* plan, cudaStream_t st) {
   using Cfg = TileCfg<BN, EPI>;
   static bool attr_done[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_done[dev]) {
-    MRCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MRCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done[dev] = true;
   }
   static int num_sms = 0;
   if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned tiles = plan->grid.x;
   const unsigned grid = tiles < (unsigned)num_sms ? tiles : (unsigned)num_sms;   // one persistent CTA per SM
-  MRCNN_CHECK_CUDA(mrcnn_launch(conv_gemm_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, plan->tmap_a,
+  MRCNN_CHECK_CUDA(mrcnn_launch(conv_gemm_kernel<BN, EPI, BMN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, plan->tmap_a,
                                 plan->tmap_b, plan->tmap_out, plan->tmap_res, plan->p));
   mrcnn_count_launch(1);
   return MRCNN_OK;
@@ -1153,6 +1165,10 @@ int conv_plan_create_ex(const mrcnn_conv_desc* d, const void* x, const void* w, 
     else if (cout_total <= 64) block_n = 64;
     else if (cout_total % 256 == 0 && m_tiles_est * (cout_total / 256) >= 2LL * sms) block_n = 256;
     else block_n = 128;
+  }
+  if (plan->b_mn) {       // tile width must divide the N extent (a box past it would read the next filter tap, not zeros)
+    while (block_n > 64 && d->cout % block_n != 0) block_n >>= 1;
+    if (block_n < 64) block_n = 64;
   }
   MRCNN_REQUIRE(block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256, "conv2d: block_n must be 32/64/128/256");
   if (d->out_mode == 1) MRCNN_REQUIRE(d->cout % block_n == 0, "conv2d: deconv cout %% block_n != 0");
@@ -1227,11 +1243,23 @@ int conv_plan_create_ex(const mrcnn_conv_desc* d, const void* x, const void* w, 
 
   // ---- B: weights [cout_total, K] K-major; rows beyond cout_total are OOB -> zero fill --------
   const unsigned long long K = (unsigned long long)d->kh * d->kw * d->cin;
+  if (plan->b_mn) {
+    // data gradient: w is the FORWARD layer's [Cout_f = d->cin rows, KH*KW*Cin_f columns] matrix, read in 64 x 64 boxes
+    MRCNN_REQUIRE(block_n >= 64 && d->cout % block_n == 0 && d->out_mode == 0, "conv2d (dgrad): Cin of the forward layer must be a "
+                  "multiple of the tile width (%d)", block_n);
+    const unsigned long long cols = (unsigned long long)d->kh * d->kw * d->cout;
+    cuuint64_t bdims[2] = {cols, (cuuint64_t)d->cin};
+    cuuint64_t bstr[1] = {cols * 2};
+    cuuint32_t bbox[2] = {64, 64};
+    rc = encode_map(&plan->tmap_b, w, 2, bdims, bstr, bbox);
+    if (rc) return rc;
+  } else {
   cuuint64_t bdims[2] = {K, (cuuint64_t)cout_total};
   cuuint64_t bstr[1] = {K * 2};
   cuuint32_t bbox[2] = {64, (cuuint32_t)block_n};
   rc = encode_map(&plan->tmap_b, w, 2, bdims, bstr, bbox);
   if (rc) return rc;
+  }
 
   memset(&plan->tmap_out, 0, sizeof(CUtensorMap));
   memset(&plan->tmap_res, 0, sizeof(CUtensorMap));
@@ -1291,6 +1319,23 @@ int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, 
 }
 
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t st) {
+  if (plan->b_mn) {
+    if (plan->epi_tma) {
+      switch (plan->block_n) {
+        case 64: return launch_tile<64, true, true>(plan, st);
+        case 128: return launch_tile<128, true, true>(plan, st);
+        case 256: return launch_tile<256, true, true>(plan, st);
+      }
+    } else {
+      switch (plan->block_n) {
+        case 64: return launch_tile<64, false, true>(plan, st);
+        case 128: return launch_tile<128, false, true>(plan, st);
+        case 256: return launch_tile<256, false, true>(plan, st);
+      }
+    }
+    mrcnn_set_error("conv2d (dgrad): bad block_n %d", plan->block_n);
+    return MRCNN_ERR_INVALID;
+  }
   if (plan->epi_tma) {
     switch (plan->block_n) {
       case 32: return launch_tile<32, true>(plan, st);
@@ -1402,4 +1447,26 @@ extern "C" int mrcnn_conv2d_wgrad_bf16(const mrcnn_conv_desc* d, const void* x, 
   p.wdot = wdot;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return bn == 128 ? launch_wgrad<128>(tdy, tx, p, st) : launch_wgrad<64>(tdy, tx, p, st);
+}
+
+extern "C" int mrcnn_conv2d_dgrad_bf16(const mrcnn_conv_desc* fwd, const void* dy, const void* w, const float* ones,
+                                       const float* zeros, void* dx, void* stream) {
+  MRCNN_REQUIRE(fwd && dy && w && ones && zeros && dx, "conv2d_dgrad: null pointer");
+  const bool k1 = fwd->kh == 1 && fwd->kw == 1 && fwd->pad == 0 && fwd->stride == 1;
+  const bool k3 = fwd->kh == 3 && fwd->kw == 3 && fwd->pad == 1 && fwd->stride == 1;
+  MRCNN_REQUIRE(k1 || k3, "conv2d_dgrad: 1x1 stride 1 or 3x3 stride 1 pad 1 only");
+  MRCNN_REQUIRE(fwd->cin % 64 == 0 && fwd->cout % 64 == 0, "conv2d_dgrad: Cin and Cout must be multiples of 64");
+  mrcnn_conv_desc d = *fwd;          // the data gradient is a stride-1 convolution of dy [N,H,W,Cout_f] giving dx [N,H,W,Cin_f]
+  d.cin = fwd->cout;
+  d.cout = fwd->cin;
+  d.relu = 0;
+  d.residual_upsample2 = 0;
+  d.out_dtype = MRCNN_DTYPE_BF16;
+  d.out_mode = 0;
+  d.out_ld = 0;
+  ConvPlan plan;
+  plan.b_mn = 1;
+  int rc = conv_plan_create(&d, dy, w, ones, zeros, nullptr, dx, 0, &plan);
+  if (rc) return rc;
+  return conv_plan_launch(&plan, static_cast<cudaStream_t>(stream));
 }

@@ -35,6 +35,7 @@ struct ConvPlan {
   CUtensorMap tmap_out;        // epi_tma: [M, cout] bf16 output, box 32 ch x 128 rows, 64B swizzle
   CUtensorMap tmap_res;        // epi_tma: same geometry over the residual tensor
   int epi_tma = 0;             // epilogue through shared memory with TMA residual loads / output stores
+  int b_mn = 0;                // set BEFORE conv_plan_create: data-gradient mode, B read MN-major from the forward weights
   ConvGemmParams p;
   int block_n;
   dim3 grid;

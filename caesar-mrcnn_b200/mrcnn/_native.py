@@ -118,6 +118,7 @@ SIGNATURES = {
     "mrcnn_host_contours": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mrcnn_host_contours_fetch": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mrcnn_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mrcnn_conv2d_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mrcnn_shuffle_key": (ctypes.c_uint32, [ctypes.c_ulonglong, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
     "mrcnn_detection_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                         c_float, c_void_p, c_int, c_int, ctypes.c_ulonglong, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -507,14 +507,15 @@ def _functions(torch):
             # data gradient: correlation of (dz * scale) with the flipped, transposed filter — the forward kernel again
             d_x = None
             if ctx.needs_input_grad[0]:
-                wt = L.w_op if KH == 1 else L.w_op.flip(1, 2)
-                wt = wt.permute(3, 1, 2, 0).contiguous()                       # [Cin, KH, KW, Cout]
+                # the same implicit GEMM with the B operand read MN-major from the forward weights themselves
+                # (mrcnn_conv2d_dgrad_bf16): no flipped / transposed copy of the weights
                 dsub = torch.empty((N, OH, OW, Cin), dtype=torch.bfloat16, device=dev)
-                desc = _native.ConvDesc(n=N, h=OH, w=OW, cin=Cout, kh=KH, kw=KW, stride=1, pad=pad, cout=Cin, relu=0,
+                desc = _native.ConvDesc(n=N, h=OH, w=OW, cin=Cin, kh=KH, kw=KW, stride=1, pad=pad, cout=Cout, relu=0,
                                         residual_upsample2=0, out_dtype=_native.DTYPE_BF16, out_mode=0, out_ld=0)
                 with torch.cuda.device(dev):
-                    _native.check(lib.mrcnn_conv2d_bf16(ctypes.byref(desc), _native.ptr(op), _native.ptr(wt), _native.ptr(L.const(Cin, 1.0)),
-                                                        _native.ptr(L.const(Cin, 0.0)), None, _native.ptr(dsub), st), "conv2d (dgrad)")
+                    _native.check(lib.mrcnn_conv2d_dgrad_bf16(ctypes.byref(desc), _native.ptr(op), _native.ptr(L.w_op),
+                                                              _native.ptr(L.const(Cin, 1.0)), _native.ptr(L.const(Cin, 0.0)),
+                                                              _native.ptr(dsub), st), "conv2d_dgrad")
                 if stride == 1:
                     d_x = dsub.permute(0, 3, 1, 2)
                 else:

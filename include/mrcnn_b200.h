@@ -172,6 +172,13 @@ int mrcnn_conv2d_bf16(const mrcnn_conv_desc* desc, const void* x, const void* w,
  * gradient of a per-channel scale applied behind the convolution (folded BatchNorm) times that scale. */
 int mrcnn_conv2d_wgrad_bf16(const mrcnn_conv_desc* desc, const void* x, const void* dy, float* dw, const void* w,
                             float* wdot, void* stream);
+/* Data gradient of mrcnn_conv2d_bf16 (train mode): dx[n,h,w,ci] = sum_{r,s,co} dy[n, h-r+pad, w-s+pad, co] * w[co,r,s,ci], the same
+ * implicit GEMM with the B operand read MN-major from the FORWARD layer's weights w [Cout,KH,KW,Cin] (no transposed copy).
+ * fwd describes the forward layer (n, h, w = the OUTPUT extent, which equals the input extent for these stride-1 layers);
+ * dy [N,H,W,Cout] bf16 (already multiplied by any per-channel scale), dx [N,H,W,Cin] bf16; ones / zeros: device float32
+ * vectors of at least Cin elements (epilogue scale / shift).  1x1 stride 1 or 3x3 stride 1 pad 1, Cin and Cout % 64 == 0. */
+int mrcnn_conv2d_dgrad_bf16(const mrcnn_conv_desc* fwd, const void* dy, const void* w, const float* ones, const float* zeros,
+                            void* dx, void* stream);
 /* reference implementation on CUDA cores (fp32 accumulate) used only by the tests to check the
  * tcgen05 path on the device at full size */
 int mrcnn_conv2d_bf16_simt(const mrcnn_conv_desc* desc, const void* x, const void* w, const float* scale,

@@ -243,8 +243,14 @@ def test_error_conventions(weights):
     bad.IMAGE_SHAPE = np.array([200, 200, 3])
     with pytest.raises(Exception, match="dividable by 2"):
         modellib.MaskRCNN(mode="inference", config=bad, model_dir="/tmp/mrcnn_logs")
+    # mode='training' builds the training graph since round 2 (tests/test_gpu_training.py); the variants it does not
+    # cover still say so
+    tb = _config(1)
+    tb.TRAIN_BN = True
     with pytest.raises(NotImplementedError):
-        modellib.MaskRCNN(mode="training", config=cfg, model_dir="/tmp/mrcnn_logs")
+        modellib.MaskRCNN(mode="training", config=tb, model_dir="/tmp/mrcnn_logs")
+    with pytest.raises(AssertionError):
+        m.train(None, None, 0.001, 1, "all")                          # "Create model in training mode."
     w = dict(weights)
     w["conv1"] = [w["conv1"][0][:, :, :, :32], w["conv1"][1]]
     with pytest.raises(Exception, match="shape mismatch"):

@@ -230,6 +230,31 @@ def test_conv_wgrad_tcgen05_vs_torch(case):
     assert np.abs(wdot.cpu().numpy() - want_dot).max() <= 2e-3 * np.abs(want_dot).max() + 1e-2, case
 
 
+@pytest.mark.parametrize("case", ["1x1", "1x1_wide", "3x3_mask", "3x3_backbone", "3x3_cin64"])
+def test_conv_dgrad_tcgen05_vs_torch(case):
+    """mrcnn_conv2d_dgrad_bf16 (the forward implicit GEMM with its B operand read MN-major from the forward weights,
+    filter flipped by coordinates) against torch's float32 conv2d_input on the same bf16 tensors."""
+    nat = _native()
+    lib = nat.lib()
+    n, h, w, cin, cout, k = {"1x1": (2, 16, 16, 256, 64, 1), "1x1_wide": (1, 32, 32, 1024, 256, 1), "3x3_mask": (19, 14, 14, 256, 256, 3),
+                             "3x3_backbone": (2, 32, 32, 128, 128, 3), "3x3_cin64": (3, 17, 23, 64, 192, 3)}[case]
+    rng = np.random.default_rng(len(case))
+    dy = torch.from_numpy(rng.normal(0, 1, (n, h, w, cout)).astype(np.float32)).cuda().to(torch.bfloat16)
+    wts = torch.from_numpy(rng.normal(0, 0.05, (cout, k, k, cin)).astype(np.float32)).cuda().to(torch.bfloat16)
+    dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device="cuda")
+    ones = torch.ones(cin, dtype=torch.float32, device="cuda")
+    zeros = torch.zeros(cin, dtype=torch.float32, device="cuda")
+    desc = nat.ConvDesc(n=n, h=h, w=w, cin=cin, kh=k, kw=k, stride=1, pad=k // 2, cout=cout, relu=0, residual_upsample2=0,
+                        out_dtype=nat.DTYPE_BF16, out_mode=0, out_ld=0)
+    nat.check(lib.mrcnn_conv2d_dgrad_bf16(ctypes.byref(desc), nat.ptr(dy), nat.ptr(wts), nat.ptr(ones), nat.ptr(zeros), nat.ptr(dx), None),
+              "conv2d_dgrad")
+    torch.cuda.synchronize()
+    want = torch.nn.grad.conv2d_input((n, cin, h, w), wts.float().permute(0, 3, 1, 2), dy.float().permute(0, 3, 1, 2), stride=1,
+                                      padding=k // 2).permute(0, 2, 3, 1).cpu().numpy()
+    got = dx.float().cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-2 * np.abs(want).max() + 1e-3, (case, np.abs(got - want).max(), np.abs(want).max())
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the whole training graph on a tiny configuration
 # ---------------------------------------------------------------------------------------------------------------
