@@ -1,7 +1,7 @@
 // ProposalLayer — one fused pass per image (one 1024-thread CTA per image):
 //   radix-select + bitonic sort top-k over the anchor fg scores (ties -> lower index first)
 //   -> gather deltas/anchors, apply_box_deltas, clip to [0,1]
-//   -> greedy NMS in shared memory in TF-1.13 pop order -> zero-padded rois.
+//   -> greedy NMS in shared memory in TF-1.13 pop order (closed form, see step 5) -> zero-padded rois.
 // Replaces mrcnn/model.py:329-406 (ProposalLayer.call), :287-326 (apply_box_deltas_graph,
 // clip_boxes_graph) and the per-image Python unrolling of utils.batch_slice (utils.py:872-906).
 // Bit-exact contract: top-k indices, NMS keep indices and rois equal oracle/graph_layers.py
@@ -118,6 +118,16 @@ __device__ inline void sort_desc_regs(unsigned long long* buf) {
 #pragma unroll
   for (int r = 0; r < 8; ++r) buf[tid * 8 + r] = e[r];
   __syncthreads();
+}
+
+// Pre-order "node, right, left" rank of heap index i (1-based) among indices below 2^16: the path from the root (bits of
+// i below its leading one, 1 = right child) inverted so that right sorts first, left-aligned, with the depth as the
+// tie-break that puts an ancestor before its right-most descendants.
+__device__ __forceinline__ uint32_t pop_key(uint32_t i) {
+  const int d = 31 - __clz(i);
+  const uint32_t path = i - (1u << d);
+  const uint32_t inv = ~path & ((1u << d) - 1u);
+  return ((inv << (16 - d)) << 5) | (uint32_t)d;
 }
 
 __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p) {
@@ -243,13 +253,40 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
   uint16_t* selected = order + ((K + 1) & ~1);                          // [R]
   float4* kept_box = reinterpret_cast<float4*>(r0 + p.kept_off);         // [R]
   float* kept_area = reinterpret_cast<float*>(kept_box + R);            // [R]
-  // first pop position whose order the heap decides (first pair of equal adjacent scores); K = no ties at all
+  // ---- 5. pop order in closed form ---------------------------------------------------------------------------------
+  // TF 1.13 pops a std::priority_queue; equal scores come out in whatever order libstdc++'s heap gives them.  The
+  // initial heap is the sorted array (entry of rank q at index q+1), every position of a heap holds the maximum of its
+  // subtree, and an element only ever moves up its own ancestor chain — so two equal elements meet exactly once, as the
+  // two children of their lowest common ancestor, where __adjust_heap takes the RIGHT child on a tie.  Hence: distinct
+  // scores pop in sorted order, and a run of equal scores pops in "node, right subtree, left subtree" pre-order of the
+  // members' heap indices (pop_key below).  This holds until an element is moved by pop_heap's "last element to the
+  // hole" step before it is popped itself, i.e. for every run that ends at or below rank K/2; a run reaching beyond
+  // (more than half of the candidates tied: a saturated plateau) is left to the heap emulation (popper warp), which the
+  // workers then wait for from that run's first position on.  tests/test_heap_pipeline_sim.py checks the closed form
+  // against libstdc++ on every tie pattern.
   if (tid == 0) misc[3] = K;
   __syncthreads();
-  for (int q = tid; q + 1 < K; q += nt)
-    if (s_scores[q] == s_scores[q + 1]) atomicMin(&misc[3], q);
+  const int half = K / 2;
+  for (int q = tid; q < K; q += nt) {
+    const float sc = s_scores[q];
+    int pos = q;
+    if ((q > 0 && s_scores[q - 1] == sc) || (q + 1 < K && s_scores[q + 1] == sc)) {
+      int s0 = q, e0 = q;
+      while (s0 > 0 && s_scores[s0 - 1] == sc) --s0;
+      while (e0 + 1 < K && s_scores[e0 + 1] == sc) ++e0;
+      if (e0 + 1 > half) {
+        atomicMin(&misc[3], s0);               // not covered: the heap decides from position s0 on
+      } else {
+        const uint32_t kq = pop_key((uint32_t)q + 1u);
+        int r = 0;
+        for (int m = s0; m <= e0; ++m) r += pop_key((uint32_t)m + 1u) < kq ? 1 : 0;
+        pos = s0 + r;
+      }
+    }
+    order[pos] = (uint16_t)q;
+  }
   __syncthreads();
-  const int first_tie = misc[3];
+  const int first_tie = misc[3];               // positions below it are final in order[]
   const bool any_tie = first_tie < K;
   if (any_tie) {
     // pushing the (already sorted) scores in order never sifts up: the array IS the initial heap
@@ -260,7 +297,6 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) proposal_kernel(PropParams p)
       heap[q + 1] = e;
     }
   }
-  for (int q = tid; q < K; q += nt) order[q] = (uint16_t)q;      // pop order below first_tie, and everywhere without ties
   __syncthreads();
 
   if (p.phase_clocks && tid == 0) p.phase_clocks[(size_t)b * 8 + 5] = clock64();

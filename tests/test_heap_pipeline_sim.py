@@ -237,3 +237,51 @@ def test_pipelined_pops_equal_std_pop_heap_reference_sizes(kind):
         assert got == ref, (kind, n)
         assert not st["hazard"]
         assert st["rounds"] <= 2.2 * st["npipe"] + 32       # freezes are rare: about two rounds per pop
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# closed-form pop order (csrc/proposal.cu step 5): no heap at all for runs of equal scores that end at or below rank K/2
+# ---------------------------------------------------------------------------------------------------------------
+
+def pop_key(i):
+    """same integer as the device function pop_key: pre-order 'node, right, left' rank of heap index i"""
+    d = i.bit_length() - 1
+    path = i - (1 << d)
+    inv = (~path) & ((1 << d) - 1)
+    return ((inv << (16 - d)) << 5) | d
+
+
+def closed_form_order(sorted_scores):
+    """-> (order, covered): order[k] for k < covered is the k-th pop; from `covered` on the heap emulation decides"""
+    n = len(sorted_scores)
+    order = list(range(n))
+    covered, q = n, 0
+    while q < n:
+        e = q
+        while e + 1 < n and sorted_scores[e + 1] == sorted_scores[q]:
+            e += 1
+        if e > q:
+            if e + 1 > n // 2:
+                covered = min(covered, q)
+            else:
+                order[q:e + 1] = sorted(range(q, e + 1), key=lambda r: pop_key(r + 1))
+        q = e + 1
+    return order, covered
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_closed_form_pop_order_equals_std_priority_queue(kind):
+    rng = np.random.default_rng(200 + KINDS.index(kind))
+    checked = 0
+    for n in list(range(1, 70)) + [127, 128, 129, 255, 256, 257, 1000, 4097, 6000, 6144]:
+        for _ in range(3 if n < 1000 else 1):
+            s = _scores(rng, n, kind)
+            ref = oracle_native.heap_pop_order(s).tolist()
+            order, covered = closed_form_order(s.tolist())
+            assert order[:covered] == ref[:covered], (kind, n, covered)
+            checked += covered
+    assert checked > 0
+    if kind in ("sparse_pairs", "many_pairs", "quantised"):         # runs that really get reordered were part of it
+        s = _scores(rng, 6000, kind)
+        order, covered = closed_form_order(s.tolist())
+        assert covered > 2500 and order[:covered] != list(range(covered))
