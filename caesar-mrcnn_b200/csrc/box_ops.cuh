@@ -73,6 +73,10 @@ __device__ __forceinline__ uint32_t float_to_key(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+__device__ __forceinline__ float key_to_float(uint32_t k) {       // inverse of float_to_key
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Exact emulation of libstdc++'s std::priority_queue<Candidate, deque, score<> pop order
 // (TF 1.13 NMS has no index tie-break; the order among equal scores is whatever
@@ -556,11 +560,13 @@ __device__ inline int block_nms(const Box4* boxes, uint16_t* order, int n, int m
   return count;
 }
 
-// block_nms for the ProposalLayer: same chunk resolution, but the popper warp runs `popper_warp` on its own and the
+// block_nms for the ProposalLayer (decode(q) -> Box4 yields the box of sorted candidate q and stores it for the output
+// stage): same chunk resolution, but the popper warp runs `popper_warp` on its own and the
 // 992 workers never wait for it at a block barrier: pop positions below `first_tie` are the sorted order itself
 // (order[] pre-filled with the identity; the heap pops the unique maximum until the first equal pair reaches the
 // root), later positions are consumed as soon as the popper has published them.  `heap` == nullptr: no ties at all.
-__device__ inline int block_nms_async(const Box4* boxes, uint16_t* order, int n, int max_out, float thr,
+template <typename Decode>
+__device__ inline int block_nms_async(Decode decode, uint16_t* order, int n, int max_out, float thr,
                                       float4* kept_box, float* kept_area, uint16_t* selected, NmsScratch* sc,
                                       PopperShared* ps, HeapEntry* heap, const float* sorted_scores, int first_tie) {
   const int tid = threadIdx.x;
@@ -589,7 +595,7 @@ __device__ inline int block_nms_async(const Box4* boxes, uint16_t* order, int n,
     if (tid < 64) {
       NBox nb;
       if (tid < n_in) {
-        nb = normalise_box(boxes[order[base + tid]]);
+        nb = normalise_box(decode((int)order[base + tid]));     // box of this candidate, computed (and stored) on first use
       } else {
         nb.ymin = nb.xmin = nb.ymax = nb.xmax = 0.f;
         nb.area = -1.f;
