@@ -8,6 +8,70 @@
 #include "common.cuh"
 #include "mrcnn_b200.h"
 
+// Pairs (i < j) inside every frame, frame-major, in the reference's double-loop order (analyze.py:1263-1266, 1335-1338).
+extern "C" int mrcnn_host_all_pairs(int n_frames, const int32_t* counts, int32_t* pairs) {
+  MRCNN_REQUIRE(n_frames >= 0 && (n_frames == 0 || counts), "host_all_pairs: bad frame list");
+  int64_t base = 0, out = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    const int n = counts[f];
+    MRCNN_REQUIRE(n >= 0, "host_all_pairs: negative frame size");
+    MRCNN_REQUIRE(pairs || n < 2, "host_all_pairs: null output");
+    for (int i = 0; i < n; ++i)
+      for (int j = i + 1; j < n; ++j) {
+        pairs[out++] = (int32_t)(base + i);
+        pairs[out++] = (int32_t)(base + j);
+      }
+    base += n;
+  }
+  return MRCNN_OK;
+}
+
+// sklearn jaccard_score(average='binary') as the reference calls it (analyze.py:1281-1284): tp / (tp + fp + fn) in
+// float64, 0.0 for an empty union
+static inline double pair_iou(int32_t inter, int32_t area_a, int32_t area_b) {
+  const int64_t uni = (int64_t)area_a + (int64_t)area_b - (int64_t)inter;
+  return uni > 0 ? (double)inter / (double)uni : 0.0;
+}
+
+// Pair tests of both graph stages of extract_det_masks for a batch (pairs implicit: mrcnn_host_all_pairs order).
+//  stage 0 (merge, analyze.py:1268-1290): flag = connected && same class && iou >= thr
+//  stage 1 (selection, analyze.py:1340-1360): flag = connected && !(split_source_sidelobe && exactly one of the two is
+//           'spurious' && iou < thr); additionally loses[v] = 1 if a linked mask has a strictly higher score, and
+//           tie_frame[f] = 1 if two linked masks of frame f have equal scores (the clique order then decides)
+extern "C" int mrcnn_host_pair_flags(int stage, int n_frames, const int32_t* counts, const int32_t* cls_or_spurious,
+                                     const float* score, const int32_t* area, const int32_t* inter, const int32_t* touch,
+                                     int use_iou, double iou_thr, uint8_t* flags, uint8_t* loses, uint8_t* tie_frame) {
+  MRCNN_REQUIRE(stage == 0 || stage == 1, "host_pair_flags: stage");
+  MRCNN_REQUIRE(n_frames >= 0 && (n_frames == 0 || counts), "host_pair_flags: bad frame list");
+  int64_t base = 0, p = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    const int n = counts[f];
+    MRCNN_REQUIRE(n >= 0, "host_pair_flags: negative frame size");
+    if (stage == 1 && tie_frame) tie_frame[f] = 0;
+    if (n >= 2) MRCNN_REQUIRE(cls_or_spurious && area && inter && touch && flags, "host_pair_flags: null pointer");
+    for (int i = 0; i < n; ++i)
+      for (int j = i + 1; j < n; ++j, ++p) {
+        const int64_t a = base + i, b = base + j;
+        bool on = touch[p] != 0;
+        if (stage == 0) {
+          on = on && cls_or_spurious[a] == cls_or_spurious[b] && pair_iou(inter[p], area[a], area[b]) >= iou_thr;
+        } else {
+          if (on && use_iou && (cls_or_spurious[a] != 0) != (cls_or_spurious[b] != 0) &&
+              pair_iou(inter[p], area[a], area[b]) < iou_thr)
+            on = false;
+          if (on && score && loses) {
+            if (score[a] < score[b]) loses[a] = 1;
+            else if (score[b] < score[a]) loses[b] = 1;
+            else if (score[a] == score[b] && tie_frame) tie_frame[f] = 1;
+          }
+        }
+        flags[p] = on ? 1 : 0;
+      }
+    base += n;
+  }
+  return MRCNN_OK;
+}
+
 extern "C" int mrcnn_host_merge_components(int n_frames, const int32_t* det_count, const int32_t* pairs,
                                            const uint8_t* mergeable, int64_t n_pairs, int32_t* members, int32_t* offsets,
                                            int32_t* frame_components, int32_t* n_components) {

@@ -115,6 +115,9 @@ SIGNATURES = {
     "mrcnn_pixel_lists_adjacent": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mrcnn_host_merge_components": (c_int, [c_int, c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p,
                                             c_void_p]),
+    "mrcnn_host_all_pairs": (c_int, [c_int, c_void_p, c_void_p]),
+    "mrcnn_host_pair_flags": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                      ctypes.c_double, c_void_p, c_void_p, c_void_p]),
     "mrcnn_host_contours": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mrcnn_host_contours_fetch": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mrcnn_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

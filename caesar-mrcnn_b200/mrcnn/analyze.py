@@ -440,6 +440,18 @@ class Analyzer(object):
         timings = getattr(self, "_timings", None)            # development aid (tools/catalog_bench.py)
         t0 = time.perf_counter()
         vmode = None if not self.compute_vertexes else ("lists" if self.pixels_as_lists else "arrays")
+        if _array_path_applies(frames, self.split_masks):
+            opts = self._options()
+            opts.pop("split_masks")
+            batch = _analyze_batch_arrays(self._side_stream_ops(), frames, H, W, self.class_names, origins, False,
+                                          timings=timings, vertexes=vmode, **opts)
+            t1 = time.perf_counter()
+            out = build_json_results_batch(batch, image_ids, name_tags if name_tags is not None else self.obj_name_tag,
+                                           self.class_names, H, W, origins, self.pixels_as_lists)
+            if timings is not None:
+                timings["analyze_frames total"] = timings.get("analyze_frames total", 0.0) + t1 - t0
+                timings["host: catalogue dicts"] = timings.get("host: catalogue dicts", 0.0) + time.perf_counter() - t1
+            return out
         results = analyze_frames(self._side_stream_ops(), frames, H, W, self.class_names, origins=origins, want_masks=False,
                                  timings=timings, vertexes=vmode, **self._options())
         t1 = time.perf_counter()
@@ -545,6 +557,46 @@ def build_json_results(image_id, obj_name_tag, class_names, ny, nx, xmin, ymin, 
     return results
 
 
+def build_json_results_batch(batch, image_ids, name_tags, class_names, ny, nx, origins, pixels_as_lists=False):
+    """build_json_results for every frame of a _BatchArrays in one pass (reference: analyze.py:1866-1942 per image): the
+    box / edge arithmetic and the scalar conversions run once over the batch. name_tags: one tag or one per frame."""
+    F = len(batch.frame_off) - 1
+    ids = image_ids if image_ids is not None else range(F)
+    out = [{"image_id": ids[f], "objs": []} for f in range(F)]
+    n = int(batch.frame_off[-1])
+    if not batch.published or n == 0:
+        return out
+    bb = batch.bbox.astype(np.int64)
+    edge = (((bb[:, [1, 3]] <= 0) | (bb[:, [1, 3]] >= nx - 1)).any(axis=1) | ((bb[:, [0, 2]] <= 0) | (bb[:, [0, 2]] >= ny - 1)).any(axis=1)).tolist()
+    per_frame = np.diff(batch.frame_off)
+    org = np.asarray([(o[0], o[1], o[0], o[1]) for o in origins], dtype=np.int64).reshape(F, 4)
+    bb = (bb + np.repeat(org, per_frame, axis=0)).tolist()
+    cids = batch.cls.tolist()
+    scores = list(batch.score)                      # numpy float32 scalars, as the reference's results carry
+    po = batch.px_off.tolist()
+    px = batch.px
+    vx = batch.vertexes
+    fo = batch.frame_off.tolist()
+    for f in range(F):
+        a, b = fo[f], fo[f + 1]
+        if a == b:
+            continue
+        tag = name_tags if isinstance(name_tags, str) else name_tags[f]
+        objs = out[f]["objs"]
+        for k in range(a, b):
+            y1, x1, y2, x2 = bb[k]
+            class_id = cids[k]
+            pix = px[po[k]:po[k + 1]]
+            objs.append({
+                "name": "S%d_%s" % (k - a + 1, tag),
+                "x1": x1, "x2": x2, "y1": y1, "y2": y2,
+                "class_id": class_id, "class_name": class_names[class_id], "score": scores[k],
+                "pixels": pix.tolist() if pixels_as_lists else pix,
+                "vertexes": vx[k] if vx is not None else [], "edge": edge[k],
+            })
+    return out
+
+
 _TRIU = {}
 
 
@@ -563,49 +615,6 @@ def _all_pairs(counts):
         base += n
     pairs = np.concatenate(chunks) if chunks else np.zeros((0, 2), dtype=np.int32)
     return pairs, slices
-
-
-# MRCNN_B200_NATIVE_GRAPH=1: the merge graph of a whole batch through the host-only C++ routine
-# mrcnn_host_merge_components instead of the per-frame Python walk (same component order; CPU-tested against the
-# reference goldens; off by default until its effect has been measured on the GPU box)
-_USE_NATIVE_GRAPH = os.environ.get("MRCNN_B200_NATIVE_GRAPH", "0") == "1"
-
-
-def _native_merge(det_count, pairs, mergeable, det_cls, det_score, det_int, any_int):
-    """Merge stage of extract_det_masks for all frames at once -> (groups as (members, offsets), merged_cls,
-    merged_score, merged_int, merged_count), or None when the score shortcut does not apply to this numpy."""
-    if not (_F32_AVG_IS_IDENTITY and all(type(x) is np.float32 for x in det_score)):
-        return None
-    lib = _native.lib()
-    n, F = len(det_cls), len(det_count)
-    counts = np.asarray(det_count, dtype=np.int32)
-    flags = np.ascontiguousarray(mergeable, dtype=np.uint8)
-    pairs = np.ascontiguousarray(pairs, dtype=np.int32)
-    members = np.empty(n, dtype=np.int32)
-    offsets = np.empty(n + 1, dtype=np.int32)
-    frame_comps = np.empty(F, dtype=np.int32)
-    ncomp = ctypes.c_int32(0)
-    _native.check(lib.mrcnn_host_merge_components(F, counts.ctypes.data, pairs.ctypes.data if len(pairs) else None,
-                                                  flags.ctypes.data if len(pairs) else None, len(pairs), members.ctypes.data,
-                                                  offsets.ctypes.data, frame_comps.ctypes.data, ctypes.byref(ncomp)),
-                  "host_merge_components")
-    G = ncomp.value
-    offsets = offsets[:G + 1]
-    last = members[offsets[1:] - 1]                     # class of the LAST member, as in the reference
-    merged_cls = [det_cls[k] for k in last.tolist()]
-    merged_score = [det_score[k] for k in members[offsets[:-1]].tolist()]      # (0 + s) * (1. / 1) is s for singletons
-    merged_int = [False] * G
-    sizes = np.diff(offsets)
-    if any_int:
-        int_arr = np.asarray(det_int, dtype=bool)
-        merged_int = np.logical_or.reduceat(int_arr[members], offsets[:-1]).tolist() if G else []
-    for g in np.nonzero(sizes > 1)[0].tolist():         # real merges: the reference's scalar arithmetic, literally
-        score_avg = 0
-        for k in members[offsets[g]:offsets[g + 1]].tolist():
-            score_avg += det_score[k]
-        score_avg *= 1. / int(sizes[g])
-        merged_score[g] = score_avg
-    return (members, offsets), merged_cls, merged_score, merged_int, frame_comps.tolist()
 
 
 def _probe_f32_average():
@@ -638,6 +647,244 @@ def _iou(inter, area_a, area_b):
     return out
 
 
+# MRCNN_B200_ANALYZE_GENERIC=1 forces the per-frame Python walk below for every call (the array path is the default
+# wherever it applies; both are replayed against the reference goldens by the CPU suite)
+_FORCE_GENERIC = os.environ.get("MRCNN_B200_ANALYZE_GENERIC", "0") == "1"
+
+
+class _BatchArrays:
+    """Result of the array path for a whole batch: the final objects of all frames as flat arrays, frame-major.
+    frame_off [F+1] object ranges; cls / score / bbox per object; px flat int32 [total,2] pixel lists (origin added) with
+    px_off [n+1]; vertexes per object (or None); masks / mask_is_int only with want_masks."""
+
+    def __init__(self, F):
+        self.frame_off = np.zeros(F + 1, dtype=np.int64)
+        self.cls = np.zeros(0, dtype=np.int32)
+        self.score = np.zeros(0, dtype=np.float32)
+        self.bbox = np.zeros((0, 4), dtype=np.int32)
+        self.px = np.zeros((0, 2), dtype=np.int32)
+        self.px_off = np.zeros(1, dtype=np.int64)
+        self.vertexes = None
+        self.masks = None
+        self.published = True          # False: select_best_overlapped_masks off -> nothing is published (analyze.py:1324)
+
+    def frame_results(self, class_names, want_captions=True):
+        """-> one _FrameResult per frame (lists, as the reference's attributes)"""
+        F = len(self.frame_off) - 1
+        out = [_FrameResult() for _ in range(F)]
+        if not self.published:
+            return out
+        fo = self.frame_off.tolist()
+        po = self.px_off.tolist()
+        for f in range(F):
+            a, b = fo[f], fo[f + 1]
+            if a == b:
+                continue
+            res = out[f]
+            res.class_ids_final = list(self.cls[a:b])
+            res.class_names_final = [class_names[c] for c in self.cls[a:b].tolist()]
+            res.scores_final = list(self.score[a:b])
+            res.bboxes = list(self.bbox[a:b])
+            if want_captions:
+                res.captions = ["{} {:.2f}".format(n, sc) for n, sc in zip(res.class_names_final, res.scores_final)]
+            res.pixels = [self.px[po[k]:po[k + 1]] for k in range(a, b)]
+            res.masks_final = [self.masks[k] for k in range(a, b)] if self.masks is not None else [None] * (b - a)
+            if self.vertexes is not None:
+                res.vertexes = self.vertexes[a:b]
+        return out
+
+
+def _array_path_applies(frames, split_masks):
+    if _FORCE_GENERIC or split_masks or not (_F32_AVG_IS_IDENTITY and _SCALAR_LT_IS_ARRAY_LT):
+        return False
+    return all(isinstance(fr.scores, np.ndarray) and fr.scores.dtype == np.float32 and isinstance(fr.class_ids, np.ndarray)
+               and fr.class_ids.dtype.kind in "iu" for fr in frames)
+
+
+def _host_pairs(counts):
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    c64 = counts.astype(np.int64)
+    P = int((c64 * (c64 - 1) // 2).sum())
+    pairs = np.empty((P, 2), dtype=np.int32)
+    _native.check(_native.lib().mrcnn_host_all_pairs(len(counts), counts.ctypes.data, pairs.ctypes.data if P else None),
+                  "host_all_pairs")
+    return counts, pairs
+
+
+def _pair_flags(stage, counts, key, score, area, inter, touch, use_iou, thr, n_total):
+    P = len(inter)
+    flags = np.empty(P, dtype=np.uint8)
+    loses = np.zeros(n_total, dtype=np.uint8)
+    tie = np.zeros(len(counts), dtype=np.uint8)
+    key = np.ascontiguousarray(key, dtype=np.int32)
+    area = np.ascontiguousarray(area, dtype=np.int32)
+    inter = np.ascontiguousarray(inter, dtype=np.int32)
+    touch = np.ascontiguousarray(touch, dtype=np.int32)
+    score = None if score is None else np.ascontiguousarray(score, dtype=np.float32)
+    _native.check(_native.lib().mrcnn_host_pair_flags(stage, len(counts), counts.ctypes.data, key.ctypes.data,
+                                                      None if score is None else score.ctypes.data, area.ctypes.data,
+                                                      inter.ctypes.data, touch.ctypes.data, 1 if use_iou else 0, float(thr),
+                                                      flags.ctypes.data, loses.ctypes.data, tie.ctypes.data), "host_pair_flags")
+    return flags, loses, tie
+
+
+def _clique_selection(n, edges, scores):
+    """analyze.py:1362-1395 for one frame: keep a mask iff it is the best-scoring member of every maximal clique it
+    belongs to; cliques from networkx in its own order (the order decides between equal scores)."""
+    import networkx as nx
+    is_selected = [True] * n
+    if not len(edges):
+        return is_selected
+    g_final = nx.Graph()
+    g_final.add_edges_from(edges)                       # same insertion order as the reference's pair loop
+    cliques = list(nx.find_cliques(g_final))
+    clique_max_scores, clique_max_score_index = [], []
+    for item in cliques:
+        max_score, max_score_index = -1, -1
+        for index in item:
+            score = scores[index]
+            if score > max_score:
+                max_score, max_score_index = score, index
+        clique_max_scores.append(max_score)
+        clique_max_score_index.append(max_score_index)
+    for q in sorted(range(len(cliques)), key=lambda k: clique_max_scores[k], reverse=True):
+        for index in cliques[q]:
+            if index != clique_max_score_index[q] and is_selected[index]:
+                is_selected[index] = False
+    return is_selected
+
+
+def _analyze_batch_arrays(ops, frames, H, W, class_names, origins, want_masks, score_thr, merge_overlapped_masks,
+                          select_best_overlapped_masks, split_source_sidelobe, merge_overlap_iou_thr, timings, vertexes):
+    """extract_det_masks + pixel lists for a batch with every per-mask quantity held in ONE array over the batch: the
+    per-frame work left in Python is one argsort (the reference's own call, so ties fall the same way); the pair tests,
+    the merge components and the pair enumeration are host C++ (csrc/host_graph.cu), everything else is numpy over the
+    batch. Same results as the per-frame walk of analyze_frames (replayed against the reference goldens by the CPU suite);
+    frames in which two linked masks tie take the reference's networkx route."""
+    import time
+
+    def mark(stage):
+        if timings is not None:
+            ops.torch.cuda.synchronize()
+            now = time.perf_counter()
+            timings[stage] = timings.get(stage, 0.0) + now - mark.t
+            mark.t = now
+    mark.t = time.perf_counter()
+
+    F = len(frames)
+    depth = frames[0].depth
+    out = _BatchArrays(F)
+    # -- score filter and descending-score order (analyze.py:1181-1203)
+    idx_chunks, cls_chunks, score_chunks, sel_count = [], [], [], []
+    for f, fr in enumerate(frames):
+        sc = fr.scores[:fr.n]
+        picked = np.nonzero(~(sc < score_thr))[0]
+        chosen = picked[np.argsort(sc[picked])[::-1]]
+        idx_chunks.append(chosen + f * depth)
+        cls_chunks.append(fr.class_ids[:fr.n][chosen])
+        score_chunks.append(sc[chosen])
+        sel_count.append(len(chosen))
+    flat_idx = np.concatenate(idx_chunks)
+    m = len(flat_idx)
+    plane_of = np.full(F * depth, -1, dtype=np.int32)
+    plane_of[flat_idx] = np.arange(m, dtype=np.int32)
+    cls_arr = np.concatenate(cls_chunks)
+    score_arr = np.concatenate(score_chunks)
+    counts = np.asarray(sel_count, dtype=np.int32)
+    mark("host: score filter + order")
+    planes = ops.pack(frames[0].masks_ptr, F, H, W, depth, plane_of, m)
+    mark("gpu: pack")
+
+    # -- merge connected same-class masks above the IOU threshold (analyze.py:1258-1320)
+    if merge_overlapped_masks and m:
+        counts, pairs = _host_pairs(counts)
+        mark("host: pair lists")
+        d_area, d_bbox = ops.area_bbox(planes, H, W)
+        d_inter, d_touch = ops.pair_stats(planes, H, W, pairs, d_bbox)
+        area, inter, touch = ops.host(d_area), ops.host(d_inter), ops.host(d_touch)
+        mark("gpu: merge pair stats (+pairs H2D, results D2H)")
+        mergeable, _, _ = _pair_flags(0, counts, cls_arr, None, area, inter, touch, True, merge_overlap_iou_thr, m)
+        members = np.empty(m, dtype=np.int32)
+        offsets = np.empty(m + 1, dtype=np.int32)
+        frame_comps = np.empty(F, dtype=np.int32)
+        ncomp = ctypes.c_int32(0)
+        _native.check(_native.lib().mrcnn_host_merge_components(
+            F, counts.ctypes.data, pairs.ctypes.data if len(pairs) else None, mergeable.ctypes.data if len(pairs) else None,
+            len(pairs), members.ctypes.data, offsets.ctypes.data, frame_comps.ctypes.data, ctypes.byref(ncomp)),
+            "host_merge_components")
+        G = ncomp.value
+        offsets = offsets[:G + 1]
+        if G < m:                                        # real merges exist
+            sizes = np.diff(offsets)
+            new_cls = cls_arr[members[offsets[1:] - 1]]      # class of the LAST member, as in the reference
+            new_score = score_arr[members[offsets[:-1]]]     # singletons: (0 + s) * (1. / 1) is s
+            for g in np.nonzero(sizes > 1)[0].tolist():      # the reference's scalar arithmetic, literally
+                score_avg = 0
+                for k in members[offsets[g]:offsets[g + 1]].tolist():
+                    score_avg += score_arr[k]
+                score_avg *= 1. / int(sizes[g])
+                new_score[g] = score_avg
+            cls_arr, score_arr, counts = new_cls, new_score, frame_comps
+            mark("host: merge graph")
+            planes = ops.union(planes, H, W, (members, offsets))
+            mark("gpu: union")
+        else:
+            mark("host: merge graph")
+    n_merged = len(cls_arr)
+    if not select_best_overlapped_masks or not n_merged:
+        out.published = bool(select_best_overlapped_masks)
+        return out
+
+    # -- best of overlapping objects through maximal cliques (analyze.py:1328-1395)
+    counts, pairs = _host_pairs(counts)
+    mark("host: pair lists")
+    d_area, d_bbox = ops.area_bbox(planes, H, W)
+    d_inter, d_touch = ops.pair_stats(planes, H, W, pairs, d_bbox)
+    area, bbox, inter, touch = ops.host(d_area), ops.host(d_bbox), ops.host(d_inter), ops.host(d_touch)
+    mark("gpu: select pair stats + bbox (+H2D/D2H)")
+    spurious = np.fromiter((name == 'spurious' for name in class_names), dtype=np.int32, count=len(class_names))[cls_arr]
+    linked, loses, tie_frame = _pair_flags(1, counts, spurious, score_arr, area, inter, touch, split_source_sidelobe,
+                                           merge_overlap_iou_thr, n_merged)
+    selected = loses == 0
+    if tie_frame.any():
+        starts = np.concatenate([[0], np.cumsum(counts)])
+        c64 = counts.astype(np.int64)
+        pstarts = np.concatenate([[0], np.cumsum(c64 * (c64 - 1) // 2)])
+        for f in np.nonzero(tie_frame)[0].tolist():
+            base, n_f = int(starts[f]), int(counts[f])
+            lo, hi = int(pstarts[f]), int(pstarts[f + 1])
+            edges = (pairs[lo:hi][linked[lo:hi] != 0] - base).tolist()
+            selected[base:base + n_f] = _clique_selection(n_f, edges, list(score_arr[base:base + n_f]))
+    bbox_ok = (bbox[:, 1] < bbox[:, 3]) & (bbox[:, 0] < bbox[:, 2])
+    for k in np.nonzero(selected & ~bbox_ok)[0].tolist():
+        bb = bbox[k]
+        logger.warning("Invalid det bbox(%d,%d,%d,%d), skip it ..." % (bb[1], bb[3], bb[0], bb[2]))
+    keep = np.nonzero(selected & bbox_ok)[0]
+    owner = np.repeat(np.arange(F), counts)[keep]
+    out.frame_off[1:] = np.cumsum(np.bincount(owner, minlength=F))
+    out.cls, out.score, out.bbox = cls_arr[keep], score_arr[keep], bbox[keep]
+    mark("host: cliques + selection")
+
+    # -- final masks and pixel lists (make_json_results: np.argwhere(mask == 1), analyze.py:1903-1909)
+    if len(keep):
+        fin = planes if len(keep) == n_merged else ops.gather(planes, keep)
+        if want_masks:
+            out.masks = ops.unpack(fin, H, W).view(np.bool_)
+        px, px_off = ops.pixels(fin, H, W, area[keep], 0, 0)          # one launch and one copy for the whole batch
+        origins = origins if origins is not None else [(0, 0)] * F
+        fo = out.frame_off.tolist()
+        po = px_off.tolist()
+        for f in range(F):
+            oy, ox = int(origins[f][0]), int(origins[f][1])
+            if (oy or ox) and fo[f] != fo[f + 1]:
+                px[po[fo[f]]:po[fo[f + 1]]] += np.array([oy, ox], dtype=np.int32)
+        out.px, out.px_off = px, px_off
+        if vertexes is not None:                                         # contours of every final object, one threaded C++ call
+            out.vertexes = contours_of_flat_pixels(px, px_off, as_lists=(vertexes == "lists"))
+    mark("gpu+host: pixel lists / final masks")
+    return out
+
+
 def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True, score_thr=0.7, split_masks=False,
                    merge_overlapped_masks=True, select_best_overlapped_masks=True, split_source_sidelobe=True,
                    merge_overlap_iou_thr=0.3, timings=None, vertexes=None):
@@ -646,6 +893,14 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
     len(frames) > 1 (the engine's result slot), or be a single frame."""
     import networkx as nx
     import time
+
+    if len(frames) and _array_path_applies(frames, split_masks):
+        depth, base_ptr = frames[0].depth, frames[0].masks_ptr
+        for f, fr in enumerate(frames):
+            assert fr.depth == depth and fr.masks_ptr == base_ptr + f * H * W * depth, "frames must be one [F,H,W,depth] block"
+        return _analyze_batch_arrays(ops, frames, H, W, class_names, origins, want_masks, score_thr, merge_overlapped_masks,
+                                     select_best_overlapped_masks, split_source_sidelobe, merge_overlap_iou_thr, timings,
+                                     vertexes).frame_results(class_names)
 
     def mark(stage):          # development aid: cumulative wall time per stage (device drained at every mark)
         if timings is not None:
@@ -736,10 +991,6 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
         mergeable = (touch != 0) & (cls_arr[pairs[:, 0]] == cls_arr[pairs[:, 1]]) & (iou >= merge_overlap_iou_thr)
         groups, merged_cls, merged_score, merged_int, merged_count = [], [], [], [], []
         any_int = any(det_int)
-        native = _native_merge(det_count, pairs, mergeable, det_cls, det_score, det_int, any_int) if _USE_NATIVE_GRAPH else None
-        if native is not None:
-            groups, merged_cls, merged_score, merged_int, merged_count = native
-            slices = ()
         for f, (lo, hi, base) in enumerate(slices):
             edges = np.nonzero(mergeable[lo:hi])[0]
             if len(edges):

@@ -355,6 +355,20 @@ int mrcnn_host_merge_components(int n_frames, const int32_t* det_count, const in
                                 int64_t n_pairs, int32_t* members, int32_t* offsets, int32_t* frame_components,
                                 int32_t* n_components);
 
+/* HOST-ONLY: all (i < j) pairs inside every frame, frame-major, in the reference's double-loop order
+ * (mrcnn/analyze.py:1263-1266 and :1335-1338); pairs [sum n_f(n_f-1)/2, 2] global indices. */
+int mrcnn_host_all_pairs(int n_frames, const int32_t* counts, int32_t* pairs);
+
+/* HOST-ONLY: the per-pair decisions of extract_det_masks for a batch, pairs implicit in mrcnn_host_all_pairs order, from
+ * the device's pair statistics (inter, touch) and plane areas.  stage 0 = merge graph edges (mrcnn/analyze.py:1268-1290:
+ * connected, same class, IOU >= iou_thr; cls_or_spurious = class ids).  stage 1 = selection graph edges (:1340-1360:
+ * connected, and with use_iou (split_source_sidelobe) not a spurious/non-spurious pair below iou_thr; cls_or_spurious =
+ * 1 for 'spurious'), plus loses[v] = 1 when a linked mask scores strictly higher (caller zero-fills) and tie_frame[f] = 1
+ * when two linked masks of frame f score equal.  IOU as sklearn's jaccard_score: float64, 0 for an empty union. */
+int mrcnn_host_pair_flags(int stage, int n_frames, const int32_t* counts, const int32_t* cls_or_spurious, const float* score,
+                          const int32_t* area, const int32_t* inter, const int32_t* touch, int use_iou, double iou_thr,
+                          uint8_t* flags, uint8_t* loses, uint8_t* tie_frame);
+
 /* HOST-ONLY: the `vertexes` of catalogue objects (mrcnn/analyze.py:1908-1927, mrcnn/sfinder.py:885-910):
  * skimage.measure.find_contours(zero-padded mask, 0.5) [scikit-image 0.15 algorithm, third-party, restated; parity
  * unpinned] computed from each object's pixel list.  pixels_yx [total,2] int32 (y, x) in image coordinates,

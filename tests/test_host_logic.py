@@ -1,5 +1,6 @@
 """CPU: host-side mirror of the reference interface (mrcnn package) + C-ABI library surface.
 No compute call needs a GPU here."""
+import json
 import os
 import re
 
@@ -423,17 +424,69 @@ def test_native_merge_components_reproduces_the_reference_graph_order():
         assert got == want and frame_comps.tolist() == want_frames and ncomp.value == len(want)
 
 
-def test_native_graph_mode_gives_the_same_catalogues(monkeypatch):
-    """MRCNN_B200_NATIVE_GRAPH=1 (merge graph in C++) == the default Python walk: reference goldens and the random
-    multi-frame comparison against the oracle are replayed with the switch on."""
+def test_generic_walk_and_array_path_give_the_same_catalogues(monkeypatch):
+    """The per-frame Python walk (MRCNN_B200_ANALYZE_GENERIC=1, also the split_masks route) == the default array path
+    (pair tests, merge components and pair lists in host C++): the reference goldens and the random multi-frame
+    comparison against the oracle are replayed with the array path switched off, and a batch with score ties, merges,
+    empty frames and per-frame origins goes through both."""
+    import analyzer_cases as C
     from mrcnn import analyze as P
-    monkeypatch.setattr(P, "_USE_NATIVE_GRAPH", True)
     calls = []
-    real = P._native_merge
-    monkeypatch.setattr(P, "_native_merge", lambda *a: (calls.append(1), real(*a))[1])
+    real = P._analyze_batch_arrays
+    monkeypatch.setattr(P, "_analyze_batch_arrays", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    test_analyzer_host_logic_reproduces_reference_goldens_with_numpy_backend()
+    assert len(calls) >= 30                              # the default route IS the array path
+    monkeypatch.setattr(P, "_FORCE_GENERIC", True)
+    n = len(calls)
     test_analyzer_host_logic_reproduces_reference_goldens_with_numpy_backend()
     test_analyzer_host_pipeline_matches_oracle_with_numpy_backend()
-    assert len(calls) > 30
+    assert len(calls) == n
+
+    names = ["bkg", "spurious", "compact", "extended", "extended-multisland", "flagged"]
+    rng = np.random.default_rng(5)
+    F, S, D = 6, 40, 30
+    masks = np.zeros((F, S, S, D), bool)
+    cls, sc = np.zeros((F, D), np.int32), np.zeros((F, D), np.float32)
+    for f in range(F):
+        masks[f], cls[f], sc[f] = C.random_detections(rng, S, S, D, density=0.7)
+    masks[3] = False
+    sc[1, ::2] = sc[1, 0]                                # ties between linked masks -> clique route
+    sc[4, :] = 0.1                                       # a frame with nothing above the threshold
+    cls[5, :] = 2                                        # one class: long merge chains
+    ops = C.NumpyPlaneOps(masks)
+    frames = [P._Frame(4096 + f * S * S * D, D, D - (f == 2) * 7, cls[f], sc[f]) for f in range(F)]
+    origins = [(0, 0), (5, 9), (0, 0), (100, 200), (3, 3), (7, 0)]
+    for opts in (dict(), dict(split_source_sidelobe=False, merge_overlap_iou_thr=0.05, score_thr=0.6),
+                 dict(merge_overlapped_masks=False), dict(select_best_overlapped_masks=False), dict(score_thr=2.0)):
+        res = {}
+        for generic in (False, True):
+            monkeypatch.setattr(P, "_FORCE_GENERIC", generic)
+            res[generic] = P.analyze_frames(ops, frames, S, S, names, origins=origins, want_masks=True, vertexes="lists", **opts)
+        for f in range(F):
+            a, g = res[False][f], res[True][f]
+            assert len(a.class_ids_final) == len(g.class_ids_final)
+            assert [int(c) for c in a.class_ids_final] == [int(c) for c in g.class_ids_final]
+            assert [(type(x), float(x)) for x in a.scores_final] == [(type(x), float(x)) for x in g.scores_final]
+            assert a.class_names_final == g.class_names_final and a.captions == g.captions
+            assert [b.tolist() for b in a.bboxes] == [b.tolist() for b in g.bboxes]
+            assert [p_.tolist() for p_ in a.pixels] == [p_.tolist() for p_ in g.pixels]
+            assert all(np.array_equal(x != 0, y != 0) for x, y in zip(a.masks_final, g.masks_final))
+            cat_a = P.build_json_results(f, "t", names, S, S, origins[f][1], origins[f][0], a.masks_final, a.class_ids_final,
+                                         a.scores_final, a.bboxes, a.pixels, vertexes=a.vertexes)
+            cat_g = P.build_json_results(f, "t", names, S, S, origins[f][1], origins[f][0], g.masks_final, g.class_ids_final,
+                                         g.scores_final, g.bboxes, g.pixels, vertexes=g.vertexes)
+            assert json.dumps(cat_a, cls=P.NumpyEncoder, sort_keys=True) == json.dumps(cat_g, cls=P.NumpyEncoder, sort_keys=True)
+    # the batched catalogue builder == build_json_results frame by frame
+    monkeypatch.setattr(P, "_FORCE_GENERIC", False)
+    batch = real(ops, frames, S, S, names, origins, False, 0.7, True, True, True, 0.3, None, "lists")
+    cats = P.build_json_results_batch(batch, ["im%d" % f for f in range(F)], ["t%d" % f for f in range(F)], names, S, S, origins, True)
+    per_frame = batch.frame_results(names)
+    for f in range(F):
+        r = per_frame[f]
+        want = P.build_json_results("im%d" % f, "t%d" % f, names, S, S, origins[f][1], origins[f][0], r.masks_final,
+                                    r.class_ids_final, r.scores_final, r.bboxes, r.pixels, vertexes=r.vertexes)
+        assert json.dumps(cats[f], cls=P.NumpyEncoder, sort_keys=True) == json.dumps(want, cls=P.NumpyEncoder, sort_keys=True)
+    assert sum(len(c["objs"]) for c in cats) > 20
 
 
 def test_drop_in_exports_of_survey_8b_exist():
