@@ -434,6 +434,35 @@ def main():
             "stage_ms_per_step": {k: v / nprof for k, v in st_acc.items()},
             "detections_in_last_batch": int(sum(len(r["class_ids"]) for r in e2e_results[0]))}
 
+    # ---- the same step when few of the 100 detection slots are used (N = 1 only; NOT the headline configuration) -------
+    # Random weights fill every slot (DETECTION_MIN_CONFIDENCE = 0), the worst case the headline is quoted on.  A trained
+    # model on a radio map fills a handful; the mask branch (45 % of the step) then runs on those only (the engine skips
+    # the M tiles of zero-padded detections).  Second engine, same weights and maps, confidence cut at the 90th percentile.
+    if world == 1 and os.environ.get("BENCH_SPARSE", "1") != "0":
+        scores = np.concatenate([np.asarray(r["scores"]) for r in e2e_results[0]] + [np.zeros(0, np.float32)])
+        if len(scores) >= 10:
+            cut = float(np.quantile(scores, 0.9))
+
+            class SparseConfig(BenchConfig):
+                DETECTION_MIN_CONFIDENCE = cut
+
+            sparse = modellib.MaskRCNN(mode="inference", config=SparseConfig(), model_dir="/tmp/mrcnn_bench", device=local_rank)
+            sparse.set_weights(weights)
+            sp_step = lambda i: sparse.detect_maps(dev_sets[i % n_sets], device_only=True)  # noqa: E731
+            for i in range(args.warmup):
+                sp_step(i)
+            stream_main = stream
+            stream = sparse._stream
+            ms_sparse = timed(sp_step, args.steps)
+            stream = stream_main
+            n_det = sum(len(r["class_ids"]) for r in sparse.detect_maps(host_sets[0]))
+            line["sparse_detections"] = {"min_confidence": cut, "detections_per_image": n_det / B, "ms_per_step": ms_sparse / args.steps,
+                                         "value": B * args.steps / (ms_sparse / 1e3), "unit": UNIT,
+                                         "note": "same maps and weights with DETECTION_MIN_CONFIDENCE at the 90th percentile of the "
+                                                 "headline run's scores: tiles of zero-padded detections are skipped in the mask branch "
+                                                 "(MRCNN_B200_SKIP_PADDED=0 computes them as the reference does); not the headline"}
+            del sparse
+
     # ---- CPU baseline: bounded sample of the same workload on the host cores (rank 0, N = 1) --------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)          # the CPU baseline gets every host core again

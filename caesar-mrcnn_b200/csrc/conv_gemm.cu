@@ -34,20 +34,28 @@ constexpr int EPI_THREADS = 256;
 // EPI_TMA: the epilogue goes through shared memory: the residual tile is fetched with TMA loads and the
 // bf16 output leaves with TMA stores ([128 rows x 32 channels] boxes, 64B swizzle), so global traffic is
 // full-line and asynchronous instead of one 16-byte piece per thread per row (32 sectors per request).
-template <int BLOCK_N, bool EPI_TMA> struct TileCfg {
-  static constexpr int STAGES = EPI_TMA ? ((BLOCK_N <= 32) ? 8 : (BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 5 : 3)))
-                                        : ((BLOCK_N <= 64) ? 8 : (BLOCK_N == 128 ? 6 : 4));
+// OCC2: two CTAs per SM (shared memory <= 113 KB, registers <= 102 per thread, 2 x 2 x BLOCK_N <= 512 TMEM columns): the
+// ring is shorter and the epilogue rotates through two staging buffers instead of three, but the fill / drain phases of one
+// CTA (first loads, accumulator read-out, the kernel's tail) run under the other CTA's MMAs, and the CTAs of the NEXT layer
+// can become resident (programmatic dependent launch) while this layer's last tiles drain.  Layers with 1-16 k-blocks per
+// tile are bound by exactly those phases.
+template <int BLOCK_N, bool EPI_TMA, bool OCC2 = false> struct TileCfg {
+  static constexpr int STAGES = OCC2 ? (EPI_TMA ? (BLOCK_N <= 32 ? 3 : 2) : (BLOCK_N <= 64 ? 4 : 3))
+                                : EPI_TMA ? ((BLOCK_N <= 32) ? 8 : (BLOCK_N == 64 ? 7 : (BLOCK_N == 128 ? 5 : 3)))
+                                          : ((BLOCK_N <= 64) ? 8 : (BLOCK_N == 128 ? 6 : 4));
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_CHUNK_BYTES = 32 * 32 * 2;                        // one warp's chunk: 32 rows x 32 bf16
-  static constexpr int STAGING_BYTES = EPI_TMA ? 8 * 3 * EPI_CHUNK_BYTES : 0; // 8 epilogue warps x 3 rotating buffers
+  static constexpr int EPI_NBUF = OCC2 ? 2 : 3;                              // rotating staging buffers per epilogue warp
+  static constexpr int STAGING_BYTES = EPI_TMA ? 8 * EPI_NBUF * EPI_CHUNK_BYTES : 0;
   // [acc][scale|shift][BLOCK_N] floats + (fused mask logits) W2 [256][4] floats + partials [128][8] floats
   static constexpr int EPI_BYTES = 2 * 2 * BLOCK_N * 4 + ((BLOCK_N == 256 && !EPI_TMA) ? (256 * 4 * 4 + 128 * 8 * 4) : 0);
   static constexpr int BAR_BYTES = 512;                                      // mbarriers + TMEM slot
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + BAR_BYTES + EPI_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;   // double-buffered accumulator (64..512, power of two)
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(!OCC2 || (SMEM_BYTES <= 115712 && BLOCK_N <= 128), "two CTAs per SM: 113 KB and 256 TMEM columns each");
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -227,13 +235,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // [Cout_f, KH, KW, Cin_f] — this GEMM's K runs over (flipped tap, Cout_f) and its N over Cin_f, which is the weights'
 // contiguous dimension — so no transposed copy of the weights is ever made: a k-block is BLOCK_N/64 TMA boxes of
 // 64 Cout_f rows x 64 Cin_f columns (the canonical MN-major SW128 layout, see wgrad_kernel).
-template <int BLOCK_N, bool EPI_TMA, bool B_MN = false>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+template <int BLOCK_N, bool EPI_TMA, bool B_MN = false, bool OCC2 = false>
+__global__ void __launch_bounds__(GEMM_THREADS, OCC2 ? 2 : 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                      const __grid_constant__ CUtensorMap tmap_b,
                                                                      const __grid_constant__ CUtensorMap tmap_out,
                                                                      const __grid_constant__ CUtensorMap tmap_res,
                                                                      const ConvGemmParams p) {
-  using Cfg = TileCfg<BLOCK_N, EPI_TMA>;
+  using Cfg = TileCfg<BLOCK_N, EPI_TMA, OCC2>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment required by the 128B swizzle
@@ -303,6 +311,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
+        if (p.tile_skip != nullptr && p.tile_skip[m_tile]) continue;
         int w0, h0, n0;
         if (p.im2col) {                       // base output pixel of this M tile, in padded-box coordinates
           const long long m0 = (long long)m_tile * BLOCK_M;
@@ -362,9 +371,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (B_MN ? (1u << 16) : 0u) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                                  ((uint32_t)(BLOCK_M >> 4) << 24);
       uint32_t stage = 0, phase = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        if (p.tile_skip != nullptr && p.tile_skip[tile / p.n_tiles]) continue;     // (tcount counts computed tiles only)
         const uint32_t acc = tcount & 1u;
         const uint32_t aph = (tcount >> 1) & 1u;
+        ++tcount;
         mbar_wait(tmem_empty_bar(acc), aph ^ 1u);      // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -423,7 +434,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       constexpr int NCH = COLS_PER_WARP / 32;                 // chunks per tile for this warp
       const bool elected = lane == 0;
       const bool has_res = p.residual != nullptr;
-      const uint32_t warp_base = staging_base + (uint32_t)ew * 3u * Cfg::EPI_CHUNK_BYTES;
+      constexpr uint32_t NBUF = Cfg::EPI_NBUF;
+      const uint32_t warp_base = staging_base + (uint32_t)ew * NBUF * Cfg::EPI_CHUNK_BYTES;
       const uint32_t row_off = (uint32_t)lane * 64u;
       const uint32_t sw = (uint32_t)((lane >> 1) & 3);
       const int row0 = q * 32;                                // first tile row of this warp
@@ -433,11 +445,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         mbar_expect_tx(res_bar(ew, 0), Cfg::EPI_CHUNK_BYTES);
         tma_load_2d(warp_base, &tmap_res, res_bar(ew, 0), (t0 % p.n_tiles) * BLOCK_N + c_begin, (t0 / p.n_tiles) * BLOCK_M + row0);
       }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t acc = tcount & 1u;
-        const uint32_t aph = (tcount >> 1) & 1u;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
+        if (p.tile_skip != nullptr && p.tile_skip[m_tile]) continue;     // (never combined with a residual: host check)
+        const uint32_t acc = tcount & 1u;
+        const uint32_t aph = (tcount >> 1) & 1u;
+        ++tcount;
         const int col_base = n_tile * BLOCK_N;
         float* t_scale = s_affine + acc * (2 * BLOCK_N);
         float* t_shift = t_scale + BLOCK_N;
@@ -456,24 +470,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
           tmem_ld_32x32b_x32(t_addr, vbuf[0]);
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci, ++g) {
-            const uint32_t b = g % 3u;
+            const uint32_t b = g % NBUF;
             const uint32_t buf = warp_base + b * Cfg::EPI_CHUNK_BYTES;
             if (has_res) {
               if (elected) {
-                // chunk g+1 (maybe of this CTA's next tile) -> buffer (g+1)%3, last read by the store of chunk g-2
+                // chunk g+1 (maybe of this CTA's next tile) -> buffer (g+1)%NBUF, last read by the store of chunk g+1-NBUF
                 int nt = tile, nci = ci + 1;
                 if (nci == NCH) { nt = tile + gridDim.x; nci = 0; }
                 if (nt < num_tiles) {
-                  bulk_wait_group_read<1>();
-                  const uint32_t nb = (g + 1u) % 3u;
+                  bulk_wait_group_read<NBUF - 2>();
+                  const uint32_t nb = (g + 1u) % NBUF;
                   mbar_expect_tx(res_bar(ew, nb), Cfg::EPI_CHUNK_BYTES);
                   tma_load_2d(warp_base + nb * Cfg::EPI_CHUNK_BYTES, &tmap_res, res_bar(ew, nb),
                               (nt % p.n_tiles) * BLOCK_N + c_begin + 32 * nci, (nt / p.n_tiles) * BLOCK_M + row0);
                 }
               }
-              mbar_wait(res_bar(ew, b), (g / 3u) & 1u);
+              mbar_wait(res_bar(ew, b), (g / NBUF) & 1u);
             } else {
-              if (elected) bulk_wait_group_read<2>();          // the store of chunk g-3 has released this buffer
+              if (elected) bulk_wait_group_read<NBUF - 1>();   // the store of chunk g-NBUF has released this buffer
               __syncwarp();
             }
             tmem_ld_wait();                                     // chunk ci has landed
@@ -529,11 +543,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
       if (elected) bulk_wait_group_all();     // smem must outlive the last store; results visible at kernel end
     } else {
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t acc = tcount & 1u;
-      const uint32_t aph = (tcount >> 1) & 1u;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
+      if (p.tile_skip != nullptr && p.tile_skip[m_tile]) continue;
+      const uint32_t acc = tcount & 1u;
+      const uint32_t aph = (tcount >> 1) & 1u;
+      ++tcount;
       const int col_base = n_tile * BLOCK_N;
       int ch_base = col_base;          // channel index used for scale/shift and the store column
       int tap = 0;
@@ -1096,20 +1112,21 @@ template <int BN> int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx
   return MRCNN_OK;
 }
 
-template <int BN, bool EPI, bool BMN = false> int launch_tile(const ConvPlan* plan, cudaStream_t st) {
-  using Cfg = TileCfg<BN, EPI>;
+template <int BN, bool EPI, bool BMN = false, bool OCC2 = false> int launch_tile(const ConvPlan* plan, cudaStream_t st) {
+  using Cfg = TileCfg<BN, EPI, OCC2>;
   static bool attr_done[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_done[dev]) {
-    MRCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MRCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, BMN, OCC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done[dev] = true;
   }
   static int num_sms = 0;
   if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned tiles = plan->grid.x;
-  const unsigned grid = tiles < (unsigned)num_sms ? tiles : (unsigned)num_sms;   // one persistent CTA per SM
-  MRCNN_CHECK_CUDA(mrcnn_launch(conv_gemm_kernel<BN, EPI, BMN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, plan->tmap_a,
+  const unsigned slots = (unsigned)num_sms * (OCC2 ? 2u : 1u);                   // persistent CTAs: one (OCC2: two) per SM
+  const unsigned grid = tiles < slots ? tiles : slots;
+  MRCNN_CHECK_CUDA(mrcnn_launch(conv_gemm_kernel<BN, EPI, BMN, OCC2>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, plan->tmap_a,
                                 plan->tmap_b, plan->tmap_out, plan->tmap_res, plan->p));
   mrcnn_count_launch(1);
   return MRCNN_OK;
@@ -1169,6 +1186,13 @@ int conv_plan_create_ex(const mrcnn_conv_desc* d, const void* x, const void* w, 
   if (plan->b_mn) {       // tile width must divide the N extent (a box past it would read the next filter tap, not zeros)
     while (block_n > 64 && d->cout % block_n != 0) block_n >>= 1;
     if (block_n < 64) block_n = 64;
+  }
+  plan->occ2 = 0;
+  if (const char* o2 = getenv("MRCNN_B200_OCC2")) {     // "2": force the two-CTAs-per-SM variant (tests); the engine autotunes it
+    if (o2[0] == '2' && !plan->b_mn && d->out_mode == 0) {
+      plan->occ2 = 1;
+      if (block_n > 128) block_n = 128;
+    }
   }
   MRCNN_REQUIRE(block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256, "conv2d: block_n must be 32/64/128/256");
   if (d->out_mode == 1) MRCNN_REQUIRE(d->cout % block_n == 0, "conv2d: deconv cout %% block_n != 0");
@@ -1292,6 +1316,7 @@ int conv_plan_create_ex(const mrcnn_conv_desc* d, const void* x, const void* w, 
   p.b2 = nullptr;
   p.nc2 = 0;
   p.unit_scale = 0;
+  p.tile_skip = nullptr;
   if (residual) MRCNN_REQUIRE(d->cout % 8 == 0, "conv2d: residual needs cout %% 8 == 0");
   p.n_tiles = ceil_div(cout_total, block_n);
   const long long ctas = (long long)p.n_tiles * p.tiles_w * p.tiles_h * p.tiles_nb;
@@ -1318,6 +1343,14 @@ int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, 
   return MRCNN_OK;
 }
 
+int conv_plan_set_tile_skip(ConvPlan* plan, const unsigned char* flags) {
+  MRCNN_REQUIRE(plan, "set_tile_skip: null plan");
+  MRCNN_REQUIRE(plan->p.flat && plan->p.tw == 128 && plan->p.th == 1 && plan->p.nb == 1 && plan->p.residual == nullptr && !plan->b_mn,
+                "set_tile_skip: needs a flat / im2col layer (M tiles = 128 consecutive rows) without residual");
+  plan->p.tile_skip = flags;
+  return MRCNN_OK;
+}
+
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t st) {
   if (plan->b_mn) {
     if (plan->epi_tma) {
@@ -1335,6 +1368,21 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t st) {
     }
     mrcnn_set_error("conv2d (dgrad): bad block_n %d", plan->block_n);
     return MRCNN_ERR_INVALID;
+  }
+  if (plan->occ2 && plan->block_n <= 128 && plan->p.out_mode != 2) {     // two CTAs per SM (autotuned per layer)
+    if (plan->epi_tma) {
+      switch (plan->block_n) {
+        case 32: return launch_tile<32, true, false, true>(plan, st);
+        case 64: return launch_tile<64, true, false, true>(plan, st);
+        case 128: return launch_tile<128, true, false, true>(plan, st);
+      }
+    } else {
+      switch (plan->block_n) {
+        case 32: return launch_tile<32, false, false, true>(plan, st);
+        case 64: return launch_tile<64, false, false, true>(plan, st);
+        case 128: return launch_tile<128, false, false, true>(plan, st);
+      }
+    }
   }
   if (plan->epi_tma) {
     switch (plan->block_n) {

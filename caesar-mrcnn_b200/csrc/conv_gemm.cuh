@@ -27,6 +27,10 @@ struct ConvGemmParams {
   const float* b2;           // [nc2]
   int nc2;
   int unit_scale;            // out_mode 2: every per-channel scale is exactly 1 (no BN on the transposed conv)
+  // optional (flat / im2col layers without residual): tile_skip[m_tile] != 0 -> this M tile is not computed and its output
+  // rows are left untouched (mask head: tiles that hold only zero-padded detections).  Device memory written by an earlier
+  // kernel of the stream; every role of the kernel reads the same flags, so ring / accumulator phases stay in step.
+  const unsigned char* tile_skip;
 };
 
 struct ConvPlan {
@@ -35,6 +39,8 @@ struct ConvPlan {
   CUtensorMap tmap_out;        // epi_tma: [M, cout] bf16 output, box 32 ch x 128 rows, 64B swizzle
   CUtensorMap tmap_res;        // epi_tma: same geometry over the residual tensor
   int epi_tma = 0;             // epilogue through shared memory with TMA residual loads / output stores
+  int occ2 = 0;                // launch attribute (may be set after conv_plan_create): two persistent CTAs per SM with a shorter
+                               // ring (block_n <= 128, forward / K-major B only); same results
   int b_mn = 0;                // set BEFORE conv_plan_create: data-gradient mode, B read MN-major from the forward weights
   ConvGemmParams p;
   int block_n;
@@ -54,5 +60,8 @@ bool conv_plan_epi_tma_eligible(const mrcnn_conv_desc* d);
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);
 // turns a 256-channel deconv plan (block_n 256) into deconv + ReLU + 1x1 conv (nc2) + sigmoid -> float32 out
 int conv_plan_fuse_mask_logits(ConvPlan* plan, const void* w2, const float* b2, int nc2, void* out, int unit_scale);
+
+// flags [m_tiles] (see ConvGemmParams::tile_skip); returns an error for plans whose M tiles are not 128 consecutive rows
+int conv_plan_set_tile_skip(ConvPlan* plan, const unsigned char* flags);
 
 void mrcnn_count_launch(unsigned long long n);

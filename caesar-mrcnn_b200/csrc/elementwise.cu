@@ -165,6 +165,32 @@ __global__ void mask_post_kernel(const float* __restrict__ logits, int ld, size_
   }
 }
 
+// Mask-head work list (engine-internal).  The reference runs the mask branch on all DETECTION_MAX_INSTANCES rows of
+// `detections`, zero padding included (mrcnn/model.py:2118-2132), and unmold_detections then drops every row from the first
+// class id 0 on (:2575-2577).  flags[t] = 1 when M tile t (tile_rows consecutive rows of the [B*D * rows_per_roi] GEMMs of
+// the mask head) holds rows of padded detections only: those tiles are never computed.
+__global__ void mask_tile_flags_kernel(const float* __restrict__ det, int n_rois, int rows_per_roi, int tile_rows, int n_tiles,
+                                       unsigned char* __restrict__ flags) {
+  pdl_prologue();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const long long r0 = (long long)t * tile_rows;
+  int lo = (int)(r0 / rows_per_roi), hi = (int)((r0 + tile_rows - 1) / rows_per_roi);
+  if (hi > n_rois - 1) hi = n_rois - 1;
+  bool any = false;
+  for (int r = lo; r <= hi; ++r) any = any || (det[(size_t)r * 6 + 4] != 0.f);
+  flags[t] = any ? 0 : 1;
+}
+
+// rows of mrcnn_mask that belong to padded detections: written as zeros (their tiles may have been skipped)
+__global__ void mask_zero_padded_kernel(const float* __restrict__ det, size_t floats_per_roi, float* __restrict__ out) {
+  pdl_prologue();
+  const int roi = blockIdx.x;
+  if (det[(size_t)roi * 6 + 4] != 0.f) return;
+  float4* dst = reinterpret_cast<float4*>(out + (size_t)roi * floats_per_roi);
+  for (size_t i = threadIdx.x; i < floats_per_roi / 4; i += blockDim.x) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 int grid_for(size_t total, int threads) {
   size_t b = (total + threads - 1) / threads;
   const size_t cap = 148 * 16;
@@ -221,6 +247,23 @@ int launch_class_post(const float* head, int ld, int M, int NC, float* probs, fl
 }
 int launch_mask_post(const float* logits, int ld, size_t M, int NC, float* out, cudaStream_t st) {
   MRCNN_CHECK_CUDA(mrcnn_launch(mask_post_kernel, dim3(grid_for(M * NC, 256)), dim3(256), 0, st, logits, ld, M, NC, out));
+  MRCNN_CHECK_CUDA(cudaGetLastError());
+  mrcnn_count_launch(1);
+  return MRCNN_OK;
+}
+
+int launch_mask_tile_flags(const float* det, int n_rois, int rows_per_roi, int tile_rows, int n_tiles, unsigned char* flags,
+                           cudaStream_t st) {
+  MRCNN_REQUIRE(det && flags && n_rois > 0 && rows_per_roi > 0 && tile_rows > 0 && n_tiles > 0, "mask_tile_flags: bad arguments");
+  MRCNN_CHECK_CUDA(mrcnn_launch(mask_tile_flags_kernel, dim3((n_tiles + 255) / 256), dim3(256), 0, st, det, n_rois, rows_per_roi,
+                                tile_rows, n_tiles, flags));
+  MRCNN_CHECK_CUDA(cudaGetLastError());
+  mrcnn_count_launch(1);
+  return MRCNN_OK;
+}
+int launch_mask_zero_padded(const float* det, int n_rois, size_t floats_per_roi, float* out, cudaStream_t st) {
+  MRCNN_REQUIRE(det && out && n_rois > 0 && floats_per_roi % 4 == 0, "mask_zero_padded: bad arguments");
+  MRCNN_CHECK_CUDA(mrcnn_launch(mask_zero_padded_kernel, dim3(n_rois), dim3(256), 0, st, det, floats_per_roi, out));
   MRCNN_CHECK_CUDA(cudaGetLastError());
   mrcnn_count_launch(1);
   return MRCNN_OK;

@@ -22,7 +22,7 @@ void mrcnn_count_launch(unsigned long long n);
 
 int launch_pyramid_roi_align(const void* const* feature_maps, const int* feat_h, const int* feat_w, int channels,
                              int dtype, const float* boxes, int box_stride, int batch, int num_boxes, int pool_size,
-                             float image_area, void* pooled, int32_t* levels, cudaStream_t st);
+                             float image_area, void* pooled, int32_t* levels, cudaStream_t st, int valid_col = -1);
 
 namespace {
 
@@ -105,7 +105,7 @@ struct mrcnn_engine {
   bool graph_fresh = false;
   unsigned long long launches_per_predict = 0;
   bool autotune = true;
-  std::map<std::string, std::pair<int, int>> tune_cache;   // layer key -> (BLOCK_N, epi_tma)
+  std::map<std::string, std::pair<int, int>> tune_cache;   // layer key -> (BLOCK_N, epi_tma | occ2 << 1)
   bool tune_cache_dirty = false;
   std::string tune_cache_path;
   int profiling = 0;                      // 0 off, 1 events around every launch, 2 events at kernel-family boundaries
@@ -382,13 +382,18 @@ int autotune_block_n(mrcnn_engine* e, const mrcnn_conv_desc* d, const void* x, c
   MRCNN_CHECK_CUDA(cudaEventCreate(&e0));
   MRCNN_CHECK_CUDA(cudaEventCreate(&e1));
   float best = 1e30f;
-  int best_bn = plan->block_n, best_epi = plan->epi_tma;
+  int best_bn = plan->block_n, best_epi = plan->epi_tma, best_occ2 = plan->occ2;
   const int n_epi = conv_plan_epi_tma_eligible(d) ? 2 : 1;
-  for (int epi = 0; epi < n_epi; ++epi) {
+  static const bool allow_occ2 = !(getenv("MRCNN_B200_OCC2") && getenv("MRCNN_B200_OCC2")[0] == '0');
+  for (int variant = 0; variant < 2 * n_epi; ++variant) {
+    const int epi = variant % n_epi, occ2 = variant / n_epi;
+    if (occ2 && !allow_occ2) continue;
     for (int bn = 32; bn <= cap; bn <<= 1) {
       if (d->out_mode == 1 && d->cout % bn != 0) continue;
+      if (occ2 && bn > 128) continue;                   // two CTAs per SM: 2 x 2 x BLOCK_N TMEM columns
       ConvPlan trial;
       if (conv_plan_create_ex(d, x, g.w, g.scale, g.shift, residual, out, bn, epi, &trial) != MRCNN_OK) continue;
+      trial.occ2 = occ2;
       float tmin = 1e30f;
       for (int rep = 0; rep < 10; ++rep) {       // 2 warm-up launches, minimum of 8
         MRCNN_CHECK_CUDA(cudaEventRecord(e0, e->stream));
@@ -404,13 +409,17 @@ int autotune_block_n(mrcnn_engine* e, const mrcnn_conv_desc* d, const void* x, c
         best = tmin;
         best_bn = bn;
         best_epi = epi;
+        best_occ2 = occ2;
       }
     }
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  if (best_bn != plan->block_n || best_epi != plan->epi_tma)
-    return conv_plan_create_ex(d, x, g.w, g.scale, g.shift, residual, out, best_bn, best_epi, plan);
+  if (best_bn != plan->block_n || best_epi != plan->epi_tma) {
+    int rc = conv_plan_create_ex(d, x, g.w, g.scale, g.shift, residual, out, best_bn, best_epi, plan);
+    if (rc) return rc;
+  }
+  plan->occ2 = best_occ2;
   return MRCNN_OK;
 }
 
@@ -455,14 +464,16 @@ int add_conv(mrcnn_engine* e, const std::string& stage, const std::string& wname
     snprintf(key, sizeof(key), "%s:%d:%d:%d:%d:%d:%d:%d:%d", out_name.c_str(), d.n, d.h, d.w, d.cin, d.cout, k, stride, out_mode);
     auto hit = e->tune_cache.find(key);
     if (hit != e->tune_cache.end()) {
-      if (hit->second.first != plan->block_n || hit->second.second != plan->epi_tma) {
-        rc = conv_plan_create_ex(&d, in.p, g.w, g.scale, g.shift, residual, t.ptr, hit->second.first, hit->second.second, plan);
+      const int c_epi = hit->second.second & 1, c_occ2 = (hit->second.second >> 1) & 1;     // second field: epi_tma | occ2 << 1
+      if (hit->second.first != plan->block_n || c_epi != plan->epi_tma) {
+        rc = conv_plan_create_ex(&d, in.p, g.w, g.scale, g.shift, residual, t.ptr, hit->second.first, c_epi, plan);
         if (rc) return rc;
       }
+      plan->occ2 = c_occ2;
     } else {
       rc = autotune_block_n(e, &d, in.p, g, residual, t.ptr, plan);
       if (rc) return rc;
-      e->tune_cache[key] = std::make_pair(plan->block_n, plan->epi_tma);
+      e->tune_cache[key] = std::make_pair(plan->block_n, plan->epi_tma | (plan->occ2 << 1));
       e->tune_cache_dirty = true;
     }
   }
@@ -650,15 +661,31 @@ int build_graph(mrcnn_engine* e) {
   }
 
   // ---- mask head ---------------------------------------------------------------------------------
-  Tensor t_pm, t_lvl_mask;
-  RC(new_tensor(e, "pooled_mask", DT_BF16, (size_t)B * D * MP * MP * PY, &t_pm));
+  // The mask branch runs on the detections that exist: `detections` is zero-padded to DETECTION_MAX_INSTANCES rows per
+  // image, the reference computes masks for the padding too and unmold_detections throws them away (mrcnn/model.py:
+  // 2575-2577).  Here a flag per 128-row M tile (mask_tile_flags_kernel, from the class-id column) lets ROIAlign and the
+  // five mask-head GEMMs skip tiles that hold padding only; mrcnn_mask rows of padded detections read as zeros.
+  // Results of real detections are unchanged (rows of a GEMM are independent; a 3x3 tap never leaves its own ROI).
+  // MRCNN_B200_SKIP_PADDED=0 computes everything, as the reference does.
+  const bool skip_padded = !(getenv("MRCNN_B200_SKIP_PADDED") && getenv("MRCNN_B200_SKIP_PADDED")[0] == '0');
+  Tensor t_pm, t_lvl_mask, t_skip;
+  const int mask_rows = MP * MP, mask_tiles = (int)(((long long)B * D * mask_rows + 127) / 128);
+  RC(new_tensor(e, "pooled_mask", DT_BF16, (size_t)B * D * MP * MP * PY, &t_pm, true));
   RC(new_tensor(e, "roi_levels_mask", DT_I32, (size_t)B * D, &t_lvl_mask, true));
+  RC(new_tensor(e, "mask_tile_skip", DT_U8, (size_t)mask_tiles, &t_skip, true));
+  const unsigned char* skip_flags = skip_padded ? static_cast<const unsigned char*>(t_skip.ptr) : nullptr;
   {
     const float* det = static_cast<const float*>(t_det.ptr);
     void* pm = t_pm.ptr;
     int32_t* lvm = static_cast<int32_t*>(t_lvl_mask.ptr);
+    unsigned char* flags = static_cast<unsigned char*>(t_skip.ptr);
+    if (skip_padded)
+      e->steps.push_back({"roialign_mask", [=](cudaStream_t st) {
+        return launch_mask_tile_flags(det, B * D, mask_rows, 128, mask_tiles, flags, st);
+      }, "mask_tile_flags"});
     e->steps.push_back({"roialign_mask", [=](cudaStream_t st) {
-      return launch_pyramid_roi_align(fp.p, fp.h, fp.w, PY, MRCNN_DTYPE_BF16, det, 6, B, D, MP, image_area, pm, lvm, st);
+      return launch_pyramid_roi_align(fp.p, fp.h, fp.w, PY, MRCNN_DTYPE_BF16, det, 6, B, D, MP, image_area, pm, lvm, st,
+                                      skip_padded ? 4 : -1);
     }, "roialign"});
   }
   Act m = {static_cast<__nv_bfloat16*>(t_pm.ptr), B * D, MP, MP, PY};
@@ -666,6 +693,8 @@ int build_graph(mrcnn_engine* e) {
     Act o;
     RC(add_conv(e, "mask_head", "mrcnn_mask_conv" + std::to_string(i), m, 3, 1, 1, nullptr, 0,
                 "mrcnn_mask_conv" + std::to_string(i) + "_out", &o));
+    ConvPlan* cp = e->plans.back();
+    if (skip_flags && cp->p.flat && cp->p.tw == 128 && cp->p.th == 1 && cp->p.nb == 1) RC(conv_plan_set_tile_skip(cp, skip_flags));
     m = o;
   }
   MRCNN_REQUIRE(NC <= 8, "engine: NUM_CLASSES=%d too large for the mask logits pitch (max 8)", NC);
@@ -684,6 +713,7 @@ int build_graph(mrcnn_engine* e) {
     e->plans.push_back(plan);
     RC(conv_plan_create(&d, m.p, gd.w, gd.scale, gd.shift, nullptr, t_mask.ptr, 256, plan));
     RC(conv_plan_fuse_mask_logits(plan, gm.w, gm.shift, NC, t_mask.ptr, /*unit_scale=*/1));   // Conv2DTranspose has no BN
+    if (skip_flags) RC(conv_plan_set_tile_skip(plan, skip_flags));
     e->flops += plan->flops;
     e->steps.push_back({"mask_head", [plan](cudaStream_t st) { return conv_plan_launch(plan, st); }, "conv_gemm",
                         "mrcnn_mask (deconv+1x1+sigmoid)", plan->flops});
@@ -696,6 +726,13 @@ int build_graph(mrcnn_engine* e) {
     float* out = static_cast<float*>(t_mask.ptr);
     const size_t M = (size_t)B * D * 4 * MP * MP;
     e->steps.push_back({"mask_head", [=](cudaStream_t st) { return launch_mask_post(lg, 8, M, NC, out, st); }, "mask_post"});
+  }
+  if (skip_flags && ((size_t)4 * MP * MP * NC) % 4 == 0) {
+    const float* det = static_cast<const float*>(t_det.ptr);
+    float* out = static_cast<float*>(t_mask.ptr);
+    const size_t per_roi = (size_t)4 * MP * MP * NC;
+    e->steps.push_back({"mask_head", [=](cudaStream_t st) { return launch_mask_zero_padded(det, B * D, per_roi, out, st); },
+                        "mask_zero_padded"});
   }
 
   // ---- stage table for timing / run_stage ----------------------------------------------------------

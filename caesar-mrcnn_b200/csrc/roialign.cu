@@ -24,6 +24,8 @@ struct RoiParams {
   int32_t* levels;      // [B,N] or null
   int levels_ready;     // levels[] was filled by roi_levels_kernel (all ROIs in parallel) before this launch
   unsigned long long one2;  // (1.0f, 1.0f) as a packed fp32 pair, see f2_add
+  int valid_col;        // >= 0: box column holding the class id; a ROI whose class id is 0 (zero padding of the detections)
+                        // is skipped and its output rows are left untouched.  -1: every ROI is pooled
 };
 
 // mrcnn/model.py:465-477 — level = min(5, max(2, 4 + int32(round(log2(sqrt(h*w)/(224/sqrt(area)))))))
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(ROI_THREADS) roialign_kernel(RoiParams p) {
   const int roi = blockIdx.x;  // b*N + n
   const int b = roi / p.N;
   const float* bp = p.boxes + (size_t)roi * p.box_stride;
+  if (p.valid_col >= 0 && bp[p.valid_col] == 0.f) return;
   const float y1 = bp[0], x1 = bp[1], y2 = bp[2], x2 = bp[3];
   int li;
   if (p.levels_ready) {
@@ -308,6 +311,7 @@ __global__ void __launch_bounds__(ROI_THREADS) roialign_rows_kernel(RoiParams p)
   const int roi = blockIdx.x;         // b*N + n
   const int b = roi / p.N;
   const float* bp = p.boxes + (size_t)roi * p.box_stride;
+  if (p.valid_col >= 0 && bp[p.valid_col] == 0.f) return;
   const int li = p.levels[roi] - 2;
   const int H = p.H[li], W = p.W[li];
   constexpr int C = 256;
@@ -400,8 +404,9 @@ extern "C" int mrcnn_roi_levels(const float* boxes, int num_boxes, float image_a
 
 int launch_pyramid_roi_align(const void* const* feature_maps, const int* feat_h, const int* feat_w, int channels,
                              int dtype, const float* boxes, int box_stride, int batch, int num_boxes, int pool_size,
-                             float image_area, void* pooled, int32_t* levels, cudaStream_t st) {
+                             float image_area, void* pooled, int32_t* levels, cudaStream_t st, int valid_col) {
   MRCNN_REQUIRE(feature_maps && feat_h && feat_w && boxes && pooled, "pyramid_roi_align: null pointer");
+  MRCNN_REQUIRE(valid_col < box_stride, "pyramid_roi_align: valid_col outside the box rows");
   MRCNN_REQUIRE(batch > 0 && num_boxes > 0 && pool_size >= 1, "pyramid_roi_align: empty input");
   MRCNN_REQUIRE(pool_size <= ROI_MAX_P, "pyramid_roi_align: pool_size %d > %d", pool_size, ROI_MAX_P);
   MRCNN_REQUIRE(dtype == MRCNN_DTYPE_F32 || dtype == MRCNN_DTYPE_BF16, "pyramid_roi_align: dtype must be f32 or bf16");
@@ -423,6 +428,7 @@ int launch_pyramid_roi_align(const void* const* feature_maps, const int* feat_h,
   p.out = pooled;
   p.levels = levels;
   p.levels_ready = 0;
+  p.valid_col = valid_col;
   if (levels) {   // all levels in one parallel pass instead of one serial double-log per ROI CTA
     MRCNN_CHECK_CUDA(mrcnn_launch(roi_levels_kernel, dim3(ceil_div(batch * num_boxes, 256)), dim3(256), 0, st, boxes, box_stride, batch * num_boxes, image_area, levels));
     MRCNN_CHECK_CUDA(cudaGetLastError());
@@ -450,5 +456,5 @@ extern "C" int mrcnn_pyramid_roi_align(const void* const* feature_maps, const in
                                        int pool_size, float image_area, void* pooled, int32_t* levels,
                                        void* stream) {
   return launch_pyramid_roi_align(feature_maps, feat_h, feat_w, channels, dtype, boxes, 4, batch, num_boxes, pool_size,
-                                  image_area, pooled, levels, static_cast<cudaStream_t>(stream));
+                                  image_area, pooled, levels, static_cast<cudaStream_t>(stream), -1);
 }

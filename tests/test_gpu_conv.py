@@ -155,6 +155,23 @@ def test_conv_tma_epilogue_is_bit_identical(name, monkeypatch):
     assert (err <= (2.0 ** -7) * ref.abs() + 2e-2).all()
 
 
+@pytest.mark.parametrize("epi", ["0", "1"])
+@pytest.mark.parametrize("name", [n for n in CASES if n != "fc_12544"])
+def test_conv_two_ctas_per_sm_variant_is_bit_identical(name, epi, monkeypatch):
+    """OCC2 launch variant (two persistent CTAs per SM, shorter ring, two staging buffers per epilogue warp; the
+    engine's autotuner picks it per layer) against the one-CTA-per-SM kernel: same K order per element, so the outputs
+    must be equal bit for bit, with both epilogues."""
+    x, w2, scale, shift, res, desc, oshape, odt, ref = make_case(17, **CASES[name])
+    monkeypatch.setenv("MRCNN_B200_EPI_TMA", epi)
+    monkeypatch.setenv("MRCNN_B200_OCC2", "0")
+    a = run_conv(x, w2, scale, shift, res, desc, oshape, odt)
+    monkeypatch.setenv("MRCNN_B200_OCC2", "2")
+    b = run_conv(x, w2, scale, shift, res, desc, oshape, odt)
+    cout = desc["cout"]
+    assert torch.isfinite(b[..., :cout].float()).all(), "non-finite output (unwritten rows?)"
+    assert torch.equal(a, b)
+
+
 def test_conv_rejects_unsupported():
     nat = _native()
     lib = nat.lib()

@@ -393,6 +393,42 @@ def test_no_detections_above_min_confidence(weights, images):
         assert r["masks"].shape == im.shape[:2] + (0,) and r["masks"].dtype == np.float64
 
 
+def test_mask_branch_skips_padded_detections_without_changing_results(weights, images, run, monkeypatch):
+    """With few detections per image the engine skips the mask-head tiles that hold only zero-padded detection rows
+    (the reference computes and discards them, mrcnn/model.py:2575-2577): every detect() result and every mrcnn_mask row
+    of a real detection must equal, bit for bit, the engine built with MRCNN_B200_SKIP_PADDED=0 (everything computed);
+    rows of padded detections read as zeros."""
+    from mrcnn import model as modellib
+
+    scores = run["detections"][..., 5]
+    cut = float(np.sort(scores[scores > 0])[-7])              # a handful of detections in total
+    got = {}
+    for skip in ("1", "0"):
+        monkeypatch.setenv("MRCNN_B200_SKIP_PADDED", skip)
+        cfg = _config(B)
+        cfg.DETECTION_MIN_CONFIDENCE = cut
+        m = modellib.MaskRCNN(mode="inference", config=cfg, model_dir="/tmp/mrcnn_logs")
+        m.set_weights(weights)
+        res = m.detect(images)
+        got[skip] = (res, m.read_tensor("detections"), m.read_tensor("mrcnn_mask"))
+        if skip == "1":                                       # a second batch through the same engine: flags are per batch
+            res2 = m.detect(images[::-1])
+            got["1b"] = (res2[::-1], None, None)
+    (ra, da, ma), (rb, db, mb) = got["1"], got["0"]
+    assert np.array_equal(da.view(np.uint32), db.view(np.uint32))
+    n_valid = (da[..., 4] != 0).sum(axis=1)
+    assert 0 < n_valid.sum() <= 14 and n_valid.max() < 100
+    for b in range(B):
+        n = int(n_valid[b])
+        assert np.array_equal(ma[b, :n].view(np.uint32), mb[b, :n].view(np.uint32))
+        assert not ma[b, n:].any()
+    for x, y, z in zip(ra, rb, got["1b"][0]):
+        for k in ("rois", "class_ids", "scores", "masks"):
+            assert np.array_equal(x[k], y[k]) and x[k].dtype == y[k].dtype
+            assert np.array_equal(x[k], z[k])
+        assert x["masks"].shape[-1] == len(x["class_ids"])
+
+
 def test_base_config_1024_chain_of_custody(weights):
     """Largest configuration (base Config: IMAGE_MAX_DIM = 1024, 261 888 anchors): one full detect_maps, then every
     index-producing stage bit-exact against the oracle fed with the engine's own tensors of that stage, ROIAlign
