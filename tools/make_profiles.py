@@ -71,7 +71,7 @@ print("GEMM launches: %d, DRAM read %.2f GB write %.2f GB per step, time-weighte
 # ---- full-set summaries -----------------------------------------------------------------------
 md = ["# %s — ncu summaries (B200, B=64, S=256, synthetic maps, seeded random weights)\n" % tag,
       "Captured with `ncu --set full --clock-control none` under gpurun after a plain run of the same command "
-      "(`gpu_prof.sh`); tables made by `tools/make_profiles.py` from the .ncu-rep files (kept in gpurun_out/, not tracked). "
+      "(`tools/gpu_runs/prof_r1.sh`); tables made by `tools/make_profiles.py` from the .ncu-rep files (kept in gpurun_out/, not tracked). "
       "Per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes.\n"]
 sets = [("prof_gemm_heads", "Class + mask head GEMMs", "FC1 12544->1024 (M=64000),FC2 1024->1024,class/bbox head N=20,mask conv1 3x3 (im2col TMA),mask conv2,mask conv3,mask conv4,deconv 2x2 + ReLU + 1x1 logits + sigmoid (fused)"),
         ("prof_gemm_res4b", "res4b bottleneck (M = 16384 rows)", "2a 1x1 1024->256,2b 3x3 256->256,2c 1x1 256->1024 + residual (TMA epilogue)"),

@@ -75,7 +75,7 @@ def main():
     shares = {k: "%.1f%%" % (100 * v / tot) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}
     print("kernel shares of the step under ncu:", shares)
     with open(os.path.join(PROF, "r02_ncu_summary.md"), "w") as f:
-        f.write("# ncu summaries, round 2 (one B200, `gpu_prof_r2.sh`; captures under a profiler are never bench values)\n\n")
+        f.write("# ncu summaries, round 2 (one B200, `tools/gpu_runs/prof_r2.sh`; captures under a profiler are never bench values)\n\n")
         f.write("Kernel-family shares of one detect step (launch list `r02_launches_one_step.csv`, %d launches, %.2f ms serialised): %s\n\n"
                 % (len(ll), tot / 1e6, ", ".join("%s %s" % kv for kv in shares.items())))
         for title, name in (("Detect path, kernels that changed in round 2 (`ncu --set full`, second step)", "prof_r2_misc.raw.csv"),
