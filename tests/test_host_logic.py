@@ -424,6 +424,48 @@ def test_native_merge_components_reproduces_the_reference_graph_order():
         assert got == want and frame_comps.tolist() == want_frames and ncomp.value == len(want)
 
 
+def test_host_pair_flags_and_pair_lists_match_the_numpy_expressions():
+    """mrcnn_host_all_pairs / mrcnn_host_pair_flags (host C++) against the numpy expressions of the per-frame walk:
+    pair order, merge edges (connected, same class, float64 IOU >= thr), selection edges (spurious-vs-source rule), the
+    'a linked mask scores higher' flags and the per-frame tie detector — including empty unions and equal scores."""
+    from mrcnn import analyze as P
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        F = int(rng.integers(1, 7))
+        counts = rng.integers(0, 12, size=F).astype(np.int32)
+        n = int(counts.sum())
+        c2, pairs = P._host_pairs(counts)
+        want_pairs, _ = P._all_pairs(counts.tolist())
+        assert np.array_equal(pairs, want_pairs.reshape(-1, 2)) and np.array_equal(c2, counts)
+        npairs = len(pairs)
+        area = rng.integers(0, 50, size=n).astype(np.int32)
+        inter = np.minimum(rng.integers(0, 50, size=npairs), np.minimum(area[pairs[:, 0]], area[pairs[:, 1]])).astype(np.int32) if npairs else np.zeros(0, np.int32)
+        touch = (rng.random(npairs) < 0.6).astype(np.int32)
+        cls = rng.integers(1, 4, size=n).astype(np.int32)
+        score = rng.choice(np.array([0.5, 0.625, 0.75, 0.875], np.float32), size=n)
+        thr = float(rng.choice([0.0, 0.3, 0.5]))
+        iou = P._iou(inter, area[pairs[:, 0]], area[pairs[:, 1]]) if npairs else np.zeros(0)
+        flags, _, _ = P._pair_flags(0, counts, cls, None, area, inter, touch, True, thr, n)
+        want = (touch != 0) & (cls[pairs[:, 0]] == cls[pairs[:, 1]]) & (iou >= thr) if npairs else np.zeros(0, bool)
+        assert np.array_equal(flags.astype(bool), want)
+        spur = (cls == 1).astype(np.int32)
+        for use_iou in (True, False):
+            linked, loses, tie = P._pair_flags(1, counts, spur, score, area, inter, touch, use_iou, thr, n)
+            want = touch != 0
+            if use_iou and npairs:
+                want &= ~((spur[pairs[:, 0]] != spur[pairs[:, 1]]) & (iou < thr))
+            assert np.array_equal(linked.astype(bool), want)
+            li, lj = pairs[want, 0], pairs[want, 1]
+            w_loses = np.zeros(n, bool)
+            w_loses[li[score[li] < score[lj]]] = True
+            w_loses[lj[score[lj] < score[li]]] = True
+            assert np.array_equal(loses.astype(bool), w_loses)
+            frame_of = np.repeat(np.arange(F), counts)
+            w_tie = np.zeros(F, bool)
+            w_tie[frame_of[li[score[li] == score[lj]]]] = True
+            assert np.array_equal(tie.astype(bool), w_tie)
+
+
 def test_generic_walk_and_array_path_give_the_same_catalogues(monkeypatch):
     """The per-frame Python walk (MRCNN_B200_ANALYZE_GENERIC=1, also the split_masks route) == the default array path
     (pair tests, merge components and pair lists in host C++): the reference goldens and the random multi-frame
