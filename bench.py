@@ -364,6 +364,7 @@ def main():
     if dbg:
         sys.stderr.write("e2e host ms between steps: " + " ".join("%.1f" % (1e3 * (b - a)) for a, b in zip(dbg, dbg[1:])) + "\n")
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    dense_share = int(round((model._dense_share_state or {}).get("k", 0.0)))
 
     # the same pipeline with the masks left as the packed bits that crossed PCIe (result(expand=False), an extension of the
     # API): separates the device + PCIe path from the host-memory cost of materialising 6.5 MB of [H,W,N] bools per image
@@ -376,11 +377,14 @@ def main():
             e2e_results[1] = pending[0].result(expand=False)
             pending[0] = None
     e2e_results.append(None)
+    share_state = model._dense_share_state
+    model._dense_share_state = {"fixed": True, "k": 0.0}      # packed results: nothing is delivered dense
     for i in range(3):
         e2e_packed_step(i)
     e2e_results[1] = pending[0].result(expand=False)
     pending[0] = None
     ms_e2e_packed = timed(e2e_packed_step, args.steps)
+    model._dense_share_state = share_state
     D = 100
     h2d = B * S * S * 4 + B * 16 * 4 + B * 16
     # boxes / class ids / scores / counts + the pixel-major mask bits (16 B per pixel for D = 100); the [H,W,N] bool
@@ -424,9 +428,13 @@ def main():
                        "parallelism": "batch-sharded, no collective", "cpu_affinity": numa,
                        "maps_total": B if world == 1 else MAPS_TOTAL, "shard_of_rank0": list(shard),
                        "host_threads": int(lib.mrcnn_host_threads())},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h + dense_share * S * S * D,
+                    "ms_per_step": ms_e2e / args.steps,
                     "masks": "shipped as pixel-major bits, expanded to [H,W,N] bool on the host (%d threads) inside the timed region"
-                             % int(lib.mrcnn_host_threads())},
+                             % int(lib.mrcnn_host_threads()) + ("" if not dense_share else "; the masks of %d of the %d images per step "
+                             "are expanded on the device instead and written dense by the DMA engine (share balanced against the host's "
+                             "measured expansion rate, rank 0's value at the end of the run)" % (dense_share, B)),
+                    "dense_share_images": dense_share},
             "e2e_packed_masks": {"value": world * B * args.steps / (ms_e2e_packed / 1e3), "unit": UNIT, "ms_per_step": ms_e2e_packed / args.steps,
                                  "note": "same calls, masks delivered to the host as packed bits (result(expand=False)); NOT the reference "
                                          "contract — shows what the [H,W,N] bool materialisation costs the host"},

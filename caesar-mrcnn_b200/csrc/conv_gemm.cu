@@ -1187,6 +1187,10 @@ int conv_plan_create_ex(const mrcnn_conv_desc* d, const void* x, const void* w, 
     while (block_n > 64 && d->cout % block_n != 0) block_n >>= 1;
     if (block_n < 64) block_n = 64;
   }
+  if (const char* fb = getenv("MRCNN_B200_BLOCK_N")) {   // development probe (tools/conv_probe.py): force the tile width
+    const int v = atoi(fb);
+    if ((v == 32 || v == 64 || v == 128 || v == 256) && !plan->b_mn && d->out_mode == 0) block_n = v;
+  }
   plan->occ2 = 0;
   if (const char* o2 = getenv("MRCNN_B200_OCC2")) {     // "2": force the two-CTAs-per-SM variant (tests); the engine autotunes it
     if (o2[0] == '2' && !plan->b_mn && d->out_mode == 0) {

@@ -129,8 +129,14 @@ struct mrcnn_engine {
     int32_t* rois = nullptr; int32_t* class_ids = nullptr; float* scores = nullptr; int32_t* counts = nullptr;
     cudaEvent_t computed = nullptr, copied = nullptr;
     bool copy_pending = false;
+    // dense share of the host results (mrcnn_engine_set_dense_output): masks of the first images expanded on the device
+    void* dense = nullptr; size_t dense_bytes = 0;
+    cudaEvent_t dense_t0 = nullptr, dense_t1 = nullptr;   // dense_t0 doubles as "everything but the dense share is on the host"
+    int dense_images = 0;
   } slots[2];
   int cur_slot = 0;
+  uint8_t* dense_host = nullptr;   // pending request for the next host-result fetch
+  int dense_n = 0;
   cudaStream_t copy_stream = nullptr;
   // preprocessing scratch (detect_maps).  Host maps of asynchronous calls are uploaded on their own stream into one
   // of two buffers, so the H2D copy of step k+1 overlaps the compute of step k
@@ -844,6 +850,9 @@ extern "C" void mrcnn_engine_destroy(mrcnn_engine* e) {
   for (auto& sl : e->slots) {
     if (sl.masks) cudaFree(sl.masks);
     if (sl.bits) cudaFree(sl.bits);
+    if (sl.dense) cudaFree(sl.dense);
+    if (sl.dense_t0) cudaEventDestroy(sl.dense_t0);
+    if (sl.dense_t1) cudaEventDestroy(sl.dense_t1);
     if (sl.computed) cudaEventDestroy(sl.computed);
     if (sl.copied) cudaEventDestroy(sl.copied);
   }
@@ -1260,6 +1269,26 @@ static int fetch_internal(mrcnn_engine* e, int slot, bool async, const int* orig
   if (scores_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(scores_host, sl.scores, (size_t)B * D * 4, cudaMemcpyDeviceToHost, st));
   if (counts_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(counts_host, sl.counts, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   if (mask_bits_host) MRCNN_CHECK_CUDA(cudaMemcpyAsync(mask_bits_host, sl.bits, mbytes, cudaMemcpyDeviceToHost, st));
+  sl.dense_images = 0;
+  if (mask_bits_host && e->dense_host && e->dense_n > 0) {
+    // hybrid delivery: the masks of the first dense_n images leave as the reference's dense [H, W, N] bytes, expanded from
+    // the bits by a small kernel and copied by the DMA engine, so the host's cores only expand the remaining images
+    const int n = e->dense_n < B ? e->dense_n : B;
+    const size_t npx = (size_t)orig_hw[0] * orig_hw[1];
+    RC(ensure_scratch(e, &sl.dense, &sl.dense_bytes, (size_t)B * npx * D));   // sized once: the share varies from call to call
+    if (!sl.dense_t0) {
+      MRCNN_CHECK_CUDA(cudaEventCreate(&sl.dense_t0));
+      MRCNN_CHECK_CUDA(cudaEventCreate(&sl.dense_t1));
+    }
+    MRCNN_CHECK_CUDA(cudaEventRecord(sl.dense_t0, st));
+    RC(mrcnn_mask_bits_expand_device(static_cast<const uint32_t*>(sl.bits), sl.counts, n, (int64_t)npx, D,
+                                     static_cast<uint8_t*>(sl.dense), st));
+    MRCNN_CHECK_CUDA(cudaMemcpyAsync(e->dense_host, sl.dense, (size_t)n * npx * D, cudaMemcpyDeviceToHost, st));
+    MRCNN_CHECK_CUDA(cudaEventRecord(sl.dense_t1, st));
+    sl.dense_images = n;
+  }
+  e->dense_host = nullptr;
+  e->dense_n = 0;
   if (async) {
     MRCNN_CHECK_CUDA(cudaEventRecord(sl.copied, e->copy_stream));
     sl.copy_pending = true;
@@ -1288,6 +1317,40 @@ extern "C" int mrcnn_engine_wait_slot(mrcnn_engine* e, int slot) {
 }
 
 extern "C" int mrcnn_engine_next_slot(const mrcnn_engine* e) { return e ? e->cur_slot : -1; }
+
+extern "C" int mrcnn_engine_wait_slot_packed(mrcnn_engine* e, int slot) {
+  MRCNN_REQUIRE(e && (slot == 0 || slot == 1), "engine_wait_slot_packed: bad arguments");
+  MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+  mrcnn_engine::ResultSlot& sl = e->slots[slot];
+  if (sl.copy_pending && sl.dense_images > 0) {
+    MRCNN_CHECK_CUDA(cudaEventSynchronize(sl.dense_t0));     // boxes / ids / scores / counts / mask bits have arrived
+    return MRCNN_OK;
+  }
+  return mrcnn_engine_wait_slot(e, slot);
+}
+
+extern "C" int mrcnn_engine_set_dense_output(mrcnn_engine* e, uint8_t* dense_host, int n_images) {
+  MRCNN_REQUIRE(e, "engine_set_dense_output: null engine");
+  MRCNN_REQUIRE(n_images >= 0 && (n_images == 0 || dense_host), "engine_set_dense_output: bad arguments");
+  MRCNN_REQUIRE(n_images == 0 || e->cfg.detection_max_instances % 4 == 0,
+                "engine_set_dense_output: DETECTION_MAX_INSTANCES must be a multiple of 4");
+  e->dense_host = n_images ? dense_host : nullptr;
+  e->dense_n = n_images;
+  return MRCNN_OK;
+}
+
+extern "C" int mrcnn_engine_dense_copy_ms(mrcnn_engine* e, int slot, int* n_images, float* ms) {
+  MRCNN_REQUIRE(e && (slot == 0 || slot == 1) && n_images && ms, "engine_dense_copy_ms: bad arguments");
+  mrcnn_engine::ResultSlot& sl = e->slots[slot];
+  *n_images = sl.dense_images;
+  *ms = 0.f;
+  if (sl.dense_images > 0) {
+    MRCNN_CHECK_CUDA(cudaSetDevice(e->device));
+    MRCNN_CHECK_CUDA(cudaEventSynchronize(sl.dense_t1));
+    MRCNN_CHECK_CUDA(cudaEventElapsedTime(ms, sl.dense_t0, sl.dense_t1));
+  }
+  return MRCNN_OK;
+}
 
 extern "C" int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, int molded_on_host,
                                           const float* metas_host, const int* orig_hw,

@@ -332,6 +332,54 @@ extern "C" int mrcnn_unmold_detections(const float* detections, const float* mrc
   return MRCNN_OK;
 }
 
+namespace {
+// bits [n_images][npx][dw] -> out [n_images][npx * D] bytes holding, per image, the dense C-order [npx, counts[i]] array
+// (the reference's [H, W, N] bool layout) in the first npx * counts[i] bytes of its slot.  One thread per (pixel, 32-bit
+// word): 4 bits become 4 bytes with one multiply ((v & 15) * 0x00204081 & 0x01010101: the 16 partial products land on 16
+// different bit positions, so nothing carries); word stores when the row length is a multiple of 4, byte stores otherwise.
+__global__ void mask_bits_expand_kernel(const uint32_t* __restrict__ bits, const int32_t* __restrict__ counts, uint32_t npx, int dw,
+                                        int D, uint8_t* __restrict__ out) {
+  const int img = blockIdx.y;
+  const int n = counts[img];
+  if (n <= 0) return;
+  const uint32_t* ib = bits + (size_t)img * npx * dw;
+  uint8_t* ob = out + (size_t)img * npx * D;
+  const uint32_t items = npx * (uint32_t)dw;
+  const bool aligned = (n & 3) == 0;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < items; t += gridDim.x * blockDim.x) {
+    const uint32_t p = t / (uint32_t)dw, j = t - p * (uint32_t)dw;       // dw is 1, 2, 4 or 8
+    const int k0 = (int)j * 32;
+    if (k0 >= n) continue;
+    const int cnt = n - k0 < 32 ? n - k0 : 32;
+    const uint32_t x = ib[t];
+    uint8_t* dst = ob + (size_t)p * n + k0;
+    if (aligned) {
+      for (int q = 0; q * 4 < cnt; ++q)
+        *reinterpret_cast<uint32_t*>(dst + 4 * q) = (((x >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
+    } else {
+      for (int k = 0; k < cnt; ++k) dst[k] = (uint8_t)((x >> k) & 1u);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int mrcnn_mask_bits_expand_device(const uint32_t* mask_bits, const int32_t* counts, int n_images,
+                                             int64_t pixels_per_image, int max_instances, uint8_t* dense, void* stream) {
+  MRCNN_REQUIRE(mask_bits && counts && dense && n_images > 0 && pixels_per_image > 0, "mask_bits_expand_device: bad arguments");
+  MRCNN_REQUIRE(max_instances > 0 && ((size_t)pixels_per_image * max_instances) % 4 == 0,
+                "mask_bits_expand_device: image slots (pixels * max_instances bytes) must be 4-byte multiples");
+  MRCNN_REQUIRE(n_images <= 65535, "mask_bits_expand_device: too many images");
+  const int dw = mrcnn_mask_bits_words(max_instances);
+  MRCNN_REQUIRE((unsigned long long)pixels_per_image * dw < (1ull << 31), "mask_bits_expand_device: image too large");
+  const size_t items = (size_t)pixels_per_image * dw;
+  const unsigned gx = (unsigned)((items + 255) / 256 < 592 ? (items + 255) / 256 : 592);
+  mask_bits_expand_kernel<<<dim3(gx, n_images), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mask_bits, counts, (uint32_t)pixels_per_image, dw, max_instances, dense);
+  MRCNN_CHECK_CUDA(cudaGetLastError());
+  mrcnn_count_launch(1);
+  return MRCNN_OK;
+}
+
 extern "C" int mrcnn_mask_bits_words(int max_instances) {
   const int need = (max_instances + 31) / 32;
   int dw = 1;

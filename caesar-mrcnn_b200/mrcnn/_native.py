@@ -102,6 +102,10 @@ SIGNATURES = {
                                        ctypes.POINTER(c_float), ctypes.POINTER(ctypes.c_double)]),
     "mrcnn_engine_kernel_times": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_float),
                                           ctypes.POINTER(c_int)]),
+    "mrcnn_mask_bits_expand_device": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_int64, c_int, c_void_p, c_void_p]),
+    "mrcnn_engine_set_dense_output": (c_int, [c_void_p, c_void_p, c_int]),
+    "mrcnn_engine_wait_slot_packed": (c_int, [c_void_p, c_int]),
+    "mrcnn_engine_dense_copy_ms": (c_int, [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_float)]),
     "mrcnn_plane_words": (c_size_t, [c_int, c_int]),
     "mrcnn_masks_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mrcnn_planes_area_bbox": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

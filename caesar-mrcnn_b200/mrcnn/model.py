@@ -14,6 +14,7 @@ import errno
 import logging
 import os
 import re
+import time
 
 import numpy as np
 
@@ -107,6 +108,11 @@ from .training import build_rpn_targets, data_generator, load_image_gt  # noqa: 
 # MaskRCNN
 # --------------------------------------------------------------------------------------------
 
+def _dense_share_requested():
+    v = os.environ.get("MRCNN_B200_DENSE_SHARE", "").strip()
+    return v != "" and v != "0"
+
+
 class _PinnedSet(object):
     """One batch worth of host result buffers: rois, class ids, scores, counts and the pixel-major mask bits
     [B, H0*W0, DW] uint32 land in PINNED memory (device->host copies); `dense` is the plain host buffer the
@@ -119,7 +125,9 @@ class _PinnedSet(object):
         self.tensors = (torch.empty((B, D, 4), dtype=torch.int32, pin_memory=pin), torch.empty((B, D), dtype=torch.int32, pin_memory=pin),
                         torch.empty((B, D), dtype=torch.float32, pin_memory=pin), torch.empty((B,), dtype=torch.int32, pin_memory=pin),
                         torch.empty((B, H0 * W0, dw), dtype=torch.int32, pin_memory=pin))
-        self.dense = torch.empty((B, H0 * W0 * D), dtype=torch.uint8)
+        # pinned as well when the hybrid delivery is on (MRCNN_B200_DENSE_SHARE): the DMA engine then writes the dense
+        # masks of some images straight into it
+        self.dense = torch.empty((B, H0 * W0 * D), dtype=torch.uint8, pin_memory=pin and _dense_share_requested())
 
 
 class _Lease(object):
@@ -153,16 +161,19 @@ def _lease_arrays(pool, pset):
 class _PendingDetection(object):
     """Handle of an asynchronous detect_maps call (keeps the pinned buffers and inputs alive)."""
 
-    def __init__(self, model, bufs, maps, slot):
-        self._model, self._bufs, self._maps, self._done, self._slot = model, bufs, maps, None, slot
+    def __init__(self, model, bufs, maps, slot, n_dense=0):
+        self._model, self._bufs, self._maps, self._done, self._slot, self._n_dense = model, bufs, maps, None, slot, n_dense
 
     def result(self, expand=True):
         """expand=False (extension): leave each image's masks as the packed bits that crossed PCIe — dict keys rois,
         class_ids, scores, mask_bits (uint32 [H*W, words], bit k of word j = detection 32*j + k), mask_shape (H, W, N) —
         for consumers that do not need the dense [H,W,N] bool arrays at once (expand_mask_bits makes them on demand)."""
         if self._done is None:
-            _native.check(self._model._lib.mrcnn_engine_wait_slot(self._model._engine, self._slot), "engine_wait_slot")
-            self._done = self._model._results_from_buffers(self._bufs, expand)
+            # first everything but the dense share; the host expands its images while the DMA copy of the share drains
+            t0 = time.perf_counter()
+            _native.check(self._model._lib.mrcnn_engine_wait_slot_packed(self._model._engine, self._slot), "engine_wait_slot_packed")
+            wait_ms = (time.perf_counter() - t0) * 1e3
+            self._done = self._model._results_from_buffers(self._bufs, expand, self._n_dense, self._model, self._slot, wait_ms)
             self._maps = None
         return self._done
 
@@ -260,6 +271,7 @@ class MaskRCNN(object):
         self._stream = torch.cuda.ExternalStream(lib.mrcnn_engine_stream(handle), device=int(self._device))
         self._pinned = {}
         self._result_pool = {}
+        self._dense_share_state = None
         return self     # callers only use .predict() on it
 
     def __del__(self):
@@ -576,6 +588,37 @@ class MaskRCNN(object):
         pset = free.pop() if free else _PinnedSet(torch, *key, dw=self._lib.mrcnn_mask_bits_words(c.DETECTION_MAX_INSTANCES))
         return _lease_arrays(self._result_pool, pset)
 
+    # -- hybrid delivery of the dense masks (opt-in: MRCNN_B200_DENSE_SHARE=<k> | auto) -----------------------------
+    # The reference's result contract is one dense [H, W, N] bool array per image: 6.5 MB per 256x256 image with 100
+    # detections, 420 MB per 64-image batch, expanded from the packed bits by this rank's host cores.  On a host with few
+    # cores per GPU the engine can instead expand the masks of the first k images on the device and let the DMA engine
+    # write them into the (then pinned) dense buffer while the cores expand the rest.  `auto` lets k follow where a
+    # pipelined caller spends its time (batch already on the host when result() asks: grow; waiting for the device or
+    # the DMA copy: shrink).  Measured: with ONE expansion thread on a 1-GPU box 25.3 -> 13.4 ms per step;
+    # on the 8-GPU box of this pool nothing is gained — its 133 GB/s of host-memory write bandwidth is the limit
+    # whichever engine writes the 8 x 420 MB — so the default is off.
+    def _dense_share(self, B, D):
+        if self._dense_share_state is None:
+            env = os.environ.get("MRCNN_B200_DENSE_SHARE", "").strip().lower()
+            if env == "auto" and D % 4 == 0:
+                self._dense_share_state = {"fixed": False, "k": float(B // 4)}
+            elif env.isdigit() and D % 4 == 0:
+                self._dense_share_state = {"fixed": True, "k": float(max(0, min(B, int(env))))}
+            else:
+                self._dense_share_state = {"fixed": True, "k": 0.0}
+        return int(round(self._dense_share_state["k"]))
+
+    def _balance_dense_share(self, B, n_dense, cpu_ms, slot, wait_ms=None, wait_dense_ms=0.0):
+        st = self._dense_share_state
+        if st is None or st["fixed"] or wait_ms is None:
+            return
+        if wait_ms > 0.5 or wait_dense_ms > 0.3:      # the device / DMA side is what this rank waits for
+            k = st["k"] - 1.0
+        else:                                         # everything was there already: the host's cores are the bottleneck
+            k = st["k"] + 2.0
+        st["k"] = float(min(max(0, B - 4), max(0.0, k)))
+        st["last"] = {"wait_ms": float(wait_ms), "wait_dense_ms": float(wait_dense_ms), "cpu_ms": float(cpu_ms), "n_dense": n_dense}
+
     def reserve_result_buffers(self, count, H0, W0):
         """Pre-allocates `count` result sets for [H0, W0] frames (keeps the allocation and the first-touch page faults
         out of the first calls)."""
@@ -585,19 +628,30 @@ class MaskRCNN(object):
         del sets
 
     @staticmethod
-    def _results_from_buffers(bufs, expand=True):
+    def _results_from_buffers(bufs, expand=True, n_dense=0, model=None, slot=0, wait_ms=None):
         """Expands the mask bits of one batch into the reference's [H0,W0,N] bool arrays (multi-threaded C++ behind the
-        C ABI) and builds the detect()-style dicts (mrcnn/model.py:2697-2703)."""
+        C ABI) and builds the detect()-style dicts (mrcnn/model.py:2697-2703). The first n_dense images arrived dense
+        already (hybrid delivery, _dense_share): only the others are expanded here."""
         rois_n, cls_n, sc_n, cnt_n, bits_n, dense_n, (H0, W0) = bufs
         B, D = cls_n.shape
         npx, dw = bits_n.shape[1], bits_n.shape[2]
         if not expand:
+            if model is not None and n_dense > 0:        # the dense share is still being written into this buffer set
+                _native.check(model._lib.mrcnn_engine_wait_slot(model._engine, slot), "engine_wait_slot")
             return [{"rois": rois_n[i, :int(cnt_n[i])], "class_ids": cls_n[i, :int(cnt_n[i])], "scores": sc_n[i, :int(cnt_n[i])],
                      "mask_bits": bits_n[i], "mask_shape": (H0, W0, int(cnt_n[i]))} for i in range(B)]
         base = dense_n.ctypes.data
-        dst = (ctypes.c_void_p * B)(*[base + i * npx * D for i in range(B)])
-        _native.check(_native.lib().mrcnn_host_expand_mask_bits(bits_n.ctypes.data, B, npx, dw, cnt_n.ctypes.data, dst, 0),
-                      "host_expand_mask_bits")
+        rest = B - n_dense
+        t0 = time.perf_counter()
+        if rest > 0:
+            dst = (ctypes.c_void_p * rest)(*[base + i * npx * D for i in range(n_dense, B)])
+            _native.check(_native.lib().mrcnn_host_expand_mask_bits(bits_n[n_dense:].ctypes.data, rest, npx, dw,
+                                                                    cnt_n[n_dense:].ctypes.data, dst, 0), "host_expand_mask_bits")
+        if model is not None:
+            cpu_ms = (time.perf_counter() - t0) * 1e3
+            t1 = time.perf_counter()
+            _native.check(model._lib.mrcnn_engine_wait_slot(model._engine, slot), "engine_wait_slot")     # the dense share
+            model._balance_dense_share(B, n_dense, cpu_ms, slot, wait_ms, (time.perf_counter() - t1) * 1e3)
         out = []
         for i in range(B):
             n = int(cnt_n[i])
@@ -687,6 +741,11 @@ class MaskRCNN(object):
             mask_format = 0 if masks_on_device else 1          # device consumers read bytes, host results travel as bits
         assert mask_format == 1 or masks_on_device or device_only, "host results are shipped as mask bits (mask_format=1)"
         slot = self._lib.mrcnn_engine_next_slot(self._engine)
+        n_dense = 0
+        if bufs is not None and not masks_on_device:
+            n_dense = self._dense_share(c.BATCH_SIZE, c.DETECTION_MAX_INSTANCES)
+            if n_dense > 0:
+                _native.check(self._lib.mrcnn_engine_set_dense_output(self._engine, bufs[5].ctypes.data, n_dense), "set_dense_output")
         with torch.cuda.stream(self._stream):
             _native.check(self._lib.mrcnn_engine_detect_maps(self._engine, _native.ptr(maps), 0 if maps.is_cuda else 1, H0, W0, con, mean,
                                                              int(out_hw[0]), int(out_hw[1]), int(top_left[0]), int(top_left[1]),
@@ -697,8 +756,8 @@ class MaskRCNN(object):
         if device_only:
             return None          # with _async=True nothing has been waited for: call wait() before reading tensors
         if _async:
-            return _PendingDetection(self, bufs, maps, slot)
-        return self._results_from_buffers(bufs)
+            return _PendingDetection(self, bufs, maps, slot, n_dense)
+        return self._results_from_buffers(bufs, True, n_dense, self, 0)
 
     def kernel_times(self):
         """{family: (ms, launches)} of the last predict; needs set_profiling(True) beforehand."""

@@ -131,6 +131,12 @@ int mrcnn_unmold_detections_bits(const float* detections, const float* mrcnn_mas
                                  const int* orig_hw, const int* image_hw, const int32_t* windows,
                                  int32_t* rois, int32_t* class_ids, float* scores, int32_t* counts,
                                  uint32_t* mask_bits, void* workspace, size_t workspace_bytes, void* stream);
+/* DEVICE counterpart of mrcnn_host_expand_mask_bits: mask_bits [n_images, pixels_per_image, DW] (DEVICE), counts
+ * [n_images] (DEVICE) -> dense [n_images, pixels_per_image * max_instances] uint8 (DEVICE): the first pixels_per_image *
+ * counts[i] bytes of slot i hold the C-order [pixels, counts[i]] 0/1 array (= masks [H0, W0, N] bool, mrcnn/model.py:
+ * 2613-2619).  pixels_per_image * max_instances must be a multiple of 4. */
+int mrcnn_mask_bits_expand_device(const uint32_t* mask_bits, const int32_t* counts, int n_images, int64_t pixels_per_image,
+                                  int max_instances, uint8_t* dense, void* stream);
 /* HOST-ONLY: expands pixel-major mask bits (HOST memory, as copied back from the device) into the reference's
  * result contract (mrcnn/model.py:2613-2619): for image b, dst[b] receives a dense C-order [pixels_per_image, counts[b]]
  * uint8 array (0/1) = masks [H0, W0, N] bool.  dst: HOST array of n_images HOST pointers (may be NULL where
@@ -253,6 +259,18 @@ int mrcnn_engine_detect_molded(mrcnn_engine* e, const float* molded, int molded_
                                const int32_t* windows_host, int32_t* rois_host,
                                int32_t* class_ids_host, float* scores_host, int32_t* counts_host,
                                uint32_t* mask_bits_host);
+/* Hybrid delivery of the host masks (optional, applies to the NEXT detect call that returns host results, then resets):
+ * the masks of images [0, n_images) are ALSO expanded on the device (mrcnn_mask_bits_expand_device) and copied by the DMA
+ * engine into dense_host (PINNED; slot i at dense_host + i * H0*W0*DETECTION_MAX_INSTANCES, dense [H0*W0, counts[i]] bytes),
+ * so the caller's cores only expand the mask bits of the remaining images.  The bits of every image are still delivered.
+ * mrcnn_engine_dense_copy_ms: after mrcnn_engine_wait_slot / a blocking call, the number of images delivered this way for
+ * that result slot and the device time of expansion + copy (for balancing the share against the host's expansion rate). */
+int mrcnn_engine_set_dense_output(mrcnn_engine* e, uint8_t* dense_host, int n_images);
+/* like mrcnn_engine_wait_slot, but returns as soon as everything except the dense share is on the host (boxes, ids, scores,
+ * counts, mask bits), so that the caller can expand the other images while the DMA copy of the dense share is still in
+ * flight; mrcnn_engine_wait_slot then waits for the rest. */
+int mrcnn_engine_wait_slot_packed(mrcnn_engine* e, int slot);
+int mrcnn_engine_dense_copy_ms(mrcnn_engine* e, int slot, int* n_images, float* ms);
 /* The whole hot path from FITS-like maps in ONE call: maps [B,map_h,map_w] float32 (HOST when
  * maps_on_host != 0, else DEVICE; NaN allowed) -> zscale/uint8 RGB (read_fits, mrcnn/utils.py:
  * 1090-1208) -> resize to (out_h,out_w), pad at (top,left), minus mean (mold_inputs, mrcnn/model.py:

@@ -352,6 +352,59 @@ def test_packed_mask_results_expand_to_the_same_masks(model):
     model.wait()
 
 
+def test_hybrid_dense_delivery_gives_the_same_results(weights, monkeypatch):
+    """MRCNN_B200_DENSE_SHARE=k: the masks of the first k images are expanded on the device and written into the dense
+    result buffer by the DMA engine, the others from the bits by the host's cores — the detect()-style results must not
+    depend on k (0, a part of the batch, the whole batch), for the blocking and the pipelined call, and the packed results
+    (expand=False) stay available."""
+    from mrcnn import model as modellib
+    Bq = 4
+    maps = synth.radio_maps(Bq, 96, start=3)
+    got = {}
+    for k in ("0", "3", "4"):
+        monkeypatch.setenv("MRCNN_B200_DENSE_SHARE", k)
+        m = modellib.MaskRCNN(mode="inference", config=_config(Bq), model_dir="/tmp/mrcnn_logs")
+        m.set_weights(weights)
+        sync = m.detect_maps(maps)
+        h1 = m.detect_maps_async(maps[::-1].copy())
+        h2 = m.detect_maps_async(maps)
+        r1, r2 = h1.result(), h2.result()
+        packed = m.detect_maps_async(maps).result(expand=False)
+        got[k] = (sync, r1, r2, packed)
+    for k in ("3", "4"):
+        for a_list, b_list in zip(got["0"][:3], got[k][:3]):
+            for a, b in zip(a_list, b_list):
+                for key in ("rois", "class_ids", "scores", "masks"):
+                    assert np.array_equal(a[key], b[key]) and a[key].dtype == b[key].dtype and a[key].shape == b[key].shape, (k, key)
+        for a, b in zip(got["0"][3], got[k][3]):
+            assert np.array_equal(a["mask_bits"], b["mask_bits"]) and a["mask_shape"] == b["mask_shape"]
+    assert sum(r["masks"].shape[-1] for r in got["0"][0]) > 0
+
+
+def test_mask_bits_expand_device_matches_host_expansion():
+    """mrcnn_mask_bits_expand_device == mrcnn_host_expand_mask_bits on random bits, ragged counts (0, 1, odd, 100)."""
+    import ctypes
+    from mrcnn import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(9)
+    n_img, npx, D = 5, 37 * 4, 100
+    dw = int(lib.mrcnn_mask_bits_words(D))
+    bits = rng.integers(0, 2 ** 32, size=(n_img, npx, dw), dtype=np.uint64).astype(np.uint32)
+    counts = np.array([100, 0, 1, 37, 64], dtype=np.int32)
+    d_bits, d_counts = torch.from_numpy(bits.view(np.int32)).cuda(), torch.from_numpy(counts).cuda()
+    d_out = torch.full((n_img, npx * D), 7, dtype=torch.uint8, device="cuda")
+    _native.check(lib.mrcnn_mask_bits_expand_device(_native.ptr(d_bits), _native.ptr(d_counts), n_img, npx, D, _native.ptr(d_out), None),
+                  "mask_bits_expand_device")
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    want = np.full((n_img, npx * D), 7, dtype=np.uint8)
+    dst = (ctypes.c_void_p * n_img)(*[want[i].ctypes.data for i in range(n_img)])
+    _native.check(lib.mrcnn_host_expand_mask_bits(bits.ctypes.data, n_img, npx, dw, counts.ctypes.data, dst, 2), "host_expand")
+    for i, n in enumerate(counts):
+        assert np.array_equal(out[i, :npx * n], want[i, :npx * n])
+        assert (out[i, npx * n:] == 7).all()
+
+
 def test_detect_images_of_different_original_sizes(model):
     """The reference only requires equal MOLDED shapes in a batch (mrcnn/model.py:2655-2658): two frames of
     different size go through one graph pass and are unmolded per image, bit-exact against the oracle."""
