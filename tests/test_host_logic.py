@@ -596,3 +596,42 @@ def test_graph_limits_are_reported_at_build_time():
     msgs = M.graph_limit_problems(Big())
     assert len(msgs) == 2 and "NUM_CLASSES=9" in msgs[0] and "DETECTION_MAX_INSTANCES=300" in msgs[1]
     assert M.graph_limit_problems(Config()) == []
+
+
+def test_dense_share_policy_is_opt_in_and_follows_the_callers_waits(monkeypatch):
+    """Hybrid delivery of the dense masks (mrcnn/model.py: _dense_share / _balance_dense_share): off unless
+    MRCNN_B200_DENSE_SHARE is set; a number fixes the share; `auto` grows it while result() finds its batch already on the
+    host (host-bound) and shrinks it while the caller waits for the device or for the DMA copy; never above B - 4."""
+    from mrcnn import model as M
+
+    class Dummy:
+        _dense_share = M.MaskRCNN._dense_share
+        _balance_dense_share = M.MaskRCNN._balance_dense_share
+
+        def __init__(self):
+            self._dense_share_state = None
+
+    B, D = 64, 100
+    monkeypatch.delenv("MRCNN_B200_DENSE_SHARE", raising=False)
+    d = Dummy()
+    assert d._dense_share(B, D) == 0 and d._dense_share_state["fixed"] and not M._dense_share_requested()
+    monkeypatch.setenv("MRCNN_B200_DENSE_SHARE", "24")
+    d = Dummy()
+    assert d._dense_share(B, D) == 24 and M._dense_share_requested()
+    d._balance_dense_share(B, 24, 5.0, 0, 0.0, 0.0)
+    assert d._dense_share(B, D) == 24                              # fixed: never adapted
+    assert Dummy()._dense_share(B, 102) == 0                       # slots must be 4-byte multiples
+    monkeypatch.setenv("MRCNN_B200_DENSE_SHARE", "auto")
+    d = Dummy()
+    assert d._dense_share(B, D) == 16 and not d._dense_share_state["fixed"]
+    for _ in range(40):                                            # host-bound: everything had arrived when asked
+        d._balance_dense_share(B, d._dense_share(B, D), 20.0, 0, 0.01, 0.0)
+    assert d._dense_share(B, D) == B - 4
+    for _ in range(10):                                            # waiting for the device: hand work back to the cores
+        d._balance_dense_share(B, d._dense_share(B, D), 2.0, 0, 3.0, 0.0)
+    assert d._dense_share(B, D) == B - 14
+    for _ in range(100):                                           # the DMA copy lags behind the cores
+        d._balance_dense_share(B, d._dense_share(B, D), 2.0, 0, 0.0, 1.0)
+    assert d._dense_share(B, D) == 0
+    d._balance_dense_share(B, 0, 2.0, 0, None, 0.0)                # blocking call: no waiting pattern to learn from
+    assert d._dense_share(B, D) == 0
