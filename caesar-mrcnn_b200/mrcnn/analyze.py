@@ -207,6 +207,10 @@ class MaskPlaneOps:
             self._call(self.lib.mrcnn_planes_unpack, _native.ptr(planes), n, H, W, _native.ptr(out), self._st(), what="planes_unpack")
         return self.host(out[:n])
 
+    def concat(self, a, b):
+        with self._ctx():
+            return self.torch.cat([a, b], dim=0)
+
     def gather(self, planes, index):
         with self._ctx():
             idx = self.torch.from_numpy(np.asarray(index, dtype=np.int64)).to(self.device)
@@ -442,7 +446,6 @@ class Analyzer(object):
         vmode = None if not self.compute_vertexes else ("lists" if self.pixels_as_lists else "arrays")
         if _array_path_applies(frames, self.split_masks):
             opts = self._options()
-            opts.pop("split_masks")
             batch = _analyze_batch_arrays(self._side_stream_ops(), frames, H, W, self.class_names, origins, False,
                                           timings=timings, vertexes=vmode, **opts)
             t1 = time.perf_counter()
@@ -694,8 +697,8 @@ class _BatchArrays:
         return out
 
 
-def _array_path_applies(frames, split_masks):
-    if _FORCE_GENERIC or split_masks or not (_F32_AVG_IS_IDENTITY and _SCALAR_LT_IS_ARRAY_LT):
+def _array_path_applies(frames, split_masks=False):
+    if _FORCE_GENERIC or not (_F32_AVG_IS_IDENTITY and _SCALAR_LT_IS_ARRAY_LT):
         return False
     return all(isinstance(fr.scores, np.ndarray) and fr.scores.dtype == np.float32 and isinstance(fr.class_ids, np.ndarray)
                and fr.class_ids.dtype.kind in "iu" for fr in frames)
@@ -755,7 +758,8 @@ def _clique_selection(n, edges, scores):
 
 
 def _analyze_batch_arrays(ops, frames, H, W, class_names, origins, want_masks, score_thr, merge_overlapped_masks,
-                          select_best_overlapped_masks, split_source_sidelobe, merge_overlap_iou_thr, timings, vertexes):
+                          select_best_overlapped_masks, split_source_sidelobe, merge_overlap_iou_thr, timings, vertexes,
+                          split_masks=False):
     """extract_det_masks + pixel lists for a batch with every per-mask quantity held in ONE array over the batch: the
     per-frame work left in Python is one argsort (the reference's own call, so ties fall the same way); the pair tests,
     the merge components and the pair enumeration are host C++ (csrc/host_graph.cu), everything else is numpy over the
@@ -795,6 +799,34 @@ def _analyze_batch_arrays(ops, frames, H, W, class_names, origins, want_masks, s
     planes = ops.pack(frames[0].masks_ptr, F, H, W, depth, plane_of, m)
     mark("gpu: pack")
 
+    # -- optional split into 4-connected components (analyze.py:1211-1255): a mask of a splittable class becomes one mask
+    #    per component (none if it is empty), each an int64 array in the reference (np.where(labels == c + 1, [1], [0]))
+    is_int = np.zeros(m, dtype=bool)
+    if split_masks and m:
+        unsplit = np.fromiter((name in _UNSPLIT_LABELS for name in class_names), dtype=bool, count=len(class_names))
+        splittable = ~unsplit[cls_arr]
+        labels, d_ncomp = ops.label(planes, H, W)
+        ncomp = np.asarray(ops.host(d_ncomp)).astype(np.int64)
+        mark("gpu: label components (+counts D2H)")
+        k = np.where(splittable, ncomp, 1)
+        src_all = np.repeat(np.arange(m, dtype=np.int64), k)           # det mask -> the selected mask it comes from
+        first = np.cumsum(k) - k
+        comp_all = np.arange(len(src_all), dtype=np.int64) - np.repeat(first, k) + 1
+        from_split = splittable[src_all]
+        parts = ops.select(labels, H, W, src_all[from_split].astype(np.int32), comp_all[from_split].astype(np.int32))
+        if from_split.all():
+            planes = parts
+        else:
+            origin_idx = np.empty(len(src_all), dtype=np.int64)         # row of cat([parts, planes]) for every det mask
+            origin_idx[from_split] = np.arange(int(from_split.sum()))
+            origin_idx[~from_split] = int(from_split.sum()) + src_all[~from_split]
+            planes = ops.gather(ops.concat(parts, planes), origin_idx)
+        frame_of_sel = np.repeat(np.arange(F), counts)
+        counts = np.bincount(frame_of_sel, weights=k, minlength=F).astype(np.int32)
+        cls_arr, score_arr, is_int = cls_arr[src_all], score_arr[src_all], from_split
+        m = len(src_all)
+        mark("host+gpu: component planes")
+
     # -- merge connected same-class masks above the IOU threshold (analyze.py:1258-1320)
     if merge_overlapped_masks and m:
         counts, pairs = _host_pairs(counts)
@@ -824,6 +856,10 @@ def _analyze_batch_arrays(ops, frames, H, W, class_names, origins, want_masks, s
                     score_avg += score_arr[k]
                 score_avg *= 1. / int(sizes[g])
                 new_score[g] = score_avg
+            if is_int.any():
+                is_int = np.logical_or.reduceat(is_int[members], offsets[:-1])
+            else:
+                is_int = np.zeros(G, dtype=bool)
             cls_arr, score_arr, counts = new_cls, new_score, frame_comps
             mark("host: merge graph")
             planes = ops.union(planes, H, W, (members, offsets))
@@ -869,7 +905,11 @@ def _analyze_batch_arrays(ops, frames, H, W, class_names, origins, want_masks, s
     if len(keep):
         fin = planes if len(keep) == n_merged else ops.gather(planes, keep)
         if want_masks:
-            out.masks = ops.unpack(fin, H, W).view(np.bool_)
+            dense = ops.unpack(fin, H, W)
+            if is_int[keep].any():                                   # masks that went through the component split are int64
+                out.masks = [dense[j].astype(np.int64) if flag else dense[j].view(np.bool_) for j, flag in enumerate(is_int[keep].tolist())]
+            else:
+                out.masks = dense.view(np.bool_)
         px, px_off = ops.pixels(fin, H, W, area[keep], 0, 0)          # one launch and one copy for the whole batch
         origins = origins if origins is not None else [(0, 0)] * F
         fo = out.frame_off.tolist()
@@ -900,7 +940,7 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
             assert fr.depth == depth and fr.masks_ptr == base_ptr + f * H * W * depth, "frames must be one [F,H,W,depth] block"
         return _analyze_batch_arrays(ops, frames, H, W, class_names, origins, want_masks, score_thr, merge_overlapped_masks,
                                      select_best_overlapped_masks, split_source_sidelobe, merge_overlap_iou_thr, timings,
-                                     vertexes).frame_results(class_names)
+                                     vertexes, split_masks).frame_results(class_names)
 
     def mark(stage):          # development aid: cumulative wall time per stage (device drained at every mark)
         if timings is not None:
@@ -972,7 +1012,7 @@ def analyze_frames(ops, frames, H, W, class_names, origins=None, want_masks=True
             origin_idx = np.empty(len(det_cls), dtype=np.int64)     # row of cat([parts, planes]) for every det mask
             origin_idx[~is_keep] = np.arange(len(src))
             origin_idx[is_keep] = len(src) + np.asarray(keep_src, dtype=np.int64)
-            planes = ops.gather(ops.torch.cat([parts, planes], dim=0), origin_idx)
+            planes = ops.gather(ops.concat(parts, planes), origin_idx)
         else:
             planes = parts
         mark("host+gpu: component planes")

@@ -136,6 +136,23 @@ class NumpyPlaneOps:
             groups = [members[offsets[i]:offsets[i + 1]] for i in range(len(offsets) - 1)]
         return _Arr(np.stack([np.any(pl.a[g], axis=0) for g in groups]) if groups else np.zeros((0, H, W), bool))
 
+    def label(self, pl, H, W):
+        """4-connected components, numbered in raster order of their first pixel (= skimage.measure.label(connectivity=1))"""
+        from scipy import ndimage
+        cross = np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]])
+        labels = np.zeros((len(pl.a), H, W), np.int32)
+        counts = np.zeros(len(pl.a), np.int32)
+        for i, m in enumerate(pl.a):
+            labels[i], counts[i] = ndimage.label(m, structure=cross)
+        return _Arr(labels), _Arr(counts)
+
+    def select(self, labels, H, W, src, comp):
+        src, comp = np.asarray(src, dtype=np.int64), np.asarray(comp, dtype=np.int64)
+        return _Arr(np.stack([labels.a[s_] == c for s_, c in zip(src, comp)]) if len(src) else np.zeros((0, H, W), bool))
+
+    def concat(self, a, b):
+        return _Arr(np.concatenate([a.a, b.a], axis=0))
+
     def gather(self, pl, index):
         return _Arr(pl.a[np.asarray(index, dtype=np.int64)])
 

@@ -357,16 +357,14 @@ def test_fits_header_only_memmap_subimage_and_writer(golden_dir, tmp_path):
 
 def test_analyzer_host_logic_reproduces_reference_goldens_with_numpy_backend():
     """The reference Analyzer's own outputs (tests/golden/analyzer_golden.json) replayed through the product's host
-    logic with the numpy test double in place of the device primitives (cases without split_masks: labelling has no
-    host-side double)."""
+    logic with the numpy test double in place of the device primitives (scipy labelling stands in for the device's
+    4-connected labelling in the split_masks cases)."""
     import analyzer_cases as C
     from mrcnn import analyze as P
     golden = C.load_golden()
     names = golden["class_names"]
     done = 0
     for case in golden["cases"]:
-        if case["options"].get("split_masks"):
-            continue
         masks, class_ids, scores = C.case_inputs(case)
         H, W, D = masks.shape
         ops = C.NumpyPlaneOps(masks[None])
@@ -378,12 +376,10 @@ def test_analyzer_host_logic_reproduces_reference_goldens_with_numpy_backend():
         for obj in cat["objs"]:
             obj["vertexes"] = []
         got = C.summarise(cat["objs"], res.masks_final, res.captions, H * W <= 64 * 64)
-        for rec in got:
-            rec["mask_dtype"] = "bool"           # the double returns uint8 frames; dtype bookkeeping is checked on the GPU
-        want = [dict(r, mask_dtype="bool") for r in case["objs"]]
+        want = case["objs"]                      # mask dtypes included: int64 for masks that went through the component split
         assert got == want, (case["name"], case["options"], case["origin"])
         done += 1
-    assert done >= 30
+    assert done >= 50
 
 
 def test_native_merge_components_reproduces_the_reference_graph_order():
@@ -499,7 +495,9 @@ def test_generic_walk_and_array_path_give_the_same_catalogues(monkeypatch):
     frames = [P._Frame(4096 + f * S * S * D, D, D - (f == 2) * 7, cls[f], sc[f]) for f in range(F)]
     origins = [(0, 0), (5, 9), (0, 0), (100, 200), (3, 3), (7, 0)]
     for opts in (dict(), dict(split_source_sidelobe=False, merge_overlap_iou_thr=0.05, score_thr=0.6),
-                 dict(merge_overlapped_masks=False), dict(select_best_overlapped_masks=False), dict(score_thr=2.0)):
+                 dict(merge_overlapped_masks=False), dict(select_best_overlapped_masks=False), dict(score_thr=2.0),
+                 dict(split_masks=True), dict(split_masks=True, merge_overlapped_masks=False),
+                 dict(split_masks=True, merge_overlap_iou_thr=0.02, split_source_sidelobe=False)):
         res = {}
         for generic in (False, True):
             monkeypatch.setattr(P, "_FORCE_GENERIC", generic)
@@ -512,7 +510,7 @@ def test_generic_walk_and_array_path_give_the_same_catalogues(monkeypatch):
             assert a.class_names_final == g.class_names_final and a.captions == g.captions
             assert [b.tolist() for b in a.bboxes] == [b.tolist() for b in g.bboxes]
             assert [p_.tolist() for p_ in a.pixels] == [p_.tolist() for p_ in g.pixels]
-            assert all(np.array_equal(x != 0, y != 0) for x, y in zip(a.masks_final, g.masks_final))
+            assert all(np.array_equal(x != 0, y != 0) and x.dtype == y.dtype for x, y in zip(a.masks_final, g.masks_final))
             cat_a = P.build_json_results(f, "t", names, S, S, origins[f][1], origins[f][0], a.masks_final, a.class_ids_final,
                                          a.scores_final, a.bboxes, a.pixels, vertexes=a.vertexes)
             cat_g = P.build_json_results(f, "t", names, S, S, origins[f][1], origins[f][0], g.masks_final, g.class_ids_final,
