@@ -266,6 +266,131 @@ def compute_overlaps(boxes1, boxes2):
         return (inter / union).astype(np.float64)
 
 
+def compute_iou(box, boxes, box_area, boxes_area):
+    """IoU of one box (y1,x1,y2,x2) with each row of `boxes`; the areas come from the caller (reference utils.py:75-93)."""
+    boxes = np.asarray(boxes)
+    dx = np.maximum(np.minimum(box[3], boxes[:, 3]) - np.maximum(box[1], boxes[:, 1]), 0)
+    dy = np.maximum(np.minimum(box[2], boxes[:, 2]) - np.maximum(box[0], boxes[:, 0]), 0)
+    inter = dx * dy
+    return inter / (box_area + boxes_area - inter)
+
+
+def compute_overlaps_masks(masks1, masks2):
+    """IoU matrix [n1, n2] of two mask stacks [H, W, n] thresholded at 0.5 (reference utils.py:166-185): float32 areas and
+    intersections through one matrix product."""
+    n1, n2 = masks1.shape[-1], masks2.shape[-1]
+    if n1 == 0 or n2 == 0:
+        return np.zeros((n1, n2))
+    a = (masks1 > .5).reshape(-1, n1).astype(np.float32)
+    b = (masks2 > .5).reshape(-1, n2).astype(np.float32)
+    inter = a.T @ b
+    return inter / (a.sum(axis=0)[:, None] + b.sum(axis=0)[None, :] - inter)
+
+
+def non_max_suppression(boxes, scores, threshold):
+    """Greedy NMS on the host -> int32 indices of the kept boxes, best score first (reference utils.py:188-222): candidates in
+    `scores.argsort()[::-1]` order, a kept box removes every later candidate whose IoU with it exceeds `threshold`."""
+    assert boxes.shape[0] > 0
+    if boxes.dtype.kind != "f":
+        boxes = boxes.astype(np.float32)
+    area = (boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])
+    order = scores.argsort()[::-1]
+    alive = np.ones(len(order), dtype=bool)
+    kept = []
+    for pos in range(len(order)):
+        if not alive[pos]:
+            continue
+        i = order[pos]
+        kept.append(i)
+        later = np.nonzero(alive[pos + 1:])[0] + pos + 1
+        if len(later):
+            rest = order[later]
+            alive[later[compute_iou(boxes[i], boxes[rest], area[i], area[rest]) > threshold]] = False
+    return np.array(kept, dtype=np.int32)
+
+
+def apply_box_deltas(boxes, deltas):
+    """Boxes (y1,x1,y2,x2) moved by (dy, dx, log dh, log dw) -> float32 [N,4] (reference utils.py:225-246)."""
+    boxes = boxes.astype(np.float32)
+    h = boxes[:, 2] - boxes[:, 0]
+    w = boxes[:, 3] - boxes[:, 1]
+    cy = boxes[:, 0] + 0.5 * h
+    cx = boxes[:, 1] + 0.5 * w
+    cy += deltas[:, 0] * h
+    cx += deltas[:, 1] * w
+    h *= np.exp(deltas[:, 2])
+    w *= np.exp(deltas[:, 3])
+    y1 = cy - 0.5 * h
+    x1 = cx - 0.5 * w
+    return np.stack([y1, x1, y1 + h, x1 + w], axis=1)
+
+
+def compute_matches(gt_boxes, gt_class_ids, gt_masks, pred_boxes, pred_class_ids, pred_scores, pred_masks,
+                    iou_threshold=0.5, score_threshold=0.0):
+    """Greedy matching of predictions (best score first) to ground-truth instances by mask IoU and class (reference
+    utils.py:725-781) -> (gt_match [n_gt], pred_match [n_pred] in score order, overlaps [n_pred, n_gt]); -1 = unmatched."""
+    gt_boxes = trim_zeros(gt_boxes)
+    gt_masks = gt_masks[..., :gt_boxes.shape[0]]
+    pred_boxes = trim_zeros(pred_boxes)
+    pred_scores = pred_scores[:pred_boxes.shape[0]]
+    by_score = np.argsort(pred_scores)[::-1]
+    pred_boxes, pred_class_ids, pred_masks = pred_boxes[by_score], pred_class_ids[by_score], pred_masks[..., by_score]
+    overlaps = compute_overlaps_masks(pred_masks, gt_masks)
+    pred_match = np.full([pred_boxes.shape[0]], -1.0)
+    gt_match = np.full([gt_boxes.shape[0]], -1.0)
+    for i in range(len(pred_boxes)):
+        candidates = np.argsort(overlaps[i])[::-1]
+        too_low = np.nonzero(overlaps[i, candidates] < score_threshold)[0]
+        if too_low.size:
+            candidates = candidates[:too_low[0]]
+        for j in candidates:
+            if gt_match[j] > -1:
+                continue                      # taken by a better-scoring prediction
+            if overlaps[i, j] < iou_threshold:
+                break                         # candidates come in descending IoU order
+            if pred_class_ids[i] == gt_class_ids[j]:
+                gt_match[j], pred_match[i] = i, j
+                break
+    return gt_match, pred_match, overlaps
+
+
+def compute_ap(gt_boxes, gt_class_ids, gt_masks, pred_boxes, pred_class_ids, pred_scores, pred_masks, iou_threshold=0.5):
+    """VOC-style average precision at one IoU threshold (reference utils.py:784-820) -> (mAP, precisions, recalls, overlaps)."""
+    gt_match, pred_match, overlaps = compute_matches(gt_boxes, gt_class_ids, gt_masks, pred_boxes, pred_class_ids, pred_scores,
+                                                     pred_masks, iou_threshold)
+    hits = np.cumsum(pred_match > -1)
+    precisions = np.concatenate([[0], hits / (np.arange(len(pred_match)) + 1), [0]])
+    recalls = np.concatenate([[0], hits.astype(np.float32) / len(gt_match), [1]])
+    precisions = np.maximum.accumulate(precisions[::-1])[::-1]         # the best precision at this or any later recall
+    step = np.nonzero(recalls[:-1] != recalls[1:])[0] + 1
+    mAP = np.sum((recalls[step] - recalls[step - 1]) * precisions[step])
+    return mAP, precisions, recalls, overlaps
+
+
+def compute_ap_range(gt_box, gt_class_id, gt_mask, pred_box, pred_class_id, pred_score, pred_mask, iou_thresholds=None, verbose=1):
+    """Mean of compute_ap over IoU thresholds, 0.5 ... 0.95 in steps of 0.05 by default (reference utils.py:823-844)."""
+    iou_thresholds = iou_thresholds or np.arange(0.5, 1.0, 0.05)
+    aps = []
+    for thr in iou_thresholds:
+        ap = compute_ap(gt_box, gt_class_id, gt_mask, pred_box, pred_class_id, pred_score, pred_mask, iou_threshold=thr)[0]
+        if verbose:
+            print("AP @{:.2f}:\t {:.3f}".format(thr, ap))
+        aps.append(ap)
+    mean_ap = np.array(aps).mean()
+    if verbose:
+        print("AP @{:.2f}-{:.2f}:\t {:.3f}".format(iou_thresholds[0], iou_thresholds[-1], mean_ap))
+    return mean_ap
+
+
+def compute_recall(pred_boxes, gt_boxes, iou):
+    """Fraction of ground-truth boxes that are the best match (box IoU >= iou) of some prediction (reference utils.py:847-863)
+    -> (recall, indices of those predictions)."""
+    overlaps = compute_overlaps(pred_boxes, gt_boxes)
+    best = np.argmax(overlaps, axis=1)
+    positive_ids = np.nonzero(np.max(overlaps, axis=1) >= iou)[0]
+    return len(set(best[positive_ids])) / gt_boxes.shape[0], positive_ids
+
+
 def box_refinement(box, gt_box):
     """(dy, dx, log dh, log dw) that turns box into gt_box, float32 like the reference (utils.py:275-298)."""
     box = np.asarray(box).astype(np.float32)
