@@ -275,6 +275,21 @@ def compute_iou(box, boxes, box_area, boxes_area):
     return inter / (box_area + boxes_area - inter)
 
 
+def get_iou(bb1, bb2):
+    """IoU of two (y1, x1, y2, x2) boxes with positive extent, 0.0 when they do not overlap (reference utils.py:100-144,
+    used by the Analyzer's ground-truth comparison)."""
+    ya, xa, yb, xb = bb1[0], bb1[1], bb1[2], bb1[3]
+    yc, xc, yd, xd = bb2[0], bb2[1], bb2[2], bb2[3]
+    assert xa < xb and ya < yb and xc < xd and yc < yd
+    left, top, right, bottom = max(xa, xc), max(ya, yc), min(xb, xd), min(yb, yd)
+    if right < left or bottom < top:
+        return 0.0
+    inter = (right - left) * (bottom - top)
+    iou = inter / float((xb - xa) * (yb - ya) + (xd - xc) * (yd - yc) - inter)
+    assert 0.0 <= iou <= 1.0
+    return iou
+
+
 def compute_overlaps_masks(masks1, masks2):
     """IoU matrix [n1, n2] of two mask stacks [H, W, n] thresholded at 0.5 (reference utils.py:166-185): float32 areas and
     intersections through one matrix product."""

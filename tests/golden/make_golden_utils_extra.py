@@ -51,6 +51,20 @@ def main():
         for thr in (0.3, 0.7):
             g["nms%d_keep_%d" % (k, int(thr * 10))] = utils.non_max_suppression(boxes, scores, thr)
         g["nms%d_applied" % k] = utils.apply_box_deltas(boxes, deltas)
+    # ---- get_iou (pairs of integer and float boxes, disjoint / touching / nested)
+    pairs = []
+    for _ in range(40):
+        a = rng.integers(0, 50, size=2)
+        b = rng.integers(0, 50, size=2)
+        bb1 = [int(a[0]), int(a[1]), int(a[0] + rng.integers(1, 30)), int(a[1] + rng.integers(1, 30))]
+        bb2 = [int(b[0]), int(b[1]), int(b[0] + rng.integers(1, 30)), int(b[1] + rng.integers(1, 30))]
+        pairs.append(bb1 + bb2)
+    pairs.append([0, 0, 10, 10, 10, 10, 20, 20])
+    pairs.append([0, 0, 10, 10, 2, 2, 5, 5])
+    pairs = np.array(pairs, dtype=np.float64)
+    pairs[::3] += 0.25
+    g["get_iou_pairs"] = pairs
+    g["get_iou_values"] = np.array([utils.get_iou(list(p[:4]), list(p[4:])) for p in pairs], dtype=np.float64)
     # ---- mask overlaps / matches / AP / recall
     for k, (n_gt, n_pred) in enumerate(((3, 5), (6, 6), (4, 0), (0, 3), (8, 12))):
         H = W = 48

@@ -540,7 +540,7 @@ def test_drop_in_exports_of_survey_8b_exist():
         assert hasattr(M, name), name
     for name in ("compute_overlaps", "box_refinement", "resize_mask", "minimize_mask", "expand_mask", "trim_zeros",
                  "compute_iou", "compute_overlaps_masks", "non_max_suppression", "apply_box_deltas", "compute_matches",
-                 "compute_ap", "compute_ap_range", "compute_recall"):       # pinned: tests/test_utils_extra_golden.py
+                 "compute_ap", "compute_ap_range", "compute_recall", "get_iou"):       # pinned: tests/test_utils_extra_golden.py
         assert hasattr(U, name), name
     # the training-path functions are real since round 2 (tests/test_training_host.py pins them to the reference)
     with pytest.raises(NotImplementedError):

@@ -30,6 +30,10 @@ def test_box_helpers_match_the_reference(g):
             keep = utils.non_max_suppression(boxes, scores, thr)
             assert same(keep, g["nms%d_keep_%d" % (k, int(thr * 10))]) and keep.dtype == np.int32
         assert same(utils.apply_box_deltas(boxes, deltas), g["nms%d_applied" % k])
+    got = np.array([utils.get_iou(list(p[:4]), list(p[4:])) for p in g["get_iou_pairs"]], dtype=np.float64)
+    assert same(got, g["get_iou_values"]) and (got == 0).any() and (got > 0.05).any()
+    with pytest.raises(AssertionError):
+        utils.get_iou([0, 0, 0, 5], [0, 0, 5, 5])
     with pytest.raises(AssertionError):
         utils.non_max_suppression(np.zeros((0, 4), np.float32), np.zeros(0, np.float32), 0.5)
 
