@@ -72,6 +72,31 @@ def test_crop_and_resize_loop_equals_vectorised():
     assert np.allclose(c[0], img[1], atol=1e-6)
 
 
+def test_crop_and_resize_matches_torch_grid_sample_inside_the_image():
+    """Independent cross-check of the tf.image.crop_and_resize restatement (third party, parity unpinned): for boxes inside
+    [0, 1] its sampling grid y1*(H-1) + i*(y2-y1)*(H-1)/(P-1) is exactly torch's bilinear grid_sample with
+    align_corners=True over the same box, so the two must agree to float32 rounding."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(17)
+    N, H, W, C, P = 2, 13, 10, 6, 7
+    img = rng.normal(size=(N, H, W, C)).astype(np.float32)
+    lo = rng.uniform(0.0, 0.6, size=(24, 2))
+    boxes = np.concatenate([lo, lo + rng.uniform(0.05, 0.4, size=(24, 2))], axis=1).astype(np.float32)
+    boxes = np.clip(boxes, 0, 1)
+    boxes[0] = [0, 0, 1, 1]
+    bi = rng.integers(0, N, 24)
+    got = GL.crop_and_resize_fast(img, boxes, bi, (P, P))
+    t = torch.from_numpy(img).permute(0, 3, 1, 2)[torch.from_numpy(bi)]           # [n,C,H,W]
+    steps = torch.linspace(0, 1, P, dtype=torch.float64)
+    b = torch.from_numpy(boxes).double()
+    ys = b[:, 0:1] + steps[None, :] * (b[:, 2:3] - b[:, 0:1])                      # normalised [0,1] sample positions
+    xs = b[:, 1:2] + steps[None, :] * (b[:, 3:4] - b[:, 1:2])
+    grid = torch.stack([(2 * xs - 1)[:, None, :].expand(-1, P, -1), (2 * ys - 1)[:, :, None].expand(-1, -1, P)], dim=-1)
+    want = torch.nn.functional.grid_sample(t.double(), grid, mode="bilinear", padding_mode="border", align_corners=True)
+    want = want.permute(0, 2, 3, 1).numpy()
+    assert np.abs(got - want).max() < 2e-5
+
+
 def test_roi_levels_edge_cases():
     boxes = np.array([[[0, 0, 1, 1], [0, 0, 0, 0], [0.1, 0.1, 0.1, 0.5], [0, 0, 224 / 256, 224 / 256],
                        [0, 0, 0.05, 0.05]]], dtype=np.float32)
