@@ -97,6 +97,25 @@ def test_crop_and_resize_matches_torch_grid_sample_inside_the_image():
     assert np.abs(got - want).max() < 2e-5
 
 
+def test_skimage_resize_matches_scipy_map_coordinates_including_borders():
+    """Second independent cross-check of the skimage.transform.resize restatement (order 1, mode='constant', cval 0; third
+    party, parity unpinned): its coordinate map (out + 0.5) * scale - 0.5 evaluated by scipy.ndimage.map_coordinates(order=1,
+    mode="grid-constant", cval=0: the input extended by zeros) — the border rows / columns that blend with cval included, which the cv2 comparison leaves out —
+    on the shapes of the detect path: 132 -> 256 upscaling, 28x28 mask -> box, downscaling."""
+    ndimage = pytest.importorskip("scipy.ndimage")
+    rng = np.random.default_rng(23)
+    for (h, w), (oh, ow) in (((132, 132), (256, 256)), ((28, 28), (61, 17)), ((28, 28), (5, 90)), ((40, 64), (20, 32))):
+        img = rng.uniform(0.2, 1.0, size=(h, w))
+        got = H.skimage_resize(img, (oh, ow))
+        r = (np.arange(oh) + 0.5) * (h / oh) - 0.5
+        c = (np.arange(ow) + 0.5) * (w / ow) - 0.5
+        rr, cc = np.meshgrid(r, c, indexing="ij")
+        want = ndimage.map_coordinates(img, [rr, cc], order=1, mode="grid-constant", cval=0.0, prefilter=False)
+        want = np.where(want != 0.0, np.clip(want, img.min(), img.max()), want)       # skimage clips to the input range
+        assert got.shape == (oh, ow)
+        assert np.abs(got - want).max() < 1e-12, ((h, w), (oh, ow), np.abs(got - want).max())
+
+
 def test_roi_levels_edge_cases():
     boxes = np.array([[[0, 0, 1, 1], [0, 0, 0, 0], [0.1, 0.1, 0.1, 0.5], [0, 0, 224 / 256, 224 / 256],
                        [0, 0, 0.05, 0.05]]], dtype=np.float32)
