@@ -283,7 +283,7 @@ def train(args, model, config, datasets):
     return 0
 
 
-def parse_args(argv=None):
+def build_parser():
     p = argparse.ArgumentParser(description="Mask R-CNN detect / train on radio maps (B200 build)")
     p.add_argument("command", metavar="<command>", help="'detect', 'test' or 'train'")
     p.add_argument("--dataloader", type=str, default="datalist", help="train: datalist (img,mask,label lines) | datalist_json")
@@ -297,9 +297,12 @@ def parse_args(argv=None):
     p.add_argument("--max_gt_instances", type=int, default=300)
     p.add_argument("--rpn_train_anchors_per_image", type=int, default=512)
     p.add_argument("--train_rois_per_image", type=int, default=512)
-    for name in ("rpn_class", "rpn_bbox", "mrcnn_class", "mrcnn_bbox", "mrcnn_mask"):
+    for name in ("rpn_class", "rpn_bbox", "mrcnn_class", "mrcnn_bbox", "mrcnn_mask"):      # scripts/run.py:1319-1343
         p.add_argument("--%s_loss_weight" % name, type=float, default=1.0)
+        p.add_argument("--%s_loss" % name, dest="%s_loss" % name, action="store_true")
         p.add_argument("--no_%s_loss" % name, dest="%s_loss" % name, action="store_false")
+        p.set_defaults(**{"%s_loss" % name: True})
+    p.add_argument("--mask_loss_function", type=str, default="binary_crossentropy", choices=["binary_crossentropy", "dice_coef_loss"])
     p.add_argument("--no_augmentation", dest="use_augmentation", action="store_false")
     p.add_argument("--weight_classes", action="store_true")
     p.add_argument("--imgsize", dest="imgsize", type=int, default=256)
@@ -308,6 +311,16 @@ def parse_args(argv=None):
     p.add_argument("--no_zscale", dest="zscale", action="store_false")
     p.add_argument("--zscale_contrasts", dest="zscale_contrasts", type=str, default="0.25,0.25,0.25")
     p.add_argument("--biascontrast", dest="biascontrast", action="store_true")
+    p.add_argument("--bias", type=float, default=0.5, help="bias of the bias-contrast stretch (only with --biascontrast, which this build rejects)")
+    p.add_argument("--contrast", type=float, default=1.0, help="contrast of the bias-contrast stretch (only with --biascontrast)")
+    # accepted for command lines written for the reference (scripts/run.py:1289-1297, 1360-1370); see validate_args
+    p.add_argument("--remap_classids", dest="remap_classids", action="store_true")
+    p.add_argument("--classid_remap_dict", type=str, default="")
+    p.add_argument("--datadir", required=False, default=None)
+    p.add_argument("--consider_sources_near_mixed_sidelobes", dest="consider_sources_near_mixed_sidelobes", action="store_true")
+    p.add_argument("--no_consider_sources_near_mixed_sidelobes", dest="consider_sources_near_mixed_sidelobes", action="store_false")
+    p.set_defaults(consider_sources_near_mixed_sidelobes=True)
+    p.add_argument("--detect_outfile", type=str, default="", help="output plot PNG of the reference: accepted, no plot is drawn")
     p.add_argument("--no_norm_img", dest="norm_img", action="store_false")
     p.add_argument("--classdict", dest="classdict", type=str, default='{"sidelobe":1,"source":2,"galaxy":3}')
     p.add_argument("--classdict_model", dest="classdict_model", type=str, default="")
@@ -338,7 +351,11 @@ def parse_args(argv=None):
     p.add_argument("--tile_ysize", type=int, default=512, help="Sub image size in pixel along y")
     p.add_argument("--tile_xstep", type=float, default=1.0, help="Sub image step fraction along x (=1 means no overlap)")
     p.add_argument("--tile_ystep", type=float, default=1.0, help="Sub image step fraction along y (=1 means no overlap)")
-    return p.parse_args(argv)
+    return p
+
+
+def parse_args(argv=None):
+    return build_parser().parse_args(argv)
 
 
 def validate_args(args):
@@ -375,6 +392,22 @@ def validate_args(args):
         if not ok:
             logger.error("Option %s is not supported by the B200 build (SURVEY.md §8a row a17)" % flag)
             return -1
+    if args.remap_classids:
+        if args.classid_remap_dict == "":          # scripts/run.py:1438-1441
+            logger.error("Classid remap dictionary is empty (you need to provide one if you give the option --remap_classids)!")
+            return -1
+        logger.error("Option --remap_classids belongs to the ground-truth metrics of the reference (ModelTester), which the B200 "
+                     "build does not provide (SURVEY.md §8: out of scope)")
+        return -1
+    if args.dataloader in ("datadir", "datadir_json"):
+        logger.error("Data loader '%s' (--datadir tree search) is not supported by the B200 build: use datalist / datalist_json"
+                     % args.dataloader)
+        return -1
+    if args.command == "train" and args.mask_loss_function != "binary_crossentropy":
+        logger.error("Option --mask_loss_function %s is not supported by the B200 build (binary_crossentropy only)" % args.mask_loss_function)
+        return -1
+    if args.detect_outfile:
+        logger.warning("--detect_outfile %s: plots are not drawn by the B200 build (DESIGN.md §6), option ignored" % args.detect_outfile)
     try:
         nclasses = len(json.loads(args.classdict_model or args.classdict)) + 1
     except Exception:
@@ -422,6 +455,7 @@ def make_config(args):
                                ("rpn_class", "rpn_bbox", "mrcnn_class", "mrcnn_bbox", "mrcnn_mask")}
         config.USE_LOSSES = {"%s_loss" % n: getattr(args, "%s_loss" % n) for n in
                              ("rpn_class", "rpn_bbox", "mrcnn_class", "mrcnn_bbox", "mrcnn_mask")}
+        config.MASK_LOSS_FUNCTION = args.mask_loss_function
     return config
 
 

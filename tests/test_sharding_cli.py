@@ -68,6 +68,23 @@ def test_cli_argument_validation(tmp_path, golden_dir):
     assert run.main(["detect", "--image", fits, "--random_weights", "0", "--grayimg"]) == 1
     assert run.main(["detect", "--image", fits, "--random_weights", "0", "--backbone", "resnet50"]) == 1
     assert run.main(["test", "--weights", "w.h5"]) == 1                            # no datalist
+    # every flag of the reference's parser (scripts/run.py:1263-1384) is accepted, so command lines written for it still parse
+    full = run.parse_args(["detect", "--image", fits, "--random_weights", "0", "--rpn_class_loss", "--no_mrcnn_mask_loss",
+                           "--mrcnn_bbox_loss_weight", "2.5", "--mask_loss_function", "binary_crossentropy", "--bias", "0.4",
+                           "--contrast", "1.2", "--classid_remap_dict", "{1:2}", "--datadir", "/data",
+                           "--no_consider_sources_near_mixed_sidelobes", "--detect_outfile", "plot.png"])
+    assert run.validate_args(full) == 0
+    assert full.rpn_class_loss is True and full.mrcnn_mask_loss is False and full.mrcnn_class_loss is True
+    assert full.mrcnn_bbox_loss_weight == 2.5 and full.bias == 0.4 and full.consider_sources_near_mixed_sidelobes is False
+    assert run.main(["detect", "--image", fits, "--random_weights", "0", "--remap_classids"]) == 1        # empty dictionary
+    assert run.main(["detect", "--image", fits, "--random_weights", "0", "--remap_classids", "--classid_remap_dict", "{1:2}"]) == 1
+    ref_flags_path = "/root/reference/scripts/run.py"
+    if os.path.exists(ref_flags_path):                                             # build container only: nothing is missing
+        import re
+        ref = set(re.findall(r"add_argument\('(--[A-Za-z_]+)'", open(ref_flags_path).read()))
+        mine = set(a.option_strings[0] for a in run.build_parser()._actions if a.option_strings) if hasattr(run, "build_parser") else None
+        if mine is not None:
+            assert not (ref - mine), sorted(ref - mine)
 
 
 def test_cli_tile_options_reach_the_tile_driver(golden_dir):
