@@ -472,6 +472,17 @@ class Analyzer(object):
         return out
 
 
+class ModelTester(object):
+    """Ground-truth evaluation of the reference (mrcnn/analyze.py:65-575: mAP, confusion matrices, purity / completeness).
+    Outside the rebuilt path (out of scope); the name is kept so that `from mrcnn.analyze import ModelTester`
+    resolves.  The pieces it is built from are available: mrcnn.utils.compute_ap / compute_matches / compute_recall
+    (pinned to the reference) and Analyzer for the detections."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("ModelTester (ground-truth metrics of the reference) is not provided by the B200 build; "
+                                  "use mrcnn.utils.compute_ap / compute_matches on Analyzer results (DESIGN.md §6)")
+
+
 class NumpyEncoder(json.JSONEncoder):
     def default(self, obj):
         if isinstance(obj, np.integer):

@@ -542,6 +542,19 @@ def test_drop_in_exports_of_survey_8b_exist():
                  "compute_iou", "compute_overlaps_masks", "non_max_suppression", "apply_box_deltas", "compute_matches",
                  "compute_ap", "compute_ap_range", "compute_recall", "get_iou"):       # pinned: tests/test_utils_extra_golden.py
         assert hasattr(U, name), name
+    # module layout of the reference package: the imports at the top of its scripts resolve (scripts/run.py:42-49)
+    from mrcnn import logger, visualize                                  # noqa: F401
+    from mrcnn.analyze import Analyzer, ModelTester                      # noqa: F401
+    from mrcnn.graph import Graph
+    from mrcnn.parallel_model import ParallelModel
+    from mrcnn.sfinder import SFinder                                    # noqa: F401
+    g = Graph(4)
+    g.addEdge(0, 2)
+    g.addEdge(2, 3)
+    assert g.connectedComponents() == [[0, 2, 3], [1]]
+    for broken in (lambda: ParallelModel(None, 2), lambda: ModelTester(None, None, None), lambda: visualize.display_instances()):
+        with pytest.raises(NotImplementedError):
+            broken()
     # the training-path functions are real since round 2 (tests/test_training_host.py pins them to the reference)
     with pytest.raises(NotImplementedError):
         M.load_image_gt(None, None, 0, augmentation=object())
